@@ -1,0 +1,123 @@
+/* libb200timm.so -- C ABI of the B200 (sm_100a) kernels behind timm's ViT / ConvNeXt hot path.
+ *
+ * The reference (huggingface/pytorch-image-models, timm 1.0.28.dev0) is pure Python and has NO native
+ * boundary: its hot path bottoms out in torch.nn.functional calls.  Each entry point below replaces
+ * one such call site (cited as reference file:line, relative to the timm checkout); INTEGRATION.md
+ * shows the ctypes binding + forward rebinding a timm maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator); the library
+ *     never allocates, frees or synchronises; all work is enqueued on `stream` (a cudaStream_t).
+ *   - return value: 0 (B200_OK) or an error code; b200_last_error() gives the message of the last
+ *     failing call on the calling thread.  There is no CPU fallback: unsupported shapes are errors.
+ *   - activations are bf16 unless noted; statistics / accumulators are fp32; parameters (bias,
+ *     LayerNorm weight, LayerScale gamma) may be bf16 or fp32 (dtype enum).
+ *   - re-entrant, stream-ordered, no global mutable state besides an immutable device-property cache.
+ */
+#ifndef B200TIMM_H_
+#define B200TIMM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID_ARG 1
+#define B200_ERR_UNSUPPORTED 2
+#define B200_ERR_CUDA 3
+
+#define B200_DTYPE_BF16 0
+#define B200_DTYPE_F32 1
+
+/* GEMM epilogues (applied to acc = A*B^T before the store). */
+#define B200_EPI_BIAS 0       /* out = acc + bias                       (bias may be NULL)          */
+#define B200_EPI_BIAS_GELU 1  /* out = gelu_erf(acc + bias)             timm/layers/mlp.py:48-49     */
+#define B200_EPI_BIAS_RESIDUAL 2 /* out = aux + gamma * (acc + bias)    vision_transformer.py:212-213, layer_scale.py:27 */
+#define B200_EPI_DGELU 3      /* out = (acc + bias) * gelu_erf'(aux)    backward of mlp.py:49        */
+
+B200_API const char* b200_last_error(void);
+B200_API int b200_abi_version(void);
+/* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
+B200_API int b200_device_check(void);
+
+/* ------------------------------------------------------------------ GEMM (tcgen05 + TMA)
+ * out[M,N] = epilogue( sum_k A[m,k] * B[n,k] )         bf16 operands, fp32 accumulation in TMEM.
+ * Replaces F.linear at timm/layers/attention.py:115,137 and timm/layers/mlp.py:48,52 (forward,
+ * a_mn=b_mn=0: A = activations [M,K], B = nn.Linear.weight [N,K]) and the autograd dgrad / wgrad
+ * GEMMs of those calls (b_mn=1: B stored [K,N]; a_mn=1: A stored [K,M]).
+ */
+typedef struct b200_gemm_desc {
+  const void* a;   /* bf16; a_mn=0: [M,K] row-major (lda = row stride in elements); a_mn=1: [K,M] */
+  const void* b;   /* bf16; b_mn=0: [N,K] row-major (ldb);                           b_mn=1: [K,N] */
+  void* out;       /* [M,N] row-major, ldo elements per row; bf16 or fp32 (out_dtype)             */
+  const void* bias;  /* [N] or NULL; dtype bias_dtype                                             */
+  const void* aux;   /* [M,N] bf16, ld = ldaux: residual (EPI_BIAS_RESIDUAL) / pre-activation (EPI_DGELU) */
+  const void* gamma; /* [N] or NULL (LayerScale), dtype gamma_dtype; EPI_BIAS_RESIDUAL only        */
+  int64_t lda, ldb, ldo, ldaux;
+  int32_t M, N, K;
+  int32_t a_mn, b_mn;
+  int32_t epilogue;
+  int32_t out_dtype;
+  int32_t bias_dtype, gamma_dtype;
+  int32_t accumulate; /* out += result instead of out = result (out_dtype f32 only)               */
+  int32_t split_k;    /* >1: K is split over CTAs, partial tiles are atomically added into fp32 out
+                         (requires out_dtype=f32, epilogue=B200_EPI_BIAS with bias=NULL)           */
+} b200_gemm_desc;
+
+B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm   timm/layers/norm.py:85-90
+ * y = (x - mean) * rstd * weight + bias over the last dim (cols).  x,y: [rows, cols]; x bf16 or f32,
+ * y bf16 or f32; mean/rstd (fp32 [rows]) are written when non-NULL (saved for backward).          */
+B200_API int b200_layernorm_fwd(const void* x, const void* weight, const void* bias, void* y, float* mean,
+                       float* rstd, int64_t rows, int32_t cols, float eps, int32_t x_dtype,
+                       int32_t y_dtype, int32_t param_dtype, void* stream);
+/* dx (same dtype as x) and, accumulated over rows, dweight/dbias written as fp32 [cols] into
+ * dw_partial/db_partial after an internal two-stage reduction (workspace: fp32 [ws_rows, 2*cols],
+ * ws_rows = b200_layernorm_bwd_ws_rows(rows)).                                                       */
+B200_API int b200_layernorm_bwd_ws_rows(int64_t rows, int32_t cols);
+B200_API int b200_layernorm_bwd(const void* dy, const void* x, const void* weight, const float* mean,
+                       const float* rstd, void* dx, float* dweight, float* dbias, float* workspace,
+                       int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
+                       int32_t param_dtype, void* stream);
+
+/* ------------------------------------------------------------------ attention   timm/layers/attention.py:115-135
+ * qkv: bf16 [B, N, 3, H, hd] (the QKV linear's output, viewed exactly as attention.py:115 reshapes it);
+ * out: bf16 [B, N, H*hd] (== x.transpose(1,2).reshape(B,N,C) of attention.py:135);
+ * lse: fp32 [B, H, N] natural-log-sum-exp of the scaled scores (NULL: not written);
+ * kv_len: int32 [B] number of valid (prefix) keys per sample or NULL (all N) -- the NaFlex key-padding
+ * mask of naflexvit.py:964-1029 given as lengths.  hd must be 64.                                    */
+B200_API int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* kv_len, int32_t B, int32_t N,
+                  int32_t H, int32_t hd, float scale, void* stream);
+/* Backward: dqkv bf16 [B,N,3,H,hd] from dout bf16 [B,N,H*hd]; recomputes P from qkv and lse.
+ * delta: fp32 workspace [B,H,N].                                                                     */
+B200_API int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                  void* dqkv, const int32_t* kv_len, int32_t B, int32_t N, int32_t H, int32_t hd,
+                  float scale, void* stream);
+
+/* ------------------------------------------------------------------ patch embed   timm/layers/patch_embed.py:136-138
+ * Gathers non-overlapping p x p patches of an NCHW bf16 image into rows of a [B*gh*gw, Kpad] bf16 matrix
+ * (k = c*p*p + ky*p + kx, matching Conv2d.weight.flatten(1)); Kpad >= C*p*p, zero padded.              */
+B200_API int b200_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
+                  int32_t Kpad, int32_t img_dtype, void* stream);
+/* tokens[b, n_prefix + i, :] = proj[b*G + i, :] + pos[n_prefix + i, :];  tokens[b, j<n_prefix, :] =
+ * prefix[j, :] + pos[j, :]   (vision_transformer.py:1038-1075 with no_embed_class=False).          */
+B200_API int b200_assemble_tokens(const void* proj, const void* prefix, const void* pos, void* tokens, int32_t B,
+                         int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype, void* stream);
+
+/* ------------------------------------------------------------------ elementwise / reductions
+ * column sums of a bf16 [rows, cols] matrix into fp32 [cols] (bias gradients).                       */
+B200_API int b200_colsum(const void* x, float* out, int64_t rows, int32_t cols, int32_t accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TIMM_H_ */

@@ -1,0 +1,36 @@
+// Host-side helpers shared by every translation unit of libb200timm.so: error reporting, the
+// driver entry point for cuTensorMapEncodeTiled (resolved at run time so the library links against
+// cudart only), device-property cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b200timm.h"
+
+namespace b200 {
+
+// Records a message retrievable through b200_last_error() and returns `code`.
+int fail(int code, const char* fmt, ...);
+
+#define B200_CHECK_ARG(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) return ::b200::fail(B200_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define B200_CUDA_OK(expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return ::b200::fail(B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                          __FILE__, __LINE__);                                                    \
+  } while (0)
+
+// Number of SMs of the current device (cached per device).
+int sm_count();
+
+// Encode a tiled tensor map over a bf16 tensor of rank `rank` (dims[0] innermost, strides in BYTES for
+// dims 1..rank-1), 128-byte swizzle, zero fill out of bounds.  Returns 0 or an error code.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+}  // namespace b200

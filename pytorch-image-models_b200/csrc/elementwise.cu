@@ -1,0 +1,194 @@
+// HBM-bound helper kernels around the GEMMs: patch gather (PatchEmbed), token assembly (cls/pos embed),
+// column sums (bias gradients).  All are 16-byte vectorised, coalesced along the innermost dimension.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// patches[(b*gh + py)*gw + px][c*p*p + ky*p + kx] = img[b][c][py*p + ky][px*p + kx]
+// One thread per 8 consecutive k.  When p % 8 == 0 (and the image is bf16) the 8 elements are one
+// aligned 16-byte load from an image row; otherwise elements are gathered one by one.
+// Replaces the im2col implied by nn.Conv2d(k=p, stride=p) at timm/layers/patch_embed.py:136.
+template <bool IMG_F32>
+__global__ void patchify_kernel(const void* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+                                int W, int p, int gh, int gw, int Kpad) {
+  const int kvecs = Kpad >> 3;
+  const long long total = static_cast<long long>(B) * gh * gw * kvecs;
+  const int K = C * p * p;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kv = static_cast<int>(idx % kvecs);
+    const long long patch = idx / kvecs;
+    const int px = static_cast<int>(patch % gw);
+    const int py = static_cast<int>((patch / gw) % gh);
+    const int b = static_cast<int>(patch / (static_cast<long long>(gw) * gh));
+    const int k0 = kv * 8;
+    uint4 q;
+    if (!IMG_F32 && (p & 7) == 0 && k0 + 8 <= K) {
+      const int c = k0 / (p * p);
+      const int rem = k0 - c * p * p;
+      const int ky = rem / p, kx = rem - ky * p;
+      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(img) +
+                                 ((static_cast<long long>(b) * C + c) * H + (py * p + ky)) * W + (px * p + kx);
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        q = __ldg(reinterpret_cast<const uint4*>(src));
+      } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+        q = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + i;
+        if (k < K) {
+          const int c = k / (p * p);
+          const int rem = k - c * p * p;
+          const int ky = rem / p, kx = rem - ky * p;
+          const long long off = ((static_cast<long long>(b) * C + c) * H + (py * p + ky)) * W + (px * p + kx);
+          v[i] = IMG_F32 ? __ldg(reinterpret_cast<const float*>(img) + off)
+                         : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(img)[off]);
+        } else {
+          v[i] = 0.f;
+        }
+      }
+      q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
+      q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    }
+    *reinterpret_cast<uint4*>(out + patch * Kpad + k0) = q;
+  }
+}
+
+__device__ __forceinline__ void ld8(const void* base, bool f32, long long idx, float (&v)[8]) {
+  if (f32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx));
+    v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+    v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+  }
+}
+
+// tokens[b][j][:] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix]) + pos[j]
+// timm/models/vision_transformer.py:1038-1075 (_pos_embed: cat cls/reg tokens, add pos_embed).
+__global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ proj, const void* __restrict__ prefix,
+                                       const void* __restrict__ pos, __nv_bfloat16* __restrict__ tokens, int B, int G,
+                                       int n_prefix, int D, int param_f32) {
+  const int dvecs = D >> 3;
+  const int ntok = G + n_prefix;
+  const long long total = static_cast<long long>(B) * ntok * dvecs;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int dv = static_cast<int>(idx % dvecs);
+    const long long t = idx / dvecs;
+    const int j = static_cast<int>(t % ntok);
+    const int b = static_cast<int>(t / ntok);
+    float v[8], pv[8];
+    if (j < n_prefix) ld8(prefix, param_f32, static_cast<long long>(j) * D + dv * 8, v);
+    else ld8(proj, false, (static_cast<long long>(b) * G + (j - n_prefix)) * D + dv * 8, v);
+    if (pos != nullptr) {
+      ld8(pos, param_f32, static_cast<long long>(j) * D + dv * 8, pv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += pv[i];
+    }
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
+    q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tokens + t * D + dv * 8) = q;
+  }
+}
+
+// out[c] += sum over a slab of rows of x[r][c]; blockIdx.x = 256-column group, blockIdx.y = row slab.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int cols,
+              long long rows_per_slab) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
+  const long long r1 = min(rows, r0 + rows_per_slab);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < cols) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      uint4 q = __ldg(reinterpret_cast<const uint4*>(x + r * cols + col));
+      acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+      acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][c];
+  if (blockIdx.x * 256 + c < cols) atomicAdd(out + blockIdx.x * 256 + c, s);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
+                             int32_t Kpad, int32_t img_dtype, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(img && patches, "b200_patchify: null pointer");
+  B200_CHECK_ARG(B > 0 && C > 0 && p > 0 && H >= p && W >= p, "b200_patchify: bad shape");
+  B200_CHECK_ARG(Kpad % 8 == 0 && Kpad >= C * p * p, "b200_patchify: Kpad=%d must be a multiple of 8 and >= C*p*p", Kpad);
+  const int gh = H / p, gw = W / p;
+  const long long total = static_cast<long long>(B) * gh * gw * (Kpad / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (img_dtype == B200_DTYPE_F32)
+    patchify_kernel<true><<<static_cast<int>(blocks), threads, 0, st>>>(img, reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p, gh, gw, Kpad);
+  else
+    patchify_kernel<false><<<static_cast<int>(blocks), threads, 0, st>>>(img, reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p, gh, gw, Kpad);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_assemble_tokens(const void* proj, const void* prefix, const void* pos, void* tokens, int32_t B,
+                                    int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(proj && tokens, "b200_assemble_tokens: null pointer");
+  B200_CHECK_ARG(n_prefix == 0 || prefix != nullptr, "b200_assemble_tokens: n_prefix > 0 needs prefix tokens");
+  B200_CHECK_ARG(B > 0 && G > 0 && n_prefix >= 0 && D > 0 && D % 8 == 0, "b200_assemble_tokens: bad shape (D %% 8 == 0)");
+  const long long total = static_cast<long long>(B) * (G + n_prefix) * (D / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  assemble_tokens_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(proj), prefix, pos, reinterpret_cast<__nv_bfloat16*>(tokens), B, G,
+      n_prefix, D, param_dtype == B200_DTYPE_F32);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_colsum(const void* x, float* out, int64_t rows, int32_t cols, int32_t accumulate, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(x && out, "b200_colsum: null pointer");
+  B200_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0, "b200_colsum: bad shape (cols %% 8 == 0)");
+  if (!accumulate) B200_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  const int gx = (cols + 255) / 256;
+  int slabs = (sm_count() * 4 + gx - 1) / gx;
+  long long rps = (rows + slabs - 1) / slabs;
+  if (rps < 8) rps = 8;
+  slabs = static_cast<int>((rows + rps - 1) / rps);
+  colsum_kernel<<<dim3(gx, slabs), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols, rps);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_attn_bwd(const void*, const void*, const void*, const float*, float*, void*, const int32_t*,
+                             int32_t, int32_t, int32_t, int32_t, float, void*) {
+  return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: not implemented yet");
+}

@@ -1,0 +1,306 @@
+// LayerNorm forward / backward over the last dimension, one warp per row, row held in registers.
+// HBM-bound: forward moves (read x + write y) bytes once; backward reads dy, x and writes dx once,
+// dweight/dbias via per-CTA partials + a second reduction kernel.
+// Replaces F.layer_norm at timm/layers/norm.py:85-90 (LayerNorm.forward) and its autograd backward.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kLnWarps = 8;
+
+template <bool F32>
+__device__ __forceinline__ void load8(const void* base, long long idx, float (&v)[8]) {
+  if constexpr (F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+    v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+  }
+}
+template <bool F32>
+__device__ __forceinline__ void store8(void* base, long long idx, const float (&v)[8]) {
+  if constexpr (F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
+    q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = q;
+  }
+}
+__device__ __forceinline__ void load8_rt(const void* base, bool f32, long long idx, float (&v)[8]) {
+  if (f32) load8<true>(base, idx, v); else load8<false>(base, idx, v);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// VPL: 8-element vectors per lane (cols <= VPL * 256).
+template <int VPL, bool XF32, bool YF32>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ w, const void* __restrict__ b,
+                     void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     long long rows, int cols, float eps, int param_f32) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
+  const long long warp_stride = static_cast<long long>(gridDim.x) * kLnWarps;
+  const int nvec = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  for (long long row = warp_global; row < rows; row += warp_stride) {
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        load8<XF32>(x, row * cols + vec * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+    }
+    const float mean = warp_sum(s) * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + i * 32 < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq = fmaf(d, d, sq); }
+      }
+    }
+    const float var = warp_sum(sq) * inv_n;
+    const float rstd = rsqrtf(var + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+        if (w != nullptr) {
+          float wv[8];
+          load8_rt(w, param_f32, vec * 8, wv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= wv[j];
+        }
+        if (b != nullptr) {
+          float bv[8];
+          load8_rt(b, param_f32, vec * 8, bv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += bv[j];
+        }
+        store8<YF32>(y, row * cols + vec * 8, o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// Backward. dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w,  xhat = (x - mean) * rstd.
+// Per-CTA partial sums of dy*xhat (dweight) and dy (dbias) go to ws[blockIdx.x][2*cols].
+template <int VPL, bool XF32, bool DYF32>
+__global__ void __launch_bounds__(kLnWarps * 32)
+layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const void* __restrict__ w,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, void* __restrict__ dx,
+                     float* __restrict__ ws, long long rows, int cols, int param_f32) {
+  extern __shared__ float red[];  // [kLnWarps][2*cols]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
+  const long long warp_stride = static_cast<long long>(gridDim.x) * kLnWarps;
+  const int nvec = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  float dw_acc[VPL][8], db_acc[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dw_acc[i][j] = 0.f; db_acc[i][j] = 0.f; }
+
+  for (long long row = warp_global; row < rows; row += warp_stride) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[VPL][8], g[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        float xv[8], dyv[8], wv[8];
+        load8<XF32>(x, row * cols + vec * 8, xv);
+        load8<DYF32>(dy, row * cols + vec * 8, dyv);
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mean) * rstd;
+          g[i][j] = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], xh[i][j], s2);
+          dw_acc[i][j] = fmaf(dyv[j], xh[i][j], dw_acc[i][j]);
+          db_acc[i][j] += dyv[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; g[i][j] = 0.f; }
+      }
+    }
+    const float m1 = warp_sum(s1) * inv_n;
+    const float m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - m1 - xh[i][j] * m2);
+        store8<XF32>(dx, row * cols + vec * 8, o);
+      }
+    }
+  }
+  // CTA reduction of the per-warp partials, then one row of the workspace per CTA.
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + i * 32;
+    if (vec < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red[warp * 2 * cols + vec * 8 + j] = dw_acc[i][j];
+        red[warp * 2 * cols + cols + vec * 8 + j] = db_acc[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnWarps; ++k) s += red[k * 2 * cols + c];
+    ws[static_cast<long long>(blockIdx.x) * 2 * cols + c] = s;
+  }
+}
+
+// out[c] = sum_r ws[r][c]; one thread per column pair group, coalesced over c.
+__global__ void reduce_rows_kernel(const float* __restrict__ ws, float* __restrict__ out0, float* __restrict__ out1,
+                                   int nrows, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 2 * cols) return;
+  float s = 0.f;
+  for (int r = 0; r < nrows; ++r) s += ws[static_cast<long long>(r) * 2 * cols + c];
+  if (c < cols) { if (out0) out0[c] = s; }
+  else          { if (out1) out1[c - cols] = s; }
+}
+
+static int ln_grid(long long rows) {
+  long long want = (rows + kLnWarps - 1) / kLnWarps;
+  long long cap = static_cast<long long>(sm_count()) * 8;
+  return static_cast<int>(want < cap ? want : cap);
+}
+static int ln_bwd_grid(long long rows) {
+  long long want = (rows + kLnWarps - 1) / kLnWarps;
+  long long cap = static_cast<long long>(sm_count()) * 2;
+  return static_cast<int>(want < cap ? want : cap);
+}
+
+template <int VPL>
+static void launch_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, long long rows,
+                       int cols, float eps, int xf32, int yf32, int pf32, cudaStream_t st) {
+  const int grid = ln_grid(rows);
+  const int threads = kLnWarps * 32;
+  if (xf32 && yf32) layernorm_fwd_kernel<VPL, true, true><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
+  else if (xf32) layernorm_fwd_kernel<VPL, true, false><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
+  else if (yf32) layernorm_fwd_kernel<VPL, false, true><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
+  else layernorm_fwd_kernel<VPL, false, false><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
+}
+
+template <int VPL>
+static int launch_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                      float* ws, long long rows, int cols, int xf32, int dyf32, int pf32, cudaStream_t st) {
+  const int grid = ln_bwd_grid(rows);
+  const int threads = kLnWarps * 32;
+  const size_t smem = static_cast<size_t>(kLnWarps) * 2 * cols * sizeof(float);
+  if (smem > 48 * 1024) {
+    auto set = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+    if (xf32 && dyf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, true, true>));
+    else if (xf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, true, false>));
+    else if (dyf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, false, true>));
+    else B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, false, false>));
+  }
+  if (xf32 && dyf32) layernorm_bwd_kernel<VPL, true, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
+  else if (xf32) layernorm_bwd_kernel<VPL, true, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
+  else if (dyf32) layernorm_bwd_kernel<VPL, false, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
+  else layernorm_bwd_kernel<VPL, false, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_layernorm_fwd(const void* x, const void* weight, const void* bias, void* y, float* mean,
+                                  float* rstd, int64_t rows, int32_t cols, float eps, int32_t x_dtype,
+                                  int32_t y_dtype, int32_t param_dtype, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(x && y, "b200_layernorm_fwd: null x/y");
+  B200_CHECK_ARG(rows >= 0 && cols > 0, "b200_layernorm_fwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
+  if (cols % 8 != 0 || cols > 2048)
+    return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_fwd: cols=%d must be a multiple of 8 and <= 2048", cols);
+  if (rows == 0) return B200_OK;
+  const int vpl = (cols + 255) / 256;
+  const int xf = x_dtype == B200_DTYPE_F32, yf = y_dtype == B200_DTYPE_F32, pf = param_dtype == B200_DTYPE_F32;
+  switch (vpl) {
+    case 1: launch_fwd<1>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
+    case 2: launch_fwd<2>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
+    case 3: launch_fwd<3>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
+    case 4: launch_fwd<4>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
+    case 5: case 6: launch_fwd<6>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
+    default: launch_fwd<8>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
+  }
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_layernorm_bwd_ws_rows(int64_t rows, int32_t cols) {
+  (void)cols;
+  return ln_bwd_grid(rows > 0 ? rows : 1);
+}
+
+extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* weight, const float* mean,
+                                  const float* rstd, void* dx, float* dweight, float* dbias, float* workspace,
+                                  int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
+                                  int32_t param_dtype, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(dy && x && mean && rstd && dx && workspace, "b200_layernorm_bwd: null pointer");
+  B200_CHECK_ARG(rows > 0 && cols > 0, "b200_layernorm_bwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
+  if (cols % 8 != 0 || cols > 2048)
+    return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_bwd: cols=%d must be a multiple of 8 and <= 2048", cols);
+  const int vpl = (cols + 255) / 256;
+  const int xf = x_dtype == B200_DTYPE_F32, dyf = dy_dtype == B200_DTYPE_F32, pf = param_dtype == B200_DTYPE_F32;
+  int rc;
+  switch (vpl) {
+    case 1: rc = launch_bwd<1>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 2: rc = launch_bwd<2>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 3: rc = launch_bwd<3>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 4: rc = launch_bwd<4>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 5: case 6: rc = launch_bwd<6>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    default: rc = launch_bwd<8>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+  }
+  if (rc) return rc;
+  B200_CUDA_OK(cudaGetLastError());
+  if (dweight || dbias) {
+    const int nrows = ln_bwd_grid(rows);
+    const int threads = 128;
+    reduce_rows_kernel<<<(2 * cols + threads - 1) / threads, threads, 0, st>>>(workspace, dweight, dbias, nrows, cols);
+    B200_CUDA_OK(cudaGetLastError());
+  }
+  return B200_OK;
+}

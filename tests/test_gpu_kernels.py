@@ -1,0 +1,220 @@
+"""Kernel-level parity on the GPU: every libb200timm entry point against a plain PyTorch fp32 restatement of
+the same op on the same seeded inputs (the op-level oracle; model-level parity lives in test_gpu_models.py).
+
+Tolerances: outputs are bf16, accumulations fp32.  A bf16 result of magnitude |y| carries up to |y| * 2^-8
+rounding error, so comparisons use atol + rtol * |ref| with rtol = 1e-2 unless stated otherwise.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from b200timm import ops
+    return ops
+
+
+def _close(got, ref, atol, rtol, what):
+    got = got.float()
+    ref = ref.float()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(got).all(), f"{what}: non-finite values"
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} elements off, max abs err {err.max().item():.4g} "
+                           f"(ref max {ref.abs().max().item():.4g})")
+
+
+def _gelu(x):
+    return 0.5 * x * (1.0 + torch.erf(x * 0.7071067811865476))
+
+
+def _dgelu(x):
+    return 0.5 * (1.0 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (1000, 768, 768), (394, 200, 72), (77, 1000, 192)])
+def test_gemm_layouts(a_mn, b_mn, M, N, K):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    b = torch.randn(N, K, device=DEV, generator=g).bfloat16()
+    # MN-major operands need M (resp. N) to be a multiple of 8 for the 16-byte TMA stride rule.
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operand with a leading dimension that is not a multiple of 8")
+    a_in = a.t().contiguous() if a_mn else a
+    b_in = b.t().contiguous() if b_mn else b
+    out = ops.gemm(a_in, b_in, M, N, K, a_mn=a_mn, b_mn=b_mn)
+    ref = a.float() @ b.float().t()
+    _close(out, ref, atol=2e-2 * math.sqrt(K / 64), rtol=1e-2, what=f"gemm a_mn={a_mn} b_mn={b_mn} {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("param_dtype", [torch.bfloat16, torch.float32])
+def test_gemm_epilogues(param_dtype):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    M, N, K = 1000, 768, 384
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g).to(param_dtype)
+    gamma = torch.randn(N, device=DEV, generator=g).to(param_dtype)
+    aux = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    acc = a.float() @ w.float().t() + bias.float()
+
+    _close(ops.gemm(a, w, M, N, K, bias=bias), acc, 2e-2, 1e-2, "bias")
+    _close(ops.gemm(a, w, M, N, K, bias=bias, epilogue=ops.EPI_BIAS_GELU), _gelu(acc), 2e-2, 1e-2, "bias+gelu")
+    _close(ops.gemm(a, w, M, N, K, bias=bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=aux), aux.float() + acc, 3e-2, 1e-2,
+           "bias+residual")
+    _close(ops.gemm(a, w, M, N, K, bias=bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=aux, gamma=gamma),
+           aux.float() + gamma.float() * acc, 3e-2, 1e-2, "bias+layerscale+residual")
+    _close(ops.gemm(a, w, M, N, K, bias=bias, epilogue=ops.EPI_DGELU, aux=aux), acc * _dgelu(aux.float()), 2e-2, 1e-2,
+           "dgelu")
+
+
+def test_gemm_fp32_out_accumulate_splitk():
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    M, N, K = 768, 384, 4096
+    a = torch.randn(K, M, device=DEV, generator=g).bfloat16()  # stored [K, M]  (a_mn)
+    b = torch.randn(K, N, device=DEV, generator=g).bfloat16()  # stored [K, N]  (b_mn)
+    ref = a.float().t() @ b.float()
+    out = ops.gemm(a, b, M, N, K, a_mn=True, b_mn=True, out_dtype=torch.float32)
+    _close(out, ref, 1e-2, 1e-3, "fp32 out")
+    base = torch.randn(M, N, device=DEV, generator=g)
+    out2 = base.clone()
+    ops.gemm(a, b, M, N, K, a_mn=True, b_mn=True, out=out2, accumulate=True)
+    _close(out2, base + ref, 1e-2, 1e-3, "accumulate")
+    out3 = base.clone()
+    ops.gemm(a, b, M, N, K, a_mn=True, b_mn=True, out=out3, split_k=8)
+    _close(out3, base + ref, 1e-2, 1e-3, "split_k=8 (atomic accumulate)")
+
+
+def test_gemm_vit_base_shapes():
+    """The four ViT-B/16 GEMMs at batch 16 (M = 16*197 = 3152, not a multiple of 128)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    M = 16 * 197
+    for N, K in ((2304, 768), (768, 768), (3072, 768), (768, 3072)):
+        a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+        w = (torch.randn(N, K, device=DEV, generator=g) * 0.02).bfloat16()
+        bias = torch.randn(N, device=DEV, generator=g).bfloat16()
+        ref = a.float() @ w.float().t() + bias.float()
+        _close(ops.linear_fwd(a, w, bias), ref, 2e-2, 1e-2, f"linear {N}x{K}")
+
+
+def test_gemm_rejects_bad_arguments():
+    ops = _ops()
+    from b200timm import B200Error
+    a = torch.zeros(16, 60, device=DEV, dtype=torch.bfloat16)  # K=60: row stride not a multiple of 16 bytes
+    w = torch.zeros(8, 60, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(B200Error):
+        ops.gemm(a, w, 16, 8, 60)
+    with pytest.raises(B200Error):
+        ops.gemm(torch.zeros(16, 64), torch.zeros(8, 64), 16, 8, 64)  # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("cols", [192, 768, 1024, 128, 1536])
+@pytest.mark.parametrize("xdt,pdt", [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32),
+                                     (torch.bfloat16, torch.float32)])
+def test_layernorm_fwd_bwd(cols, xdt, pdt):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(cols)
+    rows = 1003
+    x = (torch.randn(rows, cols, device=DEV, generator=g) * 2 + 0.5).to(xdt)
+    w = (torch.randn(cols, device=DEV, generator=g) * 0.5 + 1).to(pdt)
+    b = torch.randn(cols, device=DEV, generator=g).to(pdt)
+    dy = torch.randn(rows, cols, device=DEV, generator=g).to(xdt)
+    eps = 1e-6
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, eps, save_stats=True)
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    br = b.float().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (cols,), wr, br, eps)
+    atol = 3e-2 if xdt == torch.bfloat16 else 1e-4
+    rtol = 1e-2 if xdt == torch.bfloat16 else 1e-4
+    _close(y, yr.detach(), atol, rtol, "ln fwd")
+    _close(mean, x.float().mean(-1), 1e-4, 1e-4, "ln mean")
+    _close(rstd, 1.0 / torch.sqrt(x.float().var(-1, unbiased=False) + eps), 1e-3, 1e-3, "ln rstd")
+    yr.backward(dy.float())
+    dx, dw, db = ops.layernorm_bwd(dy, x, w, mean, rstd)
+    _close(dx, xr.grad, atol, rtol, "ln dx")
+    _close(dw, wr.grad, 2e-2 if xdt == torch.bfloat16 else 2e-3, 1e-3, "ln dweight")
+    _close(db, br.grad, 2e-2 if xdt == torch.bfloat16 else 2e-3, 1e-3, "ln dbias")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, B, N, H, hd, scale, kv_len=None):
+    q, k, v = qkv.float().view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if kv_len is not None:
+        keys = torch.arange(N, device=qkv.device)[None, None, None, :]
+        s = s.masked_fill(keys >= kv_len.view(B, 1, 1, 1), float("-inf"))
+    p = s.softmax(-1)
+    o = (p @ v).transpose(1, 2).reshape(B, N, H * hd)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 64, 3), (2, 256, 4), (1, 577, 16), (2, 208, 2), (2, 129, 2),
+                                   (1, 1025, 2)])
+def test_attention_fwd(B, N, H):
+    ops = _ops()
+    hd = 64
+    g = torch.Generator(device=DEV).manual_seed(N + H)
+    qkv = torch.randn(B, N, 3 * H * hd, device=DEV, generator=g).bfloat16()
+    scale = hd ** -0.5
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, scale, need_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, N, H, hd, scale)
+    _close(out, ref, 1e-2, 2e-2, f"attention B={B} N={N} H={H}")
+    _close(lse, lse_ref, 1e-2, 1e-3, "lse")
+
+
+@pytest.mark.parametrize("N", [197, 577])
+def test_attention_fwd_key_padding(N):
+    ops = _ops()
+    B, H, hd = 4, 4, 64
+    g = torch.Generator(device=DEV).manual_seed(N)
+    qkv = (torch.randn(B, N, 3 * H * hd, device=DEV, generator=g) * 1.5).bfloat16()
+    kv_len = torch.tensor([N, 1, N // 2, 130], device=DEV, dtype=torch.int32)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, 0.125, kv_len=kv_len, need_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, N, H, hd, 0.125, kv_len)
+    _close(out, ref, 1e-2, 2e-2, "masked attention")
+    _close(lse, lse_ref, 1e-2, 1e-3, "masked lse")
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+@pytest.mark.parametrize("p,size,dt", [(16, 224, torch.bfloat16), (14, 224, torch.bfloat16), (16, 64, torch.float32),
+                                       (4, 32, torch.bfloat16)])
+def test_patchify(p, size, dt):
+    ops = _ops()
+    B, C = 3, 3
+    g = torch.Generator(device=DEV).manual_seed(p)
+    img = torch.randn(B, C, size, size, device=DEV, generator=g).to(dt)
+    out = ops.patchify(img, p)
+    K = C * p * p
+    ref = torch.nn.functional.unfold(img.float(), kernel_size=p, stride=p).transpose(1, 2).reshape(-1, K)
+    assert out.shape[1] % 8 == 0 and out.shape[1] >= K
+    assert torch.equal(out[:, :K].float(), ref.bfloat16().float())
+    assert (out[:, K:] == 0).all()
+
+
+def test_assemble_tokens_and_colsum():
+    ops = _ops()
+    B, G, D, npre = 3, 196, 768, 1
+    g = torch.Generator(device=DEV).manual_seed(0)
+    proj = torch.randn(B * G, D, device=DEV, generator=g).bfloat16()
+    cls = torch.randn(1, 1, D, device=DEV, generator=g).bfloat16()
+    pos = torch.randn(1, G + npre, D, device=DEV, generator=g).bfloat16()
+    tok = ops.assemble_tokens(proj, cls, pos, B, G, npre, D)
+    ref = torch.cat([cls.float().expand(B, -1, -1), proj.float().view(B, G, D)], 1) + pos.float()
+    assert torch.equal(tok.float(), ref.bfloat16().float())
+    x = torch.randn(5000, 776, device=DEV, generator=g).bfloat16()
+    _close(ops.colsum(x), x.float().sum(0), 2e-2, 1e-4, "colsum")
