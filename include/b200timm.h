@@ -108,10 +108,12 @@ B200_API int b200_attn_bwd(const void* qkv, const void* out, const void* dout, c
  * (k = c*p*p + ky*p + kx, matching Conv2d.weight.flatten(1)); Kpad >= C*p*p, zero padded.              */
 B200_API int b200_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
                   int32_t Kpad, int32_t img_dtype, void* stream);
-/* tokens[b, n_prefix + i, :] = proj[b*G + i, :] + pos[n_prefix + i, :];  tokens[b, j<n_prefix, :] =
- * prefix[j, :] + pos[j, :]   (vision_transformer.py:1038-1075 with no_embed_class=False).          */
+/* pos_has_prefix=1: tokens[b, j, :] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix]) + pos[j]
+ * pos_has_prefix=0: prefix tokens get no position, patch token i gets pos[i]  (no_embed_class=True)
+ * (vision_transformer.py:1038-1075, _pos_embed).  prefix / pos: [n_prefix, D] / [.., D], dtype param_dtype. */
 B200_API int b200_assemble_tokens(const void* proj, const void* prefix, const void* pos, void* tokens, int32_t B,
-                         int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype, void* stream);
+                         int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype,
+                         int32_t pos_has_prefix, void* stream);
 
 /* ------------------------------------------------------------------ elementwise / reductions
  * column sums of a bf16 [rows, cols] matrix into fp32 [cols] (bias gradients).                       */

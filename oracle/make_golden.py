@@ -1,0 +1,116 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference (timm at /root/reference), CPU fp32.
+
+Run in the authoring container only (the GPU box has no /root/reference):
+    python oracle/make_golden.py
+Each fixture holds the reference module's state_dict, the seeded inputs and the reference outputs /
+gradients.  The oracle restatement (oracle/vit_oracle.py) is pinned against them by
+tests/test_oracle_golden.py; the CUDA path is checked against them by tests/test_gpu_models.py.
+Head dim is 64 in every config (the tcgen05 attention kernel's supported head size).
+"""
+import os
+import sys
+
+import torch
+
+REF = os.environ.get("TIMM_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _half_sd(sd):
+    return {k: v.clone() for k, v in sd.items()}
+
+
+def vit_case(name, seed, batch, kwargs, backward=True):
+    import timm  # noqa: F401
+    from timm.models.vision_transformer import VisionTransformer
+    torch.manual_seed(seed)
+    model = VisionTransformer(**kwargs)
+    # default init zeroes biases / sets LN to (1, 0): perturb so every parameter path is exercised
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+            if n in ("cls_token", "reg_token", "pos_embed"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    model.eval()
+    img = torch.randn(batch, kwargs.get("in_chans", 3), kwargs["img_size"], kwargs["img_size"], generator=g)
+    feats_per_block = []
+    hooks = [blk.register_forward_hook(lambda m, i, o: feats_per_block.append(o.detach().clone()))
+             for blk in model.blocks]
+    feats = model.forward_features(img)
+    logits = model.forward_head(feats)
+    for h in hooks:
+        h.remove()
+    fx = {"kind": "vit", "kwargs": kwargs, "state_dict": _half_sd(model.state_dict()), "img": img,
+          "features": feats.detach(), "logits": logits.detach(), "block_outputs": feats_per_block,
+          "timm_version": timm.__version__, "torch_version": str(torch.__version__)}
+    if backward:
+        # the reference's own backward test pattern: outputs.mean().backward()  (tests/test_models.py:209-242)
+        model.zero_grad()
+        model(img).mean().backward()
+        fx["grads"] = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, "logits", tuple(logits.shape), "absmax", logits.abs().max().item(),
+          "params", sum(p.numel() for p in model.parameters()))
+
+
+def layer_cases():
+    from timm.layers import Attention, LayerNorm, Mlp, PatchEmbed, LayerScale, DropPath
+    from timm.models.naflexvit import create_attention_mask
+    g = torch.Generator().manual_seed(7)
+    fx = {"kind": "layers"}
+    torch.manual_seed(7)
+    # Attention with and without a NaFlex-style key-padding mask
+    attn = Attention(128, num_heads=2, qkv_bias=True).eval()
+    with torch.no_grad():
+        attn.qkv.bias.add_(torch.randn(attn.qkv.bias.shape, generator=g) * 0.1)
+        attn.proj.bias.add_(torch.randn(attn.proj.bias.shape, generator=g) * 0.1)
+    x = torch.randn(3, 37, 128, generator=g)
+    valid = torch.zeros(3, 37, dtype=torch.bool)
+    lens = [37, 20, 5]
+    for i, n in enumerate(lens):
+        valid[i, :n] = True
+    mask = create_attention_mask(valid, num_prefix_tokens=0, dtype=torch.float32)
+    fx["attention"] = {"state_dict": _half_sd(attn.state_dict()), "x": x, "num_heads": 2, "y": attn(x).detach(),
+                       "kv_len": torch.tensor(lens, dtype=torch.int32), "y_masked": attn(x, attn_mask=mask).detach()}
+    mlp = Mlp(128, 512).eval()
+    fx["mlp"] = {"state_dict": _half_sd(mlp.state_dict()), "x": x, "y": mlp(x).detach()}
+    ln = LayerNorm(128, eps=1e-6)
+    with torch.no_grad():
+        ln.weight.add_(torch.randn(128, generator=g) * 0.2)
+        ln.bias.add_(torch.randn(128, generator=g) * 0.2)
+    fx["layernorm"] = {"state_dict": _half_sd(ln.state_dict()), "x": x * 3 + 1, "eps": 1e-6, "y": ln(x * 3 + 1).detach()}
+    for p, size in ((16, 64), (14, 56), (4, 32)):
+        pe = PatchEmbed(img_size=size, patch_size=p, in_chans=3, embed_dim=64).eval()
+        img = torch.randn(2, 3, size, size, generator=g)
+        fx[f"patch_embed_p{p}"] = {"state_dict": _half_sd(pe.state_dict()), "img": img, "patch": p, "y": pe(img).detach()}
+    ls = LayerScale(128, init_values=0.3)
+    fx["layerscale"] = {"state_dict": _half_sd(ls.state_dict()), "x": x, "y": ls(x).detach()}
+    # DropPath semantics (timm/layers/drop.py:158-175): kept samples scaled by exactly 1/keep_prob
+    torch.manual_seed(3)
+    dp = DropPath(0.25).train()
+    xin = torch.ones(64, 4, 8)
+    y = dp(xin)
+    fx["droppath"] = {"drop_prob": 0.25, "x": xin, "y": y, "keep_mask": (y[:, 0, 0] != 0).to(torch.int32)}
+    torch.save(fx, os.path.join(OUT, "layers.pt"))
+    print("layers fixture written")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    base = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=2, num_heads=2,
+                mlp_ratio=4.0, qkv_bias=True)
+    vit_case("vit_g1_default", 0, 3, base)
+    vit_case("vit_g2_layerscale_reg_avg", 1, 2,
+             dict(img_size=48, patch_size=8, in_chans=3, num_classes=7, embed_dim=128, depth=1, num_heads=2,
+                  qkv_bias=True, init_values=0.1, reg_tokens=2, global_pool="avg"), backward=False)
+    vit_case("vit_g3_prenorm_noembedclass", 2, 2,
+             dict(img_size=56, patch_size=14, in_chans=3, num_classes=5, embed_dim=64, depth=1, num_heads=1,
+                  qkv_bias=True, pre_norm=True, no_embed_class=True), backward=False)
+    layer_cases()
+
+
+if __name__ == "__main__":
+    main()

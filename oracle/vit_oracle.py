@@ -1,0 +1,264 @@
+"""ORACLE (test infrastructure, NOT product code): CPU fp32 restatement of timm's ViT hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module, and only as the checker / CPU baseline -- never as the thing shipped.  The product path lives in
+pytorch-image-models_b200/ and fails loudly when its CUDA library is missing.
+
+Parity pinning: every function below restates one reference function (file:line relative to the timm
+checkout, timm 1.0.28.dev0) and is pinned against golden vectors produced by the *unmodified* reference
+in the authoring container (oracle/make_golden.py -> tests/golden/*.pt, checked by
+tests/test_oracle_golden.py).  The reference's own golden test (tests/test_models.py:132-173) needs
+network access for pretrained weights and cannot run here, so those fixtures are the pin.
+
+The arithmetic is written out explicitly with torch CPU fp32 tensor ops (matmul / exp / mean), i.e. it does
+not call F.layer_norm, F.scaled_dot_product_attention or F.gelu, so that it is an independent statement of
+what the CUDA kernels must compute.
+"""
+import math
+
+import torch
+
+
+# ----------------------------------------------------------------------------------------------- leaf ops
+def layer_norm(x, weight, bias, eps):
+    """timm/layers/norm.py:85-90 (LayerNorm.forward -> F.layer_norm): biased variance over the last dim."""
+    mean = x.mean(-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(-1, keepdim=True)
+    y = (x - mean) / torch.sqrt(var + eps)
+    if weight is not None:
+        y = y * weight
+    if bias is not None:
+        y = y + bias
+    return y
+
+
+def gelu_erf(x):
+    """nn.GELU() default (exact erf form), timm/layers/mlp.py:24,49."""
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def linear(x, weight, bias=None):
+    """nn.Linear: y = x W^T + b (timm/layers/attention.py:100,105; mlp.py:40,44)."""
+    y = x @ weight.t()
+    return y if bias is None else y + bias
+
+
+def attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, kv_len=None):
+    """timm/layers/attention.py:108-139 (Attention.forward, qk_norm=False, no dropout).
+
+    kv_len: optional int tensor [B]; keys >= kv_len[b] are masked out, which is what the additive
+    finfo.min mask built by naflexvit.py:964-1029 does for prefix-valid padding.
+    """
+    B, N, C = x.shape
+    hd = qkv_w.shape[0] // 3 // num_heads
+    qkv = linear(x, qkv_w, qkv_b).reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)  # :115
+    q, k, v = qkv.unbind(0)                                                                 # :116
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)                                             # :127-128
+    if kv_len is not None:
+        keys = torch.arange(N)[None, None, None, :]
+        s = s.masked_fill(keys >= kv_len.view(B, 1, 1, 1), float("-inf"))
+    s = s - s.amax(-1, keepdim=True)
+    p = torch.exp(s)
+    p = p / p.sum(-1, keepdim=True)                                                         # :131 softmax
+    o = (p @ v).transpose(1, 2).reshape(B, N, num_heads * hd)                               # :133,135
+    return linear(o, proj_w, proj_b)                                                        # :137
+
+
+def mlp(x, fc1_w, fc1_b, fc2_w, fc2_b):
+    """timm/layers/mlp.py:47-54 (Mlp.forward, drop=0, norm=Identity)."""
+    return linear(gelu_erf(linear(x, fc1_w, fc1_b)), fc2_w, fc2_b)
+
+
+def drop_path(x, keep_mask, keep_prob, scale_by_keep=True):
+    """timm/layers/drop.py:158-175 with the Bernoulli draw made explicit: keep_mask is a 0/1 tensor [B]."""
+    m = keep_mask.to(x.dtype).view(-1, *([1] * (x.dim() - 1)))
+    if keep_prob > 0.0 and scale_by_keep:
+        m = m / keep_prob
+    return x * m
+
+
+def patch_embed(img, weight, bias, patch):
+    """timm/layers/patch_embed.py:117-142: Conv2d(k=stride=patch) -> flatten(2).transpose(1,2).
+
+    Written as an explicit patch gather + matmul (k = c*p*p + ky*p + kx, Conv2d.weight.flatten(1) order).
+    """
+    B, C, H, W = img.shape
+    gh, gw = H // patch, W // patch
+    x = img[:, :, :gh * patch, :gw * patch].reshape(B, C, gh, patch, gw, patch)
+    x = x.permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * patch * patch)
+    return linear(x, weight.reshape(weight.shape[0], -1), bias)
+
+
+# ----------------------------------------------------------------------------------------------- model
+def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, keep_prob=1.0):
+    """timm/models/vision_transformer.py:206-214 (Block.forward)."""
+    g = lambda k: sd.get(prefix + k)  # noqa: E731
+    h = attention(layer_norm(x, g("norm1.weight"), g("norm1.bias"), eps), g("attn.qkv.weight"), g("attn.qkv.bias"),
+                  g("attn.proj.weight"), g("attn.proj.bias"), num_heads, kv_len)
+    if g("ls1.gamma") is not None:
+        h = h * g("ls1.gamma")                                   # timm/layers/layer_scale.py:26-27
+    if keep1 is not None:
+        h = drop_path(h, keep1, keep_prob)
+    x = x + h
+    h = mlp(layer_norm(x, g("norm2.weight"), g("norm2.bias"), eps), g("mlp.fc1.weight"), g("mlp.fc1.bias"),
+            g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+    if g("ls2.gamma") is not None:
+        h = h * g("ls2.gamma")
+    if keep2 is not None:
+        h = drop_path(h, keep2, keep_prob)
+    return x + h
+
+
+def vit_forward_features(img, sd, cfg, kv_len=None, return_blocks=False):
+    """timm/models/vision_transformer.py:1231-1253 (forward_features) incl. _pos_embed :1038-1075."""
+    eps = cfg.get("eps", 1e-6)
+    x = patch_embed(img, sd["patch_embed.proj.weight"], sd.get("patch_embed.proj.bias"), cfg["patch_size"])
+    B = x.shape[0]
+    to_cat = []
+    if "cls_token" in sd:
+        to_cat.append(sd["cls_token"].expand(B, -1, -1))
+    if "reg_token" in sd:
+        to_cat.append(sd["reg_token"].expand(B, -1, -1))
+    pos = sd.get("pos_embed")
+    if cfg.get("no_embed_class", False):
+        if pos is not None:
+            x = x + pos
+        x = torch.cat(to_cat + [x], 1)
+    else:
+        x = torch.cat(to_cat + [x], 1)
+        if pos is not None:
+            x = x + pos
+    if "norm_pre.weight" in sd:
+        x = layer_norm(x, sd["norm_pre.weight"], sd["norm_pre.bias"], eps)
+    outs = []
+    for i in range(cfg["depth"]):
+        x = block(x, sd, f"blocks.{i}.", cfg["num_heads"], eps, kv_len)
+        outs.append(x)
+    if "norm.weight" in sd:
+        x = layer_norm(x, sd["norm.weight"], sd["norm.bias"], eps)
+    return (x, outs) if return_blocks else x
+
+
+def vit_forward_head(x, sd, cfg):
+    """timm/models/vision_transformer.py:1254-1292 (pool :686-708, fc_norm, head)."""
+    pool = cfg.get("global_pool", "token")
+    npre = cfg.get("num_prefix_tokens", 1)
+    if pool == "token":
+        x = x[:, 0]
+    elif pool == "avg":
+        x = x[:, npre:].mean(1)
+    elif pool:
+        raise ValueError(f"oracle: pool {pool!r} not restated")
+    if "fc_norm.weight" in sd:
+        x = layer_norm(x, sd["fc_norm.weight"], sd["fc_norm.bias"], cfg.get("eps", 1e-6))
+    if "head.weight" in sd:
+        x = linear(x, sd["head.weight"], sd.get("head.bias"))
+    return x
+
+
+def vit_forward(img, sd, cfg, kv_len=None):
+    """timm/models/vision_transformer.py:1294-1302."""
+    return vit_forward_head(vit_forward_features(img, sd, cfg, kv_len), sd, cfg)
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+VIT_CONFIGS = {
+    # name: timm kwargs (the same dict is passed to timm.models.VisionTransformer when making goldens)
+    "vit_tiny_patch16_224": dict(img_size=224, patch_size=16, embed_dim=192, depth=12, num_heads=3),
+    "vit_base_patch16_224": dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12),
+    "vit_large_patch16_224": dict(img_size=224, patch_size=16, embed_dim=1024, depth=24, num_heads=16),
+}
+
+
+def random_state_dict(cfg, seed=0, num_classes=1000, dtype=torch.float32):
+    """Random weights with timm's ViT key names / shapes (trunc-normal-like std .02 linears, small random
+    biases so that bias paths are exercised).  For full-size parity runs where no golden file exists."""
+    g = torch.Generator().manual_seed(seed)
+    D, p, C = cfg["embed_dim"], cfg["patch_size"], cfg.get("in_chans", 3)
+    hid = int(D * cfg.get("mlp_ratio", 4.0))
+    G = (cfg["img_size"] // p) ** 2
+    npre = (1 if cfg.get("class_token", True) else 0) + cfg.get("reg_tokens", 0)
+    rn = lambda *s, std=0.02: (torch.randn(*s, generator=g) * std).to(dtype)  # noqa: E731
+    sd = {"patch_embed.proj.weight": rn(D, C, p, p, std=0.05), "patch_embed.proj.bias": rn(D),
+          "pos_embed": rn(1, G + npre, D)}
+    if cfg.get("class_token", True):
+        sd["cls_token"] = rn(1, 1, D)
+    if cfg.get("reg_tokens", 0):
+        sd["reg_token"] = rn(1, cfg["reg_tokens"], D)
+    for i in range(cfg["depth"]):
+        pre = f"blocks.{i}."
+        sd.update({
+            pre + "norm1.weight": 1 + rn(D, std=0.1), pre + "norm1.bias": rn(D, std=0.05),
+            pre + "attn.qkv.weight": rn(3 * D, D), pre + "attn.qkv.bias": rn(3 * D),
+            pre + "attn.proj.weight": rn(D, D), pre + "attn.proj.bias": rn(D),
+            pre + "norm2.weight": 1 + rn(D, std=0.1), pre + "norm2.bias": rn(D, std=0.05),
+            pre + "mlp.fc1.weight": rn(hid, D), pre + "mlp.fc1.bias": rn(hid),
+            pre + "mlp.fc2.weight": rn(D, hid), pre + "mlp.fc2.bias": rn(D),
+        })
+        if cfg.get("init_values"):
+            sd[pre + "ls1.gamma"] = 0.5 + rn(D, std=0.1)
+            sd[pre + "ls2.gamma"] = 0.5 + rn(D, std=0.1)
+    sd["norm.weight"] = 1 + rn(D, std=0.1)
+    sd["norm.bias"] = rn(D, std=0.05)
+    sd["head.weight"] = rn(num_classes, D)
+    sd["head.bias"] = rn(num_classes)
+    return sd
+
+
+# ----------------------------------------------------------------------------------------------- timing port
+def vit_forward_eager(img, sd, cfg, kv_len=None):
+    """Same computation as vit_forward, issued as the reference issues it on the CPU -- F.conv2d,
+    F.layer_norm, F.linear, F.scaled_dot_product_attention, F.gelu (the call sites listed in SURVEY.md 8c) --
+    so that bench.py's cpu_baseline / --impl reference time the library kernels timm's eager path really
+    runs on the host, not the slower explicit restatement above.  Pinned to the explicit oracle and to
+    the golden vectors by tests/test_oracle_golden.py.  Works in fp32 or bf16 (dtype of `img` / `sd`)."""
+    import torch.nn.functional as F
+    eps = cfg.get("eps", 1e-6)
+    H = cfg["num_heads"]
+    x = F.conv2d(img, sd["patch_embed.proj.weight"], sd.get("patch_embed.proj.bias"), stride=cfg["patch_size"])
+    x = x.flatten(2).transpose(1, 2)
+    B = x.shape[0]
+    to_cat = [sd[k].expand(B, -1, -1) for k in ("cls_token", "reg_token") if k in sd]
+    pos = sd.get("pos_embed")
+    if cfg.get("no_embed_class", False):
+        x = x + pos if pos is not None else x
+        x = torch.cat(to_cat + [x], 1)
+    else:
+        x = torch.cat(to_cat + [x], 1)
+        x = x + pos if pos is not None else x
+    D = x.shape[-1]
+    if "norm_pre.weight" in sd:
+        x = F.layer_norm(x, (D,), sd["norm_pre.weight"], sd["norm_pre.bias"], eps)
+    mask = None
+    if kv_len is not None:
+        N = x.shape[1]
+        mask = (torch.arange(N)[None, :] < kv_len[:, None])[:, None, None, :]
+    for i in range(cfg["depth"]):
+        p = f"blocks.{i}."
+        h = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+        N = h.shape[1]
+        qkv = F.linear(h, sd[p + "attn.qkv.weight"], sd.get(p + "attn.qkv.bias")).reshape(B, N, 3, H, D // H)
+        q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
+        h = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(B, N, D)
+        h = F.linear(h, sd[p + "attn.proj.weight"], sd.get(p + "attn.proj.bias"))
+        if p + "ls1.gamma" in sd:
+            h = h * sd[p + "ls1.gamma"]
+        x = x + h
+        h = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+        h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd.get(p + "mlp.fc1.bias")))
+        h = F.linear(h, sd[p + "mlp.fc2.weight"], sd.get(p + "mlp.fc2.bias"))
+        if p + "ls2.gamma" in sd:
+            h = h * sd[p + "ls2.gamma"]
+        x = x + h
+    if "norm.weight" in sd:
+        x = F.layer_norm(x, (D,), sd["norm.weight"], sd["norm.bias"], eps)
+    pool = cfg.get("global_pool", "token")
+    if pool == "token":
+        x = x[:, 0]
+    elif pool == "avg":
+        x = x[:, cfg.get("num_prefix_tokens", 1):].mean(1)
+    if "fc_norm.weight" in sd:
+        x = F.layer_norm(x, (D,), sd["fc_norm.weight"], sd["fc_norm.bias"], eps)
+    if "head.weight" in sd:
+        x = F.linear(x, sd["head.weight"], sd.get("head.bias"))
+    return x

@@ -1,0 +1,241 @@
+"""Fused forward (inference) of timm's ViT hot path on the libb200timm kernels.
+
+The functions are duck-typed on timm's own attribute names (``blk.norm1``, ``blk.attn.qkv``, ``blk.mlp.fc1``,
+``model.patch_embed.proj`` ...) so the same code drives the mirror modules of b200timm.layers /
+b200timm.vision_transformer and -- through b200timm.plugin -- timm's unmodified classes.
+
+Fusion map per transformer block (reference: timm/models/vision_transformer.py:206-214):
+    LN1            -> layernorm kernel                              (norm.py:85-90)
+    qkv            -> GEMM + bias epilogue                          (attention.py:115)
+    sdpa           -> tcgen05 attention, reads qkv in place         (attention.py:115-135)
+    proj + ls1 + residual -> GEMM epilogue  x + gamma*(acc+b)       (attention.py:137, layer_scale.py:27, :212)
+    LN2            -> layernorm kernel
+    fc1 + GELU     -> GEMM epilogue                                 (mlp.py:48-49)
+    fc2 + ls2 + residual -> GEMM epilogue                           (mlp.py:52, :213)
+Anything the kernels do not cover (qk-norm, attention dropout, non-GELU activations, head_dim != 64, ...)
+raises B200Error: there is no PyTorch fallback on this path.
+"""
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import B200Error
+
+
+def _is_identity(m):
+    return m is None or isinstance(m, nn.Identity)
+
+
+def _ln_params(norm):
+    if _is_identity(norm):
+        return None
+    if not isinstance(norm, nn.LayerNorm):
+        raise B200Error(f"unsupported norm layer {type(norm).__name__} (LayerNorm only)")
+    return norm.weight, norm.bias, norm.eps
+
+
+def _gamma(ls):
+    if _is_identity(ls):
+        return None
+    g = getattr(ls, "gamma", None)
+    if g is None:
+        raise B200Error(f"unsupported layer-scale module {type(ls).__name__}")
+    return g
+
+
+def _check_drop(m, what):
+    if _is_identity(m):
+        return
+    p = getattr(m, "p", getattr(m, "drop_prob", 0.0))
+    if p and m.training:
+        raise B200Error(f"{what} with p={p} in training mode is not supported by the fused inference path")
+
+
+def check_attention(attn):
+    """Raise unless `attn` is a plain timm Attention the kernels cover (attention.py:43-139)."""
+    if not _is_identity(getattr(attn, "q_norm", None)) or not _is_identity(getattr(attn, "k_norm", None)):
+        raise B200Error("qk_norm attention is not supported")
+    if not _is_identity(getattr(attn, "norm", None)):
+        raise B200Error("scale_norm attention is not supported")
+    if attn.head_dim != 64:
+        raise B200Error(f"head_dim {attn.head_dim} is not supported (64 only)")
+    _check_drop(attn.attn_drop, "attn_drop")
+    _check_drop(attn.proj_drop, "proj_drop")
+
+
+def check_mlp(mlp):
+    if not isinstance(mlp.act, nn.GELU) or getattr(mlp.act, "approximate", "none") != "none":
+        raise B200Error(f"unsupported Mlp activation {mlp.act} (exact GELU only)")
+    if not _is_identity(getattr(mlp, "norm", None)):
+        raise B200Error("Mlp with an inner norm is not supported")
+    if not isinstance(mlp.fc1, nn.Linear):
+        raise B200Error("conv Mlp is not supported here")
+    _check_drop(getattr(mlp, "drop1", None), "mlp drop")
+    _check_drop(getattr(mlp, "drop2", None), "mlp drop")
+
+
+def _bf16_2d(x, cols):
+    if x.dtype != torch.bfloat16:
+        raise B200Error(f"activations must be bf16 on the fused path, got {x.dtype}")
+    x2 = x.reshape(-1, cols)
+    return x2 if x2.is_contiguous() else x2.contiguous()
+
+
+def _w(linear):
+    w = linear.weight
+    if w.dtype != torch.bfloat16:
+        raise B200Error("weights must be bf16 (use model.to(torch.bfloat16), as benchmark.py --precision bfloat16 does)")
+    return w if w.is_contiguous() else w.contiguous()
+
+
+def layernorm(norm, x):
+    """LayerNorm.forward (timm/layers/norm.py:85-90)."""
+    w, b, eps = _ln_params(norm)
+    return ops.layernorm_fwd(x, w, b, eps)[0]
+
+
+def attention_forward(attn, x, kv_len=None):
+    """Attention.forward (timm/layers/attention.py:108-139) without the output projection's residual."""
+    check_attention(attn)
+    B, N, C = x.shape
+    x2 = _bf16_2d(x, C)
+    qkv = ops.linear_fwd(x2, _w(attn.qkv), attn.qkv.bias)
+    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
+    y = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias)
+    return y.view(B, N, -1)
+
+
+def mlp_forward(mlp, x):
+    """Mlp.forward (timm/layers/mlp.py:47-54): fc2(GELU(fc1(x))), GELU fused into fc1's epilogue."""
+    check_mlp(mlp)
+    shape = x.shape
+    x2 = _bf16_2d(x, shape[-1])
+    h = ops.linear_fwd(x2, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    y = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias)
+    return y.view(*shape[:-1], -1)
+
+
+def block_forward(blk, x, kv_len=None):
+    """Block.forward (timm/models/vision_transformer.py:206-214), eval mode."""
+    attn, mlp = blk.attn, blk.mlp
+    check_attention(attn)
+    check_mlp(mlp)
+    _check_drop(blk.drop_path1, "drop_path")
+    _check_drop(blk.drop_path2, "drop_path")
+    B, N, D = x.shape
+    x2 = _bf16_2d(x, D)
+    w1, b1, eps1 = _ln_params(blk.norm1)
+    h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
+    qkv = ops.linear_fwd(h, _w(attn.qkv), attn.qkv.bias)
+    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
+    x2 = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
+                        gamma=_gamma(blk.ls1))
+    w2, b2, eps2 = _ln_params(blk.norm2)
+    h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
+    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    x2 = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=_gamma(blk.ls2))
+    return x2.view(B, N, D)
+
+
+def patch_embed_forward(pe, img):
+    """PatchEmbed.forward (timm/layers/patch_embed.py:117-142), flatten=True output [B, G, D]."""
+    if not _is_identity(pe.norm):
+        raise B200Error("PatchEmbed with a norm layer is not supported")
+    if getattr(pe, "dynamic_img_pad", False):
+        raise B200Error("dynamic_img_pad is not supported")
+    ph, pw = pe.patch_size
+    if ph != pw:
+        raise B200Error("non-square patches are not supported")
+    B, C, H, W = img.shape
+    if pe.img_size is not None and getattr(pe, "strict_img_size", True) and (H, W) != tuple(pe.img_size):
+        raise AssertionError(f"Input size ({H}x{W}) doesn't match model ({pe.img_size[0]}x{pe.img_size[1]}).")
+    if H % ph or W % pw:
+        raise AssertionError(f"Input size ({H}x{W}) should be divisible by patch size ({ph}).")
+    w = _w(pe.proj)
+    D = w.shape[0]
+    K = C * ph * pw
+    kpad = (K + 7) // 8 * 8
+    w2 = w.view(D, K)
+    if kpad != K:  # 16-byte row stride for TMA (e.g. patch 14: K = 588 -> 592), zero padded
+        cache = getattr(pe, "_b200_wpad", None)
+        if cache is None or cache[0] != (w.data_ptr(), w._version):
+            wp = torch.zeros(D, kpad, dtype=w.dtype, device=w.device)
+            wp[:, :K] = w2
+            pe._b200_wpad = ((w.data_ptr(), w._version), wp)
+            cache = pe._b200_wpad
+        w2 = cache[1]
+    patches = ops.patchify(img.contiguous(), ph, kpad)
+    y = ops.gemm(patches, w2, patches.shape[0], D, kpad, bias=pe.proj.bias)
+    return y.view(B, (H // ph) * (W // pw), D)
+
+
+def vit_embed(model, img):
+    """patch_embed + _pos_embed (+ norm_pre) of VisionTransformer.forward_features (:1238-1241)."""
+    if getattr(model, "dynamic_img_size", False):
+        raise B200Error("dynamic_img_size models are not supported by the fused path")
+    if not _is_identity(getattr(model, "patch_drop", None)):
+        raise B200Error("patch dropout is not supported")
+    _check_drop(getattr(model, "pos_drop", None), "pos_drop")
+    proj = patch_embed_forward(model.patch_embed, img)
+    B, G, D = proj.shape
+    pre = [t for t in (getattr(model, "cls_token", None), getattr(model, "reg_token", None)) if t is not None]
+    n_prefix = sum(t.shape[1] for t in pre)
+    prefix = None
+    if pre:
+        prefix = (pre[0] if len(pre) == 1 else torch.cat(pre, 1)).reshape(n_prefix, D).contiguous()
+    pos = model.pos_embed
+    if pos is None and n_prefix == 0:
+        x = proj
+    else:
+        x = ops.assemble_tokens(proj.view(B * G, D), prefix, None if pos is None else pos.contiguous(), B, G, n_prefix, D,
+                                pos_has_prefix=not getattr(model, "no_embed_class", False))
+    if not _is_identity(getattr(model, "norm_pre", None)):
+        x = layernorm(model.norm_pre, x)
+    return x
+
+
+def vit_forward_features(model, img, kv_len=None, final_norm=True):
+    """VisionTransformer.forward_features (timm/models/vision_transformer.py:1231-1253)."""
+    x = vit_embed(model, img)
+    for blk in model.blocks:
+        x = block_forward(blk, x, kv_len)
+    if final_norm and not _is_identity(model.norm):
+        x = layernorm(model.norm, x)
+    return x
+
+
+def vit_pool(model, x):
+    """VisionTransformer.pool / global_pool_nlc (:686-708, :1254-1277) for token / avg pooling."""
+    if getattr(model, "attn_pool", None) is not None:
+        raise B200Error("attention pooling heads are not supported")
+    pool = model.global_pool
+    if pool == "token":
+        return x[:, 0]
+    if pool == "avg":
+        xs = x if getattr(model, "pool_include_prefix", False) else x[:, model.num_prefix_tokens:]
+        return xs.float().mean(1).to(x.dtype)
+    if not pool:
+        return x
+    raise B200Error(f"global_pool={pool!r} is not supported")
+
+
+def vit_forward_head(model, x, pre_logits=False):
+    """VisionTransformer.forward_head (:1279-1292)."""
+    x = vit_pool(model, x)
+    if not _is_identity(model.fc_norm):
+        x = layernorm(model.fc_norm, x.contiguous())
+    _check_drop(model.head_drop, "head_drop")
+    if pre_logits or _is_identity(model.head):
+        return x
+    x2 = _bf16_2d(x, x.shape[-1])
+    return ops.linear_fwd(x2, _w(model.head), model.head.bias).view(*x.shape[:-1], -1)
+
+
+def vit_forward(model, img, kv_len=None):
+    """VisionTransformer.forward (:1294-1302).  With token pooling the final LayerNorm is applied to the
+    class-token rows only (LN is per token, so LN(x)[:, 0] == LN(x[:, 0]))."""
+    token_pool = model.global_pool == "token" and getattr(model, "attn_pool", None) is None
+    x = vit_forward_features(model, img, kv_len, final_norm=not token_pool)
+    if token_pool and not _is_identity(model.norm):
+        x = layernorm(model.norm, x[:, :1].contiguous())
+    return vit_forward_head(model, x)

@@ -1,0 +1,175 @@
+"""Drop-in mirrors of timm's hot-path layer modules: same constructor arguments, same parameter / sub-module
+names (hence identical ``state_dict()`` keys), forwards running on the libb200timm kernels.
+
+Reference classes (timm 1.0.28.dev0): timm/layers/attention.py:43 (Attention), mlp.py:14 (Mlp),
+norm.py:70 (LayerNorm), layer_scale.py:5 (LayerScale), drop.py:178 (DropPath), patch_embed.py:26 (PatchEmbed).
+The Linear / Conv2d / LayerNorm children stay real torch parameter holders (timm's weight init, checkpoint
+loaders and optimizers reach into them by name) -- only ``forward`` differs.
+"""
+from typing import Optional, Type
+
+import torch
+from torch import nn
+
+from . import functional as BF
+from ._lib import B200Error
+
+
+def _pair(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+class LayerNorm(nn.LayerNorm):
+    """timm.layers.LayerNorm: nn.LayerNorm with eps=1e-6 default (norm.py:70-90)."""
+
+    def __init__(self, num_channels: int, eps: float = 1e-6, affine: bool = True, device=None, dtype=None):
+        super().__init__(num_channels, eps=eps, elementwise_affine=affine, device=device, dtype=dtype)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return BF.layernorm(self, x)
+
+
+class LayerScale(nn.Module):
+    """timm.layers.LayerScale (layer_scale.py:5-27): x * gamma.  Inside a Block it is fused into the
+    preceding GEMM's epilogue; standalone it is a (rare) elementwise op and is not provided as a kernel."""
+
+    def __init__(self, dim: int, init_values: float = 1e-5, inplace: bool = False, device=None, dtype=None):
+        super().__init__()
+        self.inplace = inplace
+        self.gamma = nn.Parameter(init_values * torch.ones(dim, device=device, dtype=dtype))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        raise B200Error("LayerScale is fused into the proj / fc2 GEMM epilogue by Block.forward; "
+                        "calling it standalone is not on the B200 hot path")
+
+
+class DropPath(nn.Module):
+    """timm.layers.DropPath (drop.py:178-190): per-sample stochastic depth.  Identity in eval mode; in
+    training the per-sample keep mask is fused into the residual GEMM epilogue by Block.forward."""
+
+    def __init__(self, drop_prob: float = 0., scale_by_keep: bool = True):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.scale_by_keep = scale_by_keep
+
+    def forward(self, x):
+        if self.drop_prob == 0. or not self.training:
+            return x
+        raise B200Error("DropPath in training mode is fused into Block.forward; standalone use is not supported")
+
+    def extra_repr(self):
+        return f"drop_prob={round(self.drop_prob, 3):0.3f}"
+
+
+class Mlp(nn.Module):
+    """timm.layers.Mlp (mlp.py:14-54)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, norm_layer=None,
+                 bias=True, drop=0., use_conv=False, device=None, dtype=None):
+        super().__init__()
+        if use_conv:
+            raise B200Error("Mlp(use_conv=True) is not supported")
+        dd = {"device": device, "dtype": dtype}
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        bias = _pair(bias)
+        drop_probs = _pair(drop)
+        self.fc1 = nn.Linear(in_features, hidden_features, bias=bias[0], **dd)
+        self.act = act_layer()
+        self.drop1 = nn.Dropout(drop_probs[0])
+        self.norm = norm_layer(hidden_features, **dd) if norm_layer is not None else nn.Identity()
+        self.fc2 = nn.Linear(hidden_features, out_features, bias=bias[1], **dd)
+        self.drop2 = nn.Dropout(drop_probs[1])
+
+    def forward(self, x):
+        return BF.mlp_forward(self, x)
+
+
+class Attention(nn.Module):
+    """timm.layers.Attention (attention.py:43-139)."""
+
+    def __init__(self, dim: int, num_heads: int = 8, attn_head_dim: Optional[int] = None,
+                 dim_out: Optional[int] = None, qkv_bias: bool = False, qk_norm: bool = False,
+                 scale_norm: bool = False, proj_bias: bool = True, attn_drop: float = 0., proj_drop: float = 0.,
+                 norm_layer: Optional[Type[nn.Module]] = None, device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        dim_out = dim_out or dim
+        head_dim = attn_head_dim
+        if head_dim is None:
+            assert dim % num_heads == 0, "dim should be divisible by num_heads"
+            head_dim = dim // num_heads
+        if qk_norm or scale_norm:
+            assert norm_layer is not None, "norm_layer must be provided if qk_norm or scale_norm is True"
+        self.num_heads = num_heads
+        self.head_dim = head_dim
+        self.attn_dim = num_heads * head_dim
+        self.scale = head_dim ** -0.5
+        self.fused_attn = True
+        self.qkv = nn.Linear(dim, self.attn_dim * 3, bias=qkv_bias, **dd)
+        self.q_norm = norm_layer(head_dim, **dd) if qk_norm else nn.Identity()
+        self.k_norm = norm_layer(head_dim, **dd) if qk_norm else nn.Identity()
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.norm = norm_layer(self.attn_dim, **dd) if scale_norm else nn.Identity()
+        self.proj = nn.Linear(self.attn_dim, dim_out, bias=proj_bias, **dd)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, is_causal: bool = False,
+                kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if is_causal:
+            raise B200Error("causal attention is not supported")
+        if attn_mask is not None:
+            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1]) if kv_len is None else kv_len
+        return BF.attention_forward(self, x, kv_len)
+
+
+def BF_mask_to_kv_len(attn_mask: torch.Tensor, n_tokens: int) -> torch.Tensor:
+    """Convert a NaFlex key-padding mask (bool keep-mask or additive float, broadcastable to [B,1,N,N],
+    naflexvit.py:964-1029) into per-sample valid-key counts.  The collator always emits prefix-valid masks
+    (naflex_dataset.py:136-142); anything else is rejected."""
+    m = attn_mask
+    if m.dtype != torch.bool:
+        m = m > -1.0  # additive masks hold 0 (keep) or finfo.min (drop)
+    while m.dim() < 4:
+        m = m.unsqueeze(0)
+    keys = m[:, 0].any(dim=-2) if m.shape[-2] != 1 else m[:, 0, 0]   # [B, N]: key kept by at least one query
+    kv_len = keys.sum(-1).to(torch.int32)
+    expect = torch.arange(n_tokens, device=m.device)[None, :] < kv_len[:, None]
+    if not bool((keys == expect).all()):
+        raise B200Error("only prefix-valid key-padding masks are supported (NaFlex layout)")
+    return kv_len.contiguous()
+
+
+class PatchEmbed(nn.Module):
+    """timm.layers.PatchEmbed (patch_embed.py:26-142), flatten=True / NLC output."""
+
+    def __init__(self, img_size=224, patch_size: int = 16, in_chans: int = 3, embed_dim: int = 768,
+                 norm_layer=None, flatten: bool = True, output_fmt: Optional[str] = None, bias: bool = True,
+                 strict_img_size: bool = True, dynamic_img_pad: bool = False, device=None, dtype=None):
+        super().__init__()
+        if output_fmt is not None or not flatten:
+            raise B200Error("PatchEmbed output formats other than flattened NLC are not supported")
+        dd = {"device": device, "dtype": dtype}
+        self.patch_size = _pair(patch_size)
+        self.img_size, self.grid_size, self.num_patches = self._init_img_size(img_size)
+        self.flatten = flatten
+        self.strict_img_size = strict_img_size
+        self.dynamic_img_pad = dynamic_img_pad
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=bias, **dd)
+        self.norm = norm_layer(embed_dim, **dd) if norm_layer else nn.Identity()
+
+    def _init_img_size(self, img_size):
+        if img_size is None:
+            return None, None, None
+        img_size = _pair(img_size)
+        grid_size = tuple(s // p for s, p in zip(img_size, self.patch_size))
+        return img_size, grid_size, grid_size[0] * grid_size[1]
+
+    def feat_ratio(self, as_scalar=True):
+        return max(self.patch_size) if as_scalar else self.patch_size
+
+    def dynamic_feat_size(self, img_size):
+        return img_size[0] // self.patch_size[0], img_size[1] // self.patch_size[1]
+
+    def forward(self, x):
+        return BF.patch_embed_forward(self, x)

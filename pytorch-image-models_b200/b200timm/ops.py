@@ -22,6 +22,41 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ------------------------------------------------------------------------------------ launch accounting
+_launches = 0          # kernels of libb200timm launched since reset_counters()
+_gemm_timing = None    # None, or a list of (start_event, end_event, flops) while bench.py times the GEMMs
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def reset_counters():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+def enable_gemm_timing(flag):
+    """bench.py: bracket every b200_gemm launch with CUDA events on the launching stream (roofline.achieved)."""
+    global _gemm_timing
+    _gemm_timing = [] if flag else None
+
+
+def gemm_timing_summary():
+    """(total algorithmic FLOPs, total milliseconds, number of launches) of the GEMMs timed so far."""
+    if not _gemm_timing:
+        return 0.0, 0.0, 0
+    torch.cuda.synchronize()
+    flops = sum(f for _, _, f in _gemm_timing)
+    ms = sum(s.elapsed_time(e) for s, e, _ in _gemm_timing)
+    return flops, ms, len(_gemm_timing)
+
+
 def _dt(t):
     if t.dtype == torch.bfloat16:
         return DTYPE_BF16
@@ -65,6 +100,7 @@ def layernorm_fwd(x, weight, bias, eps, out_dtype=None, save_stats=False):
     rc = lib.b200_layernorm_fwd(x2.data_ptr(), _ptr(weight), _ptr(bias), y.data_ptr(), _ptr(mean), _ptr(rstd), rows,
                                 cols, float(eps), _dt(x2), _dt(y), _param_dtype(weight, bias), _stream())
     _lib.check(rc, "b200_layernorm_fwd")
+    _count()
     return y.view(*x.shape[:-1], cols), mean, rstd
 
 
@@ -91,6 +127,7 @@ def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True):
                                 dx.data_ptr(), _ptr(dw), _ptr(db), ws.data_ptr(), rows, cols, _dt(x2), _dt(dy2),
                                 _param_dtype(weight), _stream())
     _lib.check(rc, "b200_layernorm_bwd")
+    _count(2 if need_param_grads else 1)
     return dx.view(x.shape), dw, db
 
 
@@ -136,8 +173,15 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
     d.gamma_dtype = _dt(gamma) if gamma is not None else DTYPE_BF16
     d.accumulate = int(accumulate)
     d.split_k = int(split_k)
+    if _gemm_timing is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = _lib.load().b200_gemm(ctypes.byref(d), _stream())
     _lib.check(rc, "b200_gemm")
+    if _gemm_timing is not None:
+        ev1.record()
+        _gemm_timing.append((ev0, ev1, 2.0 * M * N * K))
+    _count()
     return out
 
 
@@ -161,6 +205,7 @@ def attention_fwd(qkv, B, N, H, hd, scale, kv_len=None, need_lse=False):
     rc = _lib.load().b200_attn_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(lse), _ptr(kv_len), B, N, H, hd, float(scale),
                                    _stream())
     _lib.check(rc, "b200_attn_fwd")
+    _count()
     return out, lse
 
 
@@ -177,21 +222,24 @@ def patchify(img, p, kpad=None):
     out = torch.empty(B * gh * gw, kpad, dtype=torch.bfloat16, device=img.device)
     rc = _lib.load().b200_patchify(img.data_ptr(), out.data_ptr(), B, C, H, W, p, kpad, _dt(img), _stream())
     _lib.check(rc, "b200_patchify")
+    _count()
     return out
 
 
-def assemble_tokens(proj, prefix, pos, B, G, n_prefix, D):
-    """tokens[b] = cat(prefix, proj[b]) + pos  ->  bf16 [B, n_prefix+G, D]."""
+def assemble_tokens(proj, prefix, pos, B, G, n_prefix, D, pos_has_prefix=True):
+    """tokens[b] = cat(prefix, proj[b]) + pos (pos_has_prefix) or cat(prefix, proj[b] + pos)  ->  bf16 [B, n_prefix+G, D]."""
     _need_cuda(proj, prefix, pos)
     if proj.dtype != torch.bfloat16 or not proj.is_contiguous() or proj.numel() != B * G * D:
         raise B200Error("assemble_tokens: proj must be contiguous bf16 [B*G, D]")
-    for t, n, name in ((prefix, n_prefix * D, "prefix"), (pos, (n_prefix + G) * D, "pos")):
+    npos = (n_prefix + G) if pos_has_prefix else G
+    for t, n, name in ((prefix, n_prefix * D, "prefix"), (pos, npos * D, "pos")):
         if t is not None and (not t.is_contiguous() or t.numel() != n):
             raise B200Error(f"assemble_tokens: {name} has {t.numel()} elements, expected {n}")
     tokens = torch.empty(B, n_prefix + G, D, dtype=torch.bfloat16, device=proj.device)
     rc = _lib.load().b200_assemble_tokens(proj.data_ptr(), _ptr(prefix), _ptr(pos), tokens.data_ptr(), B, G, n_prefix, D,
-                                          _param_dtype(prefix, pos), _stream())
+                                          _param_dtype(prefix, pos), int(pos_has_prefix), _stream())
     _lib.check(rc, "b200_assemble_tokens")
+    _count()
     return tokens
 
 
@@ -206,4 +254,5 @@ def colsum(x2d, out=None, accumulate=False):
         accumulate = False
     rc = _lib.load().b200_colsum(x2d.data_ptr(), out.data_ptr(), rows, cols, int(accumulate), _stream())
     _lib.check(rc, "b200_colsum")
+    _count()
     return out

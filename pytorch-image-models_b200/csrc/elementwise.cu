@@ -73,11 +73,12 @@ __device__ __forceinline__ void ld8(const void* base, bool f32, long long idx, f
   }
 }
 
-// tokens[b][j][:] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix]) + pos[j]
-// timm/models/vision_transformer.py:1038-1075 (_pos_embed: cat cls/reg tokens, add pos_embed).
+// tokens[b][j][:] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix]) + pos[j]          (pos_has_prefix)
+// tokens[b][j][:] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix] + pos[j - n_prefix]) (otherwise:
+// no_embed_class).  timm/models/vision_transformer.py:1038-1075 (_pos_embed: cat cls/reg tokens, add pos_embed).
 __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ proj, const void* __restrict__ prefix,
                                        const void* __restrict__ pos, __nv_bfloat16* __restrict__ tokens, int B, int G,
-                                       int n_prefix, int D, int param_f32) {
+                                       int n_prefix, int D, int param_f32, int pos_has_prefix) {
   const int dvecs = D >> 3;
   const int ntok = G + n_prefix;
   const long long total = static_cast<long long>(B) * ntok * dvecs;
@@ -90,8 +91,9 @@ __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ proj, c
     float v[8], pv[8];
     if (j < n_prefix) ld8(prefix, param_f32, static_cast<long long>(j) * D + dv * 8, v);
     else ld8(proj, false, (static_cast<long long>(b) * G + (j - n_prefix)) * D + dv * 8, v);
-    if (pos != nullptr) {
-      ld8(pos, param_f32, static_cast<long long>(j) * D + dv * 8, pv);
+    const int pj = pos_has_prefix ? j : j - n_prefix;
+    if (pos != nullptr && pj >= 0) {
+      ld8(pos, param_f32, static_cast<long long>(pj) * D + dv * 8, pv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] += pv[i];
     }
@@ -156,7 +158,8 @@ extern "C" int b200_patchify(const void* img, void* patches, int32_t B, int32_t 
 }
 
 extern "C" int b200_assemble_tokens(const void* proj, const void* prefix, const void* pos, void* tokens, int32_t B,
-                                    int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype, void* stream_) {
+                                    int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype,
+                                    int32_t pos_has_prefix, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(proj && tokens, "b200_assemble_tokens: null pointer");
   B200_CHECK_ARG(n_prefix == 0 || prefix != nullptr, "b200_assemble_tokens: n_prefix > 0 needs prefix tokens");
@@ -168,7 +171,7 @@ extern "C" int b200_assemble_tokens(const void* proj, const void* prefix, const 
   if (blocks > cap) blocks = cap;
   assemble_tokens_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(proj), prefix, pos, reinterpret_cast<__nv_bfloat16*>(tokens), B, G,
-      n_prefix, D, param_dtype == B200_DTYPE_F32);
+      n_prefix, D, param_dtype == B200_DTYPE_F32, pos_has_prefix);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

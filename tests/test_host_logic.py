@@ -1,0 +1,82 @@
+"""Host-side logic that needs no GPU: module / state_dict compatibility with the reference, the model-name
+resolver, mask -> key-length conversion, and the no-CPU-fallback rule."""
+import glob
+import os
+
+import pytest
+import torch
+
+from b200timm import B200Error
+from b200timm.layers import Attention, BF_mask_to_kv_len, DropPath, LayerNorm, LayerScale, Mlp, PatchEmbed
+from b200timm.vision_transformer import MODEL_ARGS, VisionTransformer, calculate_drop_path_rates, create_model
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "vit_*.pt"))))
+def test_state_dict_keys_and_shapes_match_timm(path):
+    fx = torch.load(path)
+    model = VisionTransformer(**fx["kwargs"])
+    ours = model.state_dict()
+    ref = fx["state_dict"]
+    assert list(ours.keys()) == list(ref.keys())  # same names, same registration order as timm
+    for k in ref:
+        assert ours[k].shape == ref[k].shape, k
+    model.load_state_dict(ref, strict=True)
+    if "grads" in fx:  # every parameter timm trains is a parameter here too
+        assert sorted(fx["grads"]) == sorted(n for n, _ in model.named_parameters())
+
+
+def test_vit_base_parameter_count_matches_reference_csv():
+    # results/benchmark-*.csv: vit_base_patch16_224 param_count 86.57 M; vit_tiny 5.72 M
+    n = sum(p.numel() for p in create_model("vit_base_patch16_224").parameters())
+    assert abs(n / 1e6 - 86.57) < 0.01
+    n = sum(p.numel() for p in create_model("vit_tiny_patch16_224").parameters())
+    assert abs(n / 1e6 - 5.72) < 0.01
+    with pytest.raises(B200Error):
+        create_model("resnet50")
+    assert "vit_large_patch14_clip_336" in MODEL_ARGS
+
+
+def test_block_children_names_match_reference():
+    blk = create_model("vit_tiny_patch16_224", init_values=1e-5, drop_path_rate=0.1).blocks[-1]
+    assert [n for n, _ in blk.named_children()] == ["norm1", "attn", "ls1", "drop_path1", "norm2", "mlp", "ls2", "drop_path2"]
+    assert [n for n, _ in blk.attn.named_children()] == ["qkv", "q_norm", "k_norm", "attn_drop", "norm", "proj", "proj_drop"]
+    assert [n for n, _ in blk.mlp.named_children()] == ["fc1", "act", "drop1", "norm", "fc2", "drop2"]
+    assert isinstance(blk.ls1, LayerScale) and isinstance(blk.drop_path1, DropPath)
+    assert abs(blk.drop_path1.drop_prob - 0.1) < 1e-6
+    assert calculate_drop_path_rates(0.1, 3) == pytest.approx([0.0, 0.05, 0.1])
+
+
+def test_default_init_statistics():
+    m = create_model("vit_tiny_patch16_224")
+    w = m.blocks[0].attn.qkv.weight
+    assert abs(w.std().item() - 0.02) < 1e-3   # trunc_normal_(std=.02, a=-2, b=2)
+    assert m.blocks[0].attn.qkv.bias.abs().max().item() == 0
+    assert isinstance(m.norm, LayerNorm) and m.norm.eps == 1e-6
+    assert create_model("vit_large_patch14_clip_336", depth=1).norm.eps == 1e-5
+
+
+def test_mask_to_kv_len():
+    B, N = 3, 10
+    lens = torch.tensor([10, 4, 7])
+    valid = torch.arange(N)[None, :] < lens[:, None]
+    keep = valid[:, None, :, None] & valid[:, None, None, :]
+    add = torch.zeros(B, 1, N, N).masked_fill(~keep, torch.finfo(torch.float32).min)
+    assert BF_mask_to_kv_len(keep, N).tolist() == lens.tolist()
+    assert BF_mask_to_kv_len(add, N).tolist() == lens.tolist()
+    holes = keep.clone()
+    holes[1, 0, :, 1] = False  # a non-prefix mask must be rejected, not silently mis-handled
+    with pytest.raises(B200Error):
+        BF_mask_to_kv_len(holes, N)
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(2, 5, 128, dtype=torch.bfloat16)
+    for mod in (LayerNorm(128), Mlp(128, 512), Attention(128, num_heads=2)):
+        with pytest.raises(B200Error):
+            mod.to(torch.bfloat16)(x)
+    with pytest.raises(B200Error):
+        PatchEmbed(32, 16, 3, 64).to(torch.bfloat16)(torch.zeros(1, 3, 32, 32, dtype=torch.bfloat16))
+    with pytest.raises(B200Error):
+        Attention(96, num_heads=2).to(torch.bfloat16)(torch.zeros(1, 4, 96, dtype=torch.bfloat16))  # head_dim 48

@@ -1,0 +1,87 @@
+"""Pins the oracle restatement (oracle/vit_oracle.py) against golden vectors produced by the unmodified
+reference (timm) -- see oracle/make_golden.py.  CPU only; fp32; tolerance 1e-5 absolute (the reference's own
+fused-vs-unfused attention check uses atol=1e-5, tests/test_layers.py:141-160)."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VIT_FILES = sorted(glob.glob(os.path.join(GOLDEN, "vit_*.pt")))
+
+
+def _cfg(kwargs):
+    cfg = dict(kwargs)
+    cfg["num_prefix_tokens"] = (1 if kwargs.get("class_token", True) else 0) + kwargs.get("reg_tokens", 0)
+    return cfg
+
+
+def test_golden_files_present():
+    assert len(VIT_FILES) >= 3 and os.path.exists(os.path.join(GOLDEN, "layers.pt"))
+
+
+@pytest.mark.parametrize("path", VIT_FILES, ids=[os.path.basename(p)[:-3] for p in VIT_FILES])
+def test_vit_forward_matches_reference(path):
+    fx = torch.load(path)
+    cfg = _cfg(fx["kwargs"])
+    feats, blocks = O.vit_forward_features(fx["img"], fx["state_dict"], cfg, return_blocks=True)
+    for i, (got, ref) in enumerate(zip(blocks, fx["block_outputs"])):
+        torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5, msg=lambda m: f"block {i}: {m}")
+    torch.testing.assert_close(feats, fx["features"], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(O.vit_forward_head(feats, fx["state_dict"], cfg), fx["logits"], atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("path", VIT_FILES, ids=[os.path.basename(p)[:-3] for p in VIT_FILES])
+def test_eager_timing_port_matches_reference(path):
+    """The CPU-baseline port (vit_forward_eager, timed by bench.py) computes the same function."""
+    fx = torch.load(path)
+    cfg = _cfg(fx["kwargs"])
+    with torch.no_grad():
+        torch.testing.assert_close(O.vit_forward_eager(fx["img"], fx["state_dict"], cfg), fx["logits"], atol=1e-5, rtol=1e-5)
+        kv = torch.full((fx["img"].shape[0],), 3, dtype=torch.int64)
+        got = O.vit_forward_eager(fx["img"], fx["state_dict"], cfg, kv_len=kv)
+        ref = O.vit_forward(fx["img"], fx["state_dict"], cfg, kv_len=kv)
+    if cfg.get("global_pool", "token") == "token":   # masked queries (avg pool over padding) are unspecified
+        torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_vit_backward_matches_reference():
+    """Gradients of every parameter after outputs.mean().backward() (tests/test_models.py:209-242 pattern)."""
+    fx = torch.load(os.path.join(GOLDEN, "vit_g1_default.pt"))
+    cfg = _cfg(fx["kwargs"])
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    O.vit_forward(fx["img"], sd, cfg).mean().backward()
+    assert set(fx["grads"]) == set(sd)
+    for k, ref in fx["grads"].items():
+        torch.testing.assert_close(sd[k].grad, ref, atol=1e-6, rtol=1e-4, msg=lambda m: f"{k}: {m}")
+
+
+def test_layer_goldens():
+    fx = torch.load(os.path.join(GOLDEN, "layers.pt"))
+    a = fx["attention"]
+    sd = a["state_dict"]
+    args = (sd["qkv.weight"], sd["qkv.bias"], sd["proj.weight"], sd["proj.bias"], a["num_heads"])
+    torch.testing.assert_close(O.attention(a["x"], *args), a["y"], atol=1e-5, rtol=1e-5)
+    # masked: rows whose query is itself padding are unspecified in the reference (all -inf -> uniform);
+    # compare the valid queries only, as NaFlex pooling does (naflexvit.py:1033-1102).
+    ym = O.attention(a["x"], *args, kv_len=a["kv_len"])
+    for b, n in enumerate(a["kv_len"].tolist()):
+        torch.testing.assert_close(ym[b, :n], a["y_masked"][b, :n], atol=1e-5, rtol=1e-5)
+    m = fx["mlp"]
+    sd = m["state_dict"]
+    torch.testing.assert_close(O.mlp(m["x"], sd["fc1.weight"], sd["fc1.bias"], sd["fc2.weight"], sd["fc2.bias"]),
+                               m["y"], atol=1e-5, rtol=1e-5)
+    ln = fx["layernorm"]
+    torch.testing.assert_close(O.layer_norm(ln["x"], ln["state_dict"]["weight"], ln["state_dict"]["bias"], ln["eps"]),
+                               ln["y"], atol=1e-5, rtol=1e-5)
+    for p in (16, 14, 4):
+        pe = fx[f"patch_embed_p{p}"]
+        torch.testing.assert_close(O.patch_embed(pe["img"], pe["state_dict"]["proj.weight"],
+                                                 pe["state_dict"]["proj.bias"], p), pe["y"], atol=1e-5, rtol=1e-5)
+    ls = fx["layerscale"]
+    torch.testing.assert_close(ls["x"] * ls["state_dict"]["gamma"], ls["y"])
+    dp = fx["droppath"]
+    torch.testing.assert_close(O.drop_path(dp["x"], dp["keep_mask"], 1.0 - dp["drop_prob"]), dp["y"])
