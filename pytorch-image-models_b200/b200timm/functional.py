@@ -88,6 +88,27 @@ def _w(linear):
     return w if w.is_contiguous() else w.contiguous()
 
 
+def _padded_out_linear(linear, x2):
+    """F.linear whose out_features is not a multiple of 8 (classifier heads with e.g. 10 classes): the GEMM
+    runs on a zero-padded copy of weight / bias (cached on the module, refreshed when the parameters change)
+    and the padding columns are sliced off."""
+    w, b = linear.weight, linear.bias
+    N, K = w.shape
+    npad = (N + 7) // 8 * 8
+    key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
+    cache = getattr(linear, "_b200_npad", None)
+    if cache is None or cache[0] != key:
+        wp = torch.zeros(npad, K, dtype=w.dtype, device=w.device)
+        wp[:N] = w.detach()
+        bp = None
+        if b is not None:
+            bp = torch.zeros(npad, dtype=b.dtype, device=b.device)
+            bp[:N] = b.detach()
+        cache = (key, wp, bp)
+        linear._b200_npad = cache
+    return ops.linear_fwd(x2, cache[1], cache[2])[:, :N]
+
+
 def layernorm(norm, x):
     """LayerNorm.forward (timm/layers/norm.py:85-90)."""
     w, b, eps = _ln_params(norm)
@@ -228,6 +249,9 @@ def vit_forward_head(model, x, pre_logits=False):
     if pre_logits or _is_identity(model.head):
         return x
     x2 = _bf16_2d(x, x.shape[-1])
+    if model.head.weight.shape[0] % 8:
+        _w(model.head)
+        return _padded_out_linear(model.head, x2).reshape(*x.shape[:-1], -1)
     return ops.linear_fwd(x2, _w(model.head), model.head.bias).view(*x.shape[:-1], -1)
 
 

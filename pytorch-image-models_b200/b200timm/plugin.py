@@ -1,0 +1,134 @@
+"""Drop-in plugin for an installed timm: rebinds the ``forward`` of timm's own hot-path classes to the
+libb200timm kernels, leaving constructors, parameters, ``state_dict()`` keys, the model registry,
+``create_model()``, ``benchmark.py`` / ``train.py`` / ``validate.py`` untouched (seam 3).
+
+    import b200timm.plugin; b200timm.plugin.install()         # or: python -m b200timm.run benchmark.py ...
+    train.py --device-modules b200timm.plugin ...              # timm's own import hook (train.py:186,464-466)
+    TORCH_BACKEND=b200timm.plugin pytest tests/test_models.py  # timm's test-suite hook (tests/test_models.py:36-39)
+
+Dispatch rule per call: CUDA tensor + bf16 activations and weights + a module configuration the kernels cover
+-> B200 kernels; everything else (CPU tensors such as BASELINE configs[0], fp32, scripting / export, other
+model families) keeps timm's original forward, which *is* the reference path for those cases.  If
+libb200timm.so cannot be loaded, install() raises -- it never silently leaves the PyTorch path in place.
+Set B200TIMM_STRICT=1 to raise instead of deferring to timm whenever a CUDA bf16 call is not covered.
+"""
+import os
+
+import torch
+
+from . import _lib
+from . import functional as BF
+from ._lib import B200Error
+
+_ORIG = {}
+_STRICT = os.environ.get("B200TIMM_STRICT", "0") == "1"
+
+
+def _fast(x):
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.bfloat16 and not torch.jit.is_scripting()
+            and not torch.jit.is_tracing() and not (torch.is_grad_enabled() and _GRAD_UNSUPPORTED))
+
+
+_GRAD_UNSUPPORTED = True   # flipped by b200timm.autograd once the training path is registered
+
+
+def _dispatch(name, fast_fn):
+    orig = _ORIG[name]
+
+    def forward(self, x, *args, **kwargs):
+        if _fast(x):
+            try:
+                return fast_fn(self, x, *args, **kwargs)
+            except B200Error:
+                if _STRICT:
+                    raise
+        return orig(self, x, *args, **kwargs)
+
+    forward.__name__ = "forward"
+    forward.__doc__ = f"b200timm dispatcher over {name}"
+    forward._b200_original = orig
+    return forward
+
+
+def _kv_len(attn_mask, n):
+    if attn_mask is None:
+        return None
+    from .layers import BF_mask_to_kv_len
+    return BF_mask_to_kv_len(attn_mask, n)
+
+
+def _block(self, x, attn_mask=None, is_causal=False):
+    if is_causal:
+        raise B200Error("causal attention is not covered")
+    return BF.block_forward(self, x, _kv_len(attn_mask, x.shape[1]))
+
+
+def _attention(self, x, attn_mask=None, is_causal=False):
+    if is_causal:
+        raise B200Error("causal attention is not covered")
+    return BF.attention_forward(self, x, _kv_len(attn_mask, x.shape[1]))
+
+
+def _vit_features(self, x, attn_mask=None, is_causal=False):
+    if is_causal or self.grad_checkpointing:
+        raise B200Error("causal / checkpointed forward_features is not covered")
+    n = self.patch_embed.num_patches + self.num_prefix_tokens
+    return BF.vit_forward_features(self, x, _kv_len(attn_mask, n))
+
+
+def _vit_forward(self, x, attn_mask=None, is_causal=False):
+    if is_causal or self.grad_checkpointing:
+        raise B200Error("causal / checkpointed forward is not covered")
+    n = self.patch_embed.num_patches + self.num_prefix_tokens
+    return BF.vit_forward(self, x, _kv_len(attn_mask, n))
+
+
+def install():
+    """Rebind timm's hot-path forwards.  Idempotent.  Raises if timm or libb200timm.so is unavailable."""
+    _lib.load()  # fail loudly: no silent PyTorch path when the CUDA library is missing
+    import timm  # noqa: F401
+    from timm.layers.attention import Attention
+    from timm.layers.mlp import Mlp
+    from timm.layers.norm import LayerNorm
+    from timm.layers.patch_embed import PatchEmbed
+    from timm.models.vision_transformer import Block, VisionTransformer
+    if _ORIG:
+        return
+    table = [
+        ("timm.layers.LayerNorm.forward", LayerNorm, "forward", lambda self, x: BF.layernorm(self, x)),
+        ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
+        ("timm.layers.Attention.forward", Attention, "forward", _attention),
+        ("timm.layers.PatchEmbed.forward", PatchEmbed, "forward",
+         lambda self, x: BF.patch_embed_forward(self, x) if self.flatten else (_ for _ in ()).throw(B200Error("NHWC"))),
+        ("timm.models.vision_transformer.Block.forward", Block, "forward", _block),
+        ("timm.models.vision_transformer.VisionTransformer.forward_features", VisionTransformer, "forward_features",
+         _vit_features),
+        ("timm.models.vision_transformer.VisionTransformer.forward_head", VisionTransformer, "forward_head",
+         lambda self, x, pre_logits=False: BF.vit_forward_head(self, x, pre_logits)),
+        ("timm.models.vision_transformer.VisionTransformer.forward", VisionTransformer, "forward", _vit_forward),
+    ]
+    for name, cls, attr, fn in table:
+        _ORIG[name] = getattr(cls, attr)
+        setattr(cls, attr, _dispatch(name, fn))
+        _ORIG[name + "#cls"] = (cls, attr)
+
+
+def uninstall():
+    """Restore timm's original forwards."""
+    for name in [k for k in _ORIG if not k.endswith("#cls")]:
+        cls, attr = _ORIG[name + "#cls"]
+        setattr(cls, attr, _ORIG[name])
+    _ORIG.clear()
+
+
+def installed():
+    return bool(_ORIG)
+
+
+if os.environ.get("B200TIMM_AUTOINSTALL", "1") == "1" and __name__ != "__main__":
+    # `--device-modules b200timm.plugin` / TORCH_BACKEND=b200timm.plugin only import the module:
+    # importing it is the installation (mirrors how out-of-tree torch backends register themselves).
+    try:
+        install()
+    except ImportError:
+        pass  # timm itself not importable: nothing to rebind (the mirror classes in b200timm.* still work)

@@ -17,12 +17,6 @@ namespace b200 {
 constexpr int kHd = 64;
 constexpr int kQTile = 128;
 
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 template <int KB, bool OVERLAY>
 struct AttnSmem {
   static constexpr int kQBytes = kQTile * kHd * 2;          // 16384
@@ -106,9 +100,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, kHd, false, true);
 
   float m_run = -INFINITY, l_run = 0.f;
-  float acc[kHd];
+  constexpr int kAcc = OVERLAY ? 1 : kHd / 2;   // multi-block variant keeps the running O in registers
+  f32x2 acc[kAcc];
 #pragma unroll
-  for (int i = 0; i < kHd; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0ull;
+  constexpr int kFull = KB / 32;                // 32-column chunks
+  constexpr bool kTail16 = (KB % 32) != 0;      // + one 16-column chunk (KB = 208)
 
   for (int j = 0; j < nblk; ++j) {
     const uint32_t ph = j & 1;
@@ -126,75 +123,100 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_wait(bar_s, ph);
     tc_fence_after();
 
-    // ---- pass 1: block row max over the valid keys
     const int key0 = j * KB;
-    float mb = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < KB; c += 32) {
-      if (c + 32 <= KB) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_row + c, r);
-        tmem_ld_wait();
+    const int nvalid = kvlen - key0;            // keys of this block that are not padding (may exceed KB)
+
+    // ---- pass 1: row max over the valid keys (software pipelined: load chunk c+1 while reducing chunk c)
+    float mb0 = -INFINITY, mb1 = -INFINITY;
+    {
+      uint32_t r[2][32];
+      tmem_ld_x32(tmem_row, r[0]);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (key0 + c + i < kvlen) mb = fmaxf(mb, __uint_as_float(r[i]));
-      } else {
-        uint32_t r[16];
-        tmem_ld_x16(tmem_row + c, r);
-        tmem_ld_wait();
+      for (int c = 0; c < kFull; ++c) {
+        tmem_ld_wait_x32(r[c & 1]);
+        if (c + 1 < kFull) tmem_ld_x32(tmem_row + (c + 1) * 32, r[(c + 1) & 1]);
+        else if (kTail16) tmem_ld_x16(tmem_row + kFull * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
+        if ((c + 1) * 32 <= nvalid) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mb0 = max3(mb0, __uint_as_float(r[c & 1][i]), __uint_as_float(r[c & 1][i + 1]));
+            mb1 = max3(mb1, __uint_as_float(r[c & 1][i + 2]), __uint_as_float(r[c & 1][i + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < nvalid) mb0 = fmaxf(mb0, __uint_as_float(r[c & 1][i]));
+        }
+      }
+      if (kTail16) {
+        uint32_t(&t)[16] = reinterpret_cast<uint32_t(&)[16]>(r[kFull & 1]);
+        tmem_ld_wait_x16(t);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (key0 + c + i < kvlen) mb = fmaxf(mb, __uint_as_float(r[i]));
+          if (kFull * 32 + i < nvalid) mb0 = fmaxf(mb0, __uint_as_float(t[i]));
       }
     }
-    const float m_new = fmaxf(m_run, mb);
+    const float m_new = fmaxf(m_run, fmaxf(mb0, mb1));
     const float neg_mc = -m_new * p.scale_log2e;
-    const float alpha = ex2(fmaf(m_run, p.scale_log2e, neg_mc));
-    float lsum = 0.f;
+    const float alpha = ex2_approx(fmaf(m_run, p.scale_log2e, neg_mc));
+    const f32x2 sc2 = splat(p.scale_log2e), nm2 = splat(neg_mc);
+    f32x2 lsum2 = 0ull;
 
     // ---- pass 2: p = exp2((s - m) * scale * log2e) -> bf16 core matrices in smem
     uint8_t* prow = sP + tid * 16;
-#pragma unroll 1
-    for (int c = 0; c < KB; c += 32) {
-      if (c + 32 <= KB) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_row + c, r);
-        tmem_ld_wait();
+    {
+      uint32_t r[2][32];
+      tmem_ld_x32(tmem_row, r[0]);
+#pragma unroll
+      for (int c = 0; c < kFull; ++c) {
+        tmem_ld_wait_x32(r[c & 1]);
+        if (c + 1 < kFull) tmem_ld_x32(tmem_row + (c + 1) * 32, r[(c + 1) & 1]);
+        else if (kTail16) tmem_ld_x16(tmem_row + kFull * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
+        const bool full = (c + 1) * 32 <= nvalid;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          float e[8];
+          uint32_t o[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float s = __uint_as_float(r[g * 8 + i]);
-            e[i] = (key0 + c + g * 8 + i < kvlen) ? ex2(fmaf(s, p.scale_log2e, neg_mc)) : 0.f;
-            lsum += e[i];
+          for (int i = 0; i < 4; ++i) {
+            float t0, t1;
+            upk(fma2(pk(__uint_as_float(r[c & 1][g * 8 + 2 * i]), __uint_as_float(r[c & 1][g * 8 + 2 * i + 1])), sc2, nm2), t0, t1);
+            float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+            if (!full) {
+              const int k = c * 32 + g * 8 + 2 * i;
+              e0 = (k < nvalid) ? e0 : 0.f;
+              e1 = (k + 1 < nvalid) ? e1 : 0.f;
+            }
+            lsum2 = add2(lsum2, pk(e0, e1));
+            o[i] = pack_bf16(e0, e1);
           }
-          uint4 q;
-          q.x = pack_bf16(e[0], e[1]); q.y = pack_bf16(e[2], e[3]);
-          q.z = pack_bf16(e[4], e[5]); q.w = pack_bf16(e[6], e[7]);
-          *reinterpret_cast<uint4*>(prow + ((c >> 3) + g) * (kQTile * 16)) = q;
+          *reinterpret_cast<uint4*>(prow + (c * 4 + g) * (kQTile * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-      } else {
-        uint32_t r[16];
-        tmem_ld_x16(tmem_row + c, r);
-        tmem_ld_wait();
+      }
+      if (kTail16) {
+        uint32_t(&t)[16] = reinterpret_cast<uint32_t(&)[16]>(r[kFull & 1]);
+        tmem_ld_wait_x16(t);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          float e[8];
+          uint32_t o[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float s = __uint_as_float(r[g * 8 + i]);
-            e[i] = (key0 + c + g * 8 + i < kvlen) ? ex2(fmaf(s, p.scale_log2e, neg_mc)) : 0.f;
-            lsum += e[i];
+          for (int i = 0; i < 4; ++i) {
+            float t0, t1;
+            upk(fma2(pk(__uint_as_float(t[g * 8 + 2 * i]), __uint_as_float(t[g * 8 + 2 * i + 1])), sc2, nm2), t0, t1);
+            const int k = kFull * 32 + g * 8 + 2 * i;
+            const float e0 = (k < nvalid) ? ex2_approx(t0) : 0.f;
+            const float e1 = (k + 1 < nvalid) ? ex2_approx(t1) : 0.f;
+            lsum2 = add2(lsum2, pk(e0, e1));
+            o[i] = pack_bf16(e0, e1);
           }
-          uint4 q;
-          q.x = pack_bf16(e[0], e[1]); q.y = pack_bf16(e[2], e[3]);
-          q.z = pack_bf16(e[4], e[5]); q.w = pack_bf16(e[6], e[7]);
-          *reinterpret_cast<uint4*>(prow + ((c >> 3) + g) * (kQTile * 16)) = q;
+          *reinterpret_cast<uint4*>(prow + (kFull * 4 + g) * (kQTile * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
     }
-    l_run = fmaf(l_run, alpha, lsum);
+    {
+      float s0, s1;
+      upk(lsum2, s0, s1);
+      l_run = fmaf(l_run, alpha, s0 + s1);
+    }
     m_run = m_new;
 
     fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
@@ -216,36 +238,59 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     __syncwarp();
     mbar_wait(bar_o, ph);
     tc_fence_after();
+    if constexpr (!OVERLAY) {
+      const f32x2 al2 = splat(alpha);
 #pragma unroll
-    for (int c = 0; c < kHd; c += 32) {
-      uint32_t r[32];
-      tmem_ld_x32(tmem_row + c, r);
-      tmem_ld_wait();
+      for (int c = 0; c < kHd; c += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem_row + c, r);
+        tmem_ld_wait_x32(r);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], alpha, __uint_as_float(r[i]));
-    }
-    tc_fence_before();
-    __syncthreads();  // S/O columns of TMEM and the K/V/P smem are free again
-    if (tid == 0 && j + 1 < nblk) {
-      mbar_arrive_expect_tx(bar_kv, 2 * L::kKBytes);
-      tma_load_2d(sK, &tm_kv, bar_kv, col_k, b * N + (j + 1) * KB);
-      tma_load_2d(sV, &tm_kv, bar_kv, col_v, b * N + (j + 1) * KB);
+        for (int i = 0; i < 16; ++i)
+          acc[c / 2 + i] = fma2(acc[c / 2 + i], al2, pk(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+      }
+      tc_fence_before();
+      __syncthreads();  // S/O columns of TMEM and the K/V/P smem are free again
+      if (tid == 0 && j + 1 < nblk) {
+        mbar_arrive_expect_tx(bar_kv, 2 * L::kKBytes);
+        tma_load_2d(sK, &tm_kv, bar_kv, col_k, b * N + (j + 1) * KB);
+        tma_load_2d(sV, &tm_kv, bar_kv, col_v, b * N + (j + 1) * KB);
+      }
     }
   }
 
-  if (row_in_img < N) {
-    const float inv_l = 1.0f / l_run;
+  {
+    // ---- epilogue: O / l -> bf16, merged-head layout; single-block variants read O straight from TMEM
+    const f32x2 il2 = splat(1.0f / l_run);
     __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * N + row_in_img) * (H * kHd) + h * kHd;
 #pragma unroll
-    for (int g = 0; g < kHd / 8; ++g) {
-      uint4 q;
-      q.x = pack_bf16(acc[g * 8 + 0] * inv_l, acc[g * 8 + 1] * inv_l);
-      q.y = pack_bf16(acc[g * 8 + 2] * inv_l, acc[g * 8 + 3] * inv_l);
-      q.z = pack_bf16(acc[g * 8 + 4] * inv_l, acc[g * 8 + 5] * inv_l);
-      q.w = pack_bf16(acc[g * 8 + 6] * inv_l, acc[g * 8 + 7] * inv_l);
-      reinterpret_cast<uint4*>(orow)[g] = q;
+    for (int c = 0; c < kHd; c += 32) {
+      uint32_t o[16];
+      if constexpr (OVERLAY) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem_row + c, r);
+        tmem_ld_wait_x32(r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float lo, hi;
+          upk(mul2(pk(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), il2), lo, hi);
+          o[i] = pack_bf16(lo, hi);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float lo, hi;
+          upk(mul2(acc[c / 2 + i], il2), lo, hi);
+          o[i] = pack_bf16(lo, hi);
+        }
+      }
+      if (row_in_img < N) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          reinterpret_cast<uint4*>(orow + c)[g] = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+      }
     }
-    if (p.lse != nullptr)
+    if (row_in_img < N && p.lse != nullptr)
       p.lse[(static_cast<long long>(b) * H + h) * N + row_in_img] = fmaf(m_run, p.scale, __logf(l_run));
   }
 

@@ -32,5 +32,8 @@ int sm_count();
 // dims 1..rank-1), 128-byte swizzle, zero fill out of bounds.  Returns 0 or an error code.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+// Same for an fp32 tensor (GEMM fp32 outputs: weight gradients).
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
 
 }  // namespace b200

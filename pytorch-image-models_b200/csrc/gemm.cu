@@ -4,7 +4,11 @@
 //   warp 1      : MMA issuer     (one thread issues tcgen05.mma 128 x BN x 16, accumulators in TMEM,
 //                                 two accumulator stages so the epilogue overlaps the next tile)
 //   warp 2      : TMEM allocator / deallocator
-//   warps 4..11 : epilogue       (tcgen05.ld -> bias / GELU / residual+LayerScale / dGELU -> global)
+//   warps 4..11 : epilogue       (tcgen05.ld -> bias / GELU / residual+LayerScale / dGELU -> 128B-swizzled smem
+//                                 staging tile -> TMA store; the residual / pre-activation operand comes in
+//                                 through a TMA load into the same staging tile, so every global access of the
+//                                 epilogue is a full-line bulk copy; fp32 outputs accumulate / split-K through
+//                                 TMA reduce-add)
 //
 // Replaces F.linear (+ the separate GELU / residual / LayerScale ATen passes) of
 // timm/layers/attention.py:115,137, timm/layers/mlp.py:48-52, timm/models/vision_transformer.py:212-213.
@@ -37,55 +41,61 @@ struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarrierOffset = STAGES * kStageBytes;
+  static constexpr int kStagingOffset = STAGES * kStageBytes;   // kNumEpiWarps x 4 KB (32 rows x 128 B each)
+  static constexpr int kStagingBytes = kNumEpiWarps * 4096;
+  static constexpr int kBarrierOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarrierOffset + 256 + 1024;  // + barriers + alignment slack
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  // 0.5 x (1 + erf(x / sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), 2 MUFU + 8 FMA.
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+// Shared part of GELU / GELU':  for a pair x returns erf(x / sqrt2) and e = exp(-x^2 / 2).
+// erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt2.
+__device__ __forceinline__ void erf_pair(f32x2 x, f32x2& erf_v, f32x2& e) {
+  float x0, x1;
+  upk(x, x0, x1);
+  const f32x2 z = pk(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+  float d0, d1;
+  upk(fma2(z, splat(0.3275911f), splat(1.0f)), d0, d1);
+  const f32x2 t = pk(rcp_approx(d0), rcp_approx(d1));
+  f32x2 q = fma2(t, splat(-1.061405429f), splat(1.453152027f));   // -(a1 t + ... ) with negated coefficients
+  q = fma2(q, t, splat(-1.421413741f));
+  q = fma2(q, t, splat(0.284496736f));
+  q = fma2(q, t, splat(-0.254829592f));
+  q = mul2(q, t);
+  float w0, w1;
+  upk(mul2(mul2(z, z), splat(-1.4426950408889634f)), w0, w1);
+  e = pk(ex2_approx(w0), ex2_approx(w1));                          // exp(-z^2) = exp(-x^2 / 2)
+  float a0, a1;
+  upk(fma2(q, e, splat(1.0f)), a0, a1);                            // erf(|x| / sqrt2)
+  erf_v = pk(copysignf(a0, x0), copysignf(a1, x1));
+}
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  f32x2 erf_v, e;
+  erf_pair(x, erf_v, e);
+  return mul2(x, fma2(erf_v, splat(0.5f), splat(0.5f)));           // 0.5 x (1 + erf)
+}
+__device__ __forceinline__ f32x2 dgelu_erf2(f32x2 x) {
+  f32x2 erf_v, e;
+  erf_pair(x, erf_v, e);
+  const f32x2 cdf = fma2(erf_v, splat(0.5f), splat(0.5f));
+  return fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);        // Phi(x) + x phi(x)
 }
 
-__device__ __forceinline__ float dgelu_erf(float x) {
-  // d/dx [x Phi(x)] = Phi(x) + x phi(x)
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);  // exp(-x^2/2)
-  const float erf_v = copysignf(fmaf(-p, e, 1.0f), x);
-  const float cdf = 0.5f * (1.0f + erf_v);
-  return fmaf(x * 0.3989422804014327f, e, cdf);
-}
-
-__device__ __forceinline__ void load8_param(const void* base, int f32, int col, float (&v)[8]) {
+// 8 consecutive parameters (bias / LayerScale gamma) starting at column `col`, as 4 fp32 pairs
+__device__ __forceinline__ void load8_param2(const void* base, int f32, int col, f32x2 (&v)[4]) {
   if (f32) {
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + col);
-    float4 a = __ldg(p), b = __ldg(p + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = pk(a.x, a.y); v[1] = pk(a.z, a.w); v[2] = pk(b.x, b.y); v[3] = pk(b.z, b.w);
   } else {
-    uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + col));
-    v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
-    v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + col));
+    v[0] = bf16x2_to_f32x2(q.x); v[1] = bf16x2_to_f32x2(q.y); v[2] = bf16x2_to_f32x2(q.z); v[3] = bf16x2_to_f32x2(q.w);
   }
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                  const GemmKernelParams p) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -94,7 +104,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;  // one per epilogue warp
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_bar + kNumEpiWarps);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,6 +121,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kNumEpiWarps * 32);
     }
+    for (int i = 0; i < kNumEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+    tma_prefetch_desc(&tmap_out);
+    tma_prefetch_desc(&tmap_aux);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -200,6 +214,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quad = warp_idx & 3;          // TMEM lane quadrant this warp may access
     const int half = ew >> 2;               // which half of the BN columns
     constexpr int kColsPerWarp = BN / 2;
+    uint8_t* stg = smem + L::kStagingOffset + ew * 4096;   // 32 rows x 128 B, 128B-swizzled (TMA box layout)
+    const uint32_t stg_row = smem_u32(stg) + lane * 128;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const bool has_aux = p.epilogue == B200_EPI_BIAS_RESIDUAL || p.epilogue == B200_EPI_DGELU;
+    const bool reduce_out = p.out_f32 && (p.accumulate || p.split_k > 1);
+    const int round_cols = p.out_f32 ? 32 : 64;   // 128-byte rows of the staging tile
+    uint32_t aux_phase = 0;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -207,81 +228,117 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int mn = tile - ks * tiles_mn;
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
-      const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
+      const int row0 = m_blk * BM + quad * 32;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * kColsPerWarp;
+      bool waited = false;
 #pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(taddr0 + c, r);
-        tmem_ld_wait();
-        const int col0 = n_blk * BN + half * kColsPerWarp + c;
-        if (row_ok && col0 < p.N) {
+      for (int rc = 0; rc < kColsPerWarp; rc += round_cols) {
+        const int col0 = n_blk * BN + half * kColsPerWarp + rc;
+        // the staging tile is free once the previous TMA store has finished READING it
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        if (has_aux && lane == 0) {
+          mbar_arrive_expect_tx(&aux_bar[ew], 4096);
+          tma_load_2d(stg, &tmap_aux, &aux_bar[ew], col0, row0);
+        }
+        if (!waited) {
+          mbar_wait(&tfull_bar[as], aphase);
+          tc_fence_after();
+          waited = true;
+        }
+        if (has_aux) {
+          mbar_wait(&aux_bar[ew], aux_phase);
+          aux_phase ^= 1;
+        }
+#pragma unroll 1
+        for (int c = 0; c < round_cols; c += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(taddr0 + rc + c, r);
+          tmem_ld_wait();
+          if (p.out_f32) {
+            // fp32 output (weight gradients): 32 columns = 8 chunks of 4 floats
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              if (p.bias != nullptr) {
-                float bv[8];
-                load8_param(p.bias, p.bias_f32, col, bv);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += bv[j];
-              }
-              if (p.epilogue == B200_EPI_BIAS_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-              } else if (p.epilogue == B200_EPI_BIAS_RESIDUAL) {
-                if (p.gamma != nullptr) {
-                  float gv[8];
-                  load8_param(p.gamma, p.gamma_f32, col, gv);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] *= gv[j];
-                }
-                float av[8];
-                load8_param(p.aux + static_cast<long long>(row) * p.ldaux, 0, col, av);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += av[j];
-              } else if (p.epilogue == B200_EPI_DGELU) {
-                float av[8];
-                load8_param(p.aux + static_cast<long long>(row) * p.ldaux, 0, col, av);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] *= dgelu_erf(av[j]);
-              }
-              if (p.out_f32) {
-                float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-                if (p.split_k > 1) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) atomicAdd(o + j, v[j]);
+            for (int g = 0; g < 8; ++g) {
+              const int col = col0 + g * 4;
+              float v0 = __uint_as_float(r[g * 4 + 0]), v1 = __uint_as_float(r[g * 4 + 1]);
+              float v2 = __uint_as_float(r[g * 4 + 2]), v3 = __uint_as_float(r[g * 4 + 3]);
+              if (p.bias != nullptr && col < p.N) {
+                if (p.bias_f32) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + col));
+                  v0 += b4.x; v1 += b4.y; v2 += b4.z; v3 += b4.w;
                 } else {
-                  float4* o4 = reinterpret_cast<float4*>(o);
-                  if (p.accumulate) {
-                    float4 a = o4[0], b = o4[1];
-                    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-                    v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
-                  }
-                  o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                  o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                  const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col));
+                  v0 += bf16_lo(b2.x); v1 += bf16_hi(b2.x); v2 += bf16_lo(b2.y); v3 += bf16_hi(b2.y);
                 }
-              } else {
-                uint4 q;
-                q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
-                q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                          static_cast<long long>(row) * p.ldo + col) = q;
               }
+              const uint32_t addr = stg_row + ((static_cast<uint32_t>(g) ^ sw) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + c + g * 8;
+              const uint32_t addr = stg_row + ((static_cast<uint32_t>((c >> 3) + g) ^ sw) << 4);
+              f32x2 v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = pk(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
+              if (col < p.N) {
+                if (p.bias != nullptr) {
+                  f32x2 bv[4];
+                  load8_param2(p.bias, p.bias_f32, col, bv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[j] = add2(v[j], bv[j]);
+                }
+                if (p.epilogue == B200_EPI_BIAS_GELU) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
+                } else if (has_aux) {
+                  uint4 q;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+                  const f32x2 av[4] = {bf16x2_to_f32x2(q.x), bf16x2_to_f32x2(q.y), bf16x2_to_f32x2(q.z), bf16x2_to_f32x2(q.w)};
+                  if (p.epilogue == B200_EPI_BIAS_RESIDUAL) {
+                    if (p.gamma != nullptr) {
+                      f32x2 gv[4];
+                      load8_param2(p.gamma, p.gamma_f32, col, gv);
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], gv[j], av[j]);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) v[j] = add2(v[j], av[j]);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], dgelu_erf2(av[j]));
+                  }
+                }
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                upk(v[j], lo, hi);
+                o[j] = pack_bf16(lo, hi);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                           : "memory");
             }
           }
         }
+        if (rc + round_cols >= kColsPerWarp) {  // last TMEM read of this tile: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+        }
+        fence_proxy_async_smem();  // staging writes (generic proxy) -> visible to the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0 && col0 < p.N && row0 < p.M) {
+          if (reduce_out) tma_reduce_add_2d(&tmap_out, stg, col0, row0);
+          else tma_store_2d(&tmap_out, stg, col0, row0);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -311,6 +368,25 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
     rc = encode_tmap_bf16(&tb, d.b, 2, dims, strides, box, true);
     if (rc) return rc;
   }
+  CUtensorMap tout, taux;
+  {
+    // out / aux: dims {N, M}; box = one 128-byte-wide, 32-row staging tile
+    const bool of32 = d.out_dtype == B200_DTYPE_F32;
+    uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(d.ldo) * (of32 ? 4 : 2)};
+    uint32_t box[2] = {of32 ? 32u : 64u, 32u};
+    int rc = of32 ? encode_tmap_f32(&tout, d.out, 2, dims, strides, box, true)
+                  : encode_tmap_bf16(&tout, d.out, 2, dims, strides, box, true);
+    if (rc) return rc;
+    if (d.aux != nullptr) {
+      uint64_t astr[1] = {static_cast<uint64_t>(d.ldaux) * 2};
+      uint32_t abox[2] = {64u, 32u};
+      rc = encode_tmap_bf16(&taux, d.aux, 2, dims, astr, abox, true);
+      if (rc) return rc;
+    } else {
+      taux = tout;
+    }
+  }
   GemmKernelParams p;
   p.out = d.out; p.bias = d.bias; p.aux = reinterpret_cast<const __nv_bfloat16*>(d.aux); p.gamma = d.gamma;
   p.ldo = d.ldo; p.ldaux = d.ldaux;
@@ -335,7 +411,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
   int grid = sm_count();
   if (grid > num_tiles) grid = num_tiles;
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
+  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, tout, taux, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
@@ -351,8 +427,10 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   B200_CHECK_ARG(d.a && d.b && d.out, "b200_gemm: null operand pointer");
   B200_CHECK_ARG(d.M > 0 && d.N > 0 && d.K > 0, "b200_gemm: non-positive shape M=%d N=%d K=%d", d.M, d.N, d.K);
   B200_CHECK_ARG(d.N % 8 == 0, "b200_gemm: N=%d must be a multiple of 8", d.N);
-  B200_CHECK_ARG(d.ldo % 8 == 0 && d.ldo >= d.N, "b200_gemm: ldo=%lld must be >= N and a multiple of 8",
-                 (long long)d.ldo);
+  B200_CHECK_ARG(d.ldo % (d.out_dtype == B200_DTYPE_F32 ? 4 : 8) == 0 && d.ldo >= d.N,
+                 "b200_gemm: ldo=%lld must be >= N and give 16-byte aligned rows", (long long)d.ldo);
+  if (d.out_dtype == B200_DTYPE_F32)
+    B200_CHECK_ARG(d.epilogue == B200_EPI_BIAS, "b200_gemm: fp32 outputs support only the bias epilogue");
   B200_CHECK_ARG(d.lda % 8 == 0 && d.ldb % 8 == 0, "b200_gemm: lda/ldb must be multiples of 8 (16-byte TMA strides)");
   B200_CHECK_ARG(d.lda >= (d.a_mn ? d.M : d.K), "b200_gemm: lda=%lld too small", (long long)d.lda);
   B200_CHECK_ARG(d.ldb >= (d.b_mn ? d.N : d.K), "b200_gemm: ldb=%lld too small", (long long)d.ldb);

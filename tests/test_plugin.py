@@ -1,0 +1,63 @@
+"""The timm plugin (class-level forward rebinding, SURVEY.md 8b seam 3).  Needs the reference checkout to be
+importable, which is only the case in the authoring container -- skipped on the GPU box."""
+import os
+import sys
+
+import pytest
+import torch
+
+REF = os.environ.get("TIMM_REFERENCE", "/root/reference")
+if os.path.isdir(REF) and REF not in sys.path:
+    sys.path.insert(0, REF)
+timm = pytest.importorskip("timm")
+
+
+@pytest.fixture()
+def plugin():
+    from b200timm import plugin as P
+    P.install()
+    yield P
+    P.uninstall()
+
+
+def test_install_rebinds_and_uninstall_restores(plugin):
+    from timm.layers import Attention, LayerNorm, Mlp
+    from timm.models.vision_transformer import Block, VisionTransformer
+    for cls, attr in ((Attention, "forward"), (Mlp, "forward"), (LayerNorm, "forward"), (Block, "forward"),
+                      (VisionTransformer, "forward_features"), (VisionTransformer, "forward")):
+        assert hasattr(getattr(cls, attr), "_b200_original"), f"{cls.__name__}.{attr} not rebound"
+    plugin.uninstall()
+    assert not hasattr(Block.forward, "_b200_original")
+    plugin.install()
+
+
+def test_cpu_and_fp32_calls_keep_the_reference_path(plugin):
+    """BASELINE configs[0] (vit_tiny, fp32, CPU, benchmark.py plumbing) must be untouched by the plugin."""
+    torch.manual_seed(0)
+    model = timm.create_model("vit_tiny_patch16_224", num_classes=10).eval()
+    x = torch.randn(1, 3, 224, 224)
+    with torch.no_grad():
+        y_plugin = model(x)
+    plugin.uninstall()
+    with torch.no_grad():
+        y_ref = model(x)
+    plugin.install()
+    assert torch.equal(y_plugin, y_ref)
+    # parameters and state_dict keys are timm's own: nothing was replaced or re-parented
+    assert list(model.state_dict())[:4] == ["cls_token", "pos_embed", "patch_embed.proj.weight", "patch_embed.proj.bias"]
+
+
+def test_training_and_grad_calls_defer_to_timm_until_backward_is_registered(plugin):
+    model = timm.create_model("vit_tiny_patch16_224", num_classes=4, img_size=32).train()
+    out = model(torch.randn(2, 3, 32, 32))
+    out.mean().backward()
+    assert all(p.grad is not None for p in model.parameters())
+
+
+def test_mirror_and_timm_state_dicts_are_interchangeable():
+    from b200timm.vision_transformer import create_model
+    ours = create_model("vit_tiny_patch16_224")
+    theirs = timm.create_model("vit_tiny_patch16_224")
+    assert list(ours.state_dict()) == list(theirs.state_dict())
+    theirs.load_state_dict(ours.state_dict(), strict=True)
+    ours.load_state_dict(theirs.state_dict(), strict=True)
