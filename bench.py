@@ -113,6 +113,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     batch = 16  # CPU throughput is batch-insensitive; one step = one bounded sample of the workload
+    if os.environ.get("B200_REF_TINY"):   # unit tests of the harness only
+        batch = 1
     ips32, _, _ = cpu_port_throughput(batch, 2, 1, dtype=torch.float32)
     ips, spp, cores = cpu_port_throughput(batch, args.steps, min(args.warmup, 2), dtype=torch.bfloat16)
     line = {

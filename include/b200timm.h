@@ -61,7 +61,9 @@ typedef struct b200_gemm_desc {
   const void* bias;  /* [N] or NULL; dtype bias_dtype                                             */
   const void* aux;   /* [M,N] bf16, ld = ldaux: residual (EPI_BIAS_RESIDUAL) / pre-activation (EPI_DGELU) */
   const void* gamma; /* [N] or NULL (LayerScale), dtype gamma_dtype; EPI_BIAS_RESIDUAL only        */
-  int64_t lda, ldb, ldo, ldaux;
+  void* out2;        /* optional second bf16 output [M,N] (ld = ldo2), EPI_BIAS_GELU only: receives the
+                        pre-activation acc + bias (saved for backward) while `out` receives its GELU     */
+  int64_t lda, ldb, ldo, ldaux, ldo2;
   int32_t M, N, K;
   int32_t a_mn, b_mn;
   int32_t epilogue;
@@ -80,12 +82,14 @@ B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);
 B200_API int b200_layernorm_fwd(const void* x, const void* weight, const void* bias, void* y, float* mean,
                        float* rstd, int64_t rows, int32_t cols, float eps, int32_t x_dtype,
                        int32_t y_dtype, int32_t param_dtype, void* stream);
-/* dx (same dtype as x) and, accumulated over rows, dweight/dbias written as fp32 [cols] into
+/* dres (optional, dtype of x): gradient flowing through the residual connection around the norm; dx =
+ * LN-backward(dy) + dres in one pass (Block.forward's `x + f(norm(x))`, vision_transformer.py:212-213).
+ * dx (same dtype as x) and, accumulated over rows, dweight/dbias written as fp32 [cols] into
  * dw_partial/db_partial after an internal two-stage reduction (workspace: fp32 [ws_rows, 2*cols],
  * ws_rows = b200_layernorm_bwd_ws_rows(rows)).                                                       */
 B200_API int b200_layernorm_bwd_ws_rows(int64_t rows, int32_t cols);
 B200_API int b200_layernorm_bwd(const void* dy, const void* x, const void* weight, const float* mean,
-                       const float* rstd, void* dx, float* dweight, float* dbias, float* workspace,
+                       const float* rstd, const void* dres, void* dx, float* dweight, float* dbias, float* workspace,
                        int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
                        int32_t param_dtype, void* stream);
 
@@ -116,6 +120,10 @@ B200_API int b200_assemble_tokens(const void* proj, const void* prefix, const vo
                          int32_t pos_has_prefix, void* stream);
 
 /* ------------------------------------------------------------------ elementwise / reductions
+ * dst[i] (+)= src[i]: fp32 -> bf16/fp32 hand-off of split-K weight gradients into .grad (n % 4 == 0).        */
+B200_API int b200_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, int32_t accumulate,
+                     void* stream);
+/*
  * column sums of a bf16 [rows, cols] matrix into fp32 [cols] (bias gradients).                       */
 B200_API int b200_colsum(const void* x, float* out, int64_t rows, int32_t cols, int32_t accumulate, void* stream);
 

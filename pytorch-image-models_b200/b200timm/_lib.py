@@ -31,10 +31,12 @@ class GemmDesc(ctypes.Structure):
         ("bias", ctypes.c_void_p),
         ("aux", ctypes.c_void_p),
         ("gamma", ctypes.c_void_p),
+        ("out2", ctypes.c_void_p),
         ("lda", ctypes.c_int64),
         ("ldb", ctypes.c_int64),
         ("ldo", ctypes.c_int64),
         ("ldaux", ctypes.c_int64),
+        ("ldo2", ctypes.c_int64),
         ("M", ctypes.c_int32),
         ("N", ctypes.c_int32),
         ("K", ctypes.c_int32),
@@ -60,7 +62,8 @@ SIGNATURES = {
     "b200_gemm": (ctypes.c_int, [ctypes.POINTER(GemmDesc), _vp]),
     "b200_layernorm_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),
     "b200_layernorm_bwd_ws_rows": (ctypes.c_int, [_i64, _i32]),
-    "b200_layernorm_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b200_layernorm_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "b200_convert_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "b200_attn_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "b200_attn_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "b200_patchify": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

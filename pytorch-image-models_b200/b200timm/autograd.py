@@ -1,0 +1,261 @@
+"""Training path: torch.autograd.Function wrappers whose forward AND backward run on libb200timm kernels.
+
+The reference has no backward code for this path -- gradients come from PyTorch autograd formulas of
+F.linear / F.layer_norm / SDPA / GELU (SURVEY.md 8a "Backward").  These Functions own the backward definitions;
+they are validated against autograd of the oracle (tests/test_gpu_train.py) and against the reference's own
+backward golden (tests/golden/vit_g1_default.pt "grads").
+
+Per transformer block (vision_transformer.py:206-214) the saved tensors are: x, LN1 stats + output, qkv, attention
+output + log-sum-exp, x after the attention branch, LN2 stats + output, fc1 pre-activation and its GELU (16 N*D
+units).  Backward = 4 dgrad GEMMs (GELU' fused into fc2's dgrad epilogue), 4 wgrad GEMMs (fp32 split-K through TMA
+reduce-add), attention backward, 2 LayerNorm backwards with the residual gradient folded in, 4 bias column sums.
+Parameters stay ordinary nn.Parameter leaves, so DDP's reducer hooks, optimizers and EMA work unchanged.
+"""
+import torch
+
+from . import ops
+from ._lib import B200Error
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _to_param_dtype(g32, like):
+    """fp32 gradient -> a fresh tensor with the parameter's dtype and shape (kernel conversion, no torch math)."""
+    if like.dtype == torch.float32:
+        return g32.view(like.shape)
+    out = torch.empty(like.shape, dtype=like.dtype, device=like.device)
+    n = g32.numel()
+    if n % 4 == 0:
+        ops.convert_f32(g32.reshape(-1), out.view(-1))
+    else:  # tiny odd-sized parameter (e.g. a 10-class head bias): pad to a multiple of 4
+        pad = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=g32.device)
+        pad[:n] = g32.reshape(-1)
+        tmp = torch.empty(pad.numel(), dtype=like.dtype, device=like.device)
+        ops.convert_f32(pad, tmp)
+        out.view(-1).copy_(tmp[:n])
+    return out
+
+
+def _bias_grad(dy2d, bias):
+    if bias is None:
+        return None
+    return _to_param_dtype(ops.colsum(dy2d), bias)
+
+
+def _wgrad(dy2d, x2d, weight):
+    return _to_param_dtype(ops.linear_wgrad(dy2d, x2d), weight)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """LayerNorm.forward (timm/layers/norm.py:85-90) with a kernel backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps, save_stats=True)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(_c(dy), x, weight, mean, rstd)
+        return dx, _to_param_dtype(dw, weight), (_to_param_dtype(db, weight) if ctx.has_bias else None), None
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on [..., K] activations (classifier head, vision_transformer.py:1292).  out_features that are
+    not a multiple of 8 run on zero-padded weight / bias copies (16-byte TMA rows) and are sliced back."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        shape = x.shape
+        x2 = _c(x.reshape(-1, shape[-1]))
+        N, K = weight.shape
+        npad = (N + 7) // 8 * 8
+        w, b = weight, bias
+        if npad != N:
+            w = torch.zeros(npad, K, dtype=weight.dtype, device=weight.device)
+            w[:N] = weight
+            if bias is not None:
+                b = torch.zeros(npad, dtype=bias.dtype, device=bias.device)
+                b[:N] = bias
+        y = ops.linear_fwd(x2, _c(w), b)
+        ctx.save_for_backward(x2, w, weight, bias)
+        ctx.shape = shape
+        return y[:, :N].reshape(*shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, weight, bias = ctx.saved_tensors
+        N = weight.shape[0]
+        npad = w.shape[0]
+        dy2 = dy.reshape(-1, N)
+        if npad != N:
+            pad = torch.zeros(dy2.shape[0], npad, dtype=dy2.dtype, device=dy2.device)
+            pad[:, :N] = dy2
+            dy2 = pad
+        dy2 = _c(dy2)
+        dx = ops.linear_dgrad(dy2, w).view(ctx.shape) if ctx.needs_input_grad[0] else None
+        gw = ops.linear_wgrad(dy2, x2)[:N]
+        gb = None if bias is None else ops.colsum(dy2)[:N]
+        return dx, _to_param_dtype(_c(gw), weight), (None if gb is None else _to_param_dtype(_c(gb), bias))
+
+
+class MlpFn(torch.autograd.Function):
+    """Mlp.forward (timm/layers/mlp.py:47-54): fc2(GELU(fc1(x)))."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        shape = x.shape
+        x2 = _c(x.reshape(-1, shape[-1]))
+        pre = torch.empty(x2.shape[0], w1.shape[0], dtype=torch.bfloat16, device=x.device)
+        act = ops.linear_fwd(x2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+        y = ops.linear_fwd(act, w2, b2)
+        ctx.save_for_backward(x2, w1, b1, w2, b2, pre, act)
+        ctx.shape = shape
+        return y.view(*shape[:-1], -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, b1, w2, b2, pre, act = ctx.saved_tensors
+        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        dpre = ops.linear_dgrad(dy2, w2, epilogue=ops.EPI_DGELU, aux=pre)
+        dx = ops.linear_dgrad(dpre, w1).view(ctx.shape)
+        return dx, _wgrad(dpre, x2, w1), _bias_grad(dpre, b1), _wgrad(dy2, act, w2), _bias_grad(dy2, b2)
+
+
+class AttentionFn(torch.autograd.Function):
+    """Attention.forward (timm/layers/attention.py:108-139): qkv GEMM, SDPA, proj GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, wqkv, bqkv, wproj, bproj, kv_len, num_heads, scale):
+        B, N, C = x.shape
+        hd = wqkv.shape[0] // 3 // num_heads
+        x2 = _c(x.reshape(B * N, C))
+        qkv = ops.linear_fwd(x2, wqkv, bqkv)
+        o, lse = ops.attention_fwd(qkv, B, N, num_heads, hd, scale, kv_len, need_lse=True)
+        y = ops.linear_fwd(o.view(B * N, -1), wproj, bproj)
+        ctx.save_for_backward(x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len)
+        ctx.meta = (B, N, num_heads, hd, scale)
+        return y.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len = ctx.saved_tensors
+        B, N, H, hd, scale = ctx.meta
+        dy2 = _c(dy.reshape(B * N, -1))
+        o2 = o.view(B * N, -1)
+        do = ops.linear_dgrad(dy2, wproj)
+        dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
+        dx = ops.linear_dgrad(dqkv, wqkv).view(B, N, -1)
+        return (dx, _wgrad(dqkv, x2, wqkv), _bias_grad(dqkv, bqkv), _wgrad(dy2, o2, wproj), _bias_grad(dy2, bproj),
+                None, None, None)
+
+
+class BlockFn(torch.autograd.Function):
+    """Block.forward (timm/models/vision_transformer.py:206-214), no LayerScale / DropPath (ViT-B defaults)."""
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, kv_len, num_heads, scale, eps1,
+                eps2):
+        B, N, D = x.shape
+        hd = wqkv.shape[0] // 3 // num_heads
+        x0 = _c(x.reshape(B * N, D))
+        h1, mean1, rstd1 = ops.layernorm_fwd(x0, n1w, n1b, eps1, save_stats=True)
+        qkv = ops.linear_fwd(h1, wqkv, bqkv)
+        o, lse = ops.attention_fwd(qkv, B, N, num_heads, hd, scale, kv_len, need_lse=True)
+        x1 = ops.linear_fwd(o.view(B * N, -1), wproj, bproj, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x0)
+        h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps2, save_stats=True)
+        pre = torch.empty(B * N, w1.shape[0], dtype=torch.bfloat16, device=x.device)
+        act = ops.linear_fwd(h2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+        x2 = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x1)
+        ctx.save_for_backward(x0, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, kv_len, h1, mean1, rstd1,
+                              qkv, o, lse, x1, h2, mean2, rstd2, pre, act)
+        ctx.meta = (B, N, D, num_heads, hd, scale)
+        return x2.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x0, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, kv_len, h1, mean1, rstd1, qkv, o, lse, x1, h2,
+         mean2, rstd2, pre, act) = ctx.saved_tensors
+        B, N, D, H, hd, scale = ctx.meta
+        dx2 = _c(dy.reshape(B * N, D))
+        # ---- MLP branch:  x2 = x1 + fc2(GELU(fc1(LN2(x1))))
+        dpre = ops.linear_dgrad(dx2, w2, epilogue=ops.EPI_DGELU, aux=pre)            # dY W2 * GELU'(pre)
+        g_w2, g_b2 = _wgrad(dx2, act, w2), _bias_grad(dx2, b2)
+        dh2 = ops.linear_dgrad(dpre, w1)
+        g_w1, g_b1 = _wgrad(dpre, h2, w1), _bias_grad(dpre, b1)
+        dx1, dn2w, dn2b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2)    # + residual gradient
+        # ---- attention branch:  x1 = x0 + proj(SDPA(qkv(LN1(x0))))
+        do = ops.linear_dgrad(dx1, wproj)
+        g_wp, g_bp = _wgrad(dx1, o.view(B * N, -1), wproj), _bias_grad(dx1, bproj)
+        dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
+        dh1 = ops.linear_dgrad(dqkv, wqkv)
+        g_wq, g_bq = _wgrad(dqkv, h1, wqkv), _bias_grad(dqkv, bqkv)
+        dx0, dn1w, dn1b = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1)
+        return (dx0.view(B, N, D), _to_param_dtype(dn1w, n1w), _to_param_dtype(dn1b, n1b), g_wq, g_bq, g_wp, g_bp,
+                _to_param_dtype(dn2w, n2w), _to_param_dtype(dn2b, n2b), g_w1, g_b1, g_w2, g_b2,
+                None, None, None, None, None)
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """PatchEmbed.forward (timm/layers/patch_embed.py:117-142): patch gather + GEMM; no image gradient."""
+
+    @staticmethod
+    def forward(ctx, img, weight, bias, patch):
+        B, C, H, W = img.shape
+        D = weight.shape[0]
+        K = C * patch * patch
+        kpad = (K + 7) // 8 * 8
+        w2 = weight.reshape(D, K)
+        if kpad != K:
+            wp = torch.zeros(D, kpad, dtype=weight.dtype, device=weight.device)
+            wp[:, :K] = w2
+            w2 = wp
+        patches = ops.patchify(_c(img), patch, kpad)
+        y = ops.gemm(patches, _c(w2), patches.shape[0], D, kpad, bias=bias)
+        ctx.save_for_backward(patches, weight, bias)
+        ctx.K = K
+        return y.view(B, (H // patch) * (W // patch), D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        patches, weight, bias = ctx.saved_tensors
+        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        gw = ops.linear_wgrad(dy2, patches)            # [D, Kpad] fp32
+        if gw.shape[1] != ctx.K:
+            gw = gw[:, :ctx.K].contiguous()
+        return None, _to_param_dtype(gw, weight), _bias_grad(dy2, bias), None
+
+
+class TokensFn(torch.autograd.Function):
+    """_pos_embed (vision_transformer.py:1038-1075): prefix-token concat + position-embedding add."""
+
+    @staticmethod
+    def forward(ctx, proj, prefix, pos, pos_has_prefix):
+        B, G, D = proj.shape
+        n_prefix = 0 if prefix is None else prefix.shape[-2]
+        pre2 = None if prefix is None else _c(prefix.reshape(n_prefix, D))
+        pos2 = None if pos is None else _c(pos.reshape(-1, D))
+        tokens = ops.assemble_tokens(_c(proj.reshape(B * G, D)), pre2, pos2, B, G, n_prefix, D, pos_has_prefix)
+        ctx.meta = (B, G, D, n_prefix, pos_has_prefix)
+        ctx.shapes = (None if prefix is None else (prefix.shape, prefix.dtype), None if pos is None else (pos.shape, pos.dtype))
+        return tokens
+
+    @staticmethod
+    def backward(ctx, dtok):
+        B, G, D, n_prefix, pos_has_prefix = ctx.meta
+        dtok = _c(dtok)
+        dproj = dtok[:, n_prefix:, :].contiguous() if n_prefix else dtok
+        s = ops.colsum(dtok.view(B, (G + n_prefix) * D)).view(G + n_prefix, D)     # sum over the batch, fp32
+        dprefix = dpos = None
+        if ctx.shapes[0] is not None:
+            shape, dtype = ctx.shapes[0]
+            dprefix = s[:n_prefix].to(dtype).view(shape)
+        if ctx.shapes[1] is not None:
+            shape, dtype = ctx.shapes[1]
+            dpos = (s if pos_has_prefix else s[n_prefix:]).to(dtype).view(shape)
+        return dproj, dprefix, dpos, None

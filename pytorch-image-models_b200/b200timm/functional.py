@@ -26,6 +26,16 @@ def _is_identity(m):
     return m is None or isinstance(m, nn.Identity)
 
 
+def _needs_grad(x, *modules):
+    """True when this call must be recorded for backward: grad mode on and the input or any parameter of the
+    given modules requires grad (training).  Inference (no_grad / inference_mode) takes the fused path."""
+    if not torch.is_grad_enabled():
+        return False
+    if isinstance(x, torch.Tensor) and x.requires_grad:
+        return True
+    return any(p.requires_grad for m in modules if m is not None for p in m.parameters())
+
+
 def _ln_params(norm):
     if _is_identity(norm):
         return None
@@ -112,6 +122,9 @@ def _padded_out_linear(linear, x2):
 def layernorm(norm, x):
     """LayerNorm.forward (timm/layers/norm.py:85-90)."""
     w, b, eps = _ln_params(norm)
+    if _needs_grad(x, norm):
+        from .autograd import LayerNormFn
+        return LayerNormFn.apply(x, w, b, eps)
     return ops.layernorm_fwd(x, w, b, eps)[0]
 
 
@@ -119,6 +132,11 @@ def attention_forward(attn, x, kv_len=None):
     """Attention.forward (timm/layers/attention.py:108-139) without the output projection's residual."""
     check_attention(attn)
     B, N, C = x.shape
+    if _needs_grad(x, attn):
+        from .autograd import AttentionFn
+        _bf16_2d(x, C)
+        return AttentionFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, kv_len, attn.num_heads,
+                                 attn.scale)
     x2 = _bf16_2d(x, C)
     qkv = ops.linear_fwd(x2, _w(attn.qkv), attn.qkv.bias)
     o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
@@ -130,6 +148,10 @@ def mlp_forward(mlp, x):
     """Mlp.forward (timm/layers/mlp.py:47-54): fc2(GELU(fc1(x))), GELU fused into fc1's epilogue."""
     check_mlp(mlp)
     shape = x.shape
+    if _needs_grad(x, mlp):
+        from .autograd import MlpFn
+        _bf16_2d(x, shape[-1])
+        return MlpFn.apply(x, _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias)
     x2 = _bf16_2d(x, shape[-1])
     h = ops.linear_fwd(x2, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
     y = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias)
@@ -144,6 +166,16 @@ def block_forward(blk, x, kv_len=None):
     _check_drop(blk.drop_path1, "drop_path")
     _check_drop(blk.drop_path2, "drop_path")
     B, N, D = x.shape
+    if _needs_grad(x, blk):
+        if _gamma(blk.ls1) is not None or _gamma(blk.ls2) is not None:
+            raise B200Error("training with LayerScale is not supported yet (inference is)")
+        from .autograd import BlockFn
+        _bf16_2d(x, D)
+        n1w, n1b, e1 = _ln_params(blk.norm1)
+        n2w, n2b, e2 = _ln_params(blk.norm2)
+        return BlockFn.apply(x, n1w, n1b, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, n2w, n2b,
+                             _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, kv_len, attn.num_heads, attn.scale,
+                             e1, e2)
     x2 = _bf16_2d(x, D)
     w1, b1, eps1 = _ln_params(blk.norm1)
     h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
@@ -173,6 +205,11 @@ def patch_embed_forward(pe, img):
     if H % ph or W % pw:
         raise AssertionError(f"Input size ({H}x{W}) should be divisible by patch size ({ph}).")
     w = _w(pe.proj)
+    if _needs_grad(None, pe):
+        from .autograd import PatchEmbedFn
+        if img.dtype != torch.bfloat16:
+            raise B200Error("images must be bf16 on the fused path")
+        return PatchEmbedFn.apply(img, w, pe.proj.bias, ph)
     D = w.shape[0]
     K = C * ph * pw
     kpad = (K + 7) // 8 * 8
@@ -207,6 +244,10 @@ def vit_embed(model, img):
     pos = model.pos_embed
     if pos is None and n_prefix == 0:
         x = proj
+    elif torch.is_grad_enabled() and (proj.requires_grad or any(t is not None and t.requires_grad for t in pre + [pos])):
+        from .autograd import TokensFn
+        prefix_t = None if not pre else (pre[0] if len(pre) == 1 else torch.cat(pre, 1))
+        x = TokensFn.apply(proj, prefix_t, pos, not getattr(model, "no_embed_class", False))
     else:
         x = ops.assemble_tokens(proj.view(B * G, D), prefix, None if pos is None else pos.contiguous(), B, G, n_prefix, D,
                                 pos_has_prefix=not getattr(model, "no_embed_class", False))
@@ -248,6 +289,10 @@ def vit_forward_head(model, x, pre_logits=False):
     _check_drop(model.head_drop, "head_drop")
     if pre_logits or _is_identity(model.head):
         return x
+    if _needs_grad(x, model.head):
+        from .autograd import LinearFn
+        _bf16_2d(x, x.shape[-1])
+        return LinearFn.apply(x, _w(model.head), model.head.bias)
     x2 = _bf16_2d(x, x.shape[-1])
     if model.head.weight.shape[0] % 8:
         _w(model.head)

@@ -13,8 +13,8 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
                    GemmDesc)
 
 __all__ = [
-    "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "attention_fwd", "patchify", "assemble_tokens",
-    "colsum", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
+    "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
+    "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
 ]
 
 
@@ -104,9 +104,10 @@ def layernorm_fwd(x, weight, bias, eps, out_dtype=None, save_stats=False):
     return y.view(*x.shape[:-1], cols), mean, rstd
 
 
-def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True):
-    """Returns (dx, dweight fp32, dbias fp32)."""
-    _need_cuda(dy, x, weight, mean, rstd)
+def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True, dres=None):
+    """Returns (dx, dweight fp32, dbias fp32).  dres (dtype/shape of x): gradient of the residual branch around
+    the norm, added into dx in the same pass."""
+    _need_cuda(dy, x, weight, mean, rstd, dres)
     cols = x.shape[-1]
     x2 = x.reshape(-1, cols)
     dy2 = dy.reshape(-1, cols)
@@ -123,8 +124,14 @@ def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True):
     if need_param_grads:
         dw = torch.empty(cols, dtype=torch.float32, device=x.device)
         db = torch.empty(cols, dtype=torch.float32, device=x.device)
+    if dres is not None:
+        dres = dres.reshape(-1, cols)
+        if dres.dtype != x2.dtype or dres.shape != x2.shape:
+            raise B200Error("layernorm_bwd: dres must match x in dtype and shape")
+        if not dres.is_contiguous():
+            dres = dres.contiguous()
     rc = lib.b200_layernorm_bwd(dy2.data_ptr(), x2.data_ptr(), _ptr(weight), mean.data_ptr(), rstd.data_ptr(),
-                                dx.data_ptr(), _ptr(dw), _ptr(db), ws.data_ptr(), rows, cols, _dt(x2), _dt(dy2),
+                                _ptr(dres), dx.data_ptr(), _ptr(dw), _ptr(db), ws.data_ptr(), rows, cols, _dt(x2), _dt(dy2),
                                 _param_dtype(weight), _stream())
     _lib.check(rc, "b200_layernorm_bwd")
     _count(2 if need_param_grads else 1)
@@ -139,12 +146,12 @@ def _check_2d_bf16(t, name):
 
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None, gamma=None, out=None,
-         out_dtype=torch.bfloat16, accumulate=False, split_k=1):
+         out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None):
     """out[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
     """
-    _need_cuda(a, b, bias, aux, gamma, out)
+    _need_cuda(a, b, bias, aux, gamma, out, out2)
     _check_2d_bf16(a, "a")
     _check_2d_bf16(b, "b")
     exp_a = (K, M) if a_mn else (M, K)
@@ -165,6 +172,11 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
         if tuple(aux.shape) != (M, N):
             raise B200Error("gemm: aux must be [M,N]")
         d.ldaux = aux.stride(0)
+    if out2 is not None:
+        _check_2d_bf16(out2, "out2")
+        if tuple(out2.shape) != (M, N):
+            raise B200Error("gemm: out2 must be [M,N]")
+        d.out2, d.ldo2 = out2.data_ptr(), out2.stride(0)
     d.M, d.N, d.K = M, N, K
     d.a_mn, d.b_mn = int(a_mn), int(b_mn)
     d.epilogue = epilogue
@@ -185,11 +197,47 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
     return out
 
 
-def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, out=None):
+def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, out=None, out2=None):
     """F.linear on a [M,K] bf16 activation with a fused epilogue (weight: [N,K] bf16)."""
     M, K = x2d.shape
     N = weight.shape[0]
-    return gemm(x2d, weight, M, N, K, epilogue=epilogue, bias=bias, aux=aux, gamma=gamma, out=out)
+    return gemm(x2d, weight, M, N, K, epilogue=epilogue, bias=bias, aux=aux, gamma=gamma, out=out, out2=out2)
+
+
+def linear_dgrad(dy2d, weight, epilogue=EPI_BIAS, aux=None):
+    """dX[M,K] = dY[M,N] @ W[N,K]  (W consumed MN-major in place; optional GELU' epilogue with aux = pre-activation)."""
+    M, N = dy2d.shape
+    K = weight.shape[1]
+    return gemm(dy2d, weight, M, K, N, b_mn=True, epilogue=epilogue, aux=aux)
+
+
+def _wgrad_split(rows_out, cols_out, k):
+    """Split-K factor that fills the SMs: tiles of 128 x 256 (or 128 x 128 when cols <= 128)."""
+    tiles = ((rows_out + 127) // 128) * ((cols_out + 255) // 256 if cols_out > 128 else 1)
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    split = max(1, min(sms // max(tiles, 1), (k + 4095) // 4096))
+    return split
+
+
+def linear_wgrad(dy2d, x2d, grad_out=None):
+    """dW[N,K] = dY[M,N]^T @ X[M,K] in fp32 (both operands MN-major in place, split-K through TMA reduce-add),
+    then handed to `grad_out` (the parameter's .grad buffer, bf16 or fp32): accumulated when it already exists."""
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    ws = torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)
+    gemm(dy2d, x2d, N, K, M, a_mn=True, b_mn=True, out=ws, split_k=max(2, _wgrad_split(N, K, M)))
+    return ws
+
+
+def convert_f32(src, dst, accumulate=False):
+    """dst (bf16 / fp32) (+)= src (fp32), element count a multiple of 4."""
+    _need_cuda(src, dst)
+    if src.dtype != torch.float32 or not src.is_contiguous() or not dst.is_contiguous() or src.numel() != dst.numel():
+        raise B200Error("convert_f32: need contiguous tensors of equal size, fp32 source")
+    rc = _lib.load().b200_convert_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _dt(dst), int(accumulate), _stream())
+    _lib.check(rc, "b200_convert_f32")
+    _count()
+    return dst
 
 
 # --------------------------------------------------------------------------------------------- attention
@@ -207,6 +255,23 @@ def attention_fwd(qkv, B, N, H, hd, scale, kv_len=None, need_lse=False):
     _lib.check(rc, "b200_attn_fwd")
     _count()
     return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None):
+    """dqkv [B,N,3*H*hd] bf16 from dout [B,N,H*hd]; recomputes P from qkv and the saved log-sum-exp."""
+    _need_cuda(qkv, out, dout, lse, kv_len)
+    for t, n, name in ((qkv, B * N * 3 * H * hd, "qkv"), (out, B * N * H * hd, "out"), (dout, B * N * H * hd, "dout")):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.numel() != n:
+            raise B200Error(f"attention_bwd: {name} must be a contiguous bf16 buffer of {n} elements")
+    if lse.dtype != torch.float32 or not lse.is_contiguous() or lse.numel() != B * H * N:
+        raise B200Error("attention_bwd: lse must be contiguous fp32 [B,H,N]")
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
+    rc = _lib.load().b200_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                   dqkv.data_ptr(), _ptr(kv_len), B, N, H, hd, float(scale), _stream())
+    _lib.check(rc, "b200_attn_bwd")
+    _count(2)
+    return dqkv
 
 
 # --------------------------------------------------------------------------------------------- patch embed helpers

@@ -29,7 +29,7 @@ def _fast(x):
             and not torch.jit.is_tracing() and not (torch.is_grad_enabled() and _GRAD_UNSUPPORTED))
 
 
-_GRAD_UNSUPPORTED = True   # flipped by b200timm.autograd once the training path is registered
+_GRAD_UNSUPPORTED = False  # the training path (b200timm.autograd) covers grad-enabled calls; uncovered configs raise B200Error -> timm
 
 
 def _dispatch(name, fast_fn):

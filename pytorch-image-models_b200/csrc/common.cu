@@ -83,7 +83,7 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* bas
 }  // namespace b200
 
 extern "C" const char* b200_last_error(void) { return b200::g_err; }
-extern "C" int b200_abi_version(void) { return 1; }
+extern "C" int b200_abi_version(void) { return 2; }
 
 extern "C" int b200_device_check(void) {
   int dev = 0;

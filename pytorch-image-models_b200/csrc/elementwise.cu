@@ -133,6 +133,28 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
   if (blockIdx.x * 256 + c < cols) atomicAdd(out + blockIdx.x * 256 + c, s);
 }
 
+// dst (bf16 or fp32) (+)= src fp32  -- weight-gradient hand-off from the fp32 split-K workspace to .grad
+template <bool DST_F32>
+__global__ void convert_kernel(const float* __restrict__ src, void* __restrict__ dst, long long n, int accumulate) {
+  const long long nvec = n >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    if (DST_F32) {
+      float4* d = reinterpret_cast<float4*>(dst) + i;
+      if (accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      *d = v;
+    } else {
+      uint2* d = reinterpret_cast<uint2*>(dst) + i;
+      if (accumulate) {
+        const uint2 o = *d;
+        v.x += bf16_lo(o.x); v.y += bf16_hi(o.x); v.z += bf16_lo(o.y); v.w += bf16_hi(o.y);
+      }
+      *d = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -191,7 +213,17 @@ extern "C" int b200_colsum(const void* x, float* out, int64_t rows, int32_t cols
   return B200_OK;
 }
 
-extern "C" int b200_attn_bwd(const void*, const void*, const void*, const float*, float*, void*, const int32_t*,
-                             int32_t, int32_t, int32_t, int32_t, float, void*) {
-  return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: not implemented yet");
+extern "C" int b200_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, int32_t accumulate,
+                                void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(src && dst, "b200_convert_f32: null pointer");
+  B200_CHECK_ARG(n > 0 && n % 4 == 0, "b200_convert_f32: n=%lld must be a positive multiple of 4", (long long)n);
+  const int threads = 256;
+  long long blocks = (n / 4 + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (dst_dtype == B200_DTYPE_F32) convert_kernel<true><<<static_cast<int>(blocks), threads, 0, st>>>(src, dst, n, accumulate);
+  else convert_kernel<false><<<static_cast<int>(blocks), threads, 0, st>>>(src, dst, n, accumulate);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
 }

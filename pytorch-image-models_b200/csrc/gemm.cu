@@ -26,6 +26,7 @@ constexpr int kNumThreads = 128 + kNumEpiWarps * 32;
 
 struct GemmKernelParams {
   void* out;
+  void* out2;
   const void* bias;
   const __nv_bfloat16* aux;
   const void* gamma;
@@ -47,37 +48,37 @@ struct GemmSmem {
   static constexpr int kTotal = kBarrierOffset + 256 + 1024;  // + barriers + alignment slack
 };
 
-// Shared part of GELU / GELU':  for a pair x returns erf(x / sqrt2) and e = exp(-x^2 / 2).
-// erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): 1 - (a1 t + .. + a5 t^5) exp(-z^2), t = 1/(1 + p z), z = |x|/sqrt2.
-__device__ __forceinline__ void erf_pair(f32x2 x, f32x2& erf_v, f32x2& e) {
+// erf(x / sqrt2) for a pair, Abramowitz-Stegun 7.1.28:  erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| < 3e-7.
+// One MUFU (rcp) per element; for large |z| the power overflows to +inf and rcp gives 0, i.e. erf -> 1.
+__device__ __forceinline__ f32x2 erf_pair(f32x2 x) {
   float x0, x1;
   upk(x, x0, x1);
   const f32x2 z = pk(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+  f32x2 q = fma2(z, splat(0.0000430638f), splat(0.0002765672f));
+  q = fma2(q, z, splat(0.0001520143f));
+  q = fma2(q, z, splat(0.0092705272f));
+  q = fma2(q, z, splat(0.0422820123f));
+  q = fma2(q, z, splat(0.0705230784f));
+  q = fma2(q, z, splat(1.0f));
+  q = mul2(q, q);
+  q = mul2(q, q);
+  q = mul2(q, q);
+  q = mul2(q, q);
   float d0, d1;
-  upk(fma2(z, splat(0.3275911f), splat(1.0f)), d0, d1);
-  const f32x2 t = pk(rcp_approx(d0), rcp_approx(d1));
-  f32x2 q = fma2(t, splat(-1.061405429f), splat(1.453152027f));   // -(a1 t + ... ) with negated coefficients
-  q = fma2(q, t, splat(-1.421413741f));
-  q = fma2(q, t, splat(0.284496736f));
-  q = fma2(q, t, splat(-0.254829592f));
-  q = mul2(q, t);
-  float w0, w1;
-  upk(mul2(mul2(z, z), splat(-1.4426950408889634f)), w0, w1);
-  e = pk(ex2_approx(w0), ex2_approx(w1));                          // exp(-z^2) = exp(-x^2 / 2)
-  float a0, a1;
-  upk(fma2(q, e, splat(1.0f)), a0, a1);                            // erf(|x| / sqrt2)
-  erf_v = pk(copysignf(a0, x0), copysignf(a1, x1));
+  upk(q, d0, d1);
+  const float a0 = 1.0f - rcp_approx(d0), a1 = 1.0f - rcp_approx(d1);
+  return pk(copysignf(a0, x0), copysignf(a1, x1));
 }
 __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
-  f32x2 erf_v, e;
-  erf_pair(x, erf_v, e);
-  return mul2(x, fma2(erf_v, splat(0.5f), splat(0.5f)));           // 0.5 x (1 + erf)
+  return mul2(x, fma2(erf_pair(x), splat(0.5f), splat(0.5f)));     // 0.5 x (1 + erf(x / sqrt2))
 }
 __device__ __forceinline__ f32x2 dgelu_erf2(f32x2 x) {
-  f32x2 erf_v, e;
-  erf_pair(x, erf_v, e);
-  const f32x2 cdf = fma2(erf_v, splat(0.5f), splat(0.5f));
-  return fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);        // Phi(x) + x phi(x)
+  // d/dx [x Phi(x)] = Phi(x) + x phi(x),  phi(x) = exp(-x^2 / 2) / sqrt(2 pi)
+  const f32x2 cdf = fma2(erf_pair(x), splat(0.5f), splat(0.5f));
+  float w0, w1;
+  upk(mul2(mul2(x, x), splat(-0.72134752044448170f)), w0, w1);     // -x^2/2 * log2(e)
+  const f32x2 e = pk(ex2_approx(w0), ex2_approx(w1));
+  return fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);
 }
 
 // 8 consecutive parameters (bias / LayerScale gamma) starting at column `col`, as 4 fp32 pairs
@@ -96,7 +97,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
-                 const GemmKernelParams p) {
+                 const __grid_constant__ CUtensorMap tmap_out2, const GemmKernelParams p) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,6 +125,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int i = 0; i < kNumEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     tma_prefetch_desc(&tmap_out);
     tma_prefetch_desc(&tmap_aux);
+    tma_prefetch_desc(&tmap_out2);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -219,6 +221,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     const bool has_aux = p.epilogue == B200_EPI_BIAS_RESIDUAL || p.epilogue == B200_EPI_DGELU;
     const bool reduce_out = p.out_f32 && (p.accumulate || p.split_k > 1);
+    const bool dual = p.out2 != nullptr;   // training fc1: out2 <- pre-activation, out <- GELU(pre-activation)
     const int round_cols = p.out_f32 ? 32 : 64;   // 128-byte rows of the staging tile
     uint32_t aux_phase = 0;
     int as = 0;
@@ -289,7 +292,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                   for (int j = 0; j < 4; ++j) v[j] = add2(v[j], bv[j]);
                 }
-                if (p.epilogue == B200_EPI_BIAS_GELU) {
+                if (p.epilogue == B200_EPI_BIAS_GELU && !dual) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
                 } else if (has_aux) {
@@ -327,6 +330,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (rc + round_cols >= kColsPerWarp) {  // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
           mbar_arrive(&tempty_bar[as]);
+        }
+        if (dual) {
+          // the staging tile holds the bf16 pre-activation: store it to out2, then apply GELU to exactly those
+          // bf16 values (what the backward's GELU' will see) in place and store the result to out
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (col0 < p.N && row0 < p.M) {
+              tma_store_2d(&tmap_out2, stg, col0, row0);
+              tma_store_commit();
+            }
+            tma_store_wait_read<0>();
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = stg_row + ((static_cast<uint32_t>(j) ^ sw) << 4);
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float lo, hi;
+              upk(gelu_erf2(bf16x2_to_f32x2(w[i])), lo, hi);
+              o[i] = pack_bf16(lo, hi);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+          }
         }
         fence_proxy_async_smem();  // staging writes (generic proxy) -> visible to the TMA store (async proxy)
         __syncwarp();
@@ -368,7 +400,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
     rc = encode_tmap_bf16(&tb, d.b, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  CUtensorMap tout, taux;
+  CUtensorMap tout, taux, tout2;
   {
     // out / aux: dims {N, M}; box = one 128-byte-wide, 32-row staging tile
     const bool of32 = d.out_dtype == B200_DTYPE_F32;
@@ -386,9 +418,17 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
     } else {
       taux = tout;
     }
+    if (d.out2 != nullptr) {
+      uint64_t ostr[1] = {static_cast<uint64_t>(d.ldo2) * 2};
+      uint32_t obox[2] = {64u, 32u};
+      rc = encode_tmap_bf16(&tout2, d.out2, 2, dims, ostr, obox, true);
+      if (rc) return rc;
+    } else {
+      tout2 = tout;
+    }
   }
   GemmKernelParams p;
-  p.out = d.out; p.bias = d.bias; p.aux = reinterpret_cast<const __nv_bfloat16*>(d.aux); p.gamma = d.gamma;
+  p.out = d.out; p.out2 = d.out2; p.bias = d.bias; p.aux = reinterpret_cast<const __nv_bfloat16*>(d.aux); p.gamma = d.gamma;
   p.ldo = d.ldo; p.ldaux = d.ldaux;
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.num_m_blocks = (d.M + BM - 1) / BM;
@@ -411,7 +451,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
   int grid = sm_count();
   if (grid > num_tiles) grid = num_tiles;
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, tout, taux, p);
+  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, tout, taux, tout2, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
@@ -443,6 +483,10 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
                        (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0,
                    "b200_gemm: epilogue %d needs a 16-byte aligned aux with ldaux %% 8 == 0", d.epilogue);
   }
+  if (d.out2 != nullptr)
+    B200_CHECK_ARG(d.epilogue == B200_EPI_BIAS_GELU && d.out_dtype == B200_DTYPE_BF16 && d.ldo2 % 8 == 0 &&
+                       d.ldo2 >= d.N && (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0,
+                   "b200_gemm: out2 (pre-activation) needs the GELU epilogue, bf16 output and 16-byte aligned rows");
   if (d.bias) B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "b200_gemm: bias must be 16-byte aligned");
   if (d.gamma) B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d.gamma) & 15) == 0, "b200_gemm: gamma must be 16-byte aligned");
   if (d.accumulate) B200_CHECK_ARG(d.out_dtype == B200_DTYPE_F32, "b200_gemm: accumulate needs an fp32 output");

@@ -114,7 +114,8 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ w, con
 template <int VPL, bool XF32, bool DYF32>
 __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const void* __restrict__ w,
-                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, void* __restrict__ dx,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     const void* __restrict__ dres, void* __restrict__ dx,
                      float* __restrict__ ws, long long rows, int cols, int param_f32) {
   extern __shared__ float red[];  // [kLnWarps][2*cols]
   const int lane = threadIdx.x & 31;
@@ -164,6 +165,12 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - m1 - xh[i][j] * m2);
+        if (dres != nullptr) {   // gradient arriving through the residual branch around this LayerNorm
+          float rv[8];
+          load8<XF32>(dres, row * cols + vec * 8, rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
         store8<XF32>(dx, row * cols + vec * 8, o);
       }
     }
@@ -223,8 +230,8 @@ static void launch_fwd(const void* x, const void* w, const void* b, void* y, flo
 }
 
 template <int VPL>
-static int launch_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
-                      float* ws, long long rows, int cols, int xf32, int dyf32, int pf32, cudaStream_t st) {
+static int launch_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                      const void* dres, void* dx, float* ws, long long rows, int cols, int xf32, int dyf32, int pf32, cudaStream_t st) {
   const int grid = ln_bwd_grid(rows);
   const int threads = kLnWarps * 32;
   const size_t smem = static_cast<size_t>(kLnWarps) * 2 * cols * sizeof(float);
@@ -235,10 +242,10 @@ static int launch_bwd(const void* dy, const void* x, const void* w, const float*
     else if (dyf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, false, true>));
     else B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, false, false>));
   }
-  if (xf32 && dyf32) layernorm_bwd_kernel<VPL, true, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
-  else if (xf32) layernorm_bwd_kernel<VPL, true, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
-  else if (dyf32) layernorm_bwd_kernel<VPL, false, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
-  else layernorm_bwd_kernel<VPL, false, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dx, ws, rows, cols, pf32);
+  if (xf32 && dyf32) layernorm_bwd_kernel<VPL, true, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
+  else if (xf32) layernorm_bwd_kernel<VPL, true, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
+  else if (dyf32) layernorm_bwd_kernel<VPL, false, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
+  else layernorm_bwd_kernel<VPL, false, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
   return B200_OK;
 }
 
@@ -275,7 +282,8 @@ extern "C" int b200_layernorm_bwd_ws_rows(int64_t rows, int32_t cols) {
 }
 
 extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* weight, const float* mean,
-                                  const float* rstd, void* dx, float* dweight, float* dbias, float* workspace,
+                                  const float* rstd, const void* dres, void* dx, float* dweight, float* dbias,
+                                  float* workspace,
                                   int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
                                   int32_t param_dtype, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
@@ -287,12 +295,12 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* wei
   const int xf = x_dtype == B200_DTYPE_F32, dyf = dy_dtype == B200_DTYPE_F32, pf = param_dtype == B200_DTYPE_F32;
   int rc;
   switch (vpl) {
-    case 1: rc = launch_bwd<1>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
-    case 2: rc = launch_bwd<2>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
-    case 3: rc = launch_bwd<3>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
-    case 4: rc = launch_bwd<4>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
-    case 5: case 6: rc = launch_bwd<6>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
-    default: rc = launch_bwd<8>(dy, x, weight, mean, rstd, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 1: rc = launch_bwd<1>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 2: rc = launch_bwd<2>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 3: rc = launch_bwd<3>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 4: rc = launch_bwd<4>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    case 5: case 6: rc = launch_bwd<6>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;
+    default: rc = launch_bwd<8>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;
   }
   if (rc) return rc;
   B200_CUDA_OK(cudaGetLastError());

@@ -218,3 +218,81 @@ def test_assemble_tokens_and_colsum():
     assert torch.equal(tok.float(), ref.bfloat16().float())
     x = torch.randn(5000, 776, device=DEV, generator=g).bfloat16()
     _close(ops.colsum(x), x.float().sum(0), 2e-2, 1e-4, "colsum")
+
+
+# ------------------------------------------------------------------------------------------------ backward kernels
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 64, 2), (2, 208, 3), (2, 129, 2), (1, 17, 1)])
+def test_attention_bwd(B, N, H):
+    """dq/dk/dv against PyTorch autograd of the fp32 restatement of attention.py:115-135."""
+    ops = _ops()
+    hd = 64
+    g = torch.Generator(device=DEV).manual_seed(100 + N + H)
+    qkv = torch.randn(B, N, 3 * H * hd, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B, N, H * hd, device=DEV, generator=g).bfloat16()
+    scale = hd ** -0.5
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, scale, need_lse=True)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale)
+    ref_in = qkv.float().requires_grad_(True)
+    ref_out, _ = _attn_ref(ref_in, B, N, H, hd, scale)
+    ref_out.backward(dout.float())
+    _close(dqkv, ref_in.grad, 2e-2, 2e-2, f"attention bwd B={B} N={N} H={H}")
+
+
+def test_attention_bwd_key_padding():
+    ops = _ops()
+    B, N, H, hd = 4, 197, 3, 64
+    g = torch.Generator(device=DEV).manual_seed(7)
+    qkv = torch.randn(B, N, 3 * H * hd, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B, N, H * hd, device=DEV, generator=g).bfloat16()
+    kv_len = torch.tensor([N, 1, 100, 130], device=DEV, dtype=torch.int32)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, 0.125, kv_len=kv_len, need_lse=True)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125, kv_len=kv_len)
+    ref_in = qkv.float().requires_grad_(True)
+    ref_out, _ = _attn_ref(ref_in, B, N, H, hd, 0.125, kv_len)
+    ref_out.backward(dout.float())
+    _close(dqkv, ref_in.grad, 2e-2, 2e-2, "masked attention bwd")
+
+
+def test_gemm_dual_output_and_dgrad_wgrad():
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(21)
+    M, N, K = 1576, 3072, 768
+    x = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.03).bfloat16()
+    b = torch.randn(N, device=DEV, generator=g).bfloat16()
+    pre = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    act = ops.linear_fwd(x, w, b, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+    ref_pre = x.float() @ w.float().t() + b.float()
+    _close(pre, ref_pre, 2e-2, 1e-2, "pre-activation (out2)")
+    assert torch.equal(act.float(), _gelu(pre.float()).bfloat16().float()) or \
+        (act.float() - _gelu(pre.float())).abs().max() < 2e-2   # GELU applied to the stored bf16 pre-activation
+    dy = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    _close(ops.linear_dgrad(dy, w), dy.float() @ w.float(), 5e-2, 1e-2, "dgrad")
+    da = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w2 = (torch.randn(K, N, device=DEV, generator=g) * 0.03).bfloat16()   # fc2 weight [K_out=768, N=3072]
+    _close(ops.linear_dgrad(da, w2, epilogue=ops.EPI_DGELU, aux=pre), (da.float() @ w2.float()) * _dgelu(pre.float()),
+           5e-2, 2e-2, "dgrad + GELU'")
+    _close(ops.linear_wgrad(dy, x), dy.float().t() @ x.float(), 5e-2, 2e-3, "wgrad (split-K, fp32)")
+    gbuf = torch.randn(N, K, device=DEV, generator=g).bfloat16()
+    before = gbuf.float().clone()
+    ws = ops.linear_wgrad(dy, x)
+    ops.convert_f32(ws, gbuf, accumulate=True)
+    _close(gbuf, before + ws, 0.5, 1e-2, "convert_f32 accumulate into bf16 grad")
+
+
+def test_layernorm_bwd_with_residual_gradient():
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(4)
+    rows, cols = 777, 768
+    x = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    w = torch.randn(cols, device=DEV, generator=g).bfloat16()
+    b = torch.randn(cols, device=DEV, generator=g).bfloat16()
+    dy = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    dres = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    _, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-6, save_stats=True)
+    dx0, _, _ = ops.layernorm_bwd(dy, x, w, mean, rstd)
+    dx1, _, _ = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres)
+    xr = x.float().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (cols,), w.float(), b.float(), 1e-6).backward(dy.float())
+    _close(dx1, xr.grad + dres.float(), 4e-2, 1e-2, "ln bwd + residual grad")
+    _close(dx0, xr.grad, 3e-2, 1e-2, "ln bwd")

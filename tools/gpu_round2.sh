@@ -14,6 +14,6 @@ run bench 600 python bench.py --steps 20 --warmup 5
 run bench_ref 600 python bench.py --impl reference --steps 5 --warmup 1
 KREG='regex:gemm_bf16|layernorm_|attn_fwd|patchify|assemble_tokens'
 run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 267 -c 178 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline
-run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 150 -c 4 -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 150 -c 5 -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline
 run ncu_attn 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 36 -c 1 -o gpurun_out/prof_attn python bench.py --steps 2 --warmup 3 --no-cpu-baseline
 cat gpurun_out/summary.txt
