@@ -119,6 +119,18 @@ B200_API int b200_assemble_tokens(const void* proj, const void* prefix, const vo
                          int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype,
                          int32_t pos_has_prefix, void* stream);
 
+/* ------------------------------------------------------------------ ConvNeXt (channels-last activations [B,H,W,C] bf16)
+ * Depthwise k x k convolution, stride 1, zero padding k/2, + bias: F.conv2d(groups=C) of timm/models/convnext.py:
+ * 173-182,200 evaluated NHWC so the permutes of :205,208 disappear.  weight: bf16 [C,1,k,k]; k in {3,5,7}.      */
+B200_API int b200_dwconv_nhwc(const void* x, const void* weight, const void* bias, void* y, int32_t B, int32_t H,
+                     int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype, void* stream);
+/* out[(b,oy,ox), (ky*p+kx)*C + c] = x[b, oy*p+ky, ox*p+kx, c]: the gather of the p x p / stride p downsample conv
+ * (convnext.py:263-275); the GEMM then uses the conv weight permuted to [Cout, ky, kx, Cin].                   */
+B200_API int b200_patchify_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t p,
+                       void* stream);
+/* out[b, c] = mean_hw x[b, hw, c]   (SelectAdaptivePool2d('avg'), timm/layers/classifier.py:211-213).            */
+B200_API int b200_avgpool_nhwc(const void* x, void* out, int32_t B, int32_t HW, int32_t C, void* stream);
+
 /* ------------------------------------------------------------------ elementwise / reductions
  * dst[i] (+)= src[i]: fp32 -> bf16/fp32 hand-off of split-K weight gradients into .grad (n % 4 == 0).        */
 B200_API int b200_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, int32_t accumulate,

@@ -56,6 +56,34 @@ def vit_case(name, seed, batch, kwargs, backward=True):
           "params", sum(p.numel() for p in model.parameters()))
 
 
+def convnext_case(name, seed, batch, kwargs, img_size):
+    import timm
+    from timm.models.convnext import ConvNeXt
+    torch.manual_seed(seed)
+    model = ConvNeXt(**kwargs)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:   # biases, norm weights, LayerScale gamma (1e-6 by default would hide the branch)
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+            if n.endswith("gamma"):
+                p.add_(0.5)
+    model.eval()
+    img = torch.randn(batch, 3, img_size, img_size, generator=g)
+    stage_out = []
+    hooks = [s.register_forward_hook(lambda m, i, o: stage_out.append(o.detach().clone())) for s in model.stages]
+    feats = model.forward_features(img)
+    logits = model.forward_head(feats)
+    for h in hooks:
+        h.remove()
+    fx = {"kind": "convnext", "kwargs": kwargs, "state_dict": _half_sd(model.state_dict()), "img": img,
+          "features": feats.detach(), "logits": logits.detach(), "stage_outputs": stage_out,
+          "timm_version": timm.__version__, "torch_version": str(torch.__version__)}
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, "logits", tuple(logits.shape), "absmax", logits.abs().max().item(),
+          "params", sum(p.numel() for p in model.parameters()))
+
+
 def layer_cases():
     from timm.layers import Attention, LayerNorm, Mlp, PatchEmbed, LayerScale, DropPath
     from timm.models.naflexvit import create_attention_mask
@@ -109,6 +137,7 @@ def main():
     vit_case("vit_g3_prenorm_noembedclass", 2, 2,
              dict(img_size=56, patch_size=14, in_chans=3, num_classes=5, embed_dim=64, depth=1, num_heads=1,
                   qkv_bias=True, pre_norm=True, no_embed_class=True), backward=False)
+    convnext_case("convnext_g1", 3, 2, dict(depths=(1, 1, 2, 1), dims=(16, 32, 64, 128), num_classes=10), 64)
     layer_cases()
 
 

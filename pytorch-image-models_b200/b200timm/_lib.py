@@ -69,6 +69,9 @@ SIGNATURES = {
     "b200_patchify": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_assemble_tokens": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_colsum": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "b200_dwconv_nhwc": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200_patchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200_avgpool_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

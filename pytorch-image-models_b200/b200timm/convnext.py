@@ -1,0 +1,246 @@
+"""Mirror of timm's ConvNeXt (timm/models/convnext.py: ConvNeXtBlock :117-213, ConvNeXtStage :216-307,
+ConvNeXt :338-629, NormMlpClassifierHead timm/layers/classifier.py:145-220) for the hot-path configuration:
+patch stem, LayerNorm, nn.Linear MLP with exact GELU, LayerScale `gamma`, avg-pool head.  Same module / parameter
+names as timm (``stem.0/1``, ``stages.i.downsample.0/1``, ``stages.i.blocks.j.{gamma,conv_dw,norm,mlp.fc1,mlp.fc2}``,
+``head.norm``, ``head.fc``), so timm checkpoints load with strict=True.
+
+B200 execution (inference): the network runs channels-last end to end -- activations are [B*H*W, C] bf16 rows --
+    stem        patch gather (NCHW image) + GEMM + LayerNorm kernel
+    block       depthwise 7x7 kernel (NHWC) -> LayerNorm kernel -> fc1 GEMM with fused bias+GELU ->
+                fc2 GEMM with fused bias, LayerScale gamma and the shortcut add           (convnext.py:197-213)
+    downsample  LayerNorm kernel -> 2x2 gather -> GEMM (conv weight permuted once to [Cout, ky, kx, Cin])
+    head        avg-pool kernel -> LayerNorm kernel -> GEMM
+so the permutes of convnext.py:205,208 and LayerNorm2d's permute/permute (norm.py:127-134) never happen.
+"""
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import B200Error
+from .layers import DropPath, Mlp
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """timm.layers.LayerNorm2d (norm.py:113-134): LayerNorm over C of an NCHW tensor.  Parameter holder here --
+    the fused forward applies it on channels-last rows."""
+
+    def __init__(self, num_channels: int, eps: float = 1e-6, affine: bool = True, device=None, dtype=None):
+        super().__init__(num_channels, eps=eps, elementwise_affine=affine, device=device, dtype=dtype)
+
+    def forward(self, x):
+        raise B200Error("LayerNorm2d is applied channels-last inside ConvNeXt.forward; standalone NCHW use is not covered")
+
+
+class ConvNeXtBlock(nn.Module):
+    def __init__(self, in_chs: int, out_chs: Optional[int] = None, kernel_size: int = 7, stride: int = 1,
+                 dilation=(1, 1), mlp_ratio: float = 4, conv_mlp: bool = False, conv_bias: bool = True,
+                 use_grn: bool = False, ls_init_value: Optional[float] = 1e-6, act_layer=nn.GELU, norm_layer=None,
+                 drop_path: float = 0., device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        out_chs = out_chs or in_chs
+        if conv_mlp or use_grn or stride != 1 or in_chs != out_chs or tuple(dilation) != (1, 1):
+            raise B200Error("ConvNeXtBlock: conv_mlp / GRN / strided / dilated blocks are not covered")
+        self.use_conv_mlp = False
+        self.conv_dw = nn.Conv2d(in_chs, out_chs, kernel_size, stride=1, padding=kernel_size // 2, groups=in_chs,
+                                 bias=conv_bias, **dd)
+        self.norm = (norm_layer or nn.LayerNorm)(out_chs, **dd)
+        self.mlp = Mlp(out_chs, int(mlp_ratio * out_chs), act_layer=act_layer, **dd)
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(out_chs, **dd)) if ls_init_value is not None else None
+        self.shortcut = nn.Identity()
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+
+    def forward_nhwc(self, x, B, H, W):
+        """x: [B*H*W, C] bf16 rows (channels-last).  convnext.py:197-213 without the permutes."""
+        C = x.shape[1]
+        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
+            raise B200Error("ConvNeXt DropPath in training mode is not covered")
+        y = ops.dwconv_nhwc(x.view(B, H, W, C), self.conv_dw.weight, self.conv_dw.bias).view(B * H * W, C)
+        h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+        a = ops.linear_fwd(h, self.mlp.fc1.weight, self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+        return ops.linear_fwd(a, self.mlp.fc2.weight, self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
+                              gamma=self.gamma)
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        rows = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
+        return self.forward_nhwc(rows, B, H, W).view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+class ConvNeXtStage(nn.Module):
+    def __init__(self, in_chs, out_chs, kernel_size=7, stride=2, depth=2, dilation=(1, 1), drop_path_rates=None,
+                 ls_init_value=1.0, conv_mlp=False, conv_bias=True, use_grn=False, act_layer=nn.GELU, norm_layer=None,
+                 norm_layer_cl=None, device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        self.grad_checkpointing = False
+        if in_chs != out_chs or stride > 1:
+            ds_ks = 2 if stride > 1 else 1
+            self.downsample = nn.Sequential(
+                (norm_layer or LayerNorm2d)(in_chs, **dd),
+                nn.Conv2d(in_chs, out_chs, kernel_size=ds_ks, stride=stride, bias=conv_bias, **dd))
+            in_chs = out_chs
+        else:
+            self.downsample = nn.Identity()
+        drop_path_rates = drop_path_rates or [0.] * depth
+        self.blocks = nn.Sequential(*[
+            ConvNeXtBlock(in_chs=out_chs, out_chs=out_chs, kernel_size=kernel_size, drop_path=drop_path_rates[i],
+                          ls_init_value=ls_init_value, conv_bias=conv_bias, act_layer=act_layer,
+                          norm_layer=norm_layer_cl, **dd)
+            for i in range(depth)])
+
+    def forward_nhwc(self, x, B, H, W):
+        if not isinstance(self.downsample, nn.Identity):
+            norm, conv = self.downsample[0], self.downsample[1]
+            p = conv.kernel_size[0]
+            C = x.shape[1]
+            h = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps)[0]
+            w2 = _conv_weight_khwc(conv)
+            if p > 1:
+                h = ops.patchify_nhwc(h.view(B, H, W, C), p)
+                H, W = H // p, W // p
+            x = ops.linear_fwd(h, w2, conv.bias)
+        for blk in self.blocks:
+            x = blk.forward_nhwc(x, B, H, W)
+        return x, H, W
+
+
+def _conv_weight_khwc(conv):
+    """Conv2d weight [Cout, Cin, kh, kw] -> cached contiguous [Cout, kh*kw*Cin] matching patchify_nhwc's k order."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version)
+    cache = getattr(conv, "_b200_khwc", None)
+    if cache is None or cache[0] != key:
+        conv._b200_khwc = (key, w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
+        cache = conv._b200_khwc
+    return cache[1]
+
+
+class NormMlpClassifierHead(nn.Module):
+    """timm.layers.NormMlpClassifierHead (classifier.py:145-220) without the optional hidden layer."""
+
+    def __init__(self, in_features, num_classes, hidden_size=None, pool_type="avg", drop_rate=0., norm_layer=None,
+                 act_layer=None, device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        if hidden_size or pool_type != "avg":
+            raise B200Error("NormMlpClassifierHead: hidden layer / non-avg pooling are not covered")
+        self.in_features = self.num_features = in_features
+        self.norm = (norm_layer or LayerNorm2d)(in_features, **dd)
+        self.drop = nn.Dropout(drop_rate)
+        self.fc = nn.Linear(in_features, num_classes, **dd) if num_classes > 0 else nn.Identity()
+
+    def forward_nhwc(self, x, B, HW, pre_logits=False):
+        pooled = ops.avgpool_nhwc(x.view(B, HW, -1))
+        h = ops.layernorm_fwd(pooled, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+        if pre_logits or isinstance(self.fc, nn.Identity):
+            return h
+        from .functional import _padded_out_linear
+        if self.fc.weight.shape[0] % 8:
+            return _padded_out_linear(self.fc, h)
+        return ops.linear_fwd(h, self.fc.weight, self.fc.bias)
+
+
+class ConvNeXt(nn.Module):
+    """timm.models.ConvNeXt (convnext.py:338-629), patch stem / LayerNorm / Linear-MLP configuration."""
+
+    def __init__(self, in_chans: int = 3, num_classes: int = 1000, global_pool: str = "avg", output_stride: int = 32,
+                 depths: Tuple[int, ...] = (3, 3, 9, 3), dims: Tuple[int, ...] = (96, 192, 384, 768), kernel_sizes=7,
+                 ls_init_value: Optional[float] = 1e-6, stem_type: str = "patch", patch_size: int = 4,
+                 head_init_scale: float = 1., head_norm_first: bool = False, head_hidden_size=None,
+                 conv_mlp: bool = False, conv_bias: bool = True, use_grn: bool = False, act_layer=None,
+                 norm_layer=None, norm_eps: Optional[float] = None, drop_rate: float = 0., drop_path_rate: float = 0.,
+                 device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        if (stem_type != "patch" or output_stride != 32 or head_norm_first or conv_mlp or use_grn or norm_layer
+                or global_pool != "avg" or (act_layer not in (None, "gelu", nn.GELU))):
+            raise B200Error("ConvNeXt: only the patch-stem / LayerNorm / Linear-MLP / GELU / avg-pool configuration "
+                            "is covered by the B200 path")
+        eps = norm_eps if norm_eps is not None else 1e-6
+        ks = kernel_sizes if isinstance(kernel_sizes, (tuple, list)) else (kernel_sizes,) * 4
+        ln2d = lambda c, **kw: LayerNorm2d(c, eps=eps, **kw)        # noqa: E731
+        ln = lambda c, **kw: nn.LayerNorm(c, eps=eps, **kw)         # noqa: E731
+        self.num_classes, self.in_chans, self.drop_rate = num_classes, in_chans, drop_rate
+        self.stem = nn.Sequential(nn.Conv2d(in_chans, dims[0], kernel_size=patch_size, stride=patch_size,
+                                            bias=conv_bias, **dd), ln2d(dims[0], **dd))
+        total = sum(depths)
+        rates = [x.item() for x in torch.linspace(0, drop_path_rate, total)]
+        stages, prev, k = [], dims[0], 0
+        for i in range(4):
+            stages.append(ConvNeXtStage(prev, dims[i], kernel_size=ks[i], stride=2 if i > 0 else 1, depth=depths[i],
+                                        drop_path_rates=rates[k:k + depths[i]], ls_init_value=ls_init_value,
+                                        conv_bias=conv_bias, act_layer=nn.GELU, norm_layer=ln2d, norm_layer_cl=ln, **dd))
+            k += depths[i]
+            prev = dims[i]
+        self.stages = nn.Sequential(*stages)
+        self.num_features = self.head_hidden_size = prev
+        self.norm_pre = nn.Identity()
+        self.head = NormMlpClassifierHead(prev, num_classes, pool_type=global_pool, drop_rate=drop_rate,
+                                          norm_layer=ln2d, **dd)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        """timm/models/convnext.py _init_weights: trunc_normal(.02) conv / linear weights, zero biases."""
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            nn.init.trunc_normal_(m.weight, std=.02, a=-2., b=2.)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+    def get_classifier(self):
+        return self.head.fc
+
+    def _features_nhwc(self, img):
+        if not img.is_cuda:
+            raise B200Error("libb200timm kernels need CUDA tensors (there is no CPU path)")
+        if img.dtype != torch.bfloat16 or self.stem[0].weight.dtype != torch.bfloat16:
+            raise B200Error("ConvNeXt B200 path needs bf16 inputs and weights (model.to(torch.bfloat16))")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise B200Error("ConvNeXt training (backward) is not covered yet; wrap inference in torch.no_grad()")
+        conv, norm = self.stem[0], self.stem[1]
+        p = conv.kernel_size[0]
+        B, C, H, W = img.shape
+        if H % p or W % p:
+            raise B200Error("image size must be divisible by the stem patch size")
+        K = C * p * p
+        kpad = (K + 7) // 8 * 8
+        w2 = conv.weight.view(conv.weight.shape[0], K)
+        if kpad != K:
+            raise B200Error("stem patch size with C*p*p not a multiple of 8 is not covered")
+        x = ops.gemm(ops.patchify(img.contiguous(), p, kpad), w2, B * (H // p) * (W // p), w2.shape[0], kpad, bias=conv.bias)
+        x = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps)[0]
+        H, W = H // p, W // p
+        for stage in self.stages:
+            x, H, W = stage.forward_nhwc(x, B, H, W)
+        return x, B, H, W
+
+    def forward_features(self, img):
+        """NCHW feature map like timm's forward_features (convnext.py:606-611); the permute is a view."""
+        x, B, H, W = self._features_nhwc(img)
+        return x.view(B, H, W, -1).permute(0, 3, 1, 2)
+
+    def forward_head(self, x, pre_logits: bool = False):
+        B, C, H, W = x.shape
+        rows = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
+        return self.head.forward_nhwc(rows, B, H * W, pre_logits)
+
+    def forward(self, img):
+        x, B, H, W = self._features_nhwc(img)
+        return self.head.forward_nhwc(x, B, H * W)
+
+
+MODEL_ARGS = {
+    "convnext_tiny": dict(depths=(3, 3, 9, 3), dims=(96, 192, 384, 768)),
+    "convnext_small": dict(depths=(3, 3, 27, 3), dims=(96, 192, 384, 768)),
+    "convnext_base": dict(depths=(3, 3, 27, 3), dims=(128, 256, 512, 1024)),       # convnext.py:1293-1296
+    "convnext_large": dict(depths=(3, 3, 27, 3), dims=(192, 384, 768, 1536)),
+}
+
+
+def create_model(name: str, **kwargs) -> ConvNeXt:
+    if name not in MODEL_ARGS:
+        raise B200Error(f"unknown ConvNeXt variant {name!r}; mirrored: {sorted(MODEL_ARGS)}")
+    return ConvNeXt(**dict(MODEL_ARGS[name], **kwargs))

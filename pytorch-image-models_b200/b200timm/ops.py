@@ -14,7 +14,8 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
-    "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
+    "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "patchify_nhwc",
+    "avgpool_nhwc", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
 ]
 
 
@@ -319,5 +320,49 @@ def colsum(x2d, out=None, accumulate=False):
         accumulate = False
     rc = _lib.load().b200_colsum(x2d.data_ptr(), out.data_ptr(), rows, cols, int(accumulate), _stream())
     _lib.check(rc, "b200_colsum")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------------------------- ConvNeXt (NHWC)
+def dwconv_nhwc(x, weight, bias):
+    """Depthwise k x k conv (stride 1, pad k//2) on a contiguous bf16 [B,H,W,C] tensor; weight [C,1,k,k]."""
+    _need_cuda(x, weight, bias)
+    if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise B200Error("dwconv_nhwc: need a contiguous bf16 [B,H,W,C] tensor")
+    B, H, W, C = x.shape
+    k = weight.shape[-1]
+    if tuple(weight.shape) != (C, 1, k, k) or weight.dtype != torch.bfloat16 or not weight.is_contiguous():
+        raise B200Error("dwconv_nhwc: weight must be contiguous bf16 [C,1,k,k]")
+    y = torch.empty_like(x)
+    rc = _lib.load().b200_dwconv_nhwc(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(), B, H, W, C, k,
+                                      _dt(bias) if bias is not None else DTYPE_BF16, _stream())
+    _lib.check(rc, "b200_dwconv_nhwc")
+    _count()
+    return y
+
+
+def patchify_nhwc(x, p):
+    """[B,H,W,C] bf16 -> [B*(H/p)*(W/p), p*p*C] (k = (ky*p + kx)*C + c)."""
+    _need_cuda(x)
+    if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise B200Error("patchify_nhwc: need a contiguous bf16 [B,H,W,C] tensor")
+    B, H, W, C = x.shape
+    out = torch.empty(B * (H // p) * (W // p), p * p * C, dtype=torch.bfloat16, device=x.device)
+    rc = _lib.load().b200_patchify_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, C, p, _stream())
+    _lib.check(rc, "b200_patchify_nhwc")
+    _count()
+    return out
+
+
+def avgpool_nhwc(x):
+    """[B,HW,C] (or [B,H,W,C]) bf16 -> [B,C] mean over the spatial positions."""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or not x.is_contiguous() or x.dim() not in (3, 4):
+        raise B200Error("avgpool_nhwc: need a contiguous bf16 [B,HW,C] tensor")
+    B, C = x.shape[0], x.shape[-1]
+    out = torch.empty(B, C, dtype=torch.bfloat16, device=x.device)
+    rc = _lib.load().b200_avgpool_nhwc(x.data_ptr(), out.data_ptr(), B, x.numel() // (B * C), C, _stream())
+    _lib.check(rc, "b200_avgpool_nhwc")
     _count()
     return out

@@ -80,3 +80,15 @@ def test_no_cpu_fallback():
         PatchEmbed(32, 16, 3, 64).to(torch.bfloat16)(torch.zeros(1, 3, 32, 32, dtype=torch.bfloat16))
     with pytest.raises(B200Error):
         Attention(96, num_heads=2).to(torch.bfloat16)(torch.zeros(1, 4, 96, dtype=torch.bfloat16))  # head_dim 48
+
+
+def test_convnext_state_dict_matches_timm():
+    from b200timm.convnext import ConvNeXt, create_model as create_convnext
+    fx = torch.load(os.path.join(GOLDEN, "convnext_g1.pt"))
+    model = ConvNeXt(**fx["kwargs"])
+    assert list(model.state_dict().keys()) == list(fx["state_dict"].keys())
+    model.load_state_dict(fx["state_dict"], strict=True)
+    n = sum(p.numel() for p in create_convnext("convnext_base").parameters())
+    assert abs(n / 1e6 - 88.59) < 0.01     # results/benchmark-*.csv param_count for convnext_base
+    with pytest.raises(B200Error):
+        model.to(torch.bfloat16)(torch.zeros(1, 3, 64, 64, dtype=torch.bfloat16))   # CPU: no fallback

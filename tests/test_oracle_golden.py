@@ -85,3 +85,16 @@ def test_layer_goldens():
     torch.testing.assert_close(ls["x"] * ls["state_dict"]["gamma"], ls["y"])
     dp = fx["droppath"]
     torch.testing.assert_close(O.drop_path(dp["x"], dp["keep_mask"], 1.0 - dp["drop_prob"]), dp["y"])
+
+
+def test_convnext_oracle_matches_reference():
+    from oracle import convnext_oracle as C
+    fx = torch.load(os.path.join(GOLDEN, "convnext_g1.pt"))
+    cfg = dict(fx["kwargs"])
+    with torch.no_grad():
+        feats, stages = C.convnext_forward_features(fx["img"], fx["state_dict"], cfg, return_stages=True)
+        for i, (got, ref) in enumerate(zip(stages, fx["stage_outputs"])):
+            torch.testing.assert_close(got, ref, atol=2e-5, rtol=1e-5, msg=lambda m: f"stage {i}: {m}")
+        torch.testing.assert_close(feats, fx["features"], atol=2e-5, rtol=1e-5)
+        torch.testing.assert_close(C.convnext_forward_head(feats, fx["state_dict"], cfg), fx["logits"], atol=2e-5, rtol=1e-5)
+        torch.testing.assert_close(C.convnext_forward_eager(fx["img"], fx["state_dict"], cfg), fx["logits"], atol=2e-5, rtol=1e-5)
