@@ -119,6 +119,13 @@ B200_API int b200_assemble_tokens(const void* proj, const void* prefix, const vo
                          int32_t G, int32_t n_prefix, int32_t D, int32_t param_dtype,
                          int32_t pos_has_prefix, void* stream);
 
+/* NaFlex token assembly (timm/models/naflexvit.py:857-960): tokens[b, n_prefix + i] = proj[b, i] + table[pos_off[b] + i]
+ * for i < pos_len[b] (the sample's h*w grid, row-major; `table` holds the position embeddings already interpolated to
+ * each distinct grid size, bf16 [T, D]) and proj[b, i] beyond it; tokens[b, j < n_prefix] = prefix[j].              */
+B200_API int b200_naflex_assemble(const void* proj, const void* prefix, const void* table, const int32_t* pos_off,
+                         const int32_t* pos_len, void* tokens, int32_t B, int32_t N, int32_t n_prefix,
+                         int32_t D, int32_t prefix_dtype, void* stream);
+
 /* ------------------------------------------------------------------ ConvNeXt (channels-last activations [B,H,W,C] bf16)
  * Depthwise k x k convolution, stride 1, zero padding k/2, + bias: F.conv2d(groups=C) of timm/models/convnext.py:
  * 173-182,200 evaluated NHWC so the permutes of :205,208 disappear.  weight: bf16 [C,1,k,k]; k in {3,5,7}.      */

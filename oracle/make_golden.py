@@ -84,6 +84,49 @@ def convnext_case(name, seed, batch, kwargs, img_size):
           "params", sum(p.numel() for p in model.parameters()))
 
 
+def naflex_batch(g, batch, max_grid, patch, chans=3):
+    """A NaFlex batch the way NaFlexCollator lays it out (timm/data/naflex_dataset.py:122-150): per-sample (h, w) grid,
+    row-major coords, valid prefix, zero padding up to max_grid[0]*max_grid[1] tokens."""
+    N = max_grid[0] * max_grid[1]
+    grids = [max_grid, (3, 5), (4, 2), (2, 2), (5, 3)][:batch]
+    patches = torch.zeros(batch, N, patch * patch * chans)
+    coord = torch.zeros(batch, N, 2, dtype=torch.int64)
+    valid = torch.zeros(batch, N, dtype=torch.bool)
+    for b, (h, w) in enumerate(grids):
+        n = h * w
+        patches[b, :n] = torch.randn(n, patch * patch * chans, generator=g)
+        yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        coord[b, :n] = torch.stack([yy.flatten(), xx.flatten()], -1)
+        valid[b, :n] = True
+    return patches, coord, valid
+
+
+def naflex_case(name, seed, batch):
+    import timm
+    from timm.models.naflexvit import NaFlexVit, NaFlexVitCfg
+    torch.manual_seed(seed)
+    cfg = dict(patch_size=14, embed_dim=128, depth=2, num_heads=2, class_token=True, pos_embed_grid_size=(6, 6),
+               pre_norm=True, global_pool="token")
+    model = NaFlexVit(cfg=NaFlexVitCfg(**cfg), in_chans=3, num_classes=9, img_size=84)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+            if n in ("embeds.cls_token", "embeds.pos_embed"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    model.eval()
+    patches, coord, valid = naflex_batch(g, batch, (6, 6), 14)
+    with torch.no_grad():
+        feats = model.forward_features(patches, patch_coord=coord, patch_valid=valid)
+        logits = model.forward_head(feats["patches"], patch_valid=valid)
+    fx = {"kind": "naflex", "kwargs": dict(cfg, num_classes=9), "state_dict": _half_sd(model.state_dict()),
+          "patches": patches, "patch_coord": coord, "patch_valid": valid, "features": feats["patches"].detach(),
+          "logits": logits.detach(), "timm_version": timm.__version__, "torch_version": str(torch.__version__)}
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, "logits", tuple(logits.shape), "absmax", logits.abs().max().item())
+
+
 def layer_cases():
     from timm.layers import Attention, LayerNorm, Mlp, PatchEmbed, LayerScale, DropPath
     from timm.models.naflexvit import create_attention_mask
@@ -138,6 +181,7 @@ def main():
              dict(img_size=56, patch_size=14, in_chans=3, num_classes=5, embed_dim=64, depth=1, num_heads=1,
                   qkv_bias=True, pre_norm=True, no_embed_class=True), backward=False)
     convnext_case("convnext_g1", 3, 2, dict(depths=(1, 1, 2, 1), dims=(16, 32, 64, 128), num_classes=10), 64)
+    naflex_case("naflex_g1", 4, 5)
     layer_cases()
 
 

@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
+    "avgpool_nhwc", "naflex_assemble", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
 ]
 
 
@@ -366,3 +366,25 @@ def avgpool_nhwc(x):
     _lib.check(rc, "b200_avgpool_nhwc")
     _count()
     return out
+
+
+# --------------------------------------------------------------------------------------------- NaFlex
+def naflex_assemble(proj, prefix, table, pos_off, pos_len, B, N, n_prefix, D):
+    """tokens [B, n_prefix+N, D] = cat(prefix, proj + per-sample interpolated position rows)."""
+    _need_cuda(proj, prefix, table, pos_off, pos_len)
+    if proj.dtype != torch.bfloat16 or not proj.is_contiguous() or proj.numel() != B * N * D:
+        raise B200Error("naflex_assemble: proj must be contiguous bf16 [B*N, D]")
+    if table is not None and (table.dtype != torch.bfloat16 or not table.is_contiguous() or table.shape[-1] != D):
+        raise B200Error("naflex_assemble: table must be contiguous bf16 [T, D]")
+    for t in (pos_off, pos_len):
+        if t is not None and (t.dtype != torch.int32 or t.numel() != B or not t.is_contiguous()):
+            raise B200Error("naflex_assemble: pos_off / pos_len must be contiguous int32 [B]")
+    if prefix is not None and (not prefix.is_contiguous() or prefix.numel() != n_prefix * D):
+        raise B200Error("naflex_assemble: prefix must be contiguous [n_prefix, D]")
+    tokens = torch.empty(B, n_prefix + N, D, dtype=torch.bfloat16, device=proj.device)
+    rc = _lib.load().b200_naflex_assemble(proj.data_ptr(), _ptr(prefix), _ptr(table), _ptr(pos_off), _ptr(pos_len),
+                                          tokens.data_ptr(), B, N, n_prefix, D,
+                                          _dt(prefix) if prefix is not None else DTYPE_BF16, _stream())
+    _lib.check(rc, "b200_naflex_assemble")
+    _count()
+    return tokens

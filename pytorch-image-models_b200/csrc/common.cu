@@ -45,19 +45,19 @@ static EncodeTiledFn resolve_encode() {
 }
 
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                       const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
-  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle128);
+                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle);
 }
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
-  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle128);
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
+  return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle);
 }
 
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                       const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+                       const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
   EncodeTiledFn fn = resolve_encode();
   if (fn == nullptr) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t gdim[5];
@@ -72,7 +72,7 @@ static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* bas
   }
   CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                   gdim, gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : (swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dim0 %llu, box0 %u)",

@@ -29,11 +29,11 @@ int fail(int code, const char* fmt, ...);
 int sm_count();
 
 // Encode a tiled tensor map over a bf16 tensor of rank `rank` (dims[0] innermost, strides in BYTES for
-// dims 1..rank-1), 128-byte swizzle, zero fill out of bounds.  Returns 0 or an error code.
+// dims 1..rank-1), swizzle = 0 (none) / 64 / anything else (128-byte), zero fill out of bounds.  Returns 0 or an error code.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 // Same for an fp32 tensor (GEMM fp32 outputs: weight gradients).
 int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
 
 }  // namespace b200

@@ -104,6 +104,43 @@ __global__ void assemble_tokens_kernel(const __nv_bfloat16* __restrict__ proj, c
   }
 }
 
+// NaFlex token assembly (timm/models/naflexvit.py:857-960, _apply_learned_naflex_pos_embed :567-621):
+// tokens[b][j] = prefix[j]                                   j <  n_prefix
+//              = proj[b][i] + (i < pos_len[b] ? table[pos_off[b] + i] : 0)      i = j - n_prefix
+// where table rows are the position embeddings already interpolated to each sample's (h, w) grid, row-major.
+__global__ void naflex_assemble_kernel(const __nv_bfloat16* __restrict__ proj, const void* __restrict__ prefix,
+                                       const __nv_bfloat16* __restrict__ table, const int* __restrict__ pos_off,
+                                       const int* __restrict__ pos_len, __nv_bfloat16* __restrict__ tokens, int B,
+                                       int N, int n_prefix, int D, int param_f32) {
+  const int dvecs = D >> 3;
+  const int ntok = N + n_prefix;
+  const long long total = static_cast<long long>(B) * ntok * dvecs;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int dv = static_cast<int>(idx % dvecs);
+    const long long t = idx / dvecs;
+    const int j = static_cast<int>(t % ntok);
+    const int b = static_cast<int>(t / ntok);
+    float v[8];
+    if (j < n_prefix) {
+      ld8(prefix, param_f32, static_cast<long long>(j) * D + dv * 8, v);
+    } else {
+      const int i = j - n_prefix;
+      ld8(proj, false, (static_cast<long long>(b) * N + i) * D + dv * 8, v);
+      if (table != nullptr && i < pos_len[b]) {
+        float pv[8];
+        ld8(table, false, (static_cast<long long>(pos_off[b]) + i) * D + dv * 8, pv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += pv[k];
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
+    q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tokens + t * D + dv * 8) = q;
+  }
+}
+
 // out[c] += sum over a slab of rows of x[r][c]; blockIdx.x = 256-column group, blockIdx.y = row slab.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int cols,
@@ -224,6 +261,26 @@ extern "C" int b200_convert_f32(const float* src, void* dst, int64_t n, int32_t 
   if (blocks > cap) blocks = cap;
   if (dst_dtype == B200_DTYPE_F32) convert_kernel<true><<<static_cast<int>(blocks), threads, 0, st>>>(src, dst, n, accumulate);
   else convert_kernel<false><<<static_cast<int>(blocks), threads, 0, st>>>(src, dst, n, accumulate);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_naflex_assemble(const void* proj, const void* prefix, const void* table, const int32_t* pos_off,
+                                    const int32_t* pos_len, void* tokens, int32_t B, int32_t N, int32_t n_prefix,
+                                    int32_t D, int32_t prefix_dtype, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(proj && tokens, "b200_naflex_assemble: null pointer");
+  B200_CHECK_ARG(n_prefix == 0 || prefix != nullptr, "b200_naflex_assemble: n_prefix > 0 needs prefix tokens");
+  B200_CHECK_ARG(table == nullptr || (pos_off && pos_len), "b200_naflex_assemble: a position table needs pos_off / pos_len");
+  B200_CHECK_ARG(B > 0 && N > 0 && n_prefix >= 0 && D > 0 && D % 8 == 0, "b200_naflex_assemble: bad shape (D %% 8 == 0)");
+  const long long total = static_cast<long long>(B) * (N + n_prefix) * (D / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  naflex_assemble_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(proj), prefix, reinterpret_cast<const __nv_bfloat16*>(table), pos_off, pos_len,
+      reinterpret_cast<__nv_bfloat16*>(tokens), B, N, n_prefix, D, prefix_dtype == B200_DTYPE_F32);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

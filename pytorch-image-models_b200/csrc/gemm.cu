@@ -4,7 +4,7 @@
 //   warp 1      : MMA issuer     (one thread issues tcgen05.mma 128 x BN x 16, accumulators in TMEM,
 //                                 two accumulator stages so the epilogue overlaps the next tile)
 //   warp 2      : TMEM allocator / deallocator
-//   warps 4..11 : epilogue       (tcgen05.ld -> bias / GELU / residual+LayerScale / dGELU -> 128B-swizzled smem
+//   warps 4..19 : epilogue       (tcgen05.ld -> bias / GELU / residual+LayerScale / dGELU -> 128B-swizzled smem
 //                                 staging tile -> TMA store; the residual / pre-activation operand comes in
 //                                 through a TMA load into the same staging tile, so every global access of the
 //                                 epilogue is a full-line bulk copy; fp32 outputs accumulate / split-K through
@@ -21,7 +21,7 @@ namespace b200 {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kNumEpiWarps = 8;
+constexpr int kNumEpiWarps = 16;
 constexpr int kNumThreads = 128 + kNumEpiWarps * 32;
 
 struct GemmKernelParams {
@@ -42,10 +42,10 @@ struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingOffset = STAGES * kStageBytes;   // kNumEpiWarps x 4 KB (32 rows x 128 B each)
-  static constexpr int kStagingBytes = kNumEpiWarps * 4096;
+  static constexpr int kStagingOffset = STAGES * kStageBytes;   // kNumEpiWarps x 2 KB (32 rows x 64 B each)
+  static constexpr int kStagingBytes = kNumEpiWarps * 2048;
   static constexpr int kBarrierOffset = kStagingOffset + kStagingBytes;
-  static constexpr int kTotal = kBarrierOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kTotal = kBarrierOffset + 512 + 1024;  // + barriers + alignment slack
 };
 
 // erf(x / sqrt2) for a pair, Abramowitz-Stegun 7.1.28:  erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| < 3e-7.
@@ -214,15 +214,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ epilogue
     const int ew = warp_idx - 4;
     const int quad = warp_idx & 3;          // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;               // which half of the BN columns
-    constexpr int kColsPerWarp = BN / 2;
-    uint8_t* stg = smem + L::kStagingOffset + ew * 4096;   // 32 rows x 128 B, 128B-swizzled (TMA box layout)
-    const uint32_t stg_row = smem_u32(stg) + lane * 128;
-    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const int part = ew >> 2;               // which quarter of the BN columns
+    constexpr int kColsPerWarp = BN / 4;
+    uint8_t* stg = smem + L::kStagingOffset + ew * 2048;   // 32 rows x 64 B, 64B-swizzled (TMA box layout)
+    const uint32_t stg_row = smem_u32(stg) + lane * 64;
+    const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
     const bool has_aux = p.epilogue == B200_EPI_BIAS_RESIDUAL || p.epilogue == B200_EPI_DGELU;
     const bool reduce_out = p.out_f32 && (p.accumulate || p.split_k > 1);
     const bool dual = p.out2 != nullptr;   // training fc1: out2 <- pre-activation, out <- GELU(pre-activation)
-    const int round_cols = p.out_f32 ? 32 : 64;   // 128-byte rows of the staging tile
+    const int round_cols = p.out_f32 ? 16 : 32;   // 64-byte rows of the staging tile
     uint32_t aux_phase = 0;
     int as = 0;
     uint32_t aphase = 0;
@@ -232,16 +232,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
       const int row0 = m_blk * BM + quad * 32;
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * kColsPerWarp;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + part * kColsPerWarp;
       bool waited = false;
 #pragma unroll 1
       for (int rc = 0; rc < kColsPerWarp; rc += round_cols) {
-        const int col0 = n_blk * BN + half * kColsPerWarp + rc;
+        const int col0 = n_blk * BN + part * kColsPerWarp + rc;
         // the staging tile is free once the previous TMA store has finished READING it
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         if (has_aux && lane == 0) {
-          mbar_arrive_expect_tx(&aux_bar[ew], 4096);
+          mbar_arrive_expect_tx(&aux_bar[ew], 2048);
           tma_load_2d(stg, &tmap_aux, &aux_bar[ew], col0, row0);
         }
         if (!waited) {
@@ -249,82 +249,82 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           waited = true;
         }
-        if (has_aux) {
-          mbar_wait(&aux_bar[ew], aux_phase);
-          aux_phase ^= 1;
-        }
-#pragma unroll 1
-        for (int c = 0; c < round_cols; c += 32) {
-          uint32_t r[32];
-          tmem_ld_x32(taddr0 + rc + c, r);
-          tmem_ld_wait();
-          if (p.out_f32) {
-            // fp32 output (weight gradients): 32 columns = 8 chunks of 4 floats
+        if (p.out_f32) {
+          // fp32 output (weight gradients): 16 columns = 4 chunks of 4 floats
+          uint32_t r[16];
+          tmem_ld_x16(taddr0 + rc, r);
+          tmem_ld_wait_x16(r);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int col = col0 + g * 4;
-              float v0 = __uint_as_float(r[g * 4 + 0]), v1 = __uint_as_float(r[g * 4 + 1]);
-              float v2 = __uint_as_float(r[g * 4 + 2]), v3 = __uint_as_float(r[g * 4 + 3]);
-              if (p.bias != nullptr && col < p.N) {
-                if (p.bias_f32) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + col));
-                  v0 += b4.x; v1 += b4.y; v2 += b4.z; v3 += b4.w;
-                } else {
-                  const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col));
-                  v0 += bf16_lo(b2.x); v1 += bf16_hi(b2.x); v2 += bf16_lo(b2.y); v3 += bf16_hi(b2.y);
-                }
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 4;
+            float v0 = __uint_as_float(r[g * 4 + 0]), v1 = __uint_as_float(r[g * 4 + 1]);
+            float v2 = __uint_as_float(r[g * 4 + 2]), v3 = __uint_as_float(r[g * 4 + 3]);
+            if (p.bias != nullptr && col < p.N) {
+              if (p.bias_f32) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + col));
+                v0 += b4.x; v1 += b4.y; v2 += b4.z; v3 += b4.w;
+              } else {
+                const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col));
+                v0 += bf16_lo(b2.x); v1 += bf16_hi(b2.x); v2 += bf16_lo(b2.y); v3 += bf16_hi(b2.y);
               }
-              const uint32_t addr = stg_row + ((static_cast<uint32_t>(g) ^ sw) << 4);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
             }
-          } else {
+            const uint32_t addr = stg_row + ((static_cast<uint32_t>(g) ^ sw) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+          }
+        } else {
+          uint32_t r[32];
+          tmem_ld_x32(taddr0 + rc, r);
+          tmem_ld_wait_x32(r);
+          if (has_aux) {
+            mbar_wait(&aux_bar[ew], aux_phase);
+            aux_phase ^= 1;
+          }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + c + g * 8;
-              const uint32_t addr = stg_row + ((static_cast<uint32_t>((c >> 3) + g) ^ sw) << 4);
-              f32x2 v[4];
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            const uint32_t addr = stg_row + ((static_cast<uint32_t>(g) ^ sw) << 4);
+            f32x2 v[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = pk(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
-              if (col < p.N) {
-                if (p.bias != nullptr) {
-                  f32x2 bv[4];
-                  load8_param2(p.bias, p.bias_f32, col, bv);
+            for (int j = 0; j < 4; ++j) v[j] = pk(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
+            if (col < p.N) {
+              if (p.bias != nullptr) {
+                f32x2 bv[4];
+                load8_param2(p.bias, p.bias_f32, col, bv);
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) v[j] = add2(v[j], bv[j]);
-                }
-                if (p.epilogue == B200_EPI_BIAS_GELU && !dual) {
+                for (int j = 0; j < 4; ++j) v[j] = add2(v[j], bv[j]);
+              }
+              if (p.epilogue == B200_EPI_BIAS_GELU && !dual) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
-                } else if (has_aux) {
-                  uint4 q;
-                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
-                  const f32x2 av[4] = {bf16x2_to_f32x2(q.x), bf16x2_to_f32x2(q.y), bf16x2_to_f32x2(q.z), bf16x2_to_f32x2(q.w)};
-                  if (p.epilogue == B200_EPI_BIAS_RESIDUAL) {
-                    if (p.gamma != nullptr) {
-                      f32x2 gv[4];
-                      load8_param2(p.gamma, p.gamma_f32, col, gv);
+                for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
+              } else if (has_aux) {
+                uint4 q;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+                const f32x2 av[4] = {bf16x2_to_f32x2(q.x), bf16x2_to_f32x2(q.y), bf16x2_to_f32x2(q.z), bf16x2_to_f32x2(q.w)};
+                if (p.epilogue == B200_EPI_BIAS_RESIDUAL) {
+                  if (p.gamma != nullptr) {
+                    f32x2 gv[4];
+                    load8_param2(p.gamma, p.gamma_f32, col, gv);
 #pragma unroll
-                      for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], gv[j], av[j]);
-                    } else {
-#pragma unroll
-                      for (int j = 0; j < 4; ++j) v[j] = add2(v[j], av[j]);
-                    }
+                    for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], gv[j], av[j]);
                   } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], dgelu_erf2(av[j]));
+                    for (int j = 0; j < 4; ++j) v[j] = add2(v[j], av[j]);
                   }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], dgelu_erf2(av[j]));
                 }
               }
-              uint32_t o[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float lo, hi;
-                upk(v[j], lo, hi);
-                o[j] = pack_bf16(lo, hi);
-              }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
-                           : "memory");
             }
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float lo, hi;
+              upk(v[j], lo, hi);
+              o[j] = pack_bf16(lo, hi);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                         : "memory");
           }
         }
         if (rc + round_cols >= kColsPerWarp) {  // last TMEM read of this tile: hand the accumulator back
@@ -345,7 +345,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             const uint32_t addr = stg_row + ((static_cast<uint32_t>(j) ^ sw) << 4);
             uint4 q;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
@@ -402,26 +402,26 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   }
   CUtensorMap tout, taux, tout2;
   {
-    // out / aux: dims {N, M}; box = one 128-byte-wide, 32-row staging tile
+    // out / aux: dims {N, M}; box = one 64-byte-wide, 32-row staging tile (64B swizzle)
     const bool of32 = d.out_dtype == B200_DTYPE_F32;
     uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
     uint64_t strides[1] = {static_cast<uint64_t>(d.ldo) * (of32 ? 4 : 2)};
-    uint32_t box[2] = {of32 ? 32u : 64u, 32u};
-    int rc = of32 ? encode_tmap_f32(&tout, d.out, 2, dims, strides, box, true)
-                  : encode_tmap_bf16(&tout, d.out, 2, dims, strides, box, true);
+    uint32_t box[2] = {of32 ? 16u : 32u, 32u};
+    int rc = of32 ? encode_tmap_f32(&tout, d.out, 2, dims, strides, box, 64)
+                  : encode_tmap_bf16(&tout, d.out, 2, dims, strides, box, 64);
     if (rc) return rc;
     if (d.aux != nullptr) {
       uint64_t astr[1] = {static_cast<uint64_t>(d.ldaux) * 2};
-      uint32_t abox[2] = {64u, 32u};
-      rc = encode_tmap_bf16(&taux, d.aux, 2, dims, astr, abox, true);
+      uint32_t abox[2] = {32u, 32u};
+      rc = encode_tmap_bf16(&taux, d.aux, 2, dims, astr, abox, 64);
       if (rc) return rc;
     } else {
       taux = tout;
     }
     if (d.out2 != nullptr) {
       uint64_t ostr[1] = {static_cast<uint64_t>(d.ldo2) * 2};
-      uint32_t obox[2] = {64u, 32u};
-      rc = encode_tmap_bf16(&tout2, d.out2, 2, dims, ostr, obox, true);
+      uint32_t obox[2] = {32u, 32u};
+      rc = encode_tmap_bf16(&tout2, d.out2, 2, dims, ostr, obox, 64);
       if (rc) return rc;
     } else {
       tout2 = tout;

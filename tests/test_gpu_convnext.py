@@ -1,0 +1,86 @@
+"""ConvNeXt (BASELINE.json configs[2]) on the GPU: channels-last kernels + fused GEMMs against the reference golden
+(tests/golden/convnext_g1.pt, made from unmodified timm) and the CPU oracle.  Tolerances as in test_gpu_models.py."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _check(got, ref, atol, rtol, what, min_cos=0.999):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(got).all(), f"{what}: non-finite"
+    err = (got - ref).abs()
+    bad = err > atol + rtol * ref.abs()
+    cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    assert not bad.any() and cos >= min_cos, (f"{what}: {int(bad.sum())}/{bad.numel()} off, max err {err.max().item():.4g}, "
+                                              f"ref absmax {ref.abs().max().item():.4g}, cos {cos:.6f}")
+
+
+@pytest.mark.parametrize("k", [7, 5, 3])
+@pytest.mark.parametrize("B,H,W,C", [(2, 14, 14, 512), (1, 56, 56, 128), (3, 7, 7, 1024), (2, 9, 13, 40)])
+def test_dwconv_nhwc(k, B, H, W, C):
+    from b200timm import ops
+    g = torch.Generator(device="cuda").manual_seed(k * 100 + C)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, 1, k, k, device="cuda", generator=g) * 0.2).bfloat16()
+    b = torch.randn(C, device="cuda", generator=g).bfloat16()
+    y = ops.dwconv_nhwc(x, w, b)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=k // 2, groups=C)
+    _check(y, ref.permute(0, 2, 3, 1), 2e-2, 1e-2, f"dwconv k={k} {B}x{H}x{W}x{C}")
+
+
+def test_patchify_and_avgpool_nhwc():
+    from b200timm import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(3, 8, 12, 64, device="cuda", generator=g).bfloat16()
+    out = ops.patchify_nhwc(x, 2)
+    ref = x.view(3, 4, 2, 6, 2, 64).permute(0, 1, 3, 2, 4, 5).reshape(3 * 4 * 6, 2 * 2 * 64)
+    assert torch.equal(out, ref)
+    pooled = ops.avgpool_nhwc(x)
+    _check(pooled, x.float().mean((1, 2)), 1e-2, 1e-2, "avgpool")
+
+
+def test_convnext_matches_reference_golden():
+    from oracle import convnext_oracle as C
+    from b200timm.convnext import ConvNeXt
+    fx = torch.load(os.path.join(GOLDEN, "convnext_g1.pt"))
+    model = ConvNeXt(**fx["kwargs"])
+    model.load_state_dict(fx["state_dict"], strict=True)
+    model = model.cuda().to(torch.bfloat16).eval()
+    img = fx["img"].cuda().bfloat16()
+    with torch.no_grad():
+        feats = model.forward_features(img)
+        logits = model(img)
+        logits2 = model.forward_head(feats)
+    _check(feats, fx["features"], 8e-2, 3e-2, "features vs timm golden")
+    _check(logits, fx["logits"], 2e-2, 2e-2, "logits vs timm golden")
+    _check(logits2, fx["logits"], 2e-2, 2e-2, "forward_head(forward_features) vs timm golden")
+    sd = {k: v.bfloat16().float() for k, v in fx["state_dict"].items()}
+    ref = C.convnext_forward(fx["img"].bfloat16().float(), sd, dict(fx["kwargs"]))
+    _check(logits, ref, 2e-2, 2e-2, "logits vs oracle(bf16 weights)")
+
+
+def test_convnext_base_matches_oracle():
+    """BASELINE configs[2] architecture (convnext_base @224) at batch 4 against the fp32 oracle, with the
+    SURVEY 8c yardstick |ours - fp32| <= max(2 |eager_bf16 - fp32|, atol)."""
+    from oracle import convnext_oracle as C
+    from b200timm.convnext import create_model
+    cfg = dict(C.CONVNEXT_CONFIGS["convnext_base"])
+    sd = {k: v.bfloat16().float() for k, v in C.random_state_dict(cfg, seed=2).items()}
+    model = create_model("convnext_base")
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().to(torch.bfloat16).eval()
+    img = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(3)).bfloat16()
+    with torch.no_grad():
+        logits = model(img.cuda()).float().cpu()
+        ref = C.convnext_forward_eager(img.float(), sd, cfg)
+        eager16 = C.convnext_forward_eager(img.cuda(), {k: v.cuda().bfloat16() for k, v in sd.items()}, cfg).float().cpu()
+    e_ref, e_ours = (eager16 - ref).abs().max().item(), (logits - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(logits.flatten(), ref.flatten(), dim=0).item()
+    assert torch.isfinite(logits).all()
+    assert e_ours <= max(2 * e_ref, 2e-2) and cos >= 0.9995, (
+        f"convnext_base: max err {e_ours:.4g} vs eager-bf16 {e_ref:.4g} (ref absmax {ref.abs().max().item():.3g}), cos {cos:.6f}")

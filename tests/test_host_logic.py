@@ -92,3 +92,13 @@ def test_convnext_state_dict_matches_timm():
     assert abs(n / 1e6 - 88.59) < 0.01     # results/benchmark-*.csv param_count for convnext_base
     with pytest.raises(B200Error):
         model.to(torch.bfloat16)(torch.zeros(1, 3, 64, 64, dtype=torch.bfloat16))   # CPU: no fallback
+
+
+def test_naflex_state_dict_matches_timm():
+    from b200timm.naflexvit import NaFlexVit, create_model as create_naflex
+    fx = torch.load(os.path.join(GOLDEN, "naflex_g1.pt"))
+    model = NaFlexVit(**fx["kwargs"])
+    assert sorted(model.state_dict().keys()) == sorted(fx["state_dict"].keys())
+    model.load_state_dict(fx["state_dict"], strict=True)
+    big = create_naflex("vit_large_patch14_clip_336", depth=1)
+    assert big.embeds.pos_embed.shape == (1, 24, 24, 1024) and big.embeds.proj.bias is None and big.norm.eps == 1e-5

@@ -98,3 +98,16 @@ def test_convnext_oracle_matches_reference():
         torch.testing.assert_close(feats, fx["features"], atol=2e-5, rtol=1e-5)
         torch.testing.assert_close(C.convnext_forward_head(feats, fx["state_dict"], cfg), fx["logits"], atol=2e-5, rtol=1e-5)
         torch.testing.assert_close(C.convnext_forward_eager(fx["img"], fx["state_dict"], cfg), fx["logits"], atol=2e-5, rtol=1e-5)
+
+
+def test_naflex_oracle_matches_reference():
+    from oracle import naflex_oracle as NO
+    fx = torch.load(os.path.join(GOLDEN, "naflex_g1.pt"))
+    with torch.no_grad():
+        feats, logits = NO.naflex_forward(fx["patches"], fx["patch_coord"], fx["patch_valid"], fx["state_dict"],
+                                          dict(fx["kwargs"], eps=1e-6))
+    torch.testing.assert_close(logits, fx["logits"], atol=1e-5, rtol=1e-5)
+    npre = 1
+    for b in range(feats.shape[0]):   # padded query rows are unspecified in the reference (all-masked softmax)
+        n = int(fx["patch_valid"][b].sum()) + npre
+        torch.testing.assert_close(feats[b, :n], fx["features"][b, :n], atol=1e-5, rtol=1e-5)

@@ -1,0 +1,52 @@
+"""Device-resident inference throughput of one mirrored model (ViT or ConvNeXt) -- the non-headline BASELINE configs.
+    python tools/bench_model.py convnext_base --batch 256 --steps 20
+Prints one JSON line: img/s, ms/step and the per-kernel-type time split from CUDA events."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "pytorch-image-models_b200"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("model")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--img-size", type=int, default=224)
+    args = ap.parse_args()
+    from b200timm import ops
+    if args.model.startswith("convnext"):
+        from b200timm.convnext import create_model
+        model = create_model(args.model)
+    else:
+        from b200timm.vision_transformer import create_model
+        kw = {} if args.img_size == 224 or "336" in args.model else {"img_size": args.img_size}
+        model = create_model(args.model, **kw)
+    torch.manual_seed(42)
+    model = model.cuda().to(torch.bfloat16).eval()
+    size = 336 if "336" in args.model else args.img_size
+    xs = [torch.randn(args.batch, 3, size, size, device="cuda").bfloat16() for _ in range(2)]
+    with torch.no_grad():
+        for i in range(args.warmup):
+            model(xs[i & 1])
+        torch.cuda.synchronize()
+        ops.reset_counters()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(args.steps):
+            model(xs[i & 1])
+        t1.record()
+        torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / args.steps
+    print(json.dumps({"model": args.model, "batch": args.batch, "img_size": size, "ms_per_step": round(ms, 3),
+                      "img_per_s": round(args.batch / ms * 1e3, 1), "launches_per_step": ops.launch_count() // args.steps}))
+
+
+if __name__ == "__main__":
+    main()
