@@ -57,7 +57,7 @@ class ConvNeXtBlock(nn.Module):
         C = x.shape[1]
         if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
             raise B200Error("ConvNeXt DropPath in training mode is not covered")
-        y = ops.dwconv_nhwc(x.view(B, H, W, C), self.conv_dw.weight, self.conv_dw.bias).view(B * H * W, C)
+        y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
         h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
         a = ops.linear_fwd(h, self.mlp.fc1.weight, self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
         return ops.linear_fwd(a, self.mlp.fc2.weight, self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
@@ -105,6 +105,17 @@ class ConvNeXtStage(nn.Module):
         for blk in self.blocks:
             x = blk.forward_nhwc(x, B, H, W)
         return x, H, W
+
+
+def _dw_weight_t(conv):
+    """Depthwise Conv2d weight [C,1,k,k] -> cached [k,k,C] (the layout the dwconv kernel reads 16 bytes per tap)."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version)
+    cache = getattr(conv, "_b200_wt", None)
+    if cache is None or cache[0] != key:
+        conv._b200_wt = (key, ops.dwconv_weight_t(w))
+        cache = conv._b200_wt
+    return cache[1]
 
 
 def _conv_weight_khwc(conv):

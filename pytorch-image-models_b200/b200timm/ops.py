@@ -20,7 +20,9 @@ __all__ = [
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream on the current device; torch.cuda.current_stream() costs ~13 us of
+    # Python per call (device-index / availability checks), this is a direct C call
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 # ------------------------------------------------------------------------------------ launch accounting
@@ -325,17 +327,22 @@ def colsum(x2d, out=None, accumulate=False):
 
 
 # --------------------------------------------------------------------------------------------- ConvNeXt (NHWC)
-def dwconv_nhwc(x, weight, bias):
-    """Depthwise k x k conv (stride 1, pad k//2) on a contiguous bf16 [B,H,W,C] tensor; weight [C,1,k,k]."""
-    _need_cuda(x, weight, bias)
+def dwconv_weight_t(weight):
+    """nn.Conv2d depthwise weight [C,1,k,k] -> the [k,k,C] layout b200_dwconv_nhwc consumes (do once, cache)."""
+    return weight.detach().reshape(weight.shape[0], -1).t().contiguous().view(weight.shape[-2], weight.shape[-1], -1)
+
+
+def dwconv_nhwc(x, weight_t, bias):
+    """Depthwise k x k conv (stride 1, pad k//2) on a contiguous bf16 [B,H,W,C] tensor; weight_t [k,k,C]."""
+    _need_cuda(x, weight_t, bias)
     if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_contiguous():
         raise B200Error("dwconv_nhwc: need a contiguous bf16 [B,H,W,C] tensor")
     B, H, W, C = x.shape
-    k = weight.shape[-1]
-    if tuple(weight.shape) != (C, 1, k, k) or weight.dtype != torch.bfloat16 or not weight.is_contiguous():
-        raise B200Error("dwconv_nhwc: weight must be contiguous bf16 [C,1,k,k]")
+    k = weight_t.shape[0]
+    if tuple(weight_t.shape) != (k, k, C) or weight_t.dtype != torch.bfloat16 or not weight_t.is_contiguous():
+        raise B200Error("dwconv_nhwc: weight_t must be contiguous bf16 [k,k,C] (see dwconv_weight_t)")
     y = torch.empty_like(x)
-    rc = _lib.load().b200_dwconv_nhwc(x.data_ptr(), weight.data_ptr(), _ptr(bias), y.data_ptr(), B, H, W, C, k,
+    rc = _lib.load().b200_dwconv_nhwc(x.data_ptr(), weight_t.data_ptr(), _ptr(bias), y.data_ptr(), B, H, W, C, k,
                                       _dt(bias) if bias is not None else DTYPE_BF16, _stream())
     _lib.check(rc, "b200_dwconv_nhwc")
     _count()
@@ -388,3 +395,43 @@ def naflex_assemble(proj, prefix, table, pos_off, pos_len, B, N, n_prefix, D):
     _lib.check(rc, "b200_naflex_assemble")
     _count()
     return tokens
+
+
+# --------------------------------------------------------------------------------------------- per-op timing (tools)
+_op_timing = None
+
+
+def enable_op_timing(flag):
+    """tools/bench_model.py --detail: bracket every op wrapper of this module with CUDA events (by op name)."""
+    global _op_timing
+    _op_timing = {} if flag else None
+
+
+def op_timing_summary():
+    if not _op_timing:
+        return {}
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in _op_timing.items()}
+
+
+def _timed(name, fn):
+    def wrapper(*args, **kwargs):
+        if _op_timing is None:
+            return fn(*args, **kwargs)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args, **kwargs)
+        b.record()
+        key = name
+        if name == "gemm":
+            key = f"gemm M={args[2]} N={args[3]} K={args[4]} epi={kwargs.get('epilogue', 0)}"
+        _op_timing.setdefault(key, []).append((a, b))
+        return out
+    wrapper.__name__ = fn.__name__
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
+
+
+for _n in ("layernorm_fwd", "layernorm_bwd", "gemm", "attention_fwd", "attention_bwd", "patchify", "assemble_tokens",
+           "colsum", "convert_f32", "dwconv_nhwc", "patchify_nhwc", "avgpool_nhwc", "naflex_assemble"):
+    globals()[_n] = _timed(_n, globals()[_n])

@@ -49,9 +49,12 @@ def run(args, rank, world, dev):
     ops.reset_counters()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    import time
     t0.record()
+    h0 = time.perf_counter()
     for i in range(args.steps):
         step(xs[i & 1], ys[i & 1])
+    host_ms = (time.perf_counter() - h0) * 1e3 / args.steps    # time the host needs to ENQUEUE one step
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
@@ -94,7 +97,7 @@ def run(args, rank, world, dev):
                    "flush": "two alternating 77 MB input batches; ~25 GB of activations / gradients streamed per step"},
         "e2e": {"value": round(total / (e2e_ms / 1e3), 1), "unit": "img/s",
                 "h2d_bytes_per_step": host_x[0].numel() * 2 + host_y[0].numel() * 8, "d2h_bytes_per_step": 4},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": round(host_ms, 2),
         "roofline": {"bound": "tensor", "kernel": "whole training step (3 x forward FLOPs)", "achieved": round(tf, 1),
                      "peak": peak, "unit": "TFLOP/s", "frac": round(tf / peak, 4), "traffic": None},
     }

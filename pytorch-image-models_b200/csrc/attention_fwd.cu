@@ -10,6 +10,7 @@
 // Replaces timm/layers/attention.py:115-135 (reshape/permute/unbind + F.scaled_dot_product_attention +
 // transpose/reshape); key-padding masks (naflexvit.py:964-1029) are given as per-sample key counts.
 #include "common.h"
+#include <cstdlib>
 #include "ptx.cuh"
 
 namespace b200 {
@@ -40,7 +41,7 @@ struct AttnParams {
   float scale, scale_log2e;
 };
 
-template <int KB, bool OVERLAY>
+template <int KB, bool OVERLAY, bool PTMEM>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                 const AttnParams p) {
@@ -173,6 +174,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (c + 1 < kFull) tmem_ld_x32(tmem_row + (c + 1) * 32, r[(c + 1) & 1]);
         else if (kTail16) tmem_ld_x16(tmem_row + kFull * 32, reinterpret_cast<uint32_t(&)[16]>(r[(c + 1) & 1]));
         const bool full = (c + 1) * 32 <= nvalid;
+        uint32_t pt[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint32_t o[4];
@@ -189,12 +191,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             lsum2 = add2(lsum2, pk(e0, e1));
             o[i] = pack_bf16(e0, e1);
           }
-          *reinterpret_cast<uint4*>(prow + (c * 4 + g) * (kQTile * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+          if constexpr (PTMEM) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pt[g * 4 + i] = o[i];
+          } else {
+            *reinterpret_cast<uint4*>(prow + (c * 4 + g) * (kQTile * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
         }
+        if constexpr (PTMEM) tmem_st_x16(tmem_row + c * 16, pt);   // P chunk c: bf16 pairs -> TMEM columns [16c, 16c+16)
       }
       if (kTail16) {
         uint32_t(&t)[16] = reinterpret_cast<uint32_t(&)[16]>(r[kFull & 1]);
         tmem_ld_wait_x16(t);
+        uint32_t pt8[8];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint32_t o[4];
@@ -208,8 +217,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             lsum2 = add2(lsum2, pk(e0, e1));
             o[i] = pack_bf16(e0, e1);
           }
-          *reinterpret_cast<uint4*>(prow + (kFull * 4 + g) * (kQTile * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+          if constexpr (PTMEM) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pt8[g * 4 + i] = o[i];
+          } else {
+            *reinterpret_cast<uint4*>(prow + (kFull * 4 + g) * (kQTile * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
         }
+        if constexpr (PTMEM) tmem_st_x8(tmem_row + kFull * 16, pt8);
       }
     }
     {
@@ -219,11 +234,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     m_run = m_new;
 
-    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+    if constexpr (PTMEM) tmem_st_wait();
+    else fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
 
-    if (tid == 0) {
+    constexpr int kOCol = PTMEM ? 128 : 0;   // P occupies TMEM columns [0, KB/2): O goes above it
+    if (tid == 0 && PTMEM) {
+      tc_fence_after();
+      // O = P V with P read from TMEM (bf16 pairs, 8 columns per K=16 step), V MN-major from smem
+      const uint64_t vd = make_smem_desc(smem_u32(sV), 1024, 1024, kLayoutSw128);
+#pragma unroll
+      for (int k = 0; k < KB / 16; ++k)
+        umma_ts(tmem_base + kOCol, tmem_base + k * 8, vd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o, k > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+    if (tid == 0 && !PTMEM) {
       tc_fence_after();
       // P: K-major, no swizzle: core matrices 8 rows x 16 B; row groups 128 B apart (SBO), the two
       //    8-key chunks of one K=16 step 2048 B apart (LBO).   V: MN-major SW128, 16 keys = 2048 B.
@@ -243,7 +269,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < kHd; c += 32) {
         uint32_t r[32];
-        tmem_ld_x32(tmem_row + c, r);
+        tmem_ld_x32(tmem_row + kOCol + c, r);
         tmem_ld_wait_x32(r);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -268,7 +294,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint32_t o[16];
       if constexpr (OVERLAY) {
         uint32_t r[32];
-        tmem_ld_x32(tmem_row + c, r);
+        tmem_ld_x32(tmem_row + (PTMEM ? 128 : 0) + c, r);
         tmem_ld_wait_x32(r);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -302,7 +328,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
-template <int KB, bool OVERLAY>
+template <int KB, bool OVERLAY, bool PTMEM>
 static int launch_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H,
                            float scale, cudaStream_t st) {
   using L = AttnSmem<KB, OVERLAY>;
@@ -319,7 +345,7 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse, const int32_t
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse; p.kv_len = kv_len; p.B = B; p.N = N; p.H = H;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
-  auto kern = attn_fwd_kernel<KB, OVERLAY>;
+  auto kern = attn_fwd_kernel<KB, OVERLAY, PTMEM>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -344,7 +370,9 @@ extern "C" int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32
   B200_CHECK_ARG(B <= 65535 && H <= 65535, "b200_attn_fwd: B/H exceed the grid limits");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "b200_attn_fwd: qkv/out must be 16-byte aligned");
-  if (N <= 208) return launch_attn_fwd<208, true>(qkv, out, lse, kv_len, B, N, H, scale, st);
-  if (N <= 256) return launch_attn_fwd<256, true>(qkv, out, lse, kv_len, B, N, H, scale, st);
-  return launch_attn_fwd<128, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
+  static const bool ptmem = [] { const char* e = getenv("B200_ATTN_PTMEM"); return e != nullptr && e[0] == '1'; }();
+  if (ptmem && N <= 208) return launch_attn_fwd<208, true, true>(qkv, out, lse, kv_len, B, N, H, scale, st);
+  if (N <= 208) return launch_attn_fwd<208, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
+  if (N <= 256) return launch_attn_fwd<256, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
+  return launch_attn_fwd<128, false, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
 }

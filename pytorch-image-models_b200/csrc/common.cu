@@ -2,6 +2,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <cudaTypedefs.h>
 
 namespace b200 {
@@ -56,8 +57,56 @@ int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t
   return encode_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle);
 }
 
+// Descriptor cache: cuTensorMapEncodeTiled costs a few microseconds and every GEMM launch needs up to five maps;
+// in steady state (training steps, CUDA-graph re-captures) the same (address, shape, box) tuples repeat because the
+// caching allocator hands back the same blocks.  A map encodes only address / shape / layout -- no ownership -- so
+// reusing one for an identical tuple is always valid.  Per-thread, direct-mapped, 1024 entries.
+struct TmapKey {
+  const void* base;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  int32_t rank, dt, swizzle;
+};
+struct TmapEntry {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+static thread_local TmapEntry g_tmap_cache[1024];
+
+static int encode_tmap_uncached(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank,
+                                const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle);
+
 static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.rank = rank; key.dt = static_cast<int32_t>(dt); key.swizzle = swizzle;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i > 0) key.strides[i - 1] = strides_bytes[i - 1];
+  }
+  uint64_t h = 1469598103934665603ull;
+  const unsigned char* kb = reinterpret_cast<const unsigned char*>(&key);
+  for (size_t i = 0; i < sizeof(key); ++i) h = (h ^ kb[i]) * 1099511628211ull;
+  TmapEntry& e = g_tmap_cache[h & 1023];
+  if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) {
+    *out = e.map;
+    return B200_OK;
+  }
+  const int rc = encode_tmap_uncached(out, dt, base, rank, dims, strides_bytes, box, swizzle);
+  if (rc == B200_OK) {
+    e.key = key;
+    e.map = *out;
+    e.valid = true;
+  }
+  return rc;
+}
+
+static int encode_tmap_uncached(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank,
+                                const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle) {
   EncodeTiledFn fn = resolve_encode();
   if (fn == nullptr) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t gdim[5];

@@ -6,7 +6,7 @@
 //   avgpool_nhwc     global average pool over H*W (classifier.py:211-213)
 // The depthwise conv is FMA-bound in fp32 (49 MACs per output element, 0.23 GMAC/img for ConvNeXt-B), not HBM-bound;
 // each thread keeps a strip of TW output pixels x 8 channels in registers and slides along the row so every loaded
-// input vector feeds up to 7 taps.
+// input vector feeds up to 7 taps; weights are consumed pre-transposed ([k*k][C]) so a tap is one 16-byte load.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -15,79 +15,72 @@ namespace b200 {
 constexpr int kDwTW = 7;   // output pixels per thread along W
 
 template <int KS>
-__global__ void __launch_bounds__(64)
-dwconv_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+__global__ void __launch_bounds__(256)
+dwconv_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wt,
                    const void* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C,
                    int bias_f32) {
-  // weights of this CTA's 8-channel groups, transposed to [tap][channel] so a thread reads 16 B per tap
-  extern __shared__ __align__(16) __nv_bfloat16 sw[];   // [KS*KS][cvec_per_cta * 8]
+  // wt: weights pre-transposed to [KS*KS][C] so the 8 channels of a thread are one 16-byte load per tap and
+  // consecutive threads (consecutive channel groups) read consecutive addresses (L1-resident: 49*C*2 bytes).
   constexpr int PAD = KS / 2;
   const int cvecs = C >> 3;
-  const int cv_per_cta = blockDim.x;                       // one 8-channel group per thread in x
-  const int cv0 = blockIdx.x * cv_per_cta;
-  const int cv = cv0 + threadIdx.x;
-  for (int i = threadIdx.x; i < KS * KS * cv_per_cta * 8; i += blockDim.x) {
-    const int tap = i / (cv_per_cta * 8);
-    const int cl = i - tap * (cv_per_cta * 8);
-    const int c = cv0 * 8 + cl;
-    sw[i] = (c < C) ? w[static_cast<long long>(c) * KS * KS + tap] : __float2bfloat16(0.f);
-  }
-  __syncthreads();
-  if (cv >= cvecs) return;
   const int strips = (W + kDwTW - 1) / kDwTW;
-  const long long total = static_cast<long long>(B) * H * strips;
-  float bv[8];
-  if (bias != nullptr) {
-    if (bias_f32) {
-      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bias) + cv * 8);
-      const float4 a = __ldg(p), b2 = __ldg(p + 1);
-      bv[0] = a.x; bv[1] = a.y; bv[2] = a.z; bv[3] = a.w; bv[4] = b2.x; bv[5] = b2.y; bv[6] = b2.z; bv[7] = b2.w;
-    } else {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(bias) + cv * 8));
-      bv[0] = bf16_lo(q.x); bv[1] = bf16_hi(q.x); bv[2] = bf16_lo(q.y); bv[3] = bf16_hi(q.y);
-      bv[4] = bf16_lo(q.z); bv[5] = bf16_hi(q.z); bv[6] = bf16_lo(q.w); bv[7] = bf16_hi(q.w);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) bv[j] = 0.f;
-  }
-  for (long long item = blockIdx.y; item < total; item += gridDim.y) {
+  const long long total = static_cast<long long>(B) * H * strips * cvecs;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvecs);
+    long long item = idx / cvecs;
     const int strip = static_cast<int>(item % strips);
-    const int oy = static_cast<int>((item / strips) % H);
-    const int b = static_cast<int>(item / (static_cast<long long>(strips) * H));
+    item /= strips;
+    const int oy = static_cast<int>(item % H);
+    const int b = static_cast<int>(item / H);
     const int ox0 = strip * kDwTW;
     f32x2 acc[kDwTW][4];
+    {
+      f32x2 b0 = 0ull, b1 = 0ull, b2 = 0ull, b3 = 0ull;
+      if (bias != nullptr) {
+        if (bias_f32) {
+          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bias) + cv * 8);
+          const float4 a = __ldg(p), c2 = __ldg(p + 1);
+          b0 = pk(a.x, a.y); b1 = pk(a.z, a.w); b2 = pk(c2.x, c2.y); b3 = pk(c2.z, c2.w);
+        } else {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(bias) + cv * 8));
+          b0 = bf16x2_to_f32x2(q.x); b1 = bf16x2_to_f32x2(q.y); b2 = bf16x2_to_f32x2(q.z); b3 = bf16x2_to_f32x2(q.w);
+        }
+      }
 #pragma unroll
-    for (int t = 0; t < kDwTW; ++t) {
-      acc[t][0] = pk(bv[0], bv[1]); acc[t][1] = pk(bv[2], bv[3]);
-      acc[t][2] = pk(bv[4], bv[5]); acc[t][3] = pk(bv[6], bv[7]);
+      for (int t = 0; t < kDwTW; ++t) { acc[t][0] = b0; acc[t][1] = b1; acc[t][2] = b2; acc[t][3] = b3; }
     }
 #pragma unroll 1
     for (int ky = 0; ky < KS; ++ky) {
       const int iy = oy + ky - PAD;
       if (iy < 0 || iy >= H) continue;
-      f32x2 wt[KS][4];
+      // issue every load of this kernel row first (branch-free, predicated), then do the arithmetic: the 7 weight
+      // vectors and the TW + KS - 1 input vectors are all in flight together instead of one L2 round trip each
+      uint4 wq[KS];
 #pragma unroll
-      for (int kx = 0; kx < KS; ++kx) {
-        const uint4 q = *reinterpret_cast<const uint4*>(sw + (ky * KS + kx) * (cv_per_cta * 8) + threadIdx.x * 8);
-        wt[kx][0] = bf16x2_to_f32x2(q.x); wt[kx][1] = bf16x2_to_f32x2(q.y);
-        wt[kx][2] = bf16x2_to_f32x2(q.z); wt[kx][3] = bf16x2_to_f32x2(q.w);
-      }
+      for (int kx = 0; kx < KS; ++kx)
+        wq[kx] = __ldg(reinterpret_cast<const uint4*>(wt + static_cast<long long>(ky * KS + kx) * C + cv * 8));
       const __nv_bfloat16* row = x + ((static_cast<long long>(b) * H + iy) * W) * C + cv * 8;
+      uint4 in[kDwTW + KS - 1];
 #pragma unroll
       for (int i = 0; i < kDwTW + KS - 1; ++i) {
         const int ix = ox0 + i - PAD;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * C));
-        const f32x2 v0 = bf16x2_to_f32x2(q.x), v1 = bf16x2_to_f32x2(q.y), v2 = bf16x2_to_f32x2(q.z), v3 = bf16x2_to_f32x2(q.w);
+        const bool ok = ix >= 0 && ix < W;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ok ? ix : 0) * C));
+        in[i] = ok ? q : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < kDwTW + KS - 1; ++i) {
+        const f32x2 v0 = bf16x2_to_f32x2(in[i].x), v1 = bf16x2_to_f32x2(in[i].y), v2 = bf16x2_to_f32x2(in[i].z),
+                    v3 = bf16x2_to_f32x2(in[i].w);
 #pragma unroll
         for (int kx = 0; kx < KS; ++kx) {
           const int t = i - kx;   // output pixel (within the strip) this input contributes to through tap kx
           if (t >= 0 && t < kDwTW) {
-            acc[t][0] = fma2(v0, wt[kx][0], acc[t][0]);
-            acc[t][1] = fma2(v1, wt[kx][1], acc[t][1]);
-            acc[t][2] = fma2(v2, wt[kx][2], acc[t][2]);
-            acc[t][3] = fma2(v3, wt[kx][3], acc[t][3]);
+            acc[t][0] = fma2(v0, bf16x2_to_f32x2(wq[kx].x), acc[t][0]);
+            acc[t][1] = fma2(v1, bf16x2_to_f32x2(wq[kx].y), acc[t][1]);
+            acc[t][2] = fma2(v2, bf16x2_to_f32x2(wq[kx].z), acc[t][2]);
+            acc[t][3] = fma2(v3, bf16x2_to_f32x2(wq[kx].w), acc[t][3]);
           }
         }
       }
@@ -152,25 +145,15 @@ __global__ void avgpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 }
 
 template <int KS>
-static int launch_dwconv(const void* x, const void* w, const void* bias, void* y, int B, int H, int W, int C,
+static int launch_dwconv(const void* x, const void* wt, const void* bias, void* y, int B, int H, int W, int C,
                          int bias_f32, cudaStream_t st) {
-  const int cvecs = C / 8;
-  int threads = cvecs < 64 ? ((cvecs + 31) / 32) * 32 : 64;
-  const int gx = (cvecs + threads - 1) / threads;
-  const long long items = static_cast<long long>(B) * H * ((W + kDwTW - 1) / kDwTW);
-  long long gy = items;
-  const long long cap = static_cast<long long>(sm_count()) * 16 / gx + 1;
-  if (gy > cap) gy = cap;
-  if (gy > 65535) gy = 65535;
-  const size_t smem = static_cast<size_t>(KS) * KS * threads * 8 * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(dwconv_nhwc_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      KS * KS * 64 * 8 * static_cast<int>(sizeof(__nv_bfloat16))));
-    attr_set = true;
-  }
-  dwconv_nhwc_kernel<KS><<<dim3(gx, static_cast<unsigned>(gy)), threads, smem, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(w), bias,
+  const long long total = static_cast<long long>(B) * H * ((W + kDwTW - 1) / kDwTW) * (C / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  dwconv_nhwc_kernel<KS><<<static_cast<int>(blocks), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(wt), bias,
       reinterpret_cast<__nv_bfloat16*>(y), B, H, W, C, bias_f32);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
@@ -180,16 +163,16 @@ static int launch_dwconv(const void* x, const void* w, const void* bias, void* y
 
 using namespace b200;
 
-extern "C" int b200_dwconv_nhwc(const void* x, const void* weight, const void* bias, void* y, int32_t B, int32_t H,
+extern "C" int b200_dwconv_nhwc(const void* x, const void* weight_t, const void* bias, void* y, int32_t B, int32_t H,
                                 int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  B200_CHECK_ARG(x && weight && y, "b200_dwconv_nhwc: null pointer");
+  B200_CHECK_ARG(x && weight_t && y, "b200_dwconv_nhwc: null pointer");
   B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "b200_dwconv_nhwc: bad shape (C %% 8 == 0)");
   const int bf = bias_dtype == B200_DTYPE_F32;
   switch (ksize) {
-    case 7: return launch_dwconv<7>(x, weight, bias, y, B, H, W, C, bf, st);
-    case 5: return launch_dwconv<5>(x, weight, bias, y, B, H, W, C, bf, st);
-    case 3: return launch_dwconv<3>(x, weight, bias, y, B, H, W, C, bf, st);
+    case 7: return launch_dwconv<7>(x, weight_t, bias, y, B, H, W, C, bf, st);
+    case 5: return launch_dwconv<5>(x, weight_t, bias, y, B, H, W, C, bf, st);
+    case 3: return launch_dwconv<3>(x, weight_t, bias, y, B, H, W, C, bf, st);
     default: return fail(B200_ERR_UNSUPPORTED, "b200_dwconv_nhwc: kernel size %d not supported (3, 5, 7)", ksize);
   }
 }

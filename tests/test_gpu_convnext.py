@@ -28,7 +28,7 @@ def test_dwconv_nhwc(k, B, H, W, C):
     x = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
     w = (torch.randn(C, 1, k, k, device="cuda", generator=g) * 0.2).bfloat16()
     b = torch.randn(C, device="cuda", generator=g).bfloat16()
-    y = ops.dwconv_nhwc(x, w, b)
+    y = ops.dwconv_nhwc(x, ops.dwconv_weight_t(w), b)
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=k // 2, groups=C)
     _check(y, ref.permute(0, 2, 3, 1), 2e-2, 1e-2, f"dwconv k={k} {B}x{H}x{W}x{C}")
 

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--img-size", type=int, default=224)
+    ap.add_argument("--detail", action="store_true", help="per-op CUDA-event time split of one step")
     args = ap.parse_args()
     from b200timm import ops
     if args.model.startswith("convnext"):
@@ -44,6 +45,15 @@ def main():
         t1.record()
         torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / args.steps
+    if args.detail:
+        with torch.no_grad():
+            ops.enable_op_timing(True)
+            model(xs[0])
+            det = ops.op_timing_summary()
+            ops.enable_op_timing(False)
+        tot = sum(t for _, t in det.values())
+        for k, (n, t) in sorted(det.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {t:8.3f} ms {100 * t / tot:5.1f}%  n={n:3d}  {k}")
     print(json.dumps({"model": args.model, "batch": args.batch, "img_size": size, "ms_per_step": round(ms, 3),
                       "img_per_s": round(args.batch / ms * 1e3, 1), "launches_per_step": ops.launch_count() // args.steps}))
 
