@@ -93,8 +93,8 @@ def cpu_port_throughput(batch, steps, warmup, dtype=torch.bfloat16, threads=None
     """The reference path on the host CPU: oracle.vit_oracle.vit_forward_eager issues the same torch CPU
     library calls timm's eager forward does (F.conv2d / layer_norm / linear / sdpa / gelu).  img/s."""
     from oracle import vit_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every core it may run on
+    torch.set_num_threads(threads or max(1, len(os.sched_getaffinity(0))))
     cfg = dict(O.VIT_CONFIGS[MODEL])
     sd = {k: v.to(dtype) for k, v in O.random_state_dict(cfg, seed=42).items()}
     g = torch.Generator().manual_seed(0)

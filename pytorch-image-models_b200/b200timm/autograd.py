@@ -183,22 +183,45 @@ class BlockFn(torch.autograd.Function):
          mean2, rstd2, pre, act) = ctx.saved_tensors
         B, N, D, H, hd, scale = ctx.meta
         dx2 = _c(dy.reshape(B * N, D))
+        # All parameter gradients of the block live in ONE zeroed fp32 workspace (wgrad split-K reduce-adds, bias
+        # column sums and LayerNorm dgamma/dbeta write straight into views of it) and are converted to the
+        # parameters' dtype with ONE kernel: 1 memset + 1 convert per block instead of ~20 of each.
+        params = (n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2)
+        sizes = [0 if p is None else p.numel() for p in params]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)
+        ws = torch.zeros(offs[-1], dtype=torch.float32, device=dx2.device)
+        v = [None if p is None else ws[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
         # ---- MLP branch:  x2 = x1 + fc2(GELU(fc1(LN2(x1))))
         dpre = ops.linear_dgrad(dx2, w2, epilogue=ops.EPI_DGELU, aux=pre)            # dY W2 * GELU'(pre)
-        g_w2, g_b2 = _wgrad(dx2, act, w2), _bias_grad(dx2, b2)
+        ops.linear_wgrad(dx2, act, out=v[10])
+        if b2 is not None:
+            ops.colsum(dx2, out=v[11], accumulate=True)
         dh2 = ops.linear_dgrad(dpre, w1)
-        g_w1, g_b1 = _wgrad(dpre, h2, w1), _bias_grad(dpre, b1)
-        dx1, dn2w, dn2b = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2)    # + residual gradient
+        ops.linear_wgrad(dpre, h2, out=v[8])
+        if b1 is not None:
+            ops.colsum(dpre, out=v[9], accumulate=True)
+        dx1, _, _ = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dw_out=v[6], db_out=v[7])
         # ---- attention branch:  x1 = x0 + proj(SDPA(qkv(LN1(x0))))
         do = ops.linear_dgrad(dx1, wproj)
-        g_wp, g_bp = _wgrad(dx1, o.view(B * N, -1), wproj), _bias_grad(dx1, bproj)
+        ops.linear_wgrad(dx1, o.view(B * N, -1), out=v[4])
+        if bproj is not None:
+            ops.colsum(dx1, out=v[5], accumulate=True)
         dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
         dh1 = ops.linear_dgrad(dqkv, wqkv)
-        g_wq, g_bq = _wgrad(dqkv, h1, wqkv), _bias_grad(dqkv, bqkv)
-        dx0, dn1w, dn1b = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1)
-        return (dx0.view(B, N, D), _to_param_dtype(dn1w, n1w), _to_param_dtype(dn1b, n1b), g_wq, g_bq, g_wp, g_bp,
-                _to_param_dtype(dn2w, n2w), _to_param_dtype(dn2b, n2b), g_w1, g_b1, g_w2, g_b2,
-                None, None, None, None, None)
+        ops.linear_wgrad(dqkv, h1, out=v[2])
+        if bqkv is not None:
+            ops.colsum(dqkv, out=v[3], accumulate=True)
+        dx0, _, _ = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dw_out=v[0], db_out=v[1])
+        pdt = next(p.dtype for p in params if p is not None)
+        if pdt == torch.float32:
+            grads = v
+        else:
+            gbuf = torch.empty(offs[-1], dtype=pdt, device=dx2.device)
+            ops.convert_f32(ws, gbuf)
+            grads = [None if p is None else gbuf[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
+        return (dx0.view(B, N, D), *grads, None, None, None, None, None)
 
 
 class PatchEmbedFn(torch.autograd.Function):

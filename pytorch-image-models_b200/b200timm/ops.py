@@ -107,7 +107,7 @@ def layernorm_fwd(x, weight, bias, eps, out_dtype=None, save_stats=False):
     return y.view(*x.shape[:-1], cols), mean, rstd
 
 
-def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True, dres=None):
+def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True, dres=None, dw_out=None, db_out=None):
     """Returns (dx, dweight fp32, dbias fp32).  dres (dtype/shape of x): gradient of the residual branch around
     the norm, added into dx in the same pass."""
     _need_cuda(dy, x, weight, mean, rstd, dres)
@@ -125,8 +125,8 @@ def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True, dres=None):
     dx = torch.empty_like(x2)
     dw = db = None
     if need_param_grads:
-        dw = torch.empty(cols, dtype=torch.float32, device=x.device)
-        db = torch.empty(cols, dtype=torch.float32, device=x.device)
+        dw = dw_out if dw_out is not None else torch.empty(cols, dtype=torch.float32, device=x.device)
+        db = db_out if db_out is not None else torch.empty(cols, dtype=torch.float32, device=x.device)
     if dres is not None:
         dres = dres.reshape(-1, cols)
         if dres.dtype != x2.dtype or dres.shape != x2.shape:
@@ -222,12 +222,12 @@ def _wgrad_split(rows_out, cols_out, k):
     return split
 
 
-def linear_wgrad(dy2d, x2d, grad_out=None):
-    """dW[N,K] = dY[M,N]^T @ X[M,K] in fp32 (both operands MN-major in place, split-K through TMA reduce-add),
-    then handed to `grad_out` (the parameter's .grad buffer, bf16 or fp32): accumulated when it already exists."""
+def linear_wgrad(dy2d, x2d, out=None):
+    """dW[N,K] = dY[M,N]^T @ X[M,K] in fp32 (both operands MN-major in place, split-K through TMA reduce-add).
+    `out`: optional ZERO-INITIALISED (or to-be-accumulated-into) fp32 [N,K] buffer."""
     M, N = dy2d.shape
     K = x2d.shape[1]
-    ws = torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)
+    ws = out if out is not None else torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)
     gemm(dy2d, x2d, N, K, M, a_mn=True, b_mn=True, out=ws, split_k=max(2, _wgrad_split(N, K, M)))
     return ws
 

@@ -13,6 +13,7 @@
 //     dQ  += dS K                        the same dS^T tile read MN-major as A; accumulated in TMEM over key tiles
 // so dK / dV / dQ of a head are complete inside the CTA: no atomics, no second pass.
 // delta[q] = sum_d dO[q,d] * O[q,d] comes from attn_bwd_delta_kernel.
+#include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -365,6 +366,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
 }  // namespace b200
 
+namespace b200 {
+int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                     const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st);
+}
+
 using namespace b200;
 
 extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
@@ -382,6 +388,10 @@ extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout,
         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, N, H);
     B200_CUDA_OK(cudaGetLastError());
   }
+  // v2 (attention_bwd2.cu: two query halves, 8 compute warps + issuer warp) is the default; B200_ATTN_BWD_V1=1 keeps
+  // the simpler v1 kernel of this file selectable for A/B comparison and as a cross-check in the tests.
+  static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_BWD_V1"); return e != nullptr && e[0] == '1'; }();
+  if (!use_v1) return launch_attn_bwd2(qkv, dout, lse, delta, dqkv, kv_len, B, N, H, scale, st);
   CUtensorMap tq, tdo;
   uint32_t box[2] = {kHd, kNQ};
   {

@@ -1,0 +1,311 @@
+// Attention backward v2 for sm_100a (head_dim 64, N <= 208 tokens) -- the kernel b200_attn_bwd launches.
+// Same mathematics and transposed-domain formulation as attention_bwd.cu (kept as the v1 reference path), but
+// organised so the tensor core and the 256 softmax threads overlap:
+//   * queries are processed in two halves of 112 (MMA N = 112) so that S^T and dP^T each get their OWN TMEM region
+//     (2 x 112 columns) next to the five persistent accumulators dV, dK (current key tile), dQ (both halves):
+//     112 + 112(+pad) + 64*4 = 512 columns exactly;
+//   * S^T and dP^T of a (key tile, query half) step are issued together, one pass over both produces P^T and dS^T
+//     (bf16 core matrices in smem), split by columns across two warpgroups (8 warps);
+//   * a dedicated issuer warp queues [dV += P^T dO, dK += dS^T Q, dQ += dS K] of step i followed immediately by
+//     [S^T, dP^T] of step i+1, so the MMA pipe never drains between steps.
+// No atomics: dK / dV of a key tile accumulate over the query halves, dQ of a query half over the key tiles, all in TMEM.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+namespace {
+constexpr int kHd = 64;
+constexpr int kNQ = 208;                         // tokens loaded per operand tile (TMA box rows)
+constexpr int kQH = 112;                         // queries per half (MMA N)
+constexpr int kRowB = kHd * 2;                   // 128 B per token row
+constexpr int kTileB = kNQ * kRowB;              // 26624
+constexpr int kOffQ = 0, kOffK = kTileB, kOffV = 2 * kTileB, kOffDO = 3 * kTileB;
+constexpr int kOffPad = 4 * kTileB;              // 2 KB of zeros: the q-half-1 over-read of dO (rows 208..223)
+constexpr int kOffP = kOffPad + 2048;            // P^T : 14 chunks of [128 keys x 8 queries] bf16
+constexpr int kPB = (kQH / 8) * 2048;            // 28672
+constexpr int kOffDS = kOffP + kPB;              // dS^T: 16 chunks (the dQ MMA reads a full 128-query M tile)
+constexpr int kDSB = 16 * 2048;
+constexpr int kOffLse = kOffDS + kDSB;
+constexpr int kOffDelta = kOffLse + 2 * kQH * 4;
+constexpr int kOffBar = kOffDelta + 2 * kQH * 4;
+constexpr int kSmemTotal = kOffBar + 64 + 1024;
+constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ0 = 384, kColDQ1 = 448;
+constexpr int kComputeThreads = 256;
+}  // namespace
+
+struct AttnBwd2Params {
+  const float* lse;
+  const float* delta;
+  __nv_bfloat16* dqkv;
+  const int* kv_len;
+  int B, N, H;
+  float scale, scale_log2e;
+};
+
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, uint32_t taddr, bool ok) {
+#pragma unroll
+  for (int c = 0; c < kHd; c += 32) {
+    uint32_t r[32];
+    tmem_ld_x32(taddr + c, r);
+    tmem_ld_wait_x32(r);
+    if (ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        reinterpret_cast<uint4*>(dst + c)[g] =
+            make_uint4(pack_bf16(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])),
+                       pack_bf16(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
+                       pack_bf16(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
+                       pack_bf16(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+    }
+  }
+}
+
+// one group of 8 queries: p = exp2(s*c - lse2), ds = p * (dp - delta) * scale  -> 16 B of P^T and dS^T each
+__device__ __forceinline__ void pds8(const uint32_t* s, const uint32_t* dp, const float* lse2, const float* delta,
+                                     f32x2 sc2, f32x2 scale2, bool key_ok, uint8_t* pdst, uint8_t* dsdst) {
+  uint32_t po[4], dso[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t0, t1;
+    upk(fma2(pk(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), sc2, pk(-lse2[2 * i], -lse2[2 * i + 1])), t0, t1);
+    const float p0 = key_ok ? ex2_approx(t0) : 0.f, p1 = key_ok ? ex2_approx(t1) : 0.f;
+    const f32x2 d = add2(pk(__uint_as_float(dp[2 * i]), __uint_as_float(dp[2 * i + 1])), pk(-delta[2 * i], -delta[2 * i + 1]));
+    float d0, d1;
+    upk(mul2(mul2(pk(p0, p1), d), scale2), d0, d1);
+    po[i] = pack_bf16(p0, p1);
+    dso[i] = key_ok ? pack_bf16(d0, d1) : 0u;
+  }
+  *reinterpret_cast<uint4*>(pdst) = make_uint4(po[0], po[1], po[2], po[3]);
+  *reinterpret_cast<uint4*>(dsdst) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
+}
+
+__global__ void __launch_bounds__(kComputeThreads + 32, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const AttnBwd2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + kOffQ;
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint8_t* sDO = smem + kOffDO;
+  uint8_t* sP = smem + kOffP;
+  uint8_t* sDS = smem + kOffDS;
+  float* sLse = reinterpret_cast<float*>(smem + kOffLse);
+  float* sDelta = reinterpret_cast<float*>(smem + kOffDelta);
+  uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bar_sd = bar_ld + 1;      // issuer -> compute: S^T / dP^T of the step are in TMEM
+  uint64_t* bar_p = bar_ld + 2;       // compute -> issuer: P^T / dS^T of the step are in smem (count 256)
+  uint64_t* bar_fin = bar_ld + 3;     // issuer -> compute: every MMA has completed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ld + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int N = p.N, H = p.H;
+  int kvlen = N;
+  if (p.kv_len != nullptr) kvlen = max(1, min(p.kv_len[b], N));
+  const int num_kt = (kvlen + 127) / 128;
+  const int num_steps = num_kt * 2;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_sd, 1);
+    mbar_init(bar_p, kComputeThreads);
+    mbar_init(bar_fin, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  for (int q = tid; q < 2 * kQH; q += blockDim.x) {
+    const long long idx = (static_cast<long long>(b) * H + h) * N + q;
+    sLse[q] = (q < N) ? p.lse[idx] * 1.4426950408889634f : INFINITY;   // +inf -> P = 0 for padding queries
+    sDelta[q] = (q < N) ? p.delta[idx] : 0.f;
+  }
+  for (int i = tid; i < 2048 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + kOffPad)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ issuer (TMA + tcgen05.mma), one thread
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_ld, 4 * kTileB);
+      tma_load_2d(sQ, &tm_qkv, bar_ld, h * kHd, b * N);
+      tma_load_2d(sK, &tm_qkv, bar_ld, (H + h) * kHd, b * N);
+      tma_load_2d(sV, &tm_qkv, bar_ld, (2 * H + h) * kHd, b * N);
+      tma_load_2d(sDO, &tm_do, bar_ld, h * kHd, b * N);
+      constexpr uint32_t idesc_sd = make_idesc_bf16(128, kQH, false, false);
+      constexpr uint32_t idesc_kv = make_idesc_bf16(128, kHd, false, true);
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, kHd, true, true);
+      auto issue_sd = [&](int step) {
+        const int kt = step >> 1, qh = step & 1;
+        const uint64_t kd = make_smem_desc(smem_u32(sK) + kt * 128 * kRowB, 16, 1024, kLayoutSw128);
+        const uint64_t vd = make_smem_desc(smem_u32(sV) + kt * 128 * kRowB, 16, 1024, kLayoutSw128);
+        const uint64_t qd = make_smem_desc(smem_u32(sQ) + qh * kQH * kRowB, 16, 1024, kLayoutSw128);
+        const uint64_t dod = make_smem_desc(smem_u32(sDO) + qh * kQH * kRowB, 16, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k) umma_ss(tmem_base + kColS, kd + 2 * k, qd + 2 * k, idesc_sd, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k) umma_ss(tmem_base + kColDP, vd + 2 * k, dod + 2 * k, idesc_sd, k > 0 ? 1u : 0u);
+      };
+      mbar_wait(bar_ld, 0);
+      tc_fence_after();
+      issue_sd(0);
+      umma_commit(bar_sd);
+      for (int step = 0; step < num_steps; ++step) {
+        const int kt = step >> 1, qh = step & 1;
+        mbar_wait(bar_p, step & 1);
+        tc_fence_after();
+        // dV_kt (+)= P^T dO_qh ; dK_kt (+)= dS^T Q_qh   (A: K-major core matrices, 8-query chunks 2048 B apart)
+        const uint64_t pd = make_smem_desc(smem_u32(sP), 2048, 128, kLayoutNone);
+        const uint64_t dsd = make_smem_desc(smem_u32(sDS), 2048, 128, kLayoutNone);
+        const uint64_t dob = make_smem_desc(smem_u32(sDO) + qh * kQH * kRowB, 1024, 1024, kLayoutSw128);
+        const uint64_t qb = make_smem_desc(smem_u32(sQ) + qh * kQH * kRowB, 1024, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < kQH / 16; ++k)
+          umma_ss(tmem_base + kColDV, pd + static_cast<uint64_t>(k * (4096 >> 4)), dob + static_cast<uint64_t>(k * (2048 >> 4)),
+                  idesc_kv, (qh > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < kQH / 16; ++k)
+          umma_ss(tmem_base + kColDK, dsd + static_cast<uint64_t>(k * (4096 >> 4)), qb + static_cast<uint64_t>(k * (2048 >> 4)),
+                  idesc_kv, (qh > 0 || k > 0) ? 1u : 0u);
+        // dQ_qh (+)= dS K_kt   (A: the same dS^T tile read MN-major; B: K_kt MN-major in place)
+        const uint64_t ad = make_smem_desc(smem_u32(sDS), 128, 2048, kLayoutNone);
+        const uint64_t kb = make_smem_desc(smem_u32(sK) + kt * 128 * kRowB, 1024, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_ss(tmem_base + (qh == 0 ? kColDQ0 : kColDQ1), ad + static_cast<uint64_t>(k * (256 >> 4)),
+                  kb + static_cast<uint64_t>(k * (2048 >> 4)), idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
+        if (step + 1 < num_steps) {
+          issue_sd(step + 1);
+          umma_commit(bar_sd);
+        } else {
+          umma_commit(bar_fin);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ compute warps: thread = key row, warpgroup = column half
+    const int wg = warp >> 2;                       // 0 / 1: which 56 of the 112 query columns
+    const int rowt = (warp & 3) * 32 + lane;        // key row inside the tile == TMEM lane
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const f32x2 sc2 = splat(p.scale_log2e), scale2 = splat(p.scale);
+    const long long tok_stride = 3LL * H * kHd;
+    for (int step = 0; step < num_steps; ++step) {
+      const int kt = step >> 1, qh = step & 1;
+      const int key = kt * 128 + rowt;
+      const bool key_ok = key < kvlen;
+      mbar_wait(bar_sd, step & 1);
+      tc_fence_after();
+      if (qh == 0 && kt > 0) {
+        // dV / dK of the previous key tile are complete (their MMAs were queued ahead of this step's S^T / dP^T)
+        const int pkey = (kt - 1) * 128 + rowt;
+        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * N + pkey) * tok_stride + ((wg == 0 ? 2 : 1) * H + h) * kHd;
+        store_row64(dst, tmem_row + (wg == 0 ? kColDV : kColDK), pkey < N);
+      }
+      const int c0 = wg * 56;                        // first query column (within the half) of this warpgroup
+      const float* l2 = sLse + qh * kQH + c0;
+      const float* dl = sDelta + qh * kQH + c0;
+      uint8_t* prow = sP + (c0 >> 3) * 2048 + rowt * 16;
+      uint8_t* dsrow = sDS + (c0 >> 3) * 2048 + rowt * 16;
+      {
+        uint32_t s[32], d[32];
+        tmem_ld_x32(tmem_row + kColS + c0, s);
+        tmem_ld_x32(tmem_row + kColDP + c0, d);
+        tmem_ld_wait_x32(s);
+        tmem_ld_wait_x32(d);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          pds8(s + g * 8, d + g * 8, l2 + g * 8, dl + g * 8, sc2, scale2, key_ok, prow + g * 2048, dsrow + g * 2048);
+      }
+      {
+        uint32_t s[16], d[16];
+        tmem_ld_x16(tmem_row + kColS + c0 + 32, s);
+        tmem_ld_x16(tmem_row + kColDP + c0 + 32, d);
+        tmem_ld_wait_x16(s);
+        tmem_ld_wait_x16(d);
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          pds8(s + g * 8, d + g * 8, l2 + 32 + g * 8, dl + 32 + g * 8, sc2, scale2, key_ok, prow + (4 + g) * 2048,
+               dsrow + (4 + g) * 2048);
+      }
+      {
+        uint32_t s[8], d[8];
+        tmem_ld_x8(tmem_row + kColS + c0 + 48, s);
+        tmem_ld_x8(tmem_row + kColDP + c0 + 48, d);
+        tmem_ld_wait_x8(s);
+        tmem_ld_wait_x8(d);
+        pds8(s, d, l2 + 48, dl + 48, sc2, scale2, key_ok, prow + 6 * 2048, dsrow + 6 * 2048);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    // ---- tail: last key tile's dV / dK, then dQ
+    mbar_wait(bar_fin, 0);
+    tc_fence_after();
+    {
+      const int pkey = (num_kt - 1) * 128 + rowt;
+      __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * N + pkey) * tok_stride + ((wg == 0 ? 2 : 1) * H + h) * kHd;
+      store_row64(dst, tmem_row + (wg == 0 ? kColDV : kColDK), pkey < N);
+    }
+    {
+      const int q = wg * kQH + rowt;                 // warpgroup 0 -> query half 0, warpgroup 1 -> half 1
+      __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * N + q) * tok_stride + h * kHd;
+      store_row64(dst, tmem_row + (wg == 0 ? kColDQ0 : kColDQ1), rowt < kQH && q < N);
+    }
+    // keys beyond kv_len (padding keys of a NaFlex batch) never entered a tile: their dK / dV are zero
+    for (int key = num_kt * 128 + tid; key < N; key += kComputeThreads) {
+      for (int which = 1; which <= 2; ++which) {
+        uint4* dst = reinterpret_cast<uint4*>(p.dqkv + (static_cast<long long>(b) * N + key) * tok_stride + (which * H + h) * kHd);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                     const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st) {
+  CUtensorMap tq, tdo;
+  uint32_t box[2] = {kHd, kNQ};
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(3) * H * kHd, static_cast<uint64_t>(B) * N};
+    uint64_t strides[1] = {static_cast<uint64_t>(3) * H * kHd * 2};
+    int rc = encode_tmap_bf16(&tq, qkv, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(H) * kHd, static_cast<uint64_t>(B) * N};
+    uint64_t strides[1] = {static_cast<uint64_t>(H) * kHd * 2};
+    int rc = encode_tmap_bf16(&tdo, dout, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  AttnBwd2Params p;
+  p.lse = lse; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.kv_len = kv_len;
+  p.B = B; p.N = N; p.H = H; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    attr_set = true;
+  }
+  attn_bwd2_kernel<<<dim3(H, B), kComputeThreads + 32, kSmemTotal, st>>>(tq, tdo, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // namespace b200

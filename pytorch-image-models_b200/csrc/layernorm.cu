@@ -112,7 +112,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ w, con
 // Backward. dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w,  xhat = (x - mean) * rstd.
 // Per-CTA partial sums of dy*xhat (dweight) and dy (dbias) go to ws[blockIdx.x][2*cols].
 template <int VPL, bool XF32, bool DYF32>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnWarps * 32, VPL <= 4 ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const void* __restrict__ w,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const void* __restrict__ dres, void* __restrict__ dx,
@@ -132,7 +132,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
 
   for (long long row = warp_global; row < rows; row += warp_stride) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[VPL][8], g[VPL][8];
+    // pass 1: row statistics of g = dy * w and the dgamma / dbeta partial sums.  x / dy are NOT kept in registers
+    // (that is what capped the kernel at 8 warps per SM): pass 2 re-reads them, and those reads hit L1.
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -144,27 +145,32 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
         if (w != nullptr) load8_rt(w, param_f32, vec * 8, wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          g[i][j] = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
-          s1 += g[i][j];
-          s2 = fmaf(g[i][j], xh[i][j], s2);
-          dw_acc[i][j] = fmaf(dyv[j], xh[i][j], dw_acc[i][j]);
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          dw_acc[i][j] = fmaf(dyv[j], xh, dw_acc[i][j]);
           db_acc[i][j] += dyv[j];
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; g[i][j] = 0.f; }
       }
     }
     const float m1 = warp_sum(s1) * inv_n;
     const float m2 = warp_sum(s2) * inv_n;
+    // pass 2: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ residual-branch gradient)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vec = lane + i * 32;
       if (vec < nvec) {
-        float o[8];
+        float xv[8], dyv[8], wv[8], o[8];
+        load8<XF32>(x, row * cols + vec * 8, xv);
+        load8<DYF32>(dy, row * cols + vec * 8, dyv);
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - m1 - xh[i][j] * m2);
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
+          o[j] = rstd * (g - m1 - xh * m2);
+        }
         if (dres != nullptr) {   // gradient arriving through the residual branch around this LayerNorm
           float rv[8];
           load8<XF32>(dres, row * cols + vec * 8, rv);
@@ -196,15 +202,29 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   }
 }
 
-// out[c] = sum_r ws[r][c]; one thread per column pair group, coalesced over c.
-__global__ void reduce_rows_kernel(const float* __restrict__ ws, float* __restrict__ out0, float* __restrict__ out1,
-                                   int nrows, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * cols) return;
+// Second stage: out[c] = sum_r ws[r][c] over the per-CTA partial rows.  blockDim = (32 columns, 8 row slices):
+// each warp streams its row slice with coalesced 128-byte reads, then the 8 slices are combined through smem, so
+// the reduction is a handful of independent loads per thread instead of one serial chain over all rows.
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(const float* __restrict__ ws, float* __restrict__ out0, float* __restrict__ out1, int nrows,
+                   int cols) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int r = 0; r < nrows; ++r) s += ws[static_cast<long long>(r) * 2 * cols + c];
-  if (c < cols) { if (out0) out0[c] = s; }
-  else          { if (out1) out1[c - cols] = s; }
+  if (c < 2 * cols) {
+#pragma unroll 4
+    for (int r = slice; r < nrows; r += 8) s += ws[static_cast<long long>(r) * 2 * cols + c];
+  }
+  part[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && c < 2 * cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    if (c < cols) { if (out0) out0[c] = t; }
+    else          { if (out1) out1[c - cols] = t; }
+  }
 }
 
 static int ln_grid(long long rows) {
@@ -235,8 +255,13 @@ static int launch_bwd(const void* dy, const void* x, const void* w, const float*
   const int grid = ln_bwd_grid(rows);
   const int threads = kLnWarps * 32;
   const size_t smem = static_cast<size_t>(kLnWarps) * 2 * cols * sizeof(float);
-  if (smem > 48 * 1024) {
-    auto set = [&](auto kern) { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+  {
+    // opt in to > 48 KB where needed and ask for the largest shared-memory carve-out so two CTAs fit per SM
+    auto set = [&](auto kern) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+    };
     if (xf32 && dyf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, true, true>));
     else if (xf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, true, false>));
     else if (dyf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, false, true>));
@@ -306,8 +331,7 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* wei
   B200_CUDA_OK(cudaGetLastError());
   if (dweight || dbias) {
     const int nrows = ln_bwd_grid(rows);
-    const int threads = 128;
-    reduce_rows_kernel<<<(2 * cols + threads - 1) / threads, threads, 0, st>>>(workspace, dweight, dbias, nrows, cols);
+    reduce_rows_kernel<<<(2 * cols + 31) / 32, 256, 0, st>>>(workspace, dweight, dbias, nrows, cols);
     B200_CUDA_OK(cudaGetLastError());
   }
   return B200_OK;
