@@ -359,6 +359,11 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse, const int32_t
 
 }  // namespace b200
 
+namespace b200 {
+int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H, float scale,
+                     cudaStream_t st);
+}
+
 using namespace b200;
 
 extern "C" int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* kv_len, int32_t B, int32_t N,
@@ -370,6 +375,10 @@ extern "C" int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32
   B200_CHECK_ARG(B <= 65535 && H <= 65535, "b200_attn_fwd: B/H exceed the grid limits");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "b200_attn_fwd: qkv/out must be 16-byte aligned");
+  // N <= 208 (ViT @224/16): the persistent, P-in-TMEM kernel of attention_fwd2.cu; B200_ATTN_FWD_V1=1 keeps the
+  // one-CTA-per-tile kernels of this file selectable for A/B comparison (they remain the path for N > 208).
+  static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_FWD_V1"); return e != nullptr && e[0] == '1'; }();
+  if (!use_v1 && N <= 208) return launch_attn_fwd2(qkv, out, lse, kv_len, B, N, H, scale, st);
   static const bool ptmem = [] { const char* e = getenv("B200_ATTN_PTMEM"); return e != nullptr && e[0] == '1'; }();
   if (ptmem && N <= 208) return launch_attn_fwd<208, true, true>(qkv, out, lse, kv_len, B, N, H, scale, st);
   if (N <= 208) return launch_attn_fwd<208, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
