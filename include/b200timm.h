@@ -61,8 +61,11 @@ typedef struct b200_gemm_desc {
   const void* bias;  /* [N] or NULL; dtype bias_dtype                                             */
   const void* aux;   /* [M,N] bf16, ld = ldaux: residual (EPI_BIAS_RESIDUAL) / pre-activation (EPI_DGELU) */
   const void* gamma; /* [N] or NULL (LayerScale), dtype gamma_dtype; EPI_BIAS_RESIDUAL only        */
-  void* out2;        /* optional second bf16 output [M,N] (ld = ldo2), EPI_BIAS_GELU only: receives the
-                        pre-activation acc + bias (saved for backward) while `out` receives its GELU     */
+  void* out2;        /* optional second bf16 output [M,N] (ld = ldo2): the un-transformed acc + bias, saved for
+                        backward -- the GELU pre-activation (EPI_BIAS_GELU) or the residual branch output before
+                        LayerScale / DropPath (EPI_BIAS_RESIDUAL); `out` then applies the epilogue to those bf16 values */
+  const float* row_scale; /* EPI_BIAS_RESIDUAL only, fp32 [ceil(M / rows_per_scale)] or NULL: per-sample DropPath factor
+                        (keep-mask / keep_prob, timm/layers/drop.py:158-175): out = aux + row_scale*gamma*(acc+bias) */
   int64_t lda, ldb, ldo, ldaux, ldo2;
   int32_t M, N, K;
   int32_t a_mn, b_mn;
@@ -70,6 +73,7 @@ typedef struct b200_gemm_desc {
   int32_t out_dtype;
   int32_t bias_dtype, gamma_dtype;
   int32_t accumulate; /* out += result instead of out = result (out_dtype f32 only)               */
+  int32_t rows_per_scale; /* tokens per sample: row r uses row_scale[r / rows_per_scale]                       */
   int32_t split_k;    /* >1: K is split over CTAs, partial tiles are atomically added into fp32 out
                          (requires out_dtype=f32, epilogue=B200_EPI_BIAS with bias=NULL)           */
 } b200_gemm_desc;
@@ -143,6 +147,13 @@ B200_API int b200_avgpool_nhwc(const void* x, void* out, int32_t B, int32_t HW, 
  * dst[i] (+)= src[i]: fp32 -> bf16/fp32 hand-off of split-K weight gradients into .grad (n % 4 == 0).        */
 B200_API int b200_convert_f32(const float* src, void* dst, int64_t n, int32_t dst_dtype, int32_t accumulate,
                      void* stream);
+/* out[r,c] = x[r,c] * col_scale[c] * row_scale[r / rows_per_scale] (bf16): gradient of a residual branch through
+ * LayerScale (layer_scale.py:26-27) and DropPath (drop.py:158-175); either scale may be NULL.                  */
+B200_API int b200_scale_rows_cols(const void* x, const void* col_scale, const float* row_scale, void* out, int64_t rows,
+                         int32_t cols, int32_t rows_per_scale, int32_t col_scale_dtype, void* stream);
+/* out[c] (+)= sum_r a[r,c] * b[r,c] * row_scale[r / rows_per_scale]: the LayerScale gamma gradient (fp32).        */
+B200_API int b200_colsum_mul(const void* a, const void* b, const float* row_scale, float* out, int64_t rows,
+                    int32_t cols, int32_t rows_per_scale, int32_t accumulate, void* stream);
 /*
  * column sums of a bf16 [rows, cols] matrix into fp32 [cols] (bias gradients).                       */
 B200_API int b200_colsum(const void* x, float* out, int64_t rows, int32_t cols, int32_t accumulate, void* stream);

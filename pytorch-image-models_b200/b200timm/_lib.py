@@ -32,6 +32,7 @@ class GemmDesc(ctypes.Structure):
         ("aux", ctypes.c_void_p),
         ("gamma", ctypes.c_void_p),
         ("out2", ctypes.c_void_p),
+        ("row_scale", ctypes.c_void_p),
         ("lda", ctypes.c_int64),
         ("ldb", ctypes.c_int64),
         ("ldo", ctypes.c_int64),
@@ -47,6 +48,7 @@ class GemmDesc(ctypes.Structure):
         ("bias_dtype", ctypes.c_int32),
         ("gamma_dtype", ctypes.c_int32),
         ("accumulate", ctypes.c_int32),
+        ("rows_per_scale", ctypes.c_int32),
         ("split_k", ctypes.c_int32),
     ]
 
@@ -69,6 +71,8 @@ SIGNATURES = {
     "b200_patchify": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_assemble_tokens": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_naflex_assemble": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200_scale_rows_cols": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "b200_colsum_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "b200_colsum": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "b200_dwconv_nhwc": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_patchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

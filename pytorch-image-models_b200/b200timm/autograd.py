@@ -156,58 +156,78 @@ class AttentionFn(torch.autograd.Function):
 
 
 class BlockFn(torch.autograd.Function):
-    """Block.forward (timm/models/vision_transformer.py:206-214), no LayerScale / DropPath (ViT-B defaults)."""
+    """Block.forward (timm/models/vision_transformer.py:206-214) incl. LayerScale (layer_scale.py:26-27) and
+    DropPath (drop.py:158-175): x = x + dp1(ls1(attn(norm1(x)))); x = x + dp2(ls2(mlp(norm2(x)))).
+
+    rs1 / rs2: per-sample DropPath factors (keep-mask / keep_prob, fp32 [B]) drawn by the caller from torch's CUDA
+    generator exactly as the reference draws them, or None.  g1 / g2: LayerScale gammas or None.  When a branch has
+    either, its un-scaled output is kept (GEMM out2) for the gamma gradient and its incoming gradient is scaled by
+    gamma[col] * rs[row] before the projection / fc2 backward."""
 
     @staticmethod
-    def forward(ctx, x, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, kv_len, num_heads, scale, eps1,
-                eps2):
+    def forward(ctx, x, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, g1, g2, rs1, rs2, kv_len,
+                num_heads, scale, eps1, eps2):
         B, N, D = x.shape
         hd = wqkv.shape[0] // 3 // num_heads
         x0 = _c(x.reshape(B * N, D))
         h1, mean1, rstd1 = ops.layernorm_fwd(x0, n1w, n1b, eps1, save_stats=True)
         qkv = ops.linear_fwd(h1, wqkv, bqkv)
         o, lse = ops.attention_fwd(qkv, B, N, num_heads, hd, scale, kv_len, need_lse=True)
-        x1 = ops.linear_fwd(o.view(B * N, -1), wproj, bproj, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x0)
+        br1 = torch.empty(B * N, D, dtype=torch.bfloat16, device=x.device) if g1 is not None else None
+        x1 = ops.linear_fwd(o.view(B * N, -1), wproj, bproj, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x0, gamma=g1, out2=br1,
+                            row_scale=rs1, rows_per_scale=N)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps2, save_stats=True)
         pre = torch.empty(B * N, w1.shape[0], dtype=torch.bfloat16, device=x.device)
         act = ops.linear_fwd(h2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
-        x2 = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x1)
-        ctx.save_for_backward(x0, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, kv_len, h1, mean1, rstd1,
-                              qkv, o, lse, x1, h2, mean2, rstd2, pre, act)
+        br2 = torch.empty(B * N, D, dtype=torch.bfloat16, device=x.device) if g2 is not None else None
+        x2 = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x1, gamma=g2, out2=br2, row_scale=rs2,
+                            rows_per_scale=N)
+        ctx.save_for_backward(x0, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, g1, g2, rs1, rs2, kv_len,
+                              h1, mean1, rstd1, qkv, o, lse, x1, h2, mean2, rstd2, pre, act, br1, br2)
         ctx.meta = (B, N, D, num_heads, hd, scale)
         return x2.view(B, N, D)
 
     @staticmethod
     def backward(ctx, dy):
-        (x0, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, kv_len, h1, mean1, rstd1, qkv, o, lse, x1, h2,
-         mean2, rstd2, pre, act) = ctx.saved_tensors
+        (x0, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, g1, g2, rs1, rs2, kv_len, h1, mean1, rstd1, qkv,
+         o, lse, x1, h2, mean2, rstd2, pre, act, br1, br2) = ctx.saved_tensors
         B, N, D, H, hd, scale = ctx.meta
         dx2 = _c(dy.reshape(B * N, D))
         # All parameter gradients of the block live in ONE zeroed fp32 workspace (wgrad split-K reduce-adds, bias
-        # column sums and LayerNorm dgamma/dbeta write straight into views of it) and are converted to the
-        # parameters' dtype with ONE kernel: 1 memset + 1 convert per block instead of ~20 of each.
-        params = (n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2)
+        # column sums, LayerNorm dgamma/dbeta and LayerScale dgamma write straight into views of it) and are converted
+        # to the parameters' dtype with ONE kernel: 1 memset + 1 convert per block instead of ~20 of each.
+        params = (n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, g1, g2)
         sizes = [0 if p is None else p.numel() for p in params]
         offs = [0]
         for n in sizes:
             offs.append(offs[-1] + (n + 3) // 4 * 4)
         ws = torch.zeros(offs[-1], dtype=torch.float32, device=dx2.device)
-        v = [None if p is None else ws[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
-        # ---- MLP branch:  x2 = x1 + fc2(GELU(fc1(LN2(x1))))
-        dpre = ops.linear_dgrad(dx2, w2, epilogue=ops.EPI_DGELU, aux=pre)            # dY W2 * GELU'(pre)
-        ops.linear_wgrad(dx2, act, out=v[10])
+        v = [None if p is None else ws[o_:o_ + n].view(p.shape) for p, o_, n in zip(params, offs, sizes)]
+        # ---- MLP branch:  x2 = x1 + rs2 * g2 * (fc2(GELU(fc1(LN2(x1)))) + b2)
+        dbr2 = dx2
+        if g2 is not None or rs2 is not None:
+            if g2 is not None:
+                ops.colsum_mul(dx2, br2, rs2, N, out=v[13], accumulate=True)          # dgamma2
+            dbr2 = ops.scale_rows_cols(dx2, g2, rs2, N)                               # gradient w.r.t. the branch output
+        dpre = ops.linear_dgrad(dbr2, w2, epilogue=ops.EPI_DGELU, aux=pre)            # dY W2 * GELU'(pre)
+        ops.linear_wgrad(dbr2, act, out=v[10])
         if b2 is not None:
-            ops.colsum(dx2, out=v[11], accumulate=True)
+            ops.colsum(dbr2, out=v[11], accumulate=True)
         dh2 = ops.linear_dgrad(dpre, w1)
         ops.linear_wgrad(dpre, h2, out=v[8])
         if b1 is not None:
             ops.colsum(dpre, out=v[9], accumulate=True)
         dx1, _, _ = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dw_out=v[6], db_out=v[7])
-        # ---- attention branch:  x1 = x0 + proj(SDPA(qkv(LN1(x0))))
-        do = ops.linear_dgrad(dx1, wproj)
-        ops.linear_wgrad(dx1, o.view(B * N, -1), out=v[4])
+        # ---- attention branch:  x1 = x0 + rs1 * g1 * (proj(SDPA(qkv(LN1(x0)))) + bp)
+        dbr1 = dx1
+        if g1 is not None or rs1 is not None:
+            if g1 is not None:
+                ops.colsum_mul(dx1, br1, rs1, N, out=v[12], accumulate=True)          # dgamma1
+            dbr1 = ops.scale_rows_cols(dx1, g1, rs1, N)
+        do = ops.linear_dgrad(dbr1, wproj)
+        ops.linear_wgrad(dbr1, o.view(B * N, -1), out=v[4])
         if bproj is not None:
-            ops.colsum(dx1, out=v[5], accumulate=True)
+            ops.colsum(dbr1, out=v[5], accumulate=True)
         dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
         dh1 = ops.linear_dgrad(dqkv, wqkv)
         ops.linear_wgrad(dqkv, h1, out=v[2])
@@ -220,8 +240,8 @@ class BlockFn(torch.autograd.Function):
         else:
             gbuf = torch.empty(offs[-1], dtype=pdt, device=dx2.device)
             ops.convert_f32(ws, gbuf)
-            grads = [None if p is None else gbuf[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
-        return (dx0.view(B, N, D), *grads, None, None, None, None, None)
+            grads = [None if p is None else gbuf[o_:o_ + n].view(p.shape) for p, o_, n in zip(params, offs, sizes)]
+        return (dx0.view(B, N, D), *grads, None, None, None, None, None, None, None, None)
 
 
 class PatchEmbedFn(torch.autograd.Function):

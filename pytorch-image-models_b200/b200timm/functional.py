@@ -61,6 +61,24 @@ def _check_drop(m, what):
         raise B200Error(f"{what} with p={p} in training mode is not supported by the fused inference path")
 
 
+def _drop_path_factor(dp, x):
+    """Per-sample DropPath factor (keep-mask / keep_prob) as fp32 [B], or None when the module is inactive.  The
+    Bernoulli draw is made exactly as the reference makes it -- x.new_empty((B, 1, 1)).bernoulli_(keep_prob) on the
+    torch CUDA generator (timm/layers/drop.py:170-175) -- so seeds, RNG consumption and gradient checkpointing
+    replay match the reference; applying the factor is fused into the residual GEMM epilogue."""
+    if _is_identity(dp):
+        return None
+    p = getattr(dp, "drop_prob", 0.0)
+    if not p or not dp.training:
+        return None
+    keep = 1.0 - p
+    mask = x.new_empty((x.shape[0], 1, 1)).bernoulli_(keep)
+    f = mask.reshape(-1).float()
+    if keep > 0.0 and getattr(dp, "scale_by_keep", True):
+        f = f / keep
+    return f.contiguous()
+
+
 def check_attention(attn):
     """Raise unless `attn` is a plain timm Attention the kernels cover (attention.py:43-139)."""
     if not _is_identity(getattr(attn, "q_norm", None)) or not _is_identity(getattr(attn, "k_norm", None)):
@@ -163,30 +181,29 @@ def block_forward(blk, x, kv_len=None):
     attn, mlp = blk.attn, blk.mlp
     check_attention(attn)
     check_mlp(mlp)
-    _check_drop(blk.drop_path1, "drop_path")
-    _check_drop(blk.drop_path2, "drop_path")
     B, N, D = x.shape
     if _needs_grad(x, blk):
-        if _gamma(blk.ls1) is not None or _gamma(blk.ls2) is not None:
-            raise B200Error("training with LayerScale is not supported yet (inference is)")
         from .autograd import BlockFn
         _bf16_2d(x, D)
         n1w, n1b, e1 = _ln_params(blk.norm1)
         n2w, n2b, e2 = _ln_params(blk.norm2)
+        rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)
         return BlockFn.apply(x, n1w, n1b, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, n2w, n2b,
-                             _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, kv_len, attn.num_heads, attn.scale,
-                             e1, e2)
+                             _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, _gamma(blk.ls1), _gamma(blk.ls2),
+                             rs1, rs2, kv_len, attn.num_heads, attn.scale, e1, e2)
+    rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)   # None in eval mode
     x2 = _bf16_2d(x, D)
     w1, b1, eps1 = _ln_params(blk.norm1)
     h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
     qkv = ops.linear_fwd(h, _w(attn.qkv), attn.qkv.bias)
     o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
     x2 = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
-                        gamma=_gamma(blk.ls1))
+                        gamma=_gamma(blk.ls1), row_scale=rs1, rows_per_scale=N)
     w2, b2, eps2 = _ln_params(blk.norm2)
     h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
     h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
-    x2 = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=_gamma(blk.ls2))
+    x2 = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=_gamma(blk.ls2),
+                        row_scale=rs2, rows_per_scale=N)
     return x2.view(B, N, D)
 
 

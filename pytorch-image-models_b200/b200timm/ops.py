@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
+    "avgpool_nhwc", "naflex_assemble", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
 ]
 
 
@@ -149,7 +149,7 @@ def _check_2d_bf16(t, name):
 
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None, gamma=None, out=None,
-         out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None):
+         out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None, row_scale=None, rows_per_scale=0):
     """out[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
@@ -180,6 +180,12 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
         if tuple(out2.shape) != (M, N):
             raise B200Error("gemm: out2 must be [M,N]")
         d.out2, d.ldo2 = out2.data_ptr(), out2.stride(0)
+    if row_scale is not None:
+        if row_scale.dtype != torch.float32 or not row_scale.is_contiguous() or not row_scale.is_cuda:
+            raise B200Error("gemm: row_scale must be a contiguous fp32 CUDA tensor")
+        if rows_per_scale <= 0 or row_scale.numel() * rows_per_scale < M:
+            raise B200Error("gemm: row_scale needs rows_per_scale > 0 and ceil(M / rows_per_scale) entries")
+        d.row_scale, d.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
     d.M, d.N, d.K = M, N, K
     d.a_mn, d.b_mn = int(a_mn), int(b_mn)
     d.epilogue = epilogue
@@ -200,11 +206,13 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
     return out
 
 
-def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, out=None, out2=None):
+def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, out=None, out2=None, row_scale=None,
+               rows_per_scale=0):
     """F.linear on a [M,K] bf16 activation with a fused epilogue (weight: [N,K] bf16)."""
     M, K = x2d.shape
     N = weight.shape[0]
-    return gemm(x2d, weight, M, N, K, epilogue=epilogue, bias=bias, aux=aux, gamma=gamma, out=out, out2=out2)
+    return gemm(x2d, weight, M, N, K, epilogue=epilogue, bias=bias, aux=aux, gamma=gamma, out=out, out2=out2,
+                row_scale=row_scale, rows_per_scale=rows_per_scale)
 
 
 def linear_dgrad(dy2d, weight, epilogue=EPI_BIAS, aux=None):
@@ -395,6 +403,39 @@ def naflex_assemble(proj, prefix, table, pos_off, pos_len, B, N, n_prefix, D):
     _lib.check(rc, "b200_naflex_assemble")
     _count()
     return tokens
+
+
+# --------------------------------------------------------------------------------------------- LayerScale / DropPath backward
+def scale_rows_cols(x2d, col_scale=None, row_scale=None, rows_per_scale=0):
+    """x * col_scale[c] * row_scale[r // rows_per_scale] -> bf16 (either scale may be None)."""
+    _need_cuda(x2d, col_scale, row_scale)
+    if x2d.dim() != 2 or x2d.dtype != torch.bfloat16 or not x2d.is_contiguous():
+        raise B200Error("scale_rows_cols: need a contiguous 2-D bf16 tensor")
+    rows, cols = x2d.shape
+    out = torch.empty_like(x2d)
+    rc = _lib.load().b200_scale_rows_cols(x2d.data_ptr(), _ptr(col_scale), _ptr(row_scale), out.data_ptr(), rows, cols,
+                                          int(rows_per_scale), _dt(col_scale) if col_scale is not None else DTYPE_BF16,
+                                          _stream())
+    _lib.check(rc, "b200_scale_rows_cols")
+    _count()
+    return out
+
+
+def colsum_mul(a2d, b2d, row_scale=None, rows_per_scale=0, out=None, accumulate=False):
+    """fp32 [cols]: sum_r a[r,c] * b[r,c] * row_scale[r // rows_per_scale]."""
+    _need_cuda(a2d, b2d, row_scale, out)
+    for t in (a2d, b2d):
+        if t.dim() != 2 or t.dtype != torch.bfloat16 or not t.is_contiguous() or t.shape != a2d.shape:
+            raise B200Error("colsum_mul: need two contiguous bf16 [rows, cols] tensors of equal shape")
+    rows, cols = a2d.shape
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=a2d.device)
+        accumulate = False
+    rc = _lib.load().b200_colsum_mul(a2d.data_ptr(), b2d.data_ptr(), _ptr(row_scale), out.data_ptr(), rows, cols,
+                                     int(rows_per_scale), int(accumulate), _stream())
+    _lib.check(rc, "b200_colsum_mul")
+    _count(1 if accumulate else 2)
+    return out
 
 
 # --------------------------------------------------------------------------------------------- per-op timing (tools)

@@ -170,6 +170,65 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
   if (blockIdx.x * 256 + c < cols) atomicAdd(out + blockIdx.x * 256 + c, s);
 }
 
+// out[r][c] = x[r][c] * col_scale[c] * row_scale[r / rps]: gradient of a residual branch w.r.t. its un-scaled output
+// (LayerScale gamma, timm/layers/layer_scale.py:26-27, and the DropPath factor, drop.py:158-175).
+__global__ void scale_rows_cols_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ cs,
+                                       const float* __restrict__ rs, __nv_bfloat16* __restrict__ out, long long rows,
+                                       int cols, int rps, int cs_f32) {
+  const int cvecs = cols >> 3;
+  const long long total = rows * cvecs;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvecs);
+    const long long r = idx / cvecs;
+    float v[8], c[8];
+    ld8(x, false, r * cols + cv * 8, v);
+    const float rscale = rs != nullptr ? __ldg(rs + r / rps) : 1.0f;
+    if (cs != nullptr) {
+      ld8(cs, cs_f32, cv * 8, c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= c[i] * rscale;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= rscale;
+    }
+    *reinterpret_cast<uint4*>(out + r * cols + cv * 8) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
+// out[c] += sum_r a[r][c] * b[r][c] * row_scale[r / rps]   (LayerScale gamma gradient); same blocking as colsum_kernel
+__global__ void __launch_bounds__(256)
+colsum_mul_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, const float* __restrict__ rs,
+                  float* __restrict__ out, long long rows, int cols, long long rows_per_slab, int rps) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_slab;
+  const long long r1 = min(rows, r0 + rows_per_slab);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < cols) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      float av[8], bv[8];
+      ld8(a, false, r * cols + col, av);
+      ld8(b, false, r * cols + col, bv);
+      const float s = rs != nullptr ? __ldg(rs + r / rps) : 1.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(av[i] * s, bv[i], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][c];
+  if (blockIdx.x * 256 + c < cols) atomicAdd(out + blockIdx.x * 256 + c, s);
+}
+
 // dst (bf16 or fp32) (+)= src fp32  -- weight-gradient hand-off from the fp32 split-K workspace to .grad
 template <bool DST_F32>
 __global__ void convert_kernel(const float* __restrict__ src, void* __restrict__ dst, long long n, int accumulate) {
@@ -281,6 +340,43 @@ extern "C" int b200_naflex_assemble(const void* proj, const void* prefix, const 
   naflex_assemble_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(proj), prefix, reinterpret_cast<const __nv_bfloat16*>(table), pos_off, pos_len,
       reinterpret_cast<__nv_bfloat16*>(tokens), B, N, n_prefix, D, prefix_dtype == B200_DTYPE_F32);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_scale_rows_cols(const void* x, const void* col_scale, const float* row_scale, void* out, int64_t rows,
+                                    int32_t cols, int32_t rows_per_scale, int32_t col_scale_dtype, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(x && out, "b200_scale_rows_cols: null pointer");
+  B200_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0, "b200_scale_rows_cols: bad shape (cols %% 8 == 0)");
+  B200_CHECK_ARG(row_scale == nullptr || rows_per_scale > 0, "b200_scale_rows_cols: row_scale needs rows_per_scale > 0");
+  const long long total = rows * (cols / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  scale_rows_cols_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), col_scale, row_scale, reinterpret_cast<__nv_bfloat16*>(out), rows, cols,
+      rows_per_scale > 0 ? rows_per_scale : 1, col_scale_dtype == B200_DTYPE_F32);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_colsum_mul(const void* a, const void* b, const float* row_scale, float* out, int64_t rows,
+                               int32_t cols, int32_t rows_per_scale, int32_t accumulate, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(a && b && out, "b200_colsum_mul: null pointer");
+  B200_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0, "b200_colsum_mul: bad shape (cols %% 8 == 0)");
+  B200_CHECK_ARG(row_scale == nullptr || rows_per_scale > 0, "b200_colsum_mul: row_scale needs rows_per_scale > 0");
+  if (!accumulate) B200_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  const int gx = (cols + 255) / 256;
+  int slabs = (sm_count() * 4 + gx - 1) / gx;
+  long long rps = (rows + slabs - 1) / slabs;
+  if (rps < 8) rps = 8;
+  slabs = static_cast<int>((rows + rps - 1) / rps);
+  colsum_mul_kernel<<<dim3(gx, slabs), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                      reinterpret_cast<const __nv_bfloat16*>(b), row_scale, out, rows, cols,
+                                                      rps, rows_per_scale > 0 ? rows_per_scale : 1);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -27,6 +27,8 @@ constexpr int kNumThreads = 128 + kNumEpiWarps * 32;
 struct GemmKernelParams {
   void* out;
   void* out2;
+  const float* row_scale;
+  int rows_per_scale;
   const void* bias;
   const __nv_bfloat16* aux;
   const void* gamma;
@@ -233,6 +235,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int n_blk = mn - m_blk * p.num_n_blocks;
       const int row0 = m_blk * BM + quad * 32;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + part * kColsPerWarp;
+      // per-row scale of the residual branch (DropPath keep-mask / keep_prob of the row's sample, drop.py:158-175)
+      f32x2 rs2 = splat(1.0f);
+      if (p.row_scale != nullptr && row0 + lane < p.M) rs2 = splat(__ldg(p.row_scale + (row0 + lane) / p.rows_per_scale));
       bool waited = false;
 #pragma unroll 1
       for (int rc = 0; rc < kColsPerWarp; rc += round_cols) {
@@ -249,6 +254,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           waited = true;
         }
+        uint4 aq[4] = {};   // residual tile of this round, kept when the branch output is stored first (out2)
         if (p.out_f32) {
           // fp32 output (weight gradients): 16 columns = 4 chunks of 4 floats
           uint32_t r[16];
@@ -300,15 +306,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 uint4 q;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
                 const f32x2 av[4] = {bf16x2_to_f32x2(q.x), bf16x2_to_f32x2(q.y), bf16x2_to_f32x2(q.z), bf16x2_to_f32x2(q.w)};
+                aq[g] = q;
                 if (p.epilogue == B200_EPI_BIAS_RESIDUAL) {
-                  if (p.gamma != nullptr) {
+                  if (dual) {
+                    // training with LayerScale / DropPath: the un-scaled branch output goes to out2 first
+                  } else if (p.gamma != nullptr) {
                     f32x2 gv[4];
                     load8_param2(p.gamma, p.gamma_f32, col, gv);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], gv[j], av[j]);
+                    for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], mul2(gv[j], rs2), av[j]);
                   } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = add2(v[j], av[j]);
+                    for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], rs2, av[j]);
                   }
                 } else {
 #pragma unroll
@@ -351,11 +360,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
             uint32_t o[4];
+            if (p.epilogue == B200_EPI_BIAS_GELU) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float lo, hi;
-              upk(gelu_erf2(bf16x2_to_f32x2(w[i])), lo, hi);
-              o[i] = pack_bf16(lo, hi);
+              for (int i = 0; i < 4; ++i) {
+                float lo, hi;
+                upk(gelu_erf2(bf16x2_to_f32x2(w[i])), lo, hi);
+                o[i] = pack_bf16(lo, hi);
+              }
+            } else {
+              // residual epilogue: out = aux + row_scale * gamma * branch, on the bf16 branch values just stored
+              const uint32_t aw[4] = {aq[j].x, aq[j].y, aq[j].z, aq[j].w};
+              f32x2 gv[4] = {rs2, rs2, rs2, rs2};
+              const int col = col0 + j * 8;
+              if (p.gamma != nullptr && col < p.N) {
+                load8_param2(p.gamma, p.gamma_f32, col, gv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gv[i] = mul2(gv[i], rs2);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float lo, hi;
+                upk(fma2(bf16x2_to_f32x2(w[i]), gv[i], bf16x2_to_f32x2(aw[i])), lo, hi);
+                o[i] = pack_bf16(lo, hi);
+              }
             }
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
           }
@@ -428,7 +455,8 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
     }
   }
   GemmKernelParams p;
-  p.out = d.out; p.out2 = d.out2; p.bias = d.bias; p.aux = reinterpret_cast<const __nv_bfloat16*>(d.aux); p.gamma = d.gamma;
+  p.out = d.out; p.out2 = d.out2; p.bias = d.bias;
+  p.row_scale = d.row_scale; p.rows_per_scale = d.rows_per_scale > 0 ? d.rows_per_scale : 1; p.aux = reinterpret_cast<const __nv_bfloat16*>(d.aux); p.gamma = d.gamma;
   p.ldo = d.ldo; p.ldaux = d.ldaux;
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.num_m_blocks = (d.M + BM - 1) / BM;
@@ -484,9 +512,13 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
                    "b200_gemm: epilogue %d needs a 16-byte aligned aux with ldaux %% 8 == 0", d.epilogue);
   }
   if (d.out2 != nullptr)
-    B200_CHECK_ARG(d.epilogue == B200_EPI_BIAS_GELU && d.out_dtype == B200_DTYPE_BF16 && d.ldo2 % 8 == 0 &&
-                       d.ldo2 >= d.N && (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0,
-                   "b200_gemm: out2 (pre-activation) needs the GELU epilogue, bf16 output and 16-byte aligned rows");
+    B200_CHECK_ARG((d.epilogue == B200_EPI_BIAS_GELU || d.epilogue == B200_EPI_BIAS_RESIDUAL) &&
+                       d.out_dtype == B200_DTYPE_BF16 && d.ldo2 % 8 == 0 && d.ldo2 >= d.N &&
+                       (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0,
+                   "b200_gemm: out2 needs the GELU or residual epilogue, bf16 output and 16-byte aligned rows");
+  if (d.row_scale != nullptr)
+    B200_CHECK_ARG(d.epilogue == B200_EPI_BIAS_RESIDUAL && d.rows_per_scale > 0,
+                   "b200_gemm: row_scale needs the residual epilogue and rows_per_scale > 0");
   if (d.bias) B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0, "b200_gemm: bias must be 16-byte aligned");
   if (d.gamma) B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d.gamma) & 15) == 0, "b200_gemm: gamma must be 16-byte aligned");
   if (d.accumulate) B200_CHECK_ARG(d.out_dtype == B200_DTYPE_F32, "b200_gemm: accumulate needs an fp32 output");

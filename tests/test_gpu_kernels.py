@@ -296,3 +296,34 @@ def test_layernorm_bwd_with_residual_gradient():
     torch.nn.functional.layer_norm(xr, (cols,), w.float(), b.float(), 1e-6).backward(dy.float())
     _close(dx1, xr.grad + dres.float(), 4e-2, 1e-2, "ln bwd + residual grad")
     _close(dx0, xr.grad, 3e-2, 1e-2, "ln bwd")
+
+
+def test_layerscale_droppath_kernels():
+    """Residual epilogue with per-sample DropPath factor + LayerScale and its out2 (branch output); the two backward
+    helper kernels."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(33)
+    B, N, D, K = 6, 50, 256, 128
+    M = B * N
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(D, K, device=DEV, generator=g) * 0.1).bfloat16()
+    bias = torch.randn(D, device=DEV, generator=g).bfloat16()
+    gamma = torch.randn(D, device=DEV, generator=g).bfloat16()
+    aux = torch.randn(M, D, device=DEV, generator=g).bfloat16()
+    rs = torch.tensor([0.0, 1.25, 1.25, 0.0, 1.25, 1.25], device=DEV)
+    branch = a.float() @ w.float().t() + bias.float()
+    rows = rs.repeat_interleave(N)[:, None]
+    out = ops.linear_fwd(a, w, bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=aux, gamma=gamma, row_scale=rs, rows_per_scale=N)
+    _close(out, aux.float() + rows * gamma.float() * branch, 3e-2, 1e-2, "residual + layerscale + droppath")
+    assert torch.equal(out.view(B, N, D)[0], aux.view(B, N, D)[0])          # dropped sample: branch contributes exactly 0
+    br = torch.empty(M, D, device=DEV, dtype=torch.bfloat16)
+    out2 = ops.linear_fwd(a, w, bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=aux, gamma=gamma, row_scale=rs, rows_per_scale=N,
+                          out2=br)
+    _close(br, branch, 2e-2, 1e-2, "branch output (out2)")
+    _close(out2, aux.float() + rows * gamma.float() * br.float(), 2e-2, 1e-2, "residual computed from the stored branch")
+    out3 = ops.linear_fwd(a, w, bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=aux, row_scale=rs, rows_per_scale=N)
+    _close(out3, aux.float() + rows * branch, 3e-2, 1e-2, "residual + droppath (no layerscale)")
+    dy = torch.randn(M, D, device=DEV, generator=g).bfloat16()
+    _close(ops.scale_rows_cols(dy, gamma, rs, N), dy.float() * gamma.float() * rows, 2e-2, 1e-2, "scale_rows_cols")
+    _close(ops.scale_rows_cols(dy, None, rs, N), dy.float() * rows, 1e-2, 1e-2, "scale rows only")
+    _close(ops.colsum_mul(dy, br, rs, N), (dy.float() * br.float() * rows).sum(0), 5e-2, 2e-3, "colsum_mul")

