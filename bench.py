@@ -89,12 +89,61 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def recorded_traffic():
+    """roofline.traffic: DRAM bytes per GEMM launch (mean over the four block GEMMs) from the committed ncu --set full
+    capture -- bench.py cannot run ncu itself, so the number is the recorded one and says where it came from."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        g = t["gemm_bf16_kernel"]
+        return {"traffic": g["mean_traffic_mb"] * 1e6, "traffic_unit": "bytes/launch (mean of qkv, proj, fc1, fc2)",
+                "traffic_algorithmic": g["mean_algorithmic_mb"] * 1e6, "traffic_source": t["source"]}
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None}
+
+
+_THREADS = {}
+
+
+def pick_cpu_threads(dtype):
+    """Thread count for the CPU arm: the fastest of a few candidates between the cgroup CPU quota and the affinity mask,
+    each timed on one small forward.  (A box whose mask shows 128 CPUs but whose quota is far smaller ran the port 40x
+    slower with 128 spinning OpenMP threads than with the right count -- the reference arm should not lose that way.)"""
+    if dtype in _THREADS:
+        return _THREADS[dtype]
+    from oracle import vit_oracle as O
+    aff = max(1, len(os.sched_getaffinity(0)))
+    cand = {aff, max(1, aff // 2), max(1, aff // 4)}
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            cand.add(max(1, min(aff, -(-int(quota) // int(period)))))
+    except (OSError, ValueError):
+        pass
+    cand |= {t for t in (64, 32, 16, 8) if t <= aff}
+    cfg = dict(O.VIT_CONFIGS[MODEL])
+    sd = {k: v.to(dtype) for k, v in O.random_state_dict(cfg, seed=42).items()}
+    img = torch.randn(4, 3, 224, 224).to(dtype)
+    best, best_t = aff, float("inf")
+    with torch.no_grad():
+        for t in sorted(cand, reverse=True):
+            torch.set_num_threads(t)
+            O.vit_forward_eager(img[:1], sd, cfg)
+            t0 = time.perf_counter()
+            O.vit_forward_eager(img, sd, cfg)
+            dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = t, dt
+    _THREADS[dtype] = best
+    return best
+
+
 def cpu_port_throughput(batch, steps, warmup, dtype=torch.bfloat16, threads=None):
     """The reference path on the host CPU: oracle.vit_oracle.vit_forward_eager issues the same torch CPU
     library calls timm's eager forward does (F.conv2d / layer_norm / linear / sdpa / gelu).  img/s."""
     from oracle import vit_oracle as O
     # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every core it may run on
-    torch.set_num_threads(threads or max(1, len(os.sched_getaffinity(0))))
+    torch.set_num_threads(threads or pick_cpu_threads(dtype))
     cfg = dict(O.VIT_CONFIGS[MODEL])
     sd = {k: v.to(dtype) for k, v in O.random_state_dict(cfg, seed=42).items()}
     g = torch.Generator().manual_seed(0)
@@ -297,7 +346,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,4> (qkv/proj/fc1/fc2/head GEMMs)",
                          "achieved": round(gemm_tflops, 1), "peak": peak, "unit": "TFLOP/s",
-                         "frac": round(gemm_tflops / peak, 4), "traffic": None,
+                         "frac": round(gemm_tflops / peak, 4), **recorded_traffic(),
                          "launches_timed": gemm_n, "timing": "CUDA events around every GEMM launch over K eagerly launched steps",
                          "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                          "whole_step_tflops": round(FWD_FLOPS_PER_IMG * value / world / 1e12, 1)},

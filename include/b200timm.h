@@ -133,9 +133,17 @@ B200_API int b200_naflex_assemble(const void* proj, const void* prefix, const vo
 /* ------------------------------------------------------------------ ConvNeXt (channels-last activations [B,H,W,C] bf16)
  * Depthwise k x k convolution, stride 1, zero padding k/2, + bias: F.conv2d(groups=C) of timm/models/convnext.py:
  * 173-182,200 evaluated NHWC so the permutes of :205,208 disappear.  weight_t: the conv weight [C,1,k,k] transposed to
- * bf16 [k, k, C] (one 16-byte load per tap and 8 channels); k in {3,5,7}.                                        */
-B200_API int b200_dwconv_nhwc(const void* x, const void* weight_t, const void* bias, void* y, int32_t B, int32_t H,
-                     int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype, void* stream);
+ * bf16 [k, k, C] (one 16-byte load per tap and 8 channels); k in {3,5,7}.
+ * residual (optional, bf16 [B,H,W,C]) is added to the output: the backward uses the same kernel for
+ * dx = dwconv(dy, spatially flipped weight) + shortcut gradient.                                                 */
+B200_API int b200_dwconv_nhwc(const void* x, const void* weight_t, const void* bias, const void* residual, void* y,
+                     int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype, void* stream);
+/* dweight_t[ky,kx,c] += sum_{b,y,x} dy[b,y,x,c] * x[b,y+ky-k/2,x+kx-k/2,c]  (fp32 [k,k,C], zero-initialised by the caller). */
+B200_API int b200_dwconv_nhwc_wgrad(const void* x, const void* dy, float* dweight_t, int32_t B, int32_t H, int32_t W,
+                           int32_t C, int32_t ksize, void* stream);
+/* inverse of b200_patchify_nhwc (backward of the downsample gather).                                              */
+B200_API int b200_unpatchify_nhwc(const void* patches, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t p,
+                         void* stream);
 /* out[(b,oy,ox), (ky*p+kx)*C + c] = x[b, oy*p+ky, ox*p+kx, c]: the gather of the p x p / stride p downsample conv
  * (convnext.py:263-275); the GEMM then uses the conv weight permuted to [Cout, ky, kx, Cin].                   */
 B200_API int b200_patchify_nhwc(const void* x, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t p,

@@ -22,6 +22,120 @@ from ._lib import B200Error
 from .layers import DropPath, Mlp
 
 
+def _needs_grad(module):
+    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+
+
+class _BlockFn(torch.autograd.Function):
+    """ConvNeXtBlock forward + backward on channels-last rows (timm/models/convnext.py:197-213).  Backward: LayerScale
+    gamma gradient, fc2 / fc1 dgrad (GELU' fused) + wgrad, LayerNorm backward, then the depthwise conv backward --
+    dx = dwconv(dy, spatially flipped weight) with the shortcut gradient folded in, dweight through the wgrad kernel."""
+
+    @staticmethod
+    def forward(ctx, x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, B, H, W, eps):
+        from .autograd import _c
+        C = x.shape[1]
+        k = wdw.shape[-1]
+        wt = ops.dwconv_weight_t(wdw)
+        y = ops.dwconv_nhwc(x.view(B, H, W, C), wt, bdw).view(B * H * W, C)
+        h, mean, rstd = ops.layernorm_fwd(y, nw, nb, eps, save_stats=True)
+        pre = torch.empty(x.shape[0], w1.shape[0], dtype=torch.bfloat16, device=x.device)
+        act = ops.linear_fwd(h, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+        br = torch.empty_like(x) if gamma is not None else None
+        out = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=_c(x), gamma=gamma, out2=br)
+        ctx.save_for_backward(x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br)
+        ctx.meta = (B, H, W, C, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .autograd import _c, _to_param_dtype
+        x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br = ctx.saved_tensors
+        B, H, W, C, k = ctx.meta
+        dout = _c(dout)
+        params = (bdw, nw, nb, w1, b1, w2, b2, gamma)
+        sizes = [0 if p is None else p.numel() for p in params]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + (n + 3) // 4 * 4)
+        kk_off = offs[-1]
+        ws = torch.zeros(kk_off + k * k * C, dtype=torch.float32, device=dout.device)
+        v = [None if p is None else ws[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
+        dwt = ws[kk_off:].view(k, k, C)
+        dbr = dout
+        if gamma is not None:
+            ops.colsum_mul(dout, br, out=v[7], accumulate=True)
+            dbr = ops.scale_rows_cols(dout, gamma)
+        dpre = ops.linear_dgrad(dbr, w2, epilogue=ops.EPI_DGELU, aux=pre)
+        ops.linear_wgrad(dbr, act, out=v[5])
+        if b2 is not None:
+            ops.colsum(dbr, out=v[6], accumulate=True)
+        dh = ops.linear_dgrad(dpre, w1)
+        ops.linear_wgrad(dpre, h, out=v[3])
+        if b1 is not None:
+            ops.colsum(dpre, out=v[4], accumulate=True)
+        dyc, _, _ = ops.layernorm_bwd(dh, y, nw, mean, rstd, dw_out=v[1], db_out=v[2])
+        dx = ops.dwconv_nhwc(dyc.view(B, H, W, C), wt.flip(0, 1).contiguous(), None, residual=dout.view(B, H, W, C))
+        ops.dwconv_nhwc_wgrad(x.view(B, H, W, C), dyc.view(B, H, W, C), k, out=dwt)
+        if bdw is not None:
+            ops.colsum(dyc, out=v[0], accumulate=True)
+        pdt = w1.dtype
+        if pdt == torch.float32:
+            grads = v
+        else:
+            gbuf = torch.empty(kk_off, dtype=pdt, device=dout.device)
+            ops.convert_f32(ws[:kk_off], gbuf)
+            grads = [None if p is None else gbuf[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
+        g_wdw = dwt.reshape(k * k, C).t().reshape(C, 1, k, k).to(wdw.dtype)     # [k,k,C] -> Conv2d layout (49*C values)
+        return (dx.view(B * H * W, C), g_wdw, grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7],
+                None, None, None, None)
+
+
+class _DownsampleFn(torch.autograd.Function):
+    """LayerNorm2d + 2x2 / stride-2 conv of ConvNeXtStage (convnext.py:263-275, 300-302) on channels-last rows."""
+
+    @staticmethod
+    def forward(ctx, x, nw, nb, wconv, bconv, B, H, W, eps):
+        C = x.shape[1]
+        p = wconv.shape[-1]
+        h, mean, rstd = ops.layernorm_fwd(x, nw, nb, eps, save_stats=True)
+        w2 = wconv.permute(0, 2, 3, 1).reshape(wconv.shape[0], -1).contiguous()
+        patches = ops.patchify_nhwc(h.view(B, H, W, C), p) if p > 1 else h
+        out = ops.linear_fwd(patches, w2, bconv)
+        ctx.save_for_backward(x, nw, nb, wconv, bconv, mean, rstd, patches, w2)
+        ctx.meta = (B, H, W, C, p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .autograd import _c, _to_param_dtype
+        x, nw, nb, wconv, bconv, mean, rstd, patches, w2 = ctx.saved_tensors
+        B, H, W, C, p = ctx.meta
+        dout = _c(dout)
+        dpatches = ops.linear_dgrad(dout, w2)
+        gw2 = ops.linear_wgrad(dout, patches)                                     # [Cout, p*p*Cin] fp32
+        g_w = gw2.view(wconv.shape[0], p, p, C).permute(0, 3, 1, 2).contiguous().to(wconv.dtype)
+        g_b = None if bconv is None else _to_param_dtype(ops.colsum(dout), bconv)
+        dh = ops.unpatchify_nhwc(dpatches, B, H, W, C, p).view(B * H * W, C) if p > 1 else dpatches
+        dx, dnw, dnb = ops.layernorm_bwd(dh, x, nw, mean, rstd)
+        return dx, _to_param_dtype(dnw, nw), _to_param_dtype(dnb, nb), g_w, g_b, None, None, None, None
+
+
+class _AvgPoolFn(torch.autograd.Function):
+    """Global average pool over H*W (classifier.py:211-213); backward broadcasts dy / HW."""
+
+    @staticmethod
+    def forward(ctx, x, B, HW):
+        ctx.meta = (B, HW, x.shape[-1])
+        return ops.avgpool_nhwc(x.view(B, HW, -1))
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, HW, C = ctx.meta
+        g = (dy.float() / HW).to(dy.dtype)
+        return g[:, None, :].expand(B, HW, C).reshape(B * HW, C), None, None
+
+
 class LayerNorm2d(nn.LayerNorm):
     """timm.layers.LayerNorm2d (norm.py:113-134): LayerNorm over C of an NCHW tensor.  Parameter holder here --
     the fused forward applies it on channels-last rows."""
@@ -53,20 +167,43 @@ class ConvNeXtBlock(nn.Module):
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
 
     def forward_nhwc(self, x, B, H, W):
-        """x: [B*H*W, C] bf16 rows (channels-last).  convnext.py:197-213 without the permutes."""
-        C = x.shape[1]
-        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
-            raise B200Error("ConvNeXt DropPath in training mode is not covered")
-        y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
-        h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
-        a = ops.linear_fwd(h, self.mlp.fc1.weight, self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
-        return ops.linear_fwd(a, self.mlp.fc2.weight, self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
-                              gamma=self.gamma)
+        return block_forward_nhwc(self, x, B, H, W)
 
     def forward(self, x):
         B, C, H, W = x.shape
         rows = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
         return self.forward_nhwc(rows, B, H, W).view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def _check_block(blk):
+    """Raise B200Error unless `blk` (this mirror's or timm's ConvNeXtBlock) is the configuration the kernels cover."""
+    conv = blk.conv_dw
+    k = conv.kernel_size[0]
+    if (getattr(blk, "use_conv_mlp", False) or not isinstance(blk.shortcut, nn.Identity) or conv.stride != (1, 1)
+            or conv.dilation != (1, 1) or conv.groups != conv.in_channels or conv.in_channels != conv.out_channels
+            or conv.kernel_size != (k, k) or conv.padding != (k // 2, k // 2) or hasattr(blk.mlp, "grn")
+            or type(blk.mlp.act).__name__ != "GELU" or getattr(blk.mlp.act, "approximate", "none") != "none"
+            or type(blk.norm).__name__ not in ("LayerNorm",)):
+        raise B200Error("ConvNeXtBlock: conv_mlp / GRN / strided / dilated / non-GELU blocks are not covered")
+    dp = getattr(blk, "drop_path", None)
+    if blk.training and getattr(dp, "drop_prob", 0.) > 0:
+        raise B200Error("ConvNeXt DropPath in training mode is not covered")
+
+
+def block_forward_nhwc(self, x, B, H, W):
+    """x: [B*H*W, C] bf16 rows (channels-last).  convnext.py:197-213 without the permutes.  `self` is duck-typed:
+    this mirror's ConvNeXtBlock or timm's own (the plugin rebinds timm's forward onto this function)."""
+    C = x.shape[1]
+    _check_block(self)
+    if x.requires_grad or _needs_grad(self):
+        return _BlockFn.apply(x, self.conv_dw.weight, self.conv_dw.bias, self.norm.weight, self.norm.bias,
+                              self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
+                              self.gamma, B, H, W, self.norm.eps)
+    y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
+    h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+    a = ops.linear_fwd(h, self.mlp.fc1.weight, self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    return ops.linear_fwd(a, self.mlp.fc2.weight, self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
+                          gamma=self.gamma)
 
 
 class ConvNeXtStage(nn.Module):
@@ -92,19 +229,34 @@ class ConvNeXtStage(nn.Module):
             for i in range(depth)])
 
     def forward_nhwc(self, x, B, H, W):
-        if not isinstance(self.downsample, nn.Identity):
-            norm, conv = self.downsample[0], self.downsample[1]
-            p = conv.kernel_size[0]
-            C = x.shape[1]
+        return stage_forward_nhwc(self, x, B, H, W)
+
+
+def stage_forward_nhwc(self, x, B, H, W):
+    """ConvNeXtStage.forward (convnext.py:300-309) on channels-last rows; duck-typed like block_forward_nhwc."""
+    if getattr(self, "grad_checkpointing", False):
+        raise B200Error("gradient checkpointing is not covered")
+    if not isinstance(self.downsample, nn.Identity):
+        norm, conv = self.downsample[0], self.downsample[1]
+        p = conv.kernel_size[0]
+        C = x.shape[1]
+        if (len(self.downsample) != 2 or not isinstance(conv, nn.Conv2d) or conv.kernel_size != (p, p)
+                or conv.stride != (p, p) or conv.padding != (0, 0) or conv.groups != 1 or p not in (1, 2)
+                or type(norm).__name__ != "LayerNorm2d" or H % p or W % p):
+            raise B200Error("ConvNeXtStage: only LayerNorm2d + 1x1 / 2x2-stride-2 conv downsampling is covered")
+        if x.requires_grad or _needs_grad(self.downsample):
+            x = _DownsampleFn.apply(x, norm.weight, norm.bias, conv.weight, conv.bias, B, H, W, norm.eps)
+            H, W = H // p, W // p
+        else:
             h = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps)[0]
             w2 = _conv_weight_khwc(conv)
             if p > 1:
                 h = ops.patchify_nhwc(h.view(B, H, W, C), p)
                 H, W = H // p, W // p
             x = ops.linear_fwd(h, w2, conv.bias)
-        for blk in self.blocks:
-            x = blk.forward_nhwc(x, B, H, W)
-        return x, H, W
+    for blk in self.blocks:
+        x = block_forward_nhwc(blk, x, B, H, W)
+    return x, H, W
 
 
 def _dw_weight_t(conv):
@@ -144,14 +296,30 @@ class NormMlpClassifierHead(nn.Module):
         self.fc = nn.Linear(in_features, num_classes, **dd) if num_classes > 0 else nn.Identity()
 
     def forward_nhwc(self, x, B, HW, pre_logits=False):
-        pooled = ops.avgpool_nhwc(x.view(B, HW, -1))
-        h = ops.layernorm_fwd(pooled, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+        return head_forward_nhwc(self, x, B, HW, pre_logits)
+
+
+def head_forward_nhwc(self, x, B, HW, pre_logits=False):
+    """NormMlpClassifierHead.forward (classifier.py:211-220): avg-pool -> LayerNorm2d -> fc, on channels-last rows."""
+    pool = getattr(self, "global_pool", None)
+    if ((pool is not None and getattr(pool, "pool_type", "avg") != "avg") or type(self.norm).__name__ != "LayerNorm2d"
+            or not isinstance(getattr(self, "pre_logits", nn.Identity()), nn.Identity)
+            or (self.training and getattr(self.drop, "p", 0.) > 0)):
+        raise B200Error("NormMlpClassifierHead: hidden layer / non-avg pooling / head dropout are not covered")
+    if x.requires_grad or _needs_grad(self):
+        from .autograd import LayerNormFn, LinearFn
+        h = LayerNormFn.apply(_AvgPoolFn.apply(x, B, HW), self.norm.weight, self.norm.bias, self.norm.eps)
         if pre_logits or isinstance(self.fc, nn.Identity):
             return h
-        from .functional import _padded_out_linear
-        if self.fc.weight.shape[0] % 8:
-            return _padded_out_linear(self.fc, h)
-        return ops.linear_fwd(h, self.fc.weight, self.fc.bias)
+        return LinearFn.apply(h, self.fc.weight, self.fc.bias)
+    pooled = ops.avgpool_nhwc(x.view(B, HW, -1))
+    h = ops.layernorm_fwd(pooled, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+    if pre_logits or isinstance(self.fc, nn.Identity):
+        return h
+    from .functional import _padded_out_linear
+    if self.fc.weight.shape[0] % 8:
+        return _padded_out_linear(self.fc, h)
+    return ops.linear_fwd(h, self.fc.weight, self.fc.bias)
 
 
 class ConvNeXt(nn.Module):
@@ -205,28 +373,7 @@ class ConvNeXt(nn.Module):
         return self.head.fc
 
     def _features_nhwc(self, img):
-        if not img.is_cuda:
-            raise B200Error("libb200timm kernels need CUDA tensors (there is no CPU path)")
-        if img.dtype != torch.bfloat16 or self.stem[0].weight.dtype != torch.bfloat16:
-            raise B200Error("ConvNeXt B200 path needs bf16 inputs and weights (model.to(torch.bfloat16))")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise B200Error("ConvNeXt training (backward) is not covered yet; wrap inference in torch.no_grad()")
-        conv, norm = self.stem[0], self.stem[1]
-        p = conv.kernel_size[0]
-        B, C, H, W = img.shape
-        if H % p or W % p:
-            raise B200Error("image size must be divisible by the stem patch size")
-        K = C * p * p
-        kpad = (K + 7) // 8 * 8
-        w2 = conv.weight.view(conv.weight.shape[0], K)
-        if kpad != K:
-            raise B200Error("stem patch size with C*p*p not a multiple of 8 is not covered")
-        x = ops.gemm(ops.patchify(img.contiguous(), p, kpad), w2, B * (H // p) * (W // p), w2.shape[0], kpad, bias=conv.bias)
-        x = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps)[0]
-        H, W = H // p, W // p
-        for stage in self.stages:
-            x, H, W = stage.forward_nhwc(x, B, H, W)
-        return x, B, H, W
+        return features_nhwc(self, img)
 
     def forward_features(self, img):
         """NCHW feature map like timm's forward_features (convnext.py:606-611); the permute is a view."""
@@ -241,6 +388,41 @@ class ConvNeXt(nn.Module):
     def forward(self, img):
         x, B, H, W = self._features_nhwc(img)
         return self.head.forward_nhwc(x, B, H * W)
+
+
+def features_nhwc(self, img):
+    """stem -> stages (convnext.py:606-611) on channels-last rows; `self` is this mirror's ConvNeXt or timm's."""
+    if not img.is_cuda:
+        raise B200Error("libb200timm kernels need CUDA tensors (there is no CPU path)")
+    if img.dtype != torch.bfloat16 or self.stem[0].weight.dtype != torch.bfloat16:
+        raise B200Error("ConvNeXt B200 path needs bf16 inputs and weights (model.to(torch.bfloat16))")
+    if (len(self.stem) != 2 or not isinstance(self.stem[0], nn.Conv2d) or type(self.stem[1]).__name__ != "LayerNorm2d"
+            or not isinstance(getattr(self, "norm_pre", nn.Identity()), nn.Identity)):
+        raise B200Error("ConvNeXt: only the patch stem (conv + LayerNorm2d) without norm_pre is covered")
+    conv, norm = self.stem[0], self.stem[1]
+    p = conv.kernel_size[0]
+    if conv.kernel_size != (p, p) or conv.stride != (p, p) or conv.padding != (0, 0):
+        raise B200Error("ConvNeXt: the stem must be a non-overlapping patch conv")
+    B, C, H, W = img.shape
+    if H % p or W % p:
+        raise B200Error("image size must be divisible by the stem patch size")
+    K = C * p * p
+    kpad = (K + 7) // 8 * 8
+    w2 = conv.weight.view(conv.weight.shape[0], K)
+    if kpad != K:
+        raise B200Error("stem patch size with C*p*p not a multiple of 8 is not covered")
+    if _needs_grad(self.stem):
+        from .autograd import LayerNormFn, PatchEmbedFn
+        x = PatchEmbedFn.apply(img, conv.weight, conv.bias, p).reshape(B * (H // p) * (W // p), -1)
+        x = LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+    else:
+        x = ops.gemm(ops.patchify(img.contiguous(), p, kpad), w2, B * (H // p) * (W // p), w2.shape[0], kpad,
+                     bias=conv.bias)
+        x = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps)[0]
+    H, W = H // p, W // p
+    for stage in self.stages:
+        x, H, W = stage_forward_nhwc(stage, x, B, H, W)
+    return x, B, H, W
 
 
 MODEL_ARGS = {

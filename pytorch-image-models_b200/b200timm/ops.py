@@ -14,7 +14,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
-    "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "patchify_nhwc",
+    "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
     "avgpool_nhwc", "naflex_assemble", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
 ]
 
@@ -340,9 +340,12 @@ def dwconv_weight_t(weight):
     return weight.detach().reshape(weight.shape[0], -1).t().contiguous().view(weight.shape[-2], weight.shape[-1], -1)
 
 
-def dwconv_nhwc(x, weight_t, bias):
-    """Depthwise k x k conv (stride 1, pad k//2) on a contiguous bf16 [B,H,W,C] tensor; weight_t [k,k,C]."""
-    _need_cuda(x, weight_t, bias)
+def dwconv_nhwc(x, weight_t, bias, residual=None):
+    """Depthwise k x k conv (stride 1, pad k//2) on a contiguous bf16 [B,H,W,C] tensor; weight_t [k,k,C];
+    optional residual (same shape as x) added to the output."""
+    _need_cuda(x, weight_t, bias, residual)
+    if residual is not None and (residual.dtype != torch.bfloat16 or residual.shape != x.shape or not residual.is_contiguous()):
+        raise B200Error("dwconv_nhwc: residual must be a contiguous bf16 tensor shaped like x")
     if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_contiguous():
         raise B200Error("dwconv_nhwc: need a contiguous bf16 [B,H,W,C] tensor")
     B, H, W, C = x.shape
@@ -350,11 +353,38 @@ def dwconv_nhwc(x, weight_t, bias):
     if tuple(weight_t.shape) != (k, k, C) or weight_t.dtype != torch.bfloat16 or not weight_t.is_contiguous():
         raise B200Error("dwconv_nhwc: weight_t must be contiguous bf16 [k,k,C] (see dwconv_weight_t)")
     y = torch.empty_like(x)
-    rc = _lib.load().b200_dwconv_nhwc(x.data_ptr(), weight_t.data_ptr(), _ptr(bias), y.data_ptr(), B, H, W, C, k,
+    rc = _lib.load().b200_dwconv_nhwc(x.data_ptr(), weight_t.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), B, H, W, C, k,
                                       _dt(bias) if bias is not None else DTYPE_BF16, _stream())
     _lib.check(rc, "b200_dwconv_nhwc")
     _count()
     return y
+
+
+def dwconv_nhwc_wgrad(x, dy, k, out=None):
+    """fp32 [k,k,C] gradient of the depthwise weight (transposed layout); `out` must be zero-initialised."""
+    _need_cuda(x, dy, out)
+    for t in (x, dy):
+        if t.dim() != 4 or t.dtype != torch.bfloat16 or not t.is_contiguous() or t.shape != x.shape:
+            raise B200Error("dwconv_nhwc_wgrad: need contiguous bf16 [B,H,W,C] tensors of equal shape")
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.zeros(k, k, C, dtype=torch.float32, device=x.device)
+    rc = _lib.load().b200_dwconv_nhwc_wgrad(x.data_ptr(), dy.data_ptr(), out.data_ptr(), B, H, W, C, k, _stream())
+    _lib.check(rc, "b200_dwconv_nhwc_wgrad")
+    _count()
+    return out
+
+
+def unpatchify_nhwc(patches, B, H, W, C, p):
+    """Inverse of patchify_nhwc: [B*(H/p)*(W/p), p*p*C] -> [B,H,W,C]."""
+    _need_cuda(patches)
+    if patches.dtype != torch.bfloat16 or not patches.is_contiguous() or patches.numel() != B * H * W * C:
+        raise B200Error("unpatchify_nhwc: need a contiguous bf16 patch matrix of B*H*W*C elements")
+    out = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=patches.device)
+    rc = _lib.load().b200_unpatchify_nhwc(patches.data_ptr(), out.data_ptr(), B, H, W, C, p, _stream())
+    _lib.check(rc, "b200_unpatchify_nhwc")
+    _count()
+    return out
 
 
 def patchify_nhwc(x, p):
@@ -474,5 +504,5 @@ def _timed(name, fn):
 
 
 for _n in ("layernorm_fwd", "layernorm_bwd", "gemm", "attention_fwd", "attention_bwd", "patchify", "assemble_tokens",
-           "colsum", "convert_f32", "dwconv_nhwc", "patchify_nhwc", "avgpool_nhwc", "naflex_assemble"):
+           "colsum", "convert_f32", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc", "avgpool_nhwc", "naflex_assemble"):
     globals()[_n] = _timed(_n, globals()[_n])

@@ -83,6 +83,32 @@ def _vit_forward(self, x, attn_mask=None, is_causal=False):
     return BF.vit_forward(self, x, _kv_len(attn_mask, n))
 
 
+def _convnext_forward(self, x):
+    from . import convnext as CN
+    rows, B, H, W = CN.features_nhwc(self, x)
+    return CN.head_forward_nhwc(self.head, rows, B, H * W)
+
+
+def _convnext_features(self, x):
+    from . import convnext as CN
+    rows, B, H, W = CN.features_nhwc(self, x)
+    return rows.view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def _convnext_head(self, x, pre_logits=False):
+    from . import convnext as CN
+    B, C, H, W = x.shape
+    rows = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
+    return CN.head_forward_nhwc(self.head, rows, B, H * W, pre_logits)
+
+
+def _convnext_block(self, x):
+    from . import convnext as CN
+    B, C, H, W = x.shape
+    rows = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
+    return CN.block_forward_nhwc(self, rows, B, H, W).view(B, H, W, C).permute(0, 3, 1, 2)
+
+
 def install():
     """Rebind timm's hot-path forwards.  Idempotent.  Raises if timm or libb200timm.so is unavailable."""
     _lib.load()  # fail loudly: no silent PyTorch path when the CUDA library is missing
@@ -91,6 +117,7 @@ def install():
     from timm.layers.mlp import Mlp
     from timm.layers.norm import LayerNorm
     from timm.layers.patch_embed import PatchEmbed
+    from timm.models.convnext import ConvNeXt, ConvNeXtBlock
     from timm.models.vision_transformer import Block, VisionTransformer
     if _ORIG:
         return
@@ -106,6 +133,10 @@ def install():
         ("timm.models.vision_transformer.VisionTransformer.forward_head", VisionTransformer, "forward_head",
          lambda self, x, pre_logits=False: BF.vit_forward_head(self, x, pre_logits)),
         ("timm.models.vision_transformer.VisionTransformer.forward", VisionTransformer, "forward", _vit_forward),
+        ("timm.models.convnext.ConvNeXtBlock.forward", ConvNeXtBlock, "forward", _convnext_block),
+        ("timm.models.convnext.ConvNeXt.forward_features", ConvNeXt, "forward_features", _convnext_features),
+        ("timm.models.convnext.ConvNeXt.forward_head", ConvNeXt, "forward_head", _convnext_head),
+        ("timm.models.convnext.ConvNeXt.forward", ConvNeXt, "forward", _convnext_forward),
     ]
     for name, cls, attr, fn in table:
         _ORIG[name] = getattr(cls, attr)

@@ -84,3 +84,54 @@ def test_convnext_base_matches_oracle():
     assert torch.isfinite(logits).all()
     assert e_ours <= max(2 * e_ref, 2e-2) and cos >= 0.9995, (
         f"convnext_base: max err {e_ours:.4g} vs eager-bf16 {e_ref:.4g} (ref absmax {ref.abs().max().item():.3g}), cos {cos:.6f}")
+
+
+def test_dwconv_backward_kernels():
+    from b200timm import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W, C, k = 2, 14, 14, 64, 7
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, 1, k, k, device="cuda", generator=g) * 0.2).bfloat16()
+    dy = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    res = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    torch.nn.functional.conv2d(xr, wr, None, padding=k // 2, groups=C).backward(dy.float().permute(0, 3, 1, 2))
+    wt = ops.dwconv_weight_t(w)
+    dx = ops.dwconv_nhwc(dy, wt.flip(0, 1).contiguous(), None, residual=res)
+    _check(dx, xr.grad.permute(0, 2, 3, 1) + res.float(), 3e-2, 1e-2, "dwconv dgrad (+ shortcut gradient)")
+    dwt = ops.dwconv_nhwc_wgrad(x, dy, k)
+    _check(dwt.reshape(k * k, C).t().reshape(C, 1, k, k), wr.grad, 6e-2, 1e-2, "dwconv wgrad")
+    p = ops.patchify_nhwc(x, 2)
+    assert torch.equal(ops.unpatchify_nhwc(p, B, H, W, C, 2), x)
+
+
+def test_convnext_backward_matches_oracle_autograd():
+    """Every parameter gradient of a small ConvNeXt (depthwise conv, LayerNorm, MLP, LayerScale gamma, downsample,
+    stem, head) after a cross-entropy loss, against PyTorch autograd of the fp32 oracle."""
+    from oracle import convnext_oracle as C
+    from b200timm.convnext import ConvNeXt
+    cfg = dict(depths=(1, 1, 2, 1), dims=(32, 64, 128, 256))
+    sd = {k: v.bfloat16().float() for k, v in C.random_state_dict(cfg, seed=11, num_classes=16).items()}
+    model = ConvNeXt(num_classes=16, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().to(torch.bfloat16).train()
+    g = torch.Generator().manual_seed(6)
+    img = torch.randn(4, 3, 64, 64, generator=g).bfloat16()
+    target = torch.randint(0, 16, (4,), generator=g)
+    loss = torch.nn.functional.cross_entropy(model(img.cuda()).float(), target.cuda())
+    loss.backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_loss = torch.nn.functional.cross_entropy(C.convnext_forward(img.float(), ref_sd, cfg), target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 3e-2, (loss.item(), ref_loss.item())
+    scale = max(v.grad.float().norm().item() for v in ref_sd.values())
+    for n, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        ref = ref_sd[n].grad
+        denom = ref.norm().item()
+        if denom < 1e-3 * scale:
+            continue
+        rel = (p.grad.float().cpu() - ref).norm().item() / denom
+        cos = torch.nn.functional.cosine_similarity(p.grad.float().cpu().flatten(), ref.flatten(), dim=0).item()
+        assert rel <= 5e-2 and cos >= 0.998, f"{n}: rel L2 err {rel:.4f}, cos {cos:.5f}"

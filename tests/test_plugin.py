@@ -61,3 +61,30 @@ def test_mirror_and_timm_state_dicts_are_interchangeable():
     assert list(ours.state_dict()) == list(theirs.state_dict())
     theirs.load_state_dict(ours.state_dict(), strict=True)
     ours.load_state_dict(theirs.state_dict(), strict=True)
+
+
+def test_convnext_is_rebound_and_covered_configs_are_recognised(plugin):
+    """timm's ConvNeXt / ConvNeXtBlock dispatch through the plugin; the duck-typed coverage checks accept timm's
+    convnext_tiny modules (patch stem, LayerNorm, Linear MLP, exact GELU) and reject ConvNeXt-V2's GRN blocks; a
+    CPU call keeps timm's own forward."""
+    from timm.models.convnext import ConvNeXt, ConvNeXtBlock
+    from b200timm import convnext as CN
+    from b200timm._lib import B200Error
+    assert hasattr(ConvNeXt.forward, "_b200_original") and hasattr(ConvNeXtBlock.forward, "_b200_original")
+    model = timm.create_model("convnext_tiny", num_classes=5).eval()
+    for stage in model.stages:
+        for blk in stage.blocks:
+            CN._check_block(blk)
+    v2 = timm.create_model("convnextv2_atto", num_classes=5)
+    with pytest.raises(B200Error):
+        CN._check_block(v2.stages[0].blocks[0])
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        y_plugin = model(x)
+    plugin.uninstall()
+    with torch.no_grad():
+        y_ref = model(x)
+    plugin.install()
+    assert torch.equal(y_plugin, y_ref)
+    ours = CN.create_model("convnext_tiny", num_classes=5)
+    assert list(ours.state_dict()) == list(model.state_dict())

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--img-size", type=int, default=224)
     ap.add_argument("--detail", action="store_true", help="per-op CUDA-event time split of one step")
+    ap.add_argument("--train", action="store_true", help="forward + cross-entropy + backward + SGD step")
     args = ap.parse_args()
     from b200timm import ops
     if args.model.startswith("convnext"):
@@ -33,6 +34,8 @@ def main():
     model = model.cuda().to(torch.bfloat16).eval()
     size = 336 if "336" in args.model else args.img_size
     xs = [torch.randn(args.batch, 3, size, size, device="cuda").bfloat16() for _ in range(2)]
+    if args.train:
+        return train(args, model, xs, ops)
     with torch.no_grad():
         for i in range(args.warmup):
             model(xs[i & 1])
@@ -56,6 +59,42 @@ def main():
             print(f"  {t:8.3f} ms {100 * t / tot:5.1f}%  n={n:3d}  {k}")
     print(json.dumps({"model": args.model, "batch": args.batch, "img_size": size, "ms_per_step": round(ms, 3),
                       "img_per_s": round(args.batch / ms * 1e3, 1), "launches_per_step": ops.launch_count() // args.steps}))
+
+
+def train(args, model, xs, ops):
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+    target = torch.randint(0, 1000, (args.batch,), device="cuda")
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(model(x).float(), target)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(xs[i & 1])
+    torch.cuda.synchronize()
+    ops.reset_counters()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        loss = step(xs[i & 1])
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / args.steps
+    if args.detail:
+        ops.enable_op_timing(True)
+        step(xs[0])
+        det = ops.op_timing_summary()
+        ops.enable_op_timing(False)
+        tot = sum(t for _, t in det.values())
+        for k, (n, t) in sorted(det.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {t:8.3f} ms {100 * t / tot:5.1f}%  n={n:3d}  {k}")
+    print(json.dumps({"model": args.model, "mode": "train", "batch": args.batch, "img_size": xs[0].shape[-1],
+                      "ms_per_step": round(ms, 3), "img_per_s": round(args.batch / ms * 1e3, 1), "loss": round(loss.item(), 4),
+                      "launches_per_step": ops.launch_count() // args.steps}))
 
 
 if __name__ == "__main__":
