@@ -37,12 +37,19 @@ struct GemmKernelParams {
   int num_m_blocks, num_n_blocks, num_k_blocks;  // num_k_blocks: total over K
   int split_k, k_blocks_per_split;
   int epilogue, out_f32, bias_f32, gamma_f32, accumulate;
+  unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_gemm_set_trace), nullptr in production
 };
 
-template <int BN, int STAGES>
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int BN, int STAGES, bool CTA2 = false>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (CTA2 ? BN / 2 : BN) * BK * 2;   // a CTA pair holds half of the B tile each
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingOffset = STAGES * kStageBytes;   // kNumEpiWarps x 2 KB (32 rows x 64 B each)
   static constexpr int kStagingBytes = kNumEpiWarps * 2048;
@@ -95,12 +102,17 @@ __device__ __forceinline__ void load8_param2(const void* base, int f32, int col,
   }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                  const __grid_constant__ CUtensorMap tmap_out2, const GemmKernelParams p) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CTA2>;
+  // CTA2: the kernel runs as clusters of two CTAs on one TPC.  The pair owns a 256 x BN output tile: each CTA loads
+  // its own 128 rows of A and HALF of the B tile, the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) which
+  // reads both B halves, and each CTA's TMEM receives its own 128 x BN accumulator -- per SM 32 KB instead of 48 KB
+  // of operands per k-block come through L2 / TMA / shared memory.
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
@@ -112,6 +124,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* const trace = p.trace ? p.trace + blockIdx.x * 12 : nullptr;
+  if (trace && threadIdx.x == 0) {
+    trace[0] = gtime();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace[11] = smid;
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -122,7 +141,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kNumEpiWarps * 32);
+      mbar_init(&tempty_bar[i], kNumEpiWarps * (CTA2 ? 2 : 1));   // one arrival per epilogue warp (of both CTAs)
     }
     for (int i = 0; i < kNumEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     tma_prefetch_desc(&tmap_out);
@@ -131,53 +150,92 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_ptr_smem, 2 * BN);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_pair(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (trace && threadIdx.x == 0) trace[1] = gtime();
 
-  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  // CTA2: tiles are 256-row pairs of m-blocks, walked by cluster; this CTA's m-block is 2 * pair + rank
+  const int num_m_units = CTA2 ? (p.num_m_blocks + 1) / 2 : p.num_m_blocks;
+  const int tiles_mn = num_m_units * p.num_n_blocks;
   const int num_tiles = tiles_mn * p.split_k;
+  const int tile0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp_idx == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long wait_slot = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
-      const int m_blk = mn / p.num_n_blocks;
-      const int n_blk = mn - m_blk * p.num_n_blocks;
+      const int m_unit = mn / p.num_n_blocks;
+      const int n_blk = mn - m_unit * p.num_n_blocks;
+      const int m_blk = CTA2 ? 2 * m_unit + static_cast<int>(cta_rank) : m_unit;
+      const int n_row0 = n_blk * BN + (CTA2 ? static_cast<int>(cta_rank) * (BN / 2) : 0);   // first B row this CTA loads
       const int kb0 = ks * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (trace) {
+          const long long c0 = clock64();
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          wait_slot += clock64() - c0;
+        } else {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+        }
         uint8_t* sa = smem + stage * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-        if constexpr (!A_MN) {
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
-        } else {
+        if constexpr (CTA2) {
+          // both CTAs' bytes complete on the LEADER's barrier (the leader alone issues the MMAs)
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 64; ++i)
-            tma_load_2d(sa + i * (64 * BK * 2), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
-        }
-        if constexpr (!B_MN) {
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
-        } else {
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d_pair(sa + i * (64 * BK * 2), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BK, n_row0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i)
-            tma_load_2d(sb + i * (64 * BK * 2), &tmap_b, &full_bar[stage], n_blk * BN + i * 64, kb * BK);
+            for (int i = 0; i < BN / 128; ++i)
+              tma_load_2d_pair(sb + i * (64 * BK * 2), &tmap_b, &full_bar[stage], n_row0 + i * 64, kb * BK);
+          }
+        } else {
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d(sa + i * (64 * BK * 2), &tmap_a, &full_bar[stage], m_blk * BM + i * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_row0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (64 * BK * 2), &tmap_b, &full_bar[stage], n_row0 + i * 64, kb * BK);
+          }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp_idx == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (trace) trace[9] = wait_slot;
+  } else if (warp_idx == 1 && lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (the leader CTA of a pair)
+    constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * BM : BM, BN, A_MN, B_MN);
     // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); one UMMA_K=16 step = +32 B.
     // MN-major SW128: 64-element (128 B) runs along MN, 8 k-rows per 1024 B (SBO), next 64 MN elements
     //                 64*BK*2 B further (LBO); one UMMA_K=16 step = 16 k-rows = +2048 B.
@@ -187,15 +245,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long wait_ops = 0, wait_acc = 0;
+    unsigned long long first_ops = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int ks = tile / tiles_mn;
       const int kb0 = ks * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.num_k_blocks);
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      if (trace) {
+        const long long c0 = clock64();
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        wait_acc += clock64() - c0;
+      } else {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+      }
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        if (trace) {
+          const long long c0 = clock64();
+          mbar_wait(&full_bar[stage], phase);
+          wait_ops += clock64() - c0;
+          if (first_ops == 0) first_ops = gtime();
+        } else {
+          mbar_wait(&full_bar[stage], phase);
+        }
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
         const uint32_t sb = sa + L::kABytes;
@@ -203,15 +276,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint64_t bdesc = make_smem_desc(sb, b_lbo, 1024, kLayoutSw128);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          umma_ss(tmem_d, adesc + static_cast<uint64_t>(k * a_kstep), bdesc + static_cast<uint64_t>(k * b_kstep),
-                  idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if constexpr (CTA2)
+            umma_ss_pair(tmem_d, adesc + static_cast<uint64_t>(k * a_kstep), bdesc + static_cast<uint64_t>(k * b_kstep),
+                         idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          else
+            umma_ss(tmem_d, adesc + static_cast<uint64_t>(k * a_kstep), bdesc + static_cast<uint64_t>(k * b_kstep),
+                    idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+        // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+        if constexpr (CTA2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+      // accumulator ready for the epilogue (of both CTAs)
+      if constexpr (CTA2) umma_commit_pair(&tfull_bar[as]); else umma_commit(&tfull_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (trace) { trace[7] = wait_ops; trace[8] = wait_acc; trace[2] = first_ops; }
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------ epilogue
     const int ew = warp_idx - 4;
@@ -228,11 +308,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t aux_phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    unsigned long long first_acc = 0, last_acc = 0, ntiles = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
-      const int m_blk = mn / p.num_n_blocks;
-      const int n_blk = mn - m_blk * p.num_n_blocks;
+      const int m_unit = mn / p.num_n_blocks;
+      const int n_blk = mn - m_unit * p.num_n_blocks;
+      const int m_blk = CTA2 ? 2 * m_unit + static_cast<int>(cta_rank) : m_unit;
       const int row0 = m_blk * BM + quad * 32;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + part * kColsPerWarp;
       // per-row scale of the residual branch (DropPath keep-mask / keep_prob of the row's sample, drop.py:158-175)
@@ -253,6 +335,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&tfull_bar[as], aphase);
           tc_fence_after();
           waited = true;
+          if (trace && ew == 0 && lane == 0) {
+            last_acc = gtime();
+            if (first_acc == 0) first_acc = last_acc;
+            ++ntiles;
+          }
         }
         uint4 aq[4] = {};   // residual tile of this round, kept when the branch output is stored first (out2)
         if (p.out_f32) {
@@ -338,7 +425,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if (rc + round_cols >= kColsPerWarp) {  // last TMEM read of this tile: hand the accumulator back
           tc_fence_before();
-          mbar_arrive(&tempty_bar[as]);
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CTA2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);
+          }
         }
         if (dual) {
           // the staging tile holds the bf16 pre-activation: store it to out2, then apply GELU to exactly those
@@ -398,19 +488,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();
+    if (trace && ew == 0 && lane == 0) { trace[3] = first_acc; trace[4] = last_acc; trace[10] = ntiles; trace[5] = gtime(); }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // a pair leaves together: peer smem / barriers stay valid
   if (warp_idx == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (CTA2) tmem_dealloc_pair(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
+  if (trace && threadIdx.x == 0) trace[6] = gtime();
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+static unsigned long long* g_gemm_trace = nullptr;
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2 = false>
 static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CTA2>;
+  constexpr int kBRows = CTA2 ? BN / 2 : BN;   // B rows one CTA loads per k-block
   CUtensorMap ta, tb;
   {
     // A: K-major -> dims {K, M}, box {64, 128}; MN-major -> dims {M, K}, box {64, 64}
@@ -421,7 +516,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
     strides[0] = static_cast<uint64_t>(d.lda) * 2;
     int rc = encode_tmap_bf16(&ta, d.a, 2, dims, strides, box, true);
     if (rc) return rc;
-    if (!B_MN) { dims[0] = d.K; dims[1] = d.N; box[0] = BK; box[1] = BN; }
+    if (!B_MN) { dims[0] = d.K; dims[1] = d.N; box[0] = BK; box[1] = kBRows; }
     else       { dims[0] = d.N; dims[1] = d.K; box[0] = 64; box[1] = BK; }
     strides[0] = static_cast<uint64_t>(d.ldb) * 2;
     rc = encode_tmap_bf16(&tb, d.b, 2, dims, strides, box, true);
@@ -469,24 +564,57 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.epilogue = d.epilogue; p.out_f32 = d.out_dtype == B200_DTYPE_F32;
   p.bias_f32 = d.bias_dtype == B200_DTYPE_F32; p.gamma_f32 = d.gamma_dtype == B200_DTYPE_F32;
   p.accumulate = d.accumulate;
+  p.trace = g_gemm_trace;
 
-  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2>;
   static bool attr_set = false;  // idempotent; a benign race sets the same value twice
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
-  int grid = sm_count();
-  if (grid > num_tiles) grid = num_tiles;
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, tout, taux, tout2, p);
-  B200_CUDA_OK(cudaGetLastError());
-  return B200_OK;
+  if constexpr (CTA2) {
+    const int num_tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks * p.split_k;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sm_count() & ~1, 1, 1);
+    cfg.blockDim = dim3(kNumThreads, 1, 1);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent grid = the number of CTA pairs the device can hold at once (74 on a full B200: one per TPC)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      int n = 0;
+      B200_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      if (n <= 0) return fail(B200_ERR_CUDA, "b200_gemm: the device cannot host a CTA pair of the GEMM kernel");
+      max_clusters = n;
+    }
+    const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, tout2, p));
+    return B200_OK;
+  } else {
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
+    int grid = sm_count();
+    if (grid > num_tiles) grid = num_tiles;
+    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, tout, taux, tout2, p);
+    B200_CUDA_OK(cudaGetLastError());
+    return B200_OK;
+  }
 }
 
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" void b200_gemm_set_trace(void* device_buf) {
+  g_gemm_trace = reinterpret_cast<unsigned long long*>(device_buf);
+}
 
 extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   if (dp == nullptr) return fail(B200_ERR_INVALID_ARG, "b200_gemm: null descriptor");
@@ -528,6 +656,14 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
 
   // Tile-N selection: 256 wide unless N is small (wasted columns) -- 128 then.
   const bool wide = d.N > 128;
+  // CTA pairs (256 x 256 tiles, cta_group::2) once there are enough 256-row tile pairs to fill the GPU
+  static const int pair_mode = [] { const char* e = getenv("B200_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+  if (wide && pair_mode && d.M >= 256) {
+    if (!d.a_mn && !d.b_mn) return launch_gemm<256, 6, false, false, true>(d, stream);
+    if (!d.a_mn && d.b_mn) return launch_gemm<256, 6, false, true, true>(d, stream);
+    if (d.a_mn && d.b_mn) return launch_gemm<256, 6, true, true, true>(d, stream);
+    return launch_gemm<256, 6, true, false, true>(d, stream);
+  }
   if (wide) {
     if (!d.a_mn && !d.b_mn) return launch_gemm<256, 4, false, false>(d, stream);
     if (!d.a_mn && d.b_mn) return launch_gemm<256, 4, false, true>(d, stream);

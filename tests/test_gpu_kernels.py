@@ -41,7 +41,8 @@ def _dgelu(x):
 
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (1000, 768, 768), (394, 200, 72), (77, 1000, 192)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (1000, 768, 768), (394, 200, 72), (77, 1000, 192),
+                                   (640, 520, 320)])   # 5 m-blocks: the last CTA pair has an empty second half
 def test_gemm_layouts(a_mn, b_mn, M, N, K):
     ops = _ops()
     g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
