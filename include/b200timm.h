@@ -80,11 +80,12 @@ typedef struct b200_gemm_desc {
 
 B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);
 
-/* Debug hook (tools/gemm_trace.py): when `device_buf` (>= 12 * #SMs uint64, zero-filled by the caller) is non-NULL
- * every following b200_gemm launch records per-CTA %globaltimer stamps (entry, setup done, first operands landed,
- * first / last accumulator ready, stores drained, exit) and barrier-wait cycle totals into it.  NULL switches it off.
- * Not part of the reference-facing surface. */
-B200_API void b200_gemm_set_trace(void* device_buf);
+/* Debug hook (tools/gemm_trace.py, tools/attn_trace.py), not part of the reference-facing surface.  kernel 0 = b200_gemm:
+ * with a non-NULL `device_buf` (>= 12 * #SMs uint64, zeroed by the caller) every following launch records per-CTA
+ * %globaltimer stamps (entry, setup done, first operands landed, first / last accumulator ready, stores drained, exit)
+ * and barrier-wait cycle totals.  kernel 1 = b200_attn_fwd (N <= 208 kernel): 16 int64 per CTA, cycles spent per softmax
+ * phase (wait S, max pass, exp pass, wait O, epilogue) and per issuer wait.  NULL switches a trace off. */
+B200_API void b200_set_trace(int32_t kernel, void* device_buf);
 
 /* ------------------------------------------------------------------ LayerNorm   timm/layers/norm.py:85-90
  * y = (x - mean) * rstd * weight + bias over the last dim (cols).  x,y: [rows, cols]; x bf16 or f32,

@@ -37,7 +37,7 @@ struct GemmKernelParams {
   int num_m_blocks, num_n_blocks, num_k_blocks;  // num_k_blocks: total over K
   int split_k, k_blocks_per_split;
   int epilogue, out_f32, bias_f32, gamma_f32, accumulate;
-  unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_gemm_set_trace), nullptr in production
+  unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_set_trace), nullptr in production
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -46,13 +46,13 @@ __device__ __forceinline__ unsigned long long gtime() {
   return t;
 }
 
-template <int BN, int STAGES, bool CTA2 = false>
+template <int BN, int STAGES, bool CTA2 = false, int RC = 32>
 struct GemmSmem {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (CTA2 ? BN / 2 : BN) * BK * 2;   // a CTA pair holds half of the B tile each
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingOffset = STAGES * kStageBytes;   // kNumEpiWarps x 2 KB (32 rows x 64 B each)
-  static constexpr int kStagingBytes = kNumEpiWarps * 2048;
+  static constexpr int kStagingOffset = STAGES * kStageBytes;   // kNumEpiWarps staging tiles of 32 rows x 2*RC bytes
+  static constexpr int kStagingBytes = kNumEpiWarps * 32 * RC * 2;
   static constexpr int kBarrierOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarrierOffset + 512 + 1024;  // + barriers + alignment slack
 };
@@ -102,12 +102,14 @@ __device__ __forceinline__ void load8_param2(const void* base, int f32, int col,
   }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2, int RC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                  const __grid_constant__ CUtensorMap tmap_out2, const GemmKernelParams p) {
-  using L = GemmSmem<BN, STAGES, CTA2>;
+  using L = GemmSmem<BN, STAGES, CTA2, RC>;
+  static_assert(RC == 32 || RC == 64, "staging rows are 64 or 128 bytes");
+  static_assert((BN / 4) % RC == 0, "a warp's BN/4 columns are a whole number of rounds");
   // CTA2: the kernel runs as clusters of two CTAs on one TPC.  The pair owns a 256 x BN output tile: each CTA loads
   // its own 128 rows of A and HALF of the B tile, the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) which
   // reads both B halves, and each CTA's TMEM receives its own 128 x BN accumulator -- per SM 32 KB instead of 48 KB
@@ -294,17 +296,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (trace) { trace[7] = wait_ops; trace[8] = wait_acc; trace[2] = first_ops; }
   } else if (warp_idx >= 4) {
     // ------------------------------------------------------------ epilogue
+    // Each warp owns 32 accumulator rows x BN/4 columns of the tile and moves them in rounds of RC bf16 columns
+    // (RC/2 fp32 columns): TMEM -> registers (32 columns per tcgen05.ld) -> epilogue math -> swizzled staging tile
+    // (32 rows x 2*RC bytes, the TMA box layout) -> one TMA store per round.  With RC = BN/4 a tile is a single
+    // round per warp: the residual / pre-activation tile is requested before the accumulator is even ready and the
+    // staging tile is only reused a whole mainloop later, so no TMA latency sits on the epilogue's critical path.
     const int ew = warp_idx - 4;
     const int quad = warp_idx & 3;          // TMEM lane quadrant this warp may access
     const int part = ew >> 2;               // which quarter of the BN columns
     constexpr int kColsPerWarp = BN / 4;
-    uint8_t* stg = smem + L::kStagingOffset + ew * 2048;   // 32 rows x 64 B, 64B-swizzled (TMA box layout)
-    const uint32_t stg_row = smem_u32(stg) + lane * 64;
-    const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
-    const bool has_aux = p.epilogue == B200_EPI_BIAS_RESIDUAL || p.epilogue == B200_EPI_DGELU;
+    constexpr uint32_t kRowBytes = RC * 2;                     // 64 (64B swizzle) or 128 (128B swizzle)
+    constexpr uint32_t kStgBytes = 32 * kRowBytes;
+    uint8_t* stg = smem + L::kStagingOffset + ew * kStgBytes;
+    const uint32_t stg_row = smem_u32(stg) + lane * kRowBytes;
+    const uint32_t sw = RC == 32 ? static_cast<uint32_t>((lane >> 1) & 3) : static_cast<uint32_t>(lane & 7);
+    const bool dual = p.out2 != nullptr;   // training: out2 <- pre-activation / un-scaled branch, out <- final value
+    // residual / pre-activation tile fetched by TMA into the staging tile (the dual residual mode reads it later)
+    const bool has_aux = (p.epilogue == B200_EPI_BIAS_RESIDUAL && !dual) || p.epilogue == B200_EPI_DGELU;
     const bool reduce_out = p.out_f32 && (p.accumulate || p.split_k > 1);
-    const bool dual = p.out2 != nullptr;   // training fc1: out2 <- pre-activation, out <- GELU(pre-activation)
-    const int round_cols = p.out_f32 ? 16 : 32;   // 64-byte rows of the staging tile
+    const int round_cols = p.out_f32 ? RC / 2 : RC;     // output columns per staging tile
+    const int sub_cols = p.out_f32 ? 16 : 32;           // output columns per 64-byte span (one tcgen05.ld)
     uint32_t aux_phase = 0;
     int as = 0;
     uint32_t aphase = 0;
@@ -328,7 +339,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
         if (has_aux && lane == 0) {
-          mbar_arrive_expect_tx(&aux_bar[ew], 2048);
+          mbar_arrive_expect_tx(&aux_bar[ew], kStgBytes);
           tma_load_2d(stg, &tmap_aux, &aux_bar[ew], col0, row0);
         }
         if (!waited) {
@@ -341,86 +352,88 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             ++ntiles;
           }
         }
-        uint4 aq[4] = {};   // residual tile of this round, kept when the branch output is stored first (out2)
-        if (p.out_f32) {
-          // fp32 output (weight gradients): 16 columns = 4 chunks of 4 floats
-          uint32_t r[16];
-          tmem_ld_x16(taddr0 + rc, r);
-          tmem_ld_wait_x16(r);
+        bool aux_waited = false;
+#pragma unroll 1
+        for (int sub = 0; sub < round_cols; sub += sub_cols) {
+          const uint32_t cb = static_cast<uint32_t>(sub / sub_cols) * 4;   // first 16-byte chunk of this 64-byte span
+          if (p.out_f32) {
+            // fp32 output (weight gradients): 16 columns = 4 chunks of 4 floats
+            uint32_t r[16];
+            tmem_ld_x16(taddr0 + rc + sub, r);
+            tmem_ld_wait_x16(r);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 4;
-            float v0 = __uint_as_float(r[g * 4 + 0]), v1 = __uint_as_float(r[g * 4 + 1]);
-            float v2 = __uint_as_float(r[g * 4 + 2]), v3 = __uint_as_float(r[g * 4 + 3]);
-            if (p.bias != nullptr && col < p.N) {
-              if (p.bias_f32) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + col));
-                v0 += b4.x; v1 += b4.y; v2 += b4.z; v3 += b4.w;
-              } else {
-                const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col));
-                v0 += bf16_lo(b2.x); v1 += bf16_hi(b2.x); v2 += bf16_lo(b2.y); v3 += bf16_hi(b2.y);
-              }
-            }
-            const uint32_t addr = stg_row + ((static_cast<uint32_t>(g) ^ sw) << 4);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
-          }
-        } else {
-          uint32_t r[32];
-          tmem_ld_x32(taddr0 + rc, r);
-          tmem_ld_wait_x32(r);
-          if (has_aux) {
-            mbar_wait(&aux_bar[ew], aux_phase);
-            aux_phase ^= 1;
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            const uint32_t addr = stg_row + ((static_cast<uint32_t>(g) ^ sw) << 4);
-            f32x2 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = pk(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
-            if (col < p.N) {
-              if (p.bias != nullptr) {
-                f32x2 bv[4];
-                load8_param2(p.bias, p.bias_f32, col, bv);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = add2(v[j], bv[j]);
-              }
-              if (p.epilogue == B200_EPI_BIAS_GELU && !dual) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
-              } else if (has_aux) {
-                uint4 q;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
-                const f32x2 av[4] = {bf16x2_to_f32x2(q.x), bf16x2_to_f32x2(q.y), bf16x2_to_f32x2(q.z), bf16x2_to_f32x2(q.w)};
-                aq[g] = q;
-                if (p.epilogue == B200_EPI_BIAS_RESIDUAL) {
-                  if (dual) {
-                    // training with LayerScale / DropPath: the un-scaled branch output goes to out2 first
-                  } else if (p.gamma != nullptr) {
-                    f32x2 gv[4];
-                    load8_param2(p.gamma, p.gamma_f32, col, gv);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], mul2(gv[j], rs2), av[j]);
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], rs2, av[j]);
-                  }
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + sub + g * 4;
+              float v0 = __uint_as_float(r[g * 4 + 0]), v1 = __uint_as_float(r[g * 4 + 1]);
+              float v2 = __uint_as_float(r[g * 4 + 2]), v3 = __uint_as_float(r[g * 4 + 3]);
+              if (p.bias != nullptr && col < p.N) {
+                if (p.bias_f32) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + col));
+                  v0 += b4.x; v1 += b4.y; v2 += b4.z; v3 += b4.w;
                 } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], dgelu_erf2(av[j]));
+                  const uint2 b2 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col));
+                  v0 += bf16_lo(b2.x); v1 += bf16_hi(b2.x); v2 += bf16_lo(b2.y); v3 += bf16_hi(b2.y);
                 }
               }
+              const uint32_t addr = stg_row + (((cb + static_cast<uint32_t>(g)) ^ sw) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
             }
-            uint32_t o[4];
+          } else {
+            uint32_t r[32];
+            tmem_ld_x32(taddr0 + rc + sub, r);
+            tmem_ld_wait_x32(r);
+            if (has_aux && !aux_waited) {
+              mbar_wait(&aux_bar[ew], aux_phase);
+              aux_phase ^= 1;
+              aux_waited = true;
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float lo, hi;
-              upk(v[j], lo, hi);
-              o[j] = pack_bf16(lo, hi);
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + sub + g * 8;
+              const uint32_t addr = stg_row + (((cb + static_cast<uint32_t>(g)) ^ sw) << 4);
+              f32x2 v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = pk(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
+              if (col < p.N) {
+                if (p.bias != nullptr) {
+                  f32x2 bv[4];
+                  load8_param2(p.bias, p.bias_f32, col, bv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[j] = add2(v[j], bv[j]);
+                }
+                if (p.epilogue == B200_EPI_BIAS_GELU && !dual) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
+                } else if (has_aux && !dual) {
+                  uint4 q;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+                  const f32x2 av[4] = {bf16x2_to_f32x2(q.x), bf16x2_to_f32x2(q.y), bf16x2_to_f32x2(q.z), bf16x2_to_f32x2(q.w)};
+                  if (p.epilogue == B200_EPI_BIAS_RESIDUAL) {
+                    if (p.gamma != nullptr) {
+                      f32x2 gv[4];
+                      load8_param2(p.gamma, p.gamma_f32, col, gv);
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], mul2(gv[j], rs2), av[j]);
+                    } else {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], rs2, av[j]);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], dgelu_erf2(av[j]));
+                  }
+                }
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                upk(v[j], lo, hi);
+                o[j] = pack_bf16(lo, hi);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                           : "memory");
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
-                         : "memory");
           }
         }
         if (rc + round_cols >= kColsPerWarp) {  // last TMEM read of this tile: hand the accumulator back
@@ -431,8 +444,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (dual) {
-          // the staging tile holds the bf16 pre-activation: store it to out2, then apply GELU to exactly those
-          // bf16 values (what the backward's GELU' will see) in place and store the result to out
+          // the staging tile holds the bf16 pre-activation (GELU) / un-scaled branch output (residual): store it to
+          // out2, then turn exactly those bf16 values (what the backward will see) into the final output in place
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -443,8 +456,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tma_store_wait_read<0>();
           }
           __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          const bool row_ok = row0 + lane < p.M;
+#pragma unroll 1
+          for (int j = 0; j < RC / 8; ++j) {
             const uint32_t addr = stg_row + ((static_cast<uint32_t>(j) ^ sw) << 4);
             uint4 q;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
@@ -458,15 +472,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 o[i] = pack_bf16(lo, hi);
               }
             } else {
-              // residual epilogue: out = aux + row_scale * gamma * branch, on the bf16 branch values just stored
-              const uint32_t aw[4] = {aq[j].x, aq[j].y, aq[j].z, aq[j].w};
-              f32x2 gv[4] = {rs2, rs2, rs2, rs2};
+              // residual epilogue: out = aux + row_scale * gamma * branch.  The residual row segment comes straight
+              // from global memory here (16 bytes per lane and step, every 32-byte sector fully used over two steps).
               const int col = col0 + j * 8;
-              if (p.gamma != nullptr && col < p.N) {
-                load8_param2(p.gamma, p.gamma_f32, col, gv);
+              uint4 a4 = make_uint4(0u, 0u, 0u, 0u);
+              f32x2 gv[4] = {rs2, rs2, rs2, rs2};
+              if (col < p.N) {
+                if (row_ok) a4 = __ldg(reinterpret_cast<const uint4*>(p.aux + static_cast<long long>(row0 + lane) * p.ldaux + col));
+                if (p.gamma != nullptr) {
+                  load8_param2(p.gamma, p.gamma_f32, col, gv);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gv[i] = mul2(gv[i], rs2);
+                  for (int i = 0; i < 4; ++i) gv[i] = mul2(gv[i], rs2);
+                }
               }
+              const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float lo, hi;
@@ -502,9 +521,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 static unsigned long long* g_gemm_trace = nullptr;
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2 = false>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2 = false, int RC = 32>
 static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES, CTA2>;
+  using L = GemmSmem<BN, STAGES, CTA2, RC>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
   constexpr int kBRows = CTA2 ? BN / 2 : BN;   // B rows one CTA loads per k-block
   CUtensorMap ta, tb;
   {
@@ -524,26 +544,27 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   }
   CUtensorMap tout, taux, tout2;
   {
-    // out / aux: dims {N, M}; box = one 64-byte-wide, 32-row staging tile (64B swizzle)
+    // out / aux: dims {N, M}; box = one 32-row staging tile with rows of 2*RC bytes (64B / 128B swizzle)
     const bool of32 = d.out_dtype == B200_DTYPE_F32;
+    constexpr int kSwz = RC == 32 ? 64 : 128;
     uint64_t dims[2] = {static_cast<uint64_t>(d.N), static_cast<uint64_t>(d.M)};
     uint64_t strides[1] = {static_cast<uint64_t>(d.ldo) * (of32 ? 4 : 2)};
-    uint32_t box[2] = {of32 ? 16u : 32u, 32u};
-    int rc = of32 ? encode_tmap_f32(&tout, d.out, 2, dims, strides, box, 64)
-                  : encode_tmap_bf16(&tout, d.out, 2, dims, strides, box, 64);
+    uint32_t box[2] = {of32 ? static_cast<uint32_t>(RC / 2) : static_cast<uint32_t>(RC), 32u};
+    int rc = of32 ? encode_tmap_f32(&tout, d.out, 2, dims, strides, box, kSwz)
+                  : encode_tmap_bf16(&tout, d.out, 2, dims, strides, box, kSwz);
     if (rc) return rc;
     if (d.aux != nullptr) {
       uint64_t astr[1] = {static_cast<uint64_t>(d.ldaux) * 2};
-      uint32_t abox[2] = {32u, 32u};
-      rc = encode_tmap_bf16(&taux, d.aux, 2, dims, astr, abox, 64);
+      uint32_t abox[2] = {static_cast<uint32_t>(RC), 32u};
+      rc = encode_tmap_bf16(&taux, d.aux, 2, dims, astr, abox, kSwz);
       if (rc) return rc;
     } else {
       taux = tout;
     }
     if (d.out2 != nullptr) {
       uint64_t ostr[1] = {static_cast<uint64_t>(d.ldo2) * 2};
-      uint32_t obox[2] = {32u, 32u};
-      rc = encode_tmap_bf16(&tout2, d.out2, 2, dims, ostr, obox, 64);
+      uint32_t obox[2] = {static_cast<uint32_t>(RC), 32u};
+      rc = encode_tmap_bf16(&tout2, d.out2, 2, dims, ostr, obox, kSwz);
       if (rc) return rc;
     } else {
       tout2 = tout;
@@ -566,7 +587,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.accumulate = d.accumulate;
   p.trace = g_gemm_trace;
 
-  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC>;
   static bool attr_set = false;  // idempotent; a benign race sets the same value twice
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -612,8 +633,11 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
 
 using namespace b200;
 
-extern "C" void b200_gemm_set_trace(void* device_buf) {
-  g_gemm_trace = reinterpret_cast<unsigned long long*>(device_buf);
+namespace b200 { extern long long* g_attn_fwd_trace; }
+
+extern "C" void b200_set_trace(int32_t kernel, void* device_buf) {
+  if (kernel == 0) g_gemm_trace = reinterpret_cast<unsigned long long*>(device_buf);
+  else if (kernel == 1) b200::g_attn_fwd_trace = reinterpret_cast<long long*>(device_buf);
 }
 
 extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
@@ -658,11 +682,22 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   const bool wide = d.N > 128;
   // CTA pairs (256 x 256 tiles, cta_group::2) once there are enough 256-row tile pairs to fill the GPU
   static const int pair_mode = [] { const char* e = getenv("B200_GEMM_2CTA"); return e ? atoi(e) : 1; }();
-  if (wide && pair_mode && d.M >= 256) {
+  // B200_GEMM_2CTA: 0 = single CTAs; 2 = pairs, 32-column epilogue rounds, 6-stage ring; 3 = pairs, 64-column rounds,
+  //                 5-stage ring; 1 (default) = pairs, round width chosen per epilogue
+  // default (1): the transcendental epilogues (GELU, GELU') take the 64-column rounds, whose single TMA store per tile
+  // keeps 16 busy epilogue warps off the store-completion wait; bias / residual epilogues keep the sixth ring stage
+  const bool heavy_epi = d.epilogue == B200_EPI_BIAS_GELU || d.epilogue == B200_EPI_DGELU;
+  if (wide && (pair_mode == 2 || (pair_mode == 1 && !heavy_epi)) && d.M >= 256) {
     if (!d.a_mn && !d.b_mn) return launch_gemm<256, 6, false, false, true>(d, stream);
     if (!d.a_mn && d.b_mn) return launch_gemm<256, 6, false, true, true>(d, stream);
     if (d.a_mn && d.b_mn) return launch_gemm<256, 6, true, true, true>(d, stream);
     return launch_gemm<256, 6, true, false, true>(d, stream);
+  }
+  if (wide && pair_mode && d.M >= 256) {
+    if (!d.a_mn && !d.b_mn) return launch_gemm<256, 5, false, false, true, 64>(d, stream);
+    if (!d.a_mn && d.b_mn) return launch_gemm<256, 5, false, true, true, 64>(d, stream);
+    if (d.a_mn && d.b_mn) return launch_gemm<256, 5, true, true, true, 64>(d, stream);
+    return launch_gemm<256, 5, true, false, true, 64>(d, stream);
   }
   if (wide) {
     if (!d.a_mn && !d.b_mn) return launch_gemm<256, 4, false, false>(d, stream);

@@ -1,5 +1,5 @@
 """Where does a GEMM launch spend its time?  Per-CTA %globaltimer stamps from the b200_gemm debug hook
-(include/b200timm.h: b200_gemm_set_trace), summarised as min / median / max over the 148 CTAs, relative to the
+(include/b200timm.h: b200_set_trace), summarised as min / median / max over the 148 CTAs, relative to the
 earliest CTA entry.     python tools/gemm_trace.py"""
 import os
 import sys
@@ -35,9 +35,9 @@ def trace(M, N, K, epilogue=0, aux=False):
     torch.cuda.synchronize()
     for _ in range(10):
         ops.linear_fwd(a, w, bias, epilogue=epilogue, aux=res)
-    lib.b200_gemm_set_trace(buf.data_ptr())
+    lib.b200_set_trace(0, buf.data_ptr())
     out = ops.linear_fwd(a, w, bias, epilogue=epilogue, aux=res)
-    lib.b200_gemm_set_trace(None)
+    lib.b200_set_trace(0, None)
     torch.cuda.synchronize()
     ref = torch.nn.functional.linear(a, w, bias)
     if epilogue == ops.EPI_BIAS_GELU:
