@@ -28,7 +28,8 @@ constexpr int kOffDS = kOffP + kPB;              // dS^T: 16 chunks (the dQ MMA 
 constexpr int kDSB = 16 * 2048;
 constexpr int kOffLse = kOffDS + kDSB;
 constexpr int kOffDelta = kOffLse + 2 * kQH * 4;
-constexpr int kOffBar = kOffDelta + 2 * kQH * 4;
+constexpr int kOffOut = (kOffDelta + 2 * kQH * 4 + 1023) / 1024 * 1024;   // 8 warps x (32 rows x 128 B) output staging
+constexpr int kOffBar = kOffOut + 8 * 4096;
 constexpr int kSmemTotal = kOffBar + 64 + 1024;
 constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ0 = 384, kColDQ1 = 448;
 constexpr int kComputeThreads = 256;
@@ -43,21 +44,36 @@ struct AttnBwd2Params {
   float scale, scale_log2e;
 };
 
-__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, uint32_t taddr, bool ok) {
+// One warp's 32 accumulator rows x 64 columns: TMEM -> bf16 -> 128B-swizzled staging tile -> one TMA store into
+// dqkv[b, row0 .. row0+31 (clipped at N by the 3-D map), col0 .. col0+63].  (Per-lane 16-byte global stores of 32
+// different rows cost one LSU transaction each -- ~2000 cycles per 128 x 64 tile; the TMA store is one instruction.)
+__device__ __forceinline__ void store_tile64(uint8_t* stg, uint32_t taddr, const CUtensorMap* map, int col0, int row0, int b,
+                                             int lane, bool any_row) {
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+  const uint32_t srow = smem_u32(stg) + lane * 128;
+  const uint32_t sw = static_cast<uint32_t>(lane & 7);
 #pragma unroll
   for (int c = 0; c < kHd; c += 32) {
     uint32_t r[32];
     tmem_ld_x32(taddr + c, r);
     tmem_ld_wait_x32(r);
-    if (ok) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        reinterpret_cast<uint4*>(dst + c)[g] =
-            make_uint4(pack_bf16(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1])),
-                       pack_bf16(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
-                       pack_bf16(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5])),
-                       pack_bf16(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t addr = srow + ((static_cast<uint32_t>(c / 8 + g) ^ sw) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                   "r"(pack_bf16(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]))),
+                   "r"(pack_bf16(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]))),
+                   "r"(pack_bf16(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]))),
+                   "r"(pack_bf16(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])))
+                   : "memory");
     }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0 && any_row) {
+    tma_store_3d(map, stg, col0, row0, b);
+    tma_store_commit();
   }
 }
 
@@ -82,6 +98,7 @@ __device__ __forceinline__ void pds8(const uint32_t* s, const uint32_t* dp, cons
 
 __global__ void __launch_bounds__(kComputeThreads + 32, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const __grid_constant__ CUtensorMap tm_out32, const __grid_constant__ CUtensorMap tm_out16,
                  const AttnBwd2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,6 +127,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_out32);
+    tma_prefetch_desc(&tm_out16);
     mbar_init(bar_ld, 1);
     mbar_init(bar_sd, 1);
     mbar_init(bar_p, kComputeThreads);
@@ -198,6 +217,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const f32x2 sc2 = splat(p.scale_log2e), scale2 = splat(p.scale);
     const long long tok_stride = 3LL * H * kHd;
+    uint8_t* ostg = smem + kOffOut + warp * 4096;
+    const int wrow = (warp & 3) * 32;                 // first accumulator row of this warp
     for (int step = 0; step < num_steps; ++step) {
       const int kt = step >> 1, qh = step & 1;
       const int key = kt * 128 + rowt;
@@ -206,9 +227,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       tc_fence_after();
       if (qh == 0 && kt > 0) {
         // dV / dK of the previous key tile are complete (their MMAs were queued ahead of this step's S^T / dP^T)
-        const int pkey = (kt - 1) * 128 + rowt;
-        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * N + pkey) * tok_stride + ((wg == 0 ? 2 : 1) * H + h) * kHd;
-        store_row64(dst, tmem_row + (wg == 0 ? kColDV : kColDK), pkey < N);
+        const int prow0 = (kt - 1) * 128 + wrow;
+        store_tile64(ostg, tmem_row + (wg == 0 ? kColDV : kColDK), &tm_out32, ((wg == 0 ? 2 : 1) * H + h) * kHd, prow0, b,
+                     lane, prow0 < N);
       }
       const int c0 = wg * 56;                        // first query column (within the half) of this warpgroup
       const float* l2 = sLse + qh * kQH + c0;
@@ -252,15 +273,17 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     mbar_wait(bar_fin, 0);
     tc_fence_after();
     {
-      const int pkey = (num_kt - 1) * 128 + rowt;
-      __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * N + pkey) * tok_stride + ((wg == 0 ? 2 : 1) * H + h) * kHd;
-      store_row64(dst, tmem_row + (wg == 0 ? kColDV : kColDK), pkey < N);
+      const int prow0 = (num_kt - 1) * 128 + wrow;
+      store_tile64(ostg, tmem_row + (wg == 0 ? kColDV : kColDK), &tm_out32, ((wg == 0 ? 2 : 1) * H + h) * kHd, prow0, b, lane,
+                   prow0 < N);
     }
     {
-      const int q = wg * kQH + rowt;                 // warpgroup 0 -> query half 0, warpgroup 1 -> half 1
-      __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * N + q) * tok_stride + h * kHd;
-      store_row64(dst, tmem_row + (wg == 0 ? kColDQ0 : kColDQ1), rowt < kQH && q < N);
+      // warpgroup 0 -> query half 0, warpgroup 1 -> half 1; a half has 112 rows, so the last warp stores 16 rows only
+      const int q0 = wg * kQH + wrow;
+      store_tile64(ostg, tmem_row + (wg == 0 ? kColDQ0 : kColDQ1), wrow + 32 <= kQH ? &tm_out32 : &tm_out16, h * kHd, q0, b,
+                   lane, q0 < N);
     }
+    if (lane == 0) tma_store_wait<0>();
     // keys beyond kv_len (padding keys of a NaFlex batch) never entered a tile: their dK / dV are zero
     for (int key = num_kt * 128 + tid; key < N; key += kComputeThreads) {
       for (int which = 1; which <= 2; ++which) {
@@ -295,6 +318,16 @@ int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const 
     int rc = encode_tmap_bf16(&tdo, dout, 2, dims, strides, box, true);
     if (rc) return rc;
   }
+  CUtensorMap to32, to16;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(3) * H * kHd, static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(3) * H * kHd * 2, static_cast<uint64_t>(N) * 3 * H * kHd * 2};
+    uint32_t b32[3] = {kHd, 32, 1}, b16[3] = {kHd, 16, 1};
+    int rc = encode_tmap_bf16(&to32, dqkv, 3, dims, strides, b32, 128);
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&to16, dqkv, 3, dims, strides, b16, 128);
+    if (rc) return rc;
+  }
   AttnBwd2Params p;
   p.lse = lse; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.kv_len = kv_len;
   p.B = B; p.N = N; p.H = H; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
@@ -303,7 +336,7 @@ int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const 
     B200_CUDA_OK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
-  attn_bwd2_kernel<<<dim3(H, B), kComputeThreads + 32, kSmemTotal, st>>>(tq, tdo, p);
+  attn_bwd2_kernel<<<dim3(H, B), kComputeThreads + 32, kSmemTotal, st>>>(tq, tdo, to32, to16, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

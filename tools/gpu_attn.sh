@@ -1,7 +1,5 @@
 #!/bin/bash
 cd /root/repo; mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q --no-header -p no:cacheprovider -k "attention" 2>&1 | tail -3
-for d in 0 1500 2500 3500; do
-  echo "== stagger $d"; B200_ATTN_STAGGER=$d timeout 300 python tools/microbench.py 2>&1 | grep attention | cut -c1-140
-done
-timeout 300 python tools/attn_trace.py 2>&1 | grep -E "launch|softmax|total"
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_train.py tests/test_gpu_naflex.py -m gpu -x -q --no-header -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python tools/train_detail.py 2>&1 | head -12
+timeout 600 python bench.py --mode train --steps 10 --warmup 3 2>&1 | tail -1 | cut -c80-220
