@@ -202,6 +202,113 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   }
 }
 
+// bf16 activations (the training path): ONE pass.  All of a row's x / dy / residual-gradient vectors are requested up
+// front as raw 16-byte words and stay packed in registers (9 loads in flight per lane, 16 warps per SM ~ 70 KB in
+// flight per SM -- enough to cover HBM latency), the statistics and the dx formula both run from those registers.
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+  v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32, VPL <= 3 ? 2 : 1)
+layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                          const void* __restrict__ w, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
+                          __nv_bfloat16* __restrict__ dx, float* __restrict__ ws, long long rows, int cols,
+                          int param_f32) {
+  extern __shared__ float red[];  // [kLnWarps][2*cols]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
+  const long long warp_stride = static_cast<long long>(gridDim.x) * kLnWarps;
+  const int nvec = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  float dw_acc[VPL][8], db_acc[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dw_acc[i][j] = 0.f; db_acc[i][j] = 0.f; }
+
+  for (long long row = warp_global; row < rows; row += warp_stride) {
+    uint4 xr[VPL], dyr[VPL], rr[VPL];
+    const long long base = row * cols;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        xr[i] = *reinterpret_cast<const uint4*>(x + base + vec * 8);
+        dyr[i] = *reinterpret_cast<const uint4*>(dy + base + vec * 8);
+        if (dres != nullptr) rr[i] = *reinterpret_cast<const uint4*>(dres + base + vec * 8);
+      }
+    }
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        float xv[8], dyv[8], wv[8];
+        unpack8(xr[i], xv);
+        unpack8(dyr[i], dyv);
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          dw_acc[i][j] = fmaf(dyv[j], xh, dw_acc[i][j]);
+          db_acc[i][j] += dyv[j];
+        }
+      }
+    }
+    const float m1 = warp_sum(s1) * inv_n;
+    const float m2 = warp_sum(s2) * inv_n;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        float xv[8], dyv[8], wv[8], o[8];
+        unpack8(xr[i], xv);
+        unpack8(dyr[i], dyv);
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
+          o[j] = rstd * (g - m1 - xh * m2);
+        }
+        if (dres != nullptr) {   // gradient arriving through the residual branch around this LayerNorm
+          float rv[8];
+          unpack8(rr[i], rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
+        store8<false>(dx, base + vec * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + i * 32;
+    if (vec < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red[warp * 2 * cols + vec * 8 + j] = dw_acc[i][j];
+        red[warp * 2 * cols + cols + vec * 8 + j] = db_acc[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnWarps; ++k) s += red[k * 2 * cols + c];
+    ws[static_cast<long long>(blockIdx.x) * 2 * cols + c] = s;
+  }
+}
+
 // Second stage: out[c] = sum_r ws[r][c] over the per-CTA partial rows.  blockDim = (32 columns, 8 row slices):
 // each warp streams its row slice with coalesced 128-byte reads, then the 8 slices are combined through smem, so
 // the reduction is a handful of independent loads per thread instead of one serial chain over all rows.
@@ -265,11 +372,16 @@ static int launch_bwd(const void* dy, const void* x, const void* w, const float*
     if (xf32 && dyf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, true, true>));
     else if (xf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, true, false>));
     else if (dyf32) B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, false, true>));
+    else if (VPL <= 4) B200_CUDA_OK(set(layernorm_bwd_bf16_kernel<VPL>));
     else B200_CUDA_OK(set(layernorm_bwd_kernel<VPL, false, false>));
   }
   if (xf32 && dyf32) layernorm_bwd_kernel<VPL, true, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
   else if (xf32) layernorm_bwd_kernel<VPL, true, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
   else if (dyf32) layernorm_bwd_kernel<VPL, false, true><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
+  else if (VPL <= 4)   // wider rows would not fit their packed vectors + accumulators in 128 registers
+    layernorm_bwd_bf16_kernel<VPL><<<grid, threads, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), w, mean, rstd,
+        reinterpret_cast<const __nv_bfloat16*>(dres), reinterpret_cast<__nv_bfloat16*>(dx), ws, rows, cols, pf32);
   else layernorm_bwd_kernel<VPL, false, false><<<grid, threads, smem, st>>>(dy, x, w, mean, rstd, dres, dx, ws, rows, cols, pf32);
   return B200_OK;
 }
