@@ -13,20 +13,27 @@ from b200timm import _lib, ops  # noqa: E402
 NAMES = ["entry", "setup done", "first operands", "first acc ready", "last acc ready", "stores drained", "exit"]
 
 
-def trace(M, N, K, epilogue=0, aux=False):
+def trace(M, N, K, epilogue=0, aux=False, dgrad=False):
+    """dgrad=True: out[M,N] = a[M,K] @ w[K,N] with w consumed MN-major (the backward-data layout)."""
     lib = _lib.load()
     a = torch.randn(M, K, device="cuda").bfloat16()
-    w = torch.randn(N, K, device="cuda").bfloat16()
-    bias = torch.randn(N, device="cuda").bfloat16()
+    w = (torch.randn(K, N, device="cuda") if dgrad else torch.randn(N, K, device="cuda")).bfloat16()
+    bias = None if dgrad else torch.randn(N, device="cuda").bfloat16()
     res = torch.randn(M, N, device="cuda").bfloat16() if aux else None
+
+    def run():
+        if dgrad:
+            return ops.linear_dgrad(a, w, epilogue=epilogue, aux=res)
+        return ops.linear_fwd(a, w, bias, epilogue=epilogue, aux=res)
+
     buf = torch.zeros(148 * 12, dtype=torch.int64, device="cuda")
     for _ in range(3):
-        ops.linear_fwd(a, w, bias, epilogue=epilogue, aux=res)
+        run()
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(20):
-        ops.linear_fwd(a, w, bias, epilogue=epilogue, aux=res)
+        run()
     t1.record()
     torch.cuda.synchronize()
     ev_us = t0.elapsed_time(t1) / 20 * 1e3
@@ -34,13 +41,16 @@ def trace(M, N, K, epilogue=0, aux=False):
     buf.zero_()
     torch.cuda.synchronize()
     for _ in range(10):
-        ops.linear_fwd(a, w, bias, epilogue=epilogue, aux=res)
+        run()
     lib.b200_set_trace(0, buf.data_ptr())
-    out = ops.linear_fwd(a, w, bias, epilogue=epilogue, aux=res)
+    out = run()
     lib.b200_set_trace(0, None)
     torch.cuda.synchronize()
-    ref = torch.nn.functional.linear(a, w, bias)
-    if epilogue == ops.EPI_BIAS_GELU:
+    ref = (a.float() @ w.float()).bfloat16() if dgrad else torch.nn.functional.linear(a, w, bias)
+    if epilogue == ops.EPI_DGELU:
+        x = res.float()
+        ref = (ref.float() * (0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327)).bfloat16()
+    elif epilogue == ops.EPI_BIAS_GELU:
         ref = torch.nn.functional.gelu(ref.float()).bfloat16()
     elif aux:
         ref = ref + res
@@ -68,6 +78,11 @@ def trace(M, N, K, epilogue=0, aux=False):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "heavy":
+        trace(50432, 3072, 768, dgrad=True)
+        trace(50432, 3072, 768, epilogue=ops.EPI_DGELU, aux=True, dgrad=True)
+        trace(50432, 3072, 768, epilogue=ops.EPI_BIAS_GELU)
+        sys.exit(0)
     trace(50432, 768, 768)
     trace(50432, 768, 768, epilogue=ops.EPI_BIAS_RESIDUAL, aux=True)
     trace(50432, 2304, 768)
