@@ -7,6 +7,7 @@
 // The depthwise conv is FMA-bound in fp32 (49 MACs per output element, 0.23 GMAC/img for ConvNeXt-B), not HBM-bound;
 // each thread keeps a strip of TW output pixels x 8 channels in registers and slides along the row so every loaded
 // input vector feeds up to 7 taps; weights are consumed pre-transposed ([k*k][C]) so a tap is one 16-byte load.
+#include <cstdlib>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -260,6 +261,10 @@ static int launch_dwconv(const void* x, const void* wt, const void* bias, const 
 
 }  // namespace b200
 
+namespace b200 {
+int launch_dwconv_tma(const void* x, const void* wt, const void* bias, const void* residual, void* y, int B, int H, int W,
+                      int C, int ksize, int bias_f32, cudaStream_t st);
+}
 using namespace b200;
 
 extern "C" int b200_dwconv_nhwc(const void* x, const void* weight_t, const void* bias, const void* residual, void* y,
@@ -269,6 +274,14 @@ extern "C" int b200_dwconv_nhwc(const void* x, const void* weight_t, const void*
   B200_CHECK_ARG(x && weight_t && y, "b200_dwconv_nhwc: null pointer");
   B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "b200_dwconv_nhwc: bad shape (C %% 8 == 0)");
   const int bf = bias_dtype == B200_DTYPE_F32;
+  {
+    // C %% 64 == 0, 7 x 7: the TMA-staged kernel (dwconv_tma.cu); B200_DWCONV_DIRECT=1 keeps the direct-load kernel
+    static const bool direct = [] { const char* e = getenv("B200_DWCONV_DIRECT"); return e != nullptr && e[0] == '1'; }();
+    if (!direct && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      const int rc = launch_dwconv_tma(x, weight_t, bias, residual, y, B, H, W, C, ksize, bf, st);
+      if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+  }
   switch (ksize) {
     case 7: return launch_dwconv<7>(x, weight_t, bias, residual, y, B, H, W, C, bf, st);
     case 5: return launch_dwconv<5>(x, weight_t, bias, residual, y, B, H, W, C, bf, st);
