@@ -264,6 +264,8 @@ static int launch_dwconv(const void* x, const void* wt, const void* bias, const 
 namespace b200 {
 int launch_dwconv_tma(const void* x, const void* wt, const void* bias, const void* residual, void* y, int B, int H, int W,
                       int C, int ksize, int bias_f32, cudaStream_t st);
+int launch_dwconv_wgrad_tma(const void* x, const void* dy, float* dwt, int B, int H, int W, int C, int ksize,
+                            cudaStream_t st);
 }
 using namespace b200;
 
@@ -311,6 +313,13 @@ extern "C" int b200_dwconv_nhwc_wgrad(const void* x, const void* dy, float* dwei
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(x && dy && dweight_t, "b200_dwconv_nhwc_wgrad: null pointer");
   B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "b200_dwconv_nhwc_wgrad: bad shape (C %% 8 == 0)");
+  {
+    static const bool direct = [] { const char* e = getenv("B200_DWCONV_DIRECT"); return e != nullptr && e[0] == '1'; }();
+    if (!direct && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0) {
+      const int rc = launch_dwconv_wgrad_tma(x, dy, dweight_t, B, H, W, C, ksize, st);
+      if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+  }
   switch (ksize) {
     case 7: return launch_dwconv_wgrad<7>(x, dy, dweight_t, B, H, W, C, st);
     case 5: return launch_dwconv_wgrad<5>(x, dy, dweight_t, B, H, W, C, st);

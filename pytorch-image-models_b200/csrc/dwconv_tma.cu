@@ -255,4 +255,206 @@ int launch_dwconv_tma(const void* x, const void* wt, const void* bias, const voi
   return launch_dwconv_tma_ks<7>(x, wt, bias, residual, y, B, H, W, C, bias_f32, st);
 }
 
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dw_t[ky][kx][c] += sum_{b,oy,ox} dy[b,oy,ox,c] * x[b, oy+ky-3, ox+kx-3, c]   (fp32, atomically accumulated).
+// Same work items as the forward kernel; per item two TMA loads (the 20 x 20 x-tile with its zero halo and the
+// 14 x 14 dy-tile, whose part past the image edge also arrives as zeros -- no border predicates).  A thread owns
+// (8 channels, one kernel row ky, two or three output rows of the tile) and keeps the 7 x 8 partial sums of its kernel row in
+// registers across ALL items of a channel block: per output row it reads 14 dy vectors and 20 x vectors from shared
+// memory and issues 392 FFMA2 (a 7-wide sliding window of widened x vectors, fully unrolled so the window lives in
+// registers).  At a channel-block change the partials are combined through shared-memory atomics and leave as one
+// global fp32 atomic per weight and CTA.
+namespace {
+constexpr int kWgGroups = 6;                             // row groups: rows {0-2, 3-5, 6-7, 8-9, 10-11, 12-13}
+constexpr int kWgThreads = kWgGroups * 7 * (kCB / 8);    // 336 (KS = 7): 11 warps -> a 168-register budget, no spills
+}  // namespace
+
+struct DwWgSmem {
+  static constexpr int kXBytes = 20 * 20 * kCB * 2;      // 51200
+  static constexpr int kDyBytes = kTH * kTWt * kCB * 2;  // 25088
+  static constexpr int kStage = (kXBytes + kDyBytes + 1023) / 1024 * 1024;   // 76800
+  static constexpr int kAccOff = 2 * kStage;
+  static constexpr int kAccBytes = 49 * kCB * 4;
+  static constexpr int kBarOff = kAccOff + kAccBytes;
+  static constexpr int kTotal = kBarOff + 64 + 128;
+};
+
+struct DwWgParams {
+  float* dwt;   // [49][C] fp32
+  int B, H, W, C;
+  int tiles_y, tiles_x, cblocks;
+  long long num_items;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+dwconv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dy,
+                        const DwWgParams p) {
+  using L = DwWgSmem;
+  constexpr int KS = 7, PAD = 3, IW = 20;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* sacc = reinterpret_cast<float*>(smem + L::kAccOff);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* bar_empty = bar_full + 2;
+
+  const int tid = threadIdx.x;
+  const int cv = tid & 7;
+  const int ky = (tid >> 3) % KS;
+  const int grp = tid / (8 * KS);
+  const int row_begin = grp < 2 ? 3 * grp : 2 * grp + 2;     // first output row of this group
+  const int row_count = grp < 2 ? 3 : 2;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_dy);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], kWgThreads);
+    }
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 49 * kCB; i += kWgThreads) sacc[i] = 0.f;
+  __syncthreads();
+
+  const long long per_cblock = static_cast<long long>(p.B) * p.tiles_y * p.tiles_x;
+  auto decode = [&](long long item, int& cb, int& b, int& oy0, int& ox0) {
+    cb = static_cast<int>(item / per_cblock);
+    long long r = item - cb * per_cblock;
+    b = static_cast<int>(r / (p.tiles_y * p.tiles_x));
+    r -= static_cast<long long>(b) * (p.tiles_y * p.tiles_x);
+    const int t_y = static_cast<int>(r / p.tiles_x);
+    oy0 = t_y * kTH;
+    ox0 = static_cast<int>(r - static_cast<long long>(t_y) * p.tiles_x) * kTWt;
+  };
+  auto issue = [&](long long item, int buf) {
+    int cb, b, oy0, ox0;
+    decode(item, cb, b, oy0, ox0);
+    uint8_t* st = smem + buf * L::kStage;
+    mbar_arrive_expect_tx(&bar_full[buf], L::kXBytes + L::kDyBytes);
+    tma_load_4d(st, &tm_x, &bar_full[buf], cb * kCB, ox0 - PAD, oy0 - PAD, b);
+    tma_load_4d(st + L::kXBytes, &tm_dy, &bar_full[buf], cb * kCB, ox0, oy0, b);
+  };
+  // per-thread partial sums -> shared accumulator -> one global atomic per weight
+  f32x2 acc[KS][4];
+#define DW_CLEAR_ACC()                                   \
+  _Pragma("unroll") for (int kx_ = 0; kx_ < KS; ++kx_)   \
+      _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) acc[kx_][j_] = 0ull;
+#define DW_FLUSH(cb_)                                                                              \
+  {                                                                                                \
+    _Pragma("unroll") for (int kx_ = 0; kx_ < KS; ++kx_) {                                         \
+      float* dst_ = sacc + (ky * KS + kx_) * kCB + cv * 8;                                         \
+      _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) {                                           \
+        float lo_, hi_;                                                                            \
+        upk(acc[kx_][j_], lo_, hi_);                                                               \
+        atomicAdd(dst_ + 2 * j_, lo_);                                                             \
+        atomicAdd(dst_ + 2 * j_ + 1, hi_);                                                         \
+      }                                                                                            \
+    }                                                                                              \
+    __syncthreads();                                                                               \
+    for (int i_ = tid; i_ < 49 * kCB; i_ += kWgThreads) {                                          \
+      const int tap_ = i_ / kCB, c_ = i_ - tap_ * kCB;                                             \
+      atomicAdd(p.dwt + static_cast<long long>(tap_) * p.C + (cb_) * kCB + c_, sacc[i_]);          \
+      sacc[i_] = 0.f;                                                                              \
+    }                                                                                              \
+    __syncthreads();                                                                               \
+  }
+
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (tid == 0) {
+    if (first < p.num_items) issue(first, 0);
+    if (first + step < p.num_items) issue(first + step, 1);
+  }
+  DW_CLEAR_ACC();
+  int cur_cb = -1;
+  int it = 0;
+  for (long long item = first; item < p.num_items; item += step, ++it) {
+    const int buf = it & 1;
+    int cb, b, oy0, ox0;
+    decode(item, cb, b, oy0, ox0);
+    if (cb != cur_cb) {
+      if (cur_cb >= 0) {
+        DW_FLUSH(cur_cb);
+        DW_CLEAR_ACC();
+      }
+      cur_cb = cb;
+    }
+    mbar_wait(&bar_full[buf], (it >> 1) & 1);
+    const uint32_t xt = smem_u32(smem + buf * L::kStage);
+    const uint32_t dyt = xt + L::kXBytes;
+#pragma unroll 1
+    for (int rr = 0; rr < row_count; ++rr) {
+      const int orow = row_begin + rr;
+      const uint32_t xrow = xt + (((orow + ky) * IW) * kCB + cv * 8) * 2;
+      const uint32_t dyrow = dyt + ((orow * kTWt) * kCB + cv * 8) * 2;
+      f32x2 win[KS][4];   // widened x vectors at columns t .. t+6 of the input row
+#pragma unroll
+      for (int i = 0; i < KS - 1; ++i) {
+        const uint4 q = lds128(xrow + i * (kCB * 2));
+        win[i][0] = bf16x2_to_f32x2(q.x); win[i][1] = bf16x2_to_f32x2(q.y);
+        win[i][2] = bf16x2_to_f32x2(q.z); win[i][3] = bf16x2_to_f32x2(q.w);
+      }
+#pragma unroll 1
+      for (int t0 = 0; t0 < kTWt; t0 += KS)
+#pragma unroll
+      for (int tt = 0; tt < KS; ++tt) {
+        const int t = t0 + tt;      // t % KS == tt: the window slots below are compile-time indices
+        {
+          const uint4 q = lds128(xrow + (t + KS - 1) * (kCB * 2));
+          win[(tt + KS - 1) % KS][0] = bf16x2_to_f32x2(q.x); win[(tt + KS - 1) % KS][1] = bf16x2_to_f32x2(q.y);
+          win[(tt + KS - 1) % KS][2] = bf16x2_to_f32x2(q.z); win[(tt + KS - 1) % KS][3] = bf16x2_to_f32x2(q.w);
+        }
+        const uint4 d = lds128(dyrow + t * (kCB * 2));
+        const f32x2 d0 = bf16x2_to_f32x2(d.x), d1 = bf16x2_to_f32x2(d.y), d2 = bf16x2_to_f32x2(d.z), d3 = bf16x2_to_f32x2(d.w);
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          acc[kx][0] = fma2(d0, win[(tt + kx) % KS][0], acc[kx][0]);
+          acc[kx][1] = fma2(d1, win[(tt + kx) % KS][1], acc[kx][1]);
+          acc[kx][2] = fma2(d2, win[(tt + kx) % KS][2], acc[kx][2]);
+          acc[kx][3] = fma2(d3, win[(tt + kx) % KS][3], acc[kx][3]);
+        }
+      }
+    }
+    mbar_arrive(&bar_empty[buf]);
+    if (tid == 0 && item + 2 * step < p.num_items) {
+      mbar_wait(&bar_empty[buf], (it >> 1) & 1);
+      issue(item + 2 * step, buf);
+    }
+  }
+  if (cur_cb >= 0) DW_FLUSH(cur_cb);
+#undef DW_CLEAR_ACC
+#undef DW_FLUSH
+}
+
+// Returns B200_ERR_UNSUPPORTED when the shape is outside this kernel's cover (see launch_dwconv_tma).
+int launch_dwconv_wgrad_tma(const void* x, const void* dy, float* dwt, int B, int H, int W, int C, int ksize,
+                            cudaStream_t st) {
+  if (C % kCB != 0 || ksize != 7) return B200_ERR_UNSUPPORTED;
+  using L = DwWgSmem;
+  CUtensorMap tx, tdy;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2, static_cast<uint64_t>(H) * W * C * 2};
+    uint32_t bx[4] = {kCB, 20, 20, 1}, bd[4] = {kCB, kTWt, kTH, 1};
+    int rc = encode_tmap_bf16(&tx, x, 4, dims, strides, bx, 0);
+    if (rc) return rc;
+    rc = encode_tmap_bf16(&tdy, dy, 4, dims, strides, bd, 0);
+    if (rc) return rc;
+  }
+  DwWgParams p;
+  p.dwt = dwt; p.B = B; p.H = H; p.W = W; p.C = C;
+  p.tiles_y = (H + kTH - 1) / kTH; p.tiles_x = (W + kTWt - 1) / kTWt; p.cblocks = C / kCB;
+  p.num_items = static_cast<long long>(p.cblocks) * B * p.tiles_y * p.tiles_x;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(dwconv_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  long long grid = sm_count();
+  if (grid > p.num_items) grid = p.num_items;
+  dwconv_wgrad_tma_kernel<<<static_cast<int>(grid), kWgThreads, L::kTotal, st>>>(tx, tdy, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
 }  // namespace b200
