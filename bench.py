@@ -344,7 +344,7 @@ def main():
                     "note": "pinned bf16 host batch -> H2D on a copy stream (double buffered) -> forward (CUDA-graph replay "
                             "of the model's kernels) -> logits D2H, every step inside the timed region"},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel<256,4> (qkv/proj/fc1/fc2/head GEMMs)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (CTA pairs, 256x256 tiles; qkv/proj/fc1/fc2/head GEMMs)",
                          "achieved": round(gemm_tflops, 1), "peak": peak, "unit": "TFLOP/s",
                          "frac": round(gemm_tflops / peak, 4), **recorded_traffic(),
                          "launches_timed": gemm_n, "timing": "CUDA events around every GEMM launch over K eagerly launched steps",

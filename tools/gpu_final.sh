@@ -13,9 +13,13 @@ run bench_train 600 python bench.py --mode train --steps 10 --warmup 3
 run bench_ref 600 python bench.py --impl reference --steps 5 --warmup 1
 run microbench 600 python tools/microbench.py
 run convnext 300 python tools/bench_model.py convnext_base --detail
+run convnext_train 300 python tools/bench_model.py convnext_base --batch 128 --steps 10 --warmup 3 --train --detail
 run train_detail 300 python tools/train_detail.py
+run gemm_trace 300 python tools/gemm_trace.py
+run attn_trace 300 python tools/attn_trace.py
 KREG='regex:gemm_bf16|layernorm_|attn_|patchify|assemble_tokens'
 run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 356 -c 178 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph
 run ncu_gemm 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 150 -c 5 -o gpurun_out/prof_gemm python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph
 run ncu_attn 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd2 -s 36 -c 1 -o gpurun_out/prof_attn python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph
+run ncu_dwconv 600 ncu --set full --clock-control none --import-source on -k regex:dwconv_tma -s 12 -c 1 -o gpurun_out/prof_dwconv python tools/bench_model.py convnext_base --batch 256 --steps 1 --warmup 1
 cat gpurun_out/summary.txt
