@@ -42,6 +42,9 @@ extern "C" {
 #define B200_EPI_BIAS_GELU 1  /* out = gelu_erf(acc + bias)             timm/layers/mlp.py:48-49     */
 #define B200_EPI_BIAS_RESIDUAL 2 /* out = aux + gamma * (acc + bias)    vision_transformer.py:212-213, layer_scale.py:27 */
 #define B200_EPI_DGELU 3      /* out = (acc + bias) * gelu_erf'(aux)    backward of mlp.py:49        */
+#define B200_EPI_BIAS_ROPE 4  /* out = rope(acc + bias) on the q / k columns of a fused QKV projection:
+                                 attention.py:243-253 (AttentionRope), pos_embed_sincos.py:227-297 (interleaved
+                                 `rot` layout, head_dim 64, one [sin | cos] table shared by batch and heads)       */
 
 B200_API const char* b200_last_error(void);
 B200_API int b200_abi_version(void);
@@ -76,9 +79,22 @@ typedef struct b200_gemm_desc {
   int32_t rows_per_scale; /* tokens per sample: row r uses row_scale[r / rows_per_scale]                       */
   int32_t split_k;    /* >1: K is split over CTAs, partial tiles are atomically added into fp32 out
                          (requires out_dtype=f32, epilogue=B200_EPI_BIAS with bias=NULL)           */
+  /* EPI_BIAS_ROPE only (ABI 4).  rope: fp32 [rope_tokens - rope_prefix, 128] = [sin(64) | cos(64)], the `emb` of
+   * apply_rot_embed_cat; row r of `out` is token r % rope_tokens of its sample; the first rope_prefix tokens
+   * (cls / register tokens) and the columns >= rope_cols (the V third) pass through.  The value is rounded to bf16
+   * before the rotation, as the reference rotates the bf16 output of nn.Linear in fp32 (`.type_as(v)` rounds again). */
+  const float* rope;
+  int32_t rope_tokens, rope_prefix, rope_cols, reserved0;
 } b200_gemm_desc;
 
 B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);
+
+/* In-place rotary embedding of the q and k thirds of a fused QKV activation qkv[B*N, 3*H*64] (bf16); replaces
+ * apply_rot_embed_cat at timm/layers/attention.py:249-253 (pos_embed_sincos.py:227-297).  emb: fp32 [N - num_prefix, 128]
+ * = [sin | cos].  half_layout: 0 = interleaved pairs (`rot`), 1 = `rope_rotate_half`.  inverse = 1 applies the
+ * transposed map (the backward of the rotation, run on the q / k thirds of d(qkv)). */
+B200_API int b200_rope_qk(void* qkv, const float* emb, int32_t B, int32_t N, int32_t H, int32_t num_prefix,
+                          int32_t half_layout, int32_t inverse, void* stream);
 
 /* Debug hook (tools/gemm_trace.py, tools/attn_trace.py), not part of the reference-facing surface.  kernel 0 = b200_gemm:
  * with a non-NULL `device_buf` (>= 12 * #SMs uint64, zeroed by the caller) every following launch records per-CTA

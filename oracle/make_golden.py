@@ -169,7 +169,36 @@ def layer_cases():
     print("layers fixture written")
 
 
+def rope_cases():
+    """timm.layers.AttentionRope with the [sin | cos] table of RotaryEmbeddingCat (pos_embed_sincos.py:534-715), both
+    rotation layouts, one cls + one register token left un-rotated; outputs and all gradients after out.sum()-style
+    weighting.  Stored separately (tests/golden/rope.pt) so the other fixtures stay byte-identical."""
+    from timm.layers import AttentionRope, RotaryEmbeddingCat
+    g = torch.Generator().manual_seed(11)
+    fx = {"timm_version": __import__("timm").__version__, "torch_version": str(torch.__version__)}
+    dim, heads, grid, npt, B = 128, 2, (6, 5), 2, 3
+    N = grid[0] * grid[1] + npt
+    rope = RotaryEmbeddingCat(dim // heads, in_pixels=False, feat_shape=list(grid), ref_feat_shape=list(grid))
+    emb = rope.get_embed()
+    for half in (False, True):
+        torch.manual_seed(20 + int(half))
+        m = AttentionRope(dim, num_heads=heads, qkv_bias=True, num_prefix_tokens=npt, rotate_half=half).eval()
+        x = torch.randn(B, N, dim, generator=g).requires_grad_(True)
+        wgt = torch.randn(B, N, dim, generator=g)
+        y = m(x, rope=emb)
+        (y * wgt).sum().backward()
+        fx["half" if half else "interleaved"] = {
+            "state_dict": _half_sd(m.state_dict()), "x": x.detach().clone(), "emb": emb.detach().clone(), "y": y.detach().clone(),
+            "wgt": wgt, "dx": x.grad.clone(), "grads": {k: p.grad.clone() for k, p in m.named_parameters()},
+            "num_heads": heads, "num_prefix": npt, "grid": grid}
+    torch.save(fx, os.path.join(OUT, "rope.pt"))
+    print("rope fixture written", tuple(emb.shape))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "rope":
+        os.makedirs(OUT, exist_ok=True)
+        return rope_cases()
     os.makedirs(OUT, exist_ok=True)
     base = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=2, num_heads=2,
                 mlp_ratio=4.0, qkv_bias=True)
@@ -183,6 +212,7 @@ def main():
     convnext_case("convnext_g1", 3, 2, dict(depths=(1, 1, 2, 1), dims=(16, 32, 64, 128), num_classes=10), 64)
     naflex_case("naflex_g1", 4, 5)
     layer_cases()
+    rope_cases()
 
 
 if __name__ == "__main__":

@@ -64,6 +64,50 @@ def attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, kv_len=None):
     return linear(o, proj_w, proj_b)                                                        # :137
 
 
+def rope_rotate(x, emb, half=False):
+    """apply_rot_embed_cat (timm/layers/pos_embed_sincos.py:281-297): emb = [sin | cos] along the last dim,
+    x * cos + rot(x) * sin with rot = interleaved pairs (`rot`, :227-230: [-x1, x0, -x3, x2, ...]) or, for half=True,
+    `rope_rotate_half` (:233-237: [-x_{d/2..}, x_{..d/2}])."""
+    d = x.shape[-1]
+    sin, cos = emb[..., :d], emb[..., d:]
+    if half:
+        r = torch.cat([-x[..., d // 2:], x[..., :d // 2]], dim=-1)
+    else:
+        r = torch.empty_like(x)
+        r[..., 0::2] = -x[..., 1::2]
+        r[..., 1::2] = x[..., 0::2]
+    return x * cos + r * sin
+
+
+def attention_rope(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, rope, num_prefix=1, half=False, kv_len=None,
+                   round_qkv=None):
+    """timm/layers/attention.py:224-282 (AttentionRope.forward, fused qkv, no qk-norm / scale-norm / dropout):
+    q, k of every token after the first `num_prefix` are rotated by `rope` ([N - num_prefix, 2 * head_dim]) before the
+    scaled-dot-product attention (:249-253).  round_qkv: optional dtype the Linear output is rounded to before the
+    rotation and again after it (what a bf16 module does: nn.Linear emits bf16, `.type_as(v)` rounds the result)."""
+    B, N, C = x.shape
+    hd = qkv_w.shape[0] // 3 // num_heads
+    qkv = linear(x, qkv_w, qkv_b)
+    if round_qkv is not None:
+        qkv = qkv.to(round_qkv).to(x.dtype)
+    qkv = qkv.reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)                        # :236-237
+    q, k, v = qkv.unbind(0)
+    if rope is not None:
+        def rot(t):
+            out = torch.cat([t[:, :, :num_prefix], rope_rotate(t[:, :, num_prefix:], rope.to(t.dtype), half)], dim=2)
+            return out if round_qkv is None else out.to(round_qkv).to(t.dtype)
+        q, k = rot(q), rot(k)                                                               # :252-253
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    if kv_len is not None:
+        keys = torch.arange(N)[None, None, None, :]
+        s = s.masked_fill(keys >= kv_len.view(B, 1, 1, 1), float("-inf"))
+    s = s - s.amax(-1, keepdim=True)
+    p = torch.exp(s)
+    p = p / p.sum(-1, keepdim=True)
+    o = (p @ v).transpose(1, 2).reshape(B, N, num_heads * hd)
+    return linear(o, proj_w, proj_b)
+
+
 def mlp(x, fc1_w, fc1_b, fc2_w, fc2_b):
     """timm/layers/mlp.py:47-54 (Mlp.forward, drop=0, norm=Identity)."""
     return linear(gelu_erf(linear(x, fc1_w, fc1_b)), fc2_w, fc2_b)

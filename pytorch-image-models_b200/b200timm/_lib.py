@@ -14,7 +14,7 @@ HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "b200t
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 DTYPE_BF16, DTYPE_F32 = 0, 1
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_BIAS_ROPE = 0, 1, 2, 3, 4
 
 
 class B200Error(RuntimeError):
@@ -50,6 +50,11 @@ class GemmDesc(ctypes.Structure):
         ("accumulate", ctypes.c_int32),
         ("rows_per_scale", ctypes.c_int32),
         ("split_k", ctypes.c_int32),
+        ("rope", ctypes.c_void_p),
+        ("rope_tokens", ctypes.c_int32),
+        ("rope_prefix", ctypes.c_int32),
+        ("rope_cols", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
     ]
 
 
@@ -63,6 +68,7 @@ SIGNATURES = {
     "b200_device_check": (ctypes.c_int, []),
     "b200_gemm": (ctypes.c_int, [ctypes.POINTER(GemmDesc), _vp]),
     "b200_set_trace": (None, [_i32, _vp]),
+    "b200_rope_qk": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_layernorm_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),
     "b200_layernorm_bwd_ws_rows": (ctypes.c_int, [_i64, _i32]),
     "b200_layernorm_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),

@@ -155,6 +155,39 @@ class AttentionFn(torch.autograd.Function):
                 None, None, None)
 
 
+class AttentionRopeFn(torch.autograd.Function):
+    """AttentionRope.forward (timm/layers/attention.py:224-282).  The saved qkv holds the ROTATED q / k (what the
+    attention kernels consumed); the backward un-rotates d(q), d(k) in place (transpose of the rotation) before the
+    QKV projection's dgrad / wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, wqkv, bqkv, wproj, bproj, emb, kv_len, num_heads, scale, npt, half):
+        from .functional import rope_qkv_projection
+        B, N, C = x.shape
+        hd = wqkv.shape[0] // 3 // num_heads
+        x2 = _c(x.reshape(B * N, C))
+        qkv = rope_qkv_projection(x2, wqkv, bqkv, emb, B, N, num_heads, npt, half)
+        o, lse = ops.attention_fwd(qkv, B, N, num_heads, hd, scale, kv_len, need_lse=True)
+        y = ops.linear_fwd(o.view(B * N, -1), wproj, bproj)
+        ctx.save_for_backward(x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len, emb)
+        ctx.meta = (B, N, num_heads, hd, scale, npt, half)
+        return y.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len, emb = ctx.saved_tensors
+        B, N, H, hd, scale, npt, half = ctx.meta
+        dy2 = _c(dy.reshape(B * N, -1))
+        o2 = o.view(B * N, -1)
+        do = ops.linear_dgrad(dy2, wproj)
+        dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
+        if emb is not None:
+            ops.rope_qk(dqkv, emb, B, N, H, npt, half=half, inverse=True)
+        dx = ops.linear_dgrad(dqkv, wqkv).view(B, N, -1)
+        return (dx, _wgrad(dqkv, x2, wqkv), _bias_grad(dqkv, bqkv), _wgrad(dy2, o2, wproj), _bias_grad(dy2, bproj),
+                None, None, None, None, None, None)
+
+
 class BlockFn(torch.autograd.Function):
     """Block.forward (timm/models/vision_transformer.py:206-214) incl. LayerScale (layer_scale.py:26-27) and
     DropPath (drop.py:158-175): x = x + dp1(ls1(attn(norm1(x)))); x = x + dp2(ls2(mlp(norm2(x)))).

@@ -162,6 +162,59 @@ def attention_forward(attn, x, kv_len=None):
     return y.view(B, N, -1)
 
 
+def _rope_table(rope, n_rot, head_dim, device):
+    """The `rope` argument of AttentionRope.forward -> contiguous fp32 [n_rot, 2 * head_dim] = [sin | cos] on `device`
+    (the reference broadcasts `emb` against q[B, H, n_rot, hd]; a per-sample [B, 1, N, 2 hd] table is not covered)."""
+    if head_dim != 64:
+        raise B200Error("AttentionRope: only head_dim 64 is covered")
+    r = rope
+    while r.dim() > 2 and r.shape[0] == 1:
+        r = r[0]
+    if r.dim() != 2 or tuple(r.shape) != (n_rot, 2 * head_dim):
+        raise B200Error(f"AttentionRope: rope must broadcast from [{n_rot}, {2 * head_dim}], got {tuple(rope.shape)}")
+    key = (rope.data_ptr(), rope._version, str(device))
+    cache = _rope_table.cache
+    if cache.get("key") != key:
+        cache["key"], cache["val"] = key, r.detach().to(device=device, dtype=torch.float32).contiguous()
+    return cache["val"]
+
+
+_rope_table.cache = {}
+
+
+def attention_rope_forward(attn, x, rope=None, kv_len=None):
+    """AttentionRope.forward (timm/layers/attention.py:224-282): fused QKV projection + rotary embedding of q / k
+    (all tokens after the first num_prefix_tokens) + attention + output projection."""
+    if (attn.qkv is None or not isinstance(attn.q_norm, nn.Identity) or not isinstance(attn.k_norm, nn.Identity)
+            or not isinstance(attn.norm, nn.Identity) or (attn.training and (attn.attn_drop.p > 0 or attn.proj_drop.p > 0))):
+        raise B200Error("AttentionRope: separate q/k/v projections, qk-norm, scale-norm and dropout are not covered")
+    B, N, C = x.shape
+    H, hd = attn.num_heads, attn.head_dim
+    half = bool(getattr(attn, "rotate_half", False))
+    npt = attn.num_prefix_tokens
+    emb = None if rope is None else _rope_table(rope, N - npt, hd, x.device)
+    if _needs_grad(x, attn):
+        from .autograd import AttentionRopeFn
+        _bf16_2d(x, C)
+        return AttentionRopeFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, emb, kv_len, H,
+                                     attn.scale, npt, half)
+    x2 = _bf16_2d(x, C)
+    qkv = rope_qkv_projection(x2, _w(attn.qkv), attn.qkv.bias, emb, B, N, H, npt, half)
+    o, _ = ops.attention_fwd(qkv, B, N, H, hd, attn.scale, kv_len)
+    y = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias)
+    return y.view(B, N, -1)
+
+
+def rope_qkv_projection(x2, wqkv, bqkv, emb, B, N, H, npt, half):
+    """qkv = x W^T + b with q / k rotated: in the GEMM epilogue for the interleaved layout (neighbouring columns pair
+    up inside one thread's registers), by one in-place pass for the half layout (partners are 32 columns apart)."""
+    if emb is None:
+        return ops.linear_fwd(x2, wqkv, bqkv)
+    if not half:
+        return ops.linear_fwd(x2, wqkv, bqkv, epilogue=ops.EPI_BIAS_ROPE, rope=(emb, N, npt, 2 * H * 64))
+    return ops.rope_qk(ops.linear_fwd(x2, wqkv, bqkv), emb, B, N, H, npt, half=True)
+
+
 def mlp_forward(mlp, x):
     """Mlp.forward (timm/layers/mlp.py:47-54): fc2(GELU(fc1(x))), GELU fused into fc1's epilogue."""
     check_mlp(mlp)

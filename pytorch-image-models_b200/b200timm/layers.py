@@ -123,6 +123,49 @@ class Attention(nn.Module):
         return BF.attention_forward(self, x, kv_len)
 
 
+class AttentionRope(nn.Module):
+    """timm.layers.AttentionRope (attention.py:143-282), fused-QKV configuration: the rotary embedding is applied to
+    q and k inside the QKV projection's epilogue (interleaved layout) or by one in-place pass (half layout)."""
+
+    def __init__(self, dim: int, num_heads: int = 8, dim_out: Optional[int] = None, qkv_bias: bool = True,
+                 qkv_fused: bool = True, num_prefix_tokens: int = 1, attn_drop: float = 0., proj_drop: float = 0.,
+                 attn_head_dim: Optional[int] = None, norm_layer: Optional[Type[nn.Module]] = None,
+                 qk_norm: bool = False, scale_norm: bool = False, proj_bias: bool = True, rotate_half: bool = False,
+                 device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        if not qkv_fused or qk_norm or scale_norm:
+            raise B200Error("AttentionRope: separate q/k/v projections, qk-norm and scale-norm are not covered")
+        dim_out = dim_out or dim
+        head_dim = attn_head_dim
+        if head_dim is None:
+            assert dim % num_heads == 0, "dim should be divisible by num_heads"
+            head_dim = dim // num_heads
+        self.num_heads = num_heads
+        self.head_dim = head_dim
+        self.attn_dim = head_dim * num_heads
+        self.scale = head_dim ** -0.5
+        self.num_prefix_tokens = num_prefix_tokens
+        self.fused_attn = True
+        self.rotate_half = rotate_half
+        self.qkv = nn.Linear(dim, self.attn_dim * 3, bias=qkv_bias, **dd)
+        self.q_proj = self.k_proj = self.v_proj = None
+        self.q_norm = nn.Identity()
+        self.k_norm = nn.Identity()
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.norm = nn.Identity()
+        self.proj = nn.Linear(self.attn_dim, dim_out, bias=proj_bias, **dd)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    def forward(self, x: torch.Tensor, rope: Optional[torch.Tensor] = None, attn_mask: Optional[torch.Tensor] = None,
+                is_causal: bool = False, kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if is_causal:
+            raise B200Error("causal attention is not supported")
+        if attn_mask is not None:
+            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1]) if kv_len is None else kv_len
+        return BF.attention_rope_forward(self, x, rope, kv_len)
+
+
 def BF_mask_to_kv_len(attn_mask: torch.Tensor, n_tokens: int) -> torch.Tensor:
     """Convert a NaFlex key-padding mask (bool keep-mask or additive float, broadcastable to [B,1,N,N],
     naflexvit.py:964-1029) into per-sample valid-key counts.  The collator always emits prefix-valid masks

@@ -9,13 +9,13 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, B200Error,
+from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_BIAS_ROPE, EPI_DGELU, B200Error,
                    GemmDesc)
 
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU",
+    "avgpool_nhwc", "naflex_assemble", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk",
 ]
 
 
@@ -149,7 +149,7 @@ def _check_2d_bf16(t, name):
 
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None, gamma=None, out=None,
-         out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None, row_scale=None, rows_per_scale=0):
+         out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None, row_scale=None, rows_per_scale=0, rope=None):
     """out[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
@@ -186,6 +186,10 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
         if rows_per_scale <= 0 or row_scale.numel() * rows_per_scale < M:
             raise B200Error("gemm: row_scale needs rows_per_scale > 0 and ceil(M / rows_per_scale) entries")
         d.row_scale, d.rows_per_scale = row_scale.data_ptr(), int(rows_per_scale)
+    if rope is not None:
+        emb, tokens, prefix, cols = rope       # ([tokens - prefix, 128] fp32 = [sin | cos], N, prefix tokens, q+k columns)
+        _check_rope(emb, tokens, prefix)
+        d.rope, d.rope_tokens, d.rope_prefix, d.rope_cols = emb.data_ptr(), int(tokens), int(prefix), int(cols)
     d.M, d.N, d.K = M, N, K
     d.a_mn, d.b_mn = int(a_mn), int(b_mn)
     d.epilogue = epilogue
@@ -207,12 +211,31 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
 
 
 def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, out=None, out2=None, row_scale=None,
-               rows_per_scale=0):
+               rows_per_scale=0, rope=None):
     """F.linear on a [M,K] bf16 activation with a fused epilogue (weight: [N,K] bf16)."""
     M, K = x2d.shape
     N = weight.shape[0]
     return gemm(x2d, weight, M, N, K, epilogue=epilogue, bias=bias, aux=aux, gamma=gamma, out=out, out2=out2,
-                row_scale=row_scale, rows_per_scale=rows_per_scale)
+                row_scale=row_scale, rows_per_scale=rows_per_scale, rope=rope)
+
+
+def _check_rope(emb, tokens, prefix):
+    if (emb.dtype != torch.float32 or not emb.is_cuda or not emb.is_contiguous() or emb.dim() != 2
+            or emb.shape[1] != 128 or emb.shape[0] != tokens - prefix or prefix < 0):
+        raise B200Error("rope: the embedding must be a contiguous fp32 CUDA tensor [tokens - prefix, 2 * 64] = [sin | cos]")
+
+
+def rope_qk(qkv, emb, B, N, H, num_prefix, half=False, inverse=False):
+    """Rotate the q / k thirds of qkv [B*N, 3*H*64] bf16 IN PLACE (apply_rot_embed_cat, attention.py:249-253);
+    inverse=True applies the transposed map (backward of the rotation).  Returns qkv."""
+    _need_cuda(qkv, emb)
+    if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.numel() != B * N * 3 * H * 64:
+        raise B200Error("rope_qk: qkv must be a contiguous bf16 [B*N, 3*H*64] buffer (head_dim 64)")
+    _check_rope(emb, N, num_prefix)
+    rc = _lib.load().b200_rope_qk(qkv.data_ptr(), emb.data_ptr(), B, N, H, int(num_prefix), int(half), int(inverse), _stream())
+    _lib.check(rc, "b200_rope_qk")
+    _count()
+    return qkv
 
 
 def linear_dgrad(dy2d, weight, epilogue=EPI_BIAS, aux=None):

@@ -69,6 +69,12 @@ def _attention(self, x, attn_mask=None, is_causal=False):
     return BF.attention_forward(self, x, _kv_len(attn_mask, x.shape[1]))
 
 
+def _attention_rope(self, x, rope=None, attn_mask=None, is_causal=False):
+    if is_causal:
+        raise B200Error("causal attention is not covered")
+    return BF.attention_rope_forward(self, x, rope, _kv_len(attn_mask, x.shape[1]))
+
+
 def _vit_features(self, x, attn_mask=None, is_causal=False):
     if is_causal or self.grad_checkpointing:
         raise B200Error("causal / checkpointed forward_features is not covered")
@@ -113,7 +119,7 @@ def install():
     """Rebind timm's hot-path forwards.  Idempotent.  Raises if timm or libb200timm.so is unavailable."""
     _lib.load()  # fail loudly: no silent PyTorch path when the CUDA library is missing
     import timm  # noqa: F401
-    from timm.layers.attention import Attention
+    from timm.layers.attention import Attention, AttentionRope
     from timm.layers.mlp import Mlp
     from timm.layers.norm import LayerNorm
     from timm.layers.patch_embed import PatchEmbed
@@ -125,6 +131,7 @@ def install():
         ("timm.layers.LayerNorm.forward", LayerNorm, "forward", lambda self, x: BF.layernorm(self, x)),
         ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
         ("timm.layers.Attention.forward", Attention, "forward", _attention),
+        ("timm.layers.AttentionRope.forward", AttentionRope, "forward", _attention_rope),
         ("timm.layers.PatchEmbed.forward", PatchEmbed, "forward",
          lambda self, x: BF.patch_embed_forward(self, x) if self.flatten else (_ for _ in ()).throw(B200Error("NHWC"))),
         ("timm.models.vision_transformer.Block.forward", Block, "forward", _block),

@@ -132,7 +132,7 @@ static int encode_tmap_uncached(CUtensorMap* out, CUtensorMapDataType dt, const 
 }  // namespace b200
 
 extern "C" const char* b200_last_error(void) { return b200::g_err; }
-extern "C" int b200_abi_version(void) { return 3; }
+extern "C" int b200_abi_version(void) { return 4; }
 
 extern "C" int b200_device_check(void) {
   int dev = 0;

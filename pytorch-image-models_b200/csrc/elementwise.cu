@@ -251,6 +251,60 @@ __global__ void convert_kernel(const float* __restrict__ src, void* __restrict__
   }
 }
 
+// Rotary embedding of the q / k thirds of qkv[B*N, 3*H*64] in place (AttentionRope, timm/layers/attention.py:249-253).
+// A thread owns token row r, head slot g (q heads then k heads) and the 8-column chunks at d0 and d0 + 32 of the head:
+// both layouts pair columns inside those 16 values (interleaved: neighbours; half: d <-> d + 32).
+__global__ void __launch_bounds__(256)
+rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ emb, long long rows, int N, int H, int prefix,
+               int half_layout, int inverse) {
+  const long long total = rows * (2LL * H) * 4;
+  const long long ld = 3LL * H * 64;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d0 = static_cast<int>(idx & 3) * 8;
+    const long long t = idx >> 2;
+    const int g = static_cast<int>(t % (2 * H));
+    const long long r = t / (2 * H);
+    const int tok = static_cast<int>(r % N) - prefix;
+    if (tok < 0) continue;
+    __nv_bfloat16* px = qkv + r * ld + g * 64 + d0;
+    const float* e = emb + static_cast<long long>(tok) * 128 + d0;
+    float x[16], sn[16], cs[16], y[16];
+    {
+      const uint4 a = *reinterpret_cast<const uint4*>(px), b = *reinterpret_cast<const uint4*>(px + 32);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x[2 * i] = bf16_lo(w[i]); x[2 * i + 1] = bf16_hi(w[i]); }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(e + 32 * i)), s1 = __ldg(reinterpret_cast<const float4*>(e + 32 * i + 4));
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(e + 64 + 32 * i)), c1 = __ldg(reinterpret_cast<const float4*>(e + 64 + 32 * i + 4));
+        sn[8 * i + 0] = s0.x; sn[8 * i + 1] = s0.y; sn[8 * i + 2] = s0.z; sn[8 * i + 3] = s0.w;
+        sn[8 * i + 4] = s1.x; sn[8 * i + 5] = s1.y; sn[8 * i + 6] = s1.z; sn[8 * i + 7] = s1.w;
+        cs[8 * i + 0] = c0.x; cs[8 * i + 1] = c0.y; cs[8 * i + 2] = c0.z; cs[8 * i + 3] = c0.w;
+        cs[8 * i + 4] = c1.x; cs[8 * i + 5] = c1.y; cs[8 * i + 6] = c1.z; cs[8 * i + 7] = c1.w;
+      }
+    }
+    // forward:  y[a] = x[a] cos[a] - x[b] sin[a],  y[b] = x[b] cos[b] + x[a] sin[b]   for each pair (a, b)
+    // inverse (transpose): y[a] = x[a] cos[a] + x[b] sin[b],  y[b] = x[b] cos[b] - x[a] sin[a]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int a = half_layout ? i : (i < 4 ? 2 * i : 8 + 2 * (i - 4));
+      const int b = half_layout ? i + 8 : a + 1;
+      if (!inverse) {
+        y[a] = fmaf(x[a], cs[a], -x[b] * sn[a]);
+        y[b] = fmaf(x[b], cs[b], x[a] * sn[b]);
+      } else {
+        y[a] = fmaf(x[a], cs[a], x[b] * sn[b]);
+        y[b] = fmaf(x[b], cs[b], -x[a] * sn[a]);
+      }
+    }
+    *reinterpret_cast<uint4*>(px) = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+    *reinterpret_cast<uint4*>(px + 32) =
+        make_uint4(pack_bf16(y[8], y[9]), pack_bf16(y[10], y[11]), pack_bf16(y[12], y[13]), pack_bf16(y[14], y[15]));
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -377,6 +431,24 @@ extern "C" int b200_colsum_mul(const void* a, const void* b, const float* row_sc
   colsum_mul_kernel<<<dim3(gx, slabs), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
                                                       reinterpret_cast<const __nv_bfloat16*>(b), row_scale, out, rows, cols,
                                                       rps, rows_per_scale > 0 ? rows_per_scale : 1);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_rope_qk(void* qkv, const float* emb, int32_t B, int32_t N, int32_t H, int32_t num_prefix,
+                            int32_t half_layout, int32_t inverse, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(qkv && emb, "b200_rope_qk: null pointer");
+  B200_CHECK_ARG(B > 0 && N > 0 && H > 0 && num_prefix >= 0 && num_prefix < N, "b200_rope_qk: bad shape");
+  B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(emb)) & 15) == 0,
+                 "b200_rope_qk: pointers must be 16-byte aligned");
+  const long long rows = static_cast<long long>(B) * N;
+  const long long total = rows * 2 * H * 4;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  rope_qk_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(qkv), emb, rows, N, H, num_prefix,
+                                                          half_layout != 0, inverse != 0);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -37,6 +37,8 @@ struct GemmKernelParams {
   int num_m_blocks, num_n_blocks, num_k_blocks;  // num_k_blocks: total over K
   int split_k, k_blocks_per_split;
   int epilogue, out_f32, bias_f32, gamma_f32, accumulate;
+  const float* rope;           // EPI_BIAS_ROPE: [rope_tokens - rope_prefix][128] = [sin | cos]
+  int rope_tokens, rope_prefix, rope_cols;
   unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_set_trace), nullptr in production
 };
 
@@ -351,6 +353,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // per-row scale of the residual branch (DropPath keep-mask / keep_prob of the row's sample, drop.py:158-175)
       f32x2 rs2 = splat(1.0f);
       if (p.row_scale != nullptr && row0 + lane < p.M) rs2 = splat(__ldg(p.row_scale + (row0 + lane) / p.rows_per_scale));
+      // rotary embedding: this lane's row is token (row % N) of its sample; prefix tokens / rows past M pass through
+      const float* rope_row = nullptr;
+      if (EPI < 0 && epi == B200_EPI_BIAS_ROPE && row0 + lane < p.M) {
+        const int tok = (row0 + lane) % p.rope_tokens - p.rope_prefix;
+        if (tok >= 0) rope_row = p.rope + static_cast<long long>(tok) * 128;
+      }
       bool waited = false;
 #pragma unroll 1
       for (int rc = 0; rc < kColsPerWarp; rc += round_cols) {
@@ -421,7 +429,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                   for (int j = 0; j < 4; ++j) v[j] = add2(v[j], bv[j]);
                 }
-                if (epi == B200_EPI_BIAS_GELU && !dual) {
+                if (EPI < 0 && epi == B200_EPI_BIAS_ROPE) {
+                  if (rope_row != nullptr && col < p.rope_cols) {
+                    // y[2i] = x[2i] cos[2i] - x[2i+1] sin[2i];  y[2i+1] = x[2i+1] cos[2i+1] + x[2i] sin[2i+1]
+                    const float4* e = reinterpret_cast<const float4*>(rope_row + (col & 63));
+                    const float4 s0 = __ldg(e), s1 = __ldg(e + 1), c0 = __ldg(e + 16), c1 = __ldg(e + 17);
+                    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      float x0, x1;
+                      upk(v[j], x0, x1);
+                      const uint32_t xb = pack_bf16(x0, x1);           // the bf16 value nn.Linear would have emitted
+                      x0 = bf16_lo(xb);
+                      x1 = bf16_hi(xb);
+                      v[j] = pk(fmaf(x0, cs[2 * j], -x1 * sn[2 * j]), fmaf(x1, cs[2 * j + 1], x0 * sn[2 * j + 1]));
+                    }
+                  }
+                } else if (epi == B200_EPI_BIAS_GELU && !dual) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
                 } else if (has_aux && !dual) {
@@ -605,6 +630,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.epilogue = d.epilogue; p.out_f32 = d.out_dtype == B200_DTYPE_F32;
   p.bias_f32 = d.bias_dtype == B200_DTYPE_F32; p.gamma_f32 = d.gamma_dtype == B200_DTYPE_F32;
   p.accumulate = d.accumulate;
+  p.rope = d.rope; p.rope_tokens = d.rope_tokens; p.rope_prefix = d.rope_prefix; p.rope_cols = d.rope_cols;
   p.trace = g_gemm_trace;
 
   auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI>;
@@ -677,7 +703,13 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(d.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.b) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(d.out) & 15) == 0,
                  "b200_gemm: operand pointers must be 16-byte aligned");
-  B200_CHECK_ARG(d.epilogue >= B200_EPI_BIAS && d.epilogue <= B200_EPI_DGELU, "b200_gemm: bad epilogue %d", d.epilogue);
+  B200_CHECK_ARG(d.epilogue >= B200_EPI_BIAS && d.epilogue <= B200_EPI_BIAS_ROPE, "b200_gemm: bad epilogue %d", d.epilogue);
+  if (d.epilogue == B200_EPI_BIAS_ROPE)
+    B200_CHECK_ARG(d.rope != nullptr && (reinterpret_cast<uintptr_t>(d.rope) & 15) == 0 && d.rope_tokens > 0 &&
+                       d.rope_prefix >= 0 && d.rope_prefix < d.rope_tokens && d.rope_cols % 64 == 0 && d.rope_cols <= d.N &&
+                       d.out_dtype == B200_DTYPE_BF16 && d.out2 == nullptr && !d.a_mn && !d.b_mn,
+                   "b200_gemm: EPI_BIAS_ROPE needs a 16-byte aligned rope table, rope_prefix < rope_tokens, rope_cols a "
+                   "multiple of 64 (head_dim 64), bf16 output and K-major operands");
   if (d.epilogue == B200_EPI_BIAS_RESIDUAL || d.epilogue == B200_EPI_DGELU) {
     B200_CHECK_ARG(d.aux != nullptr && d.ldaux % 8 == 0 && d.ldaux >= d.N &&
                        (reinterpret_cast<uintptr_t>(d.aux) & 15) == 0,

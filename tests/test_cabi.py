@@ -28,14 +28,14 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string_without_gpu():
     lib = _lib.load()
-    assert lib.b200_abi_version() == 3
+    assert lib.b200_abi_version() == 4
     assert isinstance(lib.b200_last_error(), bytes)
 
 
 def test_gemm_desc_layout_matches_header():
     """struct b200_gemm_desc: 8 pointers, 5 int64, 12 int32."""
-    assert ctypes.sizeof(_lib.GemmDesc) == 8 * 8 + 5 * 8 + 12 * 4
-    assert _lib.GemmDesc.M.offset == 104 and _lib.GemmDesc.split_k.offset == 148
+    assert ctypes.sizeof(_lib.GemmDesc) == 8 * 8 + 5 * 8 + 12 * 4 + 8 + 4 * 4
+    assert _lib.GemmDesc.M.offset == 104 and _lib.GemmDesc.split_k.offset == 148 and _lib.GemmDesc.rope.offset == 152
 
 
 def test_argument_errors_are_reported_not_crashed():

@@ -111,3 +111,19 @@ def test_naflex_oracle_matches_reference():
     for b in range(feats.shape[0]):   # padded query rows are unspecified in the reference (all-masked softmax)
         n = int(fx["patch_valid"][b].sum()) + npre
         torch.testing.assert_close(feats[b, :n], fx["features"][b, :n], atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("layout", ["interleaved", "half"])
+def test_attention_rope_oracle_matches_reference(layout):
+    """timm.layers.AttentionRope (attention.py:224-282) with a RotaryEmbeddingCat table: the oracle restatement and its
+    autograd reproduce the reference's output, input gradient and every parameter gradient (fp32)."""
+    fx = torch.load(os.path.join(GOLDEN, "rope.pt"))[layout]
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    x = fx["x"].clone().requires_grad_(True)
+    y = O.attention_rope(x, sd["qkv.weight"], sd["qkv.bias"], sd["proj.weight"], sd["proj.bias"], fx["num_heads"],
+                         fx["emb"], num_prefix=fx["num_prefix"], half=(layout == "half"))
+    assert torch.allclose(y, fx["y"], atol=2e-5, rtol=1e-4), (y - fx["y"]).abs().max()
+    (y * fx["wgt"]).sum().backward()
+    assert torch.allclose(x.grad, fx["dx"], atol=2e-4, rtol=1e-3), (x.grad - fx["dx"]).abs().max()
+    for k, g in fx["grads"].items():
+        assert torch.allclose(sd[k].grad, g, atol=5e-4, rtol=1e-3), (k, (sd[k].grad - g).abs().max())
