@@ -362,6 +362,8 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse, const int32_t
 namespace b200 {
 int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H, float scale,
                      cudaStream_t st);
+int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H, float scale,
+                         cudaStream_t st);
 }
 
 using namespace b200;
@@ -383,5 +385,7 @@ extern "C" int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32
   if (ptmem && N <= 208) return launch_attn_fwd<208, true, true>(qkv, out, lse, kv_len, B, N, H, scale, st);
   if (N <= 208) return launch_attn_fwd<208, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
   if (N <= 256) return launch_attn_fwd<256, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
+  // longer sequences: the double-buffered online-softmax kernel of attention_fwd_long.cu
+  if (!use_v1) return launch_attn_fwd_long(qkv, out, lse, kv_len, B, N, H, scale, st);
   return launch_attn_fwd<128, false, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
 }
