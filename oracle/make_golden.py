@@ -191,6 +191,20 @@ def rope_cases():
             "state_dict": _half_sd(m.state_dict()), "x": x.detach().clone(), "emb": emb.detach().clone(), "y": y.detach().clone(),
             "wgt": wgt, "dx": x.grad.clone(), "grads": {k: p.grad.clone() for k, p in m.named_parameters()},
             "num_heads": heads, "num_prefix": npt, "grid": grid}
+    # EvaAttention (timm/models/eva.py:105-262): q_bias / v_bias parameters + zero k_bias buffer, fused qkv, no norms
+    from timm.models.eva import EvaAttention
+    torch.manual_seed(30)
+    m = EvaAttention(dim, num_heads=heads, qkv_bias=True, num_prefix_tokens=npt, scale_norm=False).eval()
+    with torch.no_grad():
+        m.q_bias.normal_(std=0.5)
+        m.v_bias.normal_(std=0.5)
+    x = torch.randn(B, N, dim, generator=g).requires_grad_(True)
+    wgt = torch.randn(B, N, dim, generator=g)
+    y = m(x, rope=emb)
+    (y * wgt).sum().backward()
+    fx["eva"] = {"state_dict": _half_sd(m.state_dict()), "x": x.detach().clone(), "emb": emb.detach().clone(),
+                 "y": y.detach().clone(), "wgt": wgt, "dx": x.grad.clone(),
+                 "grads": {k: p.grad.clone() for k, p in m.named_parameters()}, "num_heads": heads, "num_prefix": npt}
     torch.save(fx, os.path.join(OUT, "rope.pt"))
     print("rope fixture written", tuple(emb.shape))
 

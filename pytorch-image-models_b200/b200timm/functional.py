@@ -182,9 +182,18 @@ def _rope_table(rope, n_rot, head_dim, device):
 _rope_table.cache = {}
 
 
+def _qkv_bias(attn):
+    """AttentionRope keeps the bias on `qkv`; EvaAttention (timm/models/eva.py:157-165, 209-217) keeps q_bias / v_bias
+    parameters and a zero k_bias buffer and concatenates them per call -- same here (autograd splits the gradient)."""
+    if getattr(attn, "q_bias", None) is not None:
+        return torch.cat((attn.q_bias, attn.k_bias, attn.v_bias))
+    return attn.qkv.bias
+
+
 def attention_rope_forward(attn, x, rope=None, kv_len=None):
-    """AttentionRope.forward (timm/layers/attention.py:224-282): fused QKV projection + rotary embedding of q / k
-    (all tokens after the first num_prefix_tokens) + attention + output projection."""
+    """AttentionRope.forward (timm/layers/attention.py:224-282) and EvaAttention.forward (timm/models/eva.py:197-262,
+    fused qkv, no qk-norm / scale-norm): fused QKV projection + rotary embedding of q / k (all tokens after the first
+    num_prefix_tokens) + attention + output projection."""
     if (attn.qkv is None or not isinstance(attn.q_norm, nn.Identity) or not isinstance(attn.k_norm, nn.Identity)
             or not isinstance(attn.norm, nn.Identity) or (attn.training and (attn.attn_drop.p > 0 or attn.proj_drop.p > 0))):
         raise B200Error("AttentionRope: separate q/k/v projections, qk-norm, scale-norm and dropout are not covered")
@@ -196,10 +205,10 @@ def attention_rope_forward(attn, x, rope=None, kv_len=None):
     if _needs_grad(x, attn):
         from .autograd import AttentionRopeFn
         _bf16_2d(x, C)
-        return AttentionRopeFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, emb, kv_len, H,
+        return AttentionRopeFn.apply(x, _w(attn.qkv), _qkv_bias(attn), _w(attn.proj), attn.proj.bias, emb, kv_len, H,
                                      attn.scale, npt, half)
     x2 = _bf16_2d(x, C)
-    qkv = rope_qkv_projection(x2, _w(attn.qkv), attn.qkv.bias, emb, B, N, H, npt, half)
+    qkv = rope_qkv_projection(x2, _w(attn.qkv), _qkv_bias(attn), emb, B, N, H, npt, half)
     o, _ = ops.attention_fwd(qkv, B, N, H, hd, attn.scale, kv_len)
     y = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias)
     return y.view(B, N, -1)

@@ -124,6 +124,7 @@ def install():
     from timm.layers.norm import LayerNorm
     from timm.layers.patch_embed import PatchEmbed
     from timm.models.convnext import ConvNeXt, ConvNeXtBlock
+    from timm.models.eva import EvaAttention
     from timm.models.vision_transformer import Block, VisionTransformer
     if _ORIG:
         return
@@ -132,6 +133,7 @@ def install():
         ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
         ("timm.layers.Attention.forward", Attention, "forward", _attention),
         ("timm.layers.AttentionRope.forward", AttentionRope, "forward", _attention_rope),
+        ("timm.models.eva.EvaAttention.forward", EvaAttention, "forward", _attention_rope),
         ("timm.layers.PatchEmbed.forward", PatchEmbed, "forward",
          lambda self, x: BF.patch_embed_forward(self, x) if self.flatten else (_ for _ in ()).throw(B200Error("NHWC"))),
         ("timm.models.vision_transformer.Block.forward", Block, "forward", _block),

@@ -92,3 +92,44 @@ def test_attention_rope_module_forward_backward(layout):
     with torch.no_grad():
         y2 = m.eval()(x.cuda(), rope=fx["emb"])
     assert torch.equal(y2, y.detach())
+
+
+def test_eva_attention_through_the_rope_path():
+    """EvaAttention's parameter layout (q_bias, v_bias, zero k_bias buffer, bias-free qkv Linear; eva.py:157-165) runs
+    through the same fused path; gradients reach q_bias / v_bias through the per-call concatenation."""
+    import torch.nn as nn
+    from b200timm import functional as BF
+    fx = torch.load(os.path.join(GOLDEN, "rope.pt"))["eva"]
+
+    class EvaAttentionLike(nn.Module):       # attribute-for-attribute what timm.models.eva.EvaAttention holds
+        def __init__(self, dim, heads, npt):
+            super().__init__()
+            self.num_heads, self.head_dim, self.scale, self.num_prefix_tokens = heads, dim // heads, (dim // heads) ** -0.5, npt
+            self.rotate_half = False
+            self.qkv = nn.Linear(dim, 3 * dim, bias=False)
+            self.q_bias = nn.Parameter(torch.zeros(dim))
+            self.register_buffer("k_bias", torch.zeros(dim), persistent=False)
+            self.v_bias = nn.Parameter(torch.zeros(dim))
+            self.q_norm, self.k_norm, self.norm = nn.Identity(), nn.Identity(), nn.Identity()
+            self.attn_drop, self.proj_drop = nn.Dropout(0.), nn.Dropout(0.)
+            self.proj = nn.Linear(dim, dim)
+
+    sd = {k: v.bfloat16().float() for k, v in fx["state_dict"].items()}
+    m = EvaAttentionLike(128, fx["num_heads"], fx["num_prefix"])
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().to(torch.bfloat16).train()
+    x = fx["x"].bfloat16()
+    xg = x.cuda().requires_grad_(True)
+    y = BF.attention_rope_forward(m, xg, fx["emb"])
+    (y.float() * fx["wgt"].cuda()).sum().backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x.float().requires_grad_(True)
+    bias = torch.cat((ref_sd["q_bias"], torch.zeros_like(ref_sd["q_bias"]), ref_sd["v_bias"]))
+    yr = O.attention_rope(xr, ref_sd["qkv.weight"], bias, ref_sd["proj.weight"], ref_sd["proj.bias"], fx["num_heads"],
+                          fx["emb"], num_prefix=fx["num_prefix"])
+    (yr * fx["wgt"]).sum().backward()
+    assert (y.float().cpu() - yr).abs().max().item() <= 2e-2 + 2e-2 * yr.abs().max().item()
+    for k, p in m.named_parameters():
+        ref = ref_sd[k].grad
+        rel = (p.grad.float().cpu() - ref).norm().item() / max(ref.norm().item(), 1e-6)
+        assert rel <= 5e-2, f"{k}: rel L2 err {rel:.4f}"

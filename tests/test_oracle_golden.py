@@ -127,3 +127,19 @@ def test_attention_rope_oracle_matches_reference(layout):
     assert torch.allclose(x.grad, fx["dx"], atol=2e-4, rtol=1e-3), (x.grad - fx["dx"]).abs().max()
     for k, g in fx["grads"].items():
         assert torch.allclose(sd[k].grad, g, atol=5e-4, rtol=1e-3), (k, (sd[k].grad - g).abs().max())
+
+
+def test_eva_attention_oracle_matches_reference():
+    """timm.models.eva.EvaAttention (eva.py:197-262; q_bias / zero k_bias / v_bias concatenated per call): the same oracle
+    restatement with the concatenated bias reproduces output and gradients."""
+    fx = torch.load(os.path.join(GOLDEN, "rope.pt"))["eva"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    x = fx["x"].clone().requires_grad_(True)
+    bias = torch.cat((sd["q_bias"], torch.zeros_like(sd["q_bias"]), sd["v_bias"]))
+    y = O.attention_rope(x, sd["qkv.weight"], bias, sd["proj.weight"], sd["proj.bias"], fx["num_heads"], fx["emb"],
+                         num_prefix=fx["num_prefix"])
+    assert torch.allclose(y, fx["y"], atol=2e-5, rtol=1e-4), (y - fx["y"]).abs().max()
+    (y * fx["wgt"]).sum().backward()
+    assert torch.allclose(x.grad, fx["dx"], atol=2e-4, rtol=1e-3)
+    for k, g in fx["grads"].items():
+        assert torch.allclose(sd[k].grad, g, atol=5e-4, rtol=1e-3), (k, (sd[k].grad - g).abs().max())
