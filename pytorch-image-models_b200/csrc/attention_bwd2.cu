@@ -9,6 +9,8 @@
 //   * a dedicated issuer warp queues [dV += P^T dO, dK += dS^T Q, dQ += dS K] of step i followed immediately by
 //     [S^T, dP^T] of step i+1, so the MMA pipe never drains between steps.
 // No atomics: dK / dV of a key tile accumulate over the query halves, dQ of a query half over the key tiles, all in TMEM.
+// Persistent: one CTA per SM loops over (image, head) items; as soon as an item's last MMA has completed the issuer
+// requests the NEXT item's Q / K / V / dO, so those loads run under the current item's dV / dK / dQ read-out and stores.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -113,16 +115,23 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* bar_sd = bar_ld + 1;      // issuer -> compute: S^T / dP^T of the step are in TMEM
   uint64_t* bar_p = bar_ld + 2;       // compute -> issuer: P^T / dS^T of the step are in smem (count 256)
-  uint64_t* bar_fin = bar_ld + 3;     // issuer -> compute: every MMA has completed
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ld + 4);
+  uint64_t* bar_fin = bar_ld + 3;     // issuer -> compute: every MMA of the item has completed
+  uint64_t* bar_tail = bar_ld + 4;    // compute -> issuer: the item's dV / dK / dQ accumulators have been read (count 256)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ld + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x, b = blockIdx.y;
   const int N = p.N, H = p.H;
-  int kvlen = N;
-  if (p.kv_len != nullptr) kvlen = max(1, min(p.kv_len[b], N));
-  const int num_kt = (kvlen + 127) / 128;
-  const int num_steps = num_kt * 2;
+  const int num_items = p.B * H;
+  auto item_kvlen = [&](int item) {
+    return p.kv_len != nullptr ? max(1, min(p.kv_len[item / H], N)) : N;
+  };
+  auto load_stats = [&](int item, int t0, int nthreads) {   // lse (log2 domain) / delta rows of an item -> smem
+    for (int q = t0; q < 2 * kQH; q += nthreads) {
+      const long long idx = static_cast<long long>(item) * N + q;      // item = b * H + h
+      sLse[q] = (q < N) ? p.lse[idx] * 1.4426950408889634f : INFINITY;   // +inf -> P = 0 for padding queries
+      sDelta[q] = (q < N) ? p.delta[idx] : 0.f;
+    }
+  };
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -133,6 +142,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     mbar_init(bar_sd, 1);
     mbar_init(bar_p, kComputeThreads);
     mbar_init(bar_fin, 1);
+    mbar_init(bar_tail, kComputeThreads);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -140,11 +150,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
-  for (int q = tid; q < 2 * kQH; q += blockDim.x) {
-    const long long idx = (static_cast<long long>(b) * H + h) * N + q;
-    sLse[q] = (q < N) ? p.lse[idx] * 1.4426950408889634f : INFINITY;   // +inf -> P = 0 for padding queries
-    sDelta[q] = (q < N) ? p.delta[idx] : 0.f;
-  }
+  if (static_cast<int>(blockIdx.x) < num_items) load_stats(blockIdx.x, tid, blockDim.x);
   for (int i = tid; i < 2048 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + kOffPad)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -155,14 +161,17 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   if (warp == 8) {
     // ------------------------------------------------------------------ issuer (TMA + tcgen05.mma), one thread
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_ld, 4 * kTileB);
-      tma_load_2d(sQ, &tm_qkv, bar_ld, h * kHd, b * N);
-      tma_load_2d(sK, &tm_qkv, bar_ld, (H + h) * kHd, b * N);
-      tma_load_2d(sV, &tm_qkv, bar_ld, (2 * H + h) * kHd, b * N);
-      tma_load_2d(sDO, &tm_do, bar_ld, h * kHd, b * N);
       constexpr uint32_t idesc_sd = make_idesc_bf16(128, kQH, false, false);
       constexpr uint32_t idesc_kv = make_idesc_bf16(128, kHd, false, true);
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, kHd, true, true);
+      auto load_item = [&](int item) {
+        const int b = item / H, h = item - b * H;
+        mbar_arrive_expect_tx(bar_ld, 4 * kTileB);
+        tma_load_2d(sQ, &tm_qkv, bar_ld, h * kHd, b * N);
+        tma_load_2d(sK, &tm_qkv, bar_ld, (H + h) * kHd, b * N);
+        tma_load_2d(sV, &tm_qkv, bar_ld, (2 * H + h) * kHd, b * N);
+        tma_load_2d(sDO, &tm_do, bar_ld, h * kHd, b * N);
+      };
       auto issue_sd = [&](int step) {
         const int kt = step >> 1, qh = step & 1;
         const uint64_t kd = make_smem_desc(smem_u32(sK) + kt * 128 * kRowB, 16, 1024, kLayoutSw128);
@@ -174,39 +183,52 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 #pragma unroll
         for (int k = 0; k < kHd / 16; ++k) umma_ss(tmem_base + kColDP, vd + 2 * k, dod + 2 * k, idesc_sd, k > 0 ? 1u : 0u);
       };
-      mbar_wait(bar_ld, 0);
-      tc_fence_after();
-      issue_sd(0);
-      umma_commit(bar_sd);
-      for (int step = 0; step < num_steps; ++step) {
-        const int kt = step >> 1, qh = step & 1;
-        mbar_wait(bar_p, step & 1);
+      if (static_cast<int>(blockIdx.x) < num_items) load_item(blockIdx.x);
+      int it = 0;
+      uint32_t gs = 0;                       // global step counter: phase of bar_sd / bar_p
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int num_steps = ((item_kvlen(item) + 127) / 128) * 2;
+        mbar_wait(bar_ld, it & 1);
         tc_fence_after();
-        // dV_kt (+)= P^T dO_qh ; dK_kt (+)= dS^T Q_qh   (A: K-major core matrices, 8-query chunks 2048 B apart)
-        const uint64_t pd = make_smem_desc(smem_u32(sP), 2048, 128, kLayoutNone);
-        const uint64_t dsd = make_smem_desc(smem_u32(sDS), 2048, 128, kLayoutNone);
-        const uint64_t dob = make_smem_desc(smem_u32(sDO) + qh * kQH * kRowB, 1024, 1024, kLayoutSw128);
-        const uint64_t qb = make_smem_desc(smem_u32(sQ) + qh * kQH * kRowB, 1024, 1024, kLayoutSw128);
+        issue_sd(0);
+        umma_commit(bar_sd);
+        for (int step = 0; step < num_steps; ++step, ++gs) {
+          const int kt = step >> 1, qh = step & 1;
+          mbar_wait(bar_p, gs & 1);
+          if (step == 0 && it > 0) mbar_wait(bar_tail, (it - 1) & 1);   // previous item's accumulators were read out
+          tc_fence_after();
+          // dV_kt (+)= P^T dO_qh ; dK_kt (+)= dS^T Q_qh   (A: K-major core matrices, 8-query chunks 2048 B apart)
+          const uint64_t pd = make_smem_desc(smem_u32(sP), 2048, 128, kLayoutNone);
+          const uint64_t dsd = make_smem_desc(smem_u32(sDS), 2048, 128, kLayoutNone);
+          const uint64_t dob = make_smem_desc(smem_u32(sDO) + qh * kQH * kRowB, 1024, 1024, kLayoutSw128);
+          const uint64_t qb = make_smem_desc(smem_u32(sQ) + qh * kQH * kRowB, 1024, 1024, kLayoutSw128);
 #pragma unroll
-        for (int k = 0; k < kQH / 16; ++k)
-          umma_ss(tmem_base + kColDV, pd + static_cast<uint64_t>(k * (4096 >> 4)), dob + static_cast<uint64_t>(k * (2048 >> 4)),
-                  idesc_kv, (qh > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kQH / 16; ++k)
+            umma_ss(tmem_base + kColDV, pd + static_cast<uint64_t>(k * (4096 >> 4)), dob + static_cast<uint64_t>(k * (2048 >> 4)),
+                    idesc_kv, (qh > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < kQH / 16; ++k)
-          umma_ss(tmem_base + kColDK, dsd + static_cast<uint64_t>(k * (4096 >> 4)), qb + static_cast<uint64_t>(k * (2048 >> 4)),
-                  idesc_kv, (qh > 0 || k > 0) ? 1u : 0u);
-        // dQ_qh (+)= dS K_kt   (A: the same dS^T tile read MN-major; B: K_kt MN-major in place)
-        const uint64_t ad = make_smem_desc(smem_u32(sDS), 128, 2048, kLayoutNone);
-        const uint64_t kb = make_smem_desc(smem_u32(sK) + kt * 128 * kRowB, 1024, 1024, kLayoutSw128);
+          for (int k = 0; k < kQH / 16; ++k)
+            umma_ss(tmem_base + kColDK, dsd + static_cast<uint64_t>(k * (4096 >> 4)), qb + static_cast<uint64_t>(k * (2048 >> 4)),
+                    idesc_kv, (qh > 0 || k > 0) ? 1u : 0u);
+          // dQ_qh (+)= dS K_kt   (A: the same dS^T tile read MN-major; B: K_kt MN-major in place)
+          const uint64_t ad = make_smem_desc(smem_u32(sDS), 128, 2048, kLayoutNone);
+          const uint64_t kb = make_smem_desc(smem_u32(sK) + kt * 128 * kRowB, 1024, 1024, kLayoutSw128);
 #pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_ss(tmem_base + (qh == 0 ? kColDQ0 : kColDQ1), ad + static_cast<uint64_t>(k * (256 >> 4)),
-                  kb + static_cast<uint64_t>(k * (2048 >> 4)), idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
-        if (step + 1 < num_steps) {
-          issue_sd(step + 1);
-          umma_commit(bar_sd);
-        } else {
-          umma_commit(bar_fin);
+          for (int k = 0; k < 128 / 16; ++k)
+            umma_ss(tmem_base + (qh == 0 ? kColDQ0 : kColDQ1), ad + static_cast<uint64_t>(k * (256 >> 4)),
+                    kb + static_cast<uint64_t>(k * (2048 >> 4)), idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
+          if (step + 1 < num_steps) {
+            issue_sd(step + 1);
+            umma_commit(bar_sd);
+          } else {
+            umma_commit(bar_fin);
+          }
+        }
+        // every MMA of this item has completed -> the operand tiles are free: fetch the next item under the stores
+        const int next = item + gridDim.x;
+        if (next < num_items) {
+          mbar_wait(bar_fin, it & 1);
+          load_item(next);
         }
       }
     }
@@ -219,11 +241,18 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     const long long tok_stride = 3LL * H * kHd;
     uint8_t* ostg = smem + kOffOut + warp * 4096;
     const int wrow = (warp & 3) * 32;                 // first accumulator row of this warp
-    for (int step = 0; step < num_steps; ++step) {
+    int it = 0;
+    uint32_t gs = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    const int b = item / H, h = item - b * H;
+    const int kvlen = item_kvlen(item);
+    const int num_kt = (kvlen + 127) / 128;
+    const int num_steps = num_kt * 2;
+    for (int step = 0; step < num_steps; ++step, ++gs) {
       const int kt = step >> 1, qh = step & 1;
       const int key = kt * 128 + rowt;
       const bool key_ok = key < kvlen;
-      mbar_wait(bar_sd, step & 1);
+      mbar_wait(bar_sd, gs & 1);
       tc_fence_after();
       if (qh == 0 && kt > 0) {
         // dV / dK of the previous key tile are complete (their MMAs were queued ahead of this step's S^T / dP^T)
@@ -270,7 +299,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       mbar_arrive(bar_p);
     }
     // ---- tail: last key tile's dV / dK, then dQ
-    mbar_wait(bar_fin, 0);
+    mbar_wait(bar_fin, it & 1);
     tc_fence_after();
     {
       const int prow0 = (num_kt - 1) * 128 + wrow;
@@ -283,7 +312,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       store_tile64(ostg, tmem_row + (wg == 0 ? kColDQ0 : kColDQ1), wrow + 32 <= kQH ? &tm_out32 : &tm_out16, h * kHd, q0, b,
                    lane, q0 < N);
     }
-    if (lane == 0) tma_store_wait<0>();
+    tc_fence_before();
+    mbar_arrive(bar_tail);            // accumulators read: the issuer may start the next item's dV / dK / dQ MMAs
     // keys beyond kv_len (padding keys of a NaFlex batch) never entered a tile: their dK / dV are zero
     for (int key = num_kt * 128 + tid; key < N; key += kComputeThreads) {
       for (int which = 1; which <= 2; ++which) {
@@ -292,6 +322,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0u, 0u, 0u, 0u);
       }
     }
+    // the next item's softmax statistics (every compute thread is past its last use of this item's)
+    if (item + static_cast<int>(gridDim.x) < num_items) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      load_stats(item + gridDim.x, tid, kComputeThreads);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    }   // items
+    if (lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -336,7 +374,9 @@ int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const 
     B200_CUDA_OK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
-  attn_bwd2_kernel<<<dim3(H, B), kComputeThreads + 32, kSmemTotal, st>>>(tq, tdo, to32, to16, p);
+  int grid = sm_count();
+  if (grid > B * H) grid = B * H;
+  attn_bwd2_kernel<<<grid, kComputeThreads + 32, kSmemTotal, st>>>(tq, tdo, to32, to16, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

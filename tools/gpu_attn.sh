@@ -1,6 +1,5 @@
 #!/bin/bash
 cd /root/repo; mkdir -p gpurun_out
-for m in 0 4 6; do
-echo "== poly $m"; B200_ATTN_LONG_POLY=$m timeout 600 python tools/bench_model.py naflex:vit_large_patch14_clip_336 --batch 64 --steps 10 --warmup 3 --detail 2>&1 | grep -E "attention|img_per_s" | cut -c1-200
-done
-echo "== v1"; B200_ATTN_FWD_V1=1 timeout 600 python tools/bench_model.py naflex:vit_large_patch14_clip_336 --batch 64 --steps 10 --warmup 3 --detail 2>&1 | grep -E "attention|img_per_s" | cut -c1-200
+timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_train.py tests/test_gpu_rope.py -m gpu -x -q --no-header -p no:cacheprovider 2>&1 | tail -4
+timeout 300 python tools/train_detail.py 2>&1 | head -4
+timeout 600 python bench.py --mode train --steps 10 --warmup 3 2>&1 | tail -1 | cut -c80-220
