@@ -119,6 +119,17 @@ def install():
     """Rebind timm's hot-path forwards.  Idempotent.  Raises if timm or libb200timm.so is unavailable."""
     _lib.load()  # fail loudly: no silent PyTorch path when the CUDA library is missing
     import timm  # noqa: F401
+    if _ORIG:
+        return
+    table = _table()
+    for name, cls, attr, fn in table:
+        _ORIG[name] = getattr(cls, attr)
+        setattr(cls, attr, _dispatch(name, fn))
+        _ORIG[name + "#cls"] = (cls, attr)
+
+
+def _table():
+    """(qualified name, class, attribute, fast function) of every forward the plugin covers."""
     from timm.layers.attention import Attention, AttentionRope
     from timm.layers.mlp import Mlp
     from timm.layers.norm import LayerNorm
@@ -126,9 +137,7 @@ def install():
     from timm.models.convnext import ConvNeXt, ConvNeXtBlock
     from timm.models.eva import EvaAttention
     from timm.models.vision_transformer import Block, VisionTransformer
-    if _ORIG:
-        return
-    table = [
+    return [
         ("timm.layers.LayerNorm.forward", LayerNorm, "forward", lambda self, x: BF.layernorm(self, x)),
         ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
         ("timm.layers.Attention.forward", Attention, "forward", _attention),
@@ -147,10 +156,34 @@ def install():
         ("timm.models.convnext.ConvNeXt.forward_head", ConvNeXt, "forward_head", _convnext_head),
         ("timm.models.convnext.ConvNeXt.forward", ConvNeXt, "forward", _convnext_forward),
     ]
-    for name, cls, attr, fn in table:
-        _ORIG[name] = getattr(cls, attr)
-        setattr(cls, attr, _dispatch(name, fn))
-        _ORIG[name + "#cls"] = (cls, attr)
+
+
+def convert_to_b200(model):
+    """Post-construction conversion of ONE model (SURVEY 8b seam 2; the precedent is timm's convert_sync_batchnorm,
+    timm/layers/norm_act.py:167-208): every covered sub-module of `model` gets the B200 dispatcher bound on the
+    INSTANCE -- same Parameter objects, same state_dict keys, nothing re-parented, other models in the process
+    untouched.  Equivalent to install() for this model only; returns the model."""
+    import types
+    _lib.load()
+    table = _table()
+    for mod in model.modules():
+        for name, cls, attr, fn in table:
+            if type(mod) is cls:
+                orig = _ORIG.get(name, getattr(cls, attr))
+
+                def make(orig=orig, fn=fn):
+                    def forward(self, x, *args, **kwargs):
+                        if _fast(x):
+                            try:
+                                return fn(self, x, *args, **kwargs)
+                            except B200Error:
+                                if _STRICT:
+                                    raise
+                        return orig(self, x, *args, **kwargs)
+                    forward._b200_original = orig
+                    return forward
+                setattr(mod, attr, types.MethodType(make(), mod))
+    return model
 
 
 def uninstall():

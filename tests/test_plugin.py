@@ -89,3 +89,21 @@ def test_convnext_is_rebound_and_covered_configs_are_recognised(plugin):
     assert torch.equal(y_plugin, y_ref)
     ours = CN.create_model("convnext_tiny", num_classes=5)
     assert list(ours.state_dict()) == list(model.state_dict())
+
+
+def test_convert_to_b200_rebinds_one_model_only():
+    """Seam 2: instance-level conversion leaves classes and other models alone and keeps CPU calls on timm's path."""
+    from b200timm import plugin as P
+    P.uninstall()
+    from timm.models.vision_transformer import Block
+    a = timm.create_model("vit_tiny_patch16_224", num_classes=3, img_size=32).eval()
+    b = timm.create_model("vit_tiny_patch16_224", num_classes=3, img_size=32).eval()
+    keys = list(a.state_dict())
+    P.convert_to_b200(a)
+    assert hasattr(a.blocks[0].forward, "_b200_original") and hasattr(a.blocks[0].attn.forward, "_b200_original")
+    assert not hasattr(b.blocks[0].forward, "_b200_original") and not hasattr(Block.forward, "_b200_original")
+    assert list(a.state_dict()) == keys
+    x = torch.randn(2, 3, 32, 32)
+    b.load_state_dict(a.state_dict())
+    with torch.no_grad():
+        assert torch.equal(a(x), b(x))          # CPU fp32 input: the dispatcher defers to timm's forward
