@@ -35,19 +35,23 @@ def patch_conv(x, weight, bias):
     return linear(g, weight.reshape(weight.shape[0], -1), bias).permute(0, 3, 1, 2)
 
 
-def block(x, sd, pre, eps):
-    """ConvNeXtBlock.forward, timm/models/convnext.py:197-213 (conv_mlp=False)."""
+def block(x, sd, pre, eps, keep=None, keep_prob=1.0):
+    """ConvNeXtBlock.forward, timm/models/convnext.py:197-213 (conv_mlp=False).  keep: optional per-sample DropPath
+    keep mask [B] (1 = kept), applied as timm/layers/drop.py:158-175 does: branch * mask / keep_prob."""
     h = dwconv(x, sd[pre + "conv_dw.weight"], sd.get(pre + "conv_dw.bias")).permute(0, 2, 3, 1)      # :200,205
     h = layer_norm(h, sd[pre + "norm.weight"], sd[pre + "norm.bias"], eps)                             # :206
     h = linear(gelu_erf(linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])),
                sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"]).permute(0, 3, 1, 2)               # :207-208
     if pre + "gamma" in sd:
         h = h * sd[pre + "gamma"].view(1, -1, 1, 1)                                                    # :209-210
+    if keep is not None:
+        h = h * (keep.view(-1, 1, 1, 1) / keep_prob)                                                   # :213 drop_path
     return h + x                                                                                       # :212
 
 
-def convnext_forward_features(img, sd, cfg, return_stages=False):
-    """ConvNeXt.forward_features, timm/models/convnext.py:606-611."""
+def convnext_forward_features(img, sd, cfg, return_stages=False, keeps=None):
+    """ConvNeXt.forward_features, timm/models/convnext.py:606-611.  keeps: optional {block prefix: (mask [B], keep_prob)}
+    of DropPath draws (training mode)."""
     eps = cfg.get("eps", 1e-6)
     x = layer_norm2d(patch_conv(img, sd["stem.0.weight"], sd.get("stem.0.bias")), sd["stem.1.weight"], sd["stem.1.bias"], eps)
     outs = []
@@ -57,7 +61,8 @@ def convnext_forward_features(img, sd, cfg, return_stages=False):
             x = layer_norm2d(x, sd[pre + "downsample.0.weight"], sd[pre + "downsample.0.bias"], eps)
             x = patch_conv(x, sd[pre + "downsample.1.weight"], sd.get(pre + "downsample.1.bias"))
         for j in range(depth):
-            x = block(x, sd, f"{pre}blocks.{j}.", eps)
+            kp = (keeps or {}).get(f"{pre}blocks.{j}.")
+            x = block(x, sd, f"{pre}blocks.{j}.", eps, *(kp if kp is not None else ()))
         outs.append(x)
     return (x, outs) if return_stages else x
 

@@ -32,7 +32,7 @@ class _BlockFn(torch.autograd.Function):
     dx = dwconv(dy, spatially flipped weight) with the shortcut gradient folded in, dweight through the wgrad kernel."""
 
     @staticmethod
-    def forward(ctx, x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, B, H, W, eps):
+    def forward(ctx, x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, rs, B, H, W, eps):
         from .autograd import _c
         C = x.shape[1]
         k = wdw.shape[-1]
@@ -42,15 +42,16 @@ class _BlockFn(torch.autograd.Function):
         pre = torch.empty(x.shape[0], w1.shape[0], dtype=torch.bfloat16, device=x.device)
         act = ops.linear_fwd(h, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
         br = torch.empty_like(x) if gamma is not None else None
-        out = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=_c(x), gamma=gamma, out2=br)
-        ctx.save_for_backward(x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br)
+        out = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=_c(x), gamma=gamma, out2=br, row_scale=rs,
+                             rows_per_scale=H * W)
+        ctx.save_for_backward(x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br, rs)
         ctx.meta = (B, H, W, C, k)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         from .autograd import _c, _to_param_dtype
-        x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br = ctx.saved_tensors
+        x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br, rs = ctx.saved_tensors
         B, H, W, C, k = ctx.meta
         dout = _c(dout)
         params = (bdw, nw, nb, w1, b1, w2, b2, gamma)
@@ -63,9 +64,10 @@ class _BlockFn(torch.autograd.Function):
         v = [None if p is None else ws[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
         dwt = ws[kk_off:].view(k, k, C)
         dbr = dout
-        if gamma is not None:
-            ops.colsum_mul(dout, br, out=v[7], accumulate=True)
-            dbr = ops.scale_rows_cols(dout, gamma)
+        if gamma is not None or rs is not None:        # out = x + rs[sample] * gamma * branch  (DropPath, LayerScale)
+            if gamma is not None:
+                ops.colsum_mul(dout, br, rs, H * W, out=v[7], accumulate=True)
+            dbr = ops.scale_rows_cols(dout, gamma, rs, H * W)
         dpre = ops.linear_dgrad(dbr, w2, epilogue=ops.EPI_DGELU, aux=pre)
         ops.linear_wgrad(dbr, act, out=v[5])
         if b2 is not None:
@@ -88,7 +90,7 @@ class _BlockFn(torch.autograd.Function):
             grads = [None if p is None else gbuf[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
         g_wdw = dwt.reshape(k * k, C).t().reshape(C, 1, k, k).to(wdw.dtype)     # [k,k,C] -> Conv2d layout (49*C values)
         return (dx.view(B * H * W, C), g_wdw, grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7],
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 class _DownsampleFn(torch.autograd.Function):
@@ -185,9 +187,6 @@ def _check_block(blk):
             or type(blk.mlp.act).__name__ != "GELU" or getattr(blk.mlp.act, "approximate", "none") != "none"
             or type(blk.norm).__name__ not in ("LayerNorm",)):
         raise B200Error("ConvNeXtBlock: conv_mlp / GRN / strided / dilated / non-GELU blocks are not covered")
-    dp = getattr(blk, "drop_path", None)
-    if blk.training and getattr(dp, "drop_prob", 0.) > 0:
-        raise B200Error("ConvNeXt DropPath in training mode is not covered")
 
 
 def block_forward_nhwc(self, x, B, H, W):
@@ -195,15 +194,25 @@ def block_forward_nhwc(self, x, B, H, W):
     this mirror's ConvNeXtBlock or timm's own (the plugin rebinds timm's forward onto this function)."""
     C = x.shape[1]
     _check_block(self)
+    # DropPath (convnext.py:213, drop.py:158-175): the per-sample factor is drawn exactly as the reference draws it --
+    # bernoulli_(keep_prob) on B elements of the CUDA generator -- and applied inside the fc2 epilogue
+    rs = None
+    dp = getattr(self, "drop_path", None)
+    if self.training and getattr(dp, "drop_prob", 0.) > 0:
+        keep = 1.0 - dp.drop_prob
+        rs = x.new_empty((B, 1, 1, 1)).bernoulli_(keep).reshape(-1).float()
+        if keep > 0.0 and getattr(dp, "scale_by_keep", True):
+            rs = rs / keep
+        rs = rs.contiguous()
     if x.requires_grad or _needs_grad(self):
         return _BlockFn.apply(x, self.conv_dw.weight, self.conv_dw.bias, self.norm.weight, self.norm.bias,
                               self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
-                              self.gamma, B, H, W, self.norm.eps)
+                              self.gamma, rs, B, H, W, self.norm.eps)
     y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
     h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
     a = ops.linear_fwd(h, self.mlp.fc1.weight, self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
     return ops.linear_fwd(a, self.mlp.fc2.weight, self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
-                          gamma=self.gamma)
+                          gamma=self.gamma, row_scale=rs, rows_per_scale=H * W)
 
 
 class ConvNeXtStage(nn.Module):

@@ -135,3 +135,47 @@ def test_convnext_backward_matches_oracle_autograd():
         rel = (p.grad.float().cpu() - ref).norm().item() / denom
         cos = torch.nn.functional.cosine_similarity(p.grad.float().cpu().flatten(), ref.flatten(), dim=0).item()
         assert rel <= 5e-2 and cos >= 0.998, f"{n}: rel L2 err {rel:.4f}, cos {cos:.5f}"
+
+
+def test_convnext_droppath_training_matches_oracle():
+    """Stochastic depth in TRAIN mode (convnext.py:213): the per-sample keep masks come from the torch CUDA generator
+    exactly as timm/layers/drop.py:170-175 draws them (B Bernoulli draws per active block, in block order), so
+    re-seeding reproduces them for the oracle; loss and every parameter gradient must match its autograd."""
+    from oracle import convnext_oracle as C
+    from b200timm.convnext import ConvNeXt
+    cfg = dict(depths=(1, 1, 2, 1), dims=(32, 64, 128, 256))
+    sd = {k: v.bfloat16().float() for k, v in C.random_state_dict(cfg, seed=12, num_classes=16).items()}
+    for k in sd:
+        if k.endswith("gamma"):
+            sd[k] = torch.full_like(sd[k], 0.5)          # LayerScale large enough to matter
+    model = ConvNeXt(num_classes=16, drop_path_rate=0.4, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().to(torch.bfloat16).train()
+    B = 16
+    g = torch.Generator().manual_seed(9)
+    img = torch.randn(B, 3, 64, 64, generator=g).bfloat16()
+    target = torch.randint(0, 16, (B,), generator=g)
+    torch.manual_seed(4321)
+    loss = torch.nn.functional.cross_entropy(model(img.cuda()).float(), target.cuda())
+    loss.backward()
+    torch.manual_seed(4321)
+    keeps = {}
+    for i, stage in enumerate(model.stages):
+        for j, blk in enumerate(stage.blocks):
+            r = getattr(blk.drop_path, "drop_prob", 0.0)
+            if r > 0:
+                m = torch.empty((B, 1, 1, 1), device="cuda", dtype=torch.bfloat16).bernoulli_(1 - r).reshape(-1).float().cpu()
+                keeps[f"stages.{i}.blocks.{j}."] = (m, 1 - r)
+    assert any(0 < m.sum() < B for m, _ in keeps.values()), "test should exercise dropped and kept samples"
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    feats = C.convnext_forward_features(img.float(), ref_sd, cfg, keeps=keeps)
+    ref_loss = torch.nn.functional.cross_entropy(C.convnext_forward_head(feats, ref_sd, cfg), target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 3e-2, (loss.item(), ref_loss.item())
+    scale = max(v.grad.float().norm().item() for v in ref_sd.values())
+    for n, p in model.named_parameters():
+        ref = ref_sd[n].grad
+        if ref.norm().item() < 1e-3 * scale:
+            continue
+        rel = (p.grad.float().cpu() - ref).norm().item() / ref.norm().item()
+        assert rel <= 5e-2, f"{n}: rel L2 err {rel:.4f}"
