@@ -267,13 +267,15 @@ class BlockFn(torch.autograd.Function):
         if bqkv is not None:
             ops.colsum(dqkv, out=v[3], accumulate=True)
         dx0, _, _ = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dw_out=v[0], db_out=v[1])
-        pdt = next(p.dtype for p in params if p is not None)
-        if pdt == torch.float32:
+        # bf16 parameters (and the bf16 casts of fp32 master weights) take their gradient from one bf16 conversion of the
+        # whole workspace; fp32 parameters (AMP: biases, LayerNorm, LayerScale) take the fp32 views directly
+        if all(p is None or p.dtype == torch.float32 for p in params):
             grads = v
         else:
-            gbuf = torch.empty(offs[-1], dtype=pdt, device=dx2.device)
+            gbuf = torch.empty(offs[-1], dtype=torch.bfloat16, device=dx2.device)
             ops.convert_f32(ws, gbuf)
-            grads = [None if p is None else gbuf[o_:o_ + n].view(p.shape) for p, o_, n in zip(params, offs, sizes)]
+            grads = [None if p is None else (v[i] if p.dtype == torch.float32 else gbuf[o_:o_ + n].view(p.shape))
+                     for i, (p, o_, n) in enumerate(zip(params, offs, sizes))]
         return (dx0.view(B, N, D), *grads, None, None, None, None, None, None, None, None)
 
 

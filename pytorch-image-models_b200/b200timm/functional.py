@@ -110,10 +110,22 @@ def _bf16_2d(x, cols):
 
 
 def _w(linear):
+    """The bf16 GEMM operand of a Linear / Conv2d.  bf16 parameters (benchmark.py --precision bfloat16) are used as they
+    are.  fp32 parameters (train.py --amp: fp32 master weights under torch.autocast) are cast the way autocast casts
+    them: a differentiable `.to(bfloat16)` when the call is recorded for backward -- autograd widens the bf16 weight
+    gradient back to fp32 exactly as it does for an autocast F.linear -- and a cached cast otherwise."""
     w = linear.weight
-    if w.dtype != torch.bfloat16:
-        raise B200Error("weights must be bf16 (use model.to(torch.bfloat16), as benchmark.py --precision bfloat16 does)")
-    return w if w.is_contiguous() else w.contiguous()
+    if w.dtype == torch.bfloat16:
+        return w if w.is_contiguous() else w.contiguous()
+    if w.dtype != torch.float32:
+        raise B200Error(f"weights must be bf16 or fp32, got {w.dtype}")
+    if torch.is_grad_enabled() and w.requires_grad:
+        return w.to(torch.bfloat16)
+    key = (w.data_ptr(), w._version)
+    cache = getattr(linear, "_b200_wbf16", None)
+    if cache is None or cache[0] != key:
+        linear._b200_wbf16 = cache = (key, w.detach().to(torch.bfloat16).contiguous())
+    return cache[1]
 
 
 def _padded_out_linear(linear, x2):
@@ -126,7 +138,7 @@ def _padded_out_linear(linear, x2):
     key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
     cache = getattr(linear, "_b200_npad", None)
     if cache is None or cache[0] != key:
-        wp = torch.zeros(npad, K, dtype=w.dtype, device=w.device)
+        wp = torch.zeros(npad, K, dtype=torch.bfloat16, device=w.device)
         wp[:N] = w.detach()
         bp = None
         if b is not None:
@@ -286,8 +298,8 @@ def patch_embed_forward(pe, img):
     w = _w(pe.proj)
     if _needs_grad(None, pe):
         from .autograd import PatchEmbedFn
-        if img.dtype != torch.bfloat16:
-            raise B200Error("images must be bf16 on the fused path")
+        if img.dtype not in (torch.bfloat16, torch.float32):
+            raise B200Error("images must be bf16 or fp32 on the fused path")
         return PatchEmbedFn.apply(img, w, pe.proj.bias, ph)
     D = w.shape[0]
     K = C * ph * pw

@@ -24,9 +24,19 @@ _ORIG = {}
 _STRICT = os.environ.get("B200TIMM_STRICT", "0") == "1"
 
 
+def _autocast_bf16():
+    return torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+
+
 def _fast(x):
-    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.bfloat16 and not torch.jit.is_scripting()
-            and not torch.jit.is_tracing() and not (torch.is_grad_enabled() and _GRAD_UNSUPPORTED))
+    """CUDA bf16 activations -- or, under torch.autocast(bfloat16) (train.py --amp), fp32 IMAGES entering a rebound
+    model / patch embedding: the kernels read fp32 pixels directly and fp32 master weights are cast as autocast casts
+    them (functional._w)."""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda) or torch.jit.is_scripting() or torch.jit.is_tracing():
+        return False
+    if torch.is_grad_enabled() and _GRAD_UNSUPPORTED:
+        return False
+    return x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and x.dim() == 4 and _autocast_bf16())
 
 
 _GRAD_UNSUPPORTED = False  # the training path (b200timm.autograd) covers grad-enabled calls; uncovered configs raise B200Error -> timm

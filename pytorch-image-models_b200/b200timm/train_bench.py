@@ -22,7 +22,18 @@ def run(args, rank, world, dev):
     model = create_model(MODEL).to(dev).to(torch.bfloat16).train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=True)
+        # DDP as timm wraps it (timm/task/classification.py:64-65); B200_DDP_OPTS="bucket_view,cap=<MB>,static" switches on
+        # gradient_as_bucket_view / a larger bucket_cap_mb / static_graph for experiments
+        import os
+        kw = {}
+        for tok in filter(None, os.environ.get("B200_DDP_OPTS", "").split(",")):
+            if tok == "bucket_view":
+                kw["gradient_as_bucket_view"] = True
+            elif tok == "static":
+                kw["static_graph"] = True
+            elif tok.startswith("cap="):
+                kw["bucket_cap_mb"] = int(tok[4:])
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=True, **kw)
     opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.9)
     B = args.batch
     xs = [torch.randn(B, 3, 224, 224, device=dev).to(torch.bfloat16) for _ in range(2)]

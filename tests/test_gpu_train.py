@@ -178,3 +178,39 @@ def test_droppath_semantics_match_reference_tests():
     kept1 = m1 & ~m2
     if kept1.any():
         torch.testing.assert_close(y_train[kept1].float(), x1_train[kept1], atol=6e-2, rtol=3e-2)
+
+
+def test_amp_fp32_master_weights_match_oracle():
+    """train.py --amp mode: fp32 parameters, fp32 images, torch.autocast(bfloat16).  Weights are cast to bf16 the way
+    autocast casts them (differentiable), biases / LayerNorm / tokens stay fp32 operands; every parameter receives an
+    fp32 gradient that matches the oracle's autograd on the bf16-rounded weights."""
+    from oracle import vit_oracle as O
+    from b200timm.vision_transformer import VisionTransformer
+    cfg = dict(img_size=64, patch_size=16, embed_dim=128, depth=2, num_heads=2)
+    sd = O.random_state_dict(cfg, seed=21, num_classes=10)
+    model = VisionTransformer(num_classes=10, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()                                   # parameters stay fp32
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(8, 3, 64, 64, generator=g)
+    target = torch.randint(0, 10, (8,), generator=g)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = model(img.cuda())
+        loss = torch.nn.functional.cross_entropy(out.float(), target.cuda())
+    assert out.dtype == torch.bfloat16
+    loss.backward()
+    assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in model.parameters())
+    # oracle: the same computation with the GEMM weights rounded to bf16 (what autocast feeds the GEMMs)
+    ref_sd = {}
+    for k, v in sd.items():
+        gemm_weight = k.endswith("weight") and v.dim() >= 2
+        ref_sd[k] = (v.bfloat16().float() if gemm_weight else v.clone()).requires_grad_(True)
+    ref_loss = torch.nn.functional.cross_entropy(O.vit_forward(img.bfloat16().float(), ref_sd, cfg), target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 2e-2, (loss.item(), ref_loss.item())
+    _check_grads(model, {k: v.grad for k, v in ref_sd.items()})
+    # eval under autocast takes the cached-cast path and agrees with the training-mode forward
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out2 = model(img.cuda())
+    assert (out2.float() - out.float()).abs().max().item() < 2e-2
