@@ -22,6 +22,9 @@ from ._lib import B200Error
 from .layers import DropPath, Mlp
 
 
+from .functional import _w  # noqa: E402  (bf16 GEMM operand of a Linear / Conv2d: bf16 params as is, fp32 params cast)
+
+
 def _needs_grad(module):
     return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
 
@@ -81,13 +84,15 @@ class _BlockFn(torch.autograd.Function):
         ops.dwconv_nhwc_wgrad(x.view(B, H, W, C), dyc.view(B, H, W, C), k, out=dwt)
         if bdw is not None:
             ops.colsum(dyc, out=v[0], accumulate=True)
-        pdt = w1.dtype
-        if pdt == torch.float32:
+        # bf16 parameters / bf16 casts of fp32 master weights: one bf16 conversion of the workspace; fp32 parameters
+        # (AMP: biases, LayerNorm, gamma): the fp32 views themselves
+        if all(p is None or p.dtype == torch.float32 for p in params):
             grads = v
         else:
-            gbuf = torch.empty(kk_off, dtype=pdt, device=dout.device)
+            gbuf = torch.empty(kk_off, dtype=torch.bfloat16, device=dout.device)
             ops.convert_f32(ws[:kk_off], gbuf)
-            grads = [None if p is None else gbuf[o:o + n].view(p.shape) for p, o, n in zip(params, offs, sizes)]
+            grads = [None if p is None else (v[i] if p.dtype == torch.float32 else gbuf[o:o + n].view(p.shape))
+                     for i, (p, o, n) in enumerate(zip(params, offs, sizes))]
         g_wdw = dwt.reshape(k * k, C).t().reshape(C, 1, k, k).to(wdw.dtype)     # [k,k,C] -> Conv2d layout (49*C values)
         return (dx.view(B * H * W, C), g_wdw, grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7],
                 None, None, None, None, None)
@@ -205,13 +210,13 @@ def block_forward_nhwc(self, x, B, H, W):
             rs = rs / keep
         rs = rs.contiguous()
     if x.requires_grad or _needs_grad(self):
-        return _BlockFn.apply(x, self.conv_dw.weight, self.conv_dw.bias, self.norm.weight, self.norm.bias,
-                              self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias,
+        return _BlockFn.apply(x, _w(self.conv_dw), self.conv_dw.bias, self.norm.weight, self.norm.bias,
+                              _w(self.mlp.fc1), self.mlp.fc1.bias, _w(self.mlp.fc2), self.mlp.fc2.bias,
                               self.gamma, rs, B, H, W, self.norm.eps)
     y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
     h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
-    a = ops.linear_fwd(h, self.mlp.fc1.weight, self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
-    return ops.linear_fwd(a, self.mlp.fc2.weight, self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
+    a = ops.linear_fwd(h, _w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    return ops.linear_fwd(a, _w(self.mlp.fc2), self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
                           gamma=self.gamma, row_scale=rs, rows_per_scale=H * W)
 
 
@@ -254,7 +259,7 @@ def stage_forward_nhwc(self, x, B, H, W):
                 or type(norm).__name__ != "LayerNorm2d" or H % p or W % p):
             raise B200Error("ConvNeXtStage: only LayerNorm2d + 1x1 / 2x2-stride-2 conv downsampling is covered")
         if x.requires_grad or _needs_grad(self.downsample):
-            x = _DownsampleFn.apply(x, norm.weight, norm.bias, conv.weight, conv.bias, B, H, W, norm.eps)
+            x = _DownsampleFn.apply(x, norm.weight, norm.bias, _w(conv), conv.bias, B, H, W, norm.eps)
             H, W = H // p, W // p
         else:
             h = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps)[0]
@@ -274,7 +279,7 @@ def _dw_weight_t(conv):
     key = (w.data_ptr(), w._version)
     cache = getattr(conv, "_b200_wt", None)
     if cache is None or cache[0] != key:
-        conv._b200_wt = (key, ops.dwconv_weight_t(w))
+        conv._b200_wt = (key, ops.dwconv_weight_t(w.detach().to(torch.bfloat16)))
         cache = conv._b200_wt
     return cache[1]
 
@@ -285,7 +290,7 @@ def _conv_weight_khwc(conv):
     key = (w.data_ptr(), w._version)
     cache = getattr(conv, "_b200_khwc", None)
     if cache is None or cache[0] != key:
-        conv._b200_khwc = (key, w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
+        conv._b200_khwc = (key, w.detach().to(torch.bfloat16).permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
         cache = conv._b200_khwc
     return cache[1]
 
@@ -320,7 +325,7 @@ def head_forward_nhwc(self, x, B, HW, pre_logits=False):
         h = LayerNormFn.apply(_AvgPoolFn.apply(x, B, HW), self.norm.weight, self.norm.bias, self.norm.eps)
         if pre_logits or isinstance(self.fc, nn.Identity):
             return h
-        return LinearFn.apply(h, self.fc.weight, self.fc.bias)
+        return LinearFn.apply(h, _w(self.fc), self.fc.bias)
     pooled = ops.avgpool_nhwc(x.view(B, HW, -1))
     h = ops.layernorm_fwd(pooled, self.norm.weight, self.norm.bias, self.norm.eps)[0]
     if pre_logits or isinstance(self.fc, nn.Identity):
@@ -328,7 +333,7 @@ def head_forward_nhwc(self, x, B, HW, pre_logits=False):
     from .functional import _padded_out_linear
     if self.fc.weight.shape[0] % 8:
         return _padded_out_linear(self.fc, h)
-    return ops.linear_fwd(h, self.fc.weight, self.fc.bias)
+    return ops.linear_fwd(h, _w(self.fc), self.fc.bias)
 
 
 class ConvNeXt(nn.Module):
@@ -403,8 +408,8 @@ def features_nhwc(self, img):
     """stem -> stages (convnext.py:606-611) on channels-last rows; `self` is this mirror's ConvNeXt or timm's."""
     if not img.is_cuda:
         raise B200Error("libb200timm kernels need CUDA tensors (there is no CPU path)")
-    if img.dtype != torch.bfloat16 or self.stem[0].weight.dtype != torch.bfloat16:
-        raise B200Error("ConvNeXt B200 path needs bf16 inputs and weights (model.to(torch.bfloat16))")
+    if img.dtype not in (torch.bfloat16, torch.float32):
+        raise B200Error("ConvNeXt B200 path needs bf16 (or, under autocast with fp32 master weights, fp32) images")
     if (len(self.stem) != 2 or not isinstance(self.stem[0], nn.Conv2d) or type(self.stem[1]).__name__ != "LayerNorm2d"
             or not isinstance(getattr(self, "norm_pre", nn.Identity()), nn.Identity)):
         raise B200Error("ConvNeXt: only the patch stem (conv + LayerNorm2d) without norm_pre is covered")
@@ -417,12 +422,13 @@ def features_nhwc(self, img):
         raise B200Error("image size must be divisible by the stem patch size")
     K = C * p * p
     kpad = (K + 7) // 8 * 8
-    w2 = conv.weight.view(conv.weight.shape[0], K)
+    wc = _w(conv)
+    w2 = wc.view(wc.shape[0], K)
     if kpad != K:
         raise B200Error("stem patch size with C*p*p not a multiple of 8 is not covered")
     if _needs_grad(self.stem):
         from .autograd import LayerNormFn, PatchEmbedFn
-        x = PatchEmbedFn.apply(img, conv.weight, conv.bias, p).reshape(B * (H // p) * (W // p), -1)
+        x = PatchEmbedFn.apply(img, wc, conv.bias, p).reshape(B * (H // p) * (W // p), -1)
         x = LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
     else:
         x = ops.gemm(ops.patchify(img.contiguous(), p, kpad), w2, B * (H // p) * (W // p), w2.shape[0], kpad,

@@ -179,3 +179,37 @@ def test_convnext_droppath_training_matches_oracle():
             continue
         rel = (p.grad.float().cpu() - ref).norm().item() / ref.norm().item()
         assert rel <= 5e-2, f"{n}: rel L2 err {rel:.4f}"
+
+
+def test_convnext_amp_fp32_master_weights():
+    """train.py --amp mode on ConvNeXt: fp32 parameters + fp32 images under torch.autocast(bfloat16); fp32 gradients for
+    every parameter, matching the oracle evaluated on the bf16-rounded GEMM / conv weights."""
+    from oracle import convnext_oracle as C
+    from b200timm.convnext import ConvNeXt
+    cfg = dict(depths=(1, 1, 2, 1), dims=(32, 64, 128, 256))
+    sd = C.random_state_dict(cfg, seed=14, num_classes=16)
+    model = ConvNeXt(num_classes=16, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(4, 3, 64, 64, generator=g)
+    target = torch.randint(0, 16, (4,), generator=g)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = torch.nn.functional.cross_entropy(model(img.cuda()).float(), target.cuda())
+    loss.backward()
+    assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in model.parameters())
+    ref_sd = {k: ((v.bfloat16().float() if (k.endswith("weight") and v.dim() >= 2) else v.clone())).requires_grad_(True)
+              for k, v in sd.items()}
+    ref_loss = torch.nn.functional.cross_entropy(C.convnext_forward(img.bfloat16().float(), ref_sd, cfg), target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 3e-2, (loss.item(), ref_loss.item())
+    scale = max(v.grad.float().norm().item() for v in ref_sd.values())
+    for n, p in model.named_parameters():
+        ref = ref_sd[n].grad
+        if ref.norm().item() < 1e-3 * scale:
+            continue
+        rel = (p.grad.cpu() - ref).norm().item() / ref.norm().item()
+        assert rel <= 5e-2, f"{n}: rel L2 err {rel:.4f}"
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        assert torch.isfinite(model(img.cuda()).float()).all()
