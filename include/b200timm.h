@@ -120,6 +120,16 @@ B200_API int b200_layernorm_bwd(const void* dy, const void* x, const void* weigh
                        int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
                        int32_t param_dtype, void* stream);
 
+/* RMSNorm over the last dimension: y = x * rsqrt(mean(x^2) + eps) * weight.  Replaces rms_norm / RmsNorm.forward at
+ * timm/layers/fast_norm.py:119-139, timm/layers/norm.py:202-248 (the LayerNorm kernels with the mean pinned to zero
+ * and no bias).  rstd (fp32 [rows]) may be NULL in inference; the backward mirrors b200_layernorm_bwd (workspace of
+ * b200_layernorm_bwd_ws_rows(rows, cols) * 2 * cols floats; dres = gradient of a residual branch around the norm). */
+B200_API int b200_rmsnorm_fwd(const void* x, const void* weight, void* y, float* rstd, int64_t rows, int32_t cols, float eps,
+                              int32_t x_dtype, int32_t y_dtype, int32_t param_dtype, void* stream);
+B200_API int b200_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const float* rstd, const void* dres, void* dx,
+                              float* dweight, float* workspace, int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
+                              int32_t param_dtype, void* stream);
+
 /* ------------------------------------------------------------------ attention   timm/layers/attention.py:115-135
  * qkv: bf16 [B, N, 3, H, hd] (the QKV linear's output, viewed exactly as attention.py:115 reshapes it);
  * out: bf16 [B, N, H*hd] (== x.transpose(1,2).reshape(B,N,C) of attention.py:135);

@@ -209,10 +209,18 @@ def rope_cases():
     print("rope fixture written", tuple(emb.shape))
 
 
+# RmsNorm blocks / final norm (timm/layers/norm.py:202-248), the norm_layer string create_norm._NORM_MAP resolves
+RMS_KWARGS = dict(img_size=48, patch_size=16, in_chans=3, num_classes=6, embed_dim=128, depth=2, num_heads=2, qkv_bias=True,
+                  norm_layer="rmsnorm")
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "rope":
         os.makedirs(OUT, exist_ok=True)
         return rope_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "rmsnorm":
+        os.makedirs(OUT, exist_ok=True)
+        return vit_case("vit_g4_rmsnorm", 5, 2, RMS_KWARGS)
     os.makedirs(OUT, exist_ok=True)
     base = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=2, num_heads=2,
                 mlp_ratio=4.0, qkv_bias=True)
@@ -227,6 +235,7 @@ def main():
     naflex_case("naflex_g1", 4, 5)
     layer_cases()
     rope_cases()
+    vit_case("vit_g4_rmsnorm", 5, 2, RMS_KWARGS)
 
 
 if __name__ == "__main__":

@@ -32,6 +32,20 @@ def layer_norm(x, weight, bias, eps):
     return y
 
 
+def rms_norm(x, weight, eps):
+    """timm/layers/fast_norm.py:119-139 (rms_norm; RmsNorm.forward norm.py:241-248): x * rsqrt(mean(x^2) + eps) * w."""
+    v = (x * x).mean(-1, keepdim=True)
+    y = x * torch.rsqrt(v + eps)
+    return y if weight is None else y * weight
+
+
+def norm(x, sd, prefix, eps):
+    """LayerNorm, or RMSNorm when the state dict holds no bias for this norm (timm's RmsNorm has only `weight`)."""
+    if prefix + "bias" in sd:
+        return layer_norm(x, sd[prefix + "weight"], sd[prefix + "bias"], eps)
+    return rms_norm(x, sd[prefix + "weight"], eps)
+
+
 def gelu_erf(x):
     """nn.GELU() default (exact erf form), timm/layers/mlp.py:24,49."""
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
@@ -137,14 +151,14 @@ def patch_embed(img, weight, bias, patch):
 def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, keep_prob=1.0):
     """timm/models/vision_transformer.py:206-214 (Block.forward)."""
     g = lambda k: sd.get(prefix + k)  # noqa: E731
-    h = attention(layer_norm(x, g("norm1.weight"), g("norm1.bias"), eps), g("attn.qkv.weight"), g("attn.qkv.bias"),
+    h = attention(norm(x, sd, prefix + "norm1.", eps), g("attn.qkv.weight"), g("attn.qkv.bias"),
                   g("attn.proj.weight"), g("attn.proj.bias"), num_heads, kv_len)
     if g("ls1.gamma") is not None:
         h = h * g("ls1.gamma")                                   # timm/layers/layer_scale.py:26-27
     if keep1 is not None:
         h = drop_path(h, keep1, keep_prob)
     x = x + h
-    h = mlp(layer_norm(x, g("norm2.weight"), g("norm2.bias"), eps), g("mlp.fc1.weight"), g("mlp.fc1.bias"),
+    h = mlp(norm(x, sd, prefix + "norm2.", eps), g("mlp.fc1.weight"), g("mlp.fc1.bias"),
             g("mlp.fc2.weight"), g("mlp.fc2.bias"))
     if g("ls2.gamma") is not None:
         h = h * g("ls2.gamma")
@@ -173,13 +187,13 @@ def vit_forward_features(img, sd, cfg, kv_len=None, return_blocks=False):
         if pos is not None:
             x = x + pos
     if "norm_pre.weight" in sd:
-        x = layer_norm(x, sd["norm_pre.weight"], sd["norm_pre.bias"], eps)
+        x = norm(x, sd, "norm_pre.", eps)
     outs = []
     for i in range(cfg["depth"]):
         x = block(x, sd, f"blocks.{i}.", cfg["num_heads"], eps, kv_len)
         outs.append(x)
     if "norm.weight" in sd:
-        x = layer_norm(x, sd["norm.weight"], sd["norm.bias"], eps)
+        x = norm(x, sd, "norm.", eps)
     return (x, outs) if return_blocks else x
 
 
@@ -194,7 +208,7 @@ def vit_forward_head(x, sd, cfg):
     elif pool:
         raise ValueError(f"oracle: pool {pool!r} not restated")
     if "fc_norm.weight" in sd:
-        x = layer_norm(x, sd["fc_norm.weight"], sd["fc_norm.bias"], cfg.get("eps", 1e-6))
+        x = norm(x, sd, "fc_norm.", cfg.get("eps", 1e-6))
     if "head.weight" in sd:
         x = linear(x, sd["head.weight"], sd.get("head.bias"))
     return x
@@ -250,6 +264,16 @@ def random_state_dict(cfg, seed=0, num_classes=1000, dtype=torch.float32):
 
 
 # ----------------------------------------------------------------------------------------------- timing port
+def _eager_norm(x, sd, prefix, eps):
+    """The torch library call timm's norm layer makes: F.layer_norm (norm.py:85-90) or, for RmsNorm (no bias in the state
+    dict), the pow / mean / rsqrt / mul sequence of fast_norm.py:126-139."""
+    import torch.nn.functional as F
+    if prefix + "bias" in sd:
+        return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], eps)
+    v = torch.mean(x.pow(2), dim=(-1,), keepdim=True)
+    return x * torch.rsqrt(v + eps) * sd[prefix + "weight"]
+
+
 def vit_forward_eager(img, sd, cfg, kv_len=None):
     """Same computation as vit_forward, issued as the reference issues it on the CPU -- F.conv2d,
     F.layer_norm, F.linear, F.scaled_dot_product_attention, F.gelu (the call sites listed in SURVEY.md 8c) --
@@ -272,14 +296,14 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
         x = x + pos if pos is not None else x
     D = x.shape[-1]
     if "norm_pre.weight" in sd:
-        x = F.layer_norm(x, (D,), sd["norm_pre.weight"], sd["norm_pre.bias"], eps)
+        x = _eager_norm(x, sd, "norm_pre.", eps)
     mask = None
     if kv_len is not None:
         N = x.shape[1]
         mask = (torch.arange(N)[None, :] < kv_len[:, None])[:, None, None, :]
     for i in range(cfg["depth"]):
         p = f"blocks.{i}."
-        h = F.layer_norm(x, (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+        h = _eager_norm(x, sd, p + "norm1.", eps)
         N = h.shape[1]
         qkv = F.linear(h, sd[p + "attn.qkv.weight"], sd.get(p + "attn.qkv.bias")).reshape(B, N, 3, H, D // H)
         q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
@@ -288,21 +312,21 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
         if p + "ls1.gamma" in sd:
             h = h * sd[p + "ls1.gamma"]
         x = x + h
-        h = F.layer_norm(x, (D,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+        h = _eager_norm(x, sd, p + "norm2.", eps)
         h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd.get(p + "mlp.fc1.bias")))
         h = F.linear(h, sd[p + "mlp.fc2.weight"], sd.get(p + "mlp.fc2.bias"))
         if p + "ls2.gamma" in sd:
             h = h * sd[p + "ls2.gamma"]
         x = x + h
     if "norm.weight" in sd:
-        x = F.layer_norm(x, (D,), sd["norm.weight"], sd["norm.bias"], eps)
+        x = _eager_norm(x, sd, "norm.", eps)
     pool = cfg.get("global_pool", "token")
     if pool == "token":
         x = x[:, 0]
     elif pool == "avg":
         x = x[:, cfg.get("num_prefix_tokens", 1):].mean(1)
     if "fc_norm.weight" in sd:
-        x = F.layer_norm(x, (D,), sd["fc_norm.weight"], sd["fc_norm.bias"], eps)
+        x = _eager_norm(x, sd, "fc_norm.", eps)
     if "head.weight" in sd:
         x = F.linear(x, sd["head.weight"], sd.get("head.bias"))
     return x

@@ -39,8 +39,10 @@ def _needs_grad(x, *modules):
 def _ln_params(norm):
     if _is_identity(norm):
         return None
+    if type(norm).__name__ == "RmsNorm":     # this mirror's or timm's (timm/layers/norm.py:202-248)
+        return norm.weight, None, ops.RmsEps(norm.eps)
     if not isinstance(norm, nn.LayerNorm):
-        raise B200Error(f"unsupported norm layer {type(norm).__name__} (LayerNorm only)")
+        raise B200Error(f"unsupported norm layer {type(norm).__name__} (LayerNorm / RmsNorm only)")
     return norm.weight, norm.bias, norm.eps
 
 

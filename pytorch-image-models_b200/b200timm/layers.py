@@ -85,6 +85,23 @@ class Mlp(nn.Module):
         return BF.mlp_forward(self, x)
 
 
+class RmsNorm(nn.Module):
+    """timm.layers.RmsNorm (norm.py:202-248): y = x * rsqrt(mean(x^2) + eps) * weight."""
+
+    def __init__(self, channels: int, eps: float = 1e-6, affine: bool = True, device=None, dtype=None):
+        super().__init__()
+        self.normalized_shape = (channels,)
+        self.eps = eps
+        self.elementwise_affine = affine
+        if affine:
+            self.weight = nn.Parameter(torch.ones(channels, device=device, dtype=dtype))
+        else:
+            self.register_parameter("weight", None)
+
+    def forward(self, x):
+        return BF.layernorm(self, x)
+
+
 class Attention(nn.Module):
     """timm.layers.Attention (attention.py:43-139)."""
 

@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk",
+    "avgpool_nhwc", "naflex_assemble", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
 ]
 
 
@@ -86,9 +86,20 @@ def _param_dtype(*ps):
 
 
 # --------------------------------------------------------------------------------------------- LayerNorm
+class RmsEps(float):
+    """An eps that marks RMS mode: layernorm_fwd(x, w, None, RmsEps(1e-6)) computes x * rsqrt(mean(x^2) + eps) * w
+    (timm RmsNorm) and returns mean = None, which in turn makes layernorm_bwd take the RMS backward.  Carrying the mode
+    on the eps keeps every fused call site (BlockFn, LayerNormFn, ...) mode-agnostic."""
+
+
 def layernorm_fwd(x, weight, bias, eps, out_dtype=None, save_stats=False):
-    """y = LayerNorm(x) over the last dim.  Returns (y, mean, rstd) (stats are None unless save_stats)."""
+    """y = LayerNorm(x) (or RMSNorm(x) when eps is an RmsEps) over the last dim.  Returns (y, mean, rstd); stats are None
+    unless save_stats, mean is always None in RMS mode."""
     _need_cuda(x, weight, bias)
+    if isinstance(eps, RmsEps):
+        if bias is not None:
+            raise B200Error("RMSNorm has no bias")
+        return _rmsnorm_fwd(x, weight, eps, out_dtype, save_stats)
     cols = x.shape[-1]
     x2 = x.reshape(-1, cols)
     if not x2.is_contiguous():
@@ -107,10 +118,26 @@ def layernorm_fwd(x, weight, bias, eps, out_dtype=None, save_stats=False):
     return y.view(*x.shape[:-1], cols), mean, rstd
 
 
+def _rmsnorm_fwd(x, weight, eps, out_dtype, save_stats):
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    y = torch.empty(x2.shape, dtype=out_dtype or x.dtype, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rc = _lib.load().b200_rmsnorm_fwd(x2.data_ptr(), _ptr(weight), y.data_ptr(), _ptr(rstd), rows, cols, float(eps), _dt(x2),
+                                      _dt(y), _param_dtype(weight), _stream())
+    _lib.check(rc, "b200_rmsnorm_fwd")
+    _count()
+    return y.view(*x.shape[:-1], cols), None, rstd
+
+
 def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True, dres=None, dw_out=None, db_out=None):
     """Returns (dx, dweight fp32, dbias fp32).  dres (dtype/shape of x): gradient of the residual branch around
-    the norm, added into dx in the same pass."""
+    the norm, added into dx in the same pass.  mean = None selects the RMSNorm backward (dbias is None then)."""
     _need_cuda(dy, x, weight, mean, rstd, dres)
+    rms = mean is None
     cols = x.shape[-1]
     x2 = x.reshape(-1, cols)
     dy2 = dy.reshape(-1, cols)
@@ -126,16 +153,20 @@ def layernorm_bwd(dy, x, weight, mean, rstd, need_param_grads=True, dres=None, d
     dw = db = None
     if need_param_grads:
         dw = dw_out if dw_out is not None else torch.empty(cols, dtype=torch.float32, device=x.device)
-        db = db_out if db_out is not None else torch.empty(cols, dtype=torch.float32, device=x.device)
+        db = None if rms else (db_out if db_out is not None else torch.empty(cols, dtype=torch.float32, device=x.device))
     if dres is not None:
         dres = dres.reshape(-1, cols)
         if dres.dtype != x2.dtype or dres.shape != x2.shape:
             raise B200Error("layernorm_bwd: dres must match x in dtype and shape")
         if not dres.is_contiguous():
             dres = dres.contiguous()
-    rc = lib.b200_layernorm_bwd(dy2.data_ptr(), x2.data_ptr(), _ptr(weight), mean.data_ptr(), rstd.data_ptr(),
-                                _ptr(dres), dx.data_ptr(), _ptr(dw), _ptr(db), ws.data_ptr(), rows, cols, _dt(x2), _dt(dy2),
-                                _param_dtype(weight), _stream())
+    if rms:
+        rc = lib.b200_rmsnorm_bwd(dy2.data_ptr(), x2.data_ptr(), _ptr(weight), rstd.data_ptr(), _ptr(dres), dx.data_ptr(),
+                                  _ptr(dw), ws.data_ptr(), rows, cols, _dt(x2), _dt(dy2), _param_dtype(weight), _stream())
+    else:
+        rc = lib.b200_layernorm_bwd(dy2.data_ptr(), x2.data_ptr(), _ptr(weight), mean.data_ptr(), rstd.data_ptr(),
+                                    _ptr(dres), dx.data_ptr(), _ptr(dw), _ptr(db), ws.data_ptr(), rows, cols, _dt(x2), _dt(dy2),
+                                    _param_dtype(weight), _stream())
     _lib.check(rc, "b200_layernorm_bwd")
     _count(2 if need_param_grads else 1)
     return dx.view(x.shape), dw, db

@@ -142,13 +142,14 @@ def _table():
     """(qualified name, class, attribute, fast function) of every forward the plugin covers."""
     from timm.layers.attention import Attention, AttentionRope
     from timm.layers.mlp import Mlp
-    from timm.layers.norm import LayerNorm
+    from timm.layers.norm import LayerNorm, RmsNorm
     from timm.layers.patch_embed import PatchEmbed
     from timm.models.convnext import ConvNeXt, ConvNeXtBlock
     from timm.models.eva import EvaAttention
     from timm.models.vision_transformer import Block, VisionTransformer
     return [
         ("timm.layers.LayerNorm.forward", LayerNorm, "forward", lambda self, x: BF.layernorm(self, x)),
+        ("timm.layers.RmsNorm.forward", RmsNorm, "forward", lambda self, x: BF.layernorm(self, x)),
         ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
         ("timm.layers.Attention.forward", Attention, "forward", _attention),
         ("timm.layers.AttentionRope.forward", AttentionRope, "forward", _attention_rope),

@@ -79,6 +79,12 @@ class VisionTransformer(nn.Module):
         if dynamic_img_size or dynamic_img_pad or patch_drop_rate > 0 or embed_norm_layer is not None:
             raise B200Error("dynamic_img_size / dynamic_img_pad / patch dropout / embed norm are not supported")
         use_fc_norm = global_pool == "avg" if fc_norm is None else fc_norm
+        if isinstance(norm_layer, str):       # create_norm._NORM_MAP keys (timm/layers/create_norm.py:31-50)
+            from .layers import RmsNorm
+            known = {"layernorm": LayerNorm, "rmsnorm": RmsNorm}
+            if norm_layer not in known:
+                raise B200Error(f"norm_layer {norm_layer!r} is not covered (layernorm, rmsnorm)")
+            norm_layer = known[norm_layer]
         norm_layer = norm_layer or LayerNorm
         act_layer = act_layer or nn.GELU
         self.num_classes = num_classes

@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ w, const void* __restrict__ b,
                      void* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      long long rows, int cols, float eps, int param_f32) {
+  // param_f32: bit 0 = fp32 parameters, bit 1 = RMS mode (timm RmsNorm, norm.py:202-248 / fast_norm.py:119-139:
+  // y = x * rsqrt(mean(x^2) + eps) * w -- the same kernel with the mean pinned to zero and no bias)
+  const bool rms = (param_f32 & 2) != 0;
+  param_f32 &= 1;
   const int lane = threadIdx.x & 31;
   const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   const long long warp_stride = static_cast<long long>(gridDim.x) * kLnWarps;
@@ -69,7 +73,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ w, con
         for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
       }
     }
-    const float mean = warp_sum(s) * inv_n;
+    const float mean = rms ? 0.f : warp_sum(s) * inv_n;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -118,6 +122,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
                      const void* __restrict__ dres, void* __restrict__ dx,
                      float* __restrict__ ws, long long rows, int cols, int param_f32) {
   extern __shared__ float red[];  // [kLnWarps][2*cols]
+  const bool rms = (param_f32 & 2) != 0;   // see layernorm_fwd_kernel
+  param_f32 &= 1;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
@@ -131,7 +137,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
     for (int j = 0; j < 8; ++j) { dw_acc[i][j] = 0.f; db_acc[i][j] = 0.f; }
 
   for (long long row = warp_global; row < rows; row += warp_stride) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float mean = rms ? 0.f : mean_in[row], rstd = rstd_in[row];
     // pass 1: row statistics of g = dy * w and the dgamma / dbeta partial sums.  x / dy are NOT kept in registers
     // (that is what capped the kernel at 8 warps per SM): pass 2 re-reads them, and those reads hit L1.
     float s1 = 0.f, s2 = 0.f;
@@ -154,7 +160,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
         }
       }
     }
-    const float m1 = warp_sum(s1) * inv_n;
+    const float m1 = rms ? 0.f : warp_sum(s1) * inv_n;     // RMS mode: no mean was subtracted in the forward
     const float m2 = warp_sum(s2) * inv_n;
     // pass 2: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ residual-branch gradient)
 #pragma unroll
@@ -218,6 +224,8 @@ layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
                           __nv_bfloat16* __restrict__ dx, float* __restrict__ ws, long long rows, int cols,
                           int param_f32) {
   extern __shared__ float red[];  // [kLnWarps][2*cols]
+  const bool rms = (param_f32 & 2) != 0;   // see layernorm_fwd_kernel
+  param_f32 &= 1;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
@@ -242,7 +250,7 @@ layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
         if (dres != nullptr) rr[i] = *reinterpret_cast<const uint4*>(dres + base + vec * 8);
       }
     }
-    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float mean = rms ? 0.f : mean_in[row], rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -263,7 +271,7 @@ layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
         }
       }
     }
-    const float m1 = warp_sum(s1) * inv_n;
+    const float m1 = rms ? 0.f : warp_sum(s1) * inv_n;     // RMS mode: no mean was subtracted in the forward
     const float m2 = warp_sum(s2) * inv_n;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -390,9 +398,8 @@ static int launch_bwd(const void* dy, const void* x, const void* w, const float*
 
 using namespace b200;
 
-extern "C" int b200_layernorm_fwd(const void* x, const void* weight, const void* bias, void* y, float* mean,
-                                  float* rstd, int64_t rows, int32_t cols, float eps, int32_t x_dtype,
-                                  int32_t y_dtype, int32_t param_dtype, void* stream_) {
+static int norm_fwd(const void* x, const void* weight, const void* bias, void* y, float* mean, float* rstd, int64_t rows,
+                    int32_t cols, float eps, int32_t x_dtype, int32_t y_dtype, int32_t param_dtype, int rms, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(x && y, "b200_layernorm_fwd: null x/y");
   B200_CHECK_ARG(rows >= 0 && cols > 0, "b200_layernorm_fwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
@@ -400,7 +407,8 @@ extern "C" int b200_layernorm_fwd(const void* x, const void* weight, const void*
     return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_fwd: cols=%d must be a multiple of 8 and <= 2048", cols);
   if (rows == 0) return B200_OK;
   const int vpl = (cols + 255) / 256;
-  const int xf = x_dtype == B200_DTYPE_F32, yf = y_dtype == B200_DTYPE_F32, pf = param_dtype == B200_DTYPE_F32;
+  const int xf = x_dtype == B200_DTYPE_F32, yf = y_dtype == B200_DTYPE_F32;
+  const int pf = (param_dtype == B200_DTYPE_F32 ? 1 : 0) | (rms ? 2 : 0);
   switch (vpl) {
     case 1: launch_fwd<1>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
     case 2: launch_fwd<2>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
@@ -413,23 +421,33 @@ extern "C" int b200_layernorm_fwd(const void* x, const void* weight, const void*
   return B200_OK;
 }
 
+extern "C" int b200_layernorm_fwd(const void* x, const void* weight, const void* bias, void* y, float* mean,
+                                  float* rstd, int64_t rows, int32_t cols, float eps, int32_t x_dtype,
+                                  int32_t y_dtype, int32_t param_dtype, void* stream_) {
+  return norm_fwd(x, weight, bias, y, mean, rstd, rows, cols, eps, x_dtype, y_dtype, param_dtype, 0, stream_);
+}
+
+extern "C" int b200_rmsnorm_fwd(const void* x, const void* weight, void* y, float* rstd, int64_t rows, int32_t cols, float eps,
+                                int32_t x_dtype, int32_t y_dtype, int32_t param_dtype, void* stream_) {
+  return norm_fwd(x, weight, nullptr, y, nullptr, rstd, rows, cols, eps, x_dtype, y_dtype, param_dtype, 1, stream_);
+}
+
 extern "C" int b200_layernorm_bwd_ws_rows(int64_t rows, int32_t cols) {
   (void)cols;
   return ln_bwd_grid(rows > 0 ? rows : 1);
 }
 
-extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* weight, const float* mean,
-                                  const float* rstd, const void* dres, void* dx, float* dweight, float* dbias,
-                                  float* workspace,
-                                  int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
-                                  int32_t param_dtype, void* stream_) {
+static int norm_bwd(const void* dy, const void* x, const void* weight, const float* mean, const float* rstd, const void* dres,
+                    void* dx, float* dweight, float* dbias, float* workspace, int64_t rows, int32_t cols, int32_t x_dtype,
+                    int32_t dy_dtype, int32_t param_dtype, int rms, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  B200_CHECK_ARG(dy && x && mean && rstd && dx && workspace, "b200_layernorm_bwd: null pointer");
+  B200_CHECK_ARG(dy && x && (mean || rms) && rstd && dx && workspace, "b200_layernorm_bwd: null pointer");
   B200_CHECK_ARG(rows > 0 && cols > 0, "b200_layernorm_bwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
   if (cols % 8 != 0 || cols > 2048)
     return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_bwd: cols=%d must be a multiple of 8 and <= 2048", cols);
   const int vpl = (cols + 255) / 256;
-  const int xf = x_dtype == B200_DTYPE_F32, dyf = dy_dtype == B200_DTYPE_F32, pf = param_dtype == B200_DTYPE_F32;
+  const int xf = x_dtype == B200_DTYPE_F32, dyf = dy_dtype == B200_DTYPE_F32;
+  const int pf = (param_dtype == B200_DTYPE_F32 ? 1 : 0) | (rms ? 2 : 0);
   int rc;
   switch (vpl) {
     case 1: rc = launch_bwd<1>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;
@@ -447,4 +465,20 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* wei
     B200_CUDA_OK(cudaGetLastError());
   }
   return B200_OK;
+}
+
+extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* weight, const float* mean,
+                                  const float* rstd, const void* dres, void* dx, float* dweight, float* dbias,
+                                  float* workspace,
+                                  int64_t rows, int32_t cols, int32_t x_dtype, int32_t dy_dtype,
+                                  int32_t param_dtype, void* stream_) {
+  return norm_bwd(dy, x, weight, mean, rstd, dres, dx, dweight, dbias, workspace, rows, cols, x_dtype, dy_dtype, param_dtype, 0,
+                  stream_);
+}
+
+extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const float* rstd, const void* dres,
+                                void* dx, float* dweight, float* workspace, int64_t rows, int32_t cols, int32_t x_dtype,
+                                int32_t dy_dtype, int32_t param_dtype, void* stream_) {
+  return norm_bwd(dy, x, weight, nullptr, rstd, dres, dx, dweight, nullptr, workspace, rows, cols, x_dtype, dy_dtype, param_dtype,
+                  1, stream_);
 }

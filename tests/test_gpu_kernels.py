@@ -328,3 +328,27 @@ def test_layerscale_droppath_kernels():
     _close(ops.scale_rows_cols(dy, gamma, rs, N), dy.float() * gamma.float() * rows, 2e-2, 1e-2, "scale_rows_cols")
     _close(ops.scale_rows_cols(dy, None, rs, N), dy.float() * rows, 1e-2, 1e-2, "scale rows only")
     _close(ops.colsum_mul(dy, br, rs, N), (dy.float() * br.float() * rows).sum(0), 5e-2, 2e-3, "colsum_mul")
+
+
+@pytest.mark.parametrize("cols,pdt", [(768, torch.bfloat16), (192, torch.float32), (1024, torch.bfloat16)])
+def test_rmsnorm_fwd_bwd(cols, pdt):
+    """RMS mode of the norm kernels (timm RmsNorm, norm.py:202-248 / fast_norm.py:119-139) against fp32 autograd."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(cols)
+    rows = 333
+    x = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    w = (1 + 0.2 * torch.randn(cols, device=DEV, generator=g)).to(pdt)
+    dy = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    dres = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    eps = ops.RmsEps(1e-6)
+    y, mean, rstd = ops.layernorm_fwd(x, w, None, eps, save_stats=True)
+    assert mean is None and rstd is not None
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    yr = xr * torch.rsqrt((xr * xr).mean(-1, keepdim=True) + 1e-6) * wr
+    _close(y, yr.detach(), atol=2e-2, rtol=1e-2, what="rmsnorm fwd")
+    yr.backward(dy.float())
+    dx, dw, db = ops.layernorm_bwd(dy, x, w, None, rstd, dres=dres)
+    assert db is None
+    _close(dx, xr.grad + dres.float(), atol=4e-2, rtol=2e-2, what="rmsnorm dx (+ residual gradient)")
+    _close(dw, wr.grad, atol=0.25, rtol=2e-2, what="rmsnorm dweight")

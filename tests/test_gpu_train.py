@@ -214,3 +214,20 @@ def test_amp_fp32_master_weights_match_oracle():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         out2 = model(img.cuda())
     assert (out2.float() - out.float()).abs().max().item() < 2e-2
+
+
+def test_rmsnorm_vit_training_matches_reference_golden():
+    """A ViT built with norm_layer='rmsnorm' (RmsNorm blocks + final norm): forward against the reference's golden
+    logits, every parameter gradient against the reference's own gradients (outputs.mean().backward())."""
+    import os
+    from b200timm.vision_transformer import VisionTransformer
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vit_g4_rmsnorm.pt"))
+    sd = {k: v.bfloat16().float() for k, v in fx["state_dict"].items()}
+    model = VisionTransformer(**fx["kwargs"])
+    model.load_state_dict(sd, strict=True)
+    assert "blocks.0.norm1.bias" not in sd and type(model.blocks[0].norm1).__name__ == "RmsNorm"
+    model = model.cuda().to(torch.bfloat16).train()
+    out = model(fx["img"].bfloat16().cuda())
+    assert (out.float().cpu() - fx["logits"]).abs().max().item() <= 3e-2 + 3e-2 * fx["logits"].abs().max().item()
+    out.float().mean().backward()
+    _check_grads(model, fx["grads"], rel_tol=8e-2, min_cos=0.995)     # reference grads are for the un-rounded fp32 weights

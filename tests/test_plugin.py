@@ -21,9 +21,10 @@ def plugin():
 
 
 def test_install_rebinds_and_uninstall_restores(plugin):
-    from timm.layers import Attention, AttentionRope, LayerNorm, Mlp
+    from timm.layers import Attention, AttentionRope, LayerNorm, Mlp, RmsNorm
     from timm.models.vision_transformer import Block, VisionTransformer
     for cls, attr in ((Attention, "forward"), (AttentionRope, "forward"), (Mlp, "forward"), (LayerNorm, "forward"),
+                      (RmsNorm, "forward"),
                       (Block, "forward"),
                       (VisionTransformer, "forward_features"), (VisionTransformer, "forward")):
         assert hasattr(getattr(cls, attr), "_b200_original"), f"{cls.__name__}.{attr} not rebound"
