@@ -107,6 +107,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  griddep_launch();     // programmatic dependent launch (ptx.cuh): set-up above overlaps the QKV GEMM's tail
+  griddep_wait();
 
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
@@ -385,8 +387,7 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_l
   }
   int grid = sm_count();
   if (grid > p.num_items) grid = p.num_items;
-  kern<<<grid, kThreads, kSmemTotal, st>>>(tq, tkv, tout, p);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_pdl(kern, dim3(grid, 1, 1), dim3(kThreads, 1, 1), kSmemTotal, st, 1, tq, tkv, tout, p));
   return B200_OK;
 }
 

@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "common.h"
 
 #include <cstdarg>
@@ -132,6 +133,16 @@ static int encode_tmap_uncached(CUtensorMap* out, CUtensorMapDataType dt, const 
 }  // namespace b200
 
 extern "C" const char* b200_last_error(void) { return b200::g_err; }
+namespace b200 {
+bool pdl_enabled() {
+  // opt-in (B200_PDL=1): measured on B200 the overlap is real (tools/gap_probe.py: the next GEMM's CTAs enter 5.7 us
+  // BEFORE the previous GEMM's last CTA exits, instead of 3.8 us after) but the CUDA-graph replay of the whole forward
+  // got 2 % slower with programmatic edges, and eager launches were unchanged -- so the default stays off.
+  static const bool on = [] { const char* e = getenv("B200_PDL"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+}  // namespace b200
+
 extern "C" int b200_abi_version(void) { return 4; }
 
 extern "C" int b200_device_check(void) {

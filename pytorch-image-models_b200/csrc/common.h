@@ -28,6 +28,37 @@ int fail(int code, const char* fmt, ...);
 // Number of SMs of the current device (cached per device).
 int sm_count();
 
+// B200_PDL=1 switches programmatic dependent launch on (off by default, see pdl_enabled() in common.cu).
+bool pdl_enabled();
+
+// Launch `kern` with programmatic stream serialization (see griddep_wait in ptx.cuh) and, optionally, clusters of
+// `cluster` CTAs.  The kernel must call griddep_wait() before its first access to global memory.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Encode a tiled tensor map over a bf16 tensor of rank `rank` (dims[0] innermost, strides in BYTES for
 // dims 1..rank-1), swizzle = 0 (none) / 64 / anything else (128-byte), zero fill out of bounds.  Returns 0 or an error code.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

@@ -184,6 +184,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: the set-up above ran under the previous kernel's tail; from here on global memory
+  // written by it is read (operands, residual) or overwritten, so wait for it -- and let our own successor set up early
+  griddep_launch();
+  griddep_wait();
   if (trace && threadIdx.x == 0) trace[1] = gtime();
 
   // CTA2: tiles are 256-row pairs of m-blocks, walked by cluster; this CTA's m-block is 2 * pair + rank
@@ -662,15 +666,14 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
       max_clusters = n;
     }
     const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
-    cfg.gridDim = dim3(2 * clusters, 1, 1);
-    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, tout2, p));
+    B200_CUDA_OK(launch_pdl(kern, dim3(2 * clusters, 1, 1), dim3(kNumThreads, 1, 1), L::kTotal, stream, 2, ta, tb, tout, taux,
+                            tout2, p));
     return B200_OK;
   } else {
     const int num_tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
     int grid = sm_count();
     if (grid > num_tiles) grid = num_tiles;
-    kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, tout, taux, tout2, p);
-    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(launch_pdl(kern, dim3(grid, 1, 1), dim3(kNumThreads, 1, 1), L::kTotal, stream, 1, ta, tb, tout, taux, tout2, p));
     return B200_OK;
   }
 }

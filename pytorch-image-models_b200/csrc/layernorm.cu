@@ -53,6 +53,8 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ w, con
   // y = x * rsqrt(mean(x^2) + eps) * w -- the same kernel with the mean pinned to zero and no bias)
   const bool rms = (param_f32 & 2) != 0;
   param_f32 &= 1;
+  griddep_launch();     // programmatic dependent launch (ptx.cuh): only the launch latency overlaps here
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + (threadIdx.x >> 5);
   const long long warp_stride = static_cast<long long>(gridDim.x) * kLnWarps;
@@ -358,10 +360,12 @@ static void launch_fwd(const void* x, const void* w, const void* b, void* y, flo
                        int cols, float eps, int xf32, int yf32, int pf32, cudaStream_t st) {
   const int grid = ln_grid(rows);
   const int threads = kLnWarps * 32;
-  if (xf32 && yf32) layernorm_fwd_kernel<VPL, true, true><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
-  else if (xf32) layernorm_fwd_kernel<VPL, true, false><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
-  else if (yf32) layernorm_fwd_kernel<VPL, false, true><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
-  else layernorm_fwd_kernel<VPL, false, false><<<grid, threads, 0, st>>>(x, w, b, y, mean, rstd, rows, cols, eps, pf32);
+  const dim3 g(grid, 1, 1), t(threads, 1, 1);
+  const long long rows_ll = rows;
+  if (xf32 && yf32) launch_pdl(layernorm_fwd_kernel<VPL, true, true>, g, t, 0, st, 1, x, w, b, y, mean, rstd, rows_ll, cols, eps, pf32);
+  else if (xf32) launch_pdl(layernorm_fwd_kernel<VPL, true, false>, g, t, 0, st, 1, x, w, b, y, mean, rstd, rows_ll, cols, eps, pf32);
+  else if (yf32) launch_pdl(layernorm_fwd_kernel<VPL, false, true>, g, t, 0, st, 1, x, w, b, y, mean, rstd, rows_ll, cols, eps, pf32);
+  else launch_pdl(layernorm_fwd_kernel<VPL, false, false>, g, t, 0, st, 1, x, w, b, y, mean, rstd, rows_ll, cols, eps, pf32);
 }
 
 template <int VPL>

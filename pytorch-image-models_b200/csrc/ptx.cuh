@@ -49,6 +49,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor on the
+// stream is still draining: everything up to griddep_wait() (barrier init, TMEM allocation, descriptor prefetch)
+// overlaps the predecessor's tail; griddep_wait() returns once the predecessor grid has completed and its writes are
+// visible.  griddep_launch() lets THIS grid's successor be scheduled early in the same way.  Both are no-ops for a
+// kernel without a programmatic dependency.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
