@@ -24,7 +24,6 @@ def run(args, rank, world, dev):
     if world > 1:
         # DDP as timm wraps it (timm/task/classification.py:64-65); B200_DDP_OPTS="bucket_view,cap=<MB>,static" switches on
         # gradient_as_bucket_view / a larger bucket_cap_mb / static_graph for experiments
-        import os
         kw = {}
         for tok in filter(None, os.environ.get("B200_DDP_OPTS", "").split(",")):
             if tok == "bucket_view":
