@@ -1,14 +1,23 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  out[M,N] = epilogue(A[M,K] * B[N,K]^T)
 //
-//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, STAGES deep)
-//   warp 1      : MMA issuer     (one thread issues tcgen05.mma 128 x BN x 16, accumulators in TMEM,
-//                                 two accumulator stages so the epilogue overlaps the next tile)
+// Default mode -- CTA pairs (template CTA2): the grid is clusters of two CTAs on one TPC; a pair owns a 256 x 256
+// output tile.  Each CTA TMA-loads its own 128 rows of A and HALF of the B tile per k-block (32 KB instead of 48 KB
+// through L2 / TMA / shared memory -- single CTAs were L2->SM operand-bound), the leader issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both B halves, and each CTA's TMEM receives its 128 x 256 accumulator.
+// Single CTAs (128 x BN tiles) remain for M < 256 / N <= 128 and behind B200_GEMM_2CTA=0.
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, STAGES deep; in a pair both CTAs'
+//                                 bytes complete on the leader's mbarrier)
+//   warp 1      : MMA issuer     (one thread of the leader issues the MMAs; accumulators in TMEM, two accumulator
+//                                 stages so the epilogue overlaps the next tile; tcgen05.commit multicasts the
+//                                 "slot free" / "accumulator ready" arrivals to both CTAs)
 //   warp 2      : TMEM allocator / deallocator
-//   warps 4..19 : epilogue       (tcgen05.ld -> bias / GELU / residual+LayerScale / dGELU -> 128B-swizzled smem
-//                                 staging tile -> TMA store; the residual / pre-activation operand comes in
-//                                 through a TMA load into the same staging tile, so every global access of the
-//                                 epilogue is a full-line bulk copy; fp32 outputs accumulate / split-K through
-//                                 TMA reduce-add)
+//   warps 4..19 : epilogue       (tcgen05.ld -> bias / GELU / residual+LayerScale+DropPath / dGELU / RoPE -> swizzled
+//                                 smem staging tile -> TMA store, in rounds of RC columns; the residual /
+//                                 pre-activation operand comes in through a TMA load into the same staging tile, so
+//                                 every global access of the epilogue is a full-line bulk copy; fp32 outputs
+//                                 accumulate / split-K through TMA reduce-add; one remote mbarrier arrive per warp
+//                                 hands the accumulator back to the leader)
 //
 // Replaces F.linear (+ the separate GELU / residual / LayerScale ATen passes) of
 // timm/layers/attention.py:115,137, timm/layers/mlp.py:48-52, timm/models/vision_transformer.py:212-213.
