@@ -138,6 +138,10 @@ B200_API int b200_rmsnorm_bwd(const void* dy, const void* x, const void* weight,
  * mask of naflexvit.py:964-1029 given as lengths.  hd must be 64.                                    */
 B200_API int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* kv_len, int32_t B, int32_t N,
                   int32_t H, int32_t hd, float scale, void* stream);
+/* Floats of workspace b200_attn_bwd needs behind its `delta` argument: B*H*N for the row sums delta[b,h,q] = sum_d
+ * dO*O, plus -- for N > 208, where dQ is accumulated over key tiles in fp32 through TMA reduce-adds -- B*N*H*64. */
+B200_API int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H);
+
 /* Backward: dqkv bf16 [B,N,3,H,hd] from dout bf16 [B,N,H*hd]; recomputes P from qkv and lse.
  * delta: fp32 workspace [B,H,N].                                                                     */
 B200_API int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,

@@ -331,8 +331,9 @@ def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None):
     if lse.dtype != torch.float32 or not lse.is_contiguous() or lse.numel() != B * H * N:
         raise B200Error("attention_bwd: lse must be contiguous fp32 [B,H,N]")
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
-    rc = _lib.load().b200_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+    lib = _lib.load()
+    delta = torch.empty(lib.b200_attn_bwd_ws_floats(B, N, H), dtype=torch.float32, device=qkv.device)   # delta (+ fp32 dQ)
+    rc = lib.b200_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
                                    dqkv.data_ptr(), _ptr(kv_len), B, N, H, hd, float(scale), _stream())
     _lib.check(rc, "b200_attn_bwd")
     _count(2)

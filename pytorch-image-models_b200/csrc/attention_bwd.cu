@@ -371,7 +371,16 @@ int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const 
                      const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st);
 }
 
+namespace b200 {
+int launch_attn_bwd_long(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq32, void* dqkv,
+                         const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st);
+}
 using namespace b200;
+
+extern "C" int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H) {
+  const long long d = (static_cast<long long>(B) * H * N + 3) / 4 * 4;
+  return N > kNQ ? d + static_cast<long long>(B) * N * H * kHd : d;
+}
 
 extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                              void* dqkv, const int32_t* kv_len, int32_t B, int32_t N, int32_t H, int32_t hd,
@@ -380,13 +389,17 @@ extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout,
   B200_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "b200_attn_bwd: null pointer");
   B200_CHECK_ARG(B > 0 && N > 0 && H > 0 && B <= 65535, "b200_attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
   if (hd != kHd) return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: head_dim %d not supported (64 only)", hd);
-  if (N > kNQ) return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: N=%d tokens not supported yet (<= %d)", N, kNQ);
   {
     const long long rows = static_cast<long long>(B) * N;
     const int wpb = 8;
     attn_bwd_delta_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, N, H);
     B200_CUDA_OK(cudaGetLastError());
+  }
+  if (N > kNQ) {
+    // long sequences (attention_bwd_long.cu): the workspace continues behind delta with the fp32 dq buffer
+    float* dq32 = delta + (static_cast<long long>(B) * H * N + 3) / 4 * 4;
+    return launch_attn_bwd_long(qkv, dout, lse, delta, dq32, dqkv, kv_len, B, N, H, scale, st);
   }
   // v2 (attention_bwd2.cu: two query halves, 8 compute warps + issuer warp) is the default; B200_ATTN_BWD_V1=1 keeps
   // the simpler v1 kernel of this file selectable for A/B comparison and as a cross-check in the tests.

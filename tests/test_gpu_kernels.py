@@ -222,7 +222,8 @@ def test_assemble_tokens_and_colsum():
 
 
 # ------------------------------------------------------------------------------------------------ backward kernels
-@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 64, 2), (2, 208, 3), (2, 129, 2), (1, 17, 1)])
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 64, 2), (2, 208, 3), (2, 129, 2), (1, 17, 1),
+                                   (2, 577, 4), (1, 300, 2), (3, 224, 1), (1, 1025, 1)])   # N > 208: attention_bwd_long.cu
 def test_attention_bwd(B, N, H):
     """dq/dk/dv against PyTorch autograd of the fp32 restatement of attention.py:115-135."""
     ops = _ops()
@@ -239,13 +240,14 @@ def test_attention_bwd(B, N, H):
     _close(dqkv, ref_in.grad, 2e-2, 2e-2, f"attention bwd B={B} N={N} H={H}")
 
 
-def test_attention_bwd_key_padding():
+@pytest.mark.parametrize("N", [197, 577])
+def test_attention_bwd_key_padding(N):
     ops = _ops()
-    B, N, H, hd = 4, 197, 3, 64
+    B, H, hd = 4, 3, 64
     g = torch.Generator(device=DEV).manual_seed(7)
     qkv = torch.randn(B, N, 3 * H * hd, device=DEV, generator=g).bfloat16()
     dout = torch.randn(B, N, H * hd, device=DEV, generator=g).bfloat16()
-    kv_len = torch.tensor([N, 1, 100, 130], device=DEV, dtype=torch.int32)
+    kv_len = torch.tensor([N, 1, 100, 130 if N == 197 else 400], device=DEV, dtype=torch.int32)
     out, lse = ops.attention_fwd(qkv, B, N, H, hd, 0.125, kv_len=kv_len, need_lse=True)
     dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125, kv_len=kv_len)
     ref_in = qkv.float().requires_grad_(True)

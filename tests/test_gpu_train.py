@@ -231,3 +231,25 @@ def test_rmsnorm_vit_training_matches_reference_golden():
     assert (out.float().cpu() - fx["logits"]).abs().max().item() <= 3e-2 + 3e-2 * fx["logits"].abs().max().item()
     out.float().mean().backward()
     _check_grads(model, fx["grads"], rel_tol=8e-2, min_cos=0.995)     # reference grads are for the un-rounded fp32 weights
+
+
+def test_long_sequence_vit_training_matches_oracle():
+    """More than 208 tokens per image (the ViT-L/14 @336 regime: attention_fwd_long / attention_bwd_long kernels): loss
+    and every parameter gradient of a small ViT on 15 x 15 + 1 = 226 tokens against the oracle's autograd."""
+    from oracle import vit_oracle as O
+    from b200timm.vision_transformer import VisionTransformer
+    cfg = dict(img_size=240, patch_size=16, embed_dim=128, depth=2, num_heads=2)
+    sd = {k: v.bfloat16().float() for k, v in O.random_state_dict(cfg, seed=31, num_classes=10).items()}
+    model = VisionTransformer(num_classes=10, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().to(torch.bfloat16).train()
+    g = torch.Generator().manual_seed(2)
+    img = torch.randn(3, 3, 240, 240, generator=g).bfloat16()
+    target = torch.randint(0, 10, (3,), generator=g)
+    loss = torch.nn.functional.cross_entropy(model(img.cuda()).float(), target.cuda())
+    loss.backward()
+    ref_sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_loss = torch.nn.functional.cross_entropy(O.vit_forward(img.float(), ref_sd, cfg), target)
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 2e-2, (loss.item(), ref_loss.item())
+    _check_grads(model, {k: v.grad for k, v in ref_sd.items()})
