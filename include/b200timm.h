@@ -79,7 +79,7 @@ typedef struct b200_gemm_desc {
   int32_t rows_per_scale; /* tokens per sample: row r uses row_scale[r / rows_per_scale]                       */
   int32_t split_k;    /* >1: K is split over CTAs, partial tiles are atomically added into fp32 out
                          (requires out_dtype=f32, epilogue=B200_EPI_BIAS with bias=NULL)           */
-  /* EPI_BIAS_ROPE only (ABI 4).  rope: fp32 [rope_tokens - rope_prefix, 128] = [sin(64) | cos(64)], the `emb` of
+  /* EPI_BIAS_ROPE only (ABI >= 4).  rope: fp32 [rope_tokens - rope_prefix, 128] = [sin(64) | cos(64)], the `emb` of
    * apply_rot_embed_cat; row r of `out` is token r % rope_tokens of its sample; the first rope_prefix tokens
    * (cls / register tokens) and the columns >= rope_cols (the V third) pass through.  The value is rounded to bf16
    * before the rotation, as the reference rotates the bf16 output of nn.Linear in fp32 (`.type_as(v)` rounds again). */
@@ -166,6 +166,13 @@ B200_API int b200_assemble_tokens(const void* proj, const void* prefix, const vo
 B200_API int b200_naflex_assemble(const void* proj, const void* prefix, const void* table, const int32_t* pos_off,
                          const int32_t* pos_len, void* tokens, int32_t B, int32_t N, int32_t n_prefix,
                          int32_t D, int32_t prefix_dtype, void* stream);
+/* Backward of b200_naflex_assemble (autograd of naflexvit.py:857-960): dproj (bf16 [B*N, D]) = the patch-token rows of
+ * dtokens (bf16 [B, n_prefix+N, D]); dprefix (fp32 [n_prefix, D], may be NULL) += sum over b of the prefix rows;
+ * dtable (fp32 [T, D], may be NULL) [pos_off[b] + i] += dtokens[b, n_prefix + i] for i < pos_len[b].  dprefix / dtable
+ * are ACCUMULATED into (zero them first); the gradient of the position table through the bicubic resize is the caller's. */
+B200_API int b200_naflex_assemble_bwd(const void* dtokens, void* dproj, float* dprefix, float* dtable,
+                         const int32_t* pos_off, const int32_t* pos_len, int32_t B, int32_t N, int32_t n_prefix,
+                         int32_t D, void* stream);
 
 /* ------------------------------------------------------------------ ConvNeXt (channels-last activations [B,H,W,C] bf16)
  * Depthwise k x k convolution, stride 1, zero padding k/2, + bias: F.conv2d(groups=C) of timm/models/convnext.py:

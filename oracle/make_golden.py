@@ -123,6 +123,10 @@ def naflex_case(name, seed, batch):
     fx = {"kind": "naflex", "kwargs": dict(cfg, num_classes=9), "state_dict": _half_sd(model.state_dict()),
           "patches": patches, "patch_coord": coord, "patch_valid": valid, "features": feats["patches"].detach(),
           "logits": logits.detach(), "timm_version": timm.__version__, "torch_version": str(torch.__version__)}
+    # backward the way the reference's own model tests do it (tests/test_models.py:209-242): outputs.mean().backward()
+    model.zero_grad()
+    model(patches, patch_coord=coord, patch_valid=valid).mean().backward()
+    fx["grads"] = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
     torch.save(fx, os.path.join(OUT, name + ".pt"))
     print(name, "logits", tuple(logits.shape), "absmax", logits.abs().max().item())
 
@@ -218,6 +222,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "rope":
         os.makedirs(OUT, exist_ok=True)
         return rope_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "naflex":
+        os.makedirs(OUT, exist_ok=True)
+        return naflex_case("naflex_g1", 4, 5)
     if len(sys.argv) > 1 and sys.argv[1] == "rmsnorm":
         os.makedirs(OUT, exist_ok=True)
         return vit_case("vit_g4_rmsnorm", 5, 2, RMS_KWARGS)

@@ -25,14 +25,14 @@ def _to_param_dtype(g32, like):
     """fp32 gradient -> a fresh tensor with the parameter's dtype and shape (kernel conversion, no torch math)."""
     if like.dtype == torch.float32:
         return g32.view(like.shape)
-    out = torch.empty(like.shape, dtype=like.dtype, device=like.device)
+    out = torch.empty(like.shape, dtype=like.dtype, device=g32.device)
     n = g32.numel()
     if n % 4 == 0:
         ops.convert_f32(g32.reshape(-1), out.view(-1))
     else:  # tiny odd-sized parameter (e.g. a 10-class head bias): pad to a multiple of 4
         pad = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=g32.device)
         pad[:n] = g32.reshape(-1)
-        tmp = torch.empty(pad.numel(), dtype=like.dtype, device=like.device)
+        tmp = torch.empty(pad.numel(), dtype=like.dtype, device=g32.device)
         ops.convert_f32(pad, tmp)
         out.view(-1).copy_(tmp[:n])
     return out
@@ -337,3 +337,41 @@ class TokensFn(torch.autograd.Function):
             shape, dtype = ctx.shapes[1]
             dpos = (s if pos_has_prefix else s[n_prefix:]).to(dtype).view(shape)
         return dproj, dprefix, dpos, None
+
+
+class NaflexEmbedFn(torch.autograd.Function):
+    """NaFlexEmbeds.forward in NaFlex mode (timm/models/naflexvit.py:857-960): linear patch projection + per-sample
+    position rows + prefix tokens.  `table` is the concatenated (already interpolated) position rows: its gradient is
+    returned to autograd, which carries it through the bicubic resize to `pos_embed`."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, bias, prefix, table, pos_off, pos_len, B, N):
+        D, K = weight.shape
+        kpad = x2.shape[1]
+        w2 = weight
+        if kpad != K:      # 16-byte row pitch for TMA (p=14: 588 -> 592); x2 arrives zero-padded already
+            w2 = torch.zeros(D, kpad, dtype=weight.dtype, device=weight.device)
+            w2[:, :K] = weight
+        n_prefix = 0 if prefix is None else prefix.shape[0]
+        proj = ops.gemm(x2, _c(w2), B * N, D, kpad, bias=bias)
+        tokens = ops.naflex_assemble(proj, None if prefix is None else _c(prefix), table, pos_off, pos_len, B, N,
+                                     n_prefix, D)
+        ctx.save_for_backward(x2, weight, bias, pos_off, pos_len)
+        ctx.meta = (B, N, D, K, n_prefix, 0 if table is None else table.shape[0],
+                    None if prefix is None else prefix.dtype, None if table is None else table.dtype)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, dtok):
+        x2, weight, bias, pos_off, pos_len = ctx.saved_tensors
+        B, N, D, K, n_prefix, rows, pre_dt, tab_dt = ctx.meta
+        dproj, dprefix, dtable = ops.naflex_assemble_bwd(_c(dtok), pos_off, pos_len, rows, B, N, n_prefix, D)
+        gw = ops.linear_wgrad(dproj, x2)               # [D, Kpad] fp32
+        if gw.shape[1] != K:
+            gw = gw[:, :K].contiguous()
+        if dprefix is not None:
+            dprefix = _to_param_dtype(dprefix, torch.empty(dprefix.shape, dtype=pre_dt, device="meta"))
+        if dtable is not None:
+            dtable = _to_param_dtype(dtable, torch.empty(dtable.shape, dtype=tab_dt, device="meta"))
+        return None, _to_param_dtype(gw, weight), _bias_grad(dproj, bias), dprefix, dtable, None, None, None, None
+

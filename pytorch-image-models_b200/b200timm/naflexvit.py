@@ -109,21 +109,25 @@ class NaFlexVit(nn.Module):
         e = self.embeds
         B, N = patches.shape[:2]
         x = patches.reshape(B * N, -1)
-        if x.dtype != torch.bfloat16 or e.proj.weight.dtype != torch.bfloat16:
-            raise B200Error("NaFlexVit B200 path needs bf16 patches and weights")
+        if x.dtype == torch.float32 and e.proj.weight.dtype == torch.float32:
+            x = x.to(torch.bfloat16)        # train.py --amp: the cast autocast applies to F.linear's input
+        if x.dtype != torch.bfloat16:
+            raise B200Error("NaFlexVit B200 path needs bf16 patches (fp32 patches only with fp32 master weights)")
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in e.parameters())
+        w = BF._w(e.proj)
         K = x.shape[1]
         kpad = (K + 7) // 8 * 8
-        w = e.proj.weight
         if kpad != K:   # p=14: 588 -> 592, 16-byte row pitch for TMA (zero columns contribute nothing)
-            cache = getattr(e, "_b200_wpad", None)
-            if cache is None or cache[0] != (w.data_ptr(), w._version):
-                wp = torch.zeros(w.shape[0], kpad, dtype=w.dtype, device=w.device)
-                wp[:, :K] = w.detach()
-                e._b200_wpad = ((w.data_ptr(), w._version), wp)
-                cache = e._b200_wpad
-            w = cache[1]
             x = F.pad(x, (0, kpad - K))
-        proj = ops.gemm(x.contiguous(), w, B * N, w.shape[0], kpad, bias=e.proj.bias)
+            if not train:
+                cache = getattr(e, "_b200_wpad", None)
+                if cache is None or cache[0] != (w.data_ptr(), w._version):
+                    wp = torch.zeros(w.shape[0], kpad, dtype=w.dtype, device=w.device)
+                    wp[:, :K] = w.detach()
+                    e._b200_wpad = ((w.data_ptr(), w._version), wp)
+                    cache = e._b200_wpad
+                w = cache[1]
+        x = x.contiguous()
         # per-sample grid size from the coordinates (calculate_naflex_grid_sizes, naflexvit.py:204-208)
         sizes = [(int(h), int(w_)) for h, w_ in (patch_coord.amax(dim=1) + 1).tolist()]
         table, pos_off, pos_len = e.position_rows(sizes, torch.bfloat16, patches.device)
@@ -131,7 +135,13 @@ class NaFlexVit(nn.Module):
         prefix = None
         if pre:
             prefix = (pre[0] if len(pre) == 1 else torch.cat(pre, 1)).reshape(self.num_prefix_tokens, -1).contiguous()
-        tokens = ops.naflex_assemble(proj, prefix, table, pos_off, pos_len, B, N, self.num_prefix_tokens, self.embed_dim)
+        if train:
+            from .autograd import NaflexEmbedFn
+            tokens = NaflexEmbedFn.apply(x, w, e.proj.bias, prefix, table, pos_off, pos_len, B, N)
+        else:
+            proj = ops.gemm(x, w, B * N, w.shape[0], kpad, bias=e.proj.bias)
+            tokens = ops.naflex_assemble(proj, prefix, table, pos_off, pos_len, B, N, self.num_prefix_tokens,
+                                         self.embed_dim)
         # key-padding: prefix tokens + the valid (prefix-contiguous) patches (create_attention_mask, :964-1029)
         nvalid = patch_valid.sum(1).to(torch.int32)
         expect = torch.arange(N, device=patches.device)[None, :] < nvalid[:, None]
@@ -143,8 +153,6 @@ class NaFlexVit(nn.Module):
     def forward_features(self, patches, patch_coord=None, patch_valid=None) -> Dict[str, torch.Tensor]:
         if patch_coord is None or patch_valid is None:
             raise B200Error("NaFlexVit mirror covers the NaFlex (patches, patch_coord, patch_valid) input only")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise B200Error("NaFlexVit training is not covered yet; wrap inference in torch.no_grad()")
         x, kv_len = self._tokens(patches, patch_coord, patch_valid)
         if not isinstance(self.norm_pre, nn.Identity):
             x = BF.layernorm(self.norm_pre, x)
@@ -167,9 +175,13 @@ class NaFlexVit(nn.Module):
         if pre_logits or isinstance(self.head, nn.Identity):
             return x
         x = x.contiguous()
+        if BF._needs_grad(x, self.head):
+            from .autograd import LinearFn
+            return LinearFn.apply(x, BF._w(self.head), self.head.bias)
         if self.head.weight.shape[0] % 8:
+            BF._w(self.head)
             return BF._padded_out_linear(self.head, x)
-        return ops.linear_fwd(x, self.head.weight, self.head.bias)
+        return ops.linear_fwd(x, BF._w(self.head), self.head.bias)
 
     def forward(self, patches: Union[torch.Tensor, Dict[str, torch.Tensor]], patch_coord=None, patch_valid=None):
         if isinstance(patches, dict):

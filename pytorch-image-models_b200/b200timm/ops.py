@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
+    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
 ]
 
 
@@ -488,6 +488,21 @@ def naflex_assemble(proj, prefix, table, pos_off, pos_len, B, N, n_prefix, D):
     _lib.check(rc, "b200_naflex_assemble")
     _count()
     return tokens
+
+
+def naflex_assemble_bwd(dtokens, pos_off, pos_len, table_rows, B, N, n_prefix, D):
+    """Backward of naflex_assemble: (dproj bf16 [B*N, D], dprefix fp32 [n_prefix, D] or None, dtable fp32 [T, D] or None)."""
+    _need_cuda(dtokens, pos_off, pos_len)
+    if dtokens.dtype != torch.bfloat16 or not dtokens.is_contiguous() or dtokens.numel() != B * (N + n_prefix) * D:
+        raise B200Error("naflex_assemble_bwd: dtokens must be contiguous bf16 [B, n_prefix+N, D]")
+    dproj = torch.empty(B * N, D, dtype=torch.bfloat16, device=dtokens.device)
+    dprefix = torch.zeros(n_prefix, D, dtype=torch.float32, device=dtokens.device) if n_prefix else None
+    dtable = torch.zeros(table_rows, D, dtype=torch.float32, device=dtokens.device) if table_rows else None
+    rc = _lib.load().b200_naflex_assemble_bwd(dtokens.data_ptr(), dproj.data_ptr(), _ptr(dprefix), _ptr(dtable),
+                                              _ptr(pos_off), _ptr(pos_len), B, N, n_prefix, D, _stream())
+    _lib.check(rc, "b200_naflex_assemble_bwd")
+    _count()
+    return dproj, dprefix, dtable
 
 
 # --------------------------------------------------------------------------------------------- LayerScale / DropPath backward

@@ -305,6 +305,38 @@ rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ emb, l
   }
 }
 
+// Backward of naflex_assemble_kernel: dproj[b][i] = dtokens[b][n_prefix + i] (bf16 copy, the wgrad GEMM's operand),
+// dprefix[j] += dtokens[b][j] and dtable[pos_off[b] + i] += dtokens[b][n_prefix + i] for i < pos_len[b] (fp32, one
+// 16-byte red per 4 channels: samples sharing a grid size share table rows).  dprefix / dtable are zeroed by the caller.
+__global__ void naflex_assemble_bwd_kernel(const __nv_bfloat16* __restrict__ dtokens, __nv_bfloat16* __restrict__ dproj,
+                                           float* __restrict__ dprefix, float* __restrict__ dtable,
+                                           const int* __restrict__ pos_off, const int* __restrict__ pos_len, int B,
+                                           int N, int n_prefix, int D) {
+  const int dvecs = D >> 3;
+  const int ntok = N + n_prefix;
+  const long long total = static_cast<long long>(B) * ntok * dvecs;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int dv = static_cast<int>(idx % dvecs);
+    const long long t = idx / dvecs;
+    const int j = static_cast<int>(t % ntok);
+    const int b = static_cast<int>(t / ntok);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(dtokens + t * D + dv * 8));
+    float* acc = nullptr;
+    if (j < n_prefix) {
+      if (dprefix != nullptr) acc = dprefix + static_cast<long long>(j) * D + dv * 8;
+    } else {
+      const int i = j - n_prefix;
+      *reinterpret_cast<uint4*>(dproj + (static_cast<long long>(b) * N + i) * D + dv * 8) = q;
+      if (dtable != nullptr && i < pos_len[b]) acc = dtable + (static_cast<long long>(pos_off[b]) + i) * D + dv * 8;
+    }
+    if (acc != nullptr) {
+      atomicAdd(reinterpret_cast<float4*>(acc), make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y)));
+      atomicAdd(reinterpret_cast<float4*>(acc) + 1, make_float4(bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)));
+    }
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -394,6 +426,27 @@ extern "C" int b200_naflex_assemble(const void* proj, const void* prefix, const 
   naflex_assemble_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(proj), prefix, reinterpret_cast<const __nv_bfloat16*>(table), pos_off, pos_len,
       reinterpret_cast<__nv_bfloat16*>(tokens), B, N, n_prefix, D, prefix_dtype == B200_DTYPE_F32);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_naflex_assemble_bwd(const void* dtokens, void* dproj, float* dprefix, float* dtable,
+                                        const int32_t* pos_off, const int32_t* pos_len, int32_t B, int32_t N,
+                                        int32_t n_prefix, int32_t D, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(dtokens && dproj, "b200_naflex_assemble_bwd: null pointer");
+  B200_CHECK_ARG(dtable == nullptr || (pos_off && pos_len), "b200_naflex_assemble_bwd: dtable needs pos_off / pos_len");
+  B200_CHECK_ARG(B > 0 && N > 0 && n_prefix >= 0 && D > 0 && D % 8 == 0, "b200_naflex_assemble_bwd: bad shape (D %% 8 == 0)");
+  B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(dprefix) | reinterpret_cast<uintptr_t>(dtable)) & 15) == 0,
+                 "b200_naflex_assemble_bwd: dprefix / dtable must be 16-byte aligned");
+  const long long total = static_cast<long long>(B) * (N + n_prefix) * (D / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  naflex_assemble_bwd_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dtokens), reinterpret_cast<__nv_bfloat16*>(dproj), dprefix, dtable, pos_off,
+      pos_len, B, N, n_prefix, D);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

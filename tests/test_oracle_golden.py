@@ -113,6 +113,20 @@ def test_naflex_oracle_matches_reference():
         torch.testing.assert_close(feats[b, :n], fx["features"][b, :n], atol=1e-5, rtol=1e-5)
 
 
+def test_naflex_oracle_autograd_matches_reference_grads():
+    """Autograd of the oracle restatement reproduces the reference's parameter gradients (outputs.mean().backward()),
+    including the position table's gradient through the per-sample bicubic resize."""
+    from oracle import naflex_oracle as NO
+    fx = torch.load(os.path.join(GOLDEN, "naflex_g1.pt"))
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    _, logits = NO.naflex_forward(fx["patches"], fx["patch_coord"], fx["patch_valid"], sd, dict(fx["kwargs"], eps=1e-6))
+    logits.mean().backward()
+    assert sorted(sd) == sorted(fx["grads"])
+    for k, g in fx["grads"].items():
+        assert torch.allclose(sd[k].grad, g, atol=1e-6 + 1e-4 * g.abs().max().item(), rtol=1e-3), (
+            k, (sd[k].grad - g).abs().max().item(), g.abs().max().item())
+
+
 @pytest.mark.parametrize("layout", ["interleaved", "half"])
 def test_attention_rope_oracle_matches_reference(layout):
     """timm.layers.AttentionRope (attention.py:224-282) with a RotaryEmbeddingCat table: the oracle restatement and its

@@ -90,6 +90,34 @@ def naflex(args, ops):
 
     xs = [batch() for _ in range(2)]
     tokens = sum(int(v.sum()) for _, _, v in xs) / 2
+    if args.train:      # forward + cross-entropy + backward + SGD on the ragged batch
+        model.train()
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+        target = torch.randint(0, 1000, (B,), device="cuda")
+
+        def step(x):
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(model(*x).float(), target)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for i in range(args.warmup):
+            step(xs[i & 1])
+        torch.cuda.synchronize()
+        ops.reset_counters()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(args.steps):
+            loss = step(xs[i & 1])
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / args.steps
+        print(json.dumps({"model": args.model, "mode": "train", "batch": B, "max_patches": N,
+                          "valid_patches_per_batch": tokens, "ms_per_step": round(ms, 3),
+                          "img_per_s": round(B / ms * 1e3, 1), "loss": round(loss.item(), 4),
+                          "launches_per_step": ops.launch_count() // args.steps}))
+        return
     with torch.no_grad():
         for i in range(args.warmup):
             model(*xs[i & 1])
