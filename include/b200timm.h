@@ -210,6 +210,46 @@ B200_API int b200_colsum_mul(const void* a, const void* b, const float* row_scal
  * column sums of a bf16 [rows, cols] matrix into fp32 [cols] (bias gradients).                       */
 B200_API int b200_colsum(const void* x, float* out, int64_t rows, int32_t cols, int32_t accumulate, void* stream);
 
+/* ------------------------------------------------------------------ optimizer step
+ * The parameter update that follows the backward in timm's training loop: train.py:1262-1269 ->
+ * torch.optim.SGD / torch.optim.AdamW / torch.optim.Adam as built by timm/optim/_optim_factory.py:355-404
+ * ('sgd' = Nesterov, 'momentum', 'adamw', 'adam'), and the gradient clipping of timm/utils/clip_grad.py:18
+ * (torch.nn.utils.clip_grad_norm_, 2-norm).  One call updates a whole parameter group in ONE launch.
+ *
+ * `tensors` is a HOST array (it travels by value in the kernel's parameter space, so nothing is staged through device
+ * memory and gradient pointers may change every step); the pointers inside are device pointers.  param / grad have the
+ * dtype given by `dtype` (bf16 or fp32), optimizer state is always fp32, arithmetic is fp32.  Hyper-parameters are
+ * doubles because the reference's are Python floats: derived scalars (1 - beta, lr / (1 - beta1^t), ...) are formed in
+ * double and rounded once, exactly as torch/optim does before handing them to its kernels.
+ * grad_scale: optional device scalar multiplied into every gradient as it is read (the clip coefficient of
+ * b200_clip_coef) -- the fused form of clip_grad_norm_ followed by step(); NULL = 1.                                  */
+typedef struct b200_optim_tensor {
+  void* param;        /* [numel] dtype; updated in place                                  */
+  const void* grad;   /* [numel] dtype                                                     */
+  float* state1;      /* SGD: momentum buffer (NULL iff momentum == 0); Adam: exp_avg      */
+  float* state2;      /* Adam: exp_avg_sq; SGD: NULL                                       */
+  int64_t numel;
+} b200_optim_tensor;
+
+/* torch/optim/sgd.py _single_tensor_sgd: g += weight_decay * p; buf = first_step ? g : momentum * buf + (1 - dampening) * g;
+ * g = nesterov ? g + momentum * buf : buf; p -= lr * g.  first_step=1 for tensors whose momentum buffer has not been
+ * initialised yet (torch clones the gradient into it).                                                                */
+B200_API int b200_sgd_step(const b200_optim_tensor* tensors, int32_t n, int32_t dtype, double lr, double momentum,
+                         double dampening, double weight_decay, int32_t nesterov, int32_t first_step,
+                         const float* grad_scale, void* stream);
+/* torch/optim/adam.py _single_tensor_adam, step counted from 1.  decoupled=1 (AdamW): p *= 1 - lr * weight_decay;
+ * decoupled=0 (Adam): g += weight_decay * p.  m = lerp(m, g, 1 - beta1); v = beta2 * v + (1 - beta2) * g * g;
+ * p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps).                                                  */
+B200_API int b200_adam_step(const b200_optim_tensor* tensors, int32_t n, int32_t dtype, double lr, double beta1,
+                         double beta2, double eps, double weight_decay, int32_t step, int32_t decoupled,
+                         const float* grad_scale, void* stream);
+/* *sumsq += sum over every gradient element of g^2 (fp32 device scalar; zero it first); only grad / numel are read. */
+B200_API int b200_grad_sumsq(const b200_optim_tensor* tensors, int32_t n, int32_t dtype, float* sumsq, void* stream);
+/* torch/nn/utils/clip_grad.py: *total_norm = sqrt(*sumsq) (optional), *coef = min(1, max_norm / (total_norm + 1e-6)). */
+B200_API int b200_clip_coef(const float* sumsq, double max_norm, float* coef, float* total_norm, void* stream);
+/* g *= *scale in place over every gradient of the table (the unfused, in-place form of clip_grad_norm_). */
+B200_API int b200_grad_scale(const b200_optim_tensor* tensors, int32_t n, int32_t dtype, const float* scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

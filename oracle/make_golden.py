@@ -218,7 +218,52 @@ RMS_KWARGS = dict(img_size=48, patch_size=16, in_chans=3, num_classes=6, embed_d
                   norm_layer="rmsnorm")
 
 
+OPTIM_SHAPES = [(37,), (64, 33), (1000,), (3, 7, 11), (4096 + 5,), (1,), (32, 16)]
+OPTIM_CASES = {     # name -> (timm optimizer name, create_optimizer_v2 kwargs, clip_grad max-norm or None)
+    "sgd_nesterov_wd": ("sgd", dict(lr=0.1, momentum=0.9, weight_decay=1e-4), None),
+    "momentum_dampening": ("momentum", dict(lr=0.05, momentum=0.8, dampening=0.1, weight_decay=0.0), None),
+    "sgd_plain": ("momentum", dict(lr=0.2, momentum=0.0, weight_decay=1e-3), None),
+    "adamw": ("adamw", dict(lr=1e-3, weight_decay=0.05), None),
+    "adam_l2": ("adam", dict(lr=2e-3, weight_decay=1e-4, betas=(0.8, 0.99), eps=1e-6), None),
+    "adamw_clip": ("adamw", dict(lr=1e-3, weight_decay=0.05), 1.0),
+    "sgd_clip": ("sgd", dict(lr=0.1, momentum=0.9, weight_decay=1e-4), 0.5),
+}
+
+
+def optim_cases(steps=3):
+    """Parameter trajectories of the optimizers timm's factory builds for this path (create_optimizer_v2 on a bare
+    parameter list: one group, weight decay on every tensor) and of timm.utils.dispatch_clip_grad(mode='norm')."""
+    import timm
+    from timm.optim import create_optimizer_v2
+    from timm.utils import dispatch_clip_grad
+    g = torch.Generator().manual_seed(11)
+    init = [torch.randn(s, generator=g) for s in OPTIM_SHAPES]
+    grads = [[torch.randn(s, generator=g) * (0.5 + k) for s in OPTIM_SHAPES] for k in range(steps)]
+    fx = {"kind": "optim", "init": init, "grads": grads, "cases": {}, "timm_version": timm.__version__,
+          "torch_version": str(torch.__version__)}
+    for name, (opt, kw, clip) in OPTIM_CASES.items():
+        params = [torch.nn.Parameter(t.clone()) for t in init]
+        o = create_optimizer_v2(params, opt, **kw)
+        traj, norms = [], []
+        for k in range(steps):
+            for p, gk in zip(params, grads[k]):
+                p.grad = gk.clone()
+            if clip is not None:
+                norms.append(float(torch.nn.utils.get_total_norm([p.grad for p in params])))
+                dispatch_clip_grad(params, clip, mode="norm")
+            o.step()
+            traj.append([p.detach().clone() for p in params])
+        fx["cases"][name] = {"opt": opt, "kwargs": kw, "clip": clip, "params": traj, "norms": norms,
+                             "opt_class": type(o).__name__, "defaults": {k: v for k, v in o.defaults.items()
+                                                                         if isinstance(v, (int, float, bool, tuple))}}
+        print(name, type(o).__name__, "final |p|", float(sum(p.detach().norm() for p in params)))
+    torch.save(fx, os.path.join(OUT, "optim.pt"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "optim":
+        os.makedirs(OUT, exist_ok=True)
+        return optim_cases()
     if len(sys.argv) > 1 and sys.argv[1] == "rope":
         os.makedirs(OUT, exist_ok=True)
         return rope_cases()
@@ -243,6 +288,7 @@ def main():
     layer_cases()
     rope_cases()
     vit_case("vit_g4_rmsnorm", 5, 2, RMS_KWARGS)
+    optim_cases()
 
 
 if __name__ == "__main__":

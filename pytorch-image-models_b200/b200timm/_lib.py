@@ -58,7 +58,15 @@ class GemmDesc(ctypes.Structure):
     ]
 
 
-_vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+class OptimTensor(ctypes.Structure):
+    """Mirror of ``struct b200_optim_tensor``."""
+
+    _fields_ = [("param", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("state1", ctypes.c_void_p),
+                ("state2", ctypes.c_void_p), ("numel", ctypes.c_int64)]
+
+
+_vp, _i32, _i64, _f32, _f64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+_otp = ctypes.POINTER(OptimTensor)
 
 # name -> (restype, argtypes); must cover every B200_API prototype of include/b200timm.h
 # (tests/test_cabi.py checks the two lists against each other and against the .so's exports).
@@ -90,6 +98,11 @@ SIGNATURES = {
     "b200_unpatchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_patchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_avgpool_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "b200_sgd_step": (ctypes.c_int, [_otp, _i32, _i32, _f64, _f64, _f64, _f64, _i32, _i32, _vp, _vp]),
+    "b200_adam_step": (ctypes.c_int, [_otp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _i32, _i32, _vp, _vp]),
+    "b200_grad_sumsq": (ctypes.c_int, [_otp, _i32, _i32, _vp, _vp]),
+    "b200_clip_coef": (ctypes.c_int, [_vp, _f64, _vp, _vp, _vp]),
+    "b200_grad_scale": (ctypes.c_int, [_otp, _i32, _i32, _vp, _vp]),
 }
 
 _lib = None

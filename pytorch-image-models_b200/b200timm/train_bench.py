@@ -1,8 +1,10 @@
 """Training-step benchmark (BASELINE.json configs[3]): vit_base_patch16_224, bf16, batch 256 per GPU, DDP over
 NCCL when world_size > 1.  One step = zero_grad -> forward -> cross entropy -> backward (+ gradient all-reduce) ->
-SGD(momentum 0.9) step, i.e. benchmark.py:396-420 wrapped the way timm/task/classification.py:64-65 wraps the
-model.  Forward and backward of the model run on libb200timm kernels; loss and optimizer are torch's (out of the
-hot-path scope)."""
+SGD step, i.e. benchmark.py:396-420 wrapped the way timm/task/classification.py:64-65 wraps the model.  The optimizer
+is the one benchmark.py builds -- create_optimizer_v2(opt='sgd', lr=1e-4): Nesterov SGD, momentum 0.9, no weight decay
+(benchmark.py:383-386, timm/optim/_optim_factory.py:355-361) -- as b200timm.optim.SGD (one multi-tensor launch;
+B200_TORCH_OPTIM=1 swaps torch.optim.SGD in for A/B runs).  Forward and backward of the model run on libb200timm
+kernels; the cross-entropy loss is torch's."""
 import json
 import os
 
@@ -33,7 +35,11 @@ def run(args, rank, world, dev):
             elif tok.startswith("cap="):
                 kw["bucket_cap_mb"] = int(tok[4:])
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], broadcast_buffers=True, **kw)
-    opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.9)
+    if os.environ.get("B200_TORCH_OPTIM") == "1":
+        opt = torch.optim.SGD(model.parameters(), lr=1e-4, momentum=0.9, nesterov=True)
+    else:
+        from .optim import SGD
+        opt = SGD(model.parameters(), lr=1e-4, momentum=0.9, nesterov=True)
     B = args.batch
     xs = [torch.randn(B, 3, 224, 224, device=dev).to(torch.bfloat16) for _ in range(2)]
     ys = [torch.empty(B, dtype=torch.long, device=dev).random_(1000) for _ in range(2)]
@@ -102,7 +108,7 @@ def run(args, rank, world, dev):
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{MODEL} bf16 TRAIN step batch={B}/GPU (BASELINE.json configs[3]): fwd + CE + bwd + "
-                               "SGD(momentum), random-init weights, random targets", "global_batch": B * world,
+                               "Nesterov SGD step (b200timm.optim), random-init weights, random targets", "global_batch": B * world,
                    "parallelism": f"dp{world} (torch DDP, NCCL gradient all-reduce)" if world > 1 else "single GPU",
                    "flush": "two alternating 77 MB input batches; ~25 GB of activations / gradients streamed per step"},
         "e2e": {"value": round(total / (e2e_ms / 1e3), 1), "unit": "img/s",

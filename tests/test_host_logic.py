@@ -102,3 +102,34 @@ def test_naflex_state_dict_matches_timm():
     model.load_state_dict(fx["state_dict"], strict=True)
     big = create_naflex("vit_large_patch14_clip_336", depth=1)
     assert big.embeds.pos_embed.shape == (1, 24, 24, 1024) and big.embeds.proj.bias is None and big.norm.eps == 1e-5
+
+
+def test_optimizer_mirrors_torch_optim_interface_and_has_no_cpu_path():
+    """b200timm.optim.{SGD, AdamW, Adam}: torch.optim constructor signatures / defaults / param-group keys (what timm's
+    create_optimizer_v2 passes, timm/optim/_optim_factory.py:355-404), argument validation, and no CPU fallback."""
+    import inspect
+    from b200timm import optim as BO
+    for mine, ref in ((BO.SGD, torch.optim.SGD), (BO.AdamW, torch.optim.AdamW), (BO.Adam, torch.optim.Adam)):
+        a, b = inspect.signature(mine.__init__).parameters, inspect.signature(ref.__init__).parameters
+        for name in ("params", "lr", "weight_decay") + (("momentum", "dampening", "nesterov") if mine is BO.SGD
+                                                         else ("betas", "eps", "amsgrad")):
+            assert name in a and name in b, name
+            if name not in ("params",) and not (mine is BO.Adam and name == "weight_decay"):
+                assert a[name].default == b[name].default, (mine.__name__, name)
+    p = torch.nn.Parameter(torch.randn(4))
+    p.grad = torch.randn(4)
+    o = BO.AdamW([dict(params=[p], lr=3e-4)], weight_decay=0.05)
+    assert o.param_groups[0]["lr"] == 3e-4 and o.param_groups[0]["weight_decay"] == 0.05
+    assert o.param_groups[0]["betas"] == (0.9, 0.999)
+    with pytest.raises(B200Error):
+        o.step()                                   # CPU parameter: no fallback
+    with pytest.raises(B200Error):
+        BO.SGD([p], lr=0.1).step()
+    with pytest.raises(B200Error):
+        BO.clip_grad_norm_([p], 1.0)
+    with pytest.raises(B200Error):
+        BO.AdamW([p], amsgrad=True)
+    with pytest.raises(ValueError):
+        BO.SGD([p], lr=0.1, nesterov=True)         # Nesterov needs a momentum, as in torch
+    with pytest.raises(ValueError):
+        BO.AdamW([p], betas=(1.0, 0.999))

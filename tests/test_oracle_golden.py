@@ -157,3 +157,43 @@ def test_eva_attention_oracle_matches_reference():
     assert torch.allclose(x.grad, fx["dx"], atol=2e-4, rtol=1e-3)
     for k, g in fx["grads"].items():
         assert torch.allclose(sd[k].grad, g, atol=5e-4, rtol=1e-3), (k, (sd[k].grad - g).abs().max())
+
+
+def _oracle_optim_run(case, init, grads, round_to=None):
+    """Drive oracle/optim_oracle.py through one golden case; returns the parameter trajectory and the clip norms."""
+    from oracle import optim_oracle as OO
+    kw = dict(case["kwargs"])
+    params = [t.clone() if round_to is None else t.to(round_to).float() for t in init]
+    s1 = [torch.zeros_like(t) for t in init]
+    s2 = [torch.zeros_like(t) for t in init]
+    traj, norms = [], []
+    for k, gk in enumerate(grads):
+        gk = [g if round_to is None else g.to(round_to).float() for g in gk]
+        scale = 1.0
+        if case["clip"] is not None:
+            total, scale = OO.clip_coef(gk, case["clip"])
+            norms.append(total)
+        if case["opt"] in ("sgd", "momentum"):
+            OO.sgd_step(params, gk, s1, kw["lr"], kw.get("momentum", 0.0), kw.get("dampening", 0.0),
+                        kw.get("weight_decay", 0.0), nesterov=(case["opt"] == "sgd"), first=(k == 0), grad_scale=scale,
+                        round_to=round_to)
+        else:
+            b1, b2 = kw.get("betas", (0.9, 0.999))
+            OO.adam_step(params, gk, s1, s2, k + 1, kw["lr"], b1, b2, kw.get("eps", 1e-8), kw.get("weight_decay", 0.0),
+                         decoupled=(case["opt"] == "adamw"), grad_scale=scale, round_to=round_to)
+        traj.append([p.clone() for p in params])
+    return traj, norms
+
+
+def test_optimizer_oracle_matches_reference():
+    """oracle/optim_oracle.py against the trajectories of timm's create_optimizer_v2 optimizers + dispatch_clip_grad."""
+    fx = torch.load(os.path.join(GOLDEN, "optim.pt"))
+    assert set(fx["cases"]) >= {"sgd_nesterov_wd", "momentum_dampening", "sgd_plain", "adamw", "adam_l2", "adamw_clip",
+                                "sgd_clip"}
+    for name, case in fx["cases"].items():
+        traj, norms = _oracle_optim_run(case, fx["init"], fx["grads"])
+        for k, (got, ref) in enumerate(zip(traj, case["params"])):
+            for a, b in zip(got, ref):
+                torch.testing.assert_close(a, b, atol=2e-7, rtol=2e-6, msg=lambda m: f"{name} step {k}: {m}")
+        for a, b in zip(norms, case["norms"]):
+            assert abs(a - b) <= 1e-5 * b, (name, a, b)

@@ -108,3 +108,19 @@ def test_convert_to_b200_rebinds_one_model_only():
     b.load_state_dict(a.state_dict())
     with torch.no_grad():
         assert torch.equal(a(x), b(x))          # CPU fp32 input: the dispatcher defers to timm's forward
+
+
+def test_optimizers_register_with_timms_factory():
+    """register_with_timm() adds the libb200timm optimizers to timm's registry, so create_optimizer_v2 / train.py --opt
+    build them with timm's own param-group logic (no weight decay on 1-d parameters, _param_groups.py:19-70)."""
+    import torch
+    from b200timm import optim as BO
+    from timm.optim import create_optimizer_v2, list_optimizers
+    BO.register_with_timm()
+    assert {"b200sgd", "b200momentum", "b200adamw", "b200adam"} <= set(list_optimizers())
+    m = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.LayerNorm(8))
+    o = create_optimizer_v2(m, "b200sgd", lr=0.1, weight_decay=1e-4, momentum=0.9)
+    assert isinstance(o, BO.SGD) and o.defaults["nesterov"] is True
+    assert sorted(g["weight_decay"] for g in o.param_groups) == [0.0, 1e-4]
+    o = create_optimizer_v2(m, "b200adamw", lr=1e-3, weight_decay=0.05)
+    assert isinstance(o, BO.AdamW) and o.param_groups[0]["betas"] == (0.9, 0.999)

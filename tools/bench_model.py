@@ -92,7 +92,8 @@ def naflex(args, ops):
     tokens = sum(int(v.sum()) for _, _, v in xs) / 2
     if args.train:      # forward + cross-entropy + backward + SGD on the ragged batch
         model.train()
-        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+        from b200timm.optim import SGD
+        opt = SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
         target = torch.randint(0, 1000, (B,), device="cuda")
 
         def step(x):
@@ -145,7 +146,8 @@ def naflex(args, ops):
 
 def train(args, model, xs, ops):
     model.train()
-    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+    from b200timm.optim import SGD
+    opt = SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True)
     target = torch.randint(0, 1000, (args.batch,), device="cuda")
 
     def step(x):
