@@ -249,6 +249,27 @@ B200_API int b200_grad_sumsq(const b200_optim_tensor* tensors, int32_t n, int32_
 B200_API int b200_clip_coef(const float* sumsq, double max_norm, float* coef, float* total_norm, void* stream);
 /* g *= *scale in place over every gradient of the table (the unfused, in-place form of clip_grad_norm_). */
 B200_API int b200_grad_scale(const b200_optim_tensor* tensors, int32_t n, int32_t dtype, const float* scale, void* stream);
+/* Weight EMA, ModelEmaV3.apply_update_ (timm/utils/model_ema.py:213-231; called from train.py:1329 task.update_ema):
+ * ema.lerp_(model, weight) with weight = 1 - decay for every tensor of the table, one launch.  Table entries:
+ * param = the EMA tensor (ema_dtype, updated in place), grad = the model tensor (model_dtype); state1 / state2 unused.
+ * The two dtypes may differ (an fp32 EMA of a bf16 model keeps updates of relative size 1e-4 that bf16 would drop).     */
+B200_API int b200_ema_update(const b200_optim_tensor* tensors, int32_t n, int32_t ema_dtype, int32_t model_dtype,
+                         double weight, void* stream);
+
+/* ------------------------------------------------------------------ classification loss
+ * nn.CrossEntropyLoss (train.py:855, benchmark.py:380; smoothing = 0), LabelSmoothingCrossEntropy
+ * (timm/loss/cross_entropy.py:11-26: (1 - s) * nll + s * mean_c(-log_softmax)) with class indices `target` (int64 [B]),
+ * or SoftTargetCrossEntropy (:29-36: sum_c(-t * log_softmax)) with a distribution `soft_target` [B, C] (bf16 / fp32);
+ * exactly one of the two is non-NULL.  'mean' reduction over the B rows.  logits [B, C] bf16 or fp32, contiguous.
+ * Forward writes loss_rows[B], lse[B] (log-sum-exp), tsum[B] (sum of the row's target weights) and *loss_mean (all fp32).
+ * A class index outside [0, C) makes the row contribute 0 to the sum (the mean still divides by B).
+ * Backward: dlogits (dtype of logits) = (softmax * tsum - target distribution) * *grad_out / B.                       */
+B200_API int b200_cross_entropy_fwd(const void* logits, int32_t logits_dtype, const int64_t* target, const void* soft_target,
+                         int32_t soft_dtype, double smoothing, float* loss_rows, float* lse, float* tsum,
+                         float* loss_mean, int32_t B, int32_t C, void* stream);
+B200_API int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* target, const void* soft_target,
+                         int32_t soft_dtype, double smoothing, const float* lse, const float* tsum,
+                         const float* grad_out, void* dlogits, int32_t B, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -260,10 +260,65 @@ def optim_cases(steps=3):
     torch.save(fx, os.path.join(OUT, "optim.pt"))
 
 
+def ema_case(steps=5):
+    """timm.utils.ModelEmaV3 (train.py --model-ema --model-ema-warmup) over a drifting model with a BatchNorm buffer
+    set: the averaged state_dict after every update, and the decay schedule."""
+    import timm
+    from timm.utils import ModelEmaV3
+    torch.manual_seed(21)
+    model = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.BatchNorm1d(64), torch.nn.Linear(64, 5))
+    kw = dict(decay=0.998, use_warmup=True, update_after_step=1, warmup_gamma=1.0, warmup_power=2 / 3)
+    ema = ModelEmaV3(model, **kw)
+    g = torch.Generator().manual_seed(22)
+    fx = {"kind": "ema", "kwargs": kw, "init": {k: v.clone() for k, v in model.state_dict().items()}, "model_states": [],
+          "ema_states": [], "decays": [], "timm_version": timm.__version__}
+    for step in range(1, steps + 1):
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn(p.shape, generator=g) * 0.1)
+            model[1].running_mean.add_(torch.randn(64, generator=g) * 0.1)
+            model[1].num_batches_tracked.add_(1)
+        ema.update(model, step=step)
+        fx["model_states"].append({k: v.clone() for k, v in model.state_dict().items()})
+        fx["ema_states"].append({k: v.clone() for k, v in ema.module.state_dict().items()})
+        fx["decays"].append(ema.get_decay(step))
+    torch.save(fx, os.path.join(OUT, "ema.pt"))
+    print("ema decays", fx["decays"])
+
+
+def loss_cases():
+    """nn.CrossEntropyLoss (train.py:855), timm.loss.LabelSmoothingCrossEntropy, timm.loss.SoftTargetCrossEntropy on
+    seeded logits: loss value and d loss / d logits, appended to tests/golden/ema.pt's sibling loss.pt."""
+    import timm
+    from timm.loss import LabelSmoothingCrossEntropy, SoftTargetCrossEntropy
+    g = torch.Generator().manual_seed(31)
+    fx = {"kind": "loss", "cases": {}, "timm_version": timm.__version__}
+    for name, B, C in (("small", 7, 10), ("imagenet", 16, 1000), ("wide", 3, 2500)):
+        x = (torch.randn(B, C, generator=g) * 3).requires_grad_(True)
+        t = torch.randint(0, C, (B,), generator=g)
+        soft = torch.softmax(torch.randn(B, C, generator=g) * 2, -1)
+        case = {"logits": x.detach().clone(), "target": t, "soft_target": soft}
+        for key, fn, tgt in (("ce", torch.nn.CrossEntropyLoss(), t), ("ls", LabelSmoothingCrossEntropy(0.1), t),
+                             ("soft", SoftTargetCrossEntropy(), soft)):
+            x.grad = None
+            loss = fn(x, tgt)
+            (loss * 1.7).backward()
+            case[key] = {"loss": loss.detach().clone(), "dlogits": x.grad.clone(), "grad_out": 1.7}
+        fx["cases"][name] = case
+    torch.save(fx, os.path.join(OUT, "loss.pt"))
+    print("loss cases", {k: float(v["ls"]["loss"]) for k, v in fx["cases"].items()})
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "loss":
+        os.makedirs(OUT, exist_ok=True)
+        return loss_cases()
     if len(sys.argv) > 1 and sys.argv[1] == "optim":
         os.makedirs(OUT, exist_ok=True)
         return optim_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "ema":
+        os.makedirs(OUT, exist_ok=True)
+        return ema_case()
     if len(sys.argv) > 1 and sys.argv[1] == "rope":
         os.makedirs(OUT, exist_ok=True)
         return rope_cases()
@@ -289,6 +344,8 @@ def main():
     rope_cases()
     vit_case("vit_g4_rmsnorm", 5, 2, RMS_KWARGS)
     optim_cases()
+    ema_case()
+    loss_cases()
 
 
 if __name__ == "__main__":

@@ -60,3 +60,41 @@ def adam_step(params, grads, exp_avgs, exp_avg_sqs, step, lr, beta1=0.9, beta2=0
         v.mul_(beta2).add_(g * g, alpha=1 - beta2)
         denom = v.sqrt() / bc2_sqrt + eps
         p.copy_(_round(q - step_size * (m / denom), round_to))
+
+
+def ema_decay(step, decay=0.9999, min_decay=0.0, update_after_step=0, use_warmup=False, warmup_gamma=1.0,
+              warmup_power=2 / 3):
+    """ModelEmaV3.get_decay, timm/utils/model_ema.py:186-203."""
+    if step is None:
+        return decay
+    t = max(0, step - update_after_step - 1)
+    if t <= 0:
+        return 0.0
+    if not use_warmup:
+        return decay
+    return max(min(1 - (1 + t / warmup_gamma) ** -warmup_power, decay), min_decay)
+
+
+def ema_update(ema_sd, model_sd, decay, round_to=None):
+    """ModelEmaV3.apply_update_, model_ema.py:213-235: floating-point entries ema.lerp_(model, 1 - decay) (torch.lerp:
+    w < 0.5 -> a + w (b - a), else b - (b - a)(1 - w)), everything else copied.  In place on `ema_sd`."""
+    w = torch.tensor(1.0 - decay, dtype=torch.float32)
+    for k, e in ema_sd.items():
+        m = model_sd[k]
+        if not e.is_floating_point():
+            e.copy_(m)
+            continue
+        ef, mf = e.float(), m.float()
+        out = ef + w * (mf - ef) if float(w) < 0.5 else mf - (mf - ef) * (1 - w)
+        e.copy_(out if round_to is None else out.to(round_to))
+
+
+def cross_entropy(logits, target, smoothing=0.0):
+    """Mean loss of nn.CrossEntropyLoss (smoothing 0), timm LabelSmoothingCrossEntropy (timm/loss/cross_entropy.py:20-26:
+    (1 - s) * nll + s * mean_c(-logprobs)) for int64 class targets, or SoftTargetCrossEntropy (:34-36) for a [B, C]
+    distribution.  Differentiable torch fp32 (autograd gives the reference gradient)."""
+    logprobs = torch.log_softmax(logits.float(), dim=-1)
+    if target.dim() == 2:
+        return torch.sum(-target.float() * logprobs, dim=-1).mean()
+    nll = -logprobs.gather(-1, target.unsqueeze(1)).squeeze(1)
+    return ((1.0 - smoothing) * nll + smoothing * (-logprobs.mean(dim=-1))).mean()

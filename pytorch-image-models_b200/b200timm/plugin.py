@@ -136,6 +136,36 @@ def install():
         _ORIG[name] = getattr(cls, attr)
         setattr(cls, attr, _dispatch(name, fn))
         _ORIG[name + "#cls"] = (cls, attr)
+    _install_training_tail()
+
+
+def _ema_dispatch(orig, buffers):
+    def apply(self, model, decay):
+        first = next(iter(self.module.parameters()), None)
+        if self.foreach and first is not None and first.is_cuda:
+            try:
+                from .ema import fast_update
+                return fast_update(self, model, decay, buffers=buffers)     # validates every tensor before launching
+            except B200Error:
+                if _STRICT:
+                    raise
+        return orig(self, model, decay)
+    apply._b200_original = orig
+    return apply
+
+
+def _install_training_tail():
+    """The steps after the backward: the libb200timm optimizers join timm's registry as b200sgd / b200momentum /
+    b200adamw / b200adam (an addition -- existing names keep their torch.optim classes), and ModelEmaV3's interpolation
+    (timm/utils/model_ema.py:213-252) runs on b200_ema_update for CUDA models."""
+    from timm.utils.model_ema import ModelEmaV3
+    from .optim import register_with_timm
+    register_with_timm()
+    for attr, buffers in (("apply_update_", True), ("apply_update_no_buffers_", False)):
+        name = f"timm.utils.ModelEmaV3.{attr}"
+        _ORIG[name] = getattr(ModelEmaV3, attr)
+        _ORIG[name + "#cls"] = (ModelEmaV3, attr)
+        setattr(ModelEmaV3, attr, _ema_dispatch(_ORIG[name], buffers))
 
 
 def _table():

@@ -4,7 +4,7 @@ SGD step, i.e. benchmark.py:396-420 wrapped the way timm/task/classification.py:
 is the one benchmark.py builds -- create_optimizer_v2(opt='sgd', lr=1e-4): Nesterov SGD, momentum 0.9, no weight decay
 (benchmark.py:383-386, timm/optim/_optim_factory.py:355-361) -- as b200timm.optim.SGD (one multi-tensor launch;
 B200_TORCH_OPTIM=1 swaps torch.optim.SGD in for A/B runs).  Forward and backward of the model run on libb200timm
-kernels; the cross-entropy loss is torch's."""
+kernels, and so does the cross-entropy loss (b200timm.loss; B200_TORCH_LOSS=1 for torch's)."""
 import json
 import os
 
@@ -45,11 +45,16 @@ def run(args, rank, world, dev):
     ys = [torch.empty(B, dtype=torch.long, device=dev).random_(1000) for _ in range(2)]
     host_x = [t.cpu().pin_memory() for t in xs]
     host_y = [t.cpu().pin_memory() for t in ys]
-    loss_fn = torch.nn.CrossEntropyLoss()
+    if os.environ.get("B200_TORCH_LOSS") == "1":
+        ce = torch.nn.CrossEntropyLoss()
+        loss_fn = lambda out, y: ce(out.float(), y)      # noqa: E731
+    else:
+        from .loss import CrossEntropyLoss               # nn.CrossEntropyLoss of benchmark.py:380 on b200_cross_entropy_*
+        loss_fn = CrossEntropyLoss()
 
     def step(x, y):
         opt.zero_grad(set_to_none=True)
-        loss = loss_fn(net(x).float(), y)
+        loss = loss_fn(net(x), y)
         loss.backward()
         opt.step()
         return loss

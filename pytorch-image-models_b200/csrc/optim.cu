@@ -223,6 +223,40 @@ __global__ void __launch_bounds__(kThreads) grad_scale_kernel(const __grid_const
   }
 }
 
+// ModelEmaV3.apply_update_ (timm/utils/model_ema.py:213-231): ema.lerp_(model, weight) per tensor, torch's lerp formula
+// (weight < 0.5: a + w*(b - a); else b - (b - a)*(1 - w)).  Table entries: param = EMA tensor, grad = model tensor.
+template <bool EF32, bool MF32>
+__global__ void __launch_bounds__(kThreads) ema_update_kernel(const __grid_constant__ OptimArgs a, float w) {
+  const int total = a.chunk_start[a.n];
+  const bool low = w < 0.5f;
+  const float omw = 1.f - w;
+  for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    const int ti = find_tensor(a, chunk);
+    const b200_optim_tensor& t = a.t[ti];
+    const long long base = static_cast<long long>(chunk - a.chunk_start[ti]) * kChunk;
+    const long long rem = t.numel - base;
+    const int len = rem < kChunk ? static_cast<int>(rem) : kChunk;
+    int done = 0;
+    if (((reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad)) & 15) == 0) {
+      const int vec = len >> 3;
+      for (int i = threadIdx.x; i < vec; i += kThreads) {
+        const long long off = base + i * 8;
+        float e[8], m[8];
+        ld8v<EF32>(t.param, off, e);
+        ld8v<MF32>(t.grad, off, m);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = low ? fmaf(w, m[k] - e[k], e[k]) : fmaf(-(m[k] - e[k]), omw, m[k]);
+        st8v<EF32>(t.param, off, e);
+      }
+      done = vec << 3;
+    }
+    for (int i = done + threadIdx.x; i < len; i += kThreads) {
+      const float e = ld1<EF32>(t.param, base + i), m = ld1<MF32>(t.grad, base + i);
+      st1<EF32>(t.param, base + i, low ? fmaf(w, m - e, e) : fmaf(-(m - e), omw, m));
+    }
+  }
+}
+
 // Fill `a` from tensors[first, first+count) and return the number of chunks.
 static int fill_args(OptimArgs& a, const b200_optim_tensor* tensors, int first, int count) {
   a.n = count;
@@ -347,6 +381,38 @@ extern "C" int b200_grad_scale(const b200_optim_tensor* tensors, int32_t n, int3
     const int chunks = fill_args(a, tensors, first, count);
     if (dtype == B200_DTYPE_F32) grad_scale_kernel<true><<<grid_for(chunks), kThreads, 0, st>>>(a, scale);
     else grad_scale_kernel<false><<<grid_for(chunks), kThreads, 0, st>>>(a, scale);
+    B200_CUDA_OK(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_ema_update(const b200_optim_tensor* tensors, int32_t n, int32_t ema_dtype, int32_t model_dtype,
+                               double weight, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(tensors != nullptr && n > 0, "b200_ema_update: empty tensor table");
+  B200_CHECK_ARG((ema_dtype == B200_DTYPE_BF16 || ema_dtype == B200_DTYPE_F32) &&
+                     (model_dtype == B200_DTYPE_BF16 || model_dtype == B200_DTYPE_F32), "b200_ema_update: dtype must be bf16 or f32");
+  B200_CHECK_ARG(weight >= 0.0 && weight <= 1.0, "b200_ema_update: weight (1 - decay) must be in [0, 1]");
+  long long total_chunks = 0;
+  for (int i = 0; i < n; ++i) {
+    const b200_optim_tensor& t = tensors[i];
+    B200_CHECK_ARG(t.param != nullptr && t.grad != nullptr && t.numel > 0, "b200_ema_update: tensor %d: null pointer or numel <= 0", i);
+    B200_CHECK_ARG((reinterpret_cast<uintptr_t>(t.param) & (ema_dtype == B200_DTYPE_F32 ? 3 : 1)) == 0 &&
+                       (reinterpret_cast<uintptr_t>(t.grad) & (model_dtype == B200_DTYPE_F32 ? 3 : 1)) == 0,
+                   "b200_ema_update: tensor %d: misaligned pointer", i);
+    total_chunks += (t.numel + kChunk - 1) / kChunk;
+  }
+  B200_CHECK_ARG(total_chunks < (1ll << 31), "b200_ema_update: too many elements");
+  const float w = static_cast<float>(weight);
+  const bool ef = ema_dtype == B200_DTYPE_F32, mf = model_dtype == B200_DTYPE_F32;
+  OptimArgs a;
+  for (int first = 0; first < n; first += kMaxTensors) {
+    const int count = n - first < kMaxTensors ? n - first : kMaxTensors;
+    const int g = grid_for(fill_args(a, tensors, first, count));
+    if (ef && mf) ema_update_kernel<true, true><<<g, kThreads, 0, st>>>(a, w);
+    else if (ef) ema_update_kernel<true, false><<<g, kThreads, 0, st>>>(a, w);
+    else if (mf) ema_update_kernel<false, true><<<g, kThreads, 0, st>>>(a, w);
+    else ema_update_kernel<false, false><<<g, kThreads, 0, st>>>(a, w);
     B200_CUDA_OK(cudaGetLastError());
   }
   return B200_OK;

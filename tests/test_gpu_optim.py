@@ -176,3 +176,57 @@ def test_training_step_with_fused_optimizer_matches_torch_optimizer():
             o.step()
     for (n, a), b in zip(m1.named_parameters(), m2.parameters()):
         torch.testing.assert_close(a, b, atol=2e-5, rtol=1e-4, msg=lambda s: f"{n}: {s}")
+
+
+# ------------------------------------------------------------------------------------------------ weight EMA
+def _ema_model():
+    return torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.BatchNorm1d(64), torch.nn.Linear(64, 5))
+
+
+def test_model_ema_matches_reference_golden():
+    """b200timm.ema.ModelEma == timm.utils.ModelEmaV3 on the golden trajectory (warm-up schedule, float entries
+    interpolated by b200_ema_update, the integer BatchNorm counter copied)."""
+    from b200timm.ema import ModelEma
+    fx = torch.load(os.path.join(GOLDEN, "ema.pt"))
+    model = _ema_model()
+    model.load_state_dict(fx["init"])
+    model = model.cuda()
+    ema = ModelEma(model, **fx["kwargs"])
+    for step, (msd, want, d) in enumerate(zip(fx["model_states"], fx["ema_states"], fx["decays"]), start=1):
+        model.load_state_dict(msd)
+        assert ema.get_decay(step) == d
+        ema.update(model, step=step)
+        got = ema.module.state_dict()
+        for k in want:
+            if want[k].is_floating_point():
+                torch.testing.assert_close(got[k].cpu(), want[k], atol=1e-7, rtol=2e-6, msg=lambda m: f"step {step} {k}: {m}")
+            else:
+                assert torch.equal(got[k].cpu(), want[k]), k
+
+
+@pytest.mark.parametrize("ema_dtype", [None, torch.float32])
+def test_model_ema_bf16_model_matches_oracle(ema_dtype):
+    """bf16 model with a bf16 (reference behaviour) or fp32 average against the oracle's lerp rounded to the average's
+    dtype.  bf16 average: within one bf16 ulp everywhere and bit-exact on >= 99 % of the elements; fp32 average: atol 1e-7
+    / rtol 1e-6 after three updates (the kernel's fused multiply-add rounds once, torch's mul + add twice)."""
+    from oracle import optim_oracle as OO
+    from b200timm.ema import ModelEma
+    torch.manual_seed(5)
+    model = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.LayerNorm(256), torch.nn.Linear(256, 9)).cuda().bfloat16()
+    ema = ModelEma(model, decay=0.99, ema_dtype=ema_dtype)
+    ref = {k: v.detach().cpu().clone() for k, v in ema.module.state_dict().items()}
+    for _ in range(3):
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(torch.randn_like(p) * 0.05)
+        ema.update(model)
+        OO.ema_update(ref, {k: v.detach().cpu() for k, v in model.state_dict().items()}, 0.99,
+                      round_to=torch.bfloat16 if ema_dtype is None else torch.float32)
+    for k, v in ema.module.state_dict().items():
+        assert v.dtype == (torch.bfloat16 if ema_dtype is None else torch.float32)
+        g, w = v.float().cpu(), ref[k].float()
+        if ema_dtype is None:
+            assert ((g - w).abs() <= w.abs().clamp_min(1e-30) * 2.0 ** -7).all(), k
+            assert ((g - w).abs() > 0).float().mean() <= 0.01, k
+        else:                       # an fp32 average shows every fused-multiply-add rounding difference
+            torch.testing.assert_close(g, w, atol=1e-7, rtol=1e-6, msg=lambda m: f"{k}: {m}")

@@ -197,3 +197,30 @@ def test_optimizer_oracle_matches_reference():
                 torch.testing.assert_close(a, b, atol=2e-7, rtol=2e-6, msg=lambda m: f"{name} step {k}: {m}")
         for a, b in zip(norms, case["norms"]):
             assert abs(a - b) <= 1e-5 * b, (name, a, b)
+
+
+def test_ema_oracle_matches_reference():
+    """oracle ema_decay / ema_update against timm.utils.ModelEmaV3 with warm-up (tests/golden/ema.pt)."""
+    from oracle import optim_oracle as OO
+    fx = torch.load(os.path.join(GOLDEN, "ema.pt"))
+    ema = {k: v.clone() for k, v in fx["init"].items()}
+    for step, (msd, want, d) in enumerate(zip(fx["model_states"], fx["ema_states"], fx["decays"]), start=1):
+        decay = OO.ema_decay(step, **fx["kwargs"])
+        assert decay == d
+        OO.ema_update(ema, msd, decay)
+        for k in want:
+            torch.testing.assert_close(ema[k], want[k], atol=1e-7, rtol=1e-6, msg=lambda m: f"step {step} {k}: {m}")
+
+
+def test_loss_oracle_matches_reference():
+    """oracle cross_entropy (+ its autograd) against nn.CrossEntropyLoss / timm LabelSmoothingCrossEntropy /
+    SoftTargetCrossEntropy values and logits gradients (tests/golden/loss.pt)."""
+    from oracle import optim_oracle as OO
+    fx = torch.load(os.path.join(GOLDEN, "loss.pt"))
+    for name, case in fx["cases"].items():
+        for key, tgt, s in (("ce", case["target"], 0.0), ("ls", case["target"], 0.1), ("soft", case["soft_target"], 0.0)):
+            x = case["logits"].clone().requires_grad_(True)
+            loss = OO.cross_entropy(x, tgt, s)
+            (loss * case[key]["grad_out"]).backward()
+            torch.testing.assert_close(loss.detach(), case[key]["loss"], atol=1e-6, rtol=1e-6)
+            torch.testing.assert_close(x.grad, case[key]["dlogits"], atol=1e-8, rtol=1e-5, msg=lambda m: f"{name}/{key}: {m}")

@@ -124,3 +124,23 @@ def test_optimizers_register_with_timms_factory():
     assert sorted(g["weight_decay"] for g in o.param_groups) == [0.0, 1e-4]
     o = create_optimizer_v2(m, "b200adamw", lr=1e-3, weight_decay=0.05)
     assert isinstance(o, BO.AdamW) and o.param_groups[0]["betas"] == (0.9, 0.999)
+
+
+def test_model_ema_rebinding_keeps_cpu_models_on_timms_path():
+    """After install(), ModelEmaV3.apply_update_ is the dispatcher; a CPU model still takes timm's own foreach lerp
+    (the reference path for CPU tensors) and produces the reference result."""
+    import torch
+    from b200timm import plugin as P
+    from timm.utils import ModelEmaV3
+    P.install()
+    assert hasattr(ModelEmaV3.apply_update_, "_b200_original")
+    m = torch.nn.Linear(4, 3)
+    ema = ModelEmaV3(m, decay=0.9)
+    before = {k: v.clone() for k, v in ema.module.state_dict().items()}
+    with torch.no_grad():
+        m.weight.add_(1.0)
+    ema.update(m)
+    torch.testing.assert_close(ema.module.weight, before["weight"] + 0.1, atol=1e-6, rtol=1e-6)
+    P.uninstall()
+    assert not hasattr(ModelEmaV3.apply_update_, "_b200_original")
+    P.install()
