@@ -153,6 +153,12 @@ B200_API int b200_attn_bwd(const void* qkv, const void* out, const void* dout, c
  * (k = c*p*p + ky*p + kx, matching Conv2d.weight.flatten(1)); Kpad >= C*p*p, zero padded.              */
 B200_API int b200_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
                   int32_t Kpad, int32_t img_dtype, void* stream);
+/* The input-pipeline tail folded into the patch gather: img is the uint8 NCHW batch the loader's
+ * fast_collate produces; every pixel is normalised as PrefetchLoader does it (timm/data/loader.py:137-142:
+ * .to(float32).sub_(mean * 255).div_(std * 255)) and rounded to bf16 once: patches = bf16((u8 - mean[c]) / std[c]).
+ * mean / std: HOST arrays of C floats, already multiplied by 255 (C <= 8).                                           */
+B200_API int b200_patchify_u8(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
+                  int32_t Kpad, const float* mean, const float* std, void* stream);
 /* pos_has_prefix=1: tokens[b, j, :] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix]) + pos[j]
  * pos_has_prefix=0: prefix tokens get no position, patch token i gets pos[i]  (no_embed_class=True)
  * (vision_transformer.py:1038-1075, _pos_embed).  prefix / pos: [n_prefix, D] / [.., D], dtype param_dtype. */
@@ -173,6 +179,15 @@ B200_API int b200_naflex_assemble(const void* proj, const void* prefix, const vo
 B200_API int b200_naflex_assemble_bwd(const void* dtokens, void* dproj, float* dprefix, float* dtable,
                          const int32_t* pos_off, const int32_t* pos_len, int32_t B, int32_t N, int32_t n_prefix,
                          int32_t D, void* stream);
+
+/* ------------------------------------------------------------------ gated MLPs
+ * GluMlp / SwiGLUPacked / SwiGLU, timm/layers/mlp.py:57-165: h = fc1(x) is bf16 [M, 2H]; the gate is the first half of
+ * each row (gate_first=1: SwiGLUPacked `act(x1) * x2`, and SwiGLU with [fc1_g; fc1_x] stacked) or the second
+ * (gate_first=0: GluMlp's default `x1 * act(x2)`).  out[M, H] = act(gate) * value; act: 0 = SiLU, 1 = sigmoid.
+ * Backward: dh[M, 2H] from dout[M, H] and the saved h.  H % 8 == 0.                                                  */
+B200_API int b200_glu_fwd(const void* h, void* out, int64_t M, int32_t H, int32_t gate_first, int32_t act, void* stream);
+B200_API int b200_glu_bwd(const void* h, const void* dout, void* dh, int64_t M, int32_t H, int32_t gate_first, int32_t act,
+                  void* stream);
 
 /* ------------------------------------------------------------------ ConvNeXt (channels-last activations [B,H,W,C] bf16)
  * Depthwise k x k convolution, stride 1, zero padding k/2, + bias: F.conv2d(groups=C) of timm/models/convnext.py:

@@ -25,7 +25,13 @@ def vit_case(name, seed, batch, kwargs, backward=True):
     import timm  # noqa: F401
     from timm.models.vision_transformer import VisionTransformer
     torch.manual_seed(seed)
-    model = VisionTransformer(**kwargs)
+    build = dict(kwargs)
+    if isinstance(build.get("mlp_layer"), str):     # fixtures keep names; timm's constructor takes the classes
+        import timm.layers
+        build["mlp_layer"] = getattr(timm.layers, build["mlp_layer"])
+    if isinstance(build.get("act_layer"), str):
+        build["act_layer"] = {"silu": torch.nn.SiLU, "gelu": torch.nn.GELU}[build["act_layer"]]
+    model = VisionTransformer(**build)
     # default init zeroes biases / sets LN to (1, 0): perturb so every parameter path is exercised
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
@@ -309,7 +315,41 @@ def loss_cases():
     print("loss cases", {k: float(v["ls"]["loss"]) for k, v in fx["cases"].items()})
 
 
+def glu_cases():
+    """timm.layers.SwiGLU (with and without the inner LayerNorm, EVA-02's scale_mlp), SwiGLUPacked and the default GluMlp
+    (sigmoid gate on the second half): output, input gradient and parameter gradients -> tests/golden/glu.pt; and a ViT
+    with mlp_layer=SwiGLU (logits + parameter gradients) -> tests/golden/vit_g5_swiglu.pt."""
+    import timm
+    from timm.layers import GluMlp, LayerNorm, SwiGLU, SwiGLUPacked
+    g = torch.Generator().manual_seed(41)
+    fx = {"kind": "glu", "timm_version": timm.__version__}
+    torch.manual_seed(41)
+    mods = {"swiglu": SwiGLU(64, 128), "swiglu_norm": SwiGLU(64, 128, norm_layer=LayerNorm),
+            "swiglu_packed": SwiGLUPacked(64, 256), "glu_sigmoid": GluMlp(64, 256, bias=(True, False))}
+    for name, m in mods.items():
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() == 1:
+                    p.add_(torch.randn(p.shape, generator=g) * 0.05)
+        x = torch.randn(3, 50, 64, generator=g, requires_grad=True)
+        wgt = torch.randn(3, 50, 64, generator=g)
+        y = m(x)
+        (y * wgt).sum().backward()
+        fx[name] = {"state_dict": {k: v.clone() for k, v in m.state_dict().items()}, "x": x.detach().clone(), "y": y.detach(),
+                    "wgt": wgt, "dx": x.grad.clone(), "grads": {k: p.grad.clone() for k, p in m.named_parameters()},
+                    "act": type(m.act).__name__, "gate_last": getattr(m, "gate_last", None)}
+    torch.save(fx, os.path.join(OUT, "glu.pt"))
+    print("glu cases", {k: float(v["y"].abs().max()) for k, v in fx.items() if isinstance(v, dict)})
+    from functools import partial
+    vit_case("vit_g5_swiglu", 6, 2, dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=2,
+                                         num_heads=2, mlp_ratio=2.0, qkv_bias=True, init_values=0.1,
+                                         mlp_layer="SwiGLU", act_layer="silu"))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "glu":
+        os.makedirs(OUT, exist_ok=True)
+        return glu_cases()
     if len(sys.argv) > 1 and sys.argv[1] == "loss":
         os.makedirs(OUT, exist_ok=True)
         return loss_cases()
@@ -346,6 +386,7 @@ def main():
     optim_cases()
     ema_case()
     loss_cases()
+    glu_cases()
 
 
 if __name__ == "__main__":

@@ -127,6 +127,22 @@ def mlp(x, fc1_w, fc1_b, fc2_w, fc2_b):
     return linear(gelu_erf(linear(x, fc1_w, fc1_b)), fc2_w, fc2_b)
 
 
+def glu_mlp(x, sd, prefix, eps=1e-6, act="silu", gate_last=False):
+    """Gated MLPs, timm/layers/mlp.py.  SwiGLU.forward (:153-162, keys fc1_g / fc1_x): fc2(norm(act(fc1_g x) * fc1_x x)).
+    GluMlp.forward (:104-113, key fc1): x1, x2 = fc1(x).chunk(2); x1 * act(x2) if gate_last else act(x1) * x2
+    (SwiGLUPacked :116 = SiLU, gate_last=False).  The inner norm is applied when its weights are in `sd`."""
+    f = {"silu": lambda t: t * torch.sigmoid(t), "sigmoid": torch.sigmoid}[act]
+    g = lambda k: sd.get(prefix + k)  # noqa: E731
+    if g("fc1_g.weight") is not None:
+        h = f(linear(x, g("fc1_g.weight"), g("fc1_g.bias"))) * linear(x, g("fc1_x.weight"), g("fc1_x.bias"))
+    else:
+        x1, x2 = linear(x, g("fc1.weight"), g("fc1.bias")).chunk(2, dim=-1)
+        h = x1 * f(x2) if gate_last else f(x1) * x2
+    if g("norm.weight") is not None:
+        h = layer_norm(h, g("norm.weight"), g("norm.bias"), eps)
+    return linear(h, g("fc2.weight"), g("fc2.bias"))
+
+
 def drop_path(x, keep_mask, keep_prob, scale_by_keep=True):
     """timm/layers/drop.py:158-175 with the Bernoulli draw made explicit: keep_mask is a 0/1 tensor [B]."""
     m = keep_mask.to(x.dtype).view(-1, *([1] * (x.dim() - 1)))
@@ -148,8 +164,9 @@ def patch_embed(img, weight, bias, patch):
 
 
 # ----------------------------------------------------------------------------------------------- model
-def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, keep_prob=1.0):
-    """timm/models/vision_transformer.py:206-214 (Block.forward)."""
+def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, keep_prob=1.0, glu=None):
+    """timm/models/vision_transformer.py:206-214 (Block.forward).  glu: None (Mlp) or dict(act=, gate_last=) for a
+    gated mlp_layer (SwiGLU is recognised by its fc1_g key)."""
     g = lambda k: sd.get(prefix + k)  # noqa: E731
     h = attention(norm(x, sd, prefix + "norm1.", eps), g("attn.qkv.weight"), g("attn.qkv.bias"),
                   g("attn.proj.weight"), g("attn.proj.bias"), num_heads, kv_len)
@@ -158,8 +175,11 @@ def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, ke
     if keep1 is not None:
         h = drop_path(h, keep1, keep_prob)
     x = x + h
-    h = mlp(norm(x, sd, prefix + "norm2.", eps), g("mlp.fc1.weight"), g("mlp.fc1.bias"),
-            g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+    if glu is not None or g("mlp.fc1_g.weight") is not None:
+        h = glu_mlp(norm(x, sd, prefix + "norm2.", eps), sd, prefix + "mlp.", eps, **(glu or {}))
+    else:
+        h = mlp(norm(x, sd, prefix + "norm2.", eps), g("mlp.fc1.weight"), g("mlp.fc1.bias"),
+                g("mlp.fc2.weight"), g("mlp.fc2.bias"))
     if g("ls2.gamma") is not None:
         h = h * g("ls2.gamma")
     if keep2 is not None:
@@ -190,7 +210,7 @@ def vit_forward_features(img, sd, cfg, kv_len=None, return_blocks=False):
         x = norm(x, sd, "norm_pre.", eps)
     outs = []
     for i in range(cfg["depth"]):
-        x = block(x, sd, f"blocks.{i}.", cfg["num_heads"], eps, kv_len)
+        x = block(x, sd, f"blocks.{i}.", cfg["num_heads"], eps, kv_len, glu=cfg.get("glu"))
         outs.append(x)
     if "norm.weight" in sd:
         x = norm(x, sd, "norm.", eps)
@@ -313,7 +333,11 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
             h = h * sd[p + "ls1.gamma"]
         x = x + h
         h = _eager_norm(x, sd, p + "norm2.", eps)
-        h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd.get(p + "mlp.fc1.bias")))
+        if p + "mlp.fc1_g.weight" in sd:        # SwiGLU.forward, timm/layers/mlp.py:153-162
+            h = F.silu(F.linear(h, sd[p + "mlp.fc1_g.weight"], sd.get(p + "mlp.fc1_g.bias"))) * \
+                F.linear(h, sd[p + "mlp.fc1_x.weight"], sd.get(p + "mlp.fc1_x.bias"))
+        else:
+            h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd.get(p + "mlp.fc1.bias")))
         h = F.linear(h, sd[p + "mlp.fc2.weight"], sd.get(p + "mlp.fc2.bias"))
         if p + "ls2.gamma" in sd:
             h = h * sd[p + "ls2.gamma"]

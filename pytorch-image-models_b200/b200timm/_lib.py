@@ -87,6 +87,8 @@ SIGNATURES = {
     "b200_attn_bwd_ws_floats": (ctypes.c_int64, [_i32, _i32, _i32]),
     "b200_attn_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "b200_patchify": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200_patchify_u8": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_float),
+                                        ctypes.POINTER(ctypes.c_float), _vp]),
     "b200_assemble_tokens": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_naflex_assemble": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_naflex_assemble_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
@@ -98,6 +100,8 @@ SIGNATURES = {
     "b200_unpatchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_patchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_avgpool_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "b200_glu_fwd": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "b200_glu_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "b200_sgd_step": (ctypes.c_int, [_otp, _i32, _i32, _f64, _f64, _f64, _f64, _i32, _i32, _vp, _vp]),
     "b200_adam_step": (ctypes.c_int, [_otp, _i32, _i32, _f64, _f64, _f64, _f64, _f64, _i32, _i32, _vp, _vp]),
     "b200_grad_sumsq": (ctypes.c_int, [_otp, _i32, _i32, _vp, _vp]),

@@ -375,3 +375,39 @@ class NaflexEmbedFn(torch.autograd.Function):
             dtable = _to_param_dtype(dtable, torch.empty(dtable.shape, dtype=tab_dt, device="meta"))
         return None, _to_param_dtype(gw, weight), _bias_grad(dproj, bias), dprefix, dtable, None, None, None, None
 
+
+class GluMlpFn(torch.autograd.Function):
+    """GluMlp / SwiGLU forward (timm/layers/mlp.py:104-113, 153-162): fc2(norm(act(gate) * value)) with the gate and the
+    value as the two halves of one fc1 GEMM.  `nw is None` = no inner norm."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, nw, nb, eps, gate_first, act):
+        shape = x.shape
+        x2 = _c(x.reshape(-1, shape[-1]))
+        h = ops.linear_fwd(x2, w1, b1)
+        a = ops.glu_fwd(h, gate_first, act)
+        mean = rstd = None
+        an = a
+        if nw is not None:
+            an, mean, rstd = ops.layernorm_fwd(a, nw, nb, eps, save_stats=True)
+        y = ops.linear_fwd(an, w2, b2)
+        ctx.save_for_backward(x2, w1, b1, w2, b2, h, a, an, nw, nb, mean, rstd)
+        ctx.meta = (shape, gate_first, act)
+        return y.view(*shape[:-1], -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, b1, w2, b2, h, a, an, nw, nb, mean, rstd = ctx.saved_tensors
+        shape, gate_first, act = ctx.meta
+        dy2 = _c(dy.reshape(-1, dy.shape[-1]))
+        da = ops.linear_dgrad(dy2, w2)
+        gnw = gnb = None
+        if nw is not None:
+            da, dnw, dnb = ops.layernorm_bwd(da, a, nw, mean, rstd)
+            gnw = _to_param_dtype(dnw, nw)
+            gnb = None if nb is None else _to_param_dtype(dnb, nb)
+        dh = ops.glu_bwd(h, _c(da), gate_first, act)
+        dx = ops.linear_dgrad(dh, w1).view(shape)
+        return (dx, _wgrad(dh, x2, w1), _bias_grad(dh, b1), _wgrad(dy2, an, w2), _bias_grad(dy2, b2), gnw, gnb, None, None,
+                None)
+

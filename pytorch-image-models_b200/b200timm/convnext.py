@@ -408,8 +408,9 @@ def features_nhwc(self, img):
     """stem -> stages (convnext.py:606-611) on channels-last rows; `self` is this mirror's ConvNeXt or timm's."""
     if not img.is_cuda:
         raise B200Error("libb200timm kernels need CUDA tensors (there is no CPU path)")
-    if img.dtype not in (torch.bfloat16, torch.float32):
-        raise B200Error("ConvNeXt B200 path needs bf16 (or, under autocast with fp32 master weights, fp32) images")
+    if img.dtype not in (torch.bfloat16, torch.float32, torch.uint8):
+        raise B200Error("ConvNeXt B200 path needs bf16 images (fp32 under autocast with fp32 master weights; uint8 "
+                        "loader batches with ops.set_input_norm)")
     if (len(self.stem) != 2 or not isinstance(self.stem[0], nn.Conv2d) or type(self.stem[1]).__name__ != "LayerNorm2d"
             or not isinstance(getattr(self, "norm_pre", nn.Identity()), nn.Identity)):
         raise B200Error("ConvNeXt: only the patch stem (conv + LayerNorm2d) without norm_pre is covered")

@@ -252,10 +252,103 @@ def mlp_forward(mlp, x):
     return y.view(*shape[:-1], -1)
 
 
+def is_glu(mlp):
+    """GluMlp / SwiGLUPacked (one fc1 of width 2H) or SwiGLU (fc1_g + fc1_x), timm/layers/mlp.py:57-165."""
+    return hasattr(mlp, "fc1_g") or hasattr(mlp, "gate_last")
+
+
+def _glu_params(mlp):
+    """(w1 [2H, D] bf16, b1, gate_first, act name, norm params or None) of a gated MLP; the gate rows come first for SwiGLU
+    (fc1_g stacked on fc1_x -- a differentiable cat when training, cached otherwise)."""
+    act = {"SiLU": "silu", "Sigmoid": "sigmoid"}.get(type(mlp.act).__name__)
+    if act is None:
+        raise B200Error(f"unsupported gate activation {mlp.act} (SiLU / sigmoid)")
+    _check_drop(getattr(mlp, "drop1", None), "mlp drop")
+    _check_drop(getattr(mlp, "drop2", None), "mlp drop")
+    if hasattr(mlp, "fc1_g"):
+        wg, wx = _w(mlp.fc1_g), _w(mlp.fc1_x)
+        bg, bx = mlp.fc1_g.bias, mlp.fc1_x.bias
+        if torch.is_grad_enabled() and (wg.requires_grad or wx.requires_grad):
+            w1 = torch.cat([wg, wx], 0)
+            b1 = None if bg is None else torch.cat([bg, bx], 0)
+        else:
+            key = (wg.data_ptr(), wg._version, wx.data_ptr(), wx._version,
+                   None if bg is None else (bg.data_ptr(), bg._version, bx.data_ptr(), bx._version))
+            cache = getattr(mlp, "_b200_w1cat", None)
+            if cache is None or cache[0] != key:
+                cache = (key, torch.cat([wg, wx], 0).contiguous(), None if bg is None else torch.cat([bg, bx], 0))
+                mlp._b200_w1cat = cache
+            w1, b1 = cache[1], cache[2]
+        gate_first = True
+    else:
+        if not isinstance(mlp.fc1, nn.Linear):
+            raise B200Error("conv GluMlp is not supported")
+        w1, b1, gate_first = _w(mlp.fc1), mlp.fc1.bias, not mlp.gate_last
+    if w1.shape[0] % 16:
+        raise B200Error(f"gated MLP hidden width {w1.shape[0] // 2} is not a multiple of 8")
+    norm = None if _is_identity(getattr(mlp, "norm", None)) else _ln_params(mlp.norm)
+    if norm is not None and isinstance(norm[2], ops.RmsEps):
+        raise B200Error("gated MLP with an inner RMSNorm is not supported")
+    return w1, b1, gate_first, act, norm
+
+
+def glu_mlp_forward(mlp, x, residual=None, gamma=None, row_scale=None, rows_per_scale=0):
+    """GluMlp.forward / SwiGLU.forward (timm/layers/mlp.py:104-113, 153-162).  With `residual` (inference only) the block's
+    `x + drop_path(ls(mlp(...)))` is folded into fc2's epilogue."""
+    w1, b1, gate_first, act, norm = _glu_params(mlp)
+    shape = x.shape
+    if _needs_grad(x, mlp):
+        from .autograd import GluMlpFn
+        if residual is not None:
+            raise B200Error("glu_mlp_forward: the fused residual is an inference-only epilogue")
+        _bf16_2d(x, shape[-1])
+        nw, nb, eps = norm if norm is not None else (None, None, 0.0)
+        return GluMlpFn.apply(x, w1, b1, _w(mlp.fc2), mlp.fc2.bias, nw, nb, eps, gate_first, act)
+    x2 = _bf16_2d(x, shape[-1])
+    a = ops.glu_fwd(ops.linear_fwd(x2, w1, b1), gate_first, act)
+    if norm is not None:
+        a = ops.layernorm_fwd(a, *norm)[0]
+    if residual is not None:
+        y = ops.linear_fwd(a, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=residual, gamma=gamma,
+                           row_scale=row_scale, rows_per_scale=rows_per_scale)
+    else:
+        y = ops.linear_fwd(a, _w(mlp.fc2), mlp.fc2.bias)
+    return y.view(*shape[:-1], -1)
+
+
+def _glu_block_forward(blk, x, kv_len):
+    """Block.forward (vision_transformer.py:206-214) for a block whose mlp is gated.  Inference: the fused attention half of
+    block_forward + glu_mlp_forward with the residual in fc2's epilogue.  Training: the per-module autograd functions
+    composed the way the reference composes its modules (residual adds / LayerScale / DropPath as tensor ops)."""
+    attn, mlp = blk.attn, blk.mlp
+    B, N, D = x.shape
+    if _needs_grad(x, blk):
+        def branch(y, ls, dp):
+            g = _gamma(ls)
+            if g is not None:
+                y = y * g.to(y.dtype)
+            f = _drop_path_factor(dp, y)
+            return y if f is None else y * f.view(B, 1, 1).to(y.dtype)
+        x = x + branch(attention_forward(attn, layernorm(blk.norm1, x), kv_len), blk.ls1, blk.drop_path1)
+        return x + branch(glu_mlp_forward(mlp, layernorm(blk.norm2, x)), blk.ls2, blk.drop_path2)
+    x2 = _bf16_2d(x, D)
+    w1, b1, eps1 = _ln_params(blk.norm1)
+    h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
+    qkv = ops.linear_fwd(h, _w(attn.qkv), attn.qkv.bias)
+    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
+    x2 = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
+                        gamma=_gamma(blk.ls1))
+    w2, b2, eps2 = _ln_params(blk.norm2)
+    h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
+    return glu_mlp_forward(mlp, h, residual=x2, gamma=_gamma(blk.ls2)).view(B, N, D)
+
+
 def block_forward(blk, x, kv_len=None):
     """Block.forward (timm/models/vision_transformer.py:206-214), eval mode."""
     attn, mlp = blk.attn, blk.mlp
     check_attention(attn)
+    if is_glu(mlp):
+        return _glu_block_forward(blk, x, kv_len)
     check_mlp(mlp)
     B, N, D = x.shape
     if _needs_grad(x, blk):
@@ -300,8 +393,8 @@ def patch_embed_forward(pe, img):
     w = _w(pe.proj)
     if _needs_grad(None, pe):
         from .autograd import PatchEmbedFn
-        if img.dtype not in (torch.bfloat16, torch.float32):
-            raise B200Error("images must be bf16 or fp32 on the fused path")
+        if img.dtype not in (torch.bfloat16, torch.float32, torch.uint8):
+            raise B200Error("images must be bf16, fp32 or (with ops.set_input_norm) uint8 on the fused path")
         return PatchEmbedFn.apply(img, w, pe.proj.bias, ph)
     D = w.shape[0]
     K = C * ph * pw

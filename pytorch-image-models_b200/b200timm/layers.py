@@ -85,6 +85,75 @@ class Mlp(nn.Module):
         return BF.mlp_forward(self, x)
 
 
+class GluMlp(nn.Module):
+    """timm.layers.GluMlp (mlp.py:57-113): fc1 of width `hidden_features`, split into value / gate halves."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.Sigmoid, norm_layer=None,
+                 bias=True, drop=0., use_conv=False, gate_last=True, device=None, dtype=None):
+        super().__init__()
+        if use_conv:
+            raise B200Error("GluMlp(use_conv=True) is not supported")
+        dd = {"device": device, "dtype": dtype}
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        assert hidden_features % 2 == 0
+        bias = _pair(bias)
+        drop_probs = _pair(drop)
+        self.chunk_dim = -1
+        self.gate_last = gate_last
+        self.fc1 = nn.Linear(in_features, hidden_features, bias=bias[0], **dd)
+        self.act = act_layer()
+        self.drop1 = nn.Dropout(drop_probs[0])
+        self.norm = norm_layer(hidden_features // 2, **dd) if norm_layer is not None else nn.Identity()
+        self.fc2 = nn.Linear(hidden_features // 2, out_features, bias=bias[1], **dd)
+        self.drop2 = nn.Dropout(drop_probs[1])
+
+    def init_weights(self):
+        if self.fc1.bias is not None:
+            nn.init.ones_(self.fc1.bias[self.fc1.bias.shape[0] // 2:])
+        nn.init.normal_(self.fc1.weight[self.fc1.weight.shape[0] // 2:], std=1e-6)
+
+    def forward(self, x):
+        return BF.glu_mlp_forward(self, x)
+
+
+def SwiGLUPacked(*args, **kwargs):
+    """timm.layers.SwiGLUPacked (mlp.py:116): GluMlp with SiLU on the FIRST half."""
+    kwargs.setdefault("act_layer", nn.SiLU)
+    kwargs.setdefault("gate_last", False)
+    return GluMlp(*args, **kwargs)
+
+
+class SwiGLU(nn.Module):
+    """timm.layers.SwiGLU (mlp.py:119-162): separate gate / value projections fc1_g, fc1_x."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.SiLU, norm_layer=None,
+                 bias=True, drop=0., align_to=0, device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        bias = _pair(bias)
+        drop_probs = _pair(drop)
+        if align_to:
+            hidden_features = hidden_features + (-hidden_features % align_to)
+        self.fc1_g = nn.Linear(in_features, hidden_features, bias=bias[0], **dd)
+        self.fc1_x = nn.Linear(in_features, hidden_features, bias=bias[0], **dd)
+        self.act = act_layer()
+        self.drop1 = nn.Dropout(drop_probs[0])
+        self.norm = norm_layer(hidden_features, **dd) if norm_layer is not None else nn.Identity()
+        self.fc2 = nn.Linear(hidden_features, out_features, bias=bias[1], **dd)
+        self.drop2 = nn.Dropout(drop_probs[1])
+
+    def init_weights(self):
+        if self.fc1_g.bias is not None:
+            nn.init.ones_(self.fc1_g.bias)
+        nn.init.normal_(self.fc1_g.weight, std=1e-6)
+
+    def forward(self, x):
+        return BF.glu_mlp_forward(self, x)
+
+
 class RmsNorm(nn.Module):
     """timm.layers.RmsNorm (norm.py:202-248): y = x * rsqrt(mean(x^2) + eps) * weight."""
 

@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
+    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "set_input_norm", "input_norm", "glu_fwd", "glu_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
 ]
 
 
@@ -341,8 +341,29 @@ def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None):
 
 
 # --------------------------------------------------------------------------------------------- patch embed helpers
+_input_norm = None      # (mean * 255, std * 255) as ctypes float arrays: the loader's normalisation for uint8 images
+
+
+def set_input_norm(mean=None, std=None):
+    """Normalisation folded into the patch gather for uint8 images: PrefetchLoader's `(x - mean * 255) / (std * 255)`
+    (timm/data/loader.py:106-109,139) with `mean` / `std` per channel in [0, 1] units.  None switches it off."""
+    global _input_norm
+    if mean is None:
+        _input_norm = None
+        return
+    mean, std = [float(m) * 255 for m in mean], [float(s) * 255 for s in std]
+    if len(mean) != len(std) or not 1 <= len(mean) <= 8 or any(s == 0 for s in std):
+        raise B200Error("set_input_norm: mean / std need 1..8 channels and non-zero std")
+    # the loader builds these as fp32 tensors: round to fp32 the same way
+    _input_norm = ((ctypes.c_float * len(mean))(*mean), (ctypes.c_float * len(std))(*std))
+
+
+def input_norm():
+    return _input_norm
+
+
 def patchify(img, p, kpad=None):
-    """NCHW image (bf16 / fp32) -> [B*gh*gw, Kpad] bf16 patch matrix (k = c*p*p + ky*p + kx)."""
+    """NCHW image (bf16 / fp32, or uint8 with set_input_norm) -> [B*gh*gw, Kpad] bf16 patch matrix (k = c*p*p + ky*p + kx)."""
     _need_cuda(img)
     if img.dim() != 4 or not img.is_contiguous():
         raise B200Error("patchify: need a contiguous NCHW image")
@@ -351,6 +372,14 @@ def patchify(img, p, kpad=None):
     kpad = kpad or (K + 7) // 8 * 8
     gh, gw = H // p, W // p
     out = torch.empty(B * gh * gw, kpad, dtype=torch.bfloat16, device=img.device)
+    if img.dtype == torch.uint8:
+        if _input_norm is None or len(_input_norm[0]) != C:
+            raise B200Error("uint8 images need ops.set_input_norm(mean, std) with one entry per channel")
+        rc = _lib.load().b200_patchify_u8(img.data_ptr(), out.data_ptr(), B, C, H, W, p, kpad, _input_norm[0],
+                                          _input_norm[1], _stream())
+        _lib.check(rc, "b200_patchify_u8")
+        _count()
+        return out
     rc = _lib.load().b200_patchify(img.data_ptr(), out.data_ptr(), B, C, H, W, p, kpad, _dt(img), _stream())
     _lib.check(rc, "b200_patchify")
     _count()
@@ -466,6 +495,36 @@ def avgpool_nhwc(x):
     _lib.check(rc, "b200_avgpool_nhwc")
     _count()
     return out
+
+
+# --------------------------------------------------------------------------------------------- gated MLPs
+GLU_ACTS = {"silu": 0, "sigmoid": 1}
+
+
+def glu_fwd(h, gate_first, act="silu"):
+    """h bf16 [M, 2H] -> act(gate) * value, bf16 [M, H] (GluMlp / SwiGLU, timm/layers/mlp.py:106-108,156-158)."""
+    _need_cuda(h)
+    if h.dtype != torch.bfloat16 or h.dim() != 2 or not h.is_contiguous() or h.shape[1] % 16:
+        raise B200Error("glu_fwd: h must be contiguous bf16 [M, 2H] with H % 8 == 0")
+    M, H = h.shape[0], h.shape[1] // 2
+    out = torch.empty(M, H, dtype=torch.bfloat16, device=h.device)
+    rc = _lib.load().b200_glu_fwd(h.data_ptr(), out.data_ptr(), M, H, int(gate_first), GLU_ACTS[act], _stream())
+    _lib.check(rc, "b200_glu_fwd")
+    _count()
+    return out
+
+
+def glu_bwd(h, dout, gate_first, act="silu"):
+    """Gradient of glu_fwd with respect to h: bf16 [M, 2H]."""
+    _need_cuda(h, dout)
+    M, H = h.shape[0], h.shape[1] // 2
+    if dout.dtype != torch.bfloat16 or not dout.is_contiguous() or tuple(dout.shape) != (M, H):
+        raise B200Error("glu_bwd: dout must be contiguous bf16 [M, H]")
+    dh = torch.empty_like(h)
+    rc = _lib.load().b200_glu_bwd(h.data_ptr(), dout.data_ptr(), dh.data_ptr(), M, H, int(gate_first), GLU_ACTS[act], _stream())
+    _lib.check(rc, "b200_glu_bwd")
+    _count()
+    return dh
 
 
 # --------------------------------------------------------------------------------------------- NaFlex

@@ -36,6 +36,9 @@ def _fast(x):
         return False
     if torch.is_grad_enabled() and _GRAD_UNSUPPORTED:
         return False
+    if x.dtype == torch.uint8:     # raw loader batches: normalisation folded into the patch gather (b200timm.data)
+        from . import ops
+        return x.dim() == 4 and ops.input_norm() is not None
     return x.dtype == torch.bfloat16 or (x.dtype == torch.float32 and x.dim() == 4 and _autocast_bf16())
 
 
@@ -171,7 +174,7 @@ def _install_training_tail():
 def _table():
     """(qualified name, class, attribute, fast function) of every forward the plugin covers."""
     from timm.layers.attention import Attention, AttentionRope
-    from timm.layers.mlp import Mlp
+    from timm.layers.mlp import GluMlp, Mlp, SwiGLU
     from timm.layers.norm import LayerNorm, RmsNorm
     from timm.layers.patch_embed import PatchEmbed
     from timm.models.convnext import ConvNeXt, ConvNeXtBlock
@@ -181,6 +184,8 @@ def _table():
         ("timm.layers.LayerNorm.forward", LayerNorm, "forward", lambda self, x: BF.layernorm(self, x)),
         ("timm.layers.RmsNorm.forward", RmsNorm, "forward", lambda self, x: BF.layernorm(self, x)),
         ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
+        ("timm.layers.GluMlp.forward", GluMlp, "forward", lambda self, x: BF.glu_mlp_forward(self, x)),
+        ("timm.layers.SwiGLU.forward", SwiGLU, "forward", lambda self, x: BF.glu_mlp_forward(self, x)),
         ("timm.layers.Attention.forward", Attention, "forward", _attention),
         ("timm.layers.AttentionRope.forward", AttentionRope, "forward", _attention_rope),
         ("timm.models.eva.EvaAttention.forward", EvaAttention, "forward", _attention_rope),

@@ -85,6 +85,17 @@ class VisionTransformer(nn.Module):
             if norm_layer not in known:
                 raise B200Error(f"norm_layer {norm_layer!r} is not covered (layernorm, rmsnorm)")
             norm_layer = known[norm_layer]
+        if isinstance(act_layer, str):        # create_act keys (timm/layers/create_act.py); 'silu' goes with the gated MLPs
+            known = {"gelu": nn.GELU, "silu": nn.SiLU, "swish": nn.SiLU, "sigmoid": nn.Sigmoid}
+            if act_layer not in known:
+                raise B200Error(f"act_layer {act_layer!r} is not covered (gelu, silu, sigmoid)")
+            act_layer = known[act_layer]
+        if isinstance(mlp_layer, str):        # the reference has no string lookup for mlp_layer (vision_transformer.py:758);
+            from . import layers as _layers   # names of timm.layers classes are accepted here so fixtures / CLIs can say it
+            known = {"Mlp": Mlp, "SwiGLU": _layers.SwiGLU, "SwiGLUPacked": _layers.SwiGLUPacked, "GluMlp": _layers.GluMlp}
+            if mlp_layer not in known:
+                raise B200Error(f"mlp_layer {mlp_layer!r} is not covered ({', '.join(known)})")
+            mlp_layer = known[mlp_layer]
         norm_layer = norm_layer or LayerNorm
         act_layer = act_layer or nn.GELU
         self.num_classes = num_classes

@@ -73,6 +73,63 @@ __device__ __forceinline__ void ld8(const void* base, bool f32, long long idx, f
   }
 }
 
+// The same gather for uint8 images with the loader's normalisation folded in (timm/data/loader.py:137-142:
+// next_input.to(float32).sub_(mean * 255).div_(std * 255)): value = bf16((float(u8) - mean[c]) / std[c]) -- the fp32
+// result of the reference rounded once, with a true division so it is bit-identical to normalise-then-cast.
+struct NormParams { float mean[8], std[8]; };
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+                                   int W, int p, int gh, int gw, int Kpad, const NormParams nm) {
+  const int kvecs = Kpad >> 3;
+  const long long total = static_cast<long long>(B) * gh * gw * kvecs;
+  const int K = C * p * p;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kv = static_cast<int>(idx % kvecs);
+    const long long patch = idx / kvecs;
+    const int px = static_cast<int>(patch % gw);
+    const int py = static_cast<int>((patch / gw) % gh);
+    const int b = static_cast<int>(patch / (static_cast<long long>(gw) * gh));
+    const int k0 = kv * 8;
+    float v[8];
+    bool vec = false;
+    if ((p & 7) == 0 && k0 + 8 <= K) {          // 8 consecutive pixels of one image row: one 8-byte load
+      const int c = k0 / (p * p);
+      const int rem = k0 - c * p * p;
+      const int ky = rem / p, kx = rem - ky * p;
+      const uint8_t* src = img + ((static_cast<long long>(b) * C + c) * H + (py * p + ky)) * W + (px * p + kx);
+      if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
+        const float m = nm.mean[c], sd = nm.std[c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] = (static_cast<float>((q.x >> (8 * i)) & 0xFFu) - m) / sd;
+          v[4 + i] = (static_cast<float>((q.y >> (8 * i)) & 0xFFu) - m) / sd;
+        }
+        vec = true;
+      }
+    }
+    if (!vec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + i;
+        if (k < K) {
+          const int c = k / (p * p);
+          const int rem = k - c * p * p;
+          const int ky = rem / p, kx = rem - ky * p;
+          const long long off = ((static_cast<long long>(b) * C + c) * H + (py * p + ky)) * W + (px * p + kx);
+          v[i] = (static_cast<float>(__ldg(img + off)) - nm.mean[c]) / nm.std[c];
+        } else {
+          v[i] = 0.f;
+        }
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
+    q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(out + patch * Kpad + k0) = q;
+  }
+}
+
 // tokens[b][j][:] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix]) + pos[j]          (pos_has_prefix)
 // tokens[b][j][:] = (j < n_prefix ? prefix[j] : proj[b*G + j - n_prefix] + pos[j - n_prefix]) (otherwise:
 // no_embed_class).  timm/models/vision_transformer.py:1038-1075 (_pos_embed: cat cls/reg tokens, add pos_embed).
@@ -337,6 +394,72 @@ __global__ void naflex_assemble_bwd_kernel(const __nv_bfloat16* __restrict__ dto
   }
 }
 
+// Gated MLP activations (timm/layers/mlp.py:106-108 GluMlp, :156-158 SwiGLU): h = fc1(x) is [M, 2H] with the gate in the
+// first (gate_first) or second half of each row; out[m, j] = act(gate[m, j]) * value[m, j].  ACT: 0 SiLU, 1 sigmoid.
+template <int ACT>
+__device__ __forceinline__ float glu_act(float g) {
+  const float sg = 1.f / (1.f + __expf(-g));
+  return ACT == 0 ? g * sg : sg;
+}
+template <int ACT>
+__device__ __forceinline__ float glu_dact(float g) {
+  const float sg = 1.f / (1.f + __expf(-g));
+  return ACT == 0 ? sg * fmaf(g, 1.f - sg, 1.f) : sg * (1.f - sg);
+}
+
+template <int ACT>
+__global__ void glu_fwd_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, long long M, int H,
+                               int gate_first) {
+  const int hv = H >> 3;
+  const long long total = M * hv;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = idx / hv;
+    const int j = static_cast<int>(idx - m * hv) * 8;
+    float a[8], b[8];
+    ld8(h, false, m * 2 * H + j, a);
+    ld8(h, false, m * 2 * H + H + j, b);
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = gate_first ? glu_act<ACT>(a[k]) * b[k] : a[k] * glu_act<ACT>(b[k]);
+    uint4 q;
+    q.x = pack_bf16(o[0], o[1]); q.y = pack_bf16(o[2], o[3]);
+    q.z = pack_bf16(o[4], o[5]); q.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(out + m * H + j) = q;
+  }
+}
+
+// dh[m, gate half] = dout * value * act'(gate);  dh[m, value half] = dout * act(gate)
+template <int ACT>
+__global__ void glu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ dout,
+                               __nv_bfloat16* __restrict__ dh, long long M, int H, int gate_first) {
+  const int hv = H >> 3;
+  const long long total = M * hv;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = idx / hv;
+    const int j = static_cast<int>(idx - m * hv) * 8;
+    float a[8], b[8], d[8], da[8], db[8];
+    ld8(h, false, m * 2 * H + j, a);
+    ld8(h, false, m * 2 * H + H + j, b);
+    ld8(dout, false, m * H + j, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float g = gate_first ? a[k] : b[k], v = gate_first ? b[k] : a[k];
+      const float dg = d[k] * v * glu_dact<ACT>(g), dv = d[k] * glu_act<ACT>(g);
+      da[k] = gate_first ? dg : dv;
+      db[k] = gate_first ? dv : dg;
+    }
+    uint4 q;
+    q.x = pack_bf16(da[0], da[1]); q.y = pack_bf16(da[2], da[3]);
+    q.z = pack_bf16(da[4], da[5]); q.w = pack_bf16(da[6], da[7]);
+    *reinterpret_cast<uint4*>(dh + m * 2 * H + j) = q;
+    q.x = pack_bf16(db[0], db[1]); q.y = pack_bf16(db[2], db[3]);
+    q.z = pack_bf16(db[4], db[5]); q.w = pack_bf16(db[6], db[7]);
+    *reinterpret_cast<uint4*>(dh + m * 2 * H + H + j) = q;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -357,6 +480,31 @@ extern "C" int b200_patchify(const void* img, void* patches, int32_t B, int32_t 
     patchify_kernel<true><<<static_cast<int>(blocks), threads, 0, st>>>(img, reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p, gh, gw, Kpad);
   else
     patchify_kernel<false><<<static_cast<int>(blocks), threads, 0, st>>>(img, reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p, gh, gw, Kpad);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_patchify_u8(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
+                                int32_t Kpad, const float* mean, const float* std, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(img && patches && mean && std, "b200_patchify_u8: null pointer");
+  B200_CHECK_ARG(B > 0 && C > 0 && C <= 8 && p > 0 && H >= p && W >= p, "b200_patchify_u8: bad shape (1 <= C <= 8)");
+  B200_CHECK_ARG(Kpad % 8 == 0 && Kpad >= C * p * p, "b200_patchify_u8: Kpad=%d must be a multiple of 8 and >= C*p*p", Kpad);
+  NormParams nm = {};
+  for (int c = 0; c < C; ++c) {
+    B200_CHECK_ARG(std[c] != 0.f, "b200_patchify_u8: std[%d] is zero", c);
+    nm.mean[c] = mean[c];
+    nm.std[c] = std[c];
+  }
+  const int gh = H / p, gw = W / p;
+  const long long total = static_cast<long long>(B) * gh * gw * (Kpad / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  patchify_u8_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(reinterpret_cast<const uint8_t*>(img),
+                                                                    reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p,
+                                                                    gh, gw, Kpad, nm);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
@@ -502,6 +650,42 @@ extern "C" int b200_rope_qk(void* qkv, const float* emb, int32_t B, int32_t N, i
   if (blocks > cap) blocks = cap;
   rope_qk_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(qkv), emb, rows, N, H, num_prefix,
                                                           half_layout != 0, inverse != 0);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_glu_fwd(const void* h, void* out, int64_t M, int32_t H, int32_t gate_first, int32_t act, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(h && out && M > 0 && H > 0 && H % 8 == 0, "b200_glu_fwd: null pointer or bad shape (H %% 8 == 0)");
+  B200_CHECK_ARG(act == 0 || act == 1, "b200_glu_fwd: act must be 0 (SiLU) or 1 (sigmoid)");
+  const long long total = static_cast<long long>(M) * (H / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  auto* hp = reinterpret_cast<const __nv_bfloat16*>(h);
+  auto* op = reinterpret_cast<__nv_bfloat16*>(out);
+  if (act == 0) glu_fwd_kernel<0><<<static_cast<int>(blocks), threads, 0, st>>>(hp, op, M, H, gate_first);
+  else glu_fwd_kernel<1><<<static_cast<int>(blocks), threads, 0, st>>>(hp, op, M, H, gate_first);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_glu_bwd(const void* h, const void* dout, void* dh, int64_t M, int32_t H, int32_t gate_first, int32_t act,
+                            void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(h && dout && dh && M > 0 && H > 0 && H % 8 == 0, "b200_glu_bwd: null pointer or bad shape (H %% 8 == 0)");
+  B200_CHECK_ARG(act == 0 || act == 1, "b200_glu_bwd: act must be 0 (SiLU) or 1 (sigmoid)");
+  const long long total = static_cast<long long>(M) * (H / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  auto* hp = reinterpret_cast<const __nv_bfloat16*>(h);
+  auto* dp = reinterpret_cast<const __nv_bfloat16*>(dout);
+  auto* op = reinterpret_cast<__nv_bfloat16*>(dh);
+  if (act == 0) glu_bwd_kernel<0><<<static_cast<int>(blocks), threads, 0, st>>>(hp, dp, op, M, H, gate_first);
+  else glu_bwd_kernel<1><<<static_cast<int>(blocks), threads, 0, st>>>(hp, dp, op, M, H, gate_first);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -133,3 +133,27 @@ def test_optimizer_mirrors_torch_optim_interface_and_has_no_cpu_path():
         BO.SGD([p], lr=0.1, nesterov=True)         # Nesterov needs a momentum, as in torch
     with pytest.raises(ValueError):
         BO.AdamW([p], betas=(1.0, 0.999))
+
+
+def test_prefetch_loader_mirror_host_logic():
+    """b200timm.data.PrefetchLoader: constructor arguments of timm's PrefetchLoader (timm/data/loader.py:82-96), channel
+    adaptation of mean / std (:66-76), pass-through properties, and the refusals (random erasing, CPU device)."""
+    from b200timm import data as BD, ops
+
+    class _L(list):
+        sampler, dataset, collate_fn = "sampler", "dataset", None
+    inner = _L([(torch.zeros(2, 1, 8, 8, dtype=torch.uint8), torch.zeros(2, dtype=torch.long))])
+    try:
+        ld = BD.PrefetchLoader(inner, mean=(0.5, 0.4, 0.3), std=0.25, channels=1, device=torch.device("cpu"))
+        assert ld.mean == (pytest.approx(0.4),) and ld.std == (0.25,)
+        assert len(ld) == 1 and ld.sampler == "sampler" and ld.dataset == "dataset" and ld.mixup_enabled is False
+        norm = ops.input_norm()
+        assert [round(v, 3) for v in norm[0]] == [102.0] and list(norm[1]) == [63.75]
+        with pytest.raises(B200Error):
+            next(iter(ld))                       # CPU device: no fallback
+        with pytest.raises(B200Error):
+            BD.PrefetchLoader(inner, re_prob=0.25)
+        with pytest.raises(B200Error):
+            ops.set_input_norm((0.5,), (0.0,))
+    finally:
+        ops.set_input_norm(None)

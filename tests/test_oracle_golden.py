@@ -224,3 +224,26 @@ def test_loss_oracle_matches_reference():
             (loss * case[key]["grad_out"]).backward()
             torch.testing.assert_close(loss.detach(), case[key]["loss"], atol=1e-6, rtol=1e-6)
             torch.testing.assert_close(x.grad, case[key]["dlogits"], atol=1e-8, rtol=1e-5, msg=lambda m: f"{name}/{key}: {m}")
+
+
+@pytest.mark.parametrize("name", ["swiglu", "swiglu_norm", "swiglu_packed", "glu_sigmoid"])
+def test_glu_mlp_oracle_matches_reference(name):
+    """oracle glu_mlp (+ autograd) against timm.layers.SwiGLU / SwiGLUPacked / GluMlp (tests/golden/glu.pt)."""
+    fx = torch.load(os.path.join(GOLDEN, "glu.pt"))[name]
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    x = fx["x"].clone().requires_grad_(True)
+    y = O.glu_mlp(x, sd, "", act={"SiLU": "silu", "Sigmoid": "sigmoid"}[fx["act"]], gate_last=bool(fx["gate_last"]))
+    torch.testing.assert_close(y, fx["y"], atol=2e-6, rtol=1e-5)
+    (y * fx["wgt"]).sum().backward()
+    torch.testing.assert_close(x.grad, fx["dx"], atol=1e-5, rtol=1e-4)
+    for k, g in fx["grads"].items():
+        torch.testing.assert_close(sd[k].grad, g, atol=1e-4, rtol=1e-4, msg=lambda m: f"{k}: {m}")
+
+
+def test_swiglu_vit_oracle_matches_reference():
+    fx = torch.load(os.path.join(GOLDEN, "vit_g5_swiglu.pt"))
+    cfg = dict(fx["kwargs"], eps=1e-6)
+    with torch.no_grad():
+        feats = O.vit_forward_features(fx["img"], fx["state_dict"], cfg)
+        logits = O.vit_forward_head(feats, fx["state_dict"], cfg)
+    torch.testing.assert_close(logits, fx["logits"], atol=1e-5, rtol=1e-5)
