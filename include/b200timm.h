@@ -180,6 +180,20 @@ B200_API int b200_naflex_assemble_bwd(const void* dtokens, void* dproj, float* d
                          const int32_t* pos_off, const int32_t* pos_len, int32_t B, int32_t N, int32_t n_prefix,
                          int32_t D, void* stream);
 
+/* ------------------------------------------------------------------ q / k normalisation (row a4, qk_norm=True)
+ * `q, k = self.q_norm(q), self.k_norm(k)` with norm_layer(head_dim) = LayerNorm or RmsNorm, timm/layers/attention.py:
+ * 101-102,117.  qkv: bf16 [T, 3, H, 64] (T = B*N tokens), normalised IN PLACE on its q and k rows (v untouched).
+ * Training also gives save (bf16 [T, 2, H, 64]: the raw q / k rows) and mean / rstd (fp32 [T * 2 * H], mean unused
+ * for RMSNorm); inference passes NULL for all three.  Weights / biases: [64], param_dtype; biases NULL for RMSNorm.
+ * Backward, in place on dqkv: d(q), d(k) w.r.t. the normalised rows become gradients w.r.t. the raw rows; dparams
+ * (fp32 [4][64] = dq_weight, dq_bias, dk_weight, dk_bias) is ACCUMULATED into (zero it first).                     */
+B200_API int b200_qk_norm_fwd(void* qkv, void* save, float* mean, float* rstd, const void* q_weight, const void* q_bias,
+                      const void* k_weight, const void* k_bias, int32_t param_dtype, int64_t T, int32_t H,
+                      int32_t head_dim, float eps, int32_t rms, void* stream);
+B200_API int b200_qk_norm_bwd(void* dqkv, const void* save, const float* mean, const float* rstd, const void* q_weight,
+                      const void* k_weight, int32_t param_dtype, float* dparams, int64_t T, int32_t H,
+                      int32_t head_dim, int32_t rms, void* stream);
+
 /* ------------------------------------------------------------------ gated MLPs
  * GluMlp / SwiGLUPacked / SwiGLU, timm/layers/mlp.py:57-165: h = fc1(x) is bf16 [M, 2H]; the gate is the first half of
  * each row (gate_first=1: SwiGLUPacked `act(x1) * x2`, and SwiGLU with [fc1_g; fc1_x] stacked) or the second

@@ -346,7 +346,40 @@ def glu_cases():
                                          mlp_layer="SwiGLU", act_layer="silu"))
 
 
+def qknorm_cases():
+    """timm.layers.Attention with qk_norm (LayerNorm and RmsNorm over head_dim) and scale_norm: output, input gradient and
+    parameter gradients, with and without key padding -> tests/golden/qknorm.pt; and a ViT with qk_norm=True,
+    scale_attn_norm=True -> tests/golden/vit_g6_qknorm.pt."""
+    import timm
+    from timm.layers import Attention, LayerNorm, RmsNorm
+    g = torch.Generator().manual_seed(51)
+    torch.manual_seed(51)
+    fx = {"kind": "qknorm", "timm_version": timm.__version__}
+    mods = {"ln_qk": Attention(128, num_heads=2, qkv_bias=True, qk_norm=True, norm_layer=LayerNorm),
+            "rms_qk_scale": Attention(128, num_heads=2, qkv_bias=False, qk_norm=True, scale_norm=True, norm_layer=RmsNorm),
+            "ln_scale_only": Attention(128, num_heads=2, qkv_bias=True, scale_norm=True, norm_layer=LayerNorm)}
+    for name, m in mods.items():
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() == 1:
+                    p.add_(torch.randn(p.shape, generator=g) * 0.1)
+        x = torch.randn(3, 37, 128, generator=g, requires_grad=True)
+        wgt = torch.randn(3, 37, 128, generator=g)
+        y = m(x)
+        (y * wgt).sum().backward()
+        fx[name] = {"state_dict": {k: v.clone() for k, v in m.state_dict().items()}, "x": x.detach().clone(), "y": y.detach(),
+                    "wgt": wgt, "dx": x.grad.clone(), "grads": {k: p.grad.clone() for k, p in m.named_parameters()},
+                    "num_heads": 2, "norm": type(m.q_norm if name != "ln_scale_only" else m.norm).__name__}
+    torch.save(fx, os.path.join(OUT, "qknorm.pt"))
+    print("qknorm cases", {k: float(v["y"].abs().max()) for k, v in fx.items() if isinstance(v, dict)})
+    vit_case("vit_g6_qknorm", 7, 2, dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=2,
+                                         num_heads=2, mlp_ratio=2.0, qkv_bias=False, qk_norm=True, scale_attn_norm=True))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "qknorm":
+        os.makedirs(OUT, exist_ok=True)
+        return qknorm_cases()
     if len(sys.argv) > 1 and sys.argv[1] == "glu":
         os.makedirs(OUT, exist_ok=True)
         return glu_cases()
@@ -387,6 +420,7 @@ def main():
     ema_case()
     loss_cases()
     glu_cases()
+    qknorm_cases()
 
 
 if __name__ == "__main__":

@@ -57,8 +57,10 @@ def linear(x, weight, bias=None):
     return y if bias is None else y + bias
 
 
-def attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, kv_len=None):
-    """timm/layers/attention.py:108-139 (Attention.forward, qk_norm=False, no dropout).
+def attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, kv_len=None, norms=None):
+    """timm/layers/attention.py:108-139 (Attention.forward, no dropout).  norms = (sd, prefix, eps): the optional
+    q_norm / k_norm over head_dim (:117) and norm over the merged heads (:136) are applied when their weights are in sd
+    (LayerNorm, or RMSNorm when no bias key exists).
 
     kv_len: optional int tensor [B]; keys >= kv_len[b] are masked out, which is what the additive
     finfo.min mask built by naflexvit.py:964-1029 does for prefix-valid padding.
@@ -67,6 +69,9 @@ def attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, kv_len=None):
     hd = qkv_w.shape[0] // 3 // num_heads
     qkv = linear(x, qkv_w, qkv_b).reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)  # :115
     q, k, v = qkv.unbind(0)                                                                 # :116
+    if norms is not None and norms[1] + "q_norm.weight" in norms[0]:                        # :117
+        q = norm(q, norms[0], norms[1] + "q_norm.", norms[2])
+        k = norm(k, norms[0], norms[1] + "k_norm.", norms[2])
     s = (q * hd ** -0.5) @ k.transpose(-2, -1)                                             # :127-128
     if kv_len is not None:
         keys = torch.arange(N)[None, None, None, :]
@@ -75,6 +80,8 @@ def attention(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, kv_len=None):
     p = torch.exp(s)
     p = p / p.sum(-1, keepdim=True)                                                         # :131 softmax
     o = (p @ v).transpose(1, 2).reshape(B, N, num_heads * hd)                               # :133,135
+    if norms is not None and norms[1] + "norm.weight" in norms[0]:                          # :136 (scale_norm)
+        o = norm(o, norms[0], norms[1] + "norm.", norms[2])
     return linear(o, proj_w, proj_b)                                                        # :137
 
 
@@ -169,7 +176,7 @@ def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, ke
     gated mlp_layer (SwiGLU is recognised by its fc1_g key)."""
     g = lambda k: sd.get(prefix + k)  # noqa: E731
     h = attention(norm(x, sd, prefix + "norm1.", eps), g("attn.qkv.weight"), g("attn.qkv.bias"),
-                  g("attn.proj.weight"), g("attn.proj.bias"), num_heads, kv_len)
+                  g("attn.proj.weight"), g("attn.proj.bias"), num_heads, kv_len, norms=(sd, prefix + "attn.", eps))
     if g("ls1.gamma") is not None:
         h = h * g("ls1.gamma")                                   # timm/layers/layer_scale.py:26-27
     if keep1 is not None:
@@ -327,7 +334,11 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
         N = h.shape[1]
         qkv = F.linear(h, sd[p + "attn.qkv.weight"], sd.get(p + "attn.qkv.bias")).reshape(B, N, 3, H, D // H)
         q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
+        if p + "attn.q_norm.weight" in sd:       # qk_norm, attention.py:117
+            q, k = _eager_norm(q, sd, p + "attn.q_norm.", eps), _eager_norm(k, sd, p + "attn.k_norm.", eps)
         h = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(B, N, D)
+        if p + "attn.norm.weight" in sd:         # scale_norm, attention.py:136
+            h = _eager_norm(h, sd, p + "attn.norm.", eps)
         h = F.linear(h, sd[p + "attn.proj.weight"], sd.get(p + "attn.proj.bias"))
         if p + "ls1.gamma" in sd:
             h = h * sd[p + "ls1.gamma"]

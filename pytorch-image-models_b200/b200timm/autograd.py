@@ -411,3 +411,52 @@ class GluMlpFn(torch.autograd.Function):
         return (dx, _wgrad(dh, x2, w1), _bias_grad(dh, b1), _wgrad(dy2, an, w2), _bias_grad(dy2, b2), gnw, gnb, None, None,
                 None)
 
+
+class AttentionNormFn(torch.autograd.Function):
+    """Attention.forward with qk_norm and / or scale_norm (timm/layers/attention.py:108-139): qkv GEMM, per-head
+    normalisation of q and k (in place on the qkv buffer), SDPA, normalisation of the merged heads, proj GEMM.
+    qk = (q_weight, q_bias, k_weight, k_bias, eps) or None; sn = (weight, bias, eps) or None (eps may be an RmsEps)."""
+
+    @staticmethod
+    def forward(ctx, x, wqkv, bqkv, wproj, bproj, qw, qb, kw, kb, nw, nb, kv_len, num_heads, scale, qk_eps, sn_eps):
+        B, N, C = x.shape
+        hd = wqkv.shape[0] // 3 // num_heads
+        x2 = _c(x.reshape(B * N, C))
+        qkv = ops.linear_fwd(x2, wqkv, bqkv)
+        raw = qmean = qrstd = None
+        if qw is not None:
+            raw, qmean, qrstd = ops.qk_norm_fwd(qkv, B * N, num_heads, qw, qb, kw, kb, qk_eps, save=True)
+        o, lse = ops.attention_fwd(qkv, B, N, num_heads, hd, scale, kv_len, need_lse=True)
+        o2 = o.view(B * N, -1)
+        on, nmean, nrstd = o2, None, None
+        if nw is not None:
+            on, nmean, nrstd = ops.layernorm_fwd(o2, nw, nb, sn_eps, save_stats=True)
+        y = ops.linear_fwd(on, wproj, bproj)
+        ctx.save_for_backward(x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len, raw, qmean, qrstd, qw, qb, kw, kb, on, nmean,
+                              nrstd, nw, nb)
+        ctx.meta = (B, N, num_heads, hd, scale)
+        return y.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len, raw, qmean, qrstd, qw, qb, kw, kb, on, nmean, nrstd, nw,
+         nb) = ctx.saved_tensors
+        B, N, H, hd, scale = ctx.meta
+        dy2 = _c(dy.reshape(B * N, -1))
+        o2 = o.view(B * N, -1)
+        do = ops.linear_dgrad(dy2, wproj)
+        gnw = gnb = None
+        if nw is not None:
+            do, dnw, dnb = ops.layernorm_bwd(do, o2, nw, nmean, nrstd)
+            gnw = _to_param_dtype(dnw, nw)
+            gnb = None if nb is None else _to_param_dtype(dnb, nb)
+        dqkv = ops.attention_bwd(qkv, o, _c(do).view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
+        gq = [None] * 4
+        if qw is not None:
+            dp = ops.qk_norm_bwd(dqkv, raw, qmean, qrstd, qw, kw, B * N, H)
+            gq = [_to_param_dtype(dp[0].contiguous(), qw), None if qb is None else _to_param_dtype(dp[1].contiguous(), qb),
+                  _to_param_dtype(dp[2].contiguous(), kw), None if kb is None else _to_param_dtype(dp[3].contiguous(), kb)]
+        dx = ops.linear_dgrad(dqkv, wqkv).view(B, N, -1)
+        return (dx, _wgrad(dqkv, x2, wqkv), _bias_grad(dqkv, bqkv), _wgrad(dy2, on, wproj), _bias_grad(dy2, bproj),
+                gq[0], gq[1], gq[2], gq[3], gnw, gnb, None, None, None, None, None)
+

@@ -81,16 +81,35 @@ def _drop_path_factor(dp, x):
     return f.contiguous()
 
 
-def check_attention(attn):
-    """Raise unless `attn` is a plain timm Attention the kernels cover (attention.py:43-139)."""
-    if not _is_identity(getattr(attn, "q_norm", None)) or not _is_identity(getattr(attn, "k_norm", None)):
-        raise B200Error("qk_norm attention is not supported")
-    if not _is_identity(getattr(attn, "norm", None)):
-        raise B200Error("scale_norm attention is not supported")
+def check_attention(attn, allow_norms=False):
+    """Raise unless `attn` is a timm Attention the kernels cover (attention.py:43-139).  The fused block paths take the
+    plain module only; qk_norm / scale_norm run through attention_forward (allow_norms=True)."""
+    if not allow_norms:
+        if not _is_identity(getattr(attn, "q_norm", None)) or not _is_identity(getattr(attn, "k_norm", None)):
+            raise B200Error("qk_norm attention is not supported")
+        if not _is_identity(getattr(attn, "norm", None)):
+            raise B200Error("scale_norm attention is not supported")
     if attn.head_dim != 64:
         raise B200Error(f"head_dim {attn.head_dim} is not supported (64 only)")
     _check_drop(attn.attn_drop, "attn_drop")
     _check_drop(attn.proj_drop, "proj_drop")
+
+
+def _attn_norms(attn):
+    """((q_weight, q_bias, k_weight, k_bias, eps) or None, (weight, bias, eps) or None) of Attention's optional norms."""
+    qn, kn, sn = getattr(attn, "q_norm", None), getattr(attn, "k_norm", None), getattr(attn, "norm", None)
+    qk = None
+    if not _is_identity(qn) or not _is_identity(kn):
+        if _is_identity(qn) or _is_identity(kn) or type(qn) is not type(kn):
+            raise B200Error("q_norm and k_norm must be the same kind of layer")
+        (qw, qb, qe), (kw, kb, ke) = _ln_params(qn), _ln_params(kn)
+        if float(qe) != float(ke) or qw is None or kw is None or (qb is None) != (kb is None):
+            raise B200Error("q_norm / k_norm need equal eps and affine parameters")
+        qk = (qw, qb, kw, kb, qe)
+    sp = None if _is_identity(sn) else _ln_params(sn)
+    if sp is not None and sp[0] is None:
+        raise B200Error("scale_norm without affine parameters is not supported")
+    return qk, sp
 
 
 def check_mlp(mlp):
@@ -160,19 +179,37 @@ def layernorm(norm, x):
     return ops.layernorm_fwd(x, w, b, eps)[0]
 
 
-def attention_forward(attn, x, kv_len=None):
-    """Attention.forward (timm/layers/attention.py:108-139) without the output projection's residual."""
-    check_attention(attn)
+def attention_forward(attn, x, kv_len=None, residual=None, gamma=None):
+    """Attention.forward (timm/layers/attention.py:108-139) incl. qk_norm / scale_norm.  With `residual` (inference only)
+    the block's `x + ls(attn(...))` is folded into the output projection's epilogue."""
+    check_attention(attn, allow_norms=True)
+    qk, sn = _attn_norms(attn)
     B, N, C = x.shape
     if _needs_grad(x, attn):
-        from .autograd import AttentionFn
+        if residual is not None:
+            raise B200Error("attention_forward: the fused residual is an inference-only epilogue")
         _bf16_2d(x, C)
-        return AttentionFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, kv_len, attn.num_heads,
-                                 attn.scale)
+        if qk is None and sn is None:
+            from .autograd import AttentionFn
+            return AttentionFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, kv_len,
+                                     attn.num_heads, attn.scale)
+        from .autograd import AttentionNormFn
+        qw, qb, kw, kb, qe = qk if qk is not None else (None, None, None, None, 0.0)
+        nw, nb, ne = sn if sn is not None else (None, None, 0.0)
+        return AttentionNormFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, qw, qb, kw, kb, nw, nb,
+                                     kv_len, attn.num_heads, attn.scale, qe, ne)
     x2 = _bf16_2d(x, C)
     qkv = ops.linear_fwd(x2, _w(attn.qkv), attn.qkv.bias)
+    if qk is not None:
+        ops.qk_norm_fwd(qkv, B * N, attn.num_heads, *qk)
     o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
-    y = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias)
+    o2 = o.view(B * N, -1)
+    if sn is not None:
+        o2 = ops.layernorm_fwd(o2, *sn)[0]
+    if residual is not None:
+        y = ops.linear_fwd(o2, _w(attn.proj), attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=residual, gamma=gamma)
+    else:
+        y = ops.linear_fwd(o2, _w(attn.proj), attn.proj.bias)
     return y.view(B, N, -1)
 
 
@@ -316,12 +353,14 @@ def glu_mlp_forward(mlp, x, residual=None, gamma=None, row_scale=None, rows_per_
     return y.view(*shape[:-1], -1)
 
 
-def _glu_block_forward(blk, x, kv_len):
-    """Block.forward (vision_transformer.py:206-214) for a block whose mlp is gated.  Inference: the fused attention half of
-    block_forward + glu_mlp_forward with the residual in fc2's epilogue.  Training: the per-module autograd functions
-    composed the way the reference composes its modules (residual adds / LayerScale / DropPath as tensor ops)."""
+def _variant_block_forward(blk, x, kv_len):
+    """Block.forward (vision_transformer.py:206-214) for blocks outside the fully fused BlockFn: a gated mlp and / or an
+    attention with qk_norm / scale_norm.  Inference: every residual (+ LayerScale) rides in the epilogue of the branch's
+    last GEMM.  Training: the per-module autograd functions composed the way the reference composes its modules
+    (residual adds / LayerScale / DropPath as tensor ops)."""
     attn, mlp = blk.attn, blk.mlp
     B, N, D = x.shape
+    run_mlp = glu_mlp_forward if is_glu(mlp) else mlp_forward
     if _needs_grad(x, blk):
         def branch(y, ls, dp):
             g = _gamma(ls)
@@ -330,25 +369,27 @@ def _glu_block_forward(blk, x, kv_len):
             f = _drop_path_factor(dp, y)
             return y if f is None else y * f.view(B, 1, 1).to(y.dtype)
         x = x + branch(attention_forward(attn, layernorm(blk.norm1, x), kv_len), blk.ls1, blk.drop_path1)
-        return x + branch(glu_mlp_forward(mlp, layernorm(blk.norm2, x)), blk.ls2, blk.drop_path2)
+        return x + branch(run_mlp(mlp, layernorm(blk.norm2, x)), blk.ls2, blk.drop_path2)
     x2 = _bf16_2d(x, D)
-    w1, b1, eps1 = _ln_params(blk.norm1)
-    h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
-    qkv = ops.linear_fwd(h, _w(attn.qkv), attn.qkv.bias)
-    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
-    x2 = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
-                        gamma=_gamma(blk.ls1))
-    w2, b2, eps2 = _ln_params(blk.norm2)
-    h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
-    return glu_mlp_forward(mlp, h, residual=x2, gamma=_gamma(blk.ls2)).view(B, N, D)
+    h = ops.layernorm_fwd(x2, *_ln_params(blk.norm1))[0]
+    x2 = attention_forward(attn, h.view(B, N, D), kv_len, residual=x2, gamma=_gamma(blk.ls1)).view(B * N, D)
+    h = ops.layernorm_fwd(x2, *_ln_params(blk.norm2))[0]
+    if is_glu(mlp):
+        return glu_mlp_forward(mlp, h, residual=x2, gamma=_gamma(blk.ls2)).view(B, N, D)
+    check_mlp(mlp)
+    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    return ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
+                          gamma=_gamma(blk.ls2)).view(B, N, D)
 
 
 def block_forward(blk, x, kv_len=None):
     """Block.forward (timm/models/vision_transformer.py:206-214), eval mode."""
     attn, mlp = blk.attn, blk.mlp
+    qk, sn = _attn_norms(attn)
+    if is_glu(mlp) or qk is not None or sn is not None:
+        check_attention(attn, allow_norms=True)
+        return _variant_block_forward(blk, x, kv_len)
     check_attention(attn)
-    if is_glu(mlp):
-        return _glu_block_forward(blk, x, kv_len)
     check_mlp(mlp)
     B, N, D = x.shape
     if _needs_grad(x, blk):

@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "set_input_norm", "input_norm", "glu_fwd", "glu_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
+    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "set_input_norm", "input_norm", "glu_fwd", "glu_bwd", "qk_norm_fwd", "qk_norm_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
 ]
 
 
@@ -495,6 +495,45 @@ def avgpool_nhwc(x):
     _lib.check(rc, "b200_avgpool_nhwc")
     _count()
     return out
+
+
+# --------------------------------------------------------------------------------------------- q / k normalisation
+def qk_norm_fwd(qkv, T, H, qw, qb, kw, kb, eps, save=False):
+    """Normalises the q and k rows of qkv (bf16 [T, 3*H*64]) IN PLACE (Attention.q_norm / k_norm over head_dim 64,
+    timm/layers/attention.py:117); eps may be an RmsEps.  save=True returns (raw q/k rows bf16 [T, 2, H, 64], mean, rstd)."""
+    _need_cuda(qkv, qw, qb, kw, kb)
+    rms = isinstance(eps, RmsEps)
+    if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.numel() != T * 3 * H * 64:
+        raise B200Error("qk_norm_fwd: qkv must be a contiguous bf16 [T, 3, H, 64] buffer (head_dim 64)")
+    for w in (qw, kw):
+        if w.numel() != 64 or not w.is_contiguous():
+            raise B200Error("qk_norm_fwd: norm weights must be contiguous [64]")
+    dt = _param_dtype(qw, qb, kw, kb)
+    raw = mean = rstd = None
+    if save:
+        raw = torch.empty(T, 2, H, 64, dtype=torch.bfloat16, device=qkv.device)
+        rstd = torch.empty(T * 2 * H, dtype=torch.float32, device=qkv.device)
+        mean = None if rms else torch.empty(T * 2 * H, dtype=torch.float32, device=qkv.device)
+    rc = _lib.load().b200_qk_norm_fwd(qkv.data_ptr(), _ptr(raw), _ptr(mean), _ptr(rstd), qw.data_ptr(), _ptr(qb),
+                                      kw.data_ptr(), _ptr(kb), dt, T, H, 64, float(eps), int(rms), _stream())
+    _lib.check(rc, "b200_qk_norm_fwd")
+    _count()
+    return raw, mean, rstd
+
+
+def qk_norm_bwd(dqkv, raw, mean, rstd, qw, kw, T, H):
+    """In place on dqkv: gradients w.r.t. the normalised q / k rows -> w.r.t. the raw rows.  Returns fp32 [4, 64]:
+    dq_weight, dq_bias, dk_weight, dk_bias.  mean=None selects RMSNorm."""
+    _need_cuda(dqkv, raw, mean, rstd, qw, kw)
+    if dqkv.dtype != torch.bfloat16 or not dqkv.is_contiguous() or dqkv.numel() != T * 3 * H * 64:
+        raise B200Error("qk_norm_bwd: dqkv must be a contiguous bf16 [T, 3, H, 64] buffer")
+    dparams = torch.zeros(4, 64, dtype=torch.float32, device=dqkv.device)
+    rc = _lib.load().b200_qk_norm_bwd(dqkv.data_ptr(), raw.data_ptr(), _ptr(mean), rstd.data_ptr(), qw.data_ptr(),
+                                      kw.data_ptr(), _param_dtype(qw, kw), dparams.data_ptr(), T, H, 64, int(mean is None),
+                                      _stream())
+    _lib.check(rc, "b200_qk_norm_bwd")
+    _count()
+    return dparams
 
 
 # --------------------------------------------------------------------------------------------- gated MLPs

@@ -247,3 +247,19 @@ def test_swiglu_vit_oracle_matches_reference():
         feats = O.vit_forward_features(fx["img"], fx["state_dict"], cfg)
         logits = O.vit_forward_head(feats, fx["state_dict"], cfg)
     torch.testing.assert_close(logits, fx["logits"], atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["ln_qk", "rms_qk_scale", "ln_scale_only"])
+def test_attention_norm_oracle_matches_reference(name):
+    """oracle attention with q_norm / k_norm / norm (+ autograd) against timm.layers.Attention(qk_norm, scale_norm)."""
+    fx = torch.load(os.path.join(GOLDEN, "qknorm.pt"))[name]
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    x = fx["x"].clone().requires_grad_(True)
+    eps = 1e-6
+    y = O.attention(x, sd["qkv.weight"], sd.get("qkv.bias"), sd["proj.weight"], sd["proj.bias"], fx["num_heads"],
+                    norms=(sd, "", eps))
+    torch.testing.assert_close(y, fx["y"], atol=2e-5, rtol=1e-4)
+    (y * fx["wgt"]).sum().backward()
+    torch.testing.assert_close(x.grad, fx["dx"], atol=2e-4, rtol=1e-3)
+    for k, g in fx["grads"].items():
+        torch.testing.assert_close(sd[k].grad, g, atol=5e-4, rtol=1e-3, msg=lambda m: f"{k}: {m}")
