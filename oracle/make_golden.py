@@ -21,7 +21,7 @@ def _half_sd(sd):
     return {k: v.clone() for k, v in sd.items()}
 
 
-def vit_case(name, seed, batch, kwargs, backward=True):
+def vit_case(name, seed, batch, kwargs, backward=True, input_size=None):
     import timm  # noqa: F401
     from timm.models.vision_transformer import VisionTransformer
     torch.manual_seed(seed)
@@ -41,7 +41,8 @@ def vit_case(name, seed, batch, kwargs, backward=True):
             if n in ("cls_token", "reg_token", "pos_embed"):
                 p.copy_(torch.randn(p.shape, generator=g) * 0.02)
     model.eval()
-    img = torch.randn(batch, kwargs.get("in_chans", 3), kwargs["img_size"], kwargs["img_size"], generator=g)
+    ih, iw = input_size or (kwargs["img_size"], kwargs["img_size"])      # dynamic_img_size models: not the nominal size
+    img = torch.randn(batch, kwargs.get("in_chans", 3), ih, iw, generator=g)
     feats_per_block = []
     hooks = [blk.register_forward_hook(lambda m, i, o: feats_per_block.append(o.detach().clone()))
              for blk in model.blocks]
@@ -376,7 +377,14 @@ def qknorm_cases():
                                          num_heads=2, mlp_ratio=2.0, qkv_bias=False, qk_norm=True, scale_attn_norm=True))
 
 
+DYN_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=1, num_heads=2, mlp_ratio=2.0,
+                  qkv_bias=True, dynamic_img_size=True, reg_tokens=1)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "dynamic":
+        os.makedirs(OUT, exist_ok=True)
+        return vit_case("vit_g7_dynamic_img_size", 8, 2, DYN_KWARGS, input_size=(96, 80))
     if len(sys.argv) > 1 and sys.argv[1] == "qknorm":
         os.makedirs(OUT, exist_ok=True)
         return qknorm_cases()
@@ -421,6 +429,7 @@ def main():
     loss_cases()
     glu_cases()
     qknorm_cases()
+    vit_case("vit_g7_dynamic_img_size", 8, 2, DYN_KWARGS, input_size=(96, 80))
 
 
 if __name__ == "__main__":

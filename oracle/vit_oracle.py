@@ -170,6 +170,20 @@ def patch_embed(img, weight, bias, patch):
     return linear(x, weight.reshape(weight.shape[0], -1), bias)
 
 
+def resample_abs_pos_embed(pos, new_size, old_size, num_prefix_tokens):
+    """timm/layers/pos_embed.py:19-59: unchanged when the grid already matches (square); otherwise the grid rows go
+    through F.interpolate(bicubic, antialias=True) in fp32 as [1, D, gh, gw] and the prefix rows are put back."""
+    import torch.nn.functional as F
+    if new_size[0] * new_size[1] + num_prefix_tokens == pos.shape[1] and new_size[0] == new_size[1]:
+        return pos
+    prefix, grid = pos[:, :num_prefix_tokens], pos[:, num_prefix_tokens:]
+    D = pos.shape[-1]
+    g = F.interpolate(grid.float().reshape(1, old_size[0], old_size[1], D).permute(0, 3, 1, 2), size=tuple(new_size),
+                      mode="bicubic", antialias=True)
+    g = g.permute(0, 2, 3, 1).reshape(1, -1, D).to(pos.dtype)
+    return torch.cat([prefix, g], 1) if num_prefix_tokens else g
+
+
 # ----------------------------------------------------------------------------------------------- model
 def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, keep_prob=1.0, glu=None):
     """timm/models/vision_transformer.py:206-214 (Block.forward).  glu: None (Mlp) or dict(act=, gate_last=) for a
@@ -205,6 +219,10 @@ def vit_forward_features(img, sd, cfg, kv_len=None, return_blocks=False):
     if "reg_token" in sd:
         to_cat.append(sd["reg_token"].expand(B, -1, -1))
     pos = sd.get("pos_embed")
+    if pos is not None and cfg.get("dynamic_img_size", False):                     # :1049-1058
+        npt = 0 if cfg.get("no_embed_class", False) else sum(t.shape[1] for t in to_cat)
+        old = (cfg["img_size"] // cfg["patch_size"],) * 2
+        pos = resample_abs_pos_embed(pos, (img.shape[-2] // cfg["patch_size"], img.shape[-1] // cfg["patch_size"]), old, npt)
     if cfg.get("no_embed_class", False):
         if pos is not None:
             x = x + pos
@@ -315,6 +333,10 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
     B = x.shape[0]
     to_cat = [sd[k].expand(B, -1, -1) for k in ("cls_token", "reg_token") if k in sd]
     pos = sd.get("pos_embed")
+    if pos is not None and cfg.get("dynamic_img_size", False):
+        npt = 0 if cfg.get("no_embed_class", False) else sum(t.shape[1] for t in to_cat)
+        pos = resample_abs_pos_embed(pos, (img.shape[-2] // cfg["patch_size"], img.shape[-1] // cfg["patch_size"]),
+                                     (cfg["img_size"] // cfg["patch_size"],) * 2, npt)
     if cfg.get("no_embed_class", False):
         x = x + pos if pos is not None else x
         x = torch.cat(to_cat + [x], 1)

@@ -17,6 +17,7 @@ raises B200Error: there is no PyTorch fallback on this path.
 """
 import torch
 from torch import nn
+import torch.nn.functional as F
 
 from . import ops
 from ._lib import B200Error
@@ -454,10 +455,40 @@ def patch_embed_forward(pe, img):
     return y.view(B, (H // ph) * (W // pw), D)
 
 
+def resample_pos_embed(pos, new_size, old_size, num_prefix_tokens):
+    """resample_abs_pos_embed (timm/layers/pos_embed.py:19-59): the grid part of a learned position table [1, P + gh*gw, D]
+    resized to `new_size` by an antialiased bicubic interpolation in fp32 (a torch library call on a table of a few
+    hundred rows, as in the reference); the prefix rows are kept.  Differentiable: training resamples every step."""
+    if new_size[0] * new_size[1] + num_prefix_tokens == pos.shape[1] and new_size[0] == new_size[1]:
+        return pos
+    prefix, grid = pos[:, :num_prefix_tokens], pos[:, num_prefix_tokens:]
+    D = pos.shape[-1]
+    g = grid.float().reshape(1, old_size[0], old_size[1], D).permute(0, 3, 1, 2)
+    g = F.interpolate(g, size=tuple(new_size), mode="bicubic", antialias=True)
+    g = g.permute(0, 2, 3, 1).reshape(1, -1, D).to(pos.dtype)
+    return torch.cat([prefix, g], 1) if num_prefix_tokens else g
+
+
+def _dynamic_pos_embed(model, img):
+    """Position table for this input size of a dynamic_img_size model (_pos_embed, vision_transformer.py:1049-1058)."""
+    pe, pos = model.patch_embed, model.pos_embed
+    new = (img.shape[-2] // pe.patch_size[0], img.shape[-1] // pe.patch_size[1])
+    npt = 0 if getattr(model, "no_embed_class", False) else model.num_prefix_tokens
+    if torch.is_grad_enabled() and pos.requires_grad:
+        return resample_pos_embed(pos, new, pe.grid_size, npt)
+    key = (pos.data_ptr(), pos._version, new)
+    cache = getattr(model, "_b200_pos_cache", None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            cache = (key, resample_pos_embed(pos.detach(), new, pe.grid_size, npt).contiguous())
+        model._b200_pos_cache = cache
+    return cache[1]
+
+
 def vit_embed(model, img):
     """patch_embed + _pos_embed (+ norm_pre) of VisionTransformer.forward_features (:1238-1241)."""
-    if getattr(model, "dynamic_img_size", False):
-        raise B200Error("dynamic_img_size models are not supported by the fused path")
+    if getattr(model, "dynamic_img_size", False) and getattr(model.patch_embed, "dynamic_img_pad", False):
+        raise B200Error("dynamic_img_pad is not supported by the fused path")
     if not _is_identity(getattr(model, "patch_drop", None)):
         raise B200Error("patch dropout is not supported")
     _check_drop(getattr(model, "pos_drop", None), "pos_drop")
@@ -469,6 +500,8 @@ def vit_embed(model, img):
     if pre:
         prefix = (pre[0] if len(pre) == 1 else torch.cat(pre, 1)).reshape(n_prefix, D).contiguous()
     pos = model.pos_embed
+    if pos is not None and getattr(model, "dynamic_img_size", False):
+        pos = _dynamic_pos_embed(model, img)
     if pos is None and n_prefix == 0:
         x = proj
     elif torch.is_grad_enabled() and (proj.requires_grad or any(t is not None and t.requires_grad for t in pre + [pos])):

@@ -76,8 +76,8 @@ class VisionTransformer(nn.Module):
         assert global_pool in ("", "avg", "token"), f"global_pool={global_pool!r} is not supported by b200timm"
         assert class_token or global_pool != "token"
         assert pos_embed in ("", "none", "learn")
-        if dynamic_img_size or dynamic_img_pad or patch_drop_rate > 0 or embed_norm_layer is not None:
-            raise B200Error("dynamic_img_size / dynamic_img_pad / patch dropout / embed norm are not supported")
+        if dynamic_img_pad or patch_drop_rate > 0 or embed_norm_layer is not None:
+            raise B200Error("dynamic_img_pad / patch dropout / embed norm are not supported")
         use_fc_norm = global_pool == "avg" if fc_norm is None else fc_norm
         if isinstance(norm_layer, str):       # create_norm._NORM_MAP keys (timm/layers/create_norm.py:31-50)
             from .layers import RmsNorm
@@ -107,12 +107,13 @@ class VisionTransformer(nn.Module):
         self.has_class_token = class_token
         self.no_embed_class = no_embed_class
         self.pool_include_prefix = pool_include_prefix
-        self.dynamic_img_size = False
+        self.dynamic_img_size = dynamic_img_size
         self.grad_checkpointing = False
         self.attn_pool = None
 
+        embed_args = dict(strict_img_size=False) if dynamic_img_size else {}     # vision_transformer.py:818-821
         self.patch_embed = embed_layer(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
-                                       embed_dim=embed_dim, bias=not pre_norm, **dd)
+                                       embed_dim=embed_dim, bias=not pre_norm, **embed_args, **dd)
         num_patches = self.patch_embed.num_patches
         self.cls_token = nn.Parameter(torch.empty(1, 1, embed_dim, **dd)) if class_token else None
         self.reg_token = nn.Parameter(torch.empty(1, reg_tokens, embed_dim, **dd)) if reg_tokens else None

@@ -253,3 +253,26 @@ def test_long_sequence_vit_training_matches_oracle():
     ref_loss.backward()
     assert abs(loss.item() - ref_loss.item()) < 2e-2, (loss.item(), ref_loss.item())
     _check_grads(model, {k: v.grad for k, v in ref_sd.items()})
+
+
+def test_dynamic_img_size_vit_matches_reference_golden():
+    """dynamic_img_size=True (vision_transformer.py:1049-1058): a 64x64 model run on 96x80 inputs -- the learned position
+    table is resampled 4x4 -> 6x5 (antialiased bicubic, as the reference does it) and its gradient flows back through the
+    resampling; logits and every parameter gradient against the reference's golden; a nominal-size batch afterwards."""
+    import os
+    from b200timm.vision_transformer import VisionTransformer
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vit_g7_dynamic_img_size.pt"))
+    model = VisionTransformer(**fx["kwargs"])
+    model.load_state_dict(fx["state_dict"], strict=True)
+    model = model.cuda().to(torch.bfloat16)
+    img = fx["img"].cuda().bfloat16()
+    assert tuple(img.shape[-2:]) == (96, 80)
+    with torch.no_grad():
+        out = model.eval()(img)
+    torch.testing.assert_close(out.float().cpu(), fx["logits"], atol=2e-2, rtol=2e-2)
+    out = model.train()(img)
+    torch.testing.assert_close(out.float().cpu(), fx["logits"], atol=2e-2, rtol=2e-2)
+    out.float().mean().backward()
+    _check_grads(model, fx["grads"])
+    with torch.no_grad():
+        assert model.eval()(torch.randn(2, 3, 64, 64, device="cuda").bfloat16()).shape == (2, 10)
