@@ -194,6 +194,21 @@ B200_API int b200_qk_norm_bwd(void* dqkv, const void* save, const float* mean, c
                       const void* k_weight, int32_t param_dtype, float* dparams, int64_t T, int32_t H,
                       int32_t head_dim, int32_t rms, void* stream);
 
+/* ------------------------------------------------------------------ Global Response Norm (ConvNeXt-V2)
+ * GlobalResponseNorm inside GlobalResponseNormMlp, timm/layers/grn.py:17-49, mlp.py:251-295, on channels-last rows
+ * h bf16 [B, HW, C] (C = hidden width): gx = ||h[b,:,c]||_2, nx = gx / (mean_c gx + eps), h' = h * (1 + weight * nx) + bias.
+ * Forward, IN PLACE on h: gsq (fp32 [B, C], ZEROED by the caller) receives gx^2 and scale (fp32 [B, C]) the applied
+ * 1 + weight * nx; both are kept for the backward.
+ * Backward: dh2 = d loss / d h' (bf16 [B, HW, C]), pre = the fc1 pre-activation (h = GELU(pre) is recomputed);
+ * dpre = (dh2 * scale + h * t) * GELU'(pre), i.e. the gradient w.r.t. the pre-activation (GRN and GELU backward in one
+ * pass).  a_ws (fp32 [B, C], ZEROED) and t_ws (fp32 [B, C]) are workspaces; dweight (fp32 [C]) is ACCUMULATED into;
+ * the bias gradient is the column sum of dh2 (b200_colsum).                                                          */
+B200_API int b200_grn_fwd(void* h, float* gsq, float* scale, const void* weight, const void* bias, int32_t param_dtype,
+                  int32_t B, int32_t HW, int32_t C, float eps, void* stream);
+B200_API int b200_grn_bwd(const void* dh2, const void* pre, const float* gsq, const float* scale, const void* weight,
+                  int32_t param_dtype, float* a_ws, float* t_ws, float* dweight, void* dpre, int32_t B, int32_t HW,
+                  int32_t C, float eps, void* stream);
+
 /* ------------------------------------------------------------------ gated MLPs
  * GluMlp / SwiGLUPacked / SwiGLU, timm/layers/mlp.py:57-165: h = fc1(x) is bf16 [M, 2H]; the gate is the first half of
  * each row (gate_first=1: SwiGLUPacked `act(x1) * x2`, and SwiGLU with [fc1_g; fc1_x] stacked) or the second

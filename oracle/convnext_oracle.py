@@ -40,8 +40,12 @@ def block(x, sd, pre, eps, keep=None, keep_prob=1.0):
     keep mask [B] (1 = kept), applied as timm/layers/drop.py:158-175 does: branch * mask / keep_prob."""
     h = dwconv(x, sd[pre + "conv_dw.weight"], sd.get(pre + "conv_dw.bias")).permute(0, 2, 3, 1)      # :200,205
     h = layer_norm(h, sd[pre + "norm.weight"], sd[pre + "norm.bias"], eps)                             # :206
-    h = linear(gelu_erf(linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])),
-               sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"]).permute(0, 3, 1, 2)               # :207-208
+    h = gelu_erf(linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))
+    if pre + "mlp.grn.weight" in sd:     # ConvNeXt-V2: GlobalResponseNorm, timm/layers/grn.py:46-49 (eps 1e-6), mlp.py:289-292
+        gx = torch.sqrt((h * h).sum(dim=(1, 2), keepdim=True))
+        nx = gx / (gx.mean(dim=-1, keepdim=True) + 1e-6)
+        h = h + sd[pre + "mlp.grn.bias"] + sd[pre + "mlp.grn.weight"] * (h * nx)
+    h = linear(h, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"]).permute(0, 3, 1, 2)           # :207-208
     if pre + "gamma" in sd:
         h = h * sd[pre + "gamma"].view(1, -1, 1, 1)                                                    # :209-210
     if keep is not None:
@@ -99,8 +103,12 @@ def convnext_forward_eager(img, sd, cfg):
             k = sd[b + "conv_dw.weight"].shape[-1]
             h = F.conv2d(x, sd[b + "conv_dw.weight"], sd.get(b + "conv_dw.bias"), padding=k // 2, groups=x.shape[1])
             h = F.layer_norm(h.permute(0, 2, 3, 1), (x.shape[1],), sd[b + "norm.weight"], sd[b + "norm.bias"], eps)
-            h = F.linear(F.gelu(F.linear(h, sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"])),
-                         sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"]).permute(0, 3, 1, 2)
+            h = F.gelu(F.linear(h, sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"]))
+            if b + "mlp.grn.weight" in sd:      # GlobalResponseNorm.forward, timm/layers/grn.py:46-49
+                x_g = h.norm(p=2, dim=(1, 2), keepdim=True)
+                x_n = x_g / (x_g.mean(dim=-1, keepdim=True) + 1e-6)
+                h = h + torch.addcmul(sd[b + "mlp.grn.bias"].view(1, 1, 1, -1), sd[b + "mlp.grn.weight"].view(1, 1, 1, -1), h * x_n)
+            h = F.linear(h, sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"]).permute(0, 3, 1, 2)
             if b + "gamma" in sd:
                 h = h * sd[b + "gamma"].view(1, -1, 1, 1)
             x = h + x

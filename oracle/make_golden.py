@@ -63,7 +63,7 @@ def vit_case(name, seed, batch, kwargs, backward=True, input_size=None):
           "params", sum(p.numel() for p in model.parameters()))
 
 
-def convnext_case(name, seed, batch, kwargs, img_size):
+def convnext_case(name, seed, batch, kwargs, img_size, backward=False):
     import timm
     from timm.models.convnext import ConvNeXt
     torch.manual_seed(seed)
@@ -86,6 +86,10 @@ def convnext_case(name, seed, batch, kwargs, img_size):
     fx = {"kind": "convnext", "kwargs": kwargs, "state_dict": _half_sd(model.state_dict()), "img": img,
           "features": feats.detach(), "logits": logits.detach(), "stage_outputs": stage_out,
           "timm_version": timm.__version__, "torch_version": str(torch.__version__)}
+    if backward:        # the reference's backward test pattern (tests/test_models.py:209-242)
+        model.zero_grad()
+        model(img).mean().backward()
+        fx["grads"] = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
     torch.save(fx, os.path.join(OUT, name + ".pt"))
     print(name, "logits", tuple(logits.shape), "absmax", logits.abs().max().item(),
           "params", sum(p.numel() for p in model.parameters()))
@@ -381,7 +385,13 @@ DYN_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_
                   qkv_bias=True, dynamic_img_size=True, reg_tokens=1)
 
 
+CNX_V2_KWARGS = dict(depths=(1, 1, 2, 1), dims=(16, 32, 64, 128), num_classes=10, use_grn=True, ls_init_value=None)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "convnextv2":
+        os.makedirs(OUT, exist_ok=True)
+        return convnext_case("convnext_g2_v2_grn", 9, 2, CNX_V2_KWARGS, 64, backward=True)
     if len(sys.argv) > 1 and sys.argv[1] == "dynamic":
         os.makedirs(OUT, exist_ok=True)
         return vit_case("vit_g7_dynamic_img_size", 8, 2, DYN_KWARGS, input_size=(96, 80))
@@ -430,6 +440,7 @@ def main():
     glu_cases()
     qknorm_cases()
     vit_case("vit_g7_dynamic_img_size", 8, 2, DYN_KWARGS, input_size=(96, 80))
+    convnext_case("convnext_g2_v2_grn", 9, 2, CNX_V2_KWARGS, 64, backward=True)
 
 
 if __name__ == "__main__":

@@ -102,6 +102,8 @@ SIGNATURES = {
     "b200_avgpool_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "b200_qk_norm_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f32, _i32, _vp]),
     "b200_qk_norm_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "b200_grn_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "b200_grn_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "b200_glu_fwd": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "b200_glu_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "b200_sgd_step": (ctypes.c_int, [_otp, _i32, _i32, _f64, _f64, _f64, _f64, _i32, _i32, _vp, _vp]),

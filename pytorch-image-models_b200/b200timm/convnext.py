@@ -35,7 +35,7 @@ class _BlockFn(torch.autograd.Function):
     dx = dwconv(dy, spatially flipped weight) with the shortcut gradient folded in, dweight through the wgrad kernel."""
 
     @staticmethod
-    def forward(ctx, x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, rs, B, H, W, eps):
+    def forward(ctx, x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, rs, B, H, W, eps, gw=None, gb=None, geps=1e-6):
         from .autograd import _c
         C = x.shape[1]
         k = wdw.shape[-1]
@@ -44,20 +44,25 @@ class _BlockFn(torch.autograd.Function):
         h, mean, rstd = ops.layernorm_fwd(y, nw, nb, eps, save_stats=True)
         pre = torch.empty(x.shape[0], w1.shape[0], dtype=torch.bfloat16, device=x.device)
         act = ops.linear_fwd(h, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+        gsq = gscale = None
+        if gw is not None:          # ConvNeXt-V2: GlobalResponseNorm between GELU and fc2 (mlp.py:289-292), in place on act
+            gsq, gscale = ops.grn_fwd(act, gw, gb, B, H * W, geps)
         br = torch.empty_like(x) if gamma is not None else None
         out = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=_c(x), gamma=gamma, out2=br, row_scale=rs,
                              rows_per_scale=H * W)
-        ctx.save_for_backward(x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br, rs)
-        ctx.meta = (B, H, W, C, k)
+        ctx.save_for_backward(x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br, rs, gw, gb, gsq,
+                              gscale)
+        ctx.meta = (B, H, W, C, k, geps)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         from .autograd import _c, _to_param_dtype
-        x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br, rs = ctx.saved_tensors
-        B, H, W, C, k = ctx.meta
+        (x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br, rs, gw, gb, gsq,
+         gscale) = ctx.saved_tensors
+        B, H, W, C, k, geps = ctx.meta
         dout = _c(dout)
-        params = (bdw, nw, nb, w1, b1, w2, b2, gamma)
+        params = (bdw, nw, nb, w1, b1, w2, b2, gamma, gw, gb)
         sizes = [0 if p is None else p.numel() for p in params]
         offs = [0]
         for n in sizes:
@@ -71,7 +76,13 @@ class _BlockFn(torch.autograd.Function):
             if gamma is not None:
                 ops.colsum_mul(dout, br, rs, H * W, out=v[7], accumulate=True)
             dbr = ops.scale_rows_cols(dout, gamma, rs, H * W)
-        dpre = ops.linear_dgrad(dbr, w2, epilogue=ops.EPI_DGELU, aux=pre)
+        if gw is None:
+            dpre = ops.linear_dgrad(dbr, w2, epilogue=ops.EPI_DGELU, aux=pre)
+        else:                       # GRN + GELU backward in one pass over the hidden activations
+            dact = ops.linear_dgrad(dbr, w2)
+            if gb is not None:
+                ops.colsum(dact, out=v[9], accumulate=True)
+            dpre, _ = ops.grn_bwd(dact, pre, gsq, gscale, gw, B, H * W, geps, dweight=v[8])
         ops.linear_wgrad(dbr, act, out=v[5])
         if b2 is not None:
             ops.colsum(dbr, out=v[6], accumulate=True)
@@ -95,7 +106,7 @@ class _BlockFn(torch.autograd.Function):
                      for i, (p, o, n) in enumerate(zip(params, offs, sizes))]
         g_wdw = dwt.reshape(k * k, C).t().reshape(C, 1, k, k).to(wdw.dtype)     # [k,k,C] -> Conv2d layout (49*C values)
         return (dx.view(B * H * W, C), g_wdw, grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7],
-                None, None, None, None, None)
+                None, None, None, None, None, grads[8], grads[9], None)
 
 
 class _DownsampleFn(torch.autograd.Function):
@@ -154,6 +165,41 @@ class LayerNorm2d(nn.LayerNorm):
         raise B200Error("LayerNorm2d is applied channels-last inside ConvNeXt.forward; standalone NCHW use is not covered")
 
 
+class GlobalResponseNorm(nn.Module):
+    """Parameter holder of timm.layers.GlobalResponseNorm (grn.py:17-49), channels-last; applied by b200_grn_fwd."""
+
+    def __init__(self, dim: int, eps: float = 1e-6, channels_last: bool = True, device=None, dtype=None):
+        super().__init__()
+        if not channels_last:
+            raise B200Error("GlobalResponseNorm: channels-first is not covered")
+        self.eps = eps
+        self.weight = nn.Parameter(torch.zeros(dim, device=device, dtype=dtype))
+        self.bias = nn.Parameter(torch.zeros(dim, device=device, dtype=dtype))
+
+
+class GlobalResponseNormMlp(nn.Module):
+    """timm.layers.GlobalResponseNormMlp (mlp.py:251-295), Linear / channels-last form: fc1, GELU, GRN, fc2.  It runs
+    inside ConvNeXtBlock's fused forward (block_forward_nhwc), which needs the image's spatial extent."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, bias=True, drop=0.,
+                 use_conv=False, device=None, dtype=None):
+        super().__init__()
+        if use_conv:
+            raise B200Error("GlobalResponseNormMlp(use_conv=True) is not covered")
+        dd = {"device": device, "dtype": dtype}
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features, bias=bias, **dd)
+        self.act = act_layer()
+        self.drop1 = nn.Dropout(drop)
+        self.grn = GlobalResponseNorm(hidden_features, **dd)
+        self.fc2 = nn.Linear(hidden_features, out_features, bias=bias, **dd)
+        self.drop2 = nn.Dropout(drop)
+
+    def forward(self, x):
+        raise B200Error("GlobalResponseNormMlp runs inside ConvNeXtBlock (it needs the spatial extent of each image)")
+
+
 class ConvNeXtBlock(nn.Module):
     def __init__(self, in_chs: int, out_chs: Optional[int] = None, kernel_size: int = 7, stride: int = 1,
                  dilation=(1, 1), mlp_ratio: float = 4, conv_mlp: bool = False, conv_bias: bool = True,
@@ -162,13 +208,13 @@ class ConvNeXtBlock(nn.Module):
         super().__init__()
         dd = {"device": device, "dtype": dtype}
         out_chs = out_chs or in_chs
-        if conv_mlp or use_grn or stride != 1 or in_chs != out_chs or tuple(dilation) != (1, 1):
-            raise B200Error("ConvNeXtBlock: conv_mlp / GRN / strided / dilated blocks are not covered")
+        if conv_mlp or stride != 1 or in_chs != out_chs or tuple(dilation) != (1, 1):
+            raise B200Error("ConvNeXtBlock: conv_mlp / strided / dilated blocks are not covered")
         self.use_conv_mlp = False
         self.conv_dw = nn.Conv2d(in_chs, out_chs, kernel_size, stride=1, padding=kernel_size // 2, groups=in_chs,
                                  bias=conv_bias, **dd)
         self.norm = (norm_layer or nn.LayerNorm)(out_chs, **dd)
-        self.mlp = Mlp(out_chs, int(mlp_ratio * out_chs), act_layer=act_layer, **dd)
+        self.mlp = (GlobalResponseNormMlp if use_grn else Mlp)(out_chs, int(mlp_ratio * out_chs), act_layer=act_layer, **dd)
         self.gamma = nn.Parameter(ls_init_value * torch.ones(out_chs, **dd)) if ls_init_value is not None else None
         self.shortcut = nn.Identity()
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
@@ -188,10 +234,10 @@ def _check_block(blk):
     k = conv.kernel_size[0]
     if (getattr(blk, "use_conv_mlp", False) or not isinstance(blk.shortcut, nn.Identity) or conv.stride != (1, 1)
             or conv.dilation != (1, 1) or conv.groups != conv.in_channels or conv.in_channels != conv.out_channels
-            or conv.kernel_size != (k, k) or conv.padding != (k // 2, k // 2) or hasattr(blk.mlp, "grn")
+            or conv.kernel_size != (k, k) or conv.padding != (k // 2, k // 2)
             or type(blk.mlp.act).__name__ != "GELU" or getattr(blk.mlp.act, "approximate", "none") != "none"
             or type(blk.norm).__name__ not in ("LayerNorm",)):
-        raise B200Error("ConvNeXtBlock: conv_mlp / GRN / strided / dilated / non-GELU blocks are not covered")
+        raise B200Error("ConvNeXtBlock: conv_mlp / strided / dilated / non-GELU blocks are not covered")
 
 
 def block_forward_nhwc(self, x, B, H, W):
@@ -209,13 +255,17 @@ def block_forward_nhwc(self, x, B, H, W):
         if keep > 0.0 and getattr(dp, "scale_by_keep", True):
             rs = rs / keep
         rs = rs.contiguous()
+    grn = getattr(self.mlp, "grn", None)     # GlobalResponseNormMlp (ConvNeXt-V2, mlp.py:251-295)
     if x.requires_grad or _needs_grad(self):
+        extra = () if grn is None else (grn.weight, grn.bias, grn.eps)
         return _BlockFn.apply(x, _w(self.conv_dw), self.conv_dw.bias, self.norm.weight, self.norm.bias,
                               _w(self.mlp.fc1), self.mlp.fc1.bias, _w(self.mlp.fc2), self.mlp.fc2.bias,
-                              self.gamma, rs, B, H, W, self.norm.eps)
+                              self.gamma, rs, B, H, W, self.norm.eps, *extra)
     y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
     h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
     a = ops.linear_fwd(h, _w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    if grn is not None:
+        ops.grn_fwd(a, grn.weight, grn.bias, B, H * W, grn.eps)
     return ops.linear_fwd(a, _w(self.mlp.fc2), self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
                           gamma=self.gamma, row_scale=rs, rows_per_scale=H * W)
 
@@ -238,7 +288,7 @@ class ConvNeXtStage(nn.Module):
         drop_path_rates = drop_path_rates or [0.] * depth
         self.blocks = nn.Sequential(*[
             ConvNeXtBlock(in_chs=out_chs, out_chs=out_chs, kernel_size=kernel_size, drop_path=drop_path_rates[i],
-                          ls_init_value=ls_init_value, conv_bias=conv_bias, act_layer=act_layer,
+                          ls_init_value=ls_init_value, conv_bias=conv_bias, use_grn=use_grn, act_layer=act_layer,
                           norm_layer=norm_layer_cl, **dd)
             for i in range(depth)])
 
@@ -348,7 +398,7 @@ class ConvNeXt(nn.Module):
                  device=None, dtype=None):
         super().__init__()
         dd = {"device": device, "dtype": dtype}
-        if (stem_type != "patch" or output_stride != 32 or head_norm_first or conv_mlp or use_grn or norm_layer
+        if (stem_type != "patch" or output_stride != 32 or head_norm_first or conv_mlp or norm_layer
                 or global_pool != "avg" or (act_layer not in (None, "gelu", nn.GELU))):
             raise B200Error("ConvNeXt: only the patch-stem / LayerNorm / Linear-MLP / GELU / avg-pool configuration "
                             "is covered by the B200 path")
@@ -365,7 +415,7 @@ class ConvNeXt(nn.Module):
         for i in range(4):
             stages.append(ConvNeXtStage(prev, dims[i], kernel_size=ks[i], stride=2 if i > 0 else 1, depth=depths[i],
                                         drop_path_rates=rates[k:k + depths[i]], ls_init_value=ls_init_value,
-                                        conv_bias=conv_bias, act_layer=nn.GELU, norm_layer=ln2d, norm_layer_cl=ln, **dd))
+                                        conv_bias=conv_bias, use_grn=use_grn, act_layer=nn.GELU, norm_layer=ln2d, norm_layer_cl=ln, **dd))
             k += depths[i]
             prev = dims[i]
         self.stages = nn.Sequential(*stages)

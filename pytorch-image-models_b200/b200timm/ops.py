@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "set_input_norm", "input_norm", "glu_fwd", "glu_bwd", "qk_norm_fwd", "qk_norm_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
+    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "set_input_norm", "input_norm", "glu_fwd", "glu_bwd", "qk_norm_fwd", "qk_norm_bwd", "grn_fwd", "grn_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
 ]
 
 
@@ -534,6 +534,42 @@ def qk_norm_bwd(dqkv, raw, mean, rstd, qw, kw, T, H):
     _lib.check(rc, "b200_qk_norm_bwd")
     _count()
     return dparams
+
+
+# --------------------------------------------------------------------------------------------- Global Response Norm
+def grn_fwd(h, weight, bias, B, HW, eps=1e-6):
+    """GlobalResponseNorm (timm/layers/grn.py:46-49) IN PLACE on channels-last rows h bf16 [B*HW, C].  Returns the saved
+    (gsq fp32 [B, C], scale fp32 [B, C]) pair the backward needs."""
+    _need_cuda(h, weight, bias)
+    C = h.shape[-1]
+    if h.dtype != torch.bfloat16 or not h.is_contiguous() or h.numel() != B * HW * C or C % 8:
+        raise B200Error("grn_fwd: h must be contiguous bf16 [B*HW, C] with C % 8 == 0")
+    gsq = torch.zeros(B, C, dtype=torch.float32, device=h.device)
+    scale = torch.empty(B, C, dtype=torch.float32, device=h.device)
+    rc = _lib.load().b200_grn_fwd(h.data_ptr(), gsq.data_ptr(), scale.data_ptr(), weight.data_ptr(), _ptr(bias),
+                                  _param_dtype(weight, bias), B, HW, C, float(eps), _stream())
+    _lib.check(rc, "b200_grn_fwd")
+    _count(3)
+    return gsq, scale
+
+
+def grn_bwd(dh2, pre, gsq, scale, weight, B, HW, eps=1e-6, dweight=None):
+    """Returns (dpre bf16 [B*HW, C] = gradient w.r.t. the fc1 pre-activation (GRN + GELU backward), dweight fp32 [C])."""
+    _need_cuda(dh2, pre, gsq, scale, weight)
+    C = pre.shape[-1]
+    for t, name in ((dh2, "dh2"), (pre, "pre")):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.numel() != B * HW * C:
+            raise B200Error(f"grn_bwd: {name} must be contiguous bf16 [B*HW, C]")
+    ws = torch.zeros(2, B, C, dtype=torch.float32, device=pre.device)
+    if dweight is None:
+        dweight = torch.zeros(C, dtype=torch.float32, device=pre.device)
+    dpre = torch.empty_like(pre)
+    rc = _lib.load().b200_grn_bwd(dh2.data_ptr(), pre.data_ptr(), gsq.data_ptr(), scale.data_ptr(), weight.data_ptr(),
+                                  _param_dtype(weight), ws[0].data_ptr(), ws[1].data_ptr(), dweight.data_ptr(),
+                                  dpre.data_ptr(), B, HW, C, float(eps), _stream())
+    _lib.check(rc, "b200_grn_bwd")
+    _count(3)
+    return dpre, dweight
 
 
 # --------------------------------------------------------------------------------------------- gated MLPs

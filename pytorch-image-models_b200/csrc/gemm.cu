@@ -25,6 +25,7 @@
 // serves forward, dgrad (B MN-major) and wgrad (A and B MN-major) without transposes.
 #include "common.h"
 #include "ptx.cuh"
+#include "gelu.cuh"
 
 namespace b200 {
 
@@ -67,55 +68,6 @@ struct GemmSmem {
   static constexpr int kBarrierOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarrierOffset + 512 + 1024;  // + barriers + alignment slack
 };
-
-// erf(x / sqrt2) for a pair, Abramowitz-Stegun 7.1.28:  erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16, |err| < 3e-7.
-// One MUFU (rcp) per element; for large |z| the power overflows to +inf and rcp gives 0, i.e. erf -> 1.
-__device__ __forceinline__ f32x2 erf_pair(f32x2 x) {
-  float x0, x1;
-  upk(x, x0, x1);
-  const f32x2 z = pk(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
-  f32x2 q = fma2(z, splat(0.0000430638f), splat(0.0002765672f));
-  q = fma2(q, z, splat(0.0001520143f));
-  q = fma2(q, z, splat(0.0092705272f));
-  q = fma2(q, z, splat(0.0422820123f));
-  q = fma2(q, z, splat(0.0705230784f));
-  q = fma2(q, z, splat(1.0f));
-  q = mul2(q, q);
-  q = mul2(q, q);
-  q = mul2(q, q);
-  q = mul2(q, q);
-  float d0, d1;
-  upk(q, d0, d1);
-  const float a0 = 1.0f - rcp_approx(d0), a1 = 1.0f - rcp_approx(d1);
-  return pk(copysignf(a0, x0), copysignf(a1, x1));
-}
-__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
-  return mul2(x, fma2(erf_pair(x), splat(0.5f), splat(0.5f)));     // 0.5 x (1 + erf(x / sqrt2))
-}
-__device__ __forceinline__ f32x2 dgelu_erf2(f32x2 x) {
-  // d/dx [x Phi(x)] = Phi(x) + x phi(x),  phi(x) = exp(-x^2 / 2) / sqrt(2 pi).
-  // Phi through Abramowitz-Stegun 7.1.26, which shares the exponential phi needs anyway:
-  //   erfc(z) = (a1 t + ... + a5 t^5) e^{-z^2},  t = 1 / (1 + p z),  z = |x| / sqrt2,  |err| <= 1.5e-7
-  //   q = erfc(z) / 2 = Phi(-|x|);   Phi(x) = 1/2 + copysign(1/2 - q, x)
-  float x0, x1;
-  upk(x, x0, x1);
-  const f32x2 ax = pk(fabsf(x0), fabsf(x1));
-  float d0, d1;
-  upk(fma2(ax, splat(0.3275911f * 0.70710678118654752f), splat(1.0f)), d0, d1);
-  const f32x2 t = pk(rcp_approx(d0), rcp_approx(d1));
-  f32x2 q = fma2(t, splat(0.5f * 1.061405429f), splat(0.5f * -1.453152027f));
-  q = fma2(q, t, splat(0.5f * 1.421413741f));
-  q = fma2(q, t, splat(0.5f * -0.284496736f));
-  q = fma2(q, t, splat(0.5f * 0.254829592f));
-  q = mul2(q, t);
-  float w0, w1;
-  upk(mul2(mul2(x, x), splat(-0.72134752044448170f)), w0, w1);     // -x^2/2 * log2(e)
-  const f32x2 e = pk(ex2_approx(w0), ex2_approx(w1));
-  float s0, s1;
-  upk(fma2(q, mul2(e, splat(-1.0f)), splat(0.5f)), s0, s1);        // 1/2 - q e  (>= 0)
-  const f32x2 cdf = add2(pk(copysignf(s0, x0), copysignf(s1, x1)), splat(0.5f));
-  return fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);
-}
 
 // 8 consecutive parameters (bias / LayerScale gamma) starting at column `col`, as 4 fp32 pairs
 __device__ __forceinline__ void load8_param2(const void* base, int f32, int col, f32x2 (&v)[4]) {

@@ -213,3 +213,50 @@ def test_convnext_amp_fp32_master_weights():
     model.eval()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         assert torch.isfinite(model(img.cuda()).float()).all()
+
+
+def test_grn_kernels_match_torch():
+    """b200_grn_fwd / b200_grn_bwd against the reference formula (timm/layers/grn.py:46-49) and its autograd, with GELU in
+    front as in GlobalResponseNormMlp (the backward kernel returns the gradient w.r.t. the pre-activation)."""
+    from b200timm import ops
+    torch.manual_seed(0)
+    B, HW, C = 5, 77, 136
+    pre = torch.randn(B * HW, C, device="cuda").bfloat16()
+    w = (torch.randn(C, device="cuda") * 0.3).bfloat16()
+    b = (torch.randn(C, device="cuda") * 0.1).bfloat16()
+    d = torch.randn(B * HW, C, device="cuda").bfloat16()
+    pf = pre.float().requires_grad_(True)
+    wf, bf = w.float().requires_grad_(True), b.float().requires_grad_(True)
+    h = torch.nn.functional.gelu(pf).view(B, HW, C)
+    gx = h.norm(p=2, dim=1, keepdim=True)
+    nx = gx / (gx.mean(dim=-1, keepdim=True) + 1e-6)
+    ref = (h + torch.addcmul(bf.view(1, 1, -1), wf.view(1, 1, -1), h * nx)).view(B * HW, C)
+    ref.backward(d.float())
+    act = torch.nn.functional.gelu(pre.float()).bfloat16()
+    gsq, scale = ops.grn_fwd(act, w, b, B, HW)
+    _check(act, ref.detach(), 3e-2, 2e-2, "grn forward")
+    dpre, dw = ops.grn_bwd(d, pre, gsq, scale, w, B, HW)
+    _check(dpre, pf.grad, 4e-2, 4e-2, "grn + gelu backward", min_cos=0.9995)
+    _check(dw, wf.grad, 2e-2 * wf.grad.abs().max().item(), 2e-2, "grn weight gradient")
+
+
+def test_convnext_v2_grn_matches_reference_golden():
+    """ConvNeXt-V2 blocks (use_grn=True, no LayerScale): inference and a training step against the reference's logits
+    and parameter gradients (tests/golden/convnext_g2_v2_grn.pt)."""
+    from b200timm.convnext import ConvNeXt
+    from test_gpu_train import _check_grads
+    fx = torch.load(os.path.join(GOLDEN, "convnext_g2_v2_grn.pt"))
+    model = ConvNeXt(**fx["kwargs"])
+    model.load_state_dict(fx["state_dict"], strict=True)
+    model = model.cuda().to(torch.bfloat16)
+    img = fx["img"].cuda().bfloat16()
+    with torch.no_grad():
+        feats = model.eval().forward_features(img)
+        logits = model(img)
+    _check(feats, fx["features"], 8e-2, 3e-2, "V2 features vs timm golden")
+    _check(logits, fx["logits"], 2e-2, 2e-2, "V2 logits vs timm golden")
+    out = model.train()(img)
+    _check(out, fx["logits"], 2e-2, 2e-2, "V2 training-mode logits vs timm golden")
+    out.float().mean().backward()
+    _check_grads(model, fx["grads"], rel_tol=6e-2, min_cos=0.997)
+

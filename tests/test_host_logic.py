@@ -88,6 +88,10 @@ def test_convnext_state_dict_matches_timm():
     model = ConvNeXt(**fx["kwargs"])
     assert list(model.state_dict().keys()) == list(fx["state_dict"].keys())
     model.load_state_dict(fx["state_dict"], strict=True)
+    fx2 = torch.load(os.path.join(GOLDEN, "convnext_g2_v2_grn.pt"))         # ConvNeXt-V2: mlp.grn.{weight,bias}, no gamma
+    m2 = ConvNeXt(**fx2["kwargs"])
+    assert list(m2.state_dict().keys()) == list(fx2["state_dict"].keys())
+    m2.load_state_dict(fx2["state_dict"], strict=True)
     n = sum(p.numel() for p in create_convnext("convnext_base").parameters())
     assert abs(n / 1e6 - 88.59) < 0.01     # results/benchmark-*.csv param_count for convnext_base
     with pytest.raises(B200Error):

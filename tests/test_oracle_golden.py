@@ -87,9 +87,10 @@ def test_layer_goldens():
     torch.testing.assert_close(O.drop_path(dp["x"], dp["keep_mask"], 1.0 - dp["drop_prob"]), dp["y"])
 
 
-def test_convnext_oracle_matches_reference():
+@pytest.mark.parametrize("name", ["convnext_g1", "convnext_g2_v2_grn"])
+def test_convnext_oracle_matches_reference(name):
     from oracle import convnext_oracle as C
-    fx = torch.load(os.path.join(GOLDEN, "convnext_g1.pt"))
+    fx = torch.load(os.path.join(GOLDEN, name + ".pt"))
     cfg = dict(fx["kwargs"])
     with torch.no_grad():
         feats, stages = C.convnext_forward_features(fx["img"], fx["state_dict"], cfg, return_stages=True)
@@ -263,3 +264,16 @@ def test_attention_norm_oracle_matches_reference(name):
     torch.testing.assert_close(x.grad, fx["dx"], atol=2e-4, rtol=1e-3)
     for k, g in fx["grads"].items():
         torch.testing.assert_close(sd[k].grad, g, atol=5e-4, rtol=1e-3, msg=lambda m: f"{k}: {m}")
+
+
+def test_convnext_v2_oracle_autograd_matches_reference_grads():
+    """ConvNeXt-V2 (GlobalResponseNorm in every block): autograd of the oracle against the reference's parameter gradients."""
+    from oracle import convnext_oracle as C
+    fx = torch.load(os.path.join(GOLDEN, "convnext_g2_v2_grn.pt"))
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    C.convnext_forward(fx["img"], sd, dict(fx["kwargs"])).mean().backward()
+    assert sorted(sd) == sorted(fx["grads"])
+    for k, g in fx["grads"].items():
+        assert torch.allclose(sd[k].grad, g, atol=1e-7 + 2e-4 * g.abs().max().item(), rtol=2e-3), (
+            k, (sd[k].grad - g).abs().max().item(), g.abs().max().item())
+
