@@ -496,6 +496,10 @@ MODEL_ARGS = {
     "convnext_small": dict(depths=(3, 3, 27, 3), dims=(96, 192, 384, 768)),
     "convnext_base": dict(depths=(3, 3, 27, 3), dims=(128, 256, 512, 1024)),       # convnext.py:1293-1296
     "convnext_large": dict(depths=(3, 3, 27, 3), dims=(192, 384, 768, 1536)),
+    # ConvNeXt-V2 (Global Response Norm in the MLP, no LayerScale), convnext.py:1365-1387
+    "convnextv2_tiny": dict(depths=(3, 3, 9, 3), dims=(96, 192, 384, 768), use_grn=True, ls_init_value=None),
+    "convnextv2_base": dict(depths=(3, 3, 27, 3), dims=(128, 256, 512, 1024), use_grn=True, ls_init_value=None),
+    "convnextv2_large": dict(depths=(3, 3, 27, 3), dims=(192, 384, 768, 1536), use_grn=True, ls_init_value=None),
 }
 
 
