@@ -385,10 +385,15 @@ DYN_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_
                   qkv_bias=True, dynamic_img_size=True, reg_tokens=1)
 
 
+MAP_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=1, num_heads=2, mlp_ratio=2.0,
+                  qkv_bias=True, class_token=False, global_pool="map")        # SigLIP-style head (vision_transformer.py:882-890)
 CNX_V2_KWARGS = dict(depths=(1, 1, 2, 1), dims=(16, 32, 64, 128), num_classes=10, use_grn=True, ls_init_value=None)
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "map":
+        os.makedirs(OUT, exist_ok=True)
+        return vit_case("vit_g8_map_pool", 10, 3, MAP_KWARGS)
     if len(sys.argv) > 1 and sys.argv[1] == "convnextv2":
         os.makedirs(OUT, exist_ok=True)
         return convnext_case("convnext_g2_v2_grn", 9, 2, CNX_V2_KWARGS, 64, backward=True)
@@ -441,6 +446,7 @@ def main():
     qknorm_cases()
     vit_case("vit_g7_dynamic_img_size", 8, 2, DYN_KWARGS, input_size=(96, 80))
     convnext_case("convnext_g2_v2_grn", 9, 2, CNX_V2_KWARGS, 64, backward=True)
+    vit_case("vit_g8_map_pool", 10, 3, MAP_KWARGS)
 
 
 if __name__ == "__main__":

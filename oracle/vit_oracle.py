@@ -150,6 +150,24 @@ def glu_mlp(x, sd, prefix, eps=1e-6, act="silu", gate_last=False):
     return linear(h, g("fc2.weight"), g("fc2.bias"))
 
 
+def attention_pool_latent(x, sd, prefix, num_heads, eps=1e-6):
+    """AttentionPoolLatent.forward, timm/layers/attention_pool.py:95-128 (latent_len 1, no qk_norm / pos_embed, token pool):
+    q = q(latent), k, v = kv(x); softmax(q k^T / sqrt(hd)) v; proj; x + mlp(norm(x)); x[:, 0]."""
+    B, N, C = x.shape
+    hd = C // num_heads
+    g = lambda k: sd.get(prefix + k)  # noqa: E731
+    q = linear(g("latent").expand(B, -1, -1), g("q.weight"), g("q.bias")).reshape(B, 1, num_heads, hd).transpose(1, 2)
+    kv = linear(x, g("kv.weight"), g("kv.bias")).reshape(B, N, 2, num_heads, hd).permute(2, 0, 3, 1, 4)
+    k, v = kv.unbind(0)
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    p = torch.softmax(s, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(B, 1, C)
+    o = linear(o, g("proj.weight"), g("proj.bias"))
+    h = norm(o, sd, prefix + "norm.", eps) if g("norm.weight") is not None else o
+    o = o + mlp(h, g("mlp.fc1.weight"), g("mlp.fc1.bias"), g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+    return o[:, 0]
+
+
 def drop_path(x, keep_mask, keep_prob, scale_by_keep=True):
     """timm/layers/drop.py:158-175 with the Bernoulli draw made explicit: keep_mask is a 0/1 tensor [B]."""
     m = keep_mask.to(x.dtype).view(-1, *([1] * (x.dim() - 1)))
@@ -250,6 +268,8 @@ def vit_forward_head(x, sd, cfg):
         x = x[:, 0]
     elif pool == "avg":
         x = x[:, npre:].mean(1)
+    elif pool == "map":                                              # :1265-1269 (prefix tokens excluded)
+        x = attention_pool_latent(x[:, npre:], sd, "attn_pool.", cfg["num_heads"], cfg.get("eps", 1e-6))
     elif pool:
         raise ValueError(f"oracle: pool {pool!r} not restated")
     if "fc_norm.weight" in sd:
@@ -382,6 +402,19 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
         x = x[:, 0]
     elif pool == "avg":
         x = x[:, cfg.get("num_prefix_tokens", 1):].mean(1)
+    elif pool == "map":      # AttentionPoolLatent.forward, attention_pool.py:95-128, as its eager call sequence
+        x = x[:, cfg.get("num_prefix_tokens", 1):]
+        Bp, Np, C = x.shape
+        q = F.linear(sd["attn_pool.latent"].expand(Bp, -1, -1), sd["attn_pool.q.weight"], sd.get("attn_pool.q.bias"))
+        q = q.reshape(Bp, 1, H, C // H).transpose(1, 2)
+        kv = F.linear(x, sd["attn_pool.kv.weight"], sd.get("attn_pool.kv.bias")).reshape(Bp, Np, 2, H, C // H)
+        k, v = kv.permute(2, 0, 3, 1, 4).unbind(0)
+        x = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(Bp, 1, C)
+        x = F.linear(x, sd["attn_pool.proj.weight"], sd.get("attn_pool.proj.bias"))
+        h = _eager_norm(x, sd, "attn_pool.norm.", eps) if "attn_pool.norm.weight" in sd else x
+        h = F.linear(F.gelu(F.linear(h, sd["attn_pool.mlp.fc1.weight"], sd.get("attn_pool.mlp.fc1.bias"))),
+                     sd["attn_pool.mlp.fc2.weight"], sd.get("attn_pool.mlp.fc2.bias"))
+        x = (x + h)[:, 0]
     if "fc_norm.weight" in sd:
         x = _eager_norm(x, sd, "fc_norm.", eps)
     if "head.weight" in sd:

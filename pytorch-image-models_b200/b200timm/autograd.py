@@ -460,3 +460,35 @@ class AttentionNormFn(torch.autograd.Function):
         return (dx, _wgrad(dqkv, x2, wqkv), _bias_grad(dqkv, bqkv), _wgrad(dy2, on, wproj), _bias_grad(dy2, bproj),
                 gq[0], gq[1], gq[2], gq[3], gnw, gnb, None, None, None, None, None)
 
+
+class AttnPoolFn(torch.autograd.Function):
+    """The attention of AttentionPoolLatent (timm/layers/attention_pool.py:95-117, latent_len 1): one latent query per
+    image attends over the N tokens.  It runs on the self-attention kernels: the kv projection is written straight into
+    the k / v columns of a [B, N, 3, H, 64] buffer, the projected latent becomes query row 0 of every image (the other
+    query rows are zero and their outputs are never read), and output row 0 is the pooled vector.  The backward feeds
+    d(out) as row 0 of an otherwise zero gradient: rows with zero upstream gradient contribute nothing to dK / dV."""
+
+    @staticmethod
+    def forward(ctx, x, q, wkv, bkv, num_heads, scale):
+        B, N, D = x.shape
+        x2 = _c(x.reshape(B * N, D))
+        qkv = torch.zeros(B * N, 3 * D, dtype=torch.bfloat16, device=x.device)
+        ops.linear_fwd(x2, wkv, bkv, out=qkv[:, D:])
+        qkv.view(B, N, 3 * D)[:, 0, :D] = q.reshape(1, D)
+        o, lse = ops.attention_fwd(qkv, B, N, num_heads, D // num_heads, scale, None, need_lse=True)
+        ctx.save_for_backward(x2, wkv, bkv, qkv, o, lse)
+        ctx.meta = (B, N, D, num_heads, scale, q.shape, q.dtype)
+        return o[:, 0].contiguous()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wkv, bkv, qkv, o, lse = ctx.saved_tensors
+        B, N, D, H, scale, qshape, qdtype = ctx.meta
+        dout = torch.zeros(B, N, D, dtype=torch.bfloat16, device=dy.device)
+        dout[:, 0] = dy
+        dqkv = ops.attention_bwd(qkv, o, dout, lse, B, N, H, D // H, scale, None).view(B * N, 3 * D)
+        dq = dqkv.view(B, N, 3 * D)[:, 0, :D].float().sum(0).to(qdtype).reshape(qshape)
+        dkv = dqkv[:, D:].contiguous()                      # once per step, on the pooling head only
+        dx = ops.linear_dgrad(dkv, wkv).view(B, N, D)
+        return dx, dq, _wgrad(dkv, x2, wkv), _bias_grad(dkv, bkv), None, None
+

@@ -526,10 +526,59 @@ def vit_forward_features(model, img, kv_len=None, final_norm=True):
     return x
 
 
+def _linear(lin, x):
+    """nn.Linear on [..., K] bf16 activations through LinearFn (training) or the GEMM (inference)."""
+    if _needs_grad(x, lin):
+        from .autograd import LinearFn
+        return LinearFn.apply(x, _w(lin), lin.bias)
+    shape = x.shape
+    x2 = _bf16_2d(x, shape[-1])
+    if lin.weight.shape[0] % 8:
+        _w(lin)
+        return _padded_out_linear(lin, x2).reshape(*shape[:-1], -1)
+    return ops.linear_fwd(x2, _w(lin), lin.bias).view(*shape[:-1], -1)
+
+
+def attention_pool_forward(pool, x):
+    """AttentionPoolLatent.forward (timm/layers/attention_pool.py:95-128) for one latent (SigLIP's 'map' head): latent ->
+    q projection; tokens -> kv projection; single-query attention on the self-attention kernels (autograd.AttnPoolFn);
+    proj; x + mlp(norm(x)); token pooling."""
+    if pool.latent_len != 1 or getattr(pool, "pos_embed", None) is not None or pool.pool != "token":
+        raise B200Error("AttentionPoolLatent: only latent_len=1, no position embedding, token pooling is covered")
+    if not _is_identity(pool.q_norm) or not _is_identity(pool.k_norm):
+        raise B200Error("AttentionPoolLatent with qk_norm is not covered")
+    if pool.head_dim != 64:
+        raise B200Error(f"head_dim {pool.head_dim} is not supported (64 only)")
+    _check_drop(getattr(pool, "proj_drop", None), "proj_drop")
+    B, N, D = x.shape
+    _bf16_2d(x, D)
+    latent = pool.latent.reshape(1, D)
+    q = _linear(pool.q, latent if latent.dtype == torch.bfloat16 else latent.to(torch.bfloat16))
+    if _needs_grad(x, pool):
+        from .autograd import AttnPoolFn
+        o = AttnPoolFn.apply(x, q, _w(pool.kv), pool.kv.bias, pool.num_heads, pool.scale)
+    else:
+        qkv = torch.zeros(B * N, 3 * D, dtype=torch.bfloat16, device=x.device)
+        ops.linear_fwd(_bf16_2d(x, D), _w(pool.kv), pool.kv.bias, out=qkv[:, D:])
+        qkv.view(B, N, 3 * D)[:, 0, :D] = q.reshape(1, D)
+        o = ops.attention_fwd(qkv, B, N, pool.num_heads, 64, pool.scale, None)[0][:, 0].contiguous()
+    if _is_identity(pool.proj):
+        return o
+    o = _linear(pool.proj, o)
+    if pool.mlp is not None:
+        h = o if _is_identity(pool.norm) else layernorm(pool.norm, o)
+        o = o + mlp_forward(pool.mlp, h)
+    return o
+
+
 def vit_pool(model, x):
     """VisionTransformer.pool / global_pool_nlc (:686-708, :1254-1277) for token / avg pooling."""
-    if getattr(model, "attn_pool", None) is not None:
-        raise B200Error("attention pooling heads are not supported")
+    if getattr(model, "attn_pool", None) is not None:                     # :1265-1269
+        if type(model.attn_pool).__name__ != "AttentionPoolLatent":
+            raise B200Error(f"{type(model.attn_pool).__name__} pooling is not supported")
+        if not getattr(model, "pool_include_prefix", False) and model.num_prefix_tokens:
+            x = x[:, model.num_prefix_tokens:].contiguous()
+        return attention_pool_forward(model.attn_pool, x)
     pool = model.global_pool
     if pool == "token":
         return x[:, 0]

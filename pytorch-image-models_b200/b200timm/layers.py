@@ -154,6 +154,47 @@ class SwiGLU(nn.Module):
         return BF.glu_mlp_forward(self, x)
 
 
+class AttentionPoolLatent(nn.Module):
+    """timm.layers.AttentionPoolLatent (attention_pool.py:13-128), the 'map' pooling head of SigLIP-style ViTs: one
+    learned latent query attends over the tokens, followed by proj and x + mlp(norm(x))."""
+
+    def __init__(self, in_features: int, out_features: int = None, embed_dim: int = None, num_heads: int = 8,
+                 feat_size: Optional[int] = None, mlp_ratio: float = 4.0, qkv_bias: bool = True, qk_norm: bool = False,
+                 latent_len: int = 1, latent_dim: int = None, pos_embed: str = "", pool_type: str = "token",
+                 norm_layer=None, act_layer=nn.GELU, drop: float = 0.0, device=None, dtype=None):
+        super().__init__()
+        dd = {"device": device, "dtype": dtype}
+        embed_dim = embed_dim or in_features
+        if out_features is None:
+            out_features = in_features
+        if qk_norm or latent_len != 1 or pos_embed or pool_type != "token" or embed_dim != in_features:
+            raise B200Error("AttentionPoolLatent: qk_norm / latent_len > 1 / position embedding / avg pooling are not covered")
+        assert embed_dim % num_heads == 0
+        self.num_heads, self.head_dim = num_heads, embed_dim // num_heads
+        self.feat_size, self.scale, self.pool = feat_size, (embed_dim // num_heads) ** -0.5, pool_type
+        self.pos_embed = None
+        self.latent_dim, self.latent_len = latent_dim or embed_dim, latent_len
+        self.latent = nn.Parameter(torch.zeros(1, latent_len, embed_dim, **dd))
+        self.q = nn.Linear(embed_dim, embed_dim, bias=qkv_bias, **dd)
+        self.kv = nn.Linear(embed_dim, embed_dim * 2, bias=qkv_bias, **dd)
+        self.q_norm, self.k_norm = nn.Identity(), nn.Identity()
+        if out_features > 0:
+            self.proj = nn.Linear(embed_dim, out_features, **dd)
+            self.proj_drop = nn.Dropout(drop)
+            self.norm = norm_layer(out_features, **dd) if norm_layer is not None else nn.Identity()
+            self.mlp = Mlp(out_features, int(out_features * mlp_ratio), out_features=out_features, act_layer=act_layer, **dd)
+        else:
+            self.proj, self.proj_drop, self.norm, self.mlp = nn.Identity(), nn.Dropout(drop), nn.Identity(), None
+            out_features = embed_dim
+        self.out_features = out_features
+        nn.init.trunc_normal_(self.latent, std=self.latent_dim ** -0.5)
+
+    def forward(self, x, attn_mask: Optional[torch.Tensor] = None):
+        if attn_mask is not None:
+            raise B200Error("AttentionPoolLatent: masks are not covered")
+        return BF.attention_pool_forward(self, x)
+
+
 class RmsNorm(nn.Module):
     """timm.layers.RmsNorm (norm.py:202-248): y = x * rsqrt(mean(x^2) + eps) * weight."""
 

@@ -174,6 +174,7 @@ def _install_training_tail():
 def _table():
     """(qualified name, class, attribute, fast function) of every forward the plugin covers."""
     from timm.layers.attention import Attention, AttentionRope
+    from timm.layers.attention_pool import AttentionPoolLatent
     from timm.layers.mlp import GluMlp, Mlp, SwiGLU
     from timm.layers.norm import LayerNorm, RmsNorm
     from timm.layers.patch_embed import PatchEmbed
@@ -186,6 +187,9 @@ def _table():
         ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
         ("timm.layers.GluMlp.forward", GluMlp, "forward", lambda self, x: BF.glu_mlp_forward(self, x)),
         ("timm.layers.SwiGLU.forward", SwiGLU, "forward", lambda self, x: BF.glu_mlp_forward(self, x)),
+        ("timm.layers.AttentionPoolLatent.forward", AttentionPoolLatent, "forward",
+         lambda self, x, attn_mask=None: BF.attention_pool_forward(self, x) if attn_mask is None
+         else (_ for _ in ()).throw(B200Error("masked attention pooling"))),
         ("timm.layers.Attention.forward", Attention, "forward", _attention),
         ("timm.layers.AttentionRope.forward", AttentionRope, "forward", _attention_rope),
         ("timm.models.eva.EvaAttention.forward", EvaAttention, "forward", _attention_rope),

@@ -73,7 +73,7 @@ class VisionTransformer(nn.Module):
                  device=None, dtype=None):
         super().__init__()
         dd = {"device": device, "dtype": dtype}
-        assert global_pool in ("", "avg", "token"), f"global_pool={global_pool!r} is not supported by b200timm"
+        assert global_pool in ("", "avg", "token", "map"), f"global_pool={global_pool!r} is not supported by b200timm"
         assert class_token or global_pool != "token"
         assert pos_embed in ("", "none", "learn")
         if dynamic_img_pad or patch_drop_rate > 0 or embed_norm_layer is not None:
@@ -109,7 +109,7 @@ class VisionTransformer(nn.Module):
         self.pool_include_prefix = pool_include_prefix
         self.dynamic_img_size = dynamic_img_size
         self.grad_checkpointing = False
-        self.attn_pool = None
+        self.attn_pool = None       # replaced below for global_pool='map' (vision_transformer.py:882-890)
 
         embed_args = dict(strict_img_size=False) if dynamic_img_size else {}     # vision_transformer.py:818-821
         self.patch_embed = embed_layer(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
@@ -134,6 +134,10 @@ class VisionTransformer(nn.Module):
                      depth=i, **dd)
             for i in range(depth)])
         self.norm = norm_layer(embed_dim, **dd) if final_norm and not use_fc_norm else nn.Identity()
+        if global_pool == "map":
+            from .layers import AttentionPoolLatent
+            self.attn_pool = AttentionPoolLatent(embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, norm_layer=norm_layer,
+                                                 act_layer=act_layer, **dd)
         self.fc_norm = norm_layer(embed_dim, **dd) if final_norm and use_fc_norm else nn.Identity()
         self.head_drop = nn.Dropout(drop_rate)
         self.head = nn.Linear(embed_dim, num_classes, **dd) if num_classes > 0 else nn.Identity()

@@ -276,3 +276,24 @@ def test_dynamic_img_size_vit_matches_reference_golden():
     _check_grads(model, fx["grads"])
     with torch.no_grad():
         assert model.eval()(torch.randn(2, 3, 64, 64, device="cuda").bfloat16()).shape == (2, 10)
+
+
+def test_attention_pool_map_head_matches_reference_golden():
+    """global_pool='map' (AttentionPoolLatent, the SigLIP head; timm/layers/attention_pool.py:95-128) without a class
+    token: the single-query attention runs on the self-attention kernels (query row 0 of a packed qkv buffer).  Logits
+    and every parameter gradient (latent, q, kv, proj, norm, mlp) against the reference's golden."""
+    import os
+    from b200timm.vision_transformer import VisionTransformer
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vit_g8_map_pool.pt"))
+    model = VisionTransformer(**fx["kwargs"])
+    assert sorted(model.state_dict()) == sorted(fx["state_dict"])
+    model.load_state_dict(fx["state_dict"], strict=True)
+    model = model.cuda().to(torch.bfloat16)
+    img = fx["img"].cuda().bfloat16()
+    with torch.no_grad():
+        out = model.eval()(img)
+    torch.testing.assert_close(out.float().cpu(), fx["logits"], atol=6e-3, rtol=3e-2)
+    out = model.train()(img)
+    torch.testing.assert_close(out.float().cpu(), fx["logits"], atol=6e-3, rtol=3e-2)
+    out.float().mean().backward()
+    _check_grads(model, fx["grads"])
