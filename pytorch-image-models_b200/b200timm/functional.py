@@ -519,8 +519,16 @@ def vit_embed(model, img):
 def vit_forward_features(model, img, kv_len=None, final_norm=True):
     """VisionTransformer.forward_features (timm/models/vision_transformer.py:1231-1253)."""
     x = vit_embed(model, img)
-    for blk in model.blocks:
-        x = block_forward(blk, x, kv_len)
+    if getattr(model, "grad_checkpointing", False) and torch.is_grad_enabled() and x.requires_grad:
+        # checkpoint_seq(self.blocks, x) (vision_transformer.py:1247-1248, _manipulate.py:213-286, every=1): activations
+        # of a block are dropped after its forward and the block's kernels run again in the backward; the non-reentrant
+        # checkpoint restores the CUDA RNG state first, so the DropPath draw (functional._drop_path_factor) repeats
+        from torch.utils.checkpoint import checkpoint
+        for blk in model.blocks:
+            x = checkpoint(block_forward, blk, x, kv_len, use_reentrant=False)
+    else:
+        for blk in model.blocks:
+            x = block_forward(blk, x, kv_len)
     if final_norm and not _is_identity(model.norm):
         x = layernorm(model.norm, x)
     return x

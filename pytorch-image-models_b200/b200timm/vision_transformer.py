@@ -159,6 +159,11 @@ class VisionTransformer(nn.Module):
                     nn.init.zeros_(m.bias)
 
     @torch.jit.ignore
+    def set_grad_checkpointing(self, enable: bool = True):
+        """timm's switch (vision_transformer.py:983-990): recompute each block in the backward instead of keeping its
+        activations (functional.vit_forward_features)."""
+        self.grad_checkpointing = enable
+
     def no_weight_decay(self):
         return {"pos_embed", "cls_token", "dist_token"}
 

@@ -297,3 +297,31 @@ def test_attention_pool_map_head_matches_reference_golden():
     torch.testing.assert_close(out.float().cpu(), fx["logits"], atol=6e-3, rtol=3e-2)
     out.float().mean().backward()
     _check_grads(model, fx["grads"])
+
+
+def test_grad_checkpointing_reproduces_gradients_and_droppath_draws():
+    """set_grad_checkpointing() (timm's checkpoint_seq over the blocks): every block is recomputed in the backward.  With
+    stochastic depth active the recomputation must repeat the forward's DropPath draw (the non-reentrant checkpoint
+    restores the CUDA RNG state), so loss and all parameter gradients equal the un-checkpointed run from the same seed --
+    the equality timm's own test_model_forward checks (tests/test_models.py:196-206)."""
+    from b200timm.vision_transformer import VisionTransformer
+    torch.manual_seed(0)
+    model = VisionTransformer(img_size=64, patch_size=16, embed_dim=128, depth=4, num_heads=2, num_classes=10,
+                              drop_path_rate=0.3, init_values=0.5).cuda().to(torch.bfloat16).train()
+    x = torch.randn(8, 3, 64, 64, device="cuda").bfloat16()
+
+    def run(ckpt):
+        model.set_grad_checkpointing(ckpt)
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(123)
+        out = model(x)
+        out.float().square().mean().backward()
+        return out.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}
+
+    out0, g0 = run(False)
+    out1, g1 = run(True)
+    assert torch.equal(out0, out1)
+    assert any((out0[i] != out0[0]).any() for i in range(1, 8))
+    for n in g0:
+        a, b = g0[n].float(), g1[n].float()
+        assert (a - b).norm() <= 1e-3 * b.norm() + 1e-8, n        # split-K reduction order is the only freedom
