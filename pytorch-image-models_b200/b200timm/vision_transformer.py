@@ -164,6 +164,7 @@ class VisionTransformer(nn.Module):
         activations (functional.vit_forward_features)."""
         self.grad_checkpointing = enable
 
+    @torch.jit.ignore
     def no_weight_decay(self):
         return {"pos_embed", "cls_token", "dist_token"}
 
