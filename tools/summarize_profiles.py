@@ -78,6 +78,6 @@ def full(name):
 
 os.makedirs(OUT, exist_ok=True)
 launches()
-for n in ("prof_gemm", "prof_attn", "prof_bwd", "prof_dwconv"):
+for n in ("prof_gemm", "prof_attn", "prof_bwd", "prof_dwconv", "prof_optim"):
     full(n)
 print(os.listdir(OUT))
