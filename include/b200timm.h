@@ -84,7 +84,10 @@ typedef struct b200_gemm_desc {
    * (cls / register tokens) and the columns >= rope_cols (the V third) pass through.  The value is rounded to bf16
    * before the rotation, as the reference rotates the bf16 output of nn.Linear in fp32 (`.type_as(v)` rounds again). */
   const float* rope;
-  int32_t rope_tokens, rope_prefix, rope_cols, reserved0;
+  int32_t rope_tokens, rope_prefix, rope_cols;
+  int32_t act;      /* activation applied by EPI_BIAS_GELU / differentiated by EPI_DGELU: 0 = exact (erf) GELU (nn.GELU()),
+                       1 = tanh GELU (timm 'gelu_tanh': GELUTanh / nn.GELU(approximate='tanh'), activations.py), 2 = SiLU.
+                       (this field was `reserved0` = 0 before ABI 5)                                                  */
 } b200_gemm_desc;
 
 B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);

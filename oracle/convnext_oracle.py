@@ -6,7 +6,7 @@ tests/golden/convnext_g1.pt) by tests/test_oracle_golden.py.  Each function cite
 (timm 1.0.28.dev0)."""
 import torch
 
-from .vit_oracle import gelu_erf, layer_norm, linear
+from .vit_oracle import ACTS, gelu_erf, layer_norm, linear
 
 
 def dwconv(x, weight, bias):
@@ -35,12 +35,12 @@ def patch_conv(x, weight, bias):
     return linear(g, weight.reshape(weight.shape[0], -1), bias).permute(0, 3, 1, 2)
 
 
-def block(x, sd, pre, eps, keep=None, keep_prob=1.0):
+def block(x, sd, pre, eps, keep=None, keep_prob=1.0, act="gelu"):
     """ConvNeXtBlock.forward, timm/models/convnext.py:197-213 (conv_mlp=False).  keep: optional per-sample DropPath
     keep mask [B] (1 = kept), applied as timm/layers/drop.py:158-175 does: branch * mask / keep_prob."""
     h = dwconv(x, sd[pre + "conv_dw.weight"], sd.get(pre + "conv_dw.bias")).permute(0, 2, 3, 1)      # :200,205
     h = layer_norm(h, sd[pre + "norm.weight"], sd[pre + "norm.bias"], eps)                             # :206
-    h = gelu_erf(linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))
+    h = ACTS[act](linear(h, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"]))        # act_layer: create_act.py key
     if pre + "mlp.grn.weight" in sd:     # ConvNeXt-V2: GlobalResponseNorm, timm/layers/grn.py:46-49 (eps 1e-6), mlp.py:289-292
         gx = torch.sqrt((h * h).sum(dim=(1, 2), keepdim=True))
         nx = gx / (gx.mean(dim=-1, keepdim=True) + 1e-6)
@@ -66,7 +66,7 @@ def convnext_forward_features(img, sd, cfg, return_stages=False, keeps=None):
             x = patch_conv(x, sd[pre + "downsample.1.weight"], sd.get(pre + "downsample.1.bias"))
         for j in range(depth):
             kp = (keeps or {}).get(f"{pre}blocks.{j}.")
-            x = block(x, sd, f"{pre}blocks.{j}.", eps, *(kp if kp is not None else ()))
+            x = block(x, sd, f"{pre}blocks.{j}.", eps, *(kp if kp is not None else (None, 1.0)), act=cfg.get("act_layer") or "gelu")
         outs.append(x)
     return (x, outs) if return_stages else x
 
@@ -87,6 +87,7 @@ def convnext_forward_eager(img, sd, cfg):
     the CPU baseline bench.py times for the ConvNeXt workload."""
     import torch.nn.functional as F
     eps = cfg.get("eps", 1e-6)
+    act_fn = {"gelu": F.gelu, "gelu_tanh": lambda t: F.gelu(t, approximate="tanh"), "silu": F.silu}[cfg.get("act_layer") or "gelu"]
 
     def ln2d(t, w, b):
         return F.layer_norm(t.permute(0, 2, 3, 1), (t.shape[1],), w, b, eps).permute(0, 3, 1, 2)
@@ -103,7 +104,7 @@ def convnext_forward_eager(img, sd, cfg):
             k = sd[b + "conv_dw.weight"].shape[-1]
             h = F.conv2d(x, sd[b + "conv_dw.weight"], sd.get(b + "conv_dw.bias"), padding=k // 2, groups=x.shape[1])
             h = F.layer_norm(h.permute(0, 2, 3, 1), (x.shape[1],), sd[b + "norm.weight"], sd[b + "norm.bias"], eps)
-            h = F.gelu(F.linear(h, sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"]))
+            h = act_fn(F.linear(h, sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"]))
             if b + "mlp.grn.weight" in sd:      # GlobalResponseNorm.forward, timm/layers/grn.py:46-49
                 x_g = h.norm(p=2, dim=(1, 2), keepdim=True)
                 x_n = x_g / (x_g.mean(dim=-1, keepdim=True) + 1e-6)

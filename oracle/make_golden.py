@@ -30,7 +30,8 @@ def vit_case(name, seed, batch, kwargs, backward=True, input_size=None):
         import timm.layers
         build["mlp_layer"] = getattr(timm.layers, build["mlp_layer"])
     if isinstance(build.get("act_layer"), str):
-        build["act_layer"] = {"silu": torch.nn.SiLU, "gelu": torch.nn.GELU}[build["act_layer"]]
+        from timm.layers import get_act_layer
+        build["act_layer"] = get_act_layer(build["act_layer"])
     model = VisionTransformer(**build)
     # default init zeroes biases / sets LN to (1, 0): perturb so every parameter path is exercised
     g = torch.Generator().manual_seed(seed + 1)
@@ -385,12 +386,47 @@ DYN_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_
                   qkv_bias=True, dynamic_img_size=True, reg_tokens=1)
 
 
+SIGLIP_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=1, num_heads=2, mlp_ratio=2.0,
+                     qkv_bias=True, class_token=False, global_pool="map", act_layer="gelu_tanh")   # SigLIP: tanh GELU + map head
+CNX_TANH_KWARGS = dict(depths=(1, 1, 1, 1), dims=(16, 32, 64, 128), num_classes=10, kernel_sizes=(7, 5, 5, 3),
+                       act_layer="gelu_tanh")                                                      # timm's test_convnext family
+
+
+def mlp_act_cases():
+    """timm.layers.Mlp with act_layer 'gelu_tanh' / 'silu' (create_act.py): output, input gradient, parameter gradients."""
+    import timm
+    from timm.layers import Mlp, get_act_layer
+    g = torch.Generator().manual_seed(61)
+    torch.manual_seed(61)
+    fx = {"kind": "mlp_acts", "timm_version": timm.__version__}
+    for name in ("gelu_tanh", "silu"):
+        m = Mlp(64, 256, act_layer=get_act_layer(name))
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() == 1:
+                    p.add_(torch.randn(p.shape, generator=g) * 0.1)
+        x = (torch.randn(3, 50, 64, generator=g) * 2).requires_grad_(True)
+        wgt = torch.randn(3, 50, 64, generator=g)
+        y = m(x)
+        (y * wgt).sum().backward()
+        fx[name] = {"state_dict": {k: v.clone() for k, v in m.state_dict().items()}, "x": x.detach().clone(), "y": y.detach(),
+                    "wgt": wgt, "dx": x.grad.clone(), "grads": {k: p.grad.clone() for k, p in m.named_parameters()},
+                    "act_class": type(m.act).__name__}
+    torch.save(fx, os.path.join(OUT, "mlp_acts.pt"))
+    print("mlp act cases", {k: (v["act_class"], float(v["y"].abs().max())) for k, v in fx.items() if isinstance(v, dict)})
+
+
 MAP_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=1, num_heads=2, mlp_ratio=2.0,
                   qkv_bias=True, class_token=False, global_pool="map")        # SigLIP-style head (vision_transformer.py:882-890)
 CNX_V2_KWARGS = dict(depths=(1, 1, 2, 1), dims=(16, 32, 64, 128), num_classes=10, use_grn=True, ls_init_value=None)
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "acts":
+        os.makedirs(OUT, exist_ok=True)
+        mlp_act_cases()
+        vit_case("vit_g9_siglip_like", 11, 2, SIGLIP_KWARGS)
+        return convnext_case("convnext_g3_tanh_k7553", 12, 2, CNX_TANH_KWARGS, 64, backward=True)
     if len(sys.argv) > 1 and sys.argv[1] == "map":
         os.makedirs(OUT, exist_ok=True)
         return vit_case("vit_g8_map_pool", 10, 3, MAP_KWARGS)
@@ -447,6 +483,9 @@ def main():
     vit_case("vit_g7_dynamic_img_size", 8, 2, DYN_KWARGS, input_size=(96, 80))
     convnext_case("convnext_g2_v2_grn", 9, 2, CNX_V2_KWARGS, 64, backward=True)
     vit_case("vit_g8_map_pool", 10, 3, MAP_KWARGS)
+    mlp_act_cases()
+    vit_case("vit_g9_siglip_like", 11, 2, SIGLIP_KWARGS)
+    convnext_case("convnext_g3_tanh_k7553", 12, 2, CNX_TANH_KWARGS, 64, backward=True)
 
 
 if __name__ == "__main__":

@@ -129,9 +129,17 @@ def attention_rope(x, qkv_w, qkv_b, proj_w, proj_b, num_heads, rope, num_prefix=
     return linear(o, proj_w, proj_b)
 
 
-def mlp(x, fc1_w, fc1_b, fc2_w, fc2_b):
-    """timm/layers/mlp.py:47-54 (Mlp.forward, drop=0, norm=Identity)."""
-    return linear(gelu_erf(linear(x, fc1_w, fc1_b)), fc2_w, fc2_b)
+def gelu_tanh(x):
+    """timm GELUTanh / nn.GELU(approximate='tanh') (timm/layers/activations.py): 0.5 x (1 + tanh(sqrt(2/pi)(x + 0.044715 x^3)))."""
+    return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+
+
+ACTS = {"gelu": gelu_erf, "gelu_tanh": gelu_tanh, "silu": lambda t: t * torch.sigmoid(t)}
+
+
+def mlp(x, fc1_w, fc1_b, fc2_w, fc2_b, act="gelu"):
+    """timm/layers/mlp.py:47-54 (Mlp.forward, drop=0, norm=Identity); act = the create_act.py key of act_layer."""
+    return linear(ACTS[act](linear(x, fc1_w, fc1_b)), fc2_w, fc2_b)
 
 
 def glu_mlp(x, sd, prefix, eps=1e-6, act="silu", gate_last=False):
@@ -150,7 +158,7 @@ def glu_mlp(x, sd, prefix, eps=1e-6, act="silu", gate_last=False):
     return linear(h, g("fc2.weight"), g("fc2.bias"))
 
 
-def attention_pool_latent(x, sd, prefix, num_heads, eps=1e-6):
+def attention_pool_latent(x, sd, prefix, num_heads, eps=1e-6, act="gelu"):
     """AttentionPoolLatent.forward, timm/layers/attention_pool.py:95-128 (latent_len 1, no qk_norm / pos_embed, token pool):
     q = q(latent), k, v = kv(x); softmax(q k^T / sqrt(hd)) v; proj; x + mlp(norm(x)); x[:, 0]."""
     B, N, C = x.shape
@@ -164,7 +172,7 @@ def attention_pool_latent(x, sd, prefix, num_heads, eps=1e-6):
     o = (p @ v).transpose(1, 2).reshape(B, 1, C)
     o = linear(o, g("proj.weight"), g("proj.bias"))
     h = norm(o, sd, prefix + "norm.", eps) if g("norm.weight") is not None else o
-    o = o + mlp(h, g("mlp.fc1.weight"), g("mlp.fc1.bias"), g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+    o = o + mlp(h, g("mlp.fc1.weight"), g("mlp.fc1.bias"), g("mlp.fc2.weight"), g("mlp.fc2.bias"), act)
     return o[:, 0]
 
 
@@ -203,7 +211,7 @@ def resample_abs_pos_embed(pos, new_size, old_size, num_prefix_tokens):
 
 
 # ----------------------------------------------------------------------------------------------- model
-def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, keep_prob=1.0, glu=None):
+def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, keep_prob=1.0, glu=None, act="gelu"):
     """timm/models/vision_transformer.py:206-214 (Block.forward).  glu: None (Mlp) or dict(act=, gate_last=) for a
     gated mlp_layer (SwiGLU is recognised by its fc1_g key)."""
     g = lambda k: sd.get(prefix + k)  # noqa: E731
@@ -218,7 +226,7 @@ def block(x, sd, prefix, num_heads, eps, kv_len=None, keep1=None, keep2=None, ke
         h = glu_mlp(norm(x, sd, prefix + "norm2.", eps), sd, prefix + "mlp.", eps, **(glu or {}))
     else:
         h = mlp(norm(x, sd, prefix + "norm2.", eps), g("mlp.fc1.weight"), g("mlp.fc1.bias"),
-                g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+                g("mlp.fc2.weight"), g("mlp.fc2.bias"), act)
     if g("ls2.gamma") is not None:
         h = h * g("ls2.gamma")
     if keep2 is not None:
@@ -253,7 +261,8 @@ def vit_forward_features(img, sd, cfg, kv_len=None, return_blocks=False):
         x = norm(x, sd, "norm_pre.", eps)
     outs = []
     for i in range(cfg["depth"]):
-        x = block(x, sd, f"blocks.{i}.", cfg["num_heads"], eps, kv_len, glu=cfg.get("glu"))
+        x = block(x, sd, f"blocks.{i}.", cfg["num_heads"], eps, kv_len, glu=cfg.get("glu"),
+                  act="gelu" if cfg.get("mlp_layer") else (cfg.get("act_layer") or "gelu"))
         outs.append(x)
     if "norm.weight" in sd:
         x = norm(x, sd, "norm.", eps)
@@ -269,7 +278,8 @@ def vit_forward_head(x, sd, cfg):
     elif pool == "avg":
         x = x[:, npre:].mean(1)
     elif pool == "map":                                              # :1265-1269 (prefix tokens excluded)
-        x = attention_pool_latent(x[:, npre:], sd, "attn_pool.", cfg["num_heads"], cfg.get("eps", 1e-6))
+        x = attention_pool_latent(x[:, npre:], sd, "attn_pool.", cfg["num_heads"], cfg.get("eps", 1e-6),
+                                  act=cfg.get("act_layer") or "gelu")
     elif pool:
         raise ValueError(f"oracle: pool {pool!r} not restated")
     if "fc_norm.weight" in sd:
@@ -348,6 +358,7 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
     import torch.nn.functional as F
     eps = cfg.get("eps", 1e-6)
     H = cfg["num_heads"]
+    act_fn = {"gelu": F.gelu, "gelu_tanh": lambda t: F.gelu(t, approximate="tanh"), "silu": F.silu}[cfg.get("act_layer") or "gelu"]
     x = F.conv2d(img, sd["patch_embed.proj.weight"], sd.get("patch_embed.proj.bias"), stride=cfg["patch_size"])
     x = x.flatten(2).transpose(1, 2)
     B = x.shape[0]
@@ -390,7 +401,7 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
             h = F.silu(F.linear(h, sd[p + "mlp.fc1_g.weight"], sd.get(p + "mlp.fc1_g.bias"))) * \
                 F.linear(h, sd[p + "mlp.fc1_x.weight"], sd.get(p + "mlp.fc1_x.bias"))
         else:
-            h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd.get(p + "mlp.fc1.bias")))
+            h = act_fn(F.linear(h, sd[p + "mlp.fc1.weight"], sd.get(p + "mlp.fc1.bias")))
         h = F.linear(h, sd[p + "mlp.fc2.weight"], sd.get(p + "mlp.fc2.bias"))
         if p + "ls2.gamma" in sd:
             h = h * sd[p + "ls2.gamma"]
@@ -412,7 +423,7 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
         x = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(Bp, 1, C)
         x = F.linear(x, sd["attn_pool.proj.weight"], sd.get("attn_pool.proj.bias"))
         h = _eager_norm(x, sd, "attn_pool.norm.", eps) if "attn_pool.norm.weight" in sd else x
-        h = F.linear(F.gelu(F.linear(h, sd["attn_pool.mlp.fc1.weight"], sd.get("attn_pool.mlp.fc1.bias"))),
+        h = F.linear(act_fn(F.linear(h, sd["attn_pool.mlp.fc1.weight"], sd.get("attn_pool.mlp.fc1.bias"))),
                      sd["attn_pool.mlp.fc2.weight"], sd.get("attn_pool.mlp.fc2.bias"))
         x = (x + h)[:, 0]
     if "fc_norm.weight" in sd:

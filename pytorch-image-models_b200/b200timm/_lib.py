@@ -54,7 +54,7 @@ class GemmDesc(ctypes.Structure):
         ("rope_tokens", ctypes.c_int32),
         ("rope_prefix", ctypes.c_int32),
         ("rope_cols", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("act", ctypes.c_int32),
     ]
 
 

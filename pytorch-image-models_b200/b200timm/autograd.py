@@ -108,23 +108,23 @@ class MlpFn(torch.autograd.Function):
     """Mlp.forward (timm/layers/mlp.py:47-54): fc2(GELU(fc1(x)))."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
+    def forward(ctx, x, w1, b1, w2, b2, act_kind=0):
         shape = x.shape
         x2 = _c(x.reshape(-1, shape[-1]))
         pre = torch.empty(x2.shape[0], w1.shape[0], dtype=torch.bfloat16, device=x.device)
-        act = ops.linear_fwd(x2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+        act = ops.linear_fwd(x2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre, act=act_kind)
         y = ops.linear_fwd(act, w2, b2)
         ctx.save_for_backward(x2, w1, b1, w2, b2, pre, act)
-        ctx.shape = shape
+        ctx.shape, ctx.act_kind = shape, act_kind
         return y.view(*shape[:-1], -1)
 
     @staticmethod
     def backward(ctx, dy):
         x2, w1, b1, w2, b2, pre, act = ctx.saved_tensors
         dy2 = _c(dy.reshape(-1, dy.shape[-1]))
-        dpre = ops.linear_dgrad(dy2, w2, epilogue=ops.EPI_DGELU, aux=pre)
+        dpre = ops.linear_dgrad(dy2, w2, epilogue=ops.EPI_DGELU, aux=pre, act=ctx.act_kind)
         dx = ops.linear_dgrad(dpre, w1).view(ctx.shape)
-        return dx, _wgrad(dpre, x2, w1), _bias_grad(dpre, b1), _wgrad(dy2, act, w2), _bias_grad(dy2, b2)
+        return dx, _wgrad(dpre, x2, w1), _bias_grad(dpre, b1), _wgrad(dy2, act, w2), _bias_grad(dy2, b2), None
 
 
 class AttentionFn(torch.autograd.Function):
@@ -199,7 +199,7 @@ class BlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, g1, g2, rs1, rs2, kv_len,
-                num_heads, scale, eps1, eps2):
+                num_heads, scale, eps1, eps2, act_kind=0):
         B, N, D = x.shape
         hd = wqkv.shape[0] // 3 // num_heads
         x0 = _c(x.reshape(B * N, D))
@@ -211,13 +211,14 @@ class BlockFn(torch.autograd.Function):
                             row_scale=rs1, rows_per_scale=N)
         h2, mean2, rstd2 = ops.layernorm_fwd(x1, n2w, n2b, eps2, save_stats=True)
         pre = torch.empty(B * N, w1.shape[0], dtype=torch.bfloat16, device=x.device)
-        act = ops.linear_fwd(h2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+        act = ops.linear_fwd(h2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre, act=act_kind)
         br2 = torch.empty(B * N, D, dtype=torch.bfloat16, device=x.device) if g2 is not None else None
         x2 = ops.linear_fwd(act, w2, b2, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x1, gamma=g2, out2=br2, row_scale=rs2,
                             rows_per_scale=N)
         ctx.save_for_backward(x0, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, g1, g2, rs1, rs2, kv_len,
                               h1, mean1, rstd1, qkv, o, lse, x1, h2, mean2, rstd2, pre, act, br1, br2)
         ctx.meta = (B, N, D, num_heads, hd, scale)
+        ctx.act_kind = act_kind
         return x2.view(B, N, D)
 
     @staticmethod
@@ -242,7 +243,7 @@ class BlockFn(torch.autograd.Function):
             if g2 is not None:
                 ops.colsum_mul(dx2, br2, rs2, N, out=v[13], accumulate=True)          # dgamma2
             dbr2 = ops.scale_rows_cols(dx2, g2, rs2, N)                               # gradient w.r.t. the branch output
-        dpre = ops.linear_dgrad(dbr2, w2, epilogue=ops.EPI_DGELU, aux=pre)            # dY W2 * GELU'(pre)
+        dpre = ops.linear_dgrad(dbr2, w2, epilogue=ops.EPI_DGELU, aux=pre, act=ctx.act_kind)     # dY W2 * act'(pre)
         ops.linear_wgrad(dbr2, act, out=v[10])
         if b2 is not None:
             ops.colsum(dbr2, out=v[11], accumulate=True)
@@ -276,7 +277,7 @@ class BlockFn(torch.autograd.Function):
             ops.convert_f32(ws, gbuf)
             grads = [None if p is None else (v[i] if p.dtype == torch.float32 else gbuf[o_:o_ + n].view(p.shape))
                      for i, (p, o_, n) in enumerate(zip(params, offs, sizes))]
-        return (dx0.view(B, N, D), *grads, None, None, None, None, None, None, None, None)
+        return (dx0.view(B, N, D), *grads, None, None, None, None, None, None, None, None, None)
 
 
 class PatchEmbedFn(torch.autograd.Function):

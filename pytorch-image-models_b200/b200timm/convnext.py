@@ -22,7 +22,7 @@ from ._lib import B200Error
 from .layers import DropPath, Mlp
 
 
-from .functional import _w  # noqa: E402  (bf16 GEMM operand of a Linear / Conv2d: bf16 params as is, fp32 params cast)
+from .functional import _w, mlp_act  # noqa: E402  (bf16 GEMM operand of a Linear / Conv2d: bf16 params as is, fp32 params cast)
 
 
 def _needs_grad(module):
@@ -35,7 +35,7 @@ class _BlockFn(torch.autograd.Function):
     dx = dwconv(dy, spatially flipped weight) with the shortcut gradient folded in, dweight through the wgrad kernel."""
 
     @staticmethod
-    def forward(ctx, x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, rs, B, H, W, eps, gw=None, gb=None, geps=1e-6):
+    def forward(ctx, x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, rs, B, H, W, eps, gw=None, gb=None, geps=1e-6, act_kind=0):
         from .autograd import _c
         C = x.shape[1]
         k = wdw.shape[-1]
@@ -43,7 +43,7 @@ class _BlockFn(torch.autograd.Function):
         y = ops.dwconv_nhwc(x.view(B, H, W, C), wt, bdw).view(B * H * W, C)
         h, mean, rstd = ops.layernorm_fwd(y, nw, nb, eps, save_stats=True)
         pre = torch.empty(x.shape[0], w1.shape[0], dtype=torch.bfloat16, device=x.device)
-        act = ops.linear_fwd(h, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre)
+        act = ops.linear_fwd(h, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre, act=act_kind)
         gsq = gscale = None
         if gw is not None:          # ConvNeXt-V2: GlobalResponseNorm between GELU and fc2 (mlp.py:289-292), in place on act
             gsq, gscale = ops.grn_fwd(act, gw, gb, B, H * W, geps)
@@ -53,6 +53,7 @@ class _BlockFn(torch.autograd.Function):
         ctx.save_for_backward(x, wdw, bdw, nw, nb, w1, b1, w2, b2, gamma, wt, y, mean, rstd, h, pre, act, br, rs, gw, gb, gsq,
                               gscale)
         ctx.meta = (B, H, W, C, k, geps)
+        ctx.act_kind = act_kind
         return out
 
     @staticmethod
@@ -77,7 +78,7 @@ class _BlockFn(torch.autograd.Function):
                 ops.colsum_mul(dout, br, rs, H * W, out=v[7], accumulate=True)
             dbr = ops.scale_rows_cols(dout, gamma, rs, H * W)
         if gw is None:
-            dpre = ops.linear_dgrad(dbr, w2, epilogue=ops.EPI_DGELU, aux=pre)
+            dpre = ops.linear_dgrad(dbr, w2, epilogue=ops.EPI_DGELU, aux=pre, act=ctx.act_kind)
         else:                       # GRN + GELU backward in one pass over the hidden activations
             dact = ops.linear_dgrad(dbr, w2)
             if gb is not None:
@@ -106,7 +107,7 @@ class _BlockFn(torch.autograd.Function):
                      for i, (p, o, n) in enumerate(zip(params, offs, sizes))]
         g_wdw = dwt.reshape(k * k, C).t().reshape(C, 1, k, k).to(wdw.dtype)     # [k,k,C] -> Conv2d layout (49*C values)
         return (dx.view(B * H * W, C), g_wdw, grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6], grads[7],
-                None, None, None, None, None, grads[8], grads[9], None)
+                None, None, None, None, None, grads[8], grads[9], None, None)
 
 
 class _DownsampleFn(torch.autograd.Function):
@@ -235,9 +236,10 @@ def _check_block(blk):
     if (getattr(blk, "use_conv_mlp", False) or not isinstance(blk.shortcut, nn.Identity) or conv.stride != (1, 1)
             or conv.dilation != (1, 1) or conv.groups != conv.in_channels or conv.in_channels != conv.out_channels
             or conv.kernel_size != (k, k) or conv.padding != (k // 2, k // 2)
-            or type(blk.mlp.act).__name__ != "GELU" or getattr(blk.mlp.act, "approximate", "none") != "none"
             or type(blk.norm).__name__ not in ("LayerNorm",)):
-        raise B200Error("ConvNeXtBlock: conv_mlp / strided / dilated / non-GELU blocks are not covered")
+        raise B200Error("ConvNeXtBlock: conv_mlp / strided / dilated blocks are not covered")
+    if mlp_act(blk.mlp) != 0 and hasattr(blk.mlp, "grn"):
+        raise B200Error("GlobalResponseNormMlp: only the exact GELU is covered")
 
 
 def block_forward_nhwc(self, x, B, H, W):
@@ -257,13 +259,13 @@ def block_forward_nhwc(self, x, B, H, W):
         rs = rs.contiguous()
     grn = getattr(self.mlp, "grn", None)     # GlobalResponseNormMlp (ConvNeXt-V2, mlp.py:251-295)
     if x.requires_grad or _needs_grad(self):
-        extra = () if grn is None else (grn.weight, grn.bias, grn.eps)
+        extra = (None, None, 1e-6) if grn is None else (grn.weight, grn.bias, grn.eps)
         return _BlockFn.apply(x, _w(self.conv_dw), self.conv_dw.bias, self.norm.weight, self.norm.bias,
                               _w(self.mlp.fc1), self.mlp.fc1.bias, _w(self.mlp.fc2), self.mlp.fc2.bias,
-                              self.gamma, rs, B, H, W, self.norm.eps, *extra)
+                              self.gamma, rs, B, H, W, self.norm.eps, *extra, mlp_act(self.mlp))
     y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
     h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
-    a = ops.linear_fwd(h, _w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    a = ops.linear_fwd(h, _w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(self.mlp))
     if grn is not None:
         ops.grn_fwd(a, grn.weight, grn.bias, B, H * W, grn.eps)
     return ops.linear_fwd(a, _w(self.mlp.fc2), self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
@@ -398,10 +400,13 @@ class ConvNeXt(nn.Module):
                  device=None, dtype=None):
         super().__init__()
         dd = {"device": device, "dtype": dtype}
+        acts = {None: nn.GELU, "gelu": nn.GELU, nn.GELU: nn.GELU, "silu": nn.SiLU, nn.SiLU: nn.SiLU,
+                "gelu_tanh": lambda: nn.GELU(approximate="tanh")}       # create_act.py keys timm's ConvNeXt configs use
         if (stem_type != "patch" or output_stride != 32 or head_norm_first or conv_mlp or norm_layer
-                or global_pool != "avg" or (act_layer not in (None, "gelu", nn.GELU))):
-            raise B200Error("ConvNeXt: only the patch-stem / LayerNorm / Linear-MLP / GELU / avg-pool configuration "
-                            "is covered by the B200 path")
+                or global_pool != "avg" or act_layer not in acts):
+            raise B200Error("ConvNeXt: only the patch-stem / LayerNorm / Linear-MLP / GELU, tanh-GELU, SiLU / avg-pool "
+                            "configuration is covered by the B200 path")
+        act_cls = acts[act_layer]
         eps = norm_eps if norm_eps is not None else 1e-6
         ks = kernel_sizes if isinstance(kernel_sizes, (tuple, list)) else (kernel_sizes,) * 4
         ln2d = lambda c, **kw: LayerNorm2d(c, eps=eps, **kw)        # noqa: E731
@@ -415,7 +420,7 @@ class ConvNeXt(nn.Module):
         for i in range(4):
             stages.append(ConvNeXtStage(prev, dims[i], kernel_size=ks[i], stride=2 if i > 0 else 1, depth=depths[i],
                                         drop_path_rates=rates[k:k + depths[i]], ls_init_value=ls_init_value,
-                                        conv_bias=conv_bias, use_grn=use_grn, act_layer=nn.GELU, norm_layer=ln2d, norm_layer_cl=ln, **dd))
+                                        conv_bias=conv_bias, use_grn=use_grn, act_layer=act_cls, norm_layer=ln2d, norm_layer_cl=ln, **dd))
             k += depths[i]
             prev = dims[i]
         self.stages = nn.Sequential(*stages)

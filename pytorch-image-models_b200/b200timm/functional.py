@@ -113,9 +113,22 @@ def _attn_norms(attn):
     return qk, sp
 
 
+def mlp_act(mlp):
+    """b200_gemm_desc.act code of an Mlp's activation: exact GELU (nn.GELU / timm GELU), tanh GELU (timm 'gelu_tanh' =
+    GELUTanh, nn.GELU(approximate='tanh'); timm/layers/activations.py, create_act.py) or SiLU."""
+    a = mlp.act
+    name = type(a).__name__
+    if name == "GELUTanh" or (name == "GELU" and getattr(a, "approximate", "none") == "tanh"):
+        return ops.ACTS["gelu_tanh"]
+    if name == "GELU" and getattr(a, "approximate", "none") == "none":
+        return ops.ACTS["gelu"]
+    if name in ("SiLU", "Swish"):
+        return ops.ACTS["silu"]
+    raise B200Error(f"unsupported Mlp activation {a} (GELU, tanh GELU, SiLU)")
+
+
 def check_mlp(mlp):
-    if not isinstance(mlp.act, nn.GELU) or getattr(mlp.act, "approximate", "none") != "none":
-        raise B200Error(f"unsupported Mlp activation {mlp.act} (exact GELU only)")
+    mlp_act(mlp)
     if not _is_identity(getattr(mlp, "norm", None)):
         raise B200Error("Mlp with an inner norm is not supported")
     if not isinstance(mlp.fc1, nn.Linear):
@@ -283,9 +296,9 @@ def mlp_forward(mlp, x):
     if _needs_grad(x, mlp):
         from .autograd import MlpFn
         _bf16_2d(x, shape[-1])
-        return MlpFn.apply(x, _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias)
+        return MlpFn.apply(x, _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, mlp_act(mlp))
     x2 = _bf16_2d(x, shape[-1])
-    h = ops.linear_fwd(x2, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    h = ops.linear_fwd(x2, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(mlp))
     y = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias)
     return y.view(*shape[:-1], -1)
 
@@ -378,7 +391,7 @@ def _variant_block_forward(blk, x, kv_len):
     if is_glu(mlp):
         return glu_mlp_forward(mlp, h, residual=x2, gamma=_gamma(blk.ls2)).view(B, N, D)
     check_mlp(mlp)
-    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(mlp))
     return ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
                           gamma=_gamma(blk.ls2)).view(B, N, D)
 
@@ -401,7 +414,7 @@ def block_forward(blk, x, kv_len=None):
         rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)
         return BlockFn.apply(x, n1w, n1b, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, n2w, n2b,
                              _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, _gamma(blk.ls1), _gamma(blk.ls2),
-                             rs1, rs2, kv_len, attn.num_heads, attn.scale, e1, e2)
+                             rs1, rs2, kv_len, attn.num_heads, attn.scale, e1, e2, mlp_act(mlp))
     rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)   # None in eval mode
     x2 = _bf16_2d(x, D)
     w1, b1, eps1 = _ln_params(blk.norm1)
@@ -412,7 +425,7 @@ def block_forward(blk, x, kv_len=None):
                         gamma=_gamma(blk.ls1), row_scale=rs1, rows_per_scale=N)
     w2, b2, eps2 = _ln_params(blk.norm2)
     h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
-    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU)
+    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(mlp))
     x2 = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=_gamma(blk.ls2),
                         row_scale=rs2, rows_per_scale=N)
     return x2.view(B, N, D)

@@ -15,7 +15,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESI
 __all__ = [
     "layernorm_fwd", "layernorm_bwd", "gemm", "linear_fwd", "linear_dgrad", "linear_wgrad", "convert_f32",
     "attention_fwd", "attention_bwd", "patchify", "assemble_tokens", "colsum", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc",
-    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "set_input_norm", "input_norm", "glu_fwd", "glu_bwd", "qk_norm_fwd", "qk_norm_bwd", "grn_fwd", "grn_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps",
+    "avgpool_nhwc", "naflex_assemble", "naflex_assemble_bwd", "set_input_norm", "input_norm", "glu_fwd", "glu_bwd", "qk_norm_fwd", "qk_norm_bwd", "grn_fwd", "grn_bwd", "scale_rows_cols", "colsum_mul", "EPI_BIAS", "EPI_BIAS_GELU", "EPI_BIAS_RESIDUAL", "EPI_DGELU", "EPI_BIAS_ROPE", "rope_qk", "RmsEps", "ACTS",
 ]
 
 
@@ -179,8 +179,12 @@ def _check_2d_bf16(t, name):
                         f"strides {t.stride()}")
 
 
+ACTS = {"gelu": 0, "gelu_tanh": 1, "silu": 2}     # b200_gemm_desc.act: the activation of EPI_BIAS_GELU / EPI_DGELU
+
+
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None, gamma=None, out=None,
-         out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None, row_scale=None, rows_per_scale=0, rope=None):
+         out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None, row_scale=None, rows_per_scale=0, rope=None,
+         act=0):
     """out[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
@@ -229,6 +233,7 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
     d.gamma_dtype = _dt(gamma) if gamma is not None else DTYPE_BF16
     d.accumulate = int(accumulate)
     d.split_k = int(split_k)
+    d.act = int(act)
     if _gemm_timing is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -242,12 +247,12 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
 
 
 def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, out=None, out2=None, row_scale=None,
-               rows_per_scale=0, rope=None):
+               rows_per_scale=0, rope=None, act=0):
     """F.linear on a [M,K] bf16 activation with a fused epilogue (weight: [N,K] bf16)."""
     M, K = x2d.shape
     N = weight.shape[0]
     return gemm(x2d, weight, M, N, K, epilogue=epilogue, bias=bias, aux=aux, gamma=gamma, out=out, out2=out2,
-                row_scale=row_scale, rows_per_scale=rows_per_scale, rope=rope)
+                row_scale=row_scale, rows_per_scale=rows_per_scale, rope=rope, act=act)
 
 
 def _check_rope(emb, tokens, prefix):
@@ -269,11 +274,11 @@ def rope_qk(qkv, emb, B, N, H, num_prefix, half=False, inverse=False):
     return qkv
 
 
-def linear_dgrad(dy2d, weight, epilogue=EPI_BIAS, aux=None):
-    """dX[M,K] = dY[M,N] @ W[N,K]  (W consumed MN-major in place; optional GELU' epilogue with aux = pre-activation)."""
+def linear_dgrad(dy2d, weight, epilogue=EPI_BIAS, aux=None, act=0):
+    """dX[M,K] = dY[M,N] @ W[N,K]  (W consumed MN-major in place; optional act' epilogue with aux = pre-activation)."""
     M, N = dy2d.shape
     K = weight.shape[1]
-    return gemm(dy2d, weight, M, K, N, b_mn=True, epilogue=epilogue, aux=aux)
+    return gemm(dy2d, weight, M, K, N, b_mn=True, epilogue=epilogue, aux=aux, act=act)
 
 
 def _wgrad_split(rows_out, cols_out, k):

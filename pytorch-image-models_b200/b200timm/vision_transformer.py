@@ -86,9 +86,10 @@ class VisionTransformer(nn.Module):
                 raise B200Error(f"norm_layer {norm_layer!r} is not covered (layernorm, rmsnorm)")
             norm_layer = known[norm_layer]
         if isinstance(act_layer, str):        # create_act keys (timm/layers/create_act.py); 'silu' goes with the gated MLPs
-            known = {"gelu": nn.GELU, "silu": nn.SiLU, "swish": nn.SiLU, "sigmoid": nn.Sigmoid}
+            known = {"gelu": nn.GELU, "gelu_tanh": partial(nn.GELU, approximate="tanh"), "silu": nn.SiLU, "swish": nn.SiLU,
+                     "sigmoid": nn.Sigmoid}
             if act_layer not in known:
-                raise B200Error(f"act_layer {act_layer!r} is not covered (gelu, silu, sigmoid)")
+                raise B200Error(f"act_layer {act_layer!r} is not covered (gelu, gelu_tanh, silu, sigmoid)")
             act_layer = known[act_layer]
         if isinstance(mlp_layer, str):        # the reference has no string lookup for mlp_layer (vision_transformer.py:758);
             from . import layers as _layers   # names of timm.layers classes are accepted here so fixtures / CLIs can say it

@@ -54,4 +54,36 @@ __device__ __forceinline__ f32x2 dgelu_erf2(f32x2 x) {
   return fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);
 }
 
+// The other MLP activations timm configures on this path (create_act.py: 'gelu_tanh' = GELUTanh / nn.GELU('tanh'), used by
+// the SigLIP ViTs and timm's test_convnext; 'silu'): selected at run time by b200_gemm_desc.act in the generic kernels.
+//   tanh(u) = 1 - 2 / (1 + e^{2u})  (ex2 + rcp: two MUFU, abs. error ~1e-6, saturates correctly at +-inf)
+__device__ __forceinline__ float tanh_fast(float u) {
+  return 1.f - 2.f * rcp_approx(1.f + ex2_approx(u * 2.8853900817779268f));
+}
+__device__ __forceinline__ float gelu_tanh1(float x) {
+  return 0.5f * x * (1.f + tanh_fast(0.7978845608028654f * fmaf(0.044715f * x * x, x, x)));
+}
+__device__ __forceinline__ float dgelu_tanh1(float x) {
+  const float t = tanh_fast(0.7978845608028654f * fmaf(0.044715f * x * x, x, x));
+  return fmaf(0.5f * x * (1.f - t * t), 0.7978845608028654f * fmaf(0.134145f * x, x, 1.f), 0.5f * (1.f + t));
+}
+__device__ __forceinline__ float silu1(float x) { return x * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float dsilu1(float x) {
+  const float s = rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x));
+  return s * fmaf(x, 1.f - s, 1.f);
+}
+// act: 0 = exact GELU, 1 = tanh GELU, 2 = SiLU
+__device__ __forceinline__ f32x2 act_fwd2(f32x2 v, int act) {
+  if (act == 0) return gelu_erf2(v);
+  float a, b;
+  upk(v, a, b);
+  return act == 1 ? pk(gelu_tanh1(a), gelu_tanh1(b)) : pk(silu1(a), silu1(b));
+}
+__device__ __forceinline__ f32x2 act_bwd2(f32x2 v, int act) {
+  if (act == 0) return dgelu_erf2(v);
+  float a, b;
+  upk(v, a, b);
+  return act == 1 ? pk(dgelu_tanh1(a), dgelu_tanh1(b)) : pk(dsilu1(a), dsilu1(b));
+}
+
 }  // namespace b200

@@ -49,6 +49,7 @@ struct GemmKernelParams {
   int epilogue, out_f32, bias_f32, gamma_f32, accumulate;
   const float* rope;           // EPI_BIAS_ROPE: [rope_tokens - rope_prefix][128] = [sin | cos]
   int rope_tokens, rope_prefix, rope_cols;
+  int act;                     // activation of the GELU / DGELU epilogues in the generic kernels: 0 erf GELU, 1 tanh GELU, 2 SiLU
   unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_set_trace), nullptr in production
 };
 
@@ -413,7 +414,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   }
                 } else if (epi == B200_EPI_BIAS_GELU && !dual) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
+                  for (int j = 0; j < 4; ++j) v[j] = (EPI < 0 && p.act) ? act_fwd2(v[j], p.act) : gelu_erf2(v[j]);
                 } else if (has_aux && !dual) {
                   uint4 q;
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
@@ -430,7 +431,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                   } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) v[j] = mul2(v[j], dgelu_erf2(av[j]));
+                    for (int j = 0; j < 4; ++j)
+                      v[j] = mul2(v[j], (EPI < 0 && p.act) ? act_bwd2(av[j], p.act) : dgelu_erf2(av[j]));
                   }
                 }
               }
@@ -478,7 +480,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float lo, hi;
-                upk(gelu_erf2(bf16x2_to_f32x2(w[i])), lo, hi);
+                const f32x2 xv = bf16x2_to_f32x2(w[i]);
+                upk((EPI < 0 && p.act) ? act_fwd2(xv, p.act) : gelu_erf2(xv), lo, hi);
                 o[i] = pack_bf16(lo, hi);
               }
             } else {
@@ -596,6 +599,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.bias_f32 = d.bias_dtype == B200_DTYPE_F32; p.gamma_f32 = d.gamma_dtype == B200_DTYPE_F32;
   p.accumulate = d.accumulate;
   p.rope = d.rope; p.rope_tokens = d.rope_tokens; p.rope_prefix = d.rope_prefix; p.rope_cols = d.rope_cols;
+  p.act = d.act;
   p.trace = g_gemm_trace;
 
   auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI>;
@@ -668,6 +672,7 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
                      (reinterpret_cast<uintptr_t>(d.out) & 15) == 0,
                  "b200_gemm: operand pointers must be 16-byte aligned");
   B200_CHECK_ARG(d.epilogue >= B200_EPI_BIAS && d.epilogue <= B200_EPI_BIAS_ROPE, "b200_gemm: bad epilogue %d", d.epilogue);
+  B200_CHECK_ARG(d.act >= 0 && d.act <= 2, "b200_gemm: bad activation %d (0 erf GELU, 1 tanh GELU, 2 SiLU)", d.act);
   if (d.epilogue == B200_EPI_BIAS_ROPE)
     B200_CHECK_ARG(d.rope != nullptr && (reinterpret_cast<uintptr_t>(d.rope) & 15) == 0 && d.rope_tokens > 0 &&
                        d.rope_prefix >= 0 && d.rope_prefix < d.rope_tokens && d.rope_cols % 64 == 0 && d.rope_cols <= d.N &&
@@ -712,9 +717,9 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   if (wide && pair_mode && d.M >= 256) {
     // the two shapes the model produces get epilogue-specialised kernels: fc1 forward (K-major x K-major, GELU) and
     // the fc2 dgrad that applies GELU' (K-major x MN-major)
-    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && !d.b_mn && d.epilogue == B200_EPI_BIAS_GELU)
+    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && !d.b_mn && d.epilogue == B200_EPI_BIAS_GELU && d.act == 0)
       return launch_gemm<256, 5, false, false, true, 64, B200_EPI_BIAS_GELU>(d, stream);
-    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && d.b_mn && d.epilogue == B200_EPI_DGELU)
+    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && d.b_mn && d.epilogue == B200_EPI_DGELU && d.act == 0)
       return launch_gemm<256, 5, false, true, true, 64, B200_EPI_DGELU>(d, stream);
     if (!d.a_mn && !d.b_mn) return launch_gemm<256, 5, false, false, true, 64>(d, stream);
     if (!d.a_mn && d.b_mn) return launch_gemm<256, 5, false, true, true, 64>(d, stream);

@@ -87,7 +87,7 @@ def test_layer_goldens():
     torch.testing.assert_close(O.drop_path(dp["x"], dp["keep_mask"], 1.0 - dp["drop_prob"]), dp["y"])
 
 
-@pytest.mark.parametrize("name", ["convnext_g1", "convnext_g2_v2_grn"])
+@pytest.mark.parametrize("name", ["convnext_g1", "convnext_g2_v2_grn", "convnext_g3_tanh_k7553"])
 def test_convnext_oracle_matches_reference(name):
     from oracle import convnext_oracle as C
     fx = torch.load(os.path.join(GOLDEN, name + ".pt"))
@@ -277,3 +277,17 @@ def test_convnext_v2_oracle_autograd_matches_reference_grads():
         assert torch.allclose(sd[k].grad, g, atol=1e-7 + 2e-4 * g.abs().max().item(), rtol=2e-3), (
             k, (sd[k].grad - g).abs().max().item(), g.abs().max().item())
 
+
+
+@pytest.mark.parametrize("name", ["gelu_tanh", "silu"])
+def test_mlp_activation_oracle_matches_reference(name):
+    """oracle mlp(act=...) (+ autograd) against timm.layers.Mlp(act_layer=get_act_layer(name)) (tests/golden/mlp_acts.pt)."""
+    fx = torch.load(os.path.join(GOLDEN, "mlp_acts.pt"))[name]
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    x = fx["x"].clone().requires_grad_(True)
+    y = O.mlp(x, sd["fc1.weight"], sd["fc1.bias"], sd["fc2.weight"], sd["fc2.bias"], act=name)
+    torch.testing.assert_close(y, fx["y"], atol=2e-6, rtol=1e-5)
+    (y * fx["wgt"]).sum().backward()
+    torch.testing.assert_close(x.grad, fx["dx"], atol=1e-5, rtol=1e-4)
+    for k, g in fx["grads"].items():
+        torch.testing.assert_close(sd[k].grad, g, atol=1e-4, rtol=1e-4, msg=lambda m: f"{k}: {m}")
