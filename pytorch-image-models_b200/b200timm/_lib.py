@@ -9,7 +9,8 @@ import re
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200timm.so")
+# B200TIMM_LIB: load another build of the library instead (same-box A/B runs of two kernel versions)
+LIB_PATH = os.environ.get("B200TIMM_LIB") or os.path.join(_HERE, "libb200timm.so")
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "b200timm.h"))
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3

@@ -84,7 +84,9 @@ __device__ __forceinline__ void load8_param2(const void* base, int f32, int col,
 
 // EPI >= 0 fixes the epilogue (and bf16 output) at compile time -- the transcendental epilogues get straight-line code
 // without the per-chunk epilogue-type branches; EPI = -1 is the generic kernel that reads p.epilogue at run time.
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2, int RC, int EPI>
+// ACTRT: the GELU / DGELU epilogues of the generic kernel read the activation kind from p.act (tanh GELU, SiLU); the
+// default instantiations (ACTRT = false) are the exact-GELU kernels with no trace of that switch.
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2, int RC, int EPI, bool ACTRT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
@@ -414,7 +416,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   }
                 } else if (epi == B200_EPI_BIAS_GELU && !dual) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) v[j] = (EPI < 0 && p.act) ? act_fwd2(v[j], p.act) : gelu_erf2(v[j]);
+                  for (int j = 0; j < 4; ++j) v[j] = (EPI < 0 && ACTRT && p.act) ? act_fwd2(v[j], p.act) : gelu_erf2(v[j]);
                 } else if (has_aux && !dual) {
                   uint4 q;
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
@@ -432,7 +434,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                      v[j] = mul2(v[j], (EPI < 0 && p.act) ? act_bwd2(av[j], p.act) : dgelu_erf2(av[j]));
+                      v[j] = mul2(v[j], (EPI < 0 && ACTRT && p.act) ? act_bwd2(av[j], p.act) : dgelu_erf2(av[j]));
                   }
                 }
               }
@@ -481,7 +483,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int i = 0; i < 4; ++i) {
                 float lo, hi;
                 const f32x2 xv = bf16x2_to_f32x2(w[i]);
-                upk((EPI < 0 && p.act) ? act_fwd2(xv, p.act) : gelu_erf2(xv), lo, hi);
+                upk((EPI < 0 && ACTRT && p.act) ? act_fwd2(xv, p.act) : gelu_erf2(xv), lo, hi);
                 o[i] = pack_bf16(lo, hi);
               }
             } else {
@@ -534,7 +536,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 static unsigned long long* g_gemm_trace = nullptr;
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2 = false, int RC = 32, int EPI = -1>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2 = false, int RC = 32, int EPI = -1, bool ACTRT = false>
 static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, CTA2, RC>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
@@ -602,7 +604,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.act = d.act;
   p.trace = g_gemm_trace;
 
-  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI, ACTRT>;
   static bool attr_set = false;  // idempotent; a benign race sets the same value twice
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -702,6 +704,20 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   // Tile-N selection: 256 wide unless N is small (wasted columns) -- 128 then.
   const bool wide = d.N > 128;
   // CTA pairs (256 x 256 tiles, cta_group::2) once there are enough 256-row tile pairs to fill the GPU
+  if (d.act != 0) {
+    // tanh GELU / SiLU: the activation-at-run-time instantiations of the two shapes an MLP produces -- fc1 forward
+    // (K-major x K-major, EPI_BIAS_GELU) and the fc2 dgrad (K-major x MN-major, EPI_DGELU)
+    B200_CHECK_ARG((d.epilogue == B200_EPI_BIAS_GELU || d.epilogue == B200_EPI_DGELU) && !d.a_mn && d.out_dtype == B200_DTYPE_BF16,
+                   "b200_gemm: act != 0 applies to the GELU / DGELU epilogues of K-major activations");
+    if (wide && d.M >= 256)
+      return d.b_mn ? launch_gemm<256, 5, false, true, true, 64, -1, true>(d, stream)
+                    : launch_gemm<256, 5, false, false, true, 64, -1, true>(d, stream);
+    if (wide)
+      return d.b_mn ? launch_gemm<256, 4, false, true, false, 32, -1, true>(d, stream)
+                    : launch_gemm<256, 4, false, false, false, 32, -1, true>(d, stream);
+    return d.b_mn ? launch_gemm<128, 6, false, true, false, 32, -1, true>(d, stream)
+                  : launch_gemm<128, 6, false, false, false, 32, -1, true>(d, stream);
+  }
   static const int pair_mode = [] { const char* e = getenv("B200_GEMM_2CTA"); return e ? atoi(e) : 1; }();
   // B200_GEMM_2CTA: 0 = single CTAs; 2 = pairs, 32-column epilogue rounds, 6-stage ring; 3 = pairs, 64-column rounds,
   //                 5-stage ring; 1 (default) = pairs, round width chosen per epilogue
@@ -717,9 +733,9 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   if (wide && pair_mode && d.M >= 256) {
     // the two shapes the model produces get epilogue-specialised kernels: fc1 forward (K-major x K-major, GELU) and
     // the fc2 dgrad that applies GELU' (K-major x MN-major)
-    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && !d.b_mn && d.epilogue == B200_EPI_BIAS_GELU && d.act == 0)
+    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && !d.b_mn && d.epilogue == B200_EPI_BIAS_GELU)
       return launch_gemm<256, 5, false, false, true, 64, B200_EPI_BIAS_GELU>(d, stream);
-    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && d.b_mn && d.epilogue == B200_EPI_DGELU && d.act == 0)
+    if (d.out_dtype == B200_DTYPE_BF16 && !d.a_mn && d.b_mn && d.epilogue == B200_EPI_DGELU)
       return launch_gemm<256, 5, false, true, true, 64, B200_EPI_DGELU>(d, stream);
     if (!d.a_mn && !d.b_mn) return launch_gemm<256, 5, false, false, true, 64>(d, stream);
     if (!d.a_mn && d.b_mn) return launch_gemm<256, 5, false, true, true, 64>(d, stream);
