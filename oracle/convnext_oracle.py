@@ -6,7 +6,7 @@ tests/golden/convnext_g1.pt) by tests/test_oracle_golden.py.  Each function cite
 (timm 1.0.28.dev0)."""
 import torch
 
-from .vit_oracle import ACTS, gelu_erf, layer_norm, linear
+from .vit_oracle import ACTS, layer_norm, linear
 
 
 def dwconv(x, weight, bias):

@@ -346,7 +346,6 @@ def glu_cases():
                     "act": type(m.act).__name__, "gate_last": getattr(m, "gate_last", None)}
     torch.save(fx, os.path.join(OUT, "glu.pt"))
     print("glu cases", {k: float(v["y"].abs().max()) for k, v in fx.items() if isinstance(v, dict)})
-    from functools import partial
     vit_case("vit_g5_swiglu", 6, 2, dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=128, depth=2,
                                          num_heads=2, mlp_ratio=2.0, qkv_bias=True, init_values=0.1,
                                          mlp_layer="SwiGLU", act_layer="silu"))

@@ -13,7 +13,6 @@ differences are execution and state precision:
 
 There is no CPU path: CPU parameters raise B200Error.
 """
-import ctypes
 from typing import Iterable, Optional
 
 import torch
