@@ -66,7 +66,9 @@ def cross_entropy(logits, target, label_smoothing: float = 0.0):
 
 
 class CrossEntropyLoss(nn.Module):
-    """nn.CrossEntropyLoss() as train.py:855 / benchmark.py:380 use it (mean reduction, optional label_smoothing)."""
+    """nn.CrossEntropyLoss() as train.py:855 / benchmark.py:380 use it (mean reduction, optional label_smoothing).
+    Rows whose class index lies outside [0, C) -- e.g. ignore_index -- contribute zero loss and zero gradient; unlike
+    torch the mean still divides by the batch size (the training scripts on this path never produce such targets)."""
 
     def __init__(self, weight=None, size_average=None, ignore_index=-100, reduce=None, reduction="mean", label_smoothing=0.0):
         super().__init__()
