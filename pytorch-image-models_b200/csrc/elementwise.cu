@@ -1,6 +1,7 @@
 // HBM-bound helper kernels around the GEMMs: patch gather (PatchEmbed), token assembly (cls/pos embed),
 // column sums (bias gradients).  All are 16-byte vectorised, coalesced along the innermost dimension.
 #include "common.h"
+#include <string.h>
 #include "ptx.cuh"
 
 namespace b200 {
@@ -74,11 +75,18 @@ __device__ __forceinline__ void ld8(const void* base, bool f32, long long idx, f
 }
 
 // The same gather for uint8 images with the loader's normalisation folded in (timm/data/loader.py:137-142:
-// next_input.to(float32).sub_(mean * 255).div_(std * 255)): value = bf16((float(u8) - mean[c]) / std[c]) -- the fp32
-// result of the reference rounded once, with a true division so it is bit-identical to normalise-then-cast.
-struct NormParams { float mean[8], std[8]; };
+// next_input.to(float32).sub_(mean * 255).div_(std * 255)).  A uint8 pixel has 256 possible values, so the normalised
+// bf16 value comes from a per-channel table lut[c][v] = bf16((float(v) - mean[c]) / std[c]) that the entry point fills on
+// the host with the same IEEE fp32 subtract / divide and one round-to-nearest-even -- bit-identical to
+// normalise-then-cast, and the kernel has no division (the first version divided on the device: 72 % XU-pipe
+// utilisation, 1.3 TB/s; profiles/r01g_kernels.md).  The table travels in the kernel's parameter space and is staged in
+// shared memory.
+struct NormLut { uint16_t v[8][256]; };
 __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H,
-                                   int W, int p, int gh, int gw, int Kpad, const NormParams nm) {
+                                   int W, int p, int gh, int gw, int Kpad, const __grid_constant__ NormLut lut) {
+  __shared__ uint16_t tab[8 * 256];
+  for (int i = threadIdx.x; i < C * 256; i += blockDim.x) tab[i] = lut.v[i >> 8][i & 255];
+  __syncthreads();
   const int kvecs = Kpad >> 3;
   const long long total = static_cast<long long>(B) * gh * gw * kvecs;
   const int K = C * p * p;
@@ -90,7 +98,7 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat1
     const int py = static_cast<int>((patch / gw) % gh);
     const int b = static_cast<int>(patch / (static_cast<long long>(gw) * gh));
     const int k0 = kv * 8;
-    float v[8];
+    uint32_t h[8];
     bool vec = false;
     if ((p & 7) == 0 && k0 + 8 <= K) {          // 8 consecutive pixels of one image row: one 8-byte load
       const int c = k0 / (p * p);
@@ -99,11 +107,11 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat1
       const uint8_t* src = img + ((static_cast<long long>(b) * C + c) * H + (py * p + ky)) * W + (px * p + kx);
       if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
         const uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
-        const float m = nm.mean[c], sd = nm.std[c];
+        const uint16_t* t = tab + c * 256;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          v[i] = (static_cast<float>((q.x >> (8 * i)) & 0xFFu) - m) / sd;
-          v[4 + i] = (static_cast<float>((q.y >> (8 * i)) & 0xFFu) - m) / sd;
+          h[i] = t[(q.x >> (8 * i)) & 0xFFu];
+          h[4 + i] = t[(q.y >> (8 * i)) & 0xFFu];
         }
         vec = true;
       }
@@ -117,15 +125,15 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat1
           const int rem = k - c * p * p;
           const int ky = rem / p, kx = rem - ky * p;
           const long long off = ((static_cast<long long>(b) * C + c) * H + (py * p + ky)) * W + (px * p + kx);
-          v[i] = (static_cast<float>(__ldg(img + off)) - nm.mean[c]) / nm.std[c];
+          h[i] = tab[c * 256 + __ldg(img + off)];
         } else {
-          v[i] = 0.f;
+          h[i] = 0u;
         }
       }
     }
     uint4 q;
-    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]);
-    q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    q.x = h[0] | (h[1] << 16); q.y = h[2] | (h[3] << 16);
+    q.z = h[4] | (h[5] << 16); q.w = h[6] | (h[7] << 16);
     *reinterpret_cast<uint4*>(out + patch * Kpad + k0) = q;
   }
 }
@@ -490,11 +498,17 @@ extern "C" int b200_patchify_u8(const void* img, void* patches, int32_t B, int32
   B200_CHECK_ARG(img && patches && mean && std, "b200_patchify_u8: null pointer");
   B200_CHECK_ARG(B > 0 && C > 0 && C <= 8 && p > 0 && H >= p && W >= p, "b200_patchify_u8: bad shape (1 <= C <= 8)");
   B200_CHECK_ARG(Kpad % 8 == 0 && Kpad >= C * p * p, "b200_patchify_u8: Kpad=%d must be a multiple of 8 and >= C*p*p", Kpad);
-  NormParams nm = {};
+  NormLut lut = {};
   for (int c = 0; c < C; ++c) {
     B200_CHECK_ARG(std[c] != 0.f, "b200_patchify_u8: std[%d] is zero", c);
-    nm.mean[c] = mean[c];
-    nm.std[c] = std[c];
+    for (int v = 0; v < 256; ++v) {
+      const volatile float d = static_cast<float>(v) - mean[c];      // fp32 subtract, then fp32 divide (IEEE, no contraction)
+      const float f = d / std[c];
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      u += 0x7FFFu + ((u >> 16) & 1u);                               // round to nearest even, as cvt.rn.bf16.f32
+      lut.v[c][v] = static_cast<uint16_t>(u >> 16);
+    }
   }
   const int gh = H / p, gw = W / p;
   const long long total = static_cast<long long>(B) * gh * gw * (Kpad / 8);
@@ -504,7 +518,7 @@ extern "C" int b200_patchify_u8(const void* img, void* patches, int32_t B, int32
   if (blocks > cap) blocks = cap;
   patchify_u8_kernel<<<static_cast<int>(blocks), threads, 0, st>>>(reinterpret_cast<const uint8_t*>(img),
                                                                     reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p,
-                                                                    gh, gw, Kpad, nm);
+                                                                    gh, gw, Kpad, lut);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

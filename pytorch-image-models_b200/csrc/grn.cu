@@ -100,9 +100,19 @@ __global__ void __launch_bounds__(kGrnThreads) grn_apply_kernel(__nv_bfloat16* _
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + static_cast<long long>(img) * C + cv * 8));
     const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + static_cast<long long>(img) * C + cv * 8) + 1);
     const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (bias != nullptr) {
+      if (b_f32) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bias) + cv * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(bias) + cv * 8) + 1);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+      } else {
+        unpack8f(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(bias) + cv * 8)), bv);
+      }
+    }
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = fmaf(x[i], s[i], bias != nullptr ? ldw(bias, b_f32, cv * 8 + i) : 0.f);
+    for (int i = 0; i < 8; ++i) y[i] = fmaf(x[i], s[i], bv[i]);
     uint4 q;
     q.x = pack_bf16(y[0], y[1]); q.y = pack_bf16(y[2], y[3]);
     q.z = pack_bf16(y[4], y[5]); q.w = pack_bf16(y[6], y[7]);

@@ -53,6 +53,30 @@ def main(op):
     elif op == "colsum":
         x = r(M, 3072)
         f = lambda: ops.colsum(x)                                                        # noqa: E731
+    elif op in ("qk_norm", "qk_norm_bwd"):
+        qkv, dq = r(B * N, 3 * H * 64), r(B * N, 3 * H * 64)
+        qw, qb, kw, kb = r(64), r(64), r(64), r(64)
+        raw, mean, rstd = ops.qk_norm_fwd(qkv.clone(), B * N, H, qw, qb, kw, kb, 1e-6, save=True)
+        f = (lambda: ops.qk_norm_fwd(qkv, B * N, H, qw, qb, kw, kb, 1e-6, save=True)) if op == "qk_norm" else \
+            (lambda: ops.qk_norm_bwd(dq, raw, mean, rstd, qw, kw, B * N, H))
+    elif op == "glu":
+        h = r(M, 2 * 2048)
+        f = lambda: ops.glu_fwd(h, True, "silu")                                         # noqa: E731
+    elif op in ("grn", "grn_bwd"):                     # ConvNeXt-V2-B stage 3: [256, 14*14, 2048]
+        pre, w, b, d = r(256 * 196, 2048), r(2048, scale=0.3), r(2048, scale=0.1), r(256 * 196, 2048)
+        act = torch.nn.functional.gelu(pre.float()).bfloat16()
+        gsq, scale = ops.grn_fwd(act.clone(), w, b, 256, 196)
+        f = (lambda: ops.grn_fwd(act, w, b, 256, 196)) if op == "grn" else \
+            (lambda: ops.grn_bwd(d, pre, gsq, scale, w, 256, 196))
+    elif op == "patchify_u8":
+        img = torch.randint(0, 256, (B, 3, 224, 224), dtype=torch.uint8, device="cuda")
+        ops.set_input_norm((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+        f = lambda: ops.patchify(img, 16)                                                # noqa: E731
+    elif op == "ema":
+        from b200timm.ema import lerp_
+        es = [r(3072, 768) for _ in range(24)]
+        ms = [r(3072, 768) for _ in range(24)]
+        f = lambda: lerp_(es, ms, 1e-4)                                                  # noqa: E731
     elif op == "gemm_dgelu":
         dy, w, pre = r(M, D), r(D, 3072, scale=0.05), r(M, 3072)
         f = lambda: ops.linear_dgrad(dy, w, epilogue=ops.EPI_DGELU, aux=pre)             # noqa: E731
