@@ -54,6 +54,29 @@ __device__ __forceinline__ f32x2 dgelu_erf2(f32x2 x) {
   return fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);
 }
 
+// GELU(x) and GELU'(x) together from one evaluation of Phi (7.1.26) and phi: GELU = x Phi, GELU' = Phi + x phi.
+__device__ __forceinline__ void gelu_and_dgelu2(f32x2 x, f32x2& g, f32x2& dg) {
+  float x0, x1;
+  upk(x, x0, x1);
+  const f32x2 ax = pk(fabsf(x0), fabsf(x1));
+  float d0, d1;
+  upk(fma2(ax, splat(0.3275911f * 0.70710678118654752f), splat(1.0f)), d0, d1);
+  const f32x2 t = pk(rcp_approx(d0), rcp_approx(d1));
+  f32x2 q = fma2(t, splat(0.5f * 1.061405429f), splat(0.5f * -1.453152027f));
+  q = fma2(q, t, splat(0.5f * 1.421413741f));
+  q = fma2(q, t, splat(0.5f * -0.284496736f));
+  q = fma2(q, t, splat(0.5f * 0.254829592f));
+  q = mul2(q, t);
+  float w0, w1;
+  upk(mul2(mul2(x, x), splat(-0.72134752044448170f)), w0, w1);
+  const f32x2 e = pk(ex2_approx(w0), ex2_approx(w1));
+  float s0, s1;
+  upk(fma2(q, mul2(e, splat(-1.0f)), splat(0.5f)), s0, s1);
+  const f32x2 cdf = add2(pk(copysignf(s0, x0), copysignf(s1, x1)), splat(0.5f));
+  g = mul2(x, cdf);
+  dg = fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);
+}
+
 // The other MLP activations timm configures on this path (create_act.py: 'gelu_tanh' = GELUTanh / nn.GELU('tanh'), used by
 // the SigLIP ViTs and timm's test_convnext; 'silu'): selected at run time by b200_gemm_desc.act in the generic kernels.
 //   tanh(u) = 1 - 2 / (1 + e^{2u})  (ex2 + rcp: two MUFU, abs. error ~1e-6, saturates correctly at +-inf)

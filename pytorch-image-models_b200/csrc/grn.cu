@@ -169,10 +169,11 @@ __global__ void __launch_bounds__(kGrnThreads) grn_bwd_apply_kernel(const __nv_b
     float y[8];
 #pragma unroll
     for (int i = 0; i < 8; i += 2) {
-      const f32x2 xp = pk(x[i], x[i + 1]);
+      f32x2 gp, dgp;
+      gelu_and_dgelu2(pk(x[i], x[i + 1]), gp, dgp);
       float g0, g1, dg0, dg1;
-      upk(gelu_erf2(xp), g0, g1);
-      upk(dgelu_erf2(xp), dg0, dg1);
+      upk(gp, g0, g1);
+      upk(dgp, dg0, dg1);
       y[i] = fmaf(d[i], s[i], g0 * tt[i]) * dg0;
       y[i + 1] = fmaf(d[i + 1], s[i + 1], g1 * tt[i + 1]) * dg1;
     }
