@@ -144,3 +144,28 @@ def test_model_ema_rebinding_keeps_cpu_models_on_timms_path():
     P.uninstall()
     assert not hasattr(ModelEmaV3.apply_update_, "_b200_original")
     P.install()
+
+
+def test_variant_modules_are_rebound_and_cpu_calls_stay_on_timm(plugin):
+    """Every variant class the table gained late in round 1 (gated MLPs, attention-pool head, qk-norm attention, GRN
+    ConvNeXt blocks): rebound, and a CPU / fp32 call still produces timm's own result bit for bit."""
+    from timm.layers import Attention, AttentionPoolLatent, GluMlp, LayerNorm, SwiGLU, SwiGLUPacked
+    from timm.models.convnext import ConvNeXt
+    torch.manual_seed(0)
+    mods = [(SwiGLU(32, 64), torch.randn(2, 5, 32)), (SwiGLUPacked(32, 128), torch.randn(2, 5, 32)),
+            (GluMlp(32, 128), torch.randn(2, 5, 32)), (AttentionPoolLatent(64, num_heads=1, norm_layer=LayerNorm), torch.randn(2, 9, 64)),
+            (Attention(64, num_heads=1, qk_norm=True, scale_norm=True, norm_layer=LayerNorm), torch.randn(2, 9, 64)),
+            (ConvNeXt(depths=(1, 1, 1, 1), dims=(8, 16, 24, 32), num_classes=5, use_grn=True, ls_init_value=None), torch.randn(2, 3, 32, 32)),
+            (timm.create_model("vit_tiny_patch16_224", img_size=32, num_classes=4, global_pool="map", class_token=False,
+                               act_layer="gelu_tanh", qk_norm=True), torch.randn(2, 3, 32, 32))]
+    for cls in (SwiGLU, GluMlp, AttentionPoolLatent, Attention):
+        assert hasattr(cls.forward, "_b200_original"), cls.__name__
+    outs = []
+    with torch.no_grad():
+        for m, x in mods:
+            outs.append(m.eval()(x))
+    plugin.uninstall()
+    with torch.no_grad():
+        for (m, x), y in zip(mods, outs):
+            assert torch.equal(m(x), y), type(m).__name__
+    plugin.install()
