@@ -161,3 +161,31 @@ def test_prefetch_loader_mirror_host_logic():
             ops.set_input_norm((0.5,), (0.0,))
     finally:
         ops.set_input_norm(None)
+
+
+def test_loss_and_ema_mirrors_host_logic():
+    """b200timm.loss / b200timm.ema: class names and constructor arguments of the reference (timm/loss/cross_entropy.py,
+    timm/utils/model_ema.py:156-203), the decay schedule, and the refusal of CPU tensors (no fallback)."""
+    from b200timm import ema as BE, loss as BL
+    ls = BL.LabelSmoothingCrossEntropy(smoothing=0.2)
+    assert ls.smoothing == 0.2 and ls.confidence == 0.8
+    with pytest.raises(B200Error):
+        BL.CrossEntropyLoss(reduction="sum")
+    with pytest.raises(B200Error):
+        BL.CrossEntropyLoss(weight=torch.ones(3))
+    for mod, tgt in ((BL.CrossEntropyLoss(), torch.tensor([0, 1])), (ls, torch.tensor([0, 1])),
+                     (BL.SoftTargetCrossEntropy(), torch.full((2, 5), 0.2))):
+        with pytest.raises(B200Error):
+            mod(torch.randn(2, 5), tgt)
+    with pytest.raises(B200Error):
+        BL.SoftTargetCrossEntropy()(torch.randn(2, 5), torch.tensor([0, 1]))
+    m = torch.nn.Linear(4, 3)
+    e = BE.ModelEma(m, decay=0.998, use_warmup=True, update_after_step=1)
+    assert e.module is not m and not e.module.training
+    assert [e.get_decay(s) for s in (None, 1, 2)] == [0.998, 0.0, 0.0]
+    assert e.get_decay(3) == pytest.approx(1 - 2 ** (-2 / 3)) and e.get_decay(10 ** 9) == 0.998
+    e.set(m)
+    with pytest.raises(B200Error):
+        e.update(m, step=5)                       # CPU model: no fallback
+    e32 = BE.ModelEma(m.to(torch.bfloat16), ema_dtype=torch.float32)
+    assert e32.module.weight.dtype == torch.float32
