@@ -420,7 +420,26 @@ MAP_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_
 CNX_V2_KWARGS = dict(depths=(1, 1, 2, 1), dims=(16, 32, 64, 128), num_classes=10, use_grn=True, ls_init_value=None)
 
 
+def prefetch_case():
+    """timm.data.loader.PrefetchLoader (run on the CPU device) over one uint8 batch: the normalised fp32 batch the model
+    would receive -> tests/golden/prefetch.pt."""
+    import timm
+    from timm.data.loader import PrefetchLoader
+    g = torch.Generator().manual_seed(71)
+    batch = torch.randint(0, 256, (3, 3, 32, 32), dtype=torch.uint8, generator=g)
+    target = torch.randint(0, 10, (3,), generator=g)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    (x, y), = list(PrefetchLoader([(batch, target)], mean=mean, std=std, device=torch.device("cpu")))
+    fx = {"kind": "prefetch", "u8": batch, "target": target, "mean": mean, "std": std, "normalized": x.clone(),
+          "timm_version": timm.__version__}
+    torch.save(fx, os.path.join(OUT, "prefetch.pt"))
+    print("prefetch", x.dtype, float(x.abs().max()))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "prefetch":
+        os.makedirs(OUT, exist_ok=True)
+        return prefetch_case()
     if len(sys.argv) > 1 and sys.argv[1] == "acts":
         os.makedirs(OUT, exist_ok=True)
         mlp_act_cases()
@@ -485,6 +504,7 @@ def main():
     mlp_act_cases()
     vit_case("vit_g9_siglip_like", 11, 2, SIGLIP_KWARGS)
     convnext_case("convnext_g3_tanh_k7553", 12, 2, CNX_TANH_KWARGS, 64, backward=True)
+    prefetch_case()
 
 
 if __name__ == "__main__":

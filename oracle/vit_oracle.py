@@ -431,3 +431,14 @@ def vit_forward_eager(img, sd, cfg, kv_len=None):
     if "head.weight" in sd:
         x = F.linear(x, sd["head.weight"], sd.get("head.bias"))
     return x
+
+
+def normalize_u8(img_u8, mean, std):
+    """PrefetchLoader's device-side normalisation, timm/data/loader.py:106-109,139: mean / std (per channel, [0, 1] units)
+    become fp32 tensors of `x * 255`; the uint8 batch is widened to fp32, the mean subtracted and the result divided by std.
+    numpy float32 arithmetic (IEEE subtract, then divide) -- what the CUDA path's per-channel lookup table reproduces."""
+    import numpy as np
+    x = img_u8.numpy().astype(np.float32)
+    m = np.asarray([v * 255 for v in mean], dtype=np.float32).reshape(1, -1, 1, 1)
+    s = np.asarray([v * 255 for v in std], dtype=np.float32).reshape(1, -1, 1, 1)
+    return torch.from_numpy((x - m) / s)

@@ -291,3 +291,18 @@ def test_mlp_activation_oracle_matches_reference(name):
     torch.testing.assert_close(x.grad, fx["dx"], atol=1e-5, rtol=1e-4)
     for k, g in fx["grads"].items():
         torch.testing.assert_close(sd[k].grad, g, atol=1e-4, rtol=1e-4, msg=lambda m: f"{k}: {m}")
+
+
+def test_prefetch_normalisation_oracle_matches_reference_bit_exactly():
+    """oracle normalize_u8 == timm's PrefetchLoader output (tests/golden/prefetch.pt), bit for bit; and the bf16 rounding of
+    it equals the per-channel lookup table the CUDA patch gather builds on the host (same arithmetic in numpy)."""
+    import numpy as np
+    fx = torch.load(os.path.join(GOLDEN, "prefetch.pt"))
+    got = O.normalize_u8(fx["u8"], fx["mean"], fx["std"])
+    assert got.dtype == torch.float32 and torch.equal(got, fx["normalized"])
+    for c, (m, s) in enumerate(zip(fx["mean"], fx["std"])):
+        f = ((np.arange(256, dtype=np.float32) - np.float32(m * 255)) / np.float32(s * 255)).astype(np.float32)
+        u = f.view(np.uint32).astype(np.uint64)
+        lut = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)          # round to nearest even, as csrc/elementwise.cu
+        want = fx["normalized"][:, c].to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+        assert (lut[fx["u8"][:, c].numpy()] == want).all()
