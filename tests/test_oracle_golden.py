@@ -48,15 +48,23 @@ def test_eager_timing_port_matches_reference(path):
         torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5)
 
 
-def test_vit_backward_matches_reference():
-    """Gradients of every parameter after outputs.mean().backward() (tests/test_models.py:209-242 pattern)."""
-    fx = torch.load(os.path.join(GOLDEN, "vit_g1_default.pt"))
+GRAD_FILES = [p for p in VIT_FILES if "grads" in torch.load(p)]
+
+
+@pytest.mark.parametrize("path", GRAD_FILES, ids=[os.path.basename(p)[:-3] for p in GRAD_FILES])
+def test_vit_backward_matches_reference(path):
+    """Gradients of every parameter after outputs.mean().backward() (tests/test_models.py:209-242 pattern), for every ViT
+    fixture that carries the reference's gradients (default, RMSNorm, SwiGLU, qk-norm, dynamic size, map pool, SigLIP-like).
+    Gradients that are analytically zero (a bias on k) hold cancellation noise on both sides: absolute tolerance scaled
+    to the largest gradient."""
+    fx = torch.load(path)
     cfg = _cfg(fx["kwargs"])
     sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
     O.vit_forward(fx["img"], sd, cfg).mean().backward()
     assert set(fx["grads"]) == set(sd)
+    scale = max(g.abs().max().item() for g in fx["grads"].values())
     for k, ref in fx["grads"].items():
-        torch.testing.assert_close(sd[k].grad, ref, atol=1e-6, rtol=1e-4, msg=lambda m: f"{k}: {m}")
+        torch.testing.assert_close(sd[k].grad, ref, atol=1e-6 + 2e-6 * scale, rtol=2e-4, msg=lambda m: f"{k}: {m}")
 
 
 def test_layer_goldens():
