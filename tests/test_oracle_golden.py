@@ -274,10 +274,12 @@ def test_attention_norm_oracle_matches_reference(name):
         torch.testing.assert_close(sd[k].grad, g, atol=5e-4, rtol=1e-3, msg=lambda m: f"{k}: {m}")
 
 
-def test_convnext_v2_oracle_autograd_matches_reference_grads():
-    """ConvNeXt-V2 (GlobalResponseNorm in every block): autograd of the oracle against the reference's parameter gradients."""
+@pytest.mark.parametrize("name", ["convnext_g2_v2_grn", "convnext_g3_tanh_k7553"])
+def test_convnext_oracle_autograd_matches_reference_grads(name):
+    """ConvNeXt-V2 (GlobalResponseNorm in every block) and the tanh-GELU / mixed-kernel-size configuration: autograd of
+    the oracle against the reference's parameter gradients."""
     from oracle import convnext_oracle as C
-    fx = torch.load(os.path.join(GOLDEN, "convnext_g2_v2_grn.pt"))
+    fx = torch.load(os.path.join(GOLDEN, name + ".pt"))
     sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
     C.convnext_forward(fx["img"], sd, dict(fx["kwargs"])).mean().backward()
     assert sorted(sd) == sorted(fx["grads"])
