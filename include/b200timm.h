@@ -47,6 +47,7 @@ extern "C" {
                                  `rot` layout, head_dim 64, one [sin | cos] table shared by batch and heads)       */
 
 B200_API const char* b200_last_error(void);
+/* 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
 B200_API int b200_abi_version(void);
 /* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
 B200_API int b200_device_check(void);
