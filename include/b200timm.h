@@ -309,15 +309,17 @@ B200_API int b200_ema_update(const b200_optim_tensor* tensors, int32_t n, int32_
  * (timm/loss/cross_entropy.py:11-26: (1 - s) * nll + s * mean_c(-log_softmax)) with class indices `target` (int64 [B]),
  * or SoftTargetCrossEntropy (:29-36: sum_c(-t * log_softmax)) with a distribution `soft_target` [B, C] (bf16 / fp32);
  * exactly one of the two is non-NULL.  'mean' reduction over the B rows.  logits [B, C] bf16 or fp32, contiguous.
- * Forward writes loss_rows[B], lse[B] (log-sum-exp), tsum[B] (sum of the row's target weights) and *loss_mean (all fp32).
- * A class index outside [0, C) makes the row contribute 0 to the sum (the mean still divides by B).
- * Backward: dlogits (dtype of logits) = (softmax * tsum - target distribution) * *grad_out / B.                       */
+ * Forward writes loss_rows[B], lse[B] (log-sum-exp), tsum[B] (sum of the row's target weights), loss_mean[0] = the mean
+ * and loss_mean[1] = its denominator (all fp32).  A row whose class index equals `ignore_index` (nn.CrossEntropyLoss's
+ * argument; also any index outside [0, C)) contributes nothing and is not counted: the denominator is the number of
+ * remaining rows, as in torch (all rows ignored -> NaN, as in torch); soft targets divide by B.
+ * Backward: dlogits (dtype of logits) = (softmax * tsum - target distribution) * *grad_out / *denom.                  */
 B200_API int b200_cross_entropy_fwd(const void* logits, int32_t logits_dtype, const int64_t* target, const void* soft_target,
-                         int32_t soft_dtype, double smoothing, float* loss_rows, float* lse, float* tsum,
-                         float* loss_mean, int32_t B, int32_t C, void* stream);
+                         int32_t soft_dtype, double smoothing, int64_t ignore_index, float* loss_rows, float* lse,
+                         float* tsum, float* loss_mean, int32_t B, int32_t C, void* stream);
 B200_API int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* target, const void* soft_target,
                          int32_t soft_dtype, double smoothing, const float* lse, const float* tsum,
-                         const float* grad_out, void* dlogits, int32_t B, int32_t C, void* stream);
+                         const float* grad_out, const float* denom, void* dlogits, int32_t B, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -328,7 +328,7 @@ def stage_forward_nhwc(self, x, B, H, W):
 def _dw_weight_t(conv):
     """Depthwise Conv2d weight [C,1,k,k] -> cached [k,k,C] (the layout the dwconv kernel reads 16 bytes per tap)."""
     w = conv.weight
-    key = (w.data_ptr(), w._version)
+    key = ops.wkey(w)
     cache = getattr(conv, "_b200_wt", None)
     if cache is None or cache[0] != key:
         conv._b200_wt = (key, ops.dwconv_weight_t(w.detach().to(torch.bfloat16)))
@@ -339,7 +339,7 @@ def _dw_weight_t(conv):
 def _conv_weight_khwc(conv):
     """Conv2d weight [Cout, Cin, kh, kw] -> cached contiguous [Cout, kh*kw*Cin] matching patchify_nhwc's k order."""
     w = conv.weight
-    key = (w.data_ptr(), w._version)
+    key = ops.wkey(w)
     cache = getattr(conv, "_b200_khwc", None)
     if cache is None or cache[0] != key:
         conv._b200_khwc = (key, w.detach().to(torch.bfloat16).permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())

@@ -13,7 +13,7 @@ from torch import nn
 
 from . import _lib
 from ._lib import B200Error, DTYPE_BF16, DTYPE_F32
-from .ops import _count, _stream
+from .ops import _count, _stream, note_params_written
 from .optim import _table
 
 _DT = {torch.bfloat16: DTYPE_BF16, torch.float32: DTYPE_F32}
@@ -34,6 +34,7 @@ def lerp_(ema_tensors, model_tensors, weight: float):
         rc = lib.b200_ema_update(_table(rows), len(rows), _DT[ed], _DT[md], float(weight), _stream())
         _lib.check(rc, "b200_ema_update")
         _count()
+    note_params_written([r[0] for rows in groups.values() for r in rows])
 
 
 def fast_update(ema, model, decay: float, buffers: bool = True):

@@ -156,7 +156,7 @@ def _w(linear):
         raise B200Error(f"weights must be bf16 or fp32, got {w.dtype}")
     if torch.is_grad_enabled() and w.requires_grad:
         return w.to(torch.bfloat16)
-    key = (w.data_ptr(), w._version)
+    key = ops.wkey(w)
     cache = getattr(linear, "_b200_wbf16", None)
     if cache is None or cache[0] != key:
         linear._b200_wbf16 = cache = (key, w.detach().to(torch.bfloat16).contiguous())
@@ -170,7 +170,7 @@ def _padded_out_linear(linear, x2):
     w, b = linear.weight, linear.bias
     N, K = w.shape
     npad = (N + 7) // 8 * 8
-    key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version))
+    key = (*ops.wkey(w), None if b is None else ops.wkey(b))
     cache = getattr(linear, "_b200_npad", None)
     if cache is None or cache[0] != key:
         wp = torch.zeros(npad, K, dtype=torch.bfloat16, device=w.device)
@@ -237,7 +237,7 @@ def _rope_table(rope, n_rot, head_dim, device):
         r = r[0]
     if r.dim() != 2 or tuple(r.shape) != (n_rot, 2 * head_dim):
         raise B200Error(f"AttentionRope: rope must broadcast from [{n_rot}, {2 * head_dim}], got {tuple(rope.shape)}")
-    key = (rope.data_ptr(), rope._version, str(device))
+    key = (*ops.wkey(rope), str(device))
     cache = _rope_table.cache
     if cache.get("key") != key:
         cache["key"], cache["val"] = key, r.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -323,8 +323,8 @@ def _glu_params(mlp):
             w1 = torch.cat([wg, wx], 0)
             b1 = None if bg is None else torch.cat([bg, bx], 0)
         else:
-            key = (wg.data_ptr(), wg._version, wx.data_ptr(), wx._version,
-                   None if bg is None else (bg.data_ptr(), bg._version, bx.data_ptr(), bx._version))
+            key = (*ops.wkey(wg), *ops.wkey(wx),
+                   None if bg is None else (*ops.wkey(bg), *ops.wkey(bx)))
             cache = getattr(mlp, "_b200_w1cat", None)
             if cache is None or cache[0] != key:
                 cache = (key, torch.cat([wg, wx], 0).contiguous(), None if bg is None else torch.cat([bg, bx], 0))
@@ -457,10 +457,10 @@ def patch_embed_forward(pe, img):
     w2 = w.view(D, K)
     if kpad != K:  # 16-byte row stride for TMA (e.g. patch 14: K = 588 -> 592), zero padded
         cache = getattr(pe, "_b200_wpad", None)
-        if cache is None or cache[0] != (w.data_ptr(), w._version):
+        if cache is None or cache[0] != ops.wkey(w):
             wp = torch.zeros(D, kpad, dtype=w.dtype, device=w.device)
             wp[:, :K] = w2
-            pe._b200_wpad = ((w.data_ptr(), w._version), wp)
+            pe._b200_wpad = (ops.wkey(w), wp)
             cache = pe._b200_wpad
         w2 = cache[1]
     patches = ops.patchify(img.contiguous(), ph, kpad)
@@ -489,7 +489,7 @@ def _dynamic_pos_embed(model, img):
     npt = 0 if getattr(model, "no_embed_class", False) else model.num_prefix_tokens
     if torch.is_grad_enabled() and pos.requires_grad:
         return resample_pos_embed(pos, new, pe.grid_size, npt)
-    key = (pos.data_ptr(), pos._version, new)
+    key = (*ops.wkey(pos), new)
     cache = getattr(model, "_b200_pos_cache", None)
     if cache is None or cache[0] != key:
         with torch.no_grad():

@@ -246,7 +246,7 @@ class Attention(nn.Module):
         if is_causal:
             raise B200Error("causal attention is not supported")
         if attn_mask is not None:
-            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1]) if kv_len is None else kv_len
+            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1], x.shape[0]) if kv_len is None else kv_len
         return BF.attention_forward(self, x, kv_len)
 
 
@@ -289,14 +289,24 @@ class AttentionRope(nn.Module):
         if is_causal:
             raise B200Error("causal attention is not supported")
         if attn_mask is not None:
-            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1]) if kv_len is None else kv_len
+            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1], x.shape[0]) if kv_len is None else kv_len
         return BF.attention_rope_forward(self, x, rope, kv_len)
 
 
-def BF_mask_to_kv_len(attn_mask: torch.Tensor, n_tokens: int) -> torch.Tensor:
+_KV_CACHE = {}      # id(mask) -> (weakref to the mask, version, n_tokens, batch, kv_len): one conversion per forward, not per block
+
+
+def BF_mask_to_kv_len(attn_mask: torch.Tensor, n_tokens: int, batch: Optional[int] = None) -> torch.Tensor:
     """Convert a NaFlex key-padding mask (bool keep-mask or additive float, broadcastable to [B,1,N,N],
-    naflexvit.py:964-1029) into per-sample valid-key counts.  The collator always emits prefix-valid masks
-    (naflex_dataset.py:136-142); anything else is rejected."""
+    naflexvit.py:964-1029) into per-sample valid-key counts (int32 [B]).  The collator always emits prefix-valid masks
+    (naflex_dataset.py:136-142); anything else is rejected.  The prefix-validity check reads one flag back from the
+    device, so the result is cached on the mask object: the 24 blocks of a forward that receive the same mask tensor
+    pay for one conversion (and one host sync), and a mask with batch dimension 1 is expanded to `batch` entries."""
+    import weakref
+    key = id(attn_mask)
+    hit = _KV_CACHE.get(key)
+    if hit is not None and hit[0]() is attn_mask and hit[1:4] == (attn_mask._version, n_tokens, batch):
+        return hit[4]
     m = attn_mask
     if m.dtype != torch.bool:
         m = m > -1.0  # additive masks hold 0 (keep) or finfo.min (drop)
@@ -307,7 +317,14 @@ def BF_mask_to_kv_len(attn_mask: torch.Tensor, n_tokens: int) -> torch.Tensor:
     expect = torch.arange(n_tokens, device=m.device)[None, :] < kv_len[:, None]
     if not bool((keys == expect).all()):
         raise B200Error("only prefix-valid key-padding masks are supported (NaFlex layout)")
-    return kv_len.contiguous()
+    if batch is not None and kv_len.numel() == 1 and batch > 1:
+        kv_len = kv_len.expand(batch)
+    kv_len = kv_len.contiguous()
+    if len(_KV_CACHE) > 64:
+        for k in [k for k, v in _KV_CACHE.items() if v[0]() is None]:
+            del _KV_CACHE[k]
+    _KV_CACHE[key] = (weakref.ref(attn_mask), attn_mask._version, n_tokens, batch, kv_len)
+    return kv_len
 
 
 class PatchEmbed(nn.Module):

@@ -16,7 +16,7 @@ _DT = {torch.bfloat16: DTYPE_BF16, torch.float32: DTYPE_F32}
 
 class _CrossEntropyFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target, smoothing):
+    def forward(ctx, logits, target, smoothing, ignore_index=-100):
         if not logits.is_cuda or not target.is_cuda:
             raise B200Error("libb200timm kernels need CUDA tensors (there is no CPU path)")
         if logits.dim() != 2 or logits.dtype not in _DT:
@@ -32,11 +32,11 @@ class _CrossEntropyFn(torch.autograd.Function):
         elif target.dim() != 1 or target.shape[0] != B or target.dtype != torch.int64:
             raise B200Error("cross entropy: class-index targets must be int64 [B]")
         t = target if target.is_contiguous() else target.contiguous()
-        buf = torch.empty(3 * B + 1, dtype=torch.float32, device=logits.device)     # loss rows | lse | tsum | mean
+        buf = torch.empty(3 * B + 2, dtype=torch.float32, device=logits.device)     # loss rows | lse | tsum | mean, denominator
         p = buf.data_ptr()
         rc = _lib.load().b200_cross_entropy_fwd(x.data_ptr(), _DT[x.dtype], None if soft else t.data_ptr(),
                                                 t.data_ptr() if soft else None, _DT[t.dtype] if soft else DTYPE_F32,
-                                                float(smoothing), p, p + 4 * B, p + 8 * B, p + 12 * B, B, C, _stream())
+                                                float(smoothing), int(ignore_index), p, p + 4 * B, p + 8 * B, p + 12 * B, B, C, _stream())
         _lib.check(rc, "b200_cross_entropy_fwd")
         _count(2)
         ctx.save_for_backward(x, t, buf)
@@ -53,22 +53,23 @@ class _CrossEntropyFn(torch.autograd.Function):
         soft = ctx.soft
         rc = _lib.load().b200_cross_entropy_bwd(x.data_ptr(), _DT[x.dtype], None if soft else t.data_ptr(),
                                                 t.data_ptr() if soft else None, _DT[t.dtype] if soft else DTYPE_F32,
-                                                ctx.smoothing, p + 4 * B, p + 8 * B, g.data_ptr(), dx.data_ptr(), B, C,
+                                                ctx.smoothing, p + 4 * B, p + 8 * B, g.data_ptr(), p + 12 * B + 4, dx.data_ptr(), B, C,
                                                 _stream())
         _lib.check(rc, "b200_cross_entropy_bwd")
         _count()
-        return dx, None, None
+        return dx, None, None, None
 
 
-def cross_entropy(logits, target, label_smoothing: float = 0.0):
-    """F.cross_entropy(logits, target, label_smoothing=...) with 'mean' reduction; `target` int64 [B] or a [B, C] distribution."""
-    return _CrossEntropyFn.apply(logits, target, label_smoothing)
+def cross_entropy(logits, target, label_smoothing: float = 0.0, ignore_index: int = -100):
+    """F.cross_entropy(logits, target, ignore_index=..., label_smoothing=...) with 'mean' reduction; `target` int64 [B] or a
+    [B, C] distribution."""
+    return _CrossEntropyFn.apply(logits, target, label_smoothing, ignore_index)
 
 
 class CrossEntropyLoss(nn.Module):
     """nn.CrossEntropyLoss() as train.py:855 / benchmark.py:380 use it (mean reduction, optional label_smoothing).
-    Rows whose class index lies outside [0, C) -- e.g. ignore_index -- contribute zero loss and zero gradient; unlike
-    torch the mean still divides by the batch size (the training scripts on this path never produce such targets)."""
+    Rows whose class index equals `ignore_index` contribute zero loss and zero gradient and the mean divides by the number
+    of remaining rows, as torch does (aten/src/ATen/native/LossNLL.cpp; all rows ignored -> NaN, as in torch)."""
 
     def __init__(self, weight=None, size_average=None, ignore_index=-100, reduce=None, reduction="mean", label_smoothing=0.0):
         super().__init__()
@@ -77,7 +78,7 @@ class CrossEntropyLoss(nn.Module):
         self.ignore_index, self.label_smoothing = ignore_index, label_smoothing
 
     def forward(self, x, target):
-        return _CrossEntropyFn.apply(x, target, self.label_smoothing)
+        return _CrossEntropyFn.apply(x, target, self.label_smoothing, self.ignore_index)
 
 
 class LabelSmoothingCrossEntropy(nn.Module):

@@ -121,10 +121,10 @@ class NaFlexVit(nn.Module):
             x = F.pad(x, (0, kpad - K))
             if not train:
                 cache = getattr(e, "_b200_wpad", None)
-                if cache is None or cache[0] != (w.data_ptr(), w._version):
+                if cache is None or cache[0] != ops.wkey(w):
                     wp = torch.zeros(w.shape[0], kpad, dtype=w.dtype, device=w.device)
                     wp[:, :K] = w.detach()
-                    e._b200_wpad = ((w.data_ptr(), w._version), wp)
+                    e._b200_wpad = (ops.wkey(w), wp)
                     cache = e._b200_wpad
                 w = cache[1]
         x = x.contiguous()

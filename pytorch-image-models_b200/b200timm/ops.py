@@ -60,6 +60,26 @@ def gemm_timing_summary():
     return flops, ms, len(_gemm_timing)
 
 
+# ------------------------------------------------------------------------------------ weight-cache invalidation
+_param_epoch = 0       # bumped whenever a kernel wrote parameters through raw pointers (optimizer step, EMA, graph replay)
+
+
+def wkey(t):
+    """Cache key of a derived copy of tensor `t` (bf16 cast, padded / transposed weight ...): storage address, autograd
+    version counter AND the process-wide 'parameters written by a kernel' epoch -- raw-pointer writes of the optimizer /
+    EMA kernels do not touch `_version` on their own, and a CUDA-graph replay of a training step runs no Python at all."""
+    return (t.data_ptr(), t._version, _param_epoch)
+
+
+def note_params_written(tensors=None):
+    """Called after every launch that writes parameters through raw pointers: bumps the tensors' version counters (so
+    autograd's saved-tensor checks and the caches keyed on `_version` see the write) and the global epoch."""
+    global _param_epoch
+    _param_epoch += 1
+    if tensors:
+        torch._C._increment_version(list(tensors))
+
+
 def _dt(t):
     if t.dtype == torch.bfloat16:
         return DTYPE_BF16
@@ -359,6 +379,12 @@ def set_input_norm(mean=None, std=None):
     mean, std = [float(m) * 255 for m in mean], [float(s) * 255 for s in std]
     if len(mean) != len(std) or not 1 <= len(mean) <= 8 or any(s == 0 for s in std):
         raise B200Error("set_input_norm: mean / std need 1..8 channels and non-zero std")
+    if _input_norm is not None and (list(_input_norm[0]) != [ctypes.c_float(m).value for m in mean]
+                                    or list(_input_norm[1]) != [ctypes.c_float(s).value for s in std]):
+        # the setting is process-wide (the patch gather of EVERY uint8 batch uses it): a second loader with other
+        # statistics would silently re-normalise the first one's batches
+        raise B200Error("set_input_norm: a different uint8 normalisation is already active in this process; call "
+                        "set_input_norm(None) first (one mean / std per process)")
     # the loader builds these as fp32 tensors: round to fp32 the same way
     _input_norm = ((ctypes.c_float * len(mean))(*mean), (ctypes.c_float * len(std))(*std))
 

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import B200Error, DTYPE_BF16, DTYPE_F32, OptimTensor
-from .ops import _count, _stream
+from .ops import _count, _stream, note_params_written
 
 __all__ = ["SGD", "AdamW", "Adam", "clip_grad_norm_", "register_with_timm"]
 
@@ -82,9 +82,12 @@ class _B200Optimizer(torch.optim.Optimizer):
         self._grad_scale = coef
 
     def _take_scale(self):
+        """The pending clip coefficient as a TENSOR (or None): step() keeps it in a local until every group is launched,
+        so the caching allocator cannot hand its memory to an allocation made inside step() (momentum / exp_avg buffers
+        of a first step, fp32 state casts after load_state_dict) before the kernels have read it."""
         c = getattr(self, "_grad_scale", None)
         self._grad_scale = None
-        return None if c is None else c.data_ptr()
+        return c
 
 
 class SGD(_B200Optimizer):
@@ -106,7 +109,9 @@ class SGD(_B200Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        lib, scale = _lib.load(), self._take_scale()
+        lib, scale_t = _lib.load(), self._take_scale()
+        scale = None if scale_t is None else scale_t.data_ptr()
+        written = []
         for group in self.param_groups:
             mom = group["momentum"]
             fresh, seen = [], []
@@ -130,6 +135,9 @@ class SGD(_B200Optimizer):
                                            group["weight_decay"], int(group["nesterov"]), first, scale, st)
                     _lib.check(rc, "b200_sgd_step")
                     _count()
+                    written.extend(r[0] for r in rs)
+        del scale_t            # alive until here: every launch that reads it is enqueued
+        note_params_written(written)
         return loss
 
 
@@ -153,7 +161,9 @@ class AdamW(_B200Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        lib, scale = _lib.load(), self._take_scale()
+        lib, scale_t = _lib.load(), self._take_scale()
+        scale = None if scale_t is None else scale_t.data_ptr()
+        written = []
         for group in self.param_groups:
             by_step = {}
             for p in group["params"]:
@@ -175,6 +185,9 @@ class AdamW(_B200Optimizer):
                                         group["weight_decay"], step, int(self._decoupled), scale, st)
                 _lib.check(rc, "b200_adam_step")
                 _count()
+                written.extend(r[0] for r in rs)
+        del scale_t            # alive until here: every launch that reads it is enqueued
+        note_params_written(written)
         return loss
 
 

@@ -63,43 +63,43 @@ def _dispatch(name, fast_fn):
     return forward
 
 
-def _kv_len(attn_mask, n):
+def _kv_len(attn_mask, n, batch=None):
     if attn_mask is None:
         return None
     from .layers import BF_mask_to_kv_len
-    return BF_mask_to_kv_len(attn_mask, n)
+    return BF_mask_to_kv_len(attn_mask, n, batch)
 
 
 def _block(self, x, attn_mask=None, is_causal=False):
     if is_causal:
         raise B200Error("causal attention is not covered")
-    return BF.block_forward(self, x, _kv_len(attn_mask, x.shape[1]))
+    return BF.block_forward(self, x, _kv_len(attn_mask, x.shape[1], x.shape[0]))
 
 
 def _attention(self, x, attn_mask=None, is_causal=False):
     if is_causal:
         raise B200Error("causal attention is not covered")
-    return BF.attention_forward(self, x, _kv_len(attn_mask, x.shape[1]))
+    return BF.attention_forward(self, x, _kv_len(attn_mask, x.shape[1], x.shape[0]))
 
 
 def _attention_rope(self, x, rope=None, attn_mask=None, is_causal=False):
     if is_causal:
         raise B200Error("causal attention is not covered")
-    return BF.attention_rope_forward(self, x, rope, _kv_len(attn_mask, x.shape[1]))
+    return BF.attention_rope_forward(self, x, rope, _kv_len(attn_mask, x.shape[1], x.shape[0]))
 
 
 def _vit_features(self, x, attn_mask=None, is_causal=False):
     if is_causal or self.grad_checkpointing:
         raise B200Error("causal / checkpointed forward_features is not covered")
     n = self.patch_embed.num_patches + self.num_prefix_tokens
-    return BF.vit_forward_features(self, x, _kv_len(attn_mask, n))
+    return BF.vit_forward_features(self, x, _kv_len(attn_mask, n, x.shape[0]))
 
 
 def _vit_forward(self, x, attn_mask=None, is_causal=False):
     if is_causal or self.grad_checkpointing:
         raise B200Error("causal / checkpointed forward is not covered")
     n = self.patch_embed.num_patches + self.num_prefix_tokens
-    return BF.vit_forward(self, x, _kv_len(attn_mask, n))
+    return BF.vit_forward(self, x, _kv_len(attn_mask, n, x.shape[0]))
 
 
 def _convnext_forward(self, x):

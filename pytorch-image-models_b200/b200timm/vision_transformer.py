@@ -49,7 +49,7 @@ class Block(nn.Module):
             raise B200Error("causal attention is not supported")
         if attn_mask is not None and kv_len is None:
             from .layers import BF_mask_to_kv_len
-            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1])
+            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1], x.shape[0])
         return BF.block_forward(self, x, kv_len)
 
 
@@ -177,7 +177,7 @@ class VisionTransformer(nn.Module):
             raise B200Error("causal attention is not supported")
         if attn_mask is not None and kv_len is None:
             from .layers import BF_mask_to_kv_len
-            kv_len = BF_mask_to_kv_len(attn_mask, self.patch_embed.num_patches + self.num_prefix_tokens)
+            kv_len = BF_mask_to_kv_len(attn_mask, self.patch_embed.num_patches + self.num_prefix_tokens, x.shape[0])
         return BF.vit_forward_features(self, x, kv_len)
 
     def forward_head(self, x, pre_logits: bool = False):
@@ -188,7 +188,7 @@ class VisionTransformer(nn.Module):
             raise B200Error("causal attention is not supported")
         if attn_mask is not None and kv_len is None:
             from .layers import BF_mask_to_kv_len
-            kv_len = BF_mask_to_kv_len(attn_mask, self.patch_embed.num_patches + self.num_prefix_tokens)
+            kv_len = BF_mask_to_kv_len(attn_mask, self.patch_embed.num_patches + self.num_prefix_tokens, x.shape[0])
         return BF.vit_forward(self, x, kv_len)
 
 

@@ -35,8 +35,8 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
 template <bool XF32, bool TF32>
 __global__ void __launch_bounds__(kLossThreads) ce_fwd_kernel(const void* __restrict__ logits, const long long* __restrict__ target,
                                                               const void* __restrict__ soft, float smoothing,
-                                                              float* __restrict__ loss_rows, float* __restrict__ lse_out,
-                                                              float* __restrict__ tsum_out, int C) {
+                                                              long long ignore_index, float* __restrict__ loss_rows,
+                                                              float* __restrict__ lse_out, float* __restrict__ tsum_out, int C) {
   __shared__ float scratch[kLossThreads / 32];
   const long long row = blockIdx.x;
   const long long base = row * C;
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(kLossThreads) ce_fwd_kernel(const void* __rest
     sx = block_reduce(sx, false, scratch);
     const long long t = target[row];
     st = 1.f;
-    if (t < 0 || t >= C) {
-      loss = 0.f;                                // out-of-range class index: the row contributes nothing
+    if (t == ignore_index || t < 0 || t >= C) {
+      loss = 0.f;                                // ignore_index (or an out-of-range class index): the row contributes nothing
       st = 0.f;
     } else {
       const float xt = ldx<XF32>(logits, base + t);
@@ -80,24 +80,35 @@ __global__ void __launch_bounds__(kLossThreads) ce_fwd_kernel(const void* __rest
   }
 }
 
-__global__ void __launch_bounds__(kLossThreads) ce_mean_kernel(const float* __restrict__ loss_rows, float* __restrict__ out, int B) {
+// out[0] = mean loss, out[1] = the denominator of the mean: the number of non-ignored rows for class-index targets
+// (torch's 'mean' reduction of nll_loss divides by the count of rows whose target != ignore_index; all rows ignored ->
+// 0 / 0 = NaN, as in torch), B for soft targets.
+__global__ void __launch_bounds__(kLossThreads) ce_mean_kernel(const float* __restrict__ loss_rows, const float* __restrict__ tsum,
+                                                               int hard, float* __restrict__ out, int B) {
   __shared__ float scratch[kLossThreads / 32];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < B; i += kLossThreads) s += loss_rows[i];
+  float s = 0.f, n = 0.f;
+  for (int i = threadIdx.x; i < B; i += kLossThreads) {
+    s += loss_rows[i];
+    n += tsum[i];
+  }
   s = block_reduce(s, false, scratch);
-  if (threadIdx.x == 0) *out = s / static_cast<float>(B);
+  n = hard ? block_reduce(n, false, scratch) : static_cast<float>(B);
+  if (threadIdx.x == 0) {
+    out[0] = s / n;
+    out[1] = n;
+  }
 }
 
-// d logits[b, c] = (softmax * sum(t) - target distribution) * grad_out / B
+// d logits[b, c] = (softmax * sum(t) - target distribution) * grad_out / denom
 template <bool XF32, bool TF32>
 __global__ void __launch_bounds__(kLossThreads) ce_bwd_kernel(const void* __restrict__ logits, const long long* __restrict__ target,
                                                               const void* __restrict__ soft, float smoothing,
                                                               const float* __restrict__ lse, const float* __restrict__ tsum,
-                                                              const float* __restrict__ grad_out, void* __restrict__ dlogits,
-                                                              int B, int C) {
+                                                              const float* __restrict__ grad_out, const float* __restrict__ denom,
+                                                              void* __restrict__ dlogits, int B, int C) {
   const long long row = blockIdx.x;
   const long long base = row * C;
-  const float g = __ldg(grad_out) / static_cast<float>(B);
+  const float g = __ldg(grad_out) / __ldg(denom);
   const float l = lse[row], ts = tsum[row];
   const long long t = soft != nullptr ? -1 : target[row];
   const float uni = smoothing / static_cast<float>(C);
@@ -128,37 +139,39 @@ static int check_ce(const char* what, const void* logits, int dtype, const int64
 using namespace b200;
 
 extern "C" int b200_cross_entropy_fwd(const void* logits, int32_t logits_dtype, const int64_t* target, const void* soft_target,
-                                      int32_t soft_dtype, double smoothing, float* loss_rows, float* lse, float* tsum,
-                                      float* loss_mean, int32_t B, int32_t C, void* stream_) {
+                                      int32_t soft_dtype, double smoothing, int64_t ignore_index, float* loss_rows, float* lse,
+                                      float* tsum, float* loss_mean, int32_t B, int32_t C, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_ce("b200_cross_entropy_fwd", logits, logits_dtype, target, soft_target, soft_dtype, smoothing, B, C)) return rc;
   B200_CHECK_ARG(loss_rows && lse && tsum && loss_mean, "b200_cross_entropy_fwd: null output");
   const float s = static_cast<float>(smoothing);
+  const long long ig = static_cast<long long>(ignore_index);
   const long long* tg = reinterpret_cast<const long long*>(target);
   const bool xf = logits_dtype == B200_DTYPE_F32, tf = soft_dtype == B200_DTYPE_F32;
-  if (xf && tf) ce_fwd_kernel<true, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, loss_rows, lse, tsum, C);
-  else if (xf) ce_fwd_kernel<true, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, loss_rows, lse, tsum, C);
-  else if (tf) ce_fwd_kernel<false, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, loss_rows, lse, tsum, C);
-  else ce_fwd_kernel<false, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, loss_rows, lse, tsum, C);
+  if (xf && tf) ce_fwd_kernel<true, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, ig, loss_rows, lse, tsum, C);
+  else if (xf) ce_fwd_kernel<true, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, ig, loss_rows, lse, tsum, C);
+  else if (tf) ce_fwd_kernel<false, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, ig, loss_rows, lse, tsum, C);
+  else ce_fwd_kernel<false, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, ig, loss_rows, lse, tsum, C);
   B200_CUDA_OK(cudaGetLastError());
-  ce_mean_kernel<<<1, kLossThreads, 0, st>>>(loss_rows, loss_mean, B);
+  ce_mean_kernel<<<1, kLossThreads, 0, st>>>(loss_rows, tsum, target != nullptr ? 1 : 0, loss_mean, B);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
 
 extern "C" int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* target, const void* soft_target,
                                       int32_t soft_dtype, double smoothing, const float* lse, const float* tsum,
-                                      const float* grad_out, void* dlogits, int32_t B, int32_t C, void* stream_) {
+                                      const float* grad_out, const float* denom, void* dlogits, int32_t B, int32_t C,
+                                      void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (int rc = check_ce("b200_cross_entropy_bwd", logits, logits_dtype, target, soft_target, soft_dtype, smoothing, B, C)) return rc;
-  B200_CHECK_ARG(lse && tsum && grad_out && dlogits, "b200_cross_entropy_bwd: null pointer");
+  B200_CHECK_ARG(lse && tsum && grad_out && denom && dlogits, "b200_cross_entropy_bwd: null pointer");
   const float s = static_cast<float>(smoothing);
   const long long* tg = reinterpret_cast<const long long*>(target);
   const bool xf = logits_dtype == B200_DTYPE_F32, tf = soft_dtype == B200_DTYPE_F32;
-  if (xf && tf) ce_bwd_kernel<true, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, dlogits, B, C);
-  else if (xf) ce_bwd_kernel<true, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, dlogits, B, C);
-  else if (tf) ce_bwd_kernel<false, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, dlogits, B, C);
-  else ce_bwd_kernel<false, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, dlogits, B, C);
+  if (xf && tf) ce_bwd_kernel<true, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, denom, dlogits, B, C);
+  else if (xf) ce_bwd_kernel<true, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, denom, dlogits, B, C);
+  else if (tf) ce_bwd_kernel<false, true><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, denom, dlogits, B, C);
+  else ce_bwd_kernel<false, false><<<B, kLossThreads, 0, st>>>(logits, tg, soft_target, s, lse, tsum, grad_out, denom, dlogits, B, C);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
