@@ -11,6 +11,11 @@ Dispatch rule per call: CUDA tensor + bf16 activations and weights + a module co
 model families) keeps timm's original forward, which *is* the reference path for those cases.  If
 libb200timm.so cannot be loaded, install() raises -- it never silently leaves the PyTorch path in place.
 Set B200TIMM_STRICT=1 to raise instead of deferring to timm whenever a CUDA bf16 call is not covered.
+
+B200TIMM_FP32=bf16 (opt-in, the analogue of torch.backends.cuda.matmul.allow_tf32): fp32 CUDA calls are computed by the
+bf16 kernels as well -- the activations are cast to bf16 at the rebound forward, fp32 parameters are read the way
+torch.autocast(bfloat16) reads them (functional._w), the result is cast back.  This is how timm's own test-suite
+(tests/test_models.py builds fp32 models) runs on the kernels through its TORCH_BACKEND hook.
 """
 import os
 
@@ -22,6 +27,49 @@ from ._lib import B200Error
 
 _ORIG = {}
 _STRICT = os.environ.get("B200TIMM_STRICT", "0") == "1"
+_FP32_AS_BF16 = os.environ.get("B200TIMM_FP32", "") == "bf16"
+
+# Dispatch accounting: how many calls of each rebound forward ran on the kernels ("fast"), kept timm's forward because the
+# input is not the plugin's business (CPU / fp32 / scripting: "passthrough") or were DEFERRED to timm although the input was
+# CUDA bf16, because the kernels do not cover the module's configuration.  A deferral is reported once per (forward, reason)
+# through `warnings` -- a benchmark that silently ran cuBLAS / SDPA would not be the kernels' number -- and raises under
+# B200TIMM_STRICT=1.  stats() returns the table; B200TIMM_REPORT=<path> writes it as JSON at interpreter exit.
+_STATS = {"fast": {}, "passthrough": {}, "deferred": {}}
+_WARNED = set()
+
+
+def _note_deferral(name, err):
+    reason = str(err)
+    d = _STATS["deferred"].setdefault(name, {})
+    d[reason] = d.get(reason, 0) + 1
+    if (name, reason) not in _WARNED:
+        _WARNED.add((name, reason))
+        import warnings
+        warnings.warn(f"b200timm: {name} deferred to timm's PyTorch forward ({reason}); set B200TIMM_STRICT=1 to raise instead",
+                      RuntimeWarning, stacklevel=3)
+
+
+def stats():
+    """{'fast': {forward: calls}, 'passthrough': {...}, 'deferred': {forward: {reason: calls}}, 'kernel_launches': n}"""
+    from . import ops
+    return {"fast": dict(_STATS["fast"]), "passthrough": dict(_STATS["passthrough"]),
+            "deferred": {k: dict(v) for k, v in _STATS["deferred"].items()}, "kernel_launches": ops.launch_count()}
+
+
+def reset_stats():
+    for v in _STATS.values():
+        v.clear()
+
+
+def _write_report():
+    path = os.environ.get("B200TIMM_REPORT")
+    if path:
+        import json
+        try:
+            with open(path, "w") as f:
+                json.dump(stats(), f)
+        except OSError:
+            pass
 
 
 def _autocast_bf16():
@@ -45,16 +93,44 @@ def _fast(x):
 _GRAD_UNSUPPORTED = False  # the training path (b200timm.autograd) covers grad-enabled calls; uncovered configs raise B200Error -> timm
 
 
+def _cast_tree(out, dtype):
+    if isinstance(out, torch.Tensor):
+        return out.to(dtype) if out.is_floating_point() else out
+    if isinstance(out, (tuple, list)):
+        return type(out)(_cast_tree(o, dtype) for o in out)
+    return out
+
+
+def _fp32_as_bf16(x):
+    return (_FP32_AS_BF16 and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32
+            and not torch.is_autocast_enabled() and not (torch.jit.is_scripting() or torch.jit.is_tracing()))
+
+
 def _dispatch(name, fast_fn):
     orig = _ORIG[name]
 
     def forward(self, x, *args, **kwargs):
-        if _fast(x):
+        if _fp32_as_bf16(x):
             try:
-                return fast_fn(self, x, *args, **kwargs)
-            except B200Error:
+                out = _cast_tree(fast_fn(self, x.to(torch.bfloat16), *args, **kwargs), torch.float32)
+                _STATS["fast"][name] = _STATS["fast"].get(name, 0) + 1
+                return out
+            except B200Error as e:
                 if _STRICT:
                     raise
+                _note_deferral(name, e)
+                return orig(self, x, *args, **kwargs)
+        if _fast(x):
+            try:
+                out = fast_fn(self, x, *args, **kwargs)
+                _STATS["fast"][name] = _STATS["fast"].get(name, 0) + 1
+                return out
+            except B200Error as e:
+                if _STRICT:
+                    raise
+                _note_deferral(name, e)
+        else:
+            _STATS["passthrough"][name] = _STATS["passthrough"].get(name, 0) + 1
         return orig(self, x, *args, **kwargs)
 
     forward.__name__ = "forward"
@@ -89,15 +165,15 @@ def _attention_rope(self, x, rope=None, attn_mask=None, is_causal=False):
 
 
 def _vit_features(self, x, attn_mask=None, is_causal=False):
-    if is_causal or self.grad_checkpointing:
-        raise B200Error("causal / checkpointed forward_features is not covered")
+    if is_causal:
+        raise B200Error("causal forward_features is not covered")
     n = self.patch_embed.num_patches + self.num_prefix_tokens
     return BF.vit_forward_features(self, x, _kv_len(attn_mask, n, x.shape[0]))
 
 
 def _vit_forward(self, x, attn_mask=None, is_causal=False):
-    if is_causal or self.grad_checkpointing:
-        raise B200Error("causal / checkpointed forward is not covered")
+    if is_causal:
+        raise B200Error("causal forward is not covered")
     n = self.patch_embed.num_patches + self.num_prefix_tokens
     return BF.vit_forward(self, x, _kv_len(attn_mask, n, x.shape[0]))
 
@@ -140,6 +216,10 @@ def install():
         setattr(cls, attr, _dispatch(name, fn))
         _ORIG[name + "#cls"] = (cls, attr)
     _install_training_tail()
+    if os.environ.get("B200TIMM_REPORT") and not getattr(install, "_atexit", False):
+        import atexit
+        atexit.register(_write_report)
+        install._atexit = True
 
 
 def _ema_dispatch(orig, buffers):
@@ -149,9 +229,10 @@ def _ema_dispatch(orig, buffers):
             try:
                 from .ema import fast_update
                 return fast_update(self, model, decay, buffers=buffers)     # validates every tensor before launching
-            except B200Error:
+            except B200Error as e:
                 if _STRICT:
                     raise
+                _note_deferral("timm.utils.ModelEmaV3.apply_update_", e)
         return orig(self, model, decay)
     apply._b200_original = orig
     return apply
@@ -221,14 +302,19 @@ def convert_to_b200(model):
             if type(mod) is cls:
                 orig = _ORIG.get(name, getattr(cls, attr))
 
-                def make(orig=orig, fn=fn):
+                def make(orig=orig, fn=fn, name=name):
                     def forward(self, x, *args, **kwargs):
                         if _fast(x):
                             try:
-                                return fn(self, x, *args, **kwargs)
-                            except B200Error:
+                                out = fn(self, x, *args, **kwargs)
+                                _STATS["fast"][name] = _STATS["fast"].get(name, 0) + 1
+                                return out
+                            except B200Error as e:
                                 if _STRICT:
                                     raise
+                                _note_deferral(name, e)
+                        else:
+                            _STATS["passthrough"][name] = _STATS["passthrough"].get(name, 0) + 1
                         return orig(self, x, *args, **kwargs)
                     forward._b200_original = orig
                     return forward

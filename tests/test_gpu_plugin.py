@@ -1,0 +1,156 @@
+"""The drop-in boundary on hardware: the UNMODIFIED reference (timm installed into oracle/_ref by oracle/install_ref.py)
+with b200timm.plugin installed, on a B200.
+
+  * timm.create_model(...) + plugin: logits and every parameter gradient against the SAME timm model evaluated in fp32 on
+    the CPU (timm's own eager path), for BASELINE.json's three architectures -- with the plugin's dispatch accounting
+    asserting that the kernels ran (kernel launches > 0) and that nothing was deferred to PyTorch;
+  * timm's own tests (tests/test_models.py) through its TORCH_BACKEND hook (test_models.py:36-39), B200TIMM_FP32=bf16 so
+    that the fp32 models those tests build run on the kernels, B200TIMM_STRICT=1 so that an uncovered call fails the test;
+  * the unmodified benchmark.py through `python -m b200timm.run`.
+
+Tolerances (bf16 kernels vs fp32 reference on bf16-rounded weights): logits 2e-2 + 2e-2 |ref| for the
+12-block models, 3e-2 + 3e-2 |ref| for the 24-block ViT-L (bf16 rounding of the residual stream accumulates with depth;
+measured max error 0.024 at |ref| 1.35), cosine >= 0.999; parameter gradients relative L2 error <= 6e-2 for every tensor that carries more than 1e-3 of the largest
+gradient norm.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import install_ref  # noqa: E402
+
+if not install_ref.add_to_path():
+    pytest.skip("oracle/_ref (the installed reference) is missing: run python oracle/install_ref.py", allow_module_level=True)
+import timm  # noqa: E402
+
+
+@pytest.fixture()
+def plugin():
+    from b200timm import plugin as P
+    P.install()
+    P.reset_stats()
+    yield P
+    P.uninstall()
+
+
+CASES = [("vit_base_patch16_224", 2, {}), ("convnext_base", 2, {}), ("vit_large_patch14_clip_336", 1, {}),
+         ("vit_base_patch16_224", 2, {"drop_path_rate": 0.0, "init_values": 1e-1, "class_token": False, "global_pool": "avg"})]
+
+
+@pytest.mark.parametrize("name,batch,kw", CASES, ids=[c[0] + ("+" + "+".join(c[2]) if c[2] else "") for c in CASES])
+def test_timm_model_with_plugin_matches_timm_fp32_cpu(plugin, name, batch, kw):
+    from b200timm import ops
+    torch.manual_seed(0)
+    model = timm.create_model(name, num_classes=100, **kw)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(p.bfloat16().float())           # both paths see the same (bf16-representable) weights
+    size = model.default_cfg["input_size"]
+    x = torch.randn(batch, *size).bfloat16().float()
+    proj = torch.randn(batch, 100)
+
+    model.train()                                    # drop rates are zero: train() only switches the autograd path on
+    ref = model(x)                                   # CPU fp32: the plugin passes CPU tensors to timm's own forward
+    (ref * proj).sum().backward()
+    ref_grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    assert not plugin.stats()["fast"], "a CPU call reached the kernels"
+
+    model = model.cuda().to(torch.bfloat16)
+    plugin.reset_stats()
+    ops.reset_counters()
+    out = model(x.cuda().bfloat16())
+    (out.float() * proj.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    st = plugin.stats()
+    assert st["kernel_launches"] > 0 and st["fast"], st
+    assert not st["deferred"], f"hot-path calls deferred to PyTorch: {st['deferred']}"
+
+    got = out.float().cpu()
+    t = 3e-2 if "large" in name else 2e-2
+    tol = t + t * ref.abs()
+    assert ((got - ref).abs() <= tol).all(), f"logits: max err {(got - ref).abs().max():.4g} (|ref| max {ref.abs().max():.3g})"
+    assert torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0) > 0.999
+    scale = max(g.norm().item() for g in ref_grads.values())
+    worst = ("", 0.0)
+    for n, p in model.named_parameters():
+        assert p.grad is not None, f"no gradient for {n}"
+        r = ref_grads[n]
+        if r.norm().item() > 1e-3 * scale:
+            e = (p.grad.float().cpu() - r).norm().item() / r.norm().item()
+            if e > worst[1]:
+                worst = (n, e)
+    assert worst[1] <= 6e-2, f"gradient of {worst[0]}: relative error {worst[1]:.3g}"
+
+
+def test_inference_through_plugin_matches_eval_reference(plugin):
+    """no_grad / eval: the fused inference path (residuals in the GEMM epilogues), vit_base + convnext_base."""
+    for name in ("vit_base_patch16_224", "convnext_base"):
+        torch.manual_seed(1)
+        model = timm.create_model(name, num_classes=64).eval()
+        with torch.no_grad():
+            for p in model.parameters():
+                p.copy_(p.bfloat16().float())
+            x = torch.randn(4, 3, 224, 224).bfloat16().float()
+            ref = model(x)
+            plugin.reset_stats()
+            got = model.cuda().to(torch.bfloat16)(x.cuda().bfloat16()).float().cpu()
+        st = plugin.stats()
+        assert st["kernel_launches"] > 0 and not st["deferred"], st
+        assert ((got - ref).abs() <= 2e-2 + 2e-2 * ref.abs()).all(), f"{name}: max err {(got - ref).abs().max():.4g}"
+
+
+def _run(cmd, env, timeout=1500):
+    r = subprocess.run(cmd, env=env, cwd="/tmp", stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, text=True)
+    return r.returncode, r.stdout
+
+
+def _env(report=None, **extra):
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([install_ref.TARGET, os.path.join(ROOT, "pytorch-image-models_b200")]),
+               B200TIMM_STRICT="1", **extra)
+    if report:
+        env["B200TIMM_REPORT"] = report
+    return env
+
+
+TIMM_TESTS = ["test_model_forward[1-vit_base_patch16_224]", "test_model_backward[2-vit_base_patch16_224]",
+              "test_model_forward_intermediates[1-vit_base_patch16_224]", "test_model_forward[1-convnext_base]",
+              "test_model_backward[2-convnext_base]", "test_model_forward[1-vit_large_patch14_clip_336]"]
+
+
+def test_timms_own_tests_through_the_torch_backend_hook(tmp_path):
+    """tests/test_models.py of the reference, unmodified, with TORCH_BACKEND=b200timm.plugin TORCH_DEVICE=cuda."""
+    report = str(tmp_path / "plugin.json")
+    tests = os.path.join(install_ref.TARGET, "tests", "test_models.py")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "--rootdir", os.path.join(install_ref.TARGET, "tests")]
+    cmd += [f"{tests}::{t}" for t in TIMM_TESTS]
+    rc, out = _run(cmd, _env(report, TORCH_BACKEND="b200timm.plugin", TORCH_DEVICE="cuda", B200TIMM_FP32="bf16"))
+    assert rc == 0, out[-3000:]
+    st = json.load(open(report))
+    assert st["kernel_launches"] > 1000 and not st["deferred"], st
+    for fwd in ("timm.models.vision_transformer.VisionTransformer.forward", "timm.models.convnext.ConvNeXt.forward"):
+        assert st["fast"].get(fwd, 0) >= 3, st["fast"]
+
+
+def test_unmodified_benchmark_py_through_the_launcher(tmp_path):
+    """`python -m b200timm.run benchmark.py ...` (SURVEY 8b seam 4): inference + train of a small ViT, strict mode."""
+    report, res = str(tmp_path / "plugin.json"), str(tmp_path / "res.json")
+    cmd = [sys.executable, "-m", "b200timm.run", os.path.join(install_ref.TARGET, "scripts", "benchmark.py"), "--model",
+           "vit_small_patch16_224", "--bench", "both", "-b", "32", "--precision", "bfloat16", "--num-warm-iter", "2",
+           "--num-bench-iter", "5", "--no-retry", "--results-file", res, "--results-format", "json"]
+    rc, out = _run(cmd, _env(report))
+    assert rc == 0, out[-3000:]
+    r = json.load(open(res))
+    r = r[0] if isinstance(r, list) else r
+    assert r["infer_samples_per_sec"] > 0 and r["train_samples_per_sec"] > 0
+    st = json.load(open(report))
+    assert st["kernel_launches"] > 500 and not st["deferred"], st
+    assert st["fast"].get("timm.models.vision_transformer.VisionTransformer.forward", 0) >= 14, st["fast"]

@@ -1,15 +1,20 @@
-"""The timm plugin (class-level forward rebinding, SURVEY.md 8b seam 3).  Needs the reference checkout to be
-importable, which is only the case in the authoring container -- skipped on the GPU box."""
+"""The timm plugin (class-level forward rebinding, SURVEY.md 8b seam 3) on the CPU: rebinding / restoring, and that CPU
+and fp32 calls keep the reference's own forward.  timm comes from oracle/_ref (the unmodified reference installed by
+oracle/install_ref.py, which also ships to the GPU box; tests/test_gpu_plugin.py is the on-hardware half)."""
 import os
+import subprocess
 import sys
 
 import pytest
 import torch
 
-REF = os.environ.get("TIMM_REFERENCE", "/root/reference")
-if os.path.isdir(REF) and REF not in sys.path:
-    sys.path.insert(0, REF)
-timm = pytest.importorskip("timm")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import install_ref  # noqa: E402
+
+if install_ref.install(quiet=True) is None or not install_ref.add_to_path():
+    pytest.skip("neither oracle/_ref nor /root/reference is available", allow_module_level=True)
+import timm  # noqa: E402
 
 
 @pytest.fixture()
@@ -169,3 +174,47 @@ def test_variant_modules_are_rebound_and_cpu_calls_stay_on_timm(plugin):
         for (m, x), y in zip(mods, outs):
             assert torch.equal(m(x), y), type(m).__name__
     plugin.install()
+
+
+def test_benchmark_py_cpu_plumbing_through_the_launcher(tmp_path):
+    """BASELINE.json configs[0]: `benchmark.py --model vit_tiny_patch16_224 --bench inference -b 1 --device cpu --precision
+    float32` (unmodified script) under `python -m b200timm.run`: the plugin is installed and every call passes through
+    to timm's forward (no kernel launch, no deferral)."""
+    import json
+    report, res = str(tmp_path / "plugin.json"), str(tmp_path / "res.json")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([install_ref.TARGET, os.path.join(ROOT, "pytorch-image-models_b200")]),
+               B200TIMM_REPORT=report, B200TIMM_STRICT="1", OMP_NUM_THREADS="4")
+    cmd = [sys.executable, "-m", "b200timm.run", os.path.join(install_ref.TARGET, "scripts", "benchmark.py"), "--model",
+           "vit_tiny_patch16_224", "--bench", "inference", "-b", "1", "--device", "cpu", "--precision", "float32",
+           "--num-warm-iter", "1", "--num-bench-iter", "5", "--results-file", res, "--results-format", "json"]
+    r = subprocess.run(cmd, env=env, cwd="/tmp", stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    out = json.load(open(res))
+    out = out[0] if isinstance(out, list) else out
+    assert out["infer_samples_per_sec"] > 0
+    st = json.load(open(report))
+    assert st["kernel_launches"] == 0 and not st["fast"] and not st["deferred"]
+    assert st["passthrough"].get("timm.models.vision_transformer.VisionTransformer.forward", 0) >= 6
+
+
+def test_deferrals_are_counted_and_warned_once(plugin, monkeypatch):
+    """A covered-dtype call the kernels reject is deferred to timm WITH a warning and shows up in stats(); strict mode
+    raises.  (Driven on the CPU by faking the `_fast` gate: the fast function then fails on the CPU tensor.)"""
+    import warnings
+    from b200timm._lib import B200Error
+    monkeypatch.setattr(plugin, "_fast", lambda x: True)
+    plugin.reset_stats()
+    m = timm.layers.Mlp(8, 16).eval()
+    x = torch.randn(2, 3, 8)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        with torch.no_grad():
+            y1 = m(x)
+            y2 = m(x)
+    assert torch.equal(y1, y2)
+    d = plugin.stats()["deferred"]
+    assert sum(d["timm.layers.Mlp.forward"].values()) == 2
+    assert len([x for x in w if "deferred to timm" in str(x.message)]) == 1
+    monkeypatch.setattr(plugin, "_STRICT", True)
+    with pytest.raises(B200Error), torch.no_grad():
+        m(x)
