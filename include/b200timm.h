@@ -89,6 +89,10 @@ typedef struct b200_gemm_desc {
   int32_t act;      /* activation applied by EPI_BIAS_GELU / differentiated by EPI_DGELU: 0 = exact (erf) GELU (nn.GELU()),
                        1 = tanh GELU (timm 'gelu_tanh': GELUTanh / nn.GELU(approximate='tanh'), activations.py), 2 = SiLU.
                        (this field was `reserved0` = 0 before ABI 5)                                                  */
+  float* colsum;    /* ABI >= 6, EPI_DGELU only (bf16 output, M >= 256, N > 128), or NULL: fp32 [N] to which the column sums of
+                       `out` are ADDED (red.global.add from the epilogue's staging tile) -- the bias gradient of the Linear
+                       whose output gradient this GEMM produces (db1 = sum_rows dY1; the reference gets it from autograd of
+                       F.linear, timm/layers/mlp.py:48).  The caller zero-initialises it.                             */
 } b200_gemm_desc;
 
 B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);
@@ -147,10 +151,12 @@ B200_API int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32_t
 B200_API int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H);
 
 /* Backward: dqkv bf16 [B,N,3,H,hd] from dout bf16 [B,N,H*hd]; recomputes P from qkv and lse.
- * delta: fp32 workspace [B,H,N].                                                                     */
+ * delta: fp32 workspace [B,H,N].  dbias (ABI >= 6): NULL, or a zero-initialised fp32 [3*H*hd] that receives the column sums
+ * of dqkv over all B*N rows -- the gradient of the qkv projection's bias (autograd of F.linear at
+ * timm/layers/attention.py:115), reduced from the tiles as they are stored; N <= 208 only (else B200_ERR_UNSUPPORTED). */
 B200_API int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                   void* dqkv, const int32_t* kv_len, int32_t B, int32_t N, int32_t H, int32_t hd,
-                  float scale, void* stream);
+                  float scale, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------ patch embed   timm/layers/patch_embed.py:136-138
  * Gathers non-overlapping p x p patches of an NCHW bf16 image into rows of a [B*gh*gw, Kpad] bf16 matrix

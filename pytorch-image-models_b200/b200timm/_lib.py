@@ -56,6 +56,7 @@ class GemmDesc(ctypes.Structure):
         ("rope_prefix", ctypes.c_int32),
         ("rope_cols", ctypes.c_int32),
         ("act", ctypes.c_int32),
+        ("colsum", ctypes.c_void_p),
     ]
 
 
@@ -86,7 +87,7 @@ SIGNATURES = {
     "b200_convert_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "b200_attn_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "b200_attn_bwd_ws_floats": (ctypes.c_int64, [_i32, _i32, _i32]),
-    "b200_attn_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
+    "b200_attn_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "b200_patchify": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_patchify_u8": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_float),
                                         ctypes.POINTER(ctypes.c_float), _vp]),

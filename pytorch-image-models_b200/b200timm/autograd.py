@@ -243,13 +243,15 @@ class BlockFn(torch.autograd.Function):
             if g2 is not None:
                 ops.colsum_mul(dx2, br2, rs2, N, out=v[13], accumulate=True)          # dgamma2
             dbr2 = ops.scale_rows_cols(dx2, g2, rs2, N)                               # gradient w.r.t. the branch output
-        dpre = ops.linear_dgrad(dbr2, w2, epilogue=ops.EPI_DGELU, aux=pre, act=ctx.act_kind)     # dY W2 * act'(pre)
+        # dY W2 * act'(pre); the bias gradient of fc1 (column sums of dpre) rides in this GEMM's epilogue
+        fused_db1 = b1 is not None and ops.dgrad_colsum_fused(B * N, w2.shape[1])
+        dpre = ops.linear_dgrad(dbr2, w2, epilogue=ops.EPI_DGELU, aux=pre, act=ctx.act_kind, colsum=v[9] if fused_db1 else None)
         ops.linear_wgrad(dbr2, act, out=v[10])
         if b2 is not None:
             ops.colsum(dbr2, out=v[11], accumulate=True)
         dh2 = ops.linear_dgrad(dpre, w1)
         ops.linear_wgrad(dpre, h2, out=v[8])
-        if b1 is not None:
+        if b1 is not None and not fused_db1:
             ops.colsum(dpre, out=v[9], accumulate=True)
         dx1, _, _ = ops.layernorm_bwd(dh2, x1, n2w, mean2, rstd2, dres=dx2, dw_out=v[6], db_out=v[7])
         # ---- attention branch:  x1 = x0 + rs1 * g1 * (proj(SDPA(qkv(LN1(x0)))) + bp)
@@ -262,10 +264,12 @@ class BlockFn(torch.autograd.Function):
         ops.linear_wgrad(dbr1, o.view(B * N, -1), out=v[4])
         if bproj is not None:
             ops.colsum(dbr1, out=v[5], accumulate=True)
-        dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
+        fused_dbqkv = bqkv is not None and ops.attn_bwd_bias_fused(N)       # the qkv bias gradient rides in the attention backward
+        dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len,
+                                 dbias=v[3] if fused_dbqkv else None).view(B * N, -1)
         dh1 = ops.linear_dgrad(dqkv, wqkv)
         ops.linear_wgrad(dqkv, h1, out=v[2])
-        if bqkv is not None:
+        if bqkv is not None and not fused_dbqkv:
             ops.colsum(dqkv, out=v[3], accumulate=True)
         dx0, _, _ = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dw_out=v[0], db_out=v[1])
         # bf16 parameters (and the bf16 casts of fp32 master weights) take their gradient from one bf16 conversion of the

@@ -300,8 +300,6 @@ class ConvNeXtStage(nn.Module):
 
 def stage_forward_nhwc(self, x, B, H, W):
     """ConvNeXtStage.forward (convnext.py:300-309) on channels-last rows; duck-typed like block_forward_nhwc."""
-    if getattr(self, "grad_checkpointing", False):
-        raise B200Error("gradient checkpointing is not covered")
     if not isinstance(self.downsample, nn.Identity):
         norm, conv = self.downsample[0], self.downsample[1]
         p = conv.kernel_size[0]
@@ -320,8 +318,16 @@ def stage_forward_nhwc(self, x, B, H, W):
                 h = ops.patchify_nhwc(h.view(B, H, W, C), p)
                 H, W = H // p, W // p
             x = ops.linear_fwd(h, w2, conv.bias)
-    for blk in self.blocks:
-        x = block_forward_nhwc(blk, x, B, H, W)
+    if getattr(self, "grad_checkpointing", False) and torch.is_grad_enabled() and x.requires_grad:
+        # checkpoint_seq(self.blocks, x) (convnext.py:305-306, _manipulate.py:213-286): a block's activations are dropped
+        # after its forward and its kernels run again in the backward (non-reentrant checkpoint: the CUDA RNG state is
+        # restored first, so a DropPath draw repeats)
+        from torch.utils.checkpoint import checkpoint
+        for blk in self.blocks:
+            x = checkpoint(block_forward_nhwc, blk, x, B, H, W, use_reentrant=False)
+    else:
+        for blk in self.blocks:
+            x = block_forward_nhwc(blk, x, B, H, W)
     return x, H, W
 
 

@@ -204,7 +204,7 @@ ACTS = {"gelu": 0, "gelu_tanh": 1, "silu": 2}     # b200_gemm_desc.act: the acti
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None, gamma=None, out=None,
          out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None, row_scale=None, rows_per_scale=0, rope=None,
-         act=0):
+         act=0, colsum=None):
     """out[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
@@ -254,6 +254,10 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
     d.accumulate = int(accumulate)
     d.split_k = int(split_k)
     d.act = int(act)
+    if colsum is not None:     # fp32 [N], zero-initialised by the caller: += column sums of `out` (EPI_DGELU epilogue)
+        if colsum.dtype != torch.float32 or colsum.numel() != N or not colsum.is_contiguous() or not colsum.is_cuda:
+            raise B200Error("gemm: colsum must be a contiguous fp32 CUDA tensor [N]")
+        d.colsum = colsum.data_ptr()
     if _gemm_timing is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -294,11 +298,18 @@ def rope_qk(qkv, emb, B, N, H, num_prefix, half=False, inverse=False):
     return qkv
 
 
-def linear_dgrad(dy2d, weight, epilogue=EPI_BIAS, aux=None, act=0):
-    """dX[M,K] = dY[M,N] @ W[N,K]  (W consumed MN-major in place; optional act' epilogue with aux = pre-activation)."""
+def dgrad_colsum_fused(M, K):
+    """True when linear_dgrad(..., epilogue=EPI_DGELU, colsum=...) can fold the column sums of its output into the epilogue."""
+    return M >= 256 and K > 128
+
+
+def linear_dgrad(dy2d, weight, epilogue=EPI_BIAS, aux=None, act=0, colsum=None):
+    """dX[M,K] = dY[M,N] @ W[N,K]  (W consumed MN-major in place; optional act' epilogue with aux = pre-activation).
+    colsum (EPI_DGELU, dgrad_colsum_fused shapes): zeroed fp32 [K] that receives the column sums of dX -- the bias gradient
+    of the Linear that produced the pre-activation."""
     M, N = dy2d.shape
     K = weight.shape[1]
-    return gemm(dy2d, weight, M, K, N, b_mn=True, epilogue=epilogue, aux=aux, act=act)
+    return gemm(dy2d, weight, M, K, N, b_mn=True, epilogue=epilogue, aux=aux, act=act, colsum=colsum)
 
 
 def _wgrad_split(rows_out, cols_out, k):
@@ -347,8 +358,15 @@ def attention_fwd(qkv, B, N, H, hd, scale, kv_len=None, need_lse=False):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None):
-    """dqkv [B,N,3*H*hd] bf16 from dout [B,N,H*hd]; recomputes P from qkv and the saved log-sum-exp."""
+def attn_bwd_bias_fused(N):
+    """True when attention_bwd(..., dbias=...) can reduce the qkv bias gradient from its output tiles."""
+    import os
+    return N <= 208 and os.environ.get("B200_ATTN_BWD_V1", "0")[:1] != "1"
+
+
+def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None, dbias=None):
+    """dqkv [B,N,3*H*hd] bf16 from dout [B,N,H*hd]; recomputes P from qkv and the saved log-sum-exp.  dbias (attn_bwd_bias_fused
+    shapes): zeroed fp32 [3*H*hd] that receives the column sums of dqkv (the qkv projection's bias gradient)."""
     _need_cuda(qkv, out, dout, lse, kv_len)
     for t, n, name in ((qkv, B * N * 3 * H * hd, "qkv"), (out, B * N * H * hd, "out"), (dout, B * N * H * hd, "dout")):
         if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.numel() != n:
@@ -358,8 +376,10 @@ def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None):
     dqkv = torch.empty_like(qkv)
     lib = _lib.load()
     delta = torch.empty(lib.b200_attn_bwd_ws_floats(B, N, H), dtype=torch.float32, device=qkv.device)   # delta (+ fp32 dQ)
+    if dbias is not None and (dbias.dtype != torch.float32 or dbias.numel() != 3 * H * hd or not dbias.is_contiguous()):
+        raise B200Error("attention_bwd: dbias must be a contiguous fp32 [3*H*hd] tensor")
     rc = lib.b200_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-                                   dqkv.data_ptr(), _ptr(kv_len), B, N, H, hd, float(scale), _stream())
+                                   dqkv.data_ptr(), _ptr(kv_len), B, N, H, hd, float(scale), _ptr(dbias), _stream())
     _lib.check(rc, "b200_attn_bwd")
     _count(2)
     return dqkv

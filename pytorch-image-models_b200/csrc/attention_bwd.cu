@@ -368,7 +368,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
 namespace b200 {
 int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
-                     const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st);
+                     const int32_t* kv_len, int B, int N, int H, float scale, float* dbias, cudaStream_t st);
 }
 
 namespace b200 {
@@ -384,7 +384,7 @@ extern "C" int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H) {
 
 extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                              void* dqkv, const int32_t* kv_len, int32_t B, int32_t N, int32_t H, int32_t hd,
-                             float scale, void* stream_) {
+                             float scale, float* dbias, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "b200_attn_bwd: null pointer");
   B200_CHECK_ARG(B > 0 && N > 0 && H > 0 && B <= 65535, "b200_attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
@@ -396,6 +396,9 @@ extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout,
         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, N, H);
     B200_CUDA_OK(cudaGetLastError());
   }
+  static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_BWD_V1"); return e != nullptr && e[0] == '1'; }();
+  if (dbias != nullptr && (N > kNQ || use_v1))
+    return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: the fused qkv-bias gradient is available for N <= %d (v2 kernel) only", kNQ);
   if (N > kNQ) {
     // long sequences (attention_bwd_long.cu): the workspace continues behind delta with the fp32 dq buffer
     float* dq32 = delta + (static_cast<long long>(B) * H * N + 3) / 4 * 4;
@@ -403,8 +406,7 @@ extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout,
   }
   // v2 (attention_bwd2.cu: two query halves, 8 compute warps + issuer warp) is the default; B200_ATTN_BWD_V1=1 keeps
   // the simpler v1 kernel of this file selectable for A/B comparison and as a cross-check in the tests.
-  static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_BWD_V1"); return e != nullptr && e[0] == '1'; }();
-  if (!use_v1) return launch_attn_bwd2(qkv, dout, lse, delta, dqkv, kv_len, B, N, H, scale, st);
+  if (!use_v1) return launch_attn_bwd2(qkv, dout, lse, delta, dqkv, kv_len, B, N, H, scale, dbias, st);
   CUtensorMap tq, tdo;
   uint32_t box[2] = {kHd, kNQ};
   {

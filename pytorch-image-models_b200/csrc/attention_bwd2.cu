@@ -40,6 +40,7 @@ constexpr int kComputeThreads = 256;
 struct AttnBwd2Params {
   const float* lse;
   const float* delta;
+  float* dbias;          // optional fp32 [3 * H * 64]: += column sums of dqkv (the qkv bias gradient), from the staging tiles
   __nv_bfloat16* dqkv;
   const int* kv_len;
   int B, N, H;
@@ -49,8 +50,11 @@ struct AttnBwd2Params {
 // One warp's 32 accumulator rows x 64 columns: TMEM -> bf16 -> 128B-swizzled staging tile -> one TMA store into
 // dqkv[b, row0 .. row0+31 (clipped at N by the 3-D map), col0 .. col0+63].  (Per-lane 16-byte global stores of 32
 // different rows cost one LSU transaction each -- ~2000 cycles per 128 x 64 tile; the TMA store is one instruction.)
+// dbias != nullptr: the column sums of the staged bf16 tile (rows < nrows; rows past the sequence are exact zeros: P = 0
+// for padding queries / keys) are added to dbias[col0 ..] -- lane l owns columns 2l, 2l+1, reads them bank-conflict free
+// through the 128-byte swizzle, one vector reduction per lane and tile.
 __device__ __forceinline__ void store_tile64(uint8_t* stg, uint32_t taddr, const CUtensorMap* map, int col0, int row0, int b,
-                                             int lane, bool any_row) {
+                                             int lane, bool any_row, float* dbias = nullptr, int nrows = 32) {
   if (lane == 0) tma_store_wait_read<0>();
   __syncwarp();
   const uint32_t srow = smem_u32(stg) + lane * 128;
@@ -73,6 +77,21 @@ __device__ __forceinline__ void store_tile64(uint8_t* stg, uint32_t taddr, const
   }
   fence_proxy_async_smem();
   __syncwarp();
+  if (dbias != nullptr && any_row) {
+    const uint32_t base = smem_u32(stg) + static_cast<uint32_t>(lane & 3) * 4u;
+    const uint32_t chunk = static_cast<uint32_t>(lane >> 2);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      uint32_t w;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + r * 128u + ((chunk ^ static_cast<uint32_t>(r & 7)) << 4)));
+      if (r < nrows) {
+        s0 += bf16_lo(w);
+        s1 += bf16_hi(w);
+      }
+    }
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dbias + col0 + 2 * lane), "f"(s0), "f"(s1) : "memory");
+  }
   if (lane == 0 && any_row) {
     tma_store_3d(map, stg, col0, row0, b);
     tma_store_commit();
@@ -258,7 +277,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         // dV / dK of the previous key tile are complete (their MMAs were queued ahead of this step's S^T / dP^T)
         const int prow0 = (kt - 1) * 128 + wrow;
         store_tile64(ostg, tmem_row + (wg == 0 ? kColDV : kColDK), &tm_out32, ((wg == 0 ? 2 : 1) * H + h) * kHd, prow0, b,
-                     lane, prow0 < N);
+                     lane, prow0 < N, p.dbias);
       }
       const int c0 = wg * 56;                        // first query column (within the half) of this warpgroup
       const float* l2 = sLse + qh * kQH + c0;
@@ -304,13 +323,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     {
       const int prow0 = (num_kt - 1) * 128 + wrow;
       store_tile64(ostg, tmem_row + (wg == 0 ? kColDV : kColDK), &tm_out32, ((wg == 0 ? 2 : 1) * H + h) * kHd, prow0, b, lane,
-                   prow0 < N);
+                   prow0 < N, p.dbias);
     }
     {
       // warpgroup 0 -> query half 0, warpgroup 1 -> half 1; a half has 112 rows, so the last warp stores 16 rows only
       const int q0 = wg * kQH + wrow;
       store_tile64(ostg, tmem_row + (wg == 0 ? kColDQ0 : kColDQ1), wrow + 32 <= kQH ? &tm_out32 : &tm_out16, h * kHd, q0, b,
-                   lane, q0 < N);
+                   lane, q0 < N, p.dbias, wrow + 32 <= kQH ? 32 : 16);
     }
     tc_fence_before();
     mbar_arrive(bar_tail);            // accumulators read: the issuer may start the next item's dV / dK / dQ MMAs
@@ -341,7 +360,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 }
 
 int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
-                     const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st) {
+                     const int32_t* kv_len, int B, int N, int H, float scale, float* dbias, cudaStream_t st) {
   CUtensorMap tq, tdo;
   uint32_t box[2] = {kHd, kNQ};
   {
@@ -368,6 +387,7 @@ int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const 
   }
   AttnBwd2Params p;
   p.lse = lse; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.kv_len = kv_len;
+  p.dbias = dbias;
   p.B = B; p.N = N; p.H = H; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {

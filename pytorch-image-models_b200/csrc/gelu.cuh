@@ -54,6 +54,29 @@ __device__ __forceinline__ f32x2 dgelu_erf2(f32x2 x) {
   return fma2(mul2(x, splat(0.3989422804014327f)), e, cdf);
 }
 
+// GELU'(x) on the FMA pipe only (no MUFU): GELU'(x) - 1/2 is odd and saturates at +-1/2, so with z = clamp(x / R, -1, 1)
+// and t = 2 z^2 - 1:  GELU'(x) ~= 1/2 + z Q(t),  Q a degree-9 least-squares polynomial on R = 4.5 constrained to
+// z Q(t) = 1/2 at z = 1 (the clamp then continues it with the exact limits 0 / 1).  Max abs error 6.9e-5 over all x
+// (measured in fp32 Horner arithmetic; GELU'(4.5) - 1 = 6.9e-5 is the saturation step) -- a factor applied to a bf16
+// gradient (relative rounding 3.9e-3).  The fc2-dgrad epilogue was bound by the 16-lane MUFU (2 per element: rcp + ex2)
+// and by its FMA count; this is ~15 instructions per PAIR instead of ~26 + 4 MUFU.
+__device__ __forceinline__ f32x2 dgelu_poly2(f32x2 x) {
+  float x0, x1;
+  upk(mul2(x, splat(1.0f / 4.5f)), x0, x1);
+  const f32x2 z = pk(fminf(fmaxf(x0, -1.0f), 1.0f), fminf(fmaxf(x1, -1.0f), 1.0f));
+  const f32x2 t = fma2(mul2(z, z), splat(2.0f), splat(-1.0f));
+  f32x2 q = fma2(t, splat(-1.114164513e-01f), splat(2.526838988e-01f));
+  q = fma2(q, t, splat(-2.053749153e-01f));
+  q = fma2(q, t, splat(2.136556465e-01f));
+  q = fma2(q, t, splat(-3.936981523e-01f));
+  q = fma2(q, t, splat(4.730997042e-01f));
+  q = fma2(q, t, splat(-4.296489081e-01f));
+  q = fma2(q, t, splat(3.878010022e-01f));
+  q = fma2(q, t, splat(-4.046076170e-01f));
+  q = fma2(q, t, splat(7.175057925e-01f));
+  return fma2(z, q, splat(0.5f));
+}
+
 // GELU(x) and GELU'(x) together from one evaluation of Phi (7.1.26) and phi: GELU = x Phi, GELU' = Phi + x phi.
 __device__ __forceinline__ void gelu_and_dgelu2(f32x2 x, f32x2& g, f32x2& dg) {
   float x0, x1;

@@ -50,6 +50,8 @@ struct GemmKernelParams {
   const float* rope;           // EPI_BIAS_ROPE: [rope_tokens - rope_prefix][128] = [sin | cos]
   int rope_tokens, rope_prefix, rope_cols;
   int act;                     // activation of the GELU / DGELU epilogues in the generic kernels: 0 erf GELU, 1 tanh GELU, 2 SiLU
+  float* colsum;               // optional fp32 [N]: += column sums of the bf16 output (the bias gradient of the Linear whose
+                               // output gradient this GEMM produces), reduced from the staging tile, red.global.add
   unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_set_trace), nullptr in production
 };
 
@@ -434,7 +436,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                      v[j] = mul2(v[j], (EPI < 0 && ACTRT && p.act) ? act_bwd2(av[j], p.act) : dgelu_erf2(av[j]));
+                      v[j] = mul2(v[j], (EPI < 0 && ACTRT && p.act) ? act_bwd2(av[j], p.act) : dgelu_poly2(av[j]));
                   }
                 }
               }
@@ -513,6 +515,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         fence_proxy_async_smem();  // staging writes (generic proxy) -> visible to the TMA store (async proxy)
         __syncwarp();
+        if constexpr (RC == 64) {
+          // bias gradient of the Linear whose output gradient this tile is (db = column sums of dY, here of exactly the
+          // bf16 values being stored): lane l sums bf16 columns 2l, 2l+1 of the warp's 32 staged rows (128-byte rows,
+          // 16-byte chunks XOR-swizzled by row & 7: the 32 lanes of a row read hit 32 different banks) and adds the pair
+          // to colsum with one vector reduction.  Rows past M are zero (zero-filled operands), columns are checked.
+          if (p.colsum != nullptr && !out_f32) {
+            const uint32_t base = smem_u32(stg) + static_cast<uint32_t>(lane & 3) * 4u;
+            const uint32_t chunk = static_cast<uint32_t>(lane >> 2);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              uint32_t w;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base + r * 128u + ((chunk ^ static_cast<uint32_t>(r & 7)) << 4)));
+              s0 += bf16_lo(w);
+              s1 += bf16_hi(w);
+            }
+            const int col = col0 + 2 * lane;
+            if (col < p.N && row0 < p.M)
+              asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p.colsum + col), "f"(s0), "f"(s1) : "memory");
+          }
+        }
         if (lane == 0 && col0 < p.N && row0 < p.M) {
           if (reduce_out) tma_reduce_add_2d(&tmap_out, stg, col0, row0);
           else tma_store_2d(&tmap_out, stg, col0, row0);
@@ -602,6 +625,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.accumulate = d.accumulate;
   p.rope = d.rope; p.rope_tokens = d.rope_tokens; p.rope_prefix = d.rope_prefix; p.rope_cols = d.rope_cols;
   p.act = d.act;
+  p.colsum = d.colsum;
   p.trace = g_gemm_trace;
 
   auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI, ACTRT>;
@@ -691,6 +715,11 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
                        d.out_dtype == B200_DTYPE_BF16 && d.ldo2 % 8 == 0 && d.ldo2 >= d.N &&
                        (reinterpret_cast<uintptr_t>(d.out2) & 15) == 0,
                    "b200_gemm: out2 needs the GELU or residual epilogue, bf16 output and 16-byte aligned rows");
+  if (d.colsum != nullptr)
+    B200_CHECK_ARG(d.epilogue == B200_EPI_DGELU && d.out_dtype == B200_DTYPE_BF16 && d.M >= 256 && d.N > 128 && !d.a_mn &&
+                       (reinterpret_cast<uintptr_t>(d.colsum) & 7) == 0,
+                   "b200_gemm: colsum rides in the EPI_DGELU epilogue of the 64-column-round kernels only (bf16 output, "
+                   "M >= 256, N > 128, 8-byte aligned fp32 [N])");
   if (d.row_scale != nullptr)
     B200_CHECK_ARG(d.epilogue == B200_EPI_BIAS_RESIDUAL && d.rows_per_scale > 0,
                    "b200_gemm: row_scale needs the residual epilogue and rows_per_scale > 0");

@@ -8,6 +8,8 @@ import pytest
 
 from b200timm import _lib
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_header_and_binding_agree():
     hdr = _lib.header_symbols()
@@ -28,14 +30,25 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string_without_gpu():
     lib = _lib.load()
-    assert lib.b200_abi_version() == 5
+    assert lib.b200_abi_version() == 6
     assert isinstance(lib.b200_last_error(), bytes)
 
 
-def test_gemm_desc_layout_matches_header():
-    """struct b200_gemm_desc: 8 pointers, 5 int64, 12 int32."""
-    assert ctypes.sizeof(_lib.GemmDesc) == 8 * 8 + 5 * 8 + 12 * 4 + 8 + 4 * 4
-    assert _lib.GemmDesc.M.offset == 104 and _lib.GemmDesc.split_k.offset == 148 and _lib.GemmDesc.rope.offset == 152
+def test_gemm_desc_layout_matches_header(tmp_path):
+    """struct b200_gemm_desc as the C compiler lays it out from include/b200timm.h (gcc) == the ctypes mirror in _lib.py:
+    total size and the offset of every field."""
+    import subprocess
+    fields = [f[0] for f in _lib.GemmDesc._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200timm.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(b200_gemm_desc));\n'
+                   + "".join(f'  printf("%zu\\n", offsetof(b200_gemm_desc, {f}));\n' for f in fields) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    nums = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert ctypes.sizeof(_lib.GemmDesc) == nums[0]
+    assert [getattr(_lib.GemmDesc, f).offset for f in fields] == nums[1:]
+    assert fields[-1] == "colsum" and _lib.GemmDesc.M.offset == 104
 
 
 def test_argument_errors_are_reported_not_crashed():

@@ -354,3 +354,61 @@ def test_rmsnorm_fwd_bwd(cols, pdt):
     assert db is None
     _close(dx, xr.grad + dres.float(), atol=4e-2, rtol=2e-2, what="rmsnorm dx (+ residual gradient)")
     _close(dw, wr.grad, atol=0.25, rtol=2e-2, what="rmsnorm dweight")
+
+
+@pytest.mark.parametrize("M", [1576, 50432 // 8, 300])
+def test_dgrad_epilogue_colsum_is_the_bias_gradient(M):
+    """EPI_DGELU with `colsum`: the column sums of the bf16 output (the fc1 bias gradient) leave the GEMM epilogue; they
+    must equal b200_colsum of the stored output (same bf16 values, fp32 sums: order differs, hence rtol 1e-4) and the
+    output itself must not change.  Also pins the FMA-pipe GELU' polynomial (gelu.cuh dgelu_poly2, |err| <= 6.9e-5)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    N, K = 768, 3072                       # dY [M, 768] @ W2 [768, 3072] -> dpre [M, 3072]
+    dy = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    w2 = (torch.randn(N, K, device=DEV, generator=g) * 0.03).bfloat16()
+    pre = (torch.randn(M, K, device=DEV, generator=g) * 2.0).bfloat16()
+    plain = ops.linear_dgrad(dy, w2, epilogue=ops.EPI_DGELU, aux=pre)
+    assert ops.dgrad_colsum_fused(M, K)
+    db = torch.zeros(K, device=DEV, dtype=torch.float32)
+    fused = ops.linear_dgrad(dy, w2, epilogue=ops.EPI_DGELU, aux=pre, colsum=db)
+    assert torch.equal(plain, fused)
+    ref = ops.colsum(fused)
+    torch.testing.assert_close(db, ref, atol=2e-3, rtol=1e-4)
+    _close(fused, (dy.float() @ w2.float()) * _dgelu(pre.float()), 5e-2, 2e-2, "dgrad + GELU' (polynomial)")
+    # accumulate semantics: a second launch adds
+    ops.linear_dgrad(dy, w2, epilogue=ops.EPI_DGELU, aux=pre, colsum=db)
+    torch.testing.assert_close(db, 2 * ref, atol=4e-3, rtol=1e-4)
+
+
+def test_dgelu_polynomial_pointwise():
+    """GELU'(x) of the DGELU epilogue over a dense grid incl. the saturated tails: identity weight, dY = 1."""
+    ops = _ops()
+    M, K = 256, 256
+    x = torch.linspace(-9, 9, M * K, device=DEV).view(M, K).bfloat16()
+    eye = torch.eye(K, device=DEV).bfloat16()
+    ones = torch.ones(M, K, device=DEV).bfloat16()
+    got = ops.linear_dgrad(ones, eye, epilogue=ops.EPI_DGELU, aux=x).float()
+    ref = _dgelu(x.float())
+    assert (got - ref).abs().max().item() <= 4e-3 + 7e-5        # bf16 rounding of the output (|GELU'| <= 1.13) + polynomial
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 64, 2), (2, 208, 3), (1, 17, 1)])
+def test_attention_bwd_bias_gradient(B, N, H):
+    """b200_attn_bwd with dbias: the column sums of dqkv (the qkv bias gradient) leave the kernel's store epilogue."""
+    ops = _ops()
+    hd = 64
+    g = torch.Generator(device=DEV).manual_seed(300 + N)
+    qkv = torch.randn(B, N, 3 * H * hd, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B, N, H * hd, device=DEV, generator=g).bfloat16()
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, 0.125, need_lse=True)
+    plain = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125)
+    assert ops.attn_bwd_bias_fused(N)
+    db = torch.zeros(3 * H * hd, device=DEV, dtype=torch.float32)
+    fused = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125, dbias=db)
+    assert torch.equal(plain, fused)
+    torch.testing.assert_close(db, ops.colsum(fused.view(B * N, -1)), atol=2e-3, rtol=1e-4)
+    kv_len = torch.tensor([N] + [max(1, N // 2)] * (B - 1), device=DEV, dtype=torch.int32)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, 0.125, kv_len=kv_len, need_lse=True)
+    db.zero_()
+    fused = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125, kv_len=kv_len, dbias=db)
+    torch.testing.assert_close(db, ops.colsum(fused.view(B * N, -1)), atol=2e-3, rtol=1e-4)
