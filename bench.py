@@ -4,8 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--mode both|train|infer] [--impl ours|reference]
 
 The headline `value` is the TRAINING step (BASELINE.json configs[3]): zero_grad -> forward -> cross entropy -> backward
--> Nesterov SGD step, data parallel over N GPUs with torch DDP and the NCCL all-reduce of the gradient buckets (the only
-multi-GPU exchange on this path).  The inference half of the metric (configs[1]) rides in the same JSON
+-> Nesterov SGD step, data parallel over N GPUs.  The gradient exchange (the only multi-GPU step on this path)
+is b200timm.grad_sync by default -- every block's gradients are pushed to all ranks by multimem.red.add over the NVLink
+multicast address from the kernel that finalises them -- or torch DDP's NCCL all-reduce with --dp ddp (also the automatic
+fall-back when the node has no multicast).  The inference half of the metric (configs[1]) rides in the same JSON
 line as the sibling record `infer` (replicas, no data-path collective).  N > 1 is launched by the driver through
 torch.distributed.run (one rank per GPU); rank 0 prints ONE JSON line.  At N = 1 the line also carries
 
@@ -400,6 +402,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-script-records", action="store_true", help="skip plugin_benchmark_py / gpu_eager_baseline")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--dp", choices=["ddp", "peer"], default=os.environ.get("B200_DP", "peer"),
+                    help="N > 1 gradient exchange: torch DDP + NCCL all-reduce, or b200timm.grad_sync (multimem pushes fused "
+                         "into the gradient-finalising kernels)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

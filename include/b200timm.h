@@ -327,6 +327,15 @@ B200_API int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, co
                          int32_t soft_dtype, double smoothing, const float* lse, const float* tsum,
                          const float* grad_out, const float* denom, void* dlogits, int32_t B, int32_t C, void* stream);
 
+/* ------------------------------------------------------------------ data-parallel gradient exchange
+ * The all-reduce(mean) of the parameter gradients that the reference gets from DistributedDataParallel
+ * (timm/task/classification.py:64-65, train.py:1236-1269), fused into the kernel that finalises a block's gradients:
+ * dst[i] += bf16(src[i] * scale) on EVERY rank of the node, through one multimem.red.add per 16 bytes on the NVLink
+ * multicast address `dst_multicast` of the (symmetric, zero-initialised) flat bf16 gradient buffer.  src: fp32 (a block's
+ * gradient workspace) or bf16, n elements (multiple of 8), 16-byte aligned; scale = 1 / world_size.  The caller orders
+ * zeroing / pushes / reads with peer barriers (b200timm/grad_sync.py).  ABI >= 6.                                      */
+B200_API int b200_grad_push(const void* src, int32_t src_dtype, void* dst_multicast, int64_t n, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

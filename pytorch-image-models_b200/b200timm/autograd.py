@@ -234,7 +234,7 @@ class BlockFn(torch.autograd.Function):
         sizes = [0 if p is None else p.numel() for p in params]
         offs = [0]
         for n in sizes:
-            offs.append(offs[-1] + (n + 3) // 4 * 4)
+            offs.append(offs[-1] + (n + 7) // 8 * 8)      # 16-byte aligned bf16 slices (the layout of grad_sync's block slots)
         ws = torch.zeros(offs[-1], dtype=torch.float32, device=dx2.device)
         v = [None if p is None else ws[o_:o_ + n].view(p.shape) for p, o_, n in zip(params, offs, sizes)]
         # ---- MLP branch:  x2 = x1 + rs2 * g2 * (fc2(GELU(fc1(LN2(x1)))) + b2)
@@ -272,6 +272,16 @@ class BlockFn(torch.autograd.Function):
         if bqkv is not None and not fused_dbqkv:
             ops.colsum(dqkv, out=v[3], accumulate=True)
         dx0, _, _ = ops.layernorm_bwd(dh1, x0, n1w, mean1, rstd1, dres=dx1, dw_out=v[0], db_out=v[1])
+        # data parallel with b200timm.grad_sync.PeerGradSync: the workspace is scaled by 1 / world_size, rounded to bf16 and
+        # added into EVERY rank's flat gradient buffer by one kernel (multimem.red over the NVLink multicast address) --
+        # the gradient all-reduce happens here, block by block, under the backward GEMMs of the next block; p.grad of the
+        # parameters are views of that buffer, so nothing is returned to autograd for them
+        from .grad_sync import active_sink
+        sink = active_sink()
+        slot = None if sink is None else sink.slot_of(params)
+        if slot is not None and slot[1] == offs[-1]:
+            sink.push_block(ws, slot[0], slot[1])
+            return (dx0.view(B, N, D), *([None] * 14), None, None, None, None, None, None, None, None, None)
         # bf16 parameters (and the bf16 casts of fp32 master weights) take their gradient from one bf16 conversion of the
         # whole workspace; fp32 parameters (AMP: biases, LayerNorm, LayerScale) take the fp32 views directly
         if all(p is None or p.dtype == torch.float32 for p in params):

@@ -18,12 +18,29 @@ from .train_step import TrainStep, wrap_ddp
 TRAIN_FLOPS_PER_IMG = 3 * 35.13e9
 
 
-def build(model_name, dev, world):
+def build(model_name, dev, world, dp="ddp"):
+    """model, net (the model or its DDP wrapper), optimizer, loss, grad_sync (PeerGradSync or None)."""
     from .vision_transformer import create_model
     model = create_model(model_name).to(dev).to(torch.bfloat16).train()
     net = model
-    if world > 1:
-        kw = {}
+    sync = None
+    if world > 1 and dp == "peer":
+        # same start on every rank, as DDP's constructor guarantees by broadcasting rank 0's parameters
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+        from .grad_sync import PeerGradSync
+        flag = torch.ones(1, device=dev)
+        try:
+            sync = PeerGradSync(model)
+        except Exception as e:      # no NVLink multicast / symmetric memory on this node: every rank falls back together
+            flag.zero_()
+            if dist.get_rank() == 0:
+                print(f"[b200timm] PeerGradSync unavailable ({type(e).__name__}: {e}); using torch DDP", flush=True)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0:
+            sync, dp = None, "ddp"
+    if world > 1 and sync is None:
+        kw = {"bucket_cap_mb": 1024}      # one bucket: see DESIGN.md section 6 (the overlapped buckets cost more than they hide)
         for tok in filter(None, os.environ.get("B200_DDP_OPTS", "").split(",")):
             if tok == "no_bucket_view":
                 kw["gradient_as_bucket_view"] = False
@@ -43,20 +60,21 @@ def build(model_name, dev, world):
     else:
         from .loss import CrossEntropyLoss               # nn.CrossEntropyLoss of benchmark.py:380 on b200_cross_entropy_*
         loss_fn = CrossEntropyLoss()
-    return model, net, opt, loss_fn
+    return model, net, opt, loss_fn, sync
 
 
 def run(args, rank, world, dev, model_name="vit_base_patch16_224", clocks=None):
     """Returns the training record: value (img/s, all ranks), ms_per_step, e2e, launches, roofline of the GEMM launches."""
     torch.manual_seed(42 + rank)
-    model, net, opt, loss_fn = build(model_name, dev, world)
+    dp = getattr(args, "dp", "ddp")
+    model, net, opt, loss_fn, sync = build(model_name, dev, world, dp)
     B = args.batch
     # two device-resident input batches (2 x 77 MB > 126 MB L2) alternate between steps; a step streams ~25 GB
     xs = [torch.randn(B, 3, 224, 224, device=dev).to(torch.bfloat16) for _ in range(2)]
     ys = [torch.empty(B, dtype=torch.long, device=dev).random_(1000) for _ in range(2)]
     host_x = [t.cpu().pin_memory() for t in xs]
     host_y = [t.cpu().pin_memory() for t in ys]
-    step = TrainStep(net, loss_fn, opt, xs[0], ys[0], graph=not args.no_graph)
+    step = TrainStep(net, loss_fn, opt, xs[0], ys[0], graph=not args.no_graph, grad_sync=sync)
     runners = [step.capture_on(xs[i], ys[i]) for i in range(2)]
 
     def barrier():
@@ -145,9 +163,13 @@ def run(args, rank, world, dev, model_name="vit_base_patch16_224", clocks=None):
     value = total / (ms / 1e3)
     launches_per_step = step.launches if step.graph_enabled else eager_launches
     ddp = ""
-    if world > 1:
-        ddp = (f"dp{world} (torch DistributedDataParallel, gradient_as_bucket_view, NCCL all-reduce of the gradient buckets "
-               f"overlapped with the backward; 173 MB bf16 gradients / step / rank)")
+    if world > 1 and sync is not None:
+        ddp = (f"dp{world} (b200timm.grad_sync.PeerGradSync: every block's gradients are pushed to all ranks by multimem.red.add "
+               f"over the NVLink multicast address from the kernel that finalises them -- no all-reduce kernel; 173 MB bf16 "
+               f"gradients / step / rank; NCCL process group for setup / barriers only)")
+    elif world > 1:
+        ddp = (f"dp{world} (torch DistributedDataParallel, gradient_as_bucket_view, NCCL all-reduce of the gradient bucket(s); "
+               f"173 MB bf16 gradients / step / rank)")
     return {
         "value": round(value, 1), "unit": "img/s", "ms_per_step": round(ms / args.steps, 3),
         "workload": f"{model_name} bf16 TRAIN step batch={B}/GPU (BASELINE.json configs[3]): zero_grad + fwd + CE + bwd + "

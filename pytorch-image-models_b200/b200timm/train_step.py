@@ -54,12 +54,15 @@ class TrainStep:
 
     net: the model or its DistributedDataParallel wrapper.  graph=False keeps the eager step (same call signature)."""
 
-    def __init__(self, net, loss_fn, optimizer, example_x, example_y, graph=True, warmup=None):
+    def __init__(self, net, loss_fn, optimizer, example_x, example_y, graph=True, warmup=None, grad_sync=None):
         if not example_x.is_cuda:
             raise B200Error("TrainStep needs CUDA tensors (there is no CPU path)")
         self.net, self.loss_fn, self.opt = net, loss_fn, optimizer
         self.is_ddp = isinstance(net, torch.nn.parallel.DistributedDataParallel)
         self.graph_enabled = graph
+        self.grad_sync = grad_sync      # b200timm.grad_sync.PeerGradSync: fused gradient exchange instead of DDP's all-reduce
+        if grad_sync is not None and self.is_ddp:
+            raise B200Error("TrainStep: pass either a DistributedDataParallel wrapper or grad_sync, not both")
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.launches = 0           # kernels of libb200timm inside one step (counted on the capture pass)
@@ -71,9 +74,20 @@ class TrainStep:
 
     # ---------------------------------------------------------------------------------------------- the step itself
     def _eager(self, x, y):
-        self.opt.zero_grad(set_to_none=True)
-        loss = self.loss_fn(self.net(x), y)
-        loss.backward()
+        sync = self.grad_sync
+        if sync is None:
+            self.opt.zero_grad(set_to_none=True)
+            loss = self.loss_fn(self.net(x), y)
+            loss.backward()
+        else:
+            sync.begin()                       # zero the exchange buffer, peer barrier, tail grads -> local staging
+            try:
+                loss = self.loss_fn(self.net(x), y)
+                loss.backward()                # BlockFn pushes every block's gradients to all ranks as it finishes
+            except BaseException:
+                sync.abort()
+                raise
+            sync.finish()                      # tail push, peer barrier: every p.grad now holds the mean over ranks
         self.opt.step()
         return loss
 
@@ -97,7 +111,8 @@ class TrainStep:
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
-        self.opt.zero_grad(set_to_none=True)
+        if self.grad_sync is None:
+            self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(g, pool=self._pool):
             loss = self._eager(x, y)
         if self._pool is None:

@@ -26,15 +26,20 @@ def main():
     xs = [torch.randn(B, 3, 224, 224, device=dev).bfloat16() for _ in range(2)]
     ys = [torch.randint(0, 1000, (B,), device=dev) for _ in range(2)]
     out = {}
-    variants = [("no_ddp", None), ("ddp_default", {}), ("ddp_one_bucket", {"bucket_cap_mb": 1024})]
+    variants = [("no_ddp", None), ("ddp_default", {}), ("ddp_one_bucket", {"bucket_cap_mb": 1024}), ("peer_push", "peer")]
     if os.environ.get("VARIANTS"):
         variants = [v for v in variants if v[0] in os.environ["VARIANTS"].split(",")]
     for name, kw in variants:
         torch.manual_seed(1)
         model = create_model("vit_base_patch16_224").to(dev).to(torch.bfloat16).train()
-        net = model if kw is None else wrap_ddp(model, dev, **kw)
+        sync = None
+        if kw == "peer":
+            from b200timm.grad_sync import PeerGradSync
+            net, sync = model, PeerGradSync(model)
+        else:
+            net = model if kw is None else wrap_ddp(model, dev, **kw)
         opt = BO.SGD(model.parameters(), lr=1e-4, momentum=0.9, nesterov=True)
-        step = TrainStep(net, BL.CrossEntropyLoss(), opt, xs[0], ys[0])
+        step = TrainStep(net, BL.CrossEntropyLoss(), opt, xs[0], ys[0], grad_sync=sync)
         runners = [step.capture_on(xs[i], ys[i]) for i in range(2)]
         for i in range(4):
             runners[i & 1]()
@@ -47,6 +52,9 @@ def main():
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 20
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)       # the slower rank sets the pace of every synchronised variant
+        ms_max = t.item()
         # eager per-op split on a side stream (DDP's AccumulateGrad nodes live there)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -58,14 +66,15 @@ def main():
             ops.enable_op_timing(False)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        out[name] = {"graph_ms": round(ms, 3), "ops": {k: round(t, 3) for k, (n, t) in det.items()},
+        out[name] = {"graph_ms": round(ms, 3), "graph_ms_max_over_ranks": round(ms_max, 3), "ops": {k: round(t, 3) for k, (n, t) in det.items()},
                      "ops_total": round(sum(t for _, t in det.values()), 3)}
-        del runners, step, net, model, opt
+        del runners, step, net, model, opt, sync
         torch.cuda.empty_cache()
         dist.barrier()
     if rank == 0:
         names = list(out)
-        print(json.dumps({n: out[n]["graph_ms"] for n in names}), {n: out[n]["ops_total"] for n in names})
+        print(json.dumps({n: out[n]["graph_ms"] for n in names}), "max over ranks:",
+              json.dumps({n: out[n]["graph_ms_max_over_ranks"] for n in names}), {n: out[n]["ops_total"] for n in names})
         keys = sorted(out[names[0]]["ops"], key=lambda k: -out[names[0]]["ops"][k])
         for k in keys[:30]:
             print("  ".join(f"{out[n]['ops'].get(k, 0):8.3f}" for n in names), " ", k)
