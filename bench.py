@@ -264,6 +264,35 @@ def gpu_script_records():
     return recs
 
 
+def other_config_records():
+    """BASELINE.json configs[2] (convnext_base infer, batch 256) and configs[4] (NaFlex ViT-L/14 variable-sequence infer,
+    batch 64) measured by tools/bench_model.py (device-resident, CUDA events, two alternating input batches) in fresh
+    interpreters: sub-records of the N = 1 line, so that the driver's run carries them."""
+    recs = {}
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    for key, argv, flops in (("convnext_base_infer", ["convnext_base", "--batch", "256"], 30.71e9),
+                             ("naflex_vit_large_patch14_infer", ["naflex:vit_large_patch14_clip_336", "--batch", "64"], None)):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_model.py")] + argv + ["--steps", "10", "--warmup", "3"],
+                               env=env, cwd=ROOT, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, text=True)
+            d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            rec = {"value": d["img_per_s"], "unit": "img/s", "ms_per_step": d["ms_per_step"], "batch": d["batch"],
+                   "launches_per_step": d.get("launches_per_step"), "cmd": "python tools/bench_model.py " + " ".join(argv)}
+            if flops:
+                tf = flops * d["img_per_s"] / 1e12
+                rec["whole_step_tflops"] = round(tf, 1)
+                rec["whole_step_frac"] = round(tf / measured_peaks()["bf16_tflops_sustained"], 4)
+            for k in ("valid_tokens_per_img", "tokens_per_s"):
+                if k in d:
+                    rec[k] = d[k]
+            recs[key] = rec
+        except (subprocess.SubprocessError, OSError, ValueError, IndexError, KeyError) as e:
+            recs[key] = {"error": repr(e)[:300]}
+    return recs
+
+
 # --------------------------------------------------------------------------------------------------------- inference record
 def bench_infer(args, rank, world, dev, clocks=None):
     import torch.distributed as dist
@@ -469,6 +498,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline_record(5, 1)
         if world == 1 and not args.no_script_records:
             line.update(gpu_script_records())
+            line["other_configs"] = other_config_records()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -327,6 +327,10 @@ B200_API int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, co
                          int32_t soft_dtype, double smoothing, const float* lse, const float* tsum,
                          const float* grad_out, const float* denom, void* dlogits, int32_t B, int32_t C, void* stream);
 
+/* dpre = dy * act'(pre) elementwise (bf16, n a multiple of 8): the activation backward of an Mlp with an inner norm between
+ * the activation and fc2 (Mlp(norm_layer=...), timm/layers/mlp.py:44-53); act as in b200_gemm_desc.act.  ABI >= 6.      */
+B200_API int b200_act_bwd(const void* dy, const void* pre, void* dpre, int64_t n, int32_t act, void* stream);
+
 /* ------------------------------------------------------------------ data-parallel gradient exchange
  * The all-reduce(mean) of the parameter gradients that the reference gets from DistributedDataParallel
  * (timm/task/classification.py:64-65, train.py:1236-1269), fused into the kernel that finalises a block's gradients:

@@ -105,26 +105,39 @@ class LinearFn(torch.autograd.Function):
 
 
 class MlpFn(torch.autograd.Function):
-    """Mlp.forward (timm/layers/mlp.py:47-54): fc2(GELU(fc1(x)))."""
+    """Mlp.forward (timm/layers/mlp.py:47-54): fc2(norm(act(fc1(x)))); norm = Identity unless the Mlp was built with a
+    norm_layer (`scale_mlp_norm`, mlp.py:44): then the activation backward is its own elementwise pass (b200_act_bwd)
+    instead of the fc2-dgrad epilogue."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, act_kind=0):
+    def forward(ctx, x, w1, b1, w2, b2, act_kind=0, nw=None, nb=None, eps=0.0):
         shape = x.shape
         x2 = _c(x.reshape(-1, shape[-1]))
         pre = torch.empty(x2.shape[0], w1.shape[0], dtype=torch.bfloat16, device=x.device)
         act = ops.linear_fwd(x2, w1, b1, epilogue=ops.EPI_BIAS_GELU, out2=pre, act=act_kind)
-        y = ops.linear_fwd(act, w2, b2)
-        ctx.save_for_backward(x2, w1, b1, w2, b2, pre, act)
+        an, mean, rstd = act, None, None
+        if nw is not None:
+            an, mean, rstd = ops.layernorm_fwd(act, nw, nb, eps, save_stats=True)
+        y = ops.linear_fwd(an, w2, b2)
+        ctx.save_for_backward(x2, w1, b1, w2, b2, pre, act, an, nw, nb, mean, rstd)
         ctx.shape, ctx.act_kind = shape, act_kind
         return y.view(*shape[:-1], -1)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w1, b1, w2, b2, pre, act = ctx.saved_tensors
+        x2, w1, b1, w2, b2, pre, act, an, nw, nb, mean, rstd = ctx.saved_tensors
         dy2 = _c(dy.reshape(-1, dy.shape[-1]))
-        dpre = ops.linear_dgrad(dy2, w2, epilogue=ops.EPI_DGELU, aux=pre, act=ctx.act_kind)
+        gnw = gnb = None
+        if nw is None:
+            dpre = ops.linear_dgrad(dy2, w2, epilogue=ops.EPI_DGELU, aux=pre, act=ctx.act_kind)
+        else:
+            dan = ops.linear_dgrad(dy2, w2)
+            da, dnw, dnb = ops.layernorm_bwd(dan, act, nw, mean, rstd)
+            gnw = _to_param_dtype(dnw, nw)
+            gnb = None if nb is None else _to_param_dtype(dnb, nb)
+            dpre = ops.act_bwd(_c(da), pre, ctx.act_kind)
         dx = ops.linear_dgrad(dpre, w1).view(ctx.shape)
-        return dx, _wgrad(dpre, x2, w1), _bias_grad(dpre, b1), _wgrad(dy2, act, w2), _bias_grad(dy2, b2), None
+        return (dx, _wgrad(dpre, x2, w1), _bias_grad(dpre, b1), _wgrad(dy2, an, w2), _bias_grad(dy2, b2), None, gnw, gnb, None)
 
 
 class AttentionFn(torch.autograd.Function):
@@ -477,33 +490,58 @@ class AttentionNormFn(torch.autograd.Function):
 
 
 class AttnPoolFn(torch.autograd.Function):
-    """The attention of AttentionPoolLatent (timm/layers/attention_pool.py:95-117, latent_len 1): one latent query per
-    image attends over the N tokens.  It runs on the self-attention kernels: the kv projection is written straight into
-    the k / v columns of a [B, N, 3, H, 64] buffer, the projected latent becomes query row 0 of every image (the other
-    query rows are zero and their outputs are never read), and output row 0 is the pooled vector.  The backward feeds
-    d(out) as row 0 of an otherwise zero gradient: rows with zero upstream gradient contribute nothing to dK / dV."""
+    """The attention of AttentionPoolLatent (timm/layers/attention_pool.py:95-117): L learned latent queries per image attend
+    over the N tokens.  It runs on the self-attention kernels: the kv projection is written straight into the k / v columns
+    of a [B, N, 3, H, 64] buffer, the projected latents become query rows 0 .. L-1 of every image (the other query rows are
+    zero and their outputs are never read), and output rows 0 .. L-1 are the pooled vectors.  The backward feeds d(out) as
+    rows 0 .. L-1 of an otherwise zero gradient: rows with zero upstream gradient contribute nothing to dK / dV."""
 
     @staticmethod
     def forward(ctx, x, q, wkv, bkv, num_heads, scale):
         B, N, D = x.shape
+        Dp = wkv.shape[0] // 2                        # H * 64: the (head-padded) width of q, k and v
+        L = q.numel() // Dp
+        if L > N:
+            raise B200Error("AttentionPoolLatent: more latent queries than tokens is not covered")
         x2 = _c(x.reshape(B * N, D))
-        qkv = torch.zeros(B * N, 3 * D, dtype=torch.bfloat16, device=x.device)
-        ops.linear_fwd(x2, wkv, bkv, out=qkv[:, D:])
-        qkv.view(B, N, 3 * D)[:, 0, :D] = q.reshape(1, D)
-        o, lse = ops.attention_fwd(qkv, B, N, num_heads, D // num_heads, scale, None, need_lse=True)
+        qkv = torch.zeros(B * N, 3 * Dp, dtype=torch.bfloat16, device=x.device)
+        ops.linear_fwd(x2, wkv, bkv, out=qkv[:, Dp:])
+        qkv.view(B, N, 3 * Dp)[:, :L, :Dp] = q.reshape(1, L, Dp)
+        o, lse = ops.attention_fwd(qkv, B, N, num_heads, Dp // num_heads, scale, None, need_lse=True)
         ctx.save_for_backward(x2, wkv, bkv, qkv, o, lse)
-        ctx.meta = (B, N, D, num_heads, scale, q.shape, q.dtype)
-        return o[:, 0].contiguous()
+        ctx.meta = (B, N, D, Dp, L, num_heads, scale, q.shape, q.dtype)
+        return o[:, :L].contiguous()
 
     @staticmethod
     def backward(ctx, dy):
         x2, wkv, bkv, qkv, o, lse = ctx.saved_tensors
-        B, N, D, H, scale, qshape, qdtype = ctx.meta
-        dout = torch.zeros(B, N, D, dtype=torch.bfloat16, device=dy.device)
-        dout[:, 0] = dy
-        dqkv = ops.attention_bwd(qkv, o, dout, lse, B, N, H, D // H, scale, None).view(B * N, 3 * D)
-        dq = dqkv.view(B, N, 3 * D)[:, 0, :D].float().sum(0).to(qdtype).reshape(qshape)
-        dkv = dqkv[:, D:].contiguous()                      # once per step, on the pooling head only
+        B, N, D, Dp, L, H, scale, qshape, qdtype = ctx.meta
+        dout = torch.zeros(B, N, Dp, dtype=torch.bfloat16, device=dy.device)
+        dout[:, :L] = dy
+        dqkv = ops.attention_bwd(qkv, o, dout, lse, B, N, H, Dp // H, scale, None).view(B * N, 3 * Dp)
+        dq = dqkv.view(B, N, 3 * Dp)[:, :L, :Dp].float().sum(0).to(qdtype).reshape(qshape)
+        dkv = dqkv[:, Dp:].contiguous()                     # once per step, on the pooling head only
         dx = ops.linear_dgrad(dkv, wkv).view(B, N, D)
         return dx, dq, _wgrad(dkv, x2, wkv), _bias_grad(dkv, bkv), None, None
 
+
+class SdpaFn(torch.autograd.Function):
+    """softmax(q k^T * scale) v on a packed [B, N, 3 * H * 64] q | k | v buffer -> [B, N, H * 64]; forward and backward on the
+    attention kernels.  For callers whose projections are not the fused nn.Linear of Attention (the parameter-free
+    self-attention of AttentionPoolPrr, attention_pool.py:172-187; EvaAttention with separate q / k / v projections)."""
+
+    @staticmethod
+    def forward(ctx, qkv, kv_len, num_heads, scale):
+        B, N, C3 = qkv.shape
+        hd = C3 // 3 // num_heads
+        qkv = _c(qkv)
+        o, lse = ops.attention_fwd(qkv, B, N, num_heads, hd, scale, kv_len, need_lse=True)
+        ctx.save_for_backward(qkv, o, lse, kv_len)
+        ctx.meta = (B, N, num_heads, hd, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse, kv_len = ctx.saved_tensors
+        B, N, H, hd, scale = ctx.meta
+        return ops.attention_bwd(qkv, o, _c(do), lse, B, N, H, hd, scale, kv_len), None, None, None

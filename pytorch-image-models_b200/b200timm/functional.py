@@ -90,8 +90,7 @@ def check_attention(attn, allow_norms=False):
             raise B200Error("qk_norm attention is not supported")
         if not _is_identity(getattr(attn, "norm", None)):
             raise B200Error("scale_norm attention is not supported")
-    if attn.head_dim != 64:
-        raise B200Error(f"head_dim {attn.head_dim} is not supported (64 only)")
+    head_pad(attn.head_dim)
     _check_drop(attn.attn_drop, "attn_drop")
     _check_drop(attn.proj_drop, "proj_drop")
 
@@ -127,10 +126,10 @@ def mlp_act(mlp):
     raise B200Error(f"unsupported Mlp activation {a} (GELU, tanh GELU, SiLU)")
 
 
-def check_mlp(mlp):
+def check_mlp(mlp, allow_norm=False):
     mlp_act(mlp)
-    if not _is_identity(getattr(mlp, "norm", None)):
-        raise B200Error("Mlp with an inner norm is not supported")
+    if not allow_norm and not _is_identity(getattr(mlp, "norm", None)):
+        raise B200Error("Mlp with an inner norm runs through mlp_forward, not the fully fused block")
     if not isinstance(mlp.fc1, nn.Linear):
         raise B200Error("conv Mlp is not supported here")
     _check_drop(getattr(mlp, "drop1", None), "mlp drop")
@@ -161,6 +160,72 @@ def _w(linear):
     if cache is None or cache[0] != key:
         linear._b200_wbf16 = cache = (key, w.detach().to(torch.bfloat16).contiguous())
     return cache[1]
+
+
+# ------------------------------------------------------------------------------------------------ head_dim < 64
+# The attention kernels are built for head_dim 64 (one 128-byte swizzle atom per token row and head).  Narrower heads
+# (timm's test_vit* models: 32; attention.py:85-93 allows any dim // num_heads) run on the SAME kernels through zero
+# padding that lives entirely in the WEIGHTS: the rows of the qkv projection (and its bias) are spread to 64 per head with
+# zero rows in between, the columns of the output projection likewise -- the GEMM then writes a [M, 3 * H * 64] buffer whose
+# padding columns are exact zeros (q . k over the padding adds 0, the padded v columns produce output columns that meet zero
+# weights), and softmax scaling uses the module's own scale (true head_dim ** -0.5).  Padded weights are cached at inference
+# and built differentiably (F.pad on a view) in training, so gradients reach the real parameters through autograd.
+def head_pad(hd):
+    """Padded head width the kernels run (64), or raises for widths that cannot be padded."""
+    if hd == 64:
+        return 64
+    if hd < 64 and hd % 8 == 0:
+        return 64
+    raise B200Error(f"head_dim {hd} is not supported (64, or a multiple of 8 below 64 through weight padding)")
+
+
+def _cached(module, attr, key, build):
+    cache = getattr(module, attr, None)
+    if cache is None or cache[0] != key:
+        with torch.no_grad():
+            cache = (key, build())
+        setattr(module, attr, cache)
+    return cache[1]
+
+
+def _pad_rows(t, groups, H, hd):
+    """[groups * H * hd, ...] -> [groups * H * 64, ...]: every head's hd rows followed by 64 - hd zero rows."""
+    if t is None or hd == 64:
+        return t
+    tail = t.shape[1:]
+    v = t.reshape(groups * H, hd, *tail)
+    pad = [0, 0] * len(tail) + [0, 64 - hd]
+    return F.pad(v, pad).reshape(groups * H * 64, *tail)
+
+
+def _pad_cols(w, H, hd):
+    """[out, H * hd] -> [out, H * 64]: zero columns after every head's hd columns."""
+    if hd == 64:
+        return w
+    return F.pad(w.reshape(w.shape[0], H, hd), (0, 64 - hd)).reshape(w.shape[0], H * 64)
+
+
+def head_padded_linear_in(linear, groups, H, hd, bias=None, weight=None):
+    """(weight, bias) of a projection INTO head space (qkv: groups = 3, kv: 2, q: 1) with heads padded to 64 rows."""
+    w = _w(linear) if weight is None else weight
+    b = linear.bias if bias is None else bias
+    if hd == 64:
+        return w, b
+    if torch.is_grad_enabled() and (w.requires_grad or (b is not None and b.requires_grad)):
+        return _pad_rows(w, groups, H, hd), _pad_rows(b, groups, H, hd)
+    key = (ops.wkey(w), None if b is None else ops.wkey(b), groups, H, hd)
+    return _cached(linear, "_b200_hpad_in", key, lambda: (_pad_rows(w.detach(), groups, H, hd).contiguous(),
+                                                         None if b is None else _pad_rows(b.detach(), groups, H, hd).contiguous()))
+
+
+def head_padded_linear_out(linear, H, hd):
+    """weight of a projection OUT of head space (attention's proj) with every head's columns padded to 64."""
+    w = _w(linear)
+    if hd == 64:
+        return w
+    if torch.is_grad_enabled() and w.requires_grad:
+        return _pad_cols(w, H, hd)
+    return _cached(linear, "_b200_hpad_out", (ops.wkey(w), H, hd), lambda: _pad_cols(w.detach(), H, hd).contiguous())
 
 
 def _padded_out_linear(linear, x2):
@@ -199,31 +264,34 @@ def attention_forward(attn, x, kv_len=None, residual=None, gamma=None):
     check_attention(attn, allow_norms=True)
     qk, sn = _attn_norms(attn)
     B, N, C = x.shape
+    H, hd = attn.num_heads, attn.head_dim
+    if hd != 64 and (qk is not None or sn is not None):
+        raise B200Error("qk_norm / scale_norm with head_dim != 64 is not covered")
+    wqkv, bqkv = head_padded_linear_in(attn.qkv, 3, H, hd)
+    wproj = head_padded_linear_out(attn.proj, H, hd)
     if _needs_grad(x, attn):
         if residual is not None:
             raise B200Error("attention_forward: the fused residual is an inference-only epilogue")
         _bf16_2d(x, C)
         if qk is None and sn is None:
             from .autograd import AttentionFn
-            return AttentionFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, kv_len,
-                                     attn.num_heads, attn.scale)
+            return AttentionFn.apply(x, wqkv, bqkv, wproj, attn.proj.bias, kv_len, H, attn.scale)
         from .autograd import AttentionNormFn
         qw, qb, kw, kb, qe = qk if qk is not None else (None, None, None, None, 0.0)
         nw, nb, ne = sn if sn is not None else (None, None, 0.0)
-        return AttentionNormFn.apply(x, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, qw, qb, kw, kb, nw, nb,
-                                     kv_len, attn.num_heads, attn.scale, qe, ne)
+        return AttentionNormFn.apply(x, wqkv, bqkv, wproj, attn.proj.bias, qw, qb, kw, kb, nw, nb, kv_len, H, attn.scale, qe, ne)
     x2 = _bf16_2d(x, C)
-    qkv = ops.linear_fwd(x2, _w(attn.qkv), attn.qkv.bias)
+    qkv = ops.linear_fwd(x2, wqkv, bqkv)
     if qk is not None:
-        ops.qk_norm_fwd(qkv, B * N, attn.num_heads, *qk)
-    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
+        ops.qk_norm_fwd(qkv, B * N, H, *qk)
+    o, _ = ops.attention_fwd(qkv, B, N, H, 64, attn.scale, kv_len)
     o2 = o.view(B * N, -1)
     if sn is not None:
         o2 = ops.layernorm_fwd(o2, *sn)[0]
     if residual is not None:
-        y = ops.linear_fwd(o2, _w(attn.proj), attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=residual, gamma=gamma)
+        y = ops.linear_fwd(o2, wproj, attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=residual, gamma=gamma)
     else:
-        y = ops.linear_fwd(o2, _w(attn.proj), attn.proj.bias)
+        y = ops.linear_fwd(o2, wproj, attn.proj.bias)
     return y.view(B, N, -1)
 
 
@@ -289,17 +357,29 @@ def rope_qkv_projection(x2, wqkv, bqkv, emb, B, N, H, npt, half):
     return ops.rope_qk(ops.linear_fwd(x2, wqkv, bqkv), emb, B, N, H, npt, half=True)
 
 
-def mlp_forward(mlp, x):
-    """Mlp.forward (timm/layers/mlp.py:47-54): fc2(GELU(fc1(x))), GELU fused into fc1's epilogue."""
-    check_mlp(mlp)
+def mlp_forward(mlp, x, residual=None, gamma=None, row_scale=None, rows_per_scale=0):
+    """Mlp.forward (timm/layers/mlp.py:47-54): fc2(norm(GELU(fc1(x)))), GELU fused into fc1's epilogue, the optional inner
+    norm (Mlp(norm_layer=...): `scale_mlp_norm` blocks) as a LayerNorm kernel between the two GEMMs.  With `residual`
+    (inference only) the block's `x + drop_path(ls(mlp(...)))` is folded into fc2's epilogue."""
+    check_mlp(mlp, allow_norm=True)
     shape = x.shape
+    norm = None if _is_identity(getattr(mlp, "norm", None)) else _ln_params(mlp.norm)
     if _needs_grad(x, mlp):
         from .autograd import MlpFn
+        if residual is not None:
+            raise B200Error("mlp_forward: the fused residual is an inference-only epilogue")
         _bf16_2d(x, shape[-1])
-        return MlpFn.apply(x, _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, mlp_act(mlp))
+        nw, nb, eps = norm if norm is not None else (None, None, 0.0)
+        return MlpFn.apply(x, _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, mlp_act(mlp), nw, nb, eps)
     x2 = _bf16_2d(x, shape[-1])
     h = ops.linear_fwd(x2, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(mlp))
-    y = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias)
+    if norm is not None:
+        h = ops.layernorm_fwd(h, *norm)[0]
+    if residual is not None:
+        y = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=residual, gamma=gamma,
+                           row_scale=row_scale, rows_per_scale=rows_per_scale)
+    else:
+        y = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias)
     return y.view(*shape[:-1], -1)
 
 
@@ -390,17 +470,109 @@ def _variant_block_forward(blk, x, kv_len):
     h = ops.layernorm_fwd(x2, *_ln_params(blk.norm2))[0]
     if is_glu(mlp):
         return glu_mlp_forward(mlp, h, residual=x2, gamma=_gamma(blk.ls2)).view(B, N, D)
-    check_mlp(mlp)
-    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(mlp))
-    return ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
-                          gamma=_gamma(blk.ls2)).view(B, N, D)
+    return mlp_forward(mlp, h, residual=x2, gamma=_gamma(blk.ls2)).view(B, N, D)
+
+
+def _act_code(act_module):
+    name = type(act_module).__name__
+    if name == "GELUTanh" or (name == "GELU" and getattr(act_module, "approximate", "none") == "tanh"):
+        return ops.ACTS["gelu_tanh"]
+    if name == "GELU" and getattr(act_module, "approximate", "none") == "none":
+        return ops.ACTS["gelu"]
+    if name in ("SiLU", "Swish"):
+        return ops.ACTS["silu"]
+    raise B200Error(f"unsupported activation {act_module} (GELU, tanh GELU, SiLU)")
+
+
+def is_parallel_block(blk):
+    """timm's ParallelScalingBlock (vision_transformer.py:292-420): attention and MLP read ONE normalised input through ONE
+    fused in-projection and are summed before the residual (ViT-22B; vit_*_xp_224, test_vit3)."""
+    return hasattr(blk, "in_proj") and hasattr(blk, "in_split") and hasattr(blk, "in_norm")
+
+
+def parallel_block_forward(blk, x, kv_len=None):
+    """ParallelScalingBlock.forward (vision_transformer.py:373-420):
+
+        y = in_norm(x);  [x_mlp | q | k | v] = in_proj(y) (+ mlp_bias);  q, k = q_norm(q), k_norm(k)
+        out = x + drop_path(ls(out_proj(cat(sdpa(q, k, v), act(x_mlp)))))          (or attn_out_proj(.) + mlp_out_proj(.))
+
+    The fused in-projection runs as two GEMMs over row ranges of in_proj.weight (views, no copy): the MLP rows with the
+    activation in the epilogue, the q / k / v rows into the contiguous [M, 3D] buffer the attention kernels read in place.
+    The output projection runs as two GEMMs over column ranges of out_proj.weight (strided views) -- the concatenation is
+    never materialised; at inference both carry the residual epilogue (x + gamma * rs * (...)), so LayerScale, DropPath
+    and the residual add cost nothing.  Training composes AttentionFn / AttentionNormFn and MlpFn on those views."""
+    B, N, D = x.shape
+    H, hd = blk.num_heads, blk.head_dim
+    head_pad(hd)
+    _check_drop(blk.attn_drop, "attn_drop")
+    _check_drop(blk.mlp_drop, "mlp drop")
+    act = _act_code(blk.mlp_act)
+    hidden = blk.in_split[0]
+    if list(blk.in_split[1:]) != [D, D, D] or hidden % 8 or D % 8:
+        raise B200Error("ParallelScalingBlock: unexpected in_split / widths that are not multiples of 8")
+    qk = None
+    if not _is_identity(blk.q_norm) or not _is_identity(blk.k_norm):
+        (qw, qb, qe), (kw, kb, ke) = _ln_params(blk.q_norm), _ln_params(blk.k_norm)
+        if float(qe) != float(ke) or type(blk.q_norm) is not type(blk.k_norm) or (qb is None) != (kb is None):
+            raise B200Error("q_norm / k_norm need equal eps and affine parameters")
+        qk = (qw, qb, kw, kb, qe)
+    if hd != 64 and qk is not None:
+        raise B200Error("qk_norm with head_dim != 64 is not covered")
+    w_in = _w(blk.in_proj)
+    w_mlp, w_qkv = w_in[:hidden], w_in[hidden:]
+    b_in = blk.in_proj.bias
+    b_mlp = blk.mlp_bias if b_in is None else b_in[:hidden]
+    b_qkv = None if b_in is None else b_in[hidden:]
+    if blk.out_proj is not None:
+        w_out = _w(blk.out_proj)
+        w_ao, w_mo = w_out[:, :D], w_out[:, D:]
+        b_ao, b_mo = blk.out_proj.bias, None
+    else:
+        w_ao, w_mo = _w(blk.attn_out_proj), _w(blk.mlp_out_proj)
+        b_ao, b_mo = blk.attn_out_proj.bias, blk.mlp_out_proj.bias
+    if hd != 64:      # heads padded to 64 inside the weights (see head_pad): not cached here -- slices of a fused projection
+        w_qkv, b_qkv, w_ao = _pad_rows(w_qkv, 3, H, hd), _pad_rows(b_qkv, 3, H, hd), _pad_cols(w_ao, H, hd)
+        if not (torch.is_grad_enabled() and w_qkv.requires_grad):
+            w_qkv, w_ao = w_qkv.contiguous(), w_ao.contiguous()
+    gamma = _gamma(blk.ls)
+    if _needs_grad(x, blk):
+        from .autograd import AttentionFn, AttentionNormFn, MlpFn
+        _bf16_2d(x, D)
+        y = layernorm(blk.in_norm, x)
+        if qk is None:
+            ya = AttentionFn.apply(y, w_qkv, b_qkv, w_ao, b_ao, kv_len, H, blk.scale)
+        else:
+            ya = AttentionNormFn.apply(y, w_qkv, b_qkv, w_ao, b_ao, qk[0], qk[1], qk[2], qk[3], None, None, kv_len, H, blk.scale,
+                                       qk[4], 0.0)
+        ym = MlpFn.apply(y, w_mlp, b_mlp, w_mo, b_mo, act)
+        br = ya + ym
+        if gamma is not None:
+            br = br * gamma.to(br.dtype)
+        f = _drop_path_factor(blk.drop_path, br)
+        if f is not None:
+            br = br * f.view(B, 1, 1).to(br.dtype)
+        return x + br
+    rs = _drop_path_factor(blk.drop_path, x)          # None in eval mode
+    x2 = _bf16_2d(x, D)
+    y = ops.layernorm_fwd(x2, *_ln_params(blk.in_norm))[0]
+    hmlp = ops.linear_fwd(y, w_mlp, b_mlp, epilogue=ops.EPI_BIAS_GELU, act=act)
+    qkv = ops.linear_fwd(y, w_qkv, b_qkv)
+    if qk is not None:
+        ops.qk_norm_fwd(qkv, B * N, H, *qk)
+    o, _ = ops.attention_fwd(qkv, B, N, H, 64, blk.scale, kv_len)
+    t = ops.linear_fwd(o.view(B * N, -1), w_ao, b_ao, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=gamma, row_scale=rs,
+                       rows_per_scale=N)
+    out = ops.linear_fwd(hmlp, w_mo, b_mo, epilogue=ops.EPI_BIAS_RESIDUAL, aux=t, gamma=gamma, row_scale=rs, rows_per_scale=N)
+    return out.view(B, N, D)
 
 
 def block_forward(blk, x, kv_len=None):
     """Block.forward (timm/models/vision_transformer.py:206-214), eval mode."""
+    if is_parallel_block(blk):
+        return parallel_block_forward(blk, x, kv_len)
     attn, mlp = blk.attn, blk.mlp
     qk, sn = _attn_norms(attn)
-    if is_glu(mlp) or qk is not None or sn is not None:
+    if is_glu(mlp) or qk is not None or sn is not None or not _is_identity(getattr(mlp, "norm", None)):
         check_attention(attn, allow_norms=True)
         return _variant_block_forward(blk, x, kv_len)
     check_attention(attn)
@@ -412,16 +584,20 @@ def block_forward(blk, x, kv_len=None):
         n1w, n1b, e1 = _ln_params(blk.norm1)
         n2w, n2b, e2 = _ln_params(blk.norm2)
         rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)
-        return BlockFn.apply(x, n1w, n1b, _w(attn.qkv), attn.qkv.bias, _w(attn.proj), attn.proj.bias, n2w, n2b,
+        wqkv, bqkv = head_padded_linear_in(attn.qkv, 3, attn.num_heads, attn.head_dim)
+        return BlockFn.apply(x, n1w, n1b, wqkv, bqkv, head_padded_linear_out(attn.proj, attn.num_heads, attn.head_dim),
+                             attn.proj.bias, n2w, n2b,
                              _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, _gamma(blk.ls1), _gamma(blk.ls2),
                              rs1, rs2, kv_len, attn.num_heads, attn.scale, e1, e2, mlp_act(mlp))
     rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)   # None in eval mode
     x2 = _bf16_2d(x, D)
     w1, b1, eps1 = _ln_params(blk.norm1)
     h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
-    qkv = ops.linear_fwd(h, _w(attn.qkv), attn.qkv.bias)
-    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, attn.head_dim, attn.scale, kv_len)
-    x2 = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
+    wqkv, bqkv = head_padded_linear_in(attn.qkv, 3, attn.num_heads, attn.head_dim)
+    qkv = ops.linear_fwd(h, wqkv, bqkv)
+    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, 64, attn.scale, kv_len)
+    x2 = ops.linear_fwd(o.view(B * N, -1), head_padded_linear_out(attn.proj, attn.num_heads, attn.head_dim), attn.proj.bias,
+                        epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
                         gamma=_gamma(blk.ls1), row_scale=rs1, rows_per_scale=N)
     w2, b2, eps2 = _ln_params(blk.norm2)
     h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
@@ -435,13 +611,19 @@ def patch_embed_forward(pe, img):
     """PatchEmbed.forward (timm/layers/patch_embed.py:117-142), flatten=True output [B, G, D]."""
     if not _is_identity(pe.norm):
         raise B200Error("PatchEmbed with a norm layer is not supported")
-    if getattr(pe, "dynamic_img_pad", False):
-        raise B200Error("dynamic_img_pad is not supported")
     ph, pw = pe.patch_size
     if ph != pw:
         raise B200Error("non-square patches are not supported")
+    if getattr(pe, "dynamic_img_pad", False):      # patch_embed.py:131-134: zero-pad bottom / right up to a patch multiple
+        pad_h = (ph - img.shape[-2] % ph) % ph
+        pad_w = (pw - img.shape[-1] % pw) % pw
+        if pad_h or pad_w:
+            if img.dtype == torch.uint8:
+                raise B200Error("dynamic_img_pad with raw uint8 batches is not covered")
+            img = F.pad(img, (0, pad_w, 0, pad_h))
     B, C, H, W = img.shape
-    if pe.img_size is not None and getattr(pe, "strict_img_size", True) and (H, W) != tuple(pe.img_size):
+    if pe.img_size is not None and getattr(pe, "strict_img_size", True) and not getattr(pe, "dynamic_img_pad", False) \
+            and (H, W) != tuple(pe.img_size):
         raise AssertionError(f"Input size ({H}x{W}) doesn't match model ({pe.img_size[0]}x{pe.img_size[1]}).")
     if H % ph or W % pw:
         raise AssertionError(f"Input size ({H}x{W}) should be divisible by patch size ({ph}).")
@@ -500,8 +682,6 @@ def _dynamic_pos_embed(model, img):
 
 def vit_embed(model, img):
     """patch_embed + _pos_embed (+ norm_pre) of VisionTransformer.forward_features (:1238-1241)."""
-    if getattr(model, "dynamic_img_size", False) and getattr(model.patch_embed, "dynamic_img_pad", False):
-        raise B200Error("dynamic_img_pad is not supported by the fused path")
     if not _is_identity(getattr(model, "patch_drop", None)):
         raise B200Error("patch dropout is not supported")
     _check_drop(getattr(model, "pos_drop", None), "pos_drop")
@@ -560,46 +740,106 @@ def _linear(lin, x):
     return ops.linear_fwd(x2, _w(lin), lin.bias).view(*shape[:-1], -1)
 
 
+def sdpa_packed(qkv, num_heads, scale, kv_len=None):
+    """Attention on a packed bf16 [B, N, 3 * H * 64] buffer (q | k | v thirds, heads inside) -> [B, N, H * 64]."""
+    B, N, C3 = qkv.shape
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        from .autograd import SdpaFn
+        return SdpaFn.apply(qkv, kv_len, num_heads, scale)
+    return ops.attention_fwd(qkv.contiguous(), B, N, num_heads, C3 // 3 // num_heads, scale, kv_len)[0]
+
+
 def attention_pool_forward(pool, x):
-    """AttentionPoolLatent.forward (timm/layers/attention_pool.py:95-128) for one latent (SigLIP's 'map' head): latent ->
-    q projection; tokens -> kv projection; single-query attention on the self-attention kernels (autograd.AttnPoolFn);
-    proj; x + mlp(norm(x)); token pooling."""
-    if pool.latent_len != 1 or getattr(pool, "pos_embed", None) is not None or pool.pool != "token":
-        raise B200Error("AttentionPoolLatent: only latent_len=1, no position embedding, token pooling is covered")
-    if not _is_identity(pool.q_norm) or not _is_identity(pool.k_norm):
-        raise B200Error("AttentionPoolLatent with qk_norm is not covered")
-    if pool.head_dim != 64:
-        raise B200Error(f"head_dim {pool.head_dim} is not supported (64 only)")
+    """AttentionPoolLatent.forward (timm/layers/attention_pool.py:95-128; SigLIP's 'map' head with one latent, or several):
+    latents -> q projection; tokens (+ optional position embedding) -> kv projection; L-query attention on the
+    self-attention kernels (autograd.AttnPoolFn); proj; x + mlp(norm(x)); 'token' / 'avg' / no pooling over the latents."""
+    if pool.pool not in ("token", "avg", ""):
+        raise B200Error(f"AttentionPoolLatent: pool={pool.pool!r} is not covered")
+    qk_norm = not _is_identity(pool.q_norm) or not _is_identity(pool.k_norm)
+    H, hd = pool.num_heads, pool.head_dim
+    head_pad(hd)
+    if hd != 64 and qk_norm:
+        raise B200Error("qk_norm with head_dim != 64 is not covered")
     _check_drop(getattr(pool, "proj_drop", None), "proj_drop")
     B, N, D = x.shape
+    Dp = H * 64
+    L = pool.latent_len
+    if L > N:
+        raise B200Error("AttentionPoolLatent: more latent queries than tokens is not covered")
     _bf16_2d(x, D)
-    latent = pool.latent.reshape(1, D)
-    q = _linear(pool.q, latent if latent.dtype == torch.bfloat16 else latent.to(torch.bfloat16))
+    if getattr(pool, "pos_embed", None) is not None:
+        x = x + pool.pos_embed.unsqueeze(0).to(x.dtype)                  # attention_pool.py:97-99, a [N, D] table
+    latent = pool.latent.reshape(L, D)
+    latent = latent if latent.dtype == torch.bfloat16 else latent.to(torch.bfloat16)
+    wq, bq = head_padded_linear_in(pool.q, 1, H, hd)
+    wkv, bkv = head_padded_linear_in(pool.kv, 2, H, hd)
     if _needs_grad(x, pool):
-        from .autograd import AttnPoolFn
-        o = AttnPoolFn.apply(x, q, _w(pool.kv), pool.kv.bias, pool.num_heads, pool.scale)
+        if qk_norm:
+            raise B200Error("AttentionPoolLatent with qk_norm: the backward is not covered")
+        from .autograd import AttnPoolFn, LinearFn
+        q = LinearFn.apply(latent, wq, bq)
+        o = AttnPoolFn.apply(x, q, wkv, bkv, H, pool.scale)
     else:
-        qkv = torch.zeros(B * N, 3 * D, dtype=torch.bfloat16, device=x.device)
-        ops.linear_fwd(_bf16_2d(x, D), _w(pool.kv), pool.kv.bias, out=qkv[:, D:])
-        qkv.view(B, N, 3 * D)[:, 0, :D] = q.reshape(1, D)
-        o = ops.attention_fwd(qkv, B, N, pool.num_heads, 64, pool.scale, None)[0][:, 0].contiguous()
-    if _is_identity(pool.proj):
-        return o
-    o = _linear(pool.proj, o)
+        q = ops.linear_fwd(latent.contiguous(), wq, bq)
+        qkv = torch.zeros(B * N, 3 * Dp, dtype=torch.bfloat16, device=x.device)
+        ops.linear_fwd(_bf16_2d(x, D), wkv, bkv, out=qkv[:, Dp:])
+        qkv.view(B, N, 3 * Dp)[:, :L, :Dp] = q.reshape(1, L, Dp)
+        if qk_norm:       # q_norm / k_norm over head_dim (:107): in place on the q and k thirds (the unused query rows too)
+            (qw, qb, qe), (kw, kb, ke) = _ln_params(pool.q_norm), _ln_params(pool.k_norm)
+            if float(qe) != float(ke) or (qb is None) != (kb is None):
+                raise B200Error("q_norm / k_norm need equal eps and affine parameters")
+            ops.qk_norm_fwd(qkv, B * N, H, qw, qb, kw, kb, qe)
+        o = ops.attention_fwd(qkv, B, N, H, 64, pool.scale, None)[0][:, :L].contiguous()
+    if not _is_identity(pool.proj):
+        wp = head_padded_linear_out(pool.proj, H, hd)
+        if _needs_grad(o, pool.proj):
+            from .autograd import LinearFn
+            o = LinearFn.apply(o, wp, pool.proj.bias)
+        else:
+            o = ops.linear_fwd(o.reshape(-1, Dp), wp, pool.proj.bias).view(B, L, -1)
+    elif hd != 64:
+        o = o.view(B, L, H, 64)[..., :hd].reshape(B, L, D)
     if pool.mlp is not None:
         h = o if _is_identity(pool.norm) else layernorm(pool.norm, o)
         o = o + mlp_forward(pool.mlp, h)
+    if pool.pool == "token":
+        return o[:, 0]
+    if pool.pool == "avg":
+        return o.float().mean(1).to(o.dtype)
+    return o
+
+
+def attention_pool_prr_forward(pool, x):
+    """AttentionPoolPrr.forward (timm/layers/attention_pool.py:172-195): pre_norm -> parameter-free multi-head self-attention
+    (q = k = v = the normalised tokens) -> post_norm -> 'token' / 'avg' pooling.  The tokens are packed three times into
+    the [B, N, 3, H, 64] layout the attention kernels read (a data-movement cat; its autograd adds dq + dk + dv)."""
+    B, N, D = x.shape
+    H, hd = pool.num_heads, pool.head_dim
+    head_pad(hd)
+    _bf16_2d(x, D)
+    h = x if _is_identity(pool.pre_norm) else layernorm(pool.pre_norm, x)
+    hp = h if hd == 64 else F.pad(h.reshape(B, N, H, hd), (0, 64 - hd)).reshape(B, N, H * 64)
+    o = sdpa_packed(torch.cat([hp, hp, hp], dim=-1), H, pool.scale)
+    if hd != 64:
+        o = o.view(B, N, H, 64)[..., :hd].reshape(B, N, D)
+    o = o if _is_identity(pool.post_norm) else layernorm(pool.post_norm, o)
+    if pool.pool == "token":
+        return o[:, 0]
+    if pool.pool == "avg":
+        return o.float().mean(1).to(o.dtype)
     return o
 
 
 def vit_pool(model, x):
     """VisionTransformer.pool / global_pool_nlc (:686-708, :1254-1277) for token / avg pooling."""
     if getattr(model, "attn_pool", None) is not None:                     # :1265-1269
-        if type(model.attn_pool).__name__ != "AttentionPoolLatent":
-            raise B200Error(f"{type(model.attn_pool).__name__} pooling is not supported")
+        kind = type(model.attn_pool).__name__
+        if kind not in ("AttentionPoolLatent", "AttentionPoolPrr"):
+            raise B200Error(f"{kind} pooling is not supported")
         if not getattr(model, "pool_include_prefix", False) and model.num_prefix_tokens:
             x = x[:, model.num_prefix_tokens:].contiguous()
-        return attention_pool_forward(model.attn_pool, x)
+        return attention_pool_forward(model.attn_pool, x) if kind == "AttentionPoolLatent" else \
+            attention_pool_prr_forward(model.attn_pool, x)
     pool = model.global_pool
     if pool == "token":
         return x[:, 0]

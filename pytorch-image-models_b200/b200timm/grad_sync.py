@@ -51,6 +51,46 @@ def _get(module, dotted):
     return obj if isinstance(obj, torch.nn.Parameter) else None
 
 
+def _fused_block(m):
+    """True when functional.block_forward drives module `m` through autograd.BlockFn (whose backward pushes the slot)."""
+    from . import functional as BF
+    try:
+        if BF.is_parallel_block(m) or BF.is_glu(m.mlp) or m.attn.head_dim != 64:
+            return False
+        qk, sn = BF._attn_norms(m.attn)
+        if qk is not None or sn is not None or not BF._is_identity(getattr(m.mlp, "norm", None)):
+            return False
+        BF.check_attention(m.attn)
+        BF.check_mlp(m.mlp)
+        BF._ln_params(m.norm1), BF._ln_params(m.norm2)
+        return True
+    except (B200Error, AttributeError):
+        return False
+
+
+def plan_layout(model):
+    """(slots, tail, tail_offset, total): the flat gradient buffer's layout.  slots: id(first block parameter) -> (element
+    offset, the block's 14 parameters in BlockFn's workspace order (None = absent), padded size); every BlockFn-driven
+    block first, in module order, each parameter at an 8-element (16-byte) aligned offset; then the remaining trainable
+    parameters ("tail") from `tail_offset`.  Pure host logic (no CUDA, no process group)."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    slots, taken, off = {}, set(), 0
+    for m in model.modules():
+        ps = [_get(m, name) for name in BLOCK_PARAM_ORDER]
+        if ps[2] is None or ps[4] is None or ps[8] is None or ps[10] is None or ps[0] is None or ps[6] is None:
+            continue
+        if any(p is not None and (id(p) in taken or not p.requires_grad) for p in ps):
+            continue
+        if not _fused_block(m):     # variants that do not run autograd.BlockFn keep their gradients on the tail path
+            continue
+        size = sum(_pad8(p.numel()) for p in ps if p is not None)
+        slots[id(ps[0])] = (off, ps, size)
+        taken.update(id(p) for p in ps if p is not None)
+        off += size
+    tail = [p for p in params if id(p) not in taken]
+    return slots, tail, off, off + sum(_pad8(p.numel()) for p in tail)
+
+
 def grad_push(src, dst_multicast_ptr, n, scale):
     """dst[i] += bf16(src[i] * scale) on every rank (src fp32 / bf16 CUDA tensor, n a multiple of 8)."""
     if not src.is_cuda or not src.is_contiguous() or src.dtype not in (torch.float32, torch.bfloat16):
@@ -72,24 +112,9 @@ class PeerGradSync:
         if not params or any(p.dtype != torch.bfloat16 or not p.is_cuda for p in params):
             raise B200Error("PeerGradSync covers CUDA models with bf16 parameters (benchmark.py --precision bfloat16)")
         self.device = params[0].device
-        # ---- layout: block slots first, in module order; then the tail
-        self.slots = {}                 # id(first parameter of a block) -> (offset, [param or None] * 14, padded size)
-        taken = set()
-        off = 0
-        for m in model.modules():
-            ps = [_get(m, name) for name in BLOCK_PARAM_ORDER]
-            if ps[2] is None or ps[4] is None or ps[8] is None or ps[10] is None or ps[0] is None or ps[6] is None:
-                continue
-            if any(p is not None and (id(p) in taken or not p.requires_grad) for p in ps):
-                continue
-            size = sum(_pad8(p.numel()) for p in ps if p is not None)
-            self.slots[id(ps[0])] = (off, ps, size)
-            taken.update(id(p) for p in ps if p is not None)
-            off += size
-        self.tail_offset = off
-        self.tail = [p for p in params if id(p) not in taken]
-        tail_size = sum(_pad8(p.numel()) for p in self.tail)
-        self.total = off + tail_size
+        self.slots, self.tail, self.tail_offset, self.total = plan_layout(model)
+        off = self.tail_offset
+        tail_size = self.total - off
         # ---- the symmetric flat buffer and its multicast address
         self.flat = symm.empty(self.total, dtype=torch.bfloat16, device=self.device)
         self.handle = symm.rendezvous(self.flat, self.group.group_name if hasattr(self.group, "group_name") else self.group)

@@ -653,6 +653,20 @@ def glu_bwd(h, dout, gate_first, act="silu"):
     return dh
 
 
+def act_bwd(dy, pre, act=0):
+    """dy * act'(pre) elementwise (bf16, contiguous, equal shapes): Mlp activation backward when an inner norm separates
+    the activation from fc2 (otherwise it rides in the fc2-dgrad GEMM epilogue)."""
+    _need_cuda(dy, pre)
+    if dy.dtype != torch.bfloat16 or pre.dtype != torch.bfloat16 or dy.shape != pre.shape or not dy.is_contiguous() \
+            or not pre.is_contiguous() or dy.numel() % 8:
+        raise B200Error("act_bwd: need two contiguous bf16 tensors of equal shape, element count a multiple of 8")
+    out = torch.empty_like(pre)
+    rc = _lib.load().b200_act_bwd(dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(), int(act), _stream())
+    _lib.check(rc, "b200_act_bwd")
+    _count()
+    return out
+
+
 # --------------------------------------------------------------------------------------------- NaFlex
 def naflex_assemble(proj, prefix, table, pos_off, pos_len, B, N, n_prefix, D):
     """tokens [B, n_prefix+N, D] = cat(prefix, proj + per-sample interpolated position rows)."""

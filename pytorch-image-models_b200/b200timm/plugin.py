@@ -164,6 +164,25 @@ def _attention_rope(self, x, rope=None, attn_mask=None, is_causal=False):
     return BF.attention_rope_forward(self, x, rope, _kv_len(attn_mask, x.shape[1], x.shape[0]))
 
 
+def _patch_embed(self, x):
+    """PatchEmbed.forward (patch_embed.py:117-142) in every output format: the GEMM emits token-major rows [B, G, D], which IS
+    the NLC result (flatten=True) and, viewed [B, gh, gw, D], the NHWC one; NCHW is a permuted view of that."""
+    y = BF.patch_embed_forward(self, x)                      # [B, G, D]
+    if self.flatten:
+        return y
+    ph, pw = self.patch_size
+    H, W = x.shape[-2], x.shape[-1]
+    if getattr(self, "dynamic_img_pad", False):
+        H, W = H + (ph - H % ph) % ph, W + (pw - W % pw) % pw
+    y = y.view(y.shape[0], H // ph, W // pw, y.shape[-1])
+    fmt = getattr(self.output_fmt, "value", str(self.output_fmt))
+    if fmt == "NHWC":
+        return y
+    if fmt == "NCHW":
+        return y.permute(0, 3, 1, 2)
+    raise B200Error(f"PatchEmbed output format {fmt} is not covered")
+
+
 def _vit_features(self, x, attn_mask=None, is_causal=False):
     if is_causal:
         raise B200Error("causal forward_features is not covered")
@@ -255,14 +274,15 @@ def _install_training_tail():
 def _table():
     """(qualified name, class, attribute, fast function) of every forward the plugin covers."""
     from timm.layers.attention import Attention, AttentionRope
-    from timm.layers.attention_pool import AttentionPoolLatent
+    from timm.layers.attention_pool import AttentionPoolLatent, AttentionPoolPrr
     from timm.layers.mlp import GluMlp, Mlp, SwiGLU
     from timm.layers.norm import LayerNorm, RmsNorm
     from timm.layers.patch_embed import PatchEmbed
     from timm.models.convnext import ConvNeXt, ConvNeXtBlock
     from timm.models.eva import EvaAttention
-    from timm.models.vision_transformer import Block, VisionTransformer
+    from timm.models.vision_transformer import Block, ParallelScalingBlock, VisionTransformer
     return [
+        ("timm.models.vision_transformer.ParallelScalingBlock.forward", ParallelScalingBlock, "forward", _block),
         ("timm.layers.LayerNorm.forward", LayerNorm, "forward", lambda self, x: BF.layernorm(self, x)),
         ("timm.layers.RmsNorm.forward", RmsNorm, "forward", lambda self, x: BF.layernorm(self, x)),
         ("timm.layers.Mlp.forward", Mlp, "forward", lambda self, x: BF.mlp_forward(self, x)),
@@ -274,8 +294,9 @@ def _table():
         ("timm.layers.Attention.forward", Attention, "forward", _attention),
         ("timm.layers.AttentionRope.forward", AttentionRope, "forward", _attention_rope),
         ("timm.models.eva.EvaAttention.forward", EvaAttention, "forward", _attention_rope),
-        ("timm.layers.PatchEmbed.forward", PatchEmbed, "forward",
-         lambda self, x: BF.patch_embed_forward(self, x) if self.flatten else (_ for _ in ()).throw(B200Error("NHWC"))),
+        ("timm.layers.PatchEmbed.forward", PatchEmbed, "forward", _patch_embed),
+        ("timm.layers.AttentionPoolPrr.forward", AttentionPoolPrr, "forward",
+         lambda self, x: BF.attention_pool_prr_forward(self, x)),
         ("timm.models.vision_transformer.Block.forward", Block, "forward", _block),
         ("timm.models.vision_transformer.VisionTransformer.forward_features", VisionTransformer, "forward_features",
          _vit_features),

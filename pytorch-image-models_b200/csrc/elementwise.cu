@@ -3,6 +3,7 @@
 #include "common.h"
 #include <string.h>
 #include "ptx.cuh"
+#include "gelu.cuh"
 
 namespace b200 {
 
@@ -468,9 +469,44 @@ __global__ void glu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_b
   }
 }
 
+// dpre = dy * act'(pre): the activation backward of an Mlp whose activation output does not feed fc2 directly (an inner
+// norm sits in between: Mlp(norm_layer=...), timm/layers/mlp.py:44-53 `scale_mlp_norm`) -- otherwise GELU' rides in the
+// fc2-dgrad GEMM epilogue.  act: 0 exact GELU, 1 tanh GELU, 2 SiLU (gelu.cuh).
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pre,
+                               __nv_bfloat16* __restrict__ dpre, long long nvec, int act) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy) + i), x = __ldg(reinterpret_cast<const uint4*>(pre) + i);
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, xw[4] = {x.x, x.y, x.z, x.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float lo, hi;
+      upk(mul2(bf16x2_to_f32x2(gw[k]), act_bwd2(bf16x2_to_f32x2(xw[k]), act)), lo, hi);
+      o[k] = pack_bf16(lo, hi);
+    }
+    reinterpret_cast<uint4*>(dpre)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_act_bwd(const void* dy, const void* pre, void* dpre, int64_t n, int32_t act, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(dy && pre && dpre && n > 0 && n % 8 == 0, "b200_act_bwd: null pointer or n not a positive multiple of 8");
+  B200_CHECK_ARG(act >= 0 && act <= 2, "b200_act_bwd: bad activation %d", act);
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  act_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                 reinterpret_cast<const __nv_bfloat16*>(pre),
+                                                                 reinterpret_cast<__nv_bfloat16*>(dpre), nvec, act);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
 
 extern "C" int b200_patchify(const void* img, void* patches, int32_t B, int32_t C, int32_t H, int32_t W, int32_t p,
                              int32_t Kpad, int32_t img_dtype, void* stream_) {

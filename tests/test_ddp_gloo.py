@@ -74,4 +74,35 @@ def test_reference_arm_prints_once_under_two_ranks():
     assert len(outs[0]) == 1 and outs[1] == []
     line = json.loads(outs[0][0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["unit"] == "img/s"
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # oracle/_ref installed (this container, the GPU box): the unmodified benchmark.py is the reference arm
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "infer" in line or line["cpu_baseline"]["kind"] == "port"
+
+
+def test_peer_grad_sync_layout_covers_every_parameter_once():
+    """b200timm.grad_sync.plan_layout on the product model (host logic, no GPU): every transformer block that BlockFn drives
+    owns one slot whose parameters sit at 16-byte aligned offsets in BlockFn's workspace order (so that ONE kernel converts
+    and pushes a block's gradient workspace), every other trainable parameter is in the tail, nothing is counted twice;
+    variant blocks (qk-norm: not BlockFn) fall back to the tail."""
+    sys.path.insert(0, os.path.join(ROOT, "pytorch-image-models_b200"))
+    from b200timm.grad_sync import BLOCK_PARAM_ORDER, plan_layout
+    from b200timm.vision_transformer import VisionTransformer
+    model = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=3, num_heads=2, num_classes=10, init_values=0.1)
+    slots, tail, tail_off, total = plan_layout(model)
+    assert len(slots) == 3
+    seen, expect = set(), 0
+    for off, ps, size in sorted(slots.values(), key=lambda s: s[0]):
+        assert off == expect and size % 8 == 0 and len(ps) == len(BLOCK_PARAM_ORDER)
+        o = off
+        for p in ps:
+            assert p is not None and o % 8 == 0 and id(p) not in seen
+            seen.add(id(p))
+            o += (p.numel() + 7) // 8 * 8
+        assert o == off + size
+        expect = off + size
+    assert tail_off == expect and not (seen & {id(p) for p in tail})
+    assert seen | {id(p) for p in tail} == {id(p) for p in model.parameters()}
+    assert total == tail_off + sum((p.numel() + 7) // 8 * 8 for p in tail)
+    qk = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, num_classes=10, qk_norm=True)
+    slots, tail, _, _ = plan_layout(qk)
+    assert not slots and len(tail) == len(list(qk.parameters()))

@@ -123,7 +123,11 @@ def _env(report=None, **extra):
 
 TIMM_TESTS = ["test_model_forward[1-vit_base_patch16_224]", "test_model_backward[2-vit_base_patch16_224]",
               "test_model_forward_intermediates[1-vit_base_patch16_224]", "test_model_forward[1-convnext_base]",
-              "test_model_backward[2-convnext_base]", "test_model_forward[1-vit_large_patch14_clip_336]"]
+              "test_model_backward[2-convnext_base]", "test_model_forward[1-vit_large_patch14_clip_336]",
+              "test_model_forward[1-test_vit]", "test_model_backward[2-test_vit]", "test_model_forward[1-test_vit2]",
+              "test_model_backward[2-test_vit2]", "test_model_forward[1-test_vit3]", "test_model_backward[2-test_vit3]",
+              "test_model_forward[1-test_vit4]", "test_model_backward[2-test_vit4]",
+              "test_model_forward_intermediates[1-test_vit]", "test_model_forward[1-vit_pwee_patch16_reg1_gap_256]"]
 
 
 def test_timms_own_tests_through_the_torch_backend_hook(tmp_path):
@@ -133,7 +137,9 @@ def test_timms_own_tests_through_the_torch_backend_hook(tmp_path):
     cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", "--rootdir", os.path.join(install_ref.TARGET, "tests")]
     cmd += [f"{tests}::{t}" for t in TIMM_TESTS]
     rc, out = _run(cmd, _env(report, TORCH_BACKEND="b200timm.plugin", TORCH_DEVICE="cuda", B200TIMM_FP32="bf16"))
-    assert rc == 0, out[-3000:]
+    if rc != 0:
+        print(out[-6000:])
+    assert rc == 0, out[-1500:]
     st = json.load(open(report))
     assert st["kernel_launches"] > 1000 and not st["deferred"], st
     for fwd in ("timm.models.vision_transformer.VisionTransformer.forward", "timm.models.convnext.ConvNeXt.forward"):
@@ -154,3 +160,82 @@ def test_unmodified_benchmark_py_through_the_launcher(tmp_path):
     st = json.load(open(report))
     assert st["kernel_launches"] > 500 and not st["deferred"], st
     assert st["fast"].get("timm.models.vision_transformer.VisionTransformer.forward", 0) >= 14, st["fast"]
+
+
+# ------------------------------------------------------------------------------------------------ variants
+def _compare_module(plugin, build, make_input, grad=True, tol=2e-2, gtol=6e-2, call=None):
+    """The same timm module: fp32 on the CPU (timm's forward: the plugin passes CPU tensors through) vs bf16 on the GPU through
+    the plugin (strict: nothing may be deferred).  Output within tol + tol * |ref|, parameter gradients within gtol."""
+    from b200timm import ops
+    torch.manual_seed(0)
+    m = build()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(p.bfloat16().float())
+    m.train(grad)
+    x = make_input()
+    call = call or (lambda mod, inp: mod(inp))
+    ctx = torch.enable_grad() if grad else torch.no_grad()
+    with ctx:
+        ref = call(m, x)
+        if grad:
+            w = torch.randn_like(ref)
+            (ref * w).sum().backward()
+            ref_grads = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+            m.zero_grad(set_to_none=True)
+    m = m.cuda().to(torch.bfloat16)
+    plugin.reset_stats()
+    ops.reset_counters()
+    with ctx:
+        out = call(m, x.cuda().bfloat16())
+        if grad:
+            (out.float() * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    st = plugin.stats()
+    assert st["kernel_launches"] > 0 and st["fast"], st
+    assert not st["deferred"], f"deferred to PyTorch: {st['deferred']}"
+    got, ref = out.float().cpu(), ref.detach()
+    assert ((got - ref).abs() <= tol + tol * ref.abs()).all(), f"output: max err {(got - ref).abs().max():.4g} (|ref| max {ref.abs().max():.3g})"
+    if grad:
+        scale = max(g.norm().item() for g in ref_grads.values())
+        for n, p in m.named_parameters():
+            if n in ref_grads and ref_grads[n].norm().item() > 1e-3 * scale:
+                assert p.grad is not None, f"no gradient for {n}"
+                e = (p.grad.float().cpu() - ref_grads[n]).norm().item() / ref_grads[n].norm().item()
+                assert e <= gtol, f"gradient of {n}: relative error {e:.3g}"
+
+
+VARIANT_MODELS = [
+    ("test_vit", {}, 160),                      # head_dim 32 (heads padded to 64 inside the weights), dynamic_img_size
+    ("test_vit2", {}, 160),                     # + register token, avg pool, LayerScale
+    ("test_vit3", {}, 160),                     # + 'map' pool (AttentionPoolLatent, head_dim 32), pool_include_prefix
+    ("test_vit4", {}, 160),                     # + RmsNorm
+    ("vit_pwee_patch16_reg1_gap_256", {"depth": 3}, 256),                                   # ParallelScalingBlock
+    ("vit_base_patch16_xp_224", {"depth": 2}, 224),                                         # parallel block + qk-norm + RmsNorm
+    ("vit_base_patch16_224", {"depth": 2, "scale_mlp_norm": True, "scale_attn_norm": True, "norm_layer": "layernorm"}, 224),
+    ("vit_base_patch16_224", {"depth": 2, "global_pool": "prr", "class_token": False}, 224),
+]
+
+
+@pytest.mark.parametrize("name,kw,size", VARIANT_MODELS, ids=[f"{m[0]}{'+' + '+'.join(m[1]) if m[1] else ''}" for m in VARIANT_MODELS])
+@pytest.mark.parametrize("grad", [False, True], ids=["infer", "train"])
+def test_variant_models_through_plugin(plugin, name, kw, size, grad):
+    _compare_module(plugin, lambda: timm.create_model(name, num_classes=50, **kw),
+                    lambda: torch.randn(2, 3, size, size).bfloat16().float(), grad=grad)
+
+
+def test_attention_pool_variants_and_patch_embed_formats(plugin):
+    from timm.layers import AttentionPoolLatent, AttentionPoolPrr, LayerNorm, PatchEmbed
+    tok = lambda: torch.randn(3, 50, 128).bfloat16().float()   # noqa: E731
+    for grad in (False, True):
+        _compare_module(plugin, lambda: AttentionPoolLatent(128, num_heads=2, latent_len=4, pool_type="avg", norm_layer=LayerNorm),
+                        tok, grad=grad)
+        _compare_module(plugin, lambda: AttentionPoolLatent(128, num_heads=4, latent_len=2, pool_type="token", norm_layer=LayerNorm),
+                        tok, grad=grad)                                      # head_dim 32
+        _compare_module(plugin, lambda: AttentionPoolPrr(128, num_heads=2, pool_type="avg", pre_norm=True, post_norm=True), tok,
+                        grad=grad)
+    _compare_module(plugin, lambda: AttentionPoolLatent(128, num_heads=2, qk_norm=True, norm_layer=LayerNorm), tok, grad=False)
+    img = lambda: torch.randn(2, 3, 60, 70).bfloat16().float()   # noqa: E731
+    for fmt in ("NHWC", "NCHW"):
+        _compare_module(plugin, lambda: PatchEmbed(img_size=None, patch_size=16, embed_dim=64, flatten=False, output_fmt=fmt,
+                                                   strict_img_size=False, dynamic_img_pad=True), img, grad=True)
