@@ -100,9 +100,11 @@ B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);
 /* In-place rotary embedding of the q and k thirds of a fused QKV activation qkv[B*N, 3*H*64] (bf16); replaces
  * apply_rot_embed_cat at timm/layers/attention.py:249-253 (pos_embed_sincos.py:227-297).  emb: fp32 [N - num_prefix, 128]
  * = [sin | cos].  half_layout: 0 = interleaved pairs (`rot`), 1 = `rope_rotate_half`.  inverse = 1 applies the
- * transposed map (the backward of the rotation, run on the q / k thirds of d(qkv)). */
+ * transposed map (the backward of the rotation, run on the q / k thirds of d(qkv)).
+ * per_sample (ABI >= 6): 0 = one table for all samples; 1 = emb is [B, N - num_prefix, 128], sample b uses emb[b] (the
+ * [B, 1, N, 2 * head_dim] rope of NaFlex / variable-grid batches, attention.py:243-253). */
 B200_API int b200_rope_qk(void* qkv, const float* emb, int32_t B, int32_t N, int32_t H, int32_t num_prefix,
-                          int32_t half_layout, int32_t inverse, void* stream);
+                          int32_t half_layout, int32_t inverse, int32_t per_sample, void* stream);
 
 /* Debug hook (tools/gemm_trace.py, tools/attn_trace.py), not part of the reference-facing surface.  kernel 0 = b200_gemm:
  * with a non-NULL `device_buf` (>= 12 * #SMs uint64, zeroed by the caller) every following launch records per-CTA

@@ -78,7 +78,7 @@ SIGNATURES = {
     "b200_device_check": (ctypes.c_int, []),
     "b200_gemm": (ctypes.c_int, [ctypes.POINTER(GemmDesc), _vp]),
     "b200_set_trace": (None, [_i32, _vp]),
-    "b200_rope_qk": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200_rope_qk": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_layernorm_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),
     "b200_layernorm_bwd_ws_rows": (ctypes.c_int, [_i64, _i32]),
     "b200_layernorm_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),

@@ -446,7 +446,10 @@ class AttentionNormFn(torch.autograd.Function):
     qk = (q_weight, q_bias, k_weight, k_bias, eps) or None; sn = (weight, bias, eps) or None (eps may be an RmsEps)."""
 
     @staticmethod
-    def forward(ctx, x, wqkv, bqkv, wproj, bproj, qw, qb, kw, kb, nw, nb, kv_len, num_heads, scale, qk_eps, sn_eps):
+    def forward(ctx, x, wqkv, bqkv, wproj, bproj, qw, qb, kw, kb, nw, nb, kv_len, num_heads, scale, qk_eps, sn_eps,
+                emb=None, npt=0, half=False):
+        """emb (optional): rotary table, fp32 [N - npt, 128] or per-sample [B, N - npt, 128]; q / k are rotated AFTER their
+        normalisation (AttentionRope / EvaAttention order, attention.py:241-253); the saved qkv holds the rotated q / k."""
         B, N, C = x.shape
         hd = wqkv.shape[0] // 3 // num_heads
         x2 = _c(x.reshape(B * N, C))
@@ -454,6 +457,8 @@ class AttentionNormFn(torch.autograd.Function):
         raw = qmean = qrstd = None
         if qw is not None:
             raw, qmean, qrstd = ops.qk_norm_fwd(qkv, B * N, num_heads, qw, qb, kw, kb, qk_eps, save=True)
+        if emb is not None:
+            ops.rope_qk(qkv, emb, B, N, num_heads, npt, half=half)
         o, lse = ops.attention_fwd(qkv, B, N, num_heads, hd, scale, kv_len, need_lse=True)
         o2 = o.view(B * N, -1)
         on, nmean, nrstd = o2, None, None
@@ -461,15 +466,15 @@ class AttentionNormFn(torch.autograd.Function):
             on, nmean, nrstd = ops.layernorm_fwd(o2, nw, nb, sn_eps, save_stats=True)
         y = ops.linear_fwd(on, wproj, bproj)
         ctx.save_for_backward(x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len, raw, qmean, qrstd, qw, qb, kw, kb, on, nmean,
-                              nrstd, nw, nb)
-        ctx.meta = (B, N, num_heads, hd, scale)
+                              nrstd, nw, nb, emb)
+        ctx.meta = (B, N, num_heads, hd, scale, npt, half)
         return y.view(B, N, -1)
 
     @staticmethod
     def backward(ctx, dy):
         (x2, wqkv, bqkv, wproj, bproj, qkv, o, lse, kv_len, raw, qmean, qrstd, qw, qb, kw, kb, on, nmean, nrstd, nw,
-         nb) = ctx.saved_tensors
-        B, N, H, hd, scale = ctx.meta
+         nb, emb) = ctx.saved_tensors
+        B, N, H, hd, scale, npt, half = ctx.meta
         dy2 = _c(dy.reshape(B * N, -1))
         o2 = o.view(B * N, -1)
         do = ops.linear_dgrad(dy2, wproj)
@@ -479,6 +484,8 @@ class AttentionNormFn(torch.autograd.Function):
             gnw = _to_param_dtype(dnw, nw)
             gnb = None if nb is None else _to_param_dtype(dnb, nb)
         dqkv = ops.attention_bwd(qkv, o, _c(do).view(B, N, -1), lse, B, N, H, hd, scale, kv_len).view(B * N, -1)
+        if emb is not None:
+            ops.rope_qk(dqkv, emb, B, N, H, npt, half=half, inverse=True)
         gq = [None] * 4
         if qw is not None:
             dp = ops.qk_norm_bwd(dqkv, raw, qmean, qrstd, qw, kw, B * N, H)
@@ -486,7 +493,7 @@ class AttentionNormFn(torch.autograd.Function):
                   _to_param_dtype(dp[2].contiguous(), kw), None if kb is None else _to_param_dtype(dp[3].contiguous(), kb)]
         dx = ops.linear_dgrad(dqkv, wqkv).view(B, N, -1)
         return (dx, _wgrad(dqkv, x2, wqkv), _bias_grad(dqkv, bqkv), _wgrad(dy2, on, wproj), _bias_grad(dy2, bproj),
-                gq[0], gq[1], gq[2], gq[3], gnw, gnb, None, None, None, None, None)
+                gq[0], gq[1], gq[2], gq[3], gnw, gnb, None, None, None, None, None, None, None, None)
 
 
 class AttnPoolFn(torch.autograd.Function):

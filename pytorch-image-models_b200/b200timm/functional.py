@@ -295,17 +295,23 @@ def attention_forward(attn, x, kv_len=None, residual=None, gamma=None):
     return y.view(B, N, -1)
 
 
-def _rope_table(rope, n_rot, head_dim, device):
-    """The `rope` argument of AttentionRope.forward -> contiguous fp32 [n_rot, 2 * head_dim] = [sin | cos] on `device`
-    (the reference broadcasts `emb` against q[B, H, n_rot, hd]; a per-sample [B, 1, N, 2 hd] table is not covered)."""
+def _rope_table(rope, n_rot, head_dim, device, batch=None):
+    """The `rope` argument of AttentionRope.forward -> contiguous fp32 [n_rot, 2 * head_dim] = [sin | cos] on `device`, or
+    [B, n_rot, 2 * head_dim] for a per-sample table (the reference broadcasts `emb` against q[B, H, n_rot, hd]: shapes
+    [n_rot, 2 hd], [1, 1, n_rot, 2 hd] or [B, 1, n_rot, 2 hd], pos_embed_sincos.py:281-297)."""
     if head_dim != 64:
         raise B200Error("AttentionRope: only head_dim 64 is covered")
     r = rope
+    if r.dim() == 4 and r.shape[1] == 1:
+        r = r[:, 0]
     while r.dim() > 2 and r.shape[0] == 1:
         r = r[0]
-    if r.dim() != 2 or tuple(r.shape) != (n_rot, 2 * head_dim):
-        raise B200Error(f"AttentionRope: rope must broadcast from [{n_rot}, {2 * head_dim}], got {tuple(rope.shape)}")
-    key = (*ops.wkey(rope), str(device))
+    if r.dim() == 3 and batch is not None and tuple(r.shape) == (batch, n_rot, 2 * head_dim):
+        pass
+    elif r.dim() != 2 or tuple(r.shape) != (n_rot, 2 * head_dim):
+        raise B200Error(f"AttentionRope: rope must broadcast from [{n_rot}, {2 * head_dim}] (or [B, 1, {n_rot}, {2 * head_dim}]), "
+                        f"got {tuple(rope.shape)}")
+    key = (*ops.wkey(rope), str(device), tuple(r.shape))
     cache = _rope_table.cache
     if cache.get("key") != key:
         cache["key"], cache["val"] = key, r.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -315,35 +321,72 @@ def _rope_table(rope, n_rot, head_dim, device):
 _rope_table.cache = {}
 
 
-def _qkv_bias(attn):
-    """AttentionRope keeps the bias on `qkv`; EvaAttention (timm/models/eva.py:157-165, 209-217) keeps q_bias / v_bias
-    parameters and a zero k_bias buffer and concatenates them per call -- same here (autograd splits the gradient)."""
-    if getattr(attn, "q_bias", None) is not None:
-        return torch.cat((attn.q_bias, attn.k_bias, attn.v_bias))
-    return attn.qkv.bias
+def _qkv_params(attn):
+    """(weight [3A, C] bf16, bias [3A] or None) of the q / k / v projection(s) of AttentionRope / EvaAttention: the fused `qkv`
+    Linear (EvaAttention keeps q_bias / v_bias parameters and a zero k_bias buffer, eva.py:157-165, 209-217), or -- for
+    `qkv_fused=False` -- q_proj / k_proj / v_proj stacked into one [3A, C] operand (a differentiable cat of the WEIGHTS in
+    training, cached otherwise), so that one GEMM produces the packed [M, 3A] buffer the attention kernels read."""
+    if attn.qkv is not None:
+        if getattr(attn, "q_bias", None) is not None:
+            return _w(attn.qkv), torch.cat((attn.q_bias, attn.k_bias, attn.v_bias))
+        return _w(attn.qkv), attn.qkv.bias
+    lins = (attn.q_proj, attn.k_proj, attn.v_proj)
+    ws = [_w(l) for l in lins]
+    bs = [l.bias for l in lins]
+    has_bias = any(b is not None for b in bs)
+
+    def cat_bias():
+        ref = next(b for b in bs if b is not None)
+        return torch.cat([b if b is not None else torch.zeros(l.weight.shape[0], dtype=ref.dtype, device=ref.device)
+                          for b, l in zip(bs, lins)])
+    if torch.is_grad_enabled() and any(w.requires_grad for w in ws):
+        return torch.cat(ws, 0), (cat_bias() if has_bias else None)
+    key = tuple(ops.wkey(w) for w in ws) + tuple(None if b is None else ops.wkey(b) for b in bs)
+    return _cached(attn, "_b200_qkvcat", key, lambda: (torch.cat([w.detach() for w in ws], 0).contiguous(),
+                                                       cat_bias().detach() if has_bias else None))
 
 
 def attention_rope_forward(attn, x, rope=None, kv_len=None):
-    """AttentionRope.forward (timm/layers/attention.py:224-282) and EvaAttention.forward (timm/models/eva.py:197-262,
-    fused qkv, no qk-norm / scale-norm): fused QKV projection + rotary embedding of q / k (all tokens after the first
-    num_prefix_tokens) + attention + output projection."""
-    if (attn.qkv is None or not isinstance(attn.q_norm, nn.Identity) or not isinstance(attn.k_norm, nn.Identity)
-            or not isinstance(attn.norm, nn.Identity) or (attn.training and (attn.attn_drop.p > 0 or attn.proj_drop.p > 0))):
-        raise B200Error("AttentionRope: separate q/k/v projections, qk-norm, scale-norm and dropout are not covered")
+    """AttentionRope.forward (timm/layers/attention.py:224-282) and EvaAttention.forward (timm/models/eva.py:197-262): QKV
+    projection (fused or separate q / k / v), optional q / k normalisation, rotary embedding of q / k (all tokens after the
+    first num_prefix_tokens; one table for the batch or one per sample), attention, optional scale-norm, output projection.
+    The plain configuration (fused qkv, no norms, shared interleaved table) rotates in the QKV GEMM's epilogue."""
+    if attn.training and (attn.attn_drop.p > 0 or attn.proj_drop.p > 0):
+        raise B200Error("AttentionRope: dropout is not covered")
     B, N, C = x.shape
     H, hd = attn.num_heads, attn.head_dim
+    if hd != 64:
+        raise B200Error("AttentionRope: only head_dim 64 is covered")
     half = bool(getattr(attn, "rotate_half", False))
     npt = attn.num_prefix_tokens
-    emb = None if rope is None else _rope_table(rope, N - npt, hd, x.device)
+    emb = None if rope is None else _rope_table(rope, N - npt, hd, x.device, batch=B)
+    qk, sn = _attn_norms(attn)
+    wqkv, bqkv = _qkv_params(attn)
+    plain = qk is None and sn is None and (emb is None or emb.dim() == 2)
     if _needs_grad(x, attn):
-        from .autograd import AttentionRopeFn
         _bf16_2d(x, C)
-        return AttentionRopeFn.apply(x, _w(attn.qkv), _qkv_bias(attn), _w(attn.proj), attn.proj.bias, emb, kv_len, H,
-                                     attn.scale, npt, half)
+        if plain:
+            from .autograd import AttentionRopeFn
+            return AttentionRopeFn.apply(x, wqkv, bqkv, _w(attn.proj), attn.proj.bias, emb, kv_len, H, attn.scale, npt, half)
+        from .autograd import AttentionNormFn
+        qw, qb, kw, kb, qe = qk if qk is not None else (None, None, None, None, 0.0)
+        nw, nb, ne = sn if sn is not None else (None, None, 0.0)
+        return AttentionNormFn.apply(x, wqkv, bqkv, _w(attn.proj), attn.proj.bias, qw, qb, kw, kb, nw, nb, kv_len, H, attn.scale,
+                                     qe, ne, emb, npt, half)
     x2 = _bf16_2d(x, C)
-    qkv = rope_qkv_projection(x2, _w(attn.qkv), _qkv_bias(attn), emb, B, N, H, npt, half)
+    if plain:
+        qkv = rope_qkv_projection(x2, wqkv, bqkv, emb, B, N, H, npt, half)
+    else:
+        qkv = ops.linear_fwd(x2, wqkv, bqkv)
+        if qk is not None:
+            ops.qk_norm_fwd(qkv, B * N, H, *qk)
+        if emb is not None:
+            ops.rope_qk(qkv, emb, B, N, H, npt, half=half)
     o, _ = ops.attention_fwd(qkv, B, N, H, hd, attn.scale, kv_len)
-    y = ops.linear_fwd(o.view(B * N, -1), _w(attn.proj), attn.proj.bias)
+    o2 = o.view(B * N, -1)
+    if sn is not None:
+        o2 = ops.layernorm_fwd(o2, *sn)[0]
+    y = ops.linear_fwd(o2, _w(attn.proj), attn.proj.bias)
     return y.view(B, N, -1)
 
 

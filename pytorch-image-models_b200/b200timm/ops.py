@@ -279,10 +279,18 @@ def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, 
                 row_scale=row_scale, rows_per_scale=rows_per_scale, rope=rope, act=act)
 
 
-def _check_rope(emb, tokens, prefix):
-    if (emb.dtype != torch.float32 or not emb.is_cuda or not emb.is_contiguous() or emb.dim() != 2
-            or emb.shape[1] != 128 or emb.shape[0] != tokens - prefix or prefix < 0):
-        raise B200Error("rope: the embedding must be a contiguous fp32 CUDA tensor [tokens - prefix, 2 * 64] = [sin | cos]")
+def _check_rope(emb, tokens, prefix, batch=None):
+    """Shared table [tokens - prefix, 128]; with `batch`, also a per-sample one [batch, tokens - prefix, 128]."""
+    ok = emb.dtype == torch.float32 and emb.is_cuda and emb.is_contiguous() and emb.shape[-1] == 128 and prefix >= 0
+    if ok and emb.dim() == 2:
+        ok = emb.shape[0] == tokens - prefix
+    elif ok and emb.dim() == 3 and batch is not None:
+        ok = emb.shape[0] == batch and emb.shape[1] == tokens - prefix
+    else:
+        ok = False
+    if not ok:
+        raise B200Error("rope: the embedding must be a contiguous fp32 CUDA tensor [tokens - prefix, 2 * 64] = [sin | cos] "
+                        "(or [B, tokens - prefix, 128] for per-sample tables)")
 
 
 def rope_qk(qkv, emb, B, N, H, num_prefix, half=False, inverse=False):
@@ -291,8 +299,9 @@ def rope_qk(qkv, emb, B, N, H, num_prefix, half=False, inverse=False):
     _need_cuda(qkv, emb)
     if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.numel() != B * N * 3 * H * 64:
         raise B200Error("rope_qk: qkv must be a contiguous bf16 [B*N, 3*H*64] buffer (head_dim 64)")
-    _check_rope(emb, N, num_prefix)
-    rc = _lib.load().b200_rope_qk(qkv.data_ptr(), emb.data_ptr(), B, N, H, int(num_prefix), int(half), int(inverse), _stream())
+    _check_rope(emb, N, num_prefix, batch=B)
+    rc = _lib.load().b200_rope_qk(qkv.data_ptr(), emb.data_ptr(), B, N, H, int(num_prefix), int(half), int(inverse),
+                                  int(emb.dim() == 3), _stream())
     _lib.check(rc, "b200_rope_qk")
     _count()
     return qkv

@@ -322,7 +322,7 @@ __global__ void convert_kernel(const float* __restrict__ src, void* __restrict__
 // both layouts pair columns inside those 16 values (interleaved: neighbours; half: d <-> d + 32).
 __global__ void __launch_bounds__(256)
 rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ emb, long long rows, int N, int H, int prefix,
-               int half_layout, int inverse) {
+               int half_layout, int inverse, int per_sample) {
   const long long total = rows * (2LL * H) * 4;
   const long long ld = 3LL * H * 64;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -334,7 +334,8 @@ rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ emb, l
     const int tok = static_cast<int>(r % N) - prefix;
     if (tok < 0) continue;
     __nv_bfloat16* px = qkv + r * ld + g * 64 + d0;
-    const float* e = emb + static_cast<long long>(tok) * 128 + d0;
+    // shared table [N - prefix, 128], or one table per sample [B, N - prefix, 128] (NaFlex: rope of shape [B, 1, N, 2 hd])
+    const float* e = emb + ((per_sample ? (r / N) * (N - prefix) : 0LL) + tok) * 128 + d0;
     float x[16], sn[16], cs[16], y[16];
     {
       const uint4 a = *reinterpret_cast<const uint4*>(px), b = *reinterpret_cast<const uint4*>(px + 32);
@@ -687,7 +688,7 @@ extern "C" int b200_colsum_mul(const void* a, const void* b, const float* row_sc
 }
 
 extern "C" int b200_rope_qk(void* qkv, const float* emb, int32_t B, int32_t N, int32_t H, int32_t num_prefix,
-                            int32_t half_layout, int32_t inverse, void* stream_) {
+                            int32_t half_layout, int32_t inverse, int32_t per_sample, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv && emb, "b200_rope_qk: null pointer");
   B200_CHECK_ARG(B > 0 && N > 0 && H > 0 && num_prefix >= 0 && num_prefix < N, "b200_rope_qk: bad shape");
@@ -699,7 +700,7 @@ extern "C" int b200_rope_qk(void* qkv, const float* emb, int32_t B, int32_t N, i
   const long long cap = static_cast<long long>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   rope_qk_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(qkv), emb, rows, N, H, num_prefix,
-                                                          half_layout != 0, inverse != 0);
+                                                          half_layout != 0, inverse != 0, per_sample != 0);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

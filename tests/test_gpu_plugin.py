@@ -239,3 +239,32 @@ def test_attention_pool_variants_and_patch_embed_formats(plugin):
     for fmt in ("NHWC", "NCHW"):
         _compare_module(plugin, lambda: PatchEmbed(img_size=None, patch_size=16, embed_dim=64, flatten=False, output_fmt=fmt,
                                                    strict_img_size=False, dynamic_img_pad=True), img, grad=True)
+
+
+def test_rope_attention_variants(plugin):
+    """AttentionRope / EvaAttention beyond the fused fast path: q / k normalisation before the rotation, scale-norm, separate
+    q / k / v projections (stacked into one GEMM operand), half / interleaved layouts, one rotary table per SAMPLE
+    ([B, 1, N, 2 hd], the NaFlex-RoPE shape)."""
+    from timm.layers import AttentionRope, LayerNorm, RmsNorm
+    from timm.layers.pos_embed_sincos import RotaryEmbeddingCat
+    from timm.models.eva import EvaAttention
+    B, N, D, H = 3, 1 + 6 * 5, 128, 2
+    tok = lambda: torch.randn(B, N, D).bfloat16().float()   # noqa: E731
+    shared = RotaryEmbeddingCat(64, in_pixels=False, feat_shape=(6, 5)).get_embed()                      # [30, 128]
+    per_sample = torch.stack([RotaryEmbeddingCat(64, in_pixels=False, feat_shape=(6, 5), temperature=10000. * (i + 1)).get_embed()
+                              for i in range(B)]).unsqueeze(1)                                           # [B, 1, 30, 128]
+
+    def call(rope):
+        return lambda mod, inp: mod(inp, rope=rope.to(inp.device))
+    cases = [
+        (lambda: AttentionRope(D, num_heads=H, qk_norm=True, scale_norm=True, norm_layer=LayerNorm), shared),
+        (lambda: AttentionRope(D, num_heads=H, qkv_fused=False, rotate_half=True), shared),
+        (lambda: AttentionRope(D, num_heads=H, qkv_fused=False, qk_norm=True, norm_layer=RmsNorm), per_sample),
+        (lambda: AttentionRope(D, num_heads=H), per_sample),
+        (lambda: EvaAttention(D, num_heads=H, qkv_fused=False, norm_layer=LayerNorm, scale_norm=True), shared),
+        (lambda: EvaAttention(D, num_heads=H, qkv_fused=True, qk_norm=True, scale_norm=False, norm_layer=LayerNorm, rotate_half=True),
+         per_sample),
+    ]
+    for build, rope in cases:
+        for grad in (False, True):
+            _compare_module(plugin, build, tok, grad=grad, call=call(rope))
