@@ -319,6 +319,176 @@ layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Wide rows (2048 < cols <= 8192: the inner norm of an Mlp / gated Mlp over the HIDDEN width -- Mlp(norm_layer=...),
+// `scale_mlp_norm`, EVA-02's SwiGLU norm; timm/layers/mlp.py:44, 100, 148): one CTA of 256 threads per row, the row's
+// 16-byte vectors packed in registers (VB = ceil(cols / 2048) per thread), statistics through a two-level (warp shuffle +
+// shared memory) reduction.  bf16 activations only.  Same formulas as the warp-per-row kernels above.
+__device__ __forceinline__ float block_sum256(float v, float* scratch) {
+  v = warp_sum(v);
+  __syncthreads();                      // scratch may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += scratch[i];
+  return r;
+}
+
+template <int VB>
+__global__ void __launch_bounds__(256)
+layernorm_wide_fwd_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ w, const void* __restrict__ b,
+                          __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                          long long rows, int cols, float eps, int param_f32) {
+  __shared__ float scratch[8];
+  const bool rms = (param_f32 & 2) != 0;
+  param_f32 &= 1;
+  const int nvec = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    uint4 xr[VB];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VB; ++i) {
+      const int vec = threadIdx.x + i * 256;
+      if (vec < nvec) {
+        xr[i] = *reinterpret_cast<const uint4*>(x + row * cols + vec * 8);
+        float v[8];
+        unpack8(xr[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+      }
+    }
+    const float mean = rms ? 0.f : block_sum256(s, scratch) * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VB; ++i) {
+      if (threadIdx.x + i * 256 < nvec) {
+        float v[8];
+        unpack8(xr[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
+      }
+    }
+    const float rstd = rsqrtf(block_sum256(sq, scratch) * inv_n + eps);
+#pragma unroll
+    for (int i = 0; i < VB; ++i) {
+      const int vec = threadIdx.x + i * 256;
+      if (vec < nvec) {
+        float v[8], o[8];
+        unpack8(xr[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd;
+        if (w != nullptr) {
+          float wv[8];
+          load8_rt(w, param_f32, vec * 8, wv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= wv[j];
+        }
+        if (b != nullptr) {
+          float bv[8];
+          load8_rt(b, param_f32, vec * 8, bv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += bv[j];
+        }
+        store8<false>(y, row * cols + vec * 8, o);
+      }
+    }
+    if (threadIdx.x == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// ws[blockIdx.x][2 * cols]: this CTA's partial sums of dy * xhat | dy over its rows (finished by reduce_rows_kernel).
+template <int VB>
+__global__ void __launch_bounds__(256)
+layernorm_wide_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const void* __restrict__ w,
+                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                          const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ ws,
+                          long long rows, int cols, int param_f32) {
+  __shared__ float scratch[8];
+  const bool rms = (param_f32 & 2) != 0;
+  param_f32 &= 1;
+  const int nvec = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  float dw_acc[VB][8], db_acc[VB][8];
+#pragma unroll
+  for (int i = 0; i < VB; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dw_acc[i][j] = 0.f; db_acc[i][j] = 0.f; }
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    uint4 xr[VB], dyr[VB];
+    const float mean = rms ? 0.f : mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VB; ++i) {
+      const int vec = threadIdx.x + i * 256;
+      if (vec < nvec) {
+        xr[i] = *reinterpret_cast<const uint4*>(x + row * cols + vec * 8);
+        dyr[i] = *reinterpret_cast<const uint4*>(dy + row * cols + vec * 8);
+        float xv[8], dyv[8], wv[8];
+        unpack8(xr[i], xv);
+        unpack8(dyr[i], dyv);
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          dw_acc[i][j] = fmaf(dyv[j], xh, dw_acc[i][j]);
+          db_acc[i][j] += dyv[j];
+        }
+      }
+    }
+    const float m1 = rms ? 0.f : block_sum256(s1, scratch) * inv_n;
+    const float m2 = block_sum256(s2, scratch) * inv_n;
+#pragma unroll
+    for (int i = 0; i < VB; ++i) {
+      const int vec = threadIdx.x + i * 256;
+      if (vec < nvec) {
+        float xv[8], dyv[8], wv[8], o[8];
+        unpack8(xr[i], xv);
+        unpack8(dyr[i], dyv);
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float g = (w != nullptr) ? dyv[j] * wv[j] : dyv[j];
+          o[j] = rstd * (g - m1 - xh * m2);
+        }
+        if (dres != nullptr) {
+          float rv[8];
+          unpack8(*reinterpret_cast<const uint4*>(dres + row * cols + vec * 8), rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
+        store8<false>(dx, row * cols + vec * 8, o);
+      }
+    }
+  }
+  float* out = ws + static_cast<long long>(blockIdx.x) * 2 * cols;
+#pragma unroll
+  for (int i = 0; i < VB; ++i) {
+    const int vec = threadIdx.x + i * 256;
+    if (vec < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        out[vec * 8 + j] = dw_acc[i][j];
+        out[cols + vec * 8 + j] = db_acc[i][j];
+      }
+    }
+  }
+}
+
+constexpr int kLnMaxCols = 8192;
+static int ln_wide_grid(long long rows) {
+  const long long cap = static_cast<long long>(sm_count()) * 4;
+  return static_cast<int>(rows < cap ? rows : cap);
+}
+
 // Second stage: out[c] = sum_r ws[r][c] over the per-CTA partial rows.  blockDim = (32 columns, 8 row slices):
 // each warp streams its row slice with coalesced 128-byte reads, then the 8 slices are combined through smem, so
 // the reduction is a handful of independent loads per thread instead of one serial chain over all rows.
@@ -407,12 +577,25 @@ static int norm_fwd(const void* x, const void* weight, const void* bias, void* y
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(x && y, "b200_layernorm_fwd: null x/y");
   B200_CHECK_ARG(rows >= 0 && cols > 0, "b200_layernorm_fwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
-  if (cols % 8 != 0 || cols > 2048)
-    return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_fwd: cols=%d must be a multiple of 8 and <= 2048", cols);
+  if (cols % 8 != 0 || cols > kLnMaxCols)
+    return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_fwd: cols=%d must be a multiple of 8 and <= %d", cols, kLnMaxCols);
   if (rows == 0) return B200_OK;
   const int vpl = (cols + 255) / 256;
   const int xf = x_dtype == B200_DTYPE_F32, yf = y_dtype == B200_DTYPE_F32;
   const int pf = (param_dtype == B200_DTYPE_F32 ? 1 : 0) | (rms ? 2 : 0);
+  if (cols > 2048) {
+    if (xf || yf) return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_fwd: rows wider than 2048 need bf16 activations");
+    const int grid = ln_wide_grid(rows);
+    auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto* yp = reinterpret_cast<__nv_bfloat16*>(y);
+    switch ((cols + 2047) / 2048) {
+      case 2: layernorm_wide_fwd_kernel<2><<<grid, 256, 0, st>>>(xp, weight, bias, yp, mean, rstd, rows, cols, eps, pf); break;
+      case 3: layernorm_wide_fwd_kernel<3><<<grid, 256, 0, st>>>(xp, weight, bias, yp, mean, rstd, rows, cols, eps, pf); break;
+      default: layernorm_wide_fwd_kernel<4><<<grid, 256, 0, st>>>(xp, weight, bias, yp, mean, rstd, rows, cols, eps, pf); break;
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return B200_OK;
+  }
   switch (vpl) {
     case 1: launch_fwd<1>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
     case 2: launch_fwd<2>(x, weight, bias, y, mean, rstd, rows, cols, eps, xf, yf, pf, st); break;
@@ -437,8 +620,7 @@ extern "C" int b200_rmsnorm_fwd(const void* x, const void* weight, void* y, floa
 }
 
 extern "C" int b200_layernorm_bwd_ws_rows(int64_t rows, int32_t cols) {
-  (void)cols;
-  return ln_bwd_grid(rows > 0 ? rows : 1);
+  return cols > 2048 ? ln_wide_grid(rows > 0 ? rows : 1) : ln_bwd_grid(rows > 0 ? rows : 1);
 }
 
 static int norm_bwd(const void* dy, const void* x, const void* weight, const float* mean, const float* rstd, const void* dres,
@@ -447,11 +629,30 @@ static int norm_bwd(const void* dy, const void* x, const void* weight, const flo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(dy && x && (mean || rms) && rstd && dx && workspace, "b200_layernorm_bwd: null pointer");
   B200_CHECK_ARG(rows > 0 && cols > 0, "b200_layernorm_bwd: bad shape rows=%lld cols=%d", (long long)rows, cols);
-  if (cols % 8 != 0 || cols > 2048)
-    return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_bwd: cols=%d must be a multiple of 8 and <= 2048", cols);
+  if (cols % 8 != 0 || cols > kLnMaxCols)
+    return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_bwd: cols=%d must be a multiple of 8 and <= %d", cols, kLnMaxCols);
   const int vpl = (cols + 255) / 256;
   const int xf = x_dtype == B200_DTYPE_F32, dyf = dy_dtype == B200_DTYPE_F32;
   const int pf = (param_dtype == B200_DTYPE_F32 ? 1 : 0) | (rms ? 2 : 0);
+  if (cols > 2048) {
+    if (xf || dyf) return fail(B200_ERR_UNSUPPORTED, "b200_layernorm_bwd: rows wider than 2048 need bf16 activations");
+    const int grid = ln_wide_grid(rows);
+    auto* dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+    auto* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto* rp = reinterpret_cast<const __nv_bfloat16*>(dres);
+    auto* dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+    switch ((cols + 2047) / 2048) {
+      case 2: layernorm_wide_bwd_kernel<2><<<grid, 256, 0, st>>>(dyp, xp, weight, mean, rstd, rp, dxp, workspace, rows, cols, pf); break;
+      case 3: layernorm_wide_bwd_kernel<3><<<grid, 256, 0, st>>>(dyp, xp, weight, mean, rstd, rp, dxp, workspace, rows, cols, pf); break;
+      default: layernorm_wide_bwd_kernel<4><<<grid, 256, 0, st>>>(dyp, xp, weight, mean, rstd, rp, dxp, workspace, rows, cols, pf); break;
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    if (dweight || dbias) {
+      reduce_rows_kernel<<<(2 * cols + 31) / 32, 256, 0, st>>>(workspace, dweight, dbias, grid, cols);
+      B200_CUDA_OK(cudaGetLastError());
+    }
+    return B200_OK;
+  }
   int rc;
   switch (vpl) {
     case 1: rc = launch_bwd<1>(dy, x, weight, mean, rstd, dres, dx, workspace, rows, cols, xf, dyf, pf, st); break;

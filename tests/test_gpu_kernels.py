@@ -412,3 +412,34 @@ def test_attention_bwd_bias_gradient(B, N, H):
     db.zero_()
     fused = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125, kv_len=kv_len, dbias=db)
     torch.testing.assert_close(db, ops.colsum(fused.view(B * N, -1)), atol=2e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("cols", [3072, 4096, 2056, 8192])
+@pytest.mark.parametrize("pdt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rms", [False, True])
+def test_layernorm_wide_rows(cols, pdt, rms):
+    """Rows wider than 2048 (the inner norm of an Mlp over the hidden width): the CTA-per-row kernels, LayerNorm and RMSNorm,
+    forward, backward (with a residual gradient) and the parameter-gradient reduction, against torch fp32."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(cols)
+    rows = 777
+    x = (torch.randn(rows, cols, device=DEV, generator=g) * 2 + 0.5).bfloat16()
+    w = (torch.randn(cols, device=DEV, generator=g) * 0.5 + 1).to(pdt)
+    b = None if rms else torch.randn(cols, device=DEV, generator=g).to(pdt)
+    dy = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    dres = torch.randn(rows, cols, device=DEV, generator=g).bfloat16()
+    eps = ops.RmsEps(1e-6) if rms else 1e-6
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, eps, save_stats=True)
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    if rms:
+        yr = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * wr
+    else:
+        br = b.float().requires_grad_(True)
+        yr = torch.nn.functional.layer_norm(xr, (cols,), wr, br, 1e-6)
+    _close(y, yr.detach(), 3e-2, 1e-2, "wide ln fwd")
+    yr.backward(dy.float())
+    dx, dw, db = ops.layernorm_bwd(dy, x, w, mean, rstd, dres=dres)
+    _close(dx, xr.grad + dres.float(), 4e-2, 1e-2, "wide ln dx (+ residual gradient)")
+    _close(dw, wr.grad, 3e-2, 2e-3, "wide ln dweight")
+    if not rms:
+        _close(db, br.grad, 3e-2, 2e-3, "wide ln dbias")
