@@ -36,6 +36,7 @@ extern "C" {
 
 #define B200_DTYPE_BF16 0
 #define B200_DTYPE_F32 1
+#define B200_DTYPE_U8 2    /* images / patches of the input pipeline only (b200_batch_patchify, b200_patches_u8) */
 
 /* GEMM epilogues (applied to acc = A*B^T before the store). */
 #define B200_EPI_BIAS 0       /* out = acc + bias                       (bias may be NULL)          */
@@ -328,6 +329,20 @@ B200_API int b200_cross_entropy_fwd(const void* logits, int32_t logits_dtype, co
 B200_API int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, const int64_t* target, const void* soft_target,
                          int32_t soft_dtype, double smoothing, const float* lse, const float* tsum,
                          const float* grad_out, const float* denom, void* dlogits, int32_t B, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------ NaFlex input tail, ABI >= 6
+ * b200_batch_patchify: batch_patchify (timm/models/naflexvit.py:159-201, pad=True) as the gather that builds the patch
+ * projection's GEMM operand: NCHW image [B,C,H,W] (img_dtype uint8 / bf16 / f32) -> bf16 [B*ceil(H/p)*ceil(W/p), Kpad],
+ * patches row-major over (y, x), flat layout P-P-C (channels_last = 1: k = (ky*p + kx)*C + c, the NaFlex default) or
+ * C-P-P (0); pixels beyond H / W are zeros; columns K..Kpad are zero.  uint8 pixels are normalised
+ * (v - mean[c]) / std[c] (mean / std: HOST arrays of C floats in 0..255 units, NaFlexPrefetchLoader's mean*255 / std*255,
+ * timm/data/naflex_loader.py:75-80,161) in fp32 with one rounding to bf16; bf16 / f32 images are copied / cast.
+ * b200_patches_u8: the same normalisation for patches the dataset already cut: uint8 [rows, K] -> bf16 [rows, Kpad]. */
+B200_API int b200_batch_patchify(const void* img, int32_t img_dtype, void* patches, int32_t B, int32_t C, int32_t H, int32_t W,
+                                 int32_t p, int32_t Kpad, int32_t channels_last, const float* mean, const float* std,
+                                 void* stream);
+B200_API int b200_patches_u8(const void* patches_u8, void* out, int64_t rows, int32_t K, int32_t Kpad, int32_t C,
+                             int32_t channels_last, const float* mean, const float* std, void* stream);
 
 /* dpre = dy * act'(pre) elementwise (bf16, n a multiple of 8): the activation backward of an Mlp with an inner norm between
  * the activation and fc2 (Mlp(norm_layer=...), timm/layers/mlp.py:44-53); act as in b200_gemm_desc.act.  ABI >= 6.      */

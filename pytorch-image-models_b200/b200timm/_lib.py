@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("B200TIMM_LIB") or os.path.join(_HERE, "libb200timm.so
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "b200timm.h"))
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
-DTYPE_BF16, DTYPE_F32 = 0, 1
+DTYPE_BF16, DTYPE_F32, DTYPE_U8 = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, EPI_DGELU, EPI_BIAS_ROPE = 0, 1, 2, 3, 4
 
 
@@ -114,6 +114,8 @@ SIGNATURES = {
     "b200_clip_coef": (ctypes.c_int, [_vp, _f64, _vp, _vp, _vp]),
     "b200_grad_scale": (ctypes.c_int, [_otp, _i32, _i32, _vp, _vp]),
     "b200_ema_update": (ctypes.c_int, [_otp, _i32, _i32, _i32, _f64, _vp]),
+    "b200_batch_patchify": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200_patches_u8": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200_act_bwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp]),
     "b200_grad_push": (ctypes.c_int, [_vp, _i32, _vp, ctypes.c_int64, _f32, _vp]),
     "b200_cross_entropy_fwd": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _f64, ctypes.c_int64, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),

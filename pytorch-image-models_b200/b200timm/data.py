@@ -84,5 +84,60 @@ class PrefetchLoader:
             self.loader.collate_fn.mixup_enabled = x
 
 
+class NaFlexPrefetchLoader:
+    """Mirror of timm.data.naflex_loader.NaFlexPrefetchLoader (naflex_loader.py:27-193): moves the collated patch dict
+    (`patches` uint8 [B, N, P*P*C], `patch_coord`, `patch_valid`) to the GPU on a side stream and hands it to the model AS IS
+    -- the `(patches - mean * 255) / (std * 255)` pass (:161) and the fp32 `patches` tensor it materialises are folded into
+    the kernel that builds the patch projection's GEMM operand (b200_patches_u8: normalise + bf16 cast + K padding in one
+    pass).  Random erasing works on normalised floats and is not folded in: re_prob > 0 raises B200Error."""
+
+    def __init__(self, loader, mean: Tuple[float, ...] = IMAGENET_DEFAULT_MEAN, std: Tuple[float, ...] = IMAGENET_DEFAULT_STD,
+                 channels: int = 3, device: torch.device = torch.device("cuda"), img_dtype: Optional[torch.dtype] = None,
+                 re_prob: float = 0., re_mode: str = "const", re_count: int = 1, re_num_splits: int = 0,
+                 patchify_channels_last: bool = True):
+        if re_prob > 0.:
+            raise B200Error("NaFlexPrefetchLoader: random erasing is not folded into the patch gather (use timm's loader)")
+        if not patchify_channels_last:
+            raise B200Error("NaFlexPrefetchLoader: only the P-P-C patch layout (patchify_channels_last=True) is covered")
+        self.loader, self.device, self.channels = loader, torch.device(device), channels
+        self.mean, self.std = _per_channel(mean, channels), _per_channel(std, channels)
+        self.img_dtype = torch.uint8
+        ops.set_input_norm(self.mean, self.std)
+
+    def __iter__(self):
+        if self.device.type != "cuda":
+            raise B200Error("NaFlexPrefetchLoader: libb200timm needs a CUDA device (there is no CPU path)")
+        stream = torch.cuda.Stream(device=self.device)
+        batch = None
+        for next_dict, next_target in self.loader:
+            if next_dict["patches"].dtype != torch.uint8:
+                raise B200Error("NaFlexPrefetchLoader: expected uint8 patches from the NaFlex collator")
+            with torch.cuda.stream(stream):
+                next_dict = {k: (v.to(device=self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v)
+                             for k, v in next_dict.items()}
+                next_target = next_target.to(device=self.device, non_blocking=True)
+            if batch is not None:
+                yield batch
+            cur = torch.cuda.current_stream(device=self.device)
+            cur.wait_stream(stream)
+            for v in list(next_dict.values()) + [next_target]:
+                if isinstance(v, torch.Tensor):
+                    v.record_stream(cur)
+            batch = (next_dict, next_target)
+        if batch is not None:
+            yield batch
+
+    def __len__(self):
+        return len(self.loader)
+
+    @property
+    def sampler(self):
+        return self.loader.sampler
+
+    @property
+    def dataset(self):
+        return self.loader.dataset
+
+
 set_input_norm = ops.set_input_norm
-__all__ = ["PrefetchLoader", "set_input_norm", "IMAGENET_DEFAULT_MEAN", "IMAGENET_DEFAULT_STD"]
+__all__ = ["PrefetchLoader", "NaFlexPrefetchLoader", "set_input_norm", "IMAGENET_DEFAULT_MEAN", "IMAGENET_DEFAULT_STD"]

@@ -83,6 +83,7 @@ class NaFlexVit(nn.Module):
             raise B200Error(f"NaFlexVit global_pool={global_pool!r} is not covered (token / avg)")
         self.num_classes, self.global_pool, self.embed_dim = num_classes, global_pool, embed_dim
         self.num_prefix_tokens = (1 if class_token else 0) + reg_tokens
+        self.in_chans = in_chans
         norm_layer = lambda d, **kw: LayerNorm(d, eps=norm_eps, **kw)   # noqa: E731
         self.embeds = NaFlexEmbeds(patch_size, in_chans, embed_dim, proj_bias=not pre_norm, class_token=class_token,
                                    reg_tokens=reg_tokens, pos_embed_grid_size=pos_embed_grid_size, **dd)
@@ -103,22 +104,32 @@ class NaFlexVit(nn.Module):
                     nn.init.zeros_(m.bias)
 
     # -- embeds + blocks --------------------------------------------------------------------------------------
-    def _tokens(self, patches, patch_coord, patch_valid):
+    def _tokens(self, patches, patch_coord, patch_valid, rows=None):
+        """rows: the projection's operand already built (bf16 [B * N, Kpad], _image_to_patches); else built from `patches`."""
         if not patches.is_cuda:
             raise B200Error("libb200timm kernels need CUDA tensors (there is no CPU path)")
         e = self.embeds
         B, N = patches.shape[:2]
-        x = patches.reshape(B * N, -1)
-        if x.dtype == torch.float32 and e.proj.weight.dtype == torch.float32:
-            x = x.to(torch.bfloat16)        # train.py --amp: the cast autocast applies to F.linear's input
-        if x.dtype != torch.bfloat16:
-            raise B200Error("NaFlexVit B200 path needs bf16 patches (fp32 patches only with fp32 master weights)")
         train = torch.is_grad_enabled() and any(p.requires_grad for p in e.parameters())
         w = BF._w(e.proj)
-        K = x.shape[1]
+        K = w.shape[1]
         kpad = (K + 7) // 8 * 8
-        if kpad != K:   # p=14: 588 -> 592, 16-byte row pitch for TMA (zero columns contribute nothing)
-            x = F.pad(x, (0, kpad - K))
+        if rows is not None:
+            x = rows
+        elif patches.dtype == torch.uint8:
+            # the loader's raw uint8 patches (b200timm.data.NaFlexPrefetchLoader): normalisation, bf16 cast and the K padding
+            # happen in ONE pass (b200_patches_u8) instead of the fp32 sub / div round trip of naflex_loader.py:161
+            x = ops.patches_u8(patches.contiguous(), self.in_chans, channels_last=True, kpad=kpad)
+        else:
+            x = patches.reshape(B * N, -1)
+            if x.dtype == torch.float32 and e.proj.weight.dtype == torch.float32:
+                x = x.to(torch.bfloat16)        # train.py --amp: the cast autocast applies to F.linear's input
+            if x.dtype != torch.bfloat16:
+                raise B200Error("NaFlexVit B200 path needs bf16 patches (fp32 patches only with fp32 master weights) or the "
+                                "loader's uint8 patches")
+            if kpad != K:   # p=14: 588 -> 592, 16-byte row pitch for TMA (zero columns contribute nothing)
+                x = F.pad(x, (0, kpad - K))
+        if kpad != K:
             if not train:
                 cache = getattr(e, "_b200_wpad", None)
                 if cache is None or cache[0] != ops.wkey(w):
@@ -150,10 +161,28 @@ class NaFlexVit(nn.Module):
         kv_len = (nvalid + self.num_prefix_tokens).contiguous()
         return tokens, kv_len
 
+    def _image_to_patches(self, img):
+        """An NCHW image batch as NaFlexEmbeds.forward takes it (naflexvit.py:880-890): batch_patchify fused into the gather
+        that builds the projection's GEMM operand (b200_batch_patchify: P-P-C patch layout, ragged edges zero-padded, uint8
+        pixels normalised on the fly) + the regular grid of coordinates; every patch is valid."""
+        P = self.embeds.patch_size
+        P = P[0] if isinstance(P, (tuple, list)) else P
+        B = img.shape[0]
+        K = img.shape[1] * P * P
+        rows, (gh, gw) = ops.batch_patchify(img.contiguous(), P, channels_last=True, kpad=(K + 7) // 8 * 8)
+        ys, xs = torch.meshgrid(torch.arange(gh, device=img.device), torch.arange(gw, device=img.device), indexing="ij")
+        coord = torch.stack([ys, xs], -1).reshape(1, gh * gw, 2).expand(B, -1, -1).contiguous()
+        valid = torch.ones(B, gh * gw, dtype=torch.bool, device=img.device)
+        return rows, coord, valid
+
     def forward_features(self, patches, patch_coord=None, patch_valid=None) -> Dict[str, torch.Tensor]:
+        rows = None
+        if patches.dim() == 4 and patch_coord is None:
+            rows, patch_coord, patch_valid = self._image_to_patches(patches)
+            patches = rows.view(patches.shape[0], -1, rows.shape[1])
         if patch_coord is None or patch_valid is None:
-            raise B200Error("NaFlexVit mirror covers the NaFlex (patches, patch_coord, patch_valid) input only")
-        x, kv_len = self._tokens(patches, patch_coord, patch_valid)
+            raise B200Error("NaFlexVit mirror needs (patches, patch_coord, patch_valid) or an NCHW image batch")
+        x, kv_len = self._tokens(patches, patch_coord, patch_valid, rows)
         if not isinstance(self.norm_pre, nn.Identity):
             x = BF.layernorm(self.norm_pre, x)
         for blk in self.blocks:

@@ -662,6 +662,51 @@ def glu_bwd(h, dout, gate_first, act="silu"):
     return dh
 
 
+def batch_patchify(img, p, channels_last=True, kpad=None):
+    """batch_patchify (timm/models/naflexvit.py:159-201, pad=True) as the gather feeding the patch projection: NCHW image
+    (bf16 / fp32, or uint8 with set_input_norm) -> (bf16 [B * gh * gw, Kpad], (gh, gw)); flat patch layout P-P-C
+    (channels_last) or C-P-P; ragged edges zero-padded."""
+    _need_cuda(img)
+    if img.dim() != 4 or not img.is_contiguous():
+        raise B200Error("batch_patchify: need a contiguous NCHW image")
+    B, C, H, W = img.shape
+    K = C * p * p
+    kpad = kpad or (K + 7) // 8 * 8
+    gh, gw = -(-H // p), -(-W // p)
+    out = torch.empty(B * gh * gw, kpad, dtype=torch.bfloat16, device=img.device)
+    mean = std = None
+    if img.dtype == torch.uint8:
+        if _input_norm is None or len(_input_norm[0]) != C:
+            raise B200Error("uint8 images need ops.set_input_norm(mean, std) with one entry per channel")
+        mean, std, dt = _input_norm[0], _input_norm[1], _lib.DTYPE_U8
+    else:
+        dt = _dt(img)
+    rc = _lib.load().b200_batch_patchify(img.data_ptr(), dt, out.data_ptr(), B, C, H, W, p, kpad, int(channels_last), mean, std,
+                                         _stream())
+    _lib.check(rc, "b200_batch_patchify")
+    _count()
+    return out, (gh, gw)
+
+
+def patches_u8(patches, channels, channels_last=True, kpad=None):
+    """NaFlexPrefetchLoader's normalisation (timm/data/naflex_loader.py:126-161) of the dataset's uint8 patches
+    [..., K] -> bf16 [rows, Kpad] ((v - mean * 255) / (std * 255), set_input_norm), fused with the cast and the K padding."""
+    _need_cuda(patches)
+    if patches.dtype != torch.uint8 or not patches.is_contiguous():
+        raise B200Error("patches_u8: need a contiguous uint8 tensor")
+    if _input_norm is None or len(_input_norm[0]) != channels:
+        raise B200Error("uint8 patches need ops.set_input_norm(mean, std) with one entry per channel")
+    K = patches.shape[-1] if patches.dim() == 3 else patches[0, 0].numel()
+    rows = patches.numel() // K
+    kpad = kpad or (K + 7) // 8 * 8
+    out = torch.empty(rows, kpad, dtype=torch.bfloat16, device=patches.device)
+    rc = _lib.load().b200_patches_u8(patches.data_ptr(), out.data_ptr(), rows, K, kpad, channels, int(channels_last),
+                                     _input_norm[0], _input_norm[1], _stream())
+    _lib.check(rc, "b200_patches_u8")
+    _count()
+    return out
+
+
 def act_bwd(dy, pre, act=0):
     """dy * act'(pre) elementwise (bf16, contiguous, equal shapes): Mlp activation backward when an inner norm separates
     the activation from fc2 (otherwise it rides in the fc2-dgrad GEMM epilogue)."""

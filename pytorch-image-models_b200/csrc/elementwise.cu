@@ -470,6 +470,80 @@ __global__ void glu_bwd_kernel(const __nv_bfloat16* __restrict__ h, const __nv_b
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The NaFlex input tail: batch_patchify (timm/models/naflexvit.py:159-201) and the NaFlexPrefetchLoader
+// normalisation (timm/data/naflex_loader.py:126-161) folded into the pass that builds the patch-projection GEMM's A operand.
+//   naflex_patchify_kernel : NCHW image (uint8 / bf16 / fp32) -> [B * gh * gw, Kpad] bf16 rows, flat patch layout P-P-C
+//                            (channels_last, NaFlex default: k = (ky * p + kx) * C + c) or C-P-P; uint8 pixels are
+//                            normalised (v - mean[c]) / std[c] in fp32 and rounded once -- the loader's sub / div and the
+//                            autocast / .to(bf16) cast in one step; rows past H / W (pad=True) read as zero pixels, i.e.
+//                            (0 - mean) / std for uint8 exactly as normalising a zero-padded image would.
+//   patches_u8_kernel      : the loader's uint8 patches [rows, K] (already patchified by the dataset) -> normalised bf16
+//                            [rows, Kpad]: 1 byte read + 2 written per value instead of the fp32 round trip.
+struct Norm8 { float mean[8], std[8]; };      // per-channel statistics, by value in the kernel's parameter space
+
+template <int SRC>   // 0 = uint8, 1 = bf16, 2 = fp32
+__global__ void naflex_patchify_kernel(const void* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H, int W,
+                                       int p, int gh, int gw, int Kpad, int channels_last, const __grid_constant__ Norm8 nrm) {
+  const int kvecs = Kpad >> 3;
+  const long long total = static_cast<long long>(B) * gh * gw * kvecs;
+  const int K = C * p * p;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kv = static_cast<int>(idx % kvecs);
+    const long long patch = idx / kvecs;
+    const int px = static_cast<int>(patch % gw);
+    const int py = static_cast<int>((patch / gw) % gh);
+    const int b = static_cast<int>(patch / (static_cast<long long>(gw) * gh));
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kv * 8 + i;
+      v[i] = 0.f;
+      if (k < K) {
+        int c, ky, kx;
+        if (channels_last) { c = k % C; const int r = k / C; ky = r / p; kx = r - ky * p; }
+        else { c = k / (p * p); const int r = k - c * p * p; ky = r / p; kx = r - ky * p; }
+        const int y = py * p + ky, x = px * p + kx;
+        float pix = 0.f;
+        if (y < H && x < W) {
+          const long long off = ((static_cast<long long>(b) * C + c) * H + y) * W + x;
+          if (SRC == 0) pix = static_cast<float>(reinterpret_cast<const uint8_t*>(img)[off]);
+          else if (SRC == 1) pix = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(img)[off]);
+          else pix = __ldg(reinterpret_cast<const float*>(img) + off);
+        }
+        v[i] = (SRC == 0) ? __fdiv_rn(__fsub_rn(pix, nrm.mean[c]), nrm.std[c]) : pix;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + patch * Kpad + kv * 8) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
+__global__ void patches_u8_kernel(const uint8_t* __restrict__ src, __nv_bfloat16* __restrict__ out, long long rows, int K, int Kpad,
+                                  int C, int channels_last, const __grid_constant__ Norm8 nrm) {
+  const int kvecs = Kpad >> 3;
+  const long long total = rows * kvecs;
+  const int pp = K / C;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kv = static_cast<int>(idx % kvecs);
+    const long long row = idx / kvecs;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kv * 8 + i;
+      v[i] = 0.f;
+      if (k < K) {
+        const int c = channels_last ? k % C : k / pp;
+        v[i] = __fdiv_rn(__fsub_rn(static_cast<float>(src[row * K + k]), nrm.mean[c]), nrm.std[c]);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + row * Kpad + kv * 8) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
 // dpre = dy * act'(pre): the activation backward of an Mlp whose activation output does not feed fc2 directly (an inner
 // norm sits in between: Mlp(norm_layer=...), timm/layers/mlp.py:44-53 `scale_mlp_norm`) -- otherwise GELU' rides in the
 // fc2-dgrad GEMM epilogue.  act: 0 exact GELU, 1 tanh GELU, 2 SiLU (gelu.cuh).
@@ -493,6 +567,57 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
 }  // namespace b200
 
 using namespace b200;
+
+static Norm8 make_norm8(const float* mean, const float* std, int C) {
+  Norm8 n;
+  for (int c = 0; c < 8; ++c) { n.mean[c] = (mean && c < C) ? mean[c] : 0.f; n.std[c] = (std && c < C) ? std[c] : 1.f; }
+  return n;
+}
+
+extern "C" int b200_batch_patchify(const void* img, int32_t img_dtype, void* patches, int32_t B, int32_t C, int32_t H, int32_t W,
+                                   int32_t p, int32_t Kpad, int32_t channels_last, const float* mean, const float* std,
+                                   void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(img && patches && B > 0 && C > 0 && C <= 8 && p > 0 && H > 0 && W > 0, "b200_batch_patchify: bad arguments (1 <= C <= 8)");
+  B200_CHECK_ARG(Kpad % 8 == 0 && Kpad >= C * p * p, "b200_batch_patchify: Kpad=%d must be a multiple of 8 and >= C*p*p", Kpad);
+  B200_CHECK_ARG(img_dtype == B200_DTYPE_U8 || img_dtype == B200_DTYPE_BF16 || img_dtype == B200_DTYPE_F32,
+                 "b200_batch_patchify: image must be uint8, bf16 or f32");
+  if (img_dtype == B200_DTYPE_U8) {
+    B200_CHECK_ARG(mean && std, "b200_batch_patchify: uint8 images need mean / std");
+    for (int c = 0; c < C; ++c) B200_CHECK_ARG(std[c] != 0.f, "b200_batch_patchify: std[%d] is zero", c);
+  }
+  const Norm8 nrm = make_norm8(mean, std, C);
+  const int gh = (H + p - 1) / p, gw = (W + p - 1) / p;          // pad=True: ragged edges are zero-padded
+  const long long total = static_cast<long long>(B) * gh * gw * (Kpad / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  auto* o = reinterpret_cast<__nv_bfloat16*>(patches);
+  const int g = static_cast<int>(blocks);
+  if (img_dtype == B200_DTYPE_U8) naflex_patchify_kernel<0><<<g, 256, 0, st>>>(img, o, B, C, H, W, p, gh, gw, Kpad, channels_last, nrm);
+  else if (img_dtype == B200_DTYPE_BF16) naflex_patchify_kernel<1><<<g, 256, 0, st>>>(img, o, B, C, H, W, p, gh, gw, Kpad, channels_last, nrm);
+  else naflex_patchify_kernel<2><<<g, 256, 0, st>>>(img, o, B, C, H, W, p, gh, gw, Kpad, channels_last, nrm);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+extern "C" int b200_patches_u8(const void* patches_u8, void* out, int64_t rows, int32_t K, int32_t Kpad, int32_t C,
+                               int32_t channels_last, const float* mean, const float* std, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(patches_u8 && out && mean && std && rows > 0 && K > 0 && C > 0 && C <= 8 && K % C == 0,
+                 "b200_patches_u8: bad arguments (1 <= C <= 8, K a multiple of C)");
+  B200_CHECK_ARG(Kpad % 8 == 0 && Kpad >= K, "b200_patches_u8: Kpad=%d must be a multiple of 8 and >= K", Kpad);
+  for (int c = 0; c < C; ++c) B200_CHECK_ARG(std[c] != 0.f, "b200_patches_u8: std[%d] is zero", c);
+  const Norm8 nrm = make_norm8(mean, std, C);
+  const long long total = rows * (Kpad / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  patches_u8_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(patches_u8),
+                                                              reinterpret_cast<__nv_bfloat16*>(out), rows, K, Kpad, C, channels_last, nrm);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
 
 extern "C" int b200_act_bwd(const void* dy, const void* pre, void* dpre, int64_t n, int32_t act, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);

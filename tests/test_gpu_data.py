@@ -65,3 +65,90 @@ def test_models_take_uint8_batches_from_the_prefetch_loader():
         assert torch.equal(g1["patch_embed.proj.weight"] != 0, vit.patch_embed.proj.weight.grad != 0)
     finally:
         ops.set_input_norm(None)
+
+
+# ------------------------------------------------------------------------------------------------ NaFlex input tail
+def _timm_batch_patchify():
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from oracle import install_ref
+    if not install_ref.add_to_path():
+        pytest.skip("oracle/_ref (the installed reference) is missing")
+    from timm.models.naflexvit import batch_patchify
+    return batch_patchify
+
+
+@pytest.mark.parametrize("p,H,W", [(16, 64, 48), (14, 56, 70), (16, 50, 37), (8, 40, 40)])
+@pytest.mark.parametrize("channels_last", [True, False])
+def test_batch_patchify_matches_timms_function(p, H, W, channels_last):
+    """b200_batch_patchify == timm.models.naflexvit.batch_patchify (the unmodified function, pad=True) on bf16 / fp32 images
+    (values copied: bit-exact) and, for uint8 images, == normalise-in-fp32 -> batch_patchify -> bf16 (bit-exact too; the
+    zero PADDING pixels of a ragged edge are normalised like any other zero pixel, as in the reference order of operations
+    pad(normalise(x)) only when the image is patchified BEFORE normalisation -- the loader's order)."""
+    from b200timm import ops
+    ref_fn = _timm_batch_patchify()
+    torch.manual_seed(p + H)
+    img = torch.randn(3, 3, H, W, device="cuda")
+    for t in (img, img.bfloat16()):
+        got, grid = ops.batch_patchify(t, p, channels_last=channels_last)
+        want, rgrid = ref_fn(t.float(), (p, p), pad=True, channels_last=channels_last)
+        K = 3 * p * p
+        assert tuple(grid) == tuple(rgrid)
+        assert torch.equal(got[:, :K].float(), want.reshape(-1, K).bfloat16().float())
+        assert not got[:, K:].any()
+    u8 = torch.randint(0, 256, (3, 3, H, W), dtype=torch.uint8, device="cuda")
+    ops.set_input_norm(MEAN, STD)
+    try:
+        got, _ = ops.batch_patchify(u8, p, channels_last=channels_last)
+        # the NaFlex pipeline patchifies uint8 images in the dataset and normalises the PATCHES in the loader
+        raw, _ = ref_fn(u8.float(), (p, p), pad=True, channels_last=channels_last)           # [B, N, K] of 0..255 values
+        K = 3 * p * p
+        v = raw.view(3, -1, p * p, 3) if channels_last else raw.view(3, -1, 3, p * p)
+        shape = (1, 1, 1, 3) if channels_last else (1, 1, 3, 1)
+        mean = torch.tensor([m * 255 for m in MEAN], device="cuda").view(shape)
+        std = torch.tensor([s * 255 for s in STD], device="cuda").view(shape)
+        want = v.sub(mean).div(std).reshape(-1, K).bfloat16()
+        assert torch.equal(got[:, :K], want)
+        # the loader's already-cut uint8 patches through b200_patches_u8: the same values
+        if channels_last:
+            got2 = ops.patches_u8(raw.to(torch.uint8).contiguous(), 3, channels_last=True)
+            assert torch.equal(got2[:, :K], want) and not got2[:, K:].any()
+    finally:
+        ops.set_input_norm(None)
+
+
+def test_naflex_model_takes_images_and_uint8_patch_dicts():
+    """The mirror NaFlexVit on (a) an NCHW image batch (batch_patchify fused into the gather), (b) the loader's uint8 patch
+    dict (normalisation fused) -- both equal the forward on the explicitly prepared bf16 patch dict."""
+    from b200timm import data as BD, ops
+    from b200timm.naflexvit import NaFlexVit
+    ref_fn = _timm_batch_patchify()
+    torch.manual_seed(0)
+    model = NaFlexVit(patch_size=16, embed_dim=128, depth=2, num_heads=2, num_classes=10, pos_embed_grid_size=(4, 4))
+    model = model.cuda().to(torch.bfloat16).eval()
+    img = torch.randn(3, 3, 64, 48, device="cuda").bfloat16()
+    patches, (gh, gw) = ref_fn(img, (16, 16))
+    ys, xs = torch.meshgrid(torch.arange(gh, device="cuda"), torch.arange(gw, device="cuda"), indexing="ij")
+    coord = torch.stack([ys, xs], -1).reshape(1, -1, 2).expand(3, -1, -1).contiguous()
+    valid = torch.ones(3, gh * gw, dtype=torch.bool, device="cuda")
+    with torch.no_grad():
+        want = model(patches, coord, valid)
+        got = model(img)
+        assert torch.equal(got, want)
+        u8 = torch.randint(0, 256, (3, 3, 64, 48), dtype=torch.uint8, device="cuda")
+        raw, _ = ref_fn(u8.float(), (16, 16))
+        raw_u8 = raw.to(torch.uint8).contiguous()
+        loader = BD.NaFlexPrefetchLoader([({"patches": raw_u8.cpu(), "patch_coord": coord.cpu(), "patch_valid": valid.cpu()},
+                                           torch.zeros(3, dtype=torch.long))], mean=MEAN, std=STD)
+        try:
+            (d, tgt), = list(loader)
+            assert d["patches"].dtype == torch.uint8 and d["patches"].is_cuda
+            got = model(d)
+            mean = torch.tensor([m * 255 for m in MEAN], device="cuda").view(1, 1, 1, 3)
+            std = torch.tensor([s * 255 for s in STD], device="cuda").view(1, 1, 1, 3)
+            norm = raw.view(3, -1, 256, 3).sub(mean).div(std).reshape(3, -1, 768).bfloat16()
+            assert torch.equal(got, model(norm, coord, valid))
+        finally:
+            ops.set_input_norm(None)
