@@ -5,9 +5,13 @@
 //     (2 x 112 columns) next to the five persistent accumulators dV, dK (current key tile), dQ (both halves):
 //     112 + 112(+pad) + 64*4 = 512 columns exactly;
 //   * S^T and dP^T of a (key tile, query half) step are issued together, one pass over both produces P^T and dS^T
-//     (bf16 core matrices in smem), split by columns across two warpgroups (8 warps);
-//   * a dedicated issuer warp queues [dV += P^T dO, dK += dS^T Q, dQ += dS K] of step i followed immediately by
-//     [S^T, dP^T] of step i+1, so the MMA pipe never drains between steps.
+//     (bf16 core matrices in smem), split by columns across two warpgroups (8 warps).  The pass is bound by the TMEM read
+//     bandwidth (~64 B/clk/SM: 115 KB of fp32 S^T / dP^T per step ~ 1800 of its ~2450 cycles, tools/attn_bwd_trace.py) --
+//     a 16-warp variant (4 column groups) was measured and is NOT faster (319 vs 285 us per launch);
+//   * a dedicated issuer warp queues [S^T, dP^T] of step i+1 FIRST and [dV += P^T dO, dK += dS^T Q, dQ += dS K] of step i
+//     behind them: the compute warps start step i+1 (TMEM reads of S^T / dP^T at ~64 B/clk are the longest part of a
+//     step) while the tensor core is still busy with step i's accumulations; a "smem free" barrier committed behind
+//     those accumulations tells the compute warps when P^T / dS^T of step i may be overwritten.
 // No atomics: dK / dV of a key tile accumulate over the query halves, dQ of a query half over the key tiles, all in TMEM.
 // Persistent: one CTA per SM loops over (image, head) items; as soon as an item's last MMA has completed the issuer
 // requests the NEXT item's Q / K / V / dO, so those loads run under the current item's dV / dK / dQ read-out and stores.
@@ -29,8 +33,8 @@ constexpr int kPB = (kQH / 8) * 2048;            // 28672
 constexpr int kOffDS = kOffP + kPB;              // dS^T: 16 chunks (the dQ MMA reads a full 128-query M tile)
 constexpr int kDSB = 16 * 2048;
 constexpr int kOffLse = kOffDS + kDSB;
-constexpr int kOffDelta = kOffLse + 2 * kQH * 4;
-constexpr int kOffOut = (kOffDelta + 2 * kQH * 4 + 1023) / 1024 * 1024;   // 8 warps x (32 rows x 128 B) output staging
+constexpr int kOffDelta = kOffLse + 2 * 2 * kQH * 4;     // lse / delta: two buffers each (current item | next item)
+constexpr int kOffOut = (kOffDelta + 2 * 2 * kQH * 4 + 1023) / 1024 * 1024;   // 8 warps x (32 rows x 128 B) output staging   // 8 warps x (32 rows x 128 B) output staging
 constexpr int kOffBar = kOffOut + 8 * 4096;
 constexpr int kSmemTotal = kOffBar + 64 + 1024;
 constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ0 = 384, kColDQ1 = 448;
@@ -42,6 +46,7 @@ struct AttnBwd2Params {
   const float* delta;
   float* dbias;          // optional fp32 [3 * H * 64]: += column sums of dqkv (the qkv bias gradient), from the staging tiles
   __nv_bfloat16* dqkv;
+  long long* trace;      // debug (b200_set_trace(2, buf)): 16 cycle counters per CTA, nullptr in production
   const int* kv_len;
   int B, N, H;
   float scale, scale_log2e;
@@ -136,7 +141,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   uint64_t* bar_p = bar_ld + 2;       // compute -> issuer: P^T / dS^T of the step are in smem (count 256)
   uint64_t* bar_fin = bar_ld + 3;     // issuer -> compute: every MMA of the item has completed
   uint64_t* bar_tail = bar_ld + 4;    // compute -> issuer: the item's dV / dK / dQ accumulators have been read (count 256)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ld + 5);
+  uint64_t* bar_free = bar_ld + 5;    // issuer -> compute: the step's dV / dK / dQ MMAs are done (P^T / dS^T smem reusable)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_ld + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, H = p.H;
@@ -144,11 +150,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   auto item_kvlen = [&](int item) {
     return p.kv_len != nullptr ? max(1, min(p.kv_len[item / H], N)) : N;
   };
-  auto load_stats = [&](int item, int t0, int nthreads) {   // lse (log2 domain) / delta rows of an item -> smem
+  auto load_stats = [&](int item, int buf, int t0, int nthreads) {   // lse (log2 domain) / delta rows of an item -> smem
     for (int q = t0; q < 2 * kQH; q += nthreads) {
       const long long idx = static_cast<long long>(item) * N + q;      // item = b * H + h
-      sLse[q] = (q < N) ? p.lse[idx] * 1.4426950408889634f : INFINITY;   // +inf -> P = 0 for padding queries
-      sDelta[q] = (q < N) ? p.delta[idx] : 0.f;
+      sLse[buf * 2 * kQH + q] = (q < N) ? p.lse[idx] * 1.4426950408889634f : INFINITY;   // +inf -> P = 0 for padding queries
+      sDelta[buf * 2 * kQH + q] = (q < N) ? p.delta[idx] : 0.f;
     }
   };
 
@@ -162,6 +168,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     mbar_init(bar_p, kComputeThreads);
     mbar_init(bar_fin, 1);
     mbar_init(bar_tail, kComputeThreads);
+    mbar_init(bar_free, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -169,7 +176,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
-  if (static_cast<int>(blockIdx.x) < num_items) load_stats(blockIdx.x, tid, blockDim.x);
+  if (static_cast<int>(blockIdx.x) < num_items) load_stats(blockIdx.x, 0, tid, blockDim.x);
   for (int i = tid; i < 2048 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem + kOffPad)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -177,7 +184,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 8) {
+  if (warp == kComputeThreads / 32) {
     // ------------------------------------------------------------------ issuer (TMA + tcgen05.mma), one thread
     if (lane == 0) {
       constexpr uint32_t idesc_sd = make_idesc_bf16(128, kQH, false, false);
@@ -205,17 +212,38 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       if (static_cast<int>(blockIdx.x) < num_items) load_item(blockIdx.x);
       int it = 0;
       uint32_t gs = 0;                       // global step counter: phase of bar_sd / bar_p
+      const bool tr = p.trace != nullptr;
+      long long w_ld = 0, w_p = 0, w_tail = 0, w_fin = 0, c0 = 0;
+      const long long c_begin = tr ? clock64() : 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int num_steps = ((item_kvlen(item) + 127) / 128) * 2;
+        if (tr) c0 = clock64();
         mbar_wait(bar_ld, it & 1);
+        if (tr) w_ld += clock64() - c0;
+        if (item + static_cast<int>(gridDim.x) < num_items) {      // the next item's operands start moving HBM -> L2 now
+          const int nb = (item + gridDim.x) / H, nh = (item + gridDim.x) - nb * H;
+          tma_prefetch_2d(&tm_qkv, nh * kHd, nb * N);
+          tma_prefetch_2d(&tm_qkv, (H + nh) * kHd, nb * N);
+          tma_prefetch_2d(&tm_qkv, (2 * H + nh) * kHd, nb * N);
+          tma_prefetch_2d(&tm_do, nh * kHd, nb * N);
+        }
         tc_fence_after();
         issue_sd(0);
         umma_commit(bar_sd);
         for (int step = 0; step < num_steps; ++step, ++gs) {
           const int kt = step >> 1, qh = step & 1;
+          if (tr) c0 = clock64();
           mbar_wait(bar_p, gs & 1);
+          if (tr) { const long long c = clock64(); w_p += c - c0; c0 = c; }
           if (step == 0 && it > 0) mbar_wait(bar_tail, (it - 1) & 1);   // previous item's accumulators were read out
+          if (tr) w_tail += clock64() - c0;
           tc_fence_after();
+          // the compute warps are done with S^T / dP^T of this step: the next step's go first, so that their softmax pass
+          // (bound by the TMEM reads) runs under this step's accumulations
+          if (step + 1 < num_steps) {
+            issue_sd(step + 1);
+            umma_commit(bar_sd);
+          }
           // dV_kt (+)= P^T dO_qh ; dK_kt (+)= dS^T Q_qh   (A: K-major core matrices, 8-query chunks 2048 B apart)
           const uint64_t pd = make_smem_desc(smem_u32(sP), 2048, 128, kLayoutNone);
           const uint64_t dsd = make_smem_desc(smem_u32(sDS), 2048, 128, kLayoutNone);
@@ -236,19 +264,21 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           for (int k = 0; k < 128 / 16; ++k)
             umma_ss(tmem_base + (qh == 0 ? kColDQ0 : kColDQ1), ad + static_cast<uint64_t>(k * (256 >> 4)),
                     kb + static_cast<uint64_t>(k * (2048 >> 4)), idesc_dq, (kt > 0 || k > 0) ? 1u : 0u);
-          if (step + 1 < num_steps) {
-            issue_sd(step + 1);
-            umma_commit(bar_sd);
-          } else {
-            umma_commit(bar_fin);
-          }
+          umma_commit(bar_free);              // P^T / dS^T of this step have been consumed
+          if (step + 1 == num_steps) umma_commit(bar_fin);
         }
         // every MMA of this item has completed -> the operand tiles are free: fetch the next item under the stores
         const int next = item + gridDim.x;
         if (next < num_items) {
+          if (tr) c0 = clock64();
           mbar_wait(bar_fin, it & 1);
+          if (tr) w_fin += clock64() - c0;
           load_item(next);
         }
+      }
+      if (tr) {
+        long long* t = p.trace + blockIdx.x * 16;
+        t[8] = w_ld; t[9] = w_p; t[10] = w_tail; t[11] = w_fin; t[12] = clock64() - c_begin; t[15] = it;
       }
     }
   } else {
@@ -260,41 +290,76 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     const long long tok_stride = 3LL * H * kHd;
     uint8_t* ostg = smem + kOffOut + warp * 4096;
     const int wrow = (warp & 3) * 32;                 // first accumulator row of this warp
+    const int c0 = wg * 56;                           // first query column (within the half) of this warpgroup
     int it = 0;
     uint32_t gs = 0;
+    const bool tr = p.trace != nullptr && tid == 0;
+    long long ph[6] = {0, 0, 0, 0, 0, 0}, ck = tr ? clock64() : 0;   // wait S/dP | prev-tile store | softmax pass | wait fin | tail stores | stats
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
     const int b = item / H, h = item - b * H;
     const int kvlen = item_kvlen(item);
     const int num_kt = (kvlen + 127) / 128;
     const int num_steps = num_kt * 2;
+    const int sb = it & 1;                          // which lse / delta buffer holds this item's statistics
+    // the next item's statistics: requested now (one entry per thread), parked in registers, stored at the item's end
+    const int nitem = item + static_cast<int>(gridDim.x);
+    float n_lse = INFINITY, n_delta = 0.f;
+    if (nitem < num_items && tid < 2 * kQH && tid < N) {
+      n_lse = __ldg(p.lse + static_cast<long long>(nitem) * N + tid);
+      n_delta = __ldg(p.delta + static_cast<long long>(nitem) * N + tid);
+    }
     for (int step = 0; step < num_steps; ++step, ++gs) {
       const int kt = step >> 1, qh = step & 1;
       const int key = kt * 128 + rowt;
       const bool key_ok = key < kvlen;
       mbar_wait(bar_sd, gs & 1);
       tc_fence_after();
+      if (tr) { const long long c = clock64(); ph[0] += c - ck; ck = c; }
+      bool freed = false;               // waited for the previous step's accumulations (P^T / dS^T smem free, dV / dK final)
       if (qh == 0 && kt > 0) {
-        // dV / dK of the previous key tile are complete (their MMAs were queued ahead of this step's S^T / dP^T)
+        // dV / dK of the previous key tile: their MMAs are queued BEHIND this step's S^T / dP^T -> wait for them
+        mbar_wait(bar_free, (gs - 1) & 1);
+        tc_fence_after();
+        freed = true;
         const int prow0 = (kt - 1) * 128 + wrow;
         store_tile64(ostg, tmem_row + (wg == 0 ? kColDV : kColDK), &tm_out32, ((wg == 0 ? 2 : 1) * H + h) * kHd, prow0, b,
                      lane, prow0 < N, p.dbias);
       }
-      const int c0 = wg * 56;                        // first query column (within the half) of this warpgroup
-      const float* l2 = sLse + qh * kQH + c0;
-      const float* dl = sDelta + qh * kQH + c0;
+      if (tr) { const long long c = clock64(); ph[1] += c - ck; ck = c; }
+      const float* l2 = sLse + sb * 2 * kQH + qh * kQH + c0;
+      const float* dl = sDelta + sb * 2 * kQH + qh * kQH + c0;
       uint8_t* prow = sP + (c0 >> 3) * 2048 + rowt * 16;
       uint8_t* dsrow = sDS + (c0 >> 3) * 2048 + rowt * 16;
-      {
+      // Dead work is skipped instead of computed: the warp's 32 key rows all lie past kv_len (second key tile of N = 197:
+      // keys 224..255), or a chunk's queries all lie past N (second query half: 200..223) -> P^T = dS^T = 0 without
+      // touching TMEM.  The pass is bound by the TMEM read bandwidth, so this is ~22 % of it at N = 197.
+      const bool rows_dead = kt * 128 + (warp & 3) * 32 >= kvlen;
+      const int q_a = qh * kQH + c0;
+      auto zero_groups = [&](int g0, int ng) {
+        if (!freed && gs > 0) { mbar_wait(bar_free, (gs - 1) & 1); freed = true; }
+        for (int g = g0; g < g0 + ng; ++g) {
+          *reinterpret_cast<uint4*>(prow + g * 2048) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dsrow + g * 2048) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if (rows_dead || q_a >= N) {
+        zero_groups(0, 4);
+      } else {
         uint32_t s[32], d[32];
         tmem_ld_x32(tmem_row + kColS + c0, s);
         tmem_ld_x32(tmem_row + kColDP + c0, d);
         tmem_ld_wait_x32(s);
         tmem_ld_wait_x32(d);
+        // first write into P^T / dS^T: the previous step's dV / dK / dQ MMAs must have finished reading them (their
+        // completion normally lies well inside the TMEM reads above)
+        if (!freed && gs > 0) { mbar_wait(bar_free, (gs - 1) & 1); freed = true; }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           pds8(s + g * 8, d + g * 8, l2 + g * 8, dl + g * 8, sc2, scale2, key_ok, prow + g * 2048, dsrow + g * 2048);
       }
-      {
+      if (rows_dead || q_a + 32 >= N) {
+        zero_groups(4, 2);
+      } else {
         uint32_t s[16], d[16];
         tmem_ld_x16(tmem_row + kColS + c0 + 32, s);
         tmem_ld_x16(tmem_row + kColDP + c0 + 32, d);
@@ -305,7 +370,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           pds8(s + g * 8, d + g * 8, l2 + 32 + g * 8, dl + 32 + g * 8, sc2, scale2, key_ok, prow + (4 + g) * 2048,
                dsrow + (4 + g) * 2048);
       }
-      {
+      if (rows_dead || q_a + 48 >= N) {
+        zero_groups(6, 1);
+      } else {
         uint32_t s[8], d[8];
         tmem_ld_x8(tmem_row + kColS + c0 + 48, s);
         tmem_ld_x8(tmem_row + kColDP + c0 + 48, d);
@@ -316,10 +383,12 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar_p);
+      if (tr) { const long long c = clock64(); ph[2] += c - ck; ck = c; }
     }
     // ---- tail: last key tile's dV / dK, then dQ
     mbar_wait(bar_fin, it & 1);
     tc_fence_after();
+    if (tr) { const long long c = clock64(); ph[3] += c - ck; ck = c; }
     {
       const int prow0 = (num_kt - 1) * 128 + wrow;
       store_tile64(ostg, tmem_row + (wg == 0 ? kColDV : kColDK), &tm_out32, ((wg == 0 ? 2 : 1) * H + h) * kHd, prow0, b, lane,
@@ -333,6 +402,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     }
     tc_fence_before();
     mbar_arrive(bar_tail);            // accumulators read: the issuer may start the next item's dV / dK / dQ MMAs
+    if (tr) { const long long c = clock64(); ph[4] += c - ck; ck = c; }
     // keys beyond kv_len (padding keys of a NaFlex batch) never entered a tile: their dK / dV are zero
     for (int key = num_kt * 128 + tid; key < N; key += kComputeThreads) {
       for (int which = 1; which <= 2; ++which) {
@@ -342,12 +412,19 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       }
     }
     // the next item's softmax statistics (every compute thread is past its last use of this item's)
-    if (item + static_cast<int>(gridDim.x) < num_items) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      load_stats(item + gridDim.x, tid, kComputeThreads);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (nitem < num_items) {
+      if (tid < 2 * kQH) {
+        sLse[(sb ^ 1) * 2 * kQH + tid] = n_lse * 1.4426950408889634f;     // +inf stays +inf (padding queries -> P = 0)
+        sDelta[(sb ^ 1) * 2 * kQH + tid] = n_delta;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // visible to every compute thread before the next item reads them
     }
+    if (tr) { const long long c = clock64(); ph[5] += c - ck; ck = c; }
     }   // items
+    if (tr) {
+      long long* t = p.trace + blockIdx.x * 16;
+      for (int i = 0; i < 6; ++i) t[i] = ph[i];
+    }
     if (lane == 0) tma_store_wait<0>();
   }
 
@@ -358,6 +435,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     tmem_dealloc(tmem_base, 512);
   }
 }
+
+long long* g_attn_bwd_trace = nullptr;
 
 int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
                      const int32_t* kv_len, int B, int N, int H, float scale, float* dbias, cudaStream_t st) {
@@ -388,6 +467,7 @@ int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const 
   AttnBwd2Params p;
   p.lse = lse; p.delta = delta; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv); p.kv_len = kv_len;
   p.dbias = dbias;
+  p.trace = g_attn_bwd_trace;
   p.B = B; p.N = N; p.H = H; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {

@@ -673,11 +673,12 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
 
 using namespace b200;
 
-namespace b200 { extern long long* g_attn_fwd_trace; }
+namespace b200 { extern long long* g_attn_fwd_trace; extern long long* g_attn_bwd_trace; }
 
 extern "C" void b200_set_trace(int32_t kernel, void* device_buf) {
   if (kernel == 0) g_gemm_trace = reinterpret_cast<unsigned long long*>(device_buf);
   else if (kernel == 1) b200::g_attn_fwd_trace = reinterpret_cast<long long*>(device_buf);
+  else if (kernel == 2) b200::g_attn_bwd_trace = reinterpret_cast<long long*>(device_buf);
 }
 
 extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
