@@ -356,6 +356,11 @@ B200_API int b200_act_bwd(const void* dy, const void* pre, void* dpre, int64_t n
  * gradient workspace) or bf16, n elements (multiple of 8), 16-byte aligned; scale = 1 / world_size.  The caller orders
  * zeroing / pushes / reads with peer barriers (b200timm/grad_sync.py).  ABI >= 6.                                      */
 B200_API int b200_grad_push(const void* src, int32_t src_dtype, void* dst_multicast, int64_t n, float scale, void* stream);
+/* Replica consistency after the pushes: the adds land in arrival order and bf16 addition is not associative, so with more
+ * than two ranks the copies may differ in the last bit.  Rank r re-publishes ITS slice of the buffer (`src_local`: the
+ * slice in this rank's copy, `dst_multicast`: the same slice's multicast address, `bytes` a multiple of 16) to every rank
+ * with multimem.st -- afterwards all copies are bit-identical, as after an all-reduce.                                  */
+B200_API int b200_grad_publish(const void* src_local, void* dst_multicast, int64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

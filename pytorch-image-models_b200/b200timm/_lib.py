@@ -117,6 +117,7 @@ SIGNATURES = {
     "b200_batch_patchify": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200_patches_u8": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200_act_bwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp]),
+    "b200_grad_publish": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     "b200_grad_push": (ctypes.c_int, [_vp, _i32, _vp, ctypes.c_int64, _f32, _vp]),
     "b200_cross_entropy_fwd": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _f64, ctypes.c_int64, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "b200_cross_entropy_bwd": (ctypes.c_int, [_vp, _i32, _vp, _vp, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),

@@ -16,7 +16,10 @@ parameter is a persistent view into the buffer: the optimizer kernels read the r
 Per step:  begin()   zero the buffer (and the tail staging buffer), peer barrier A (nobody pushes into a buffer that is
                      still being read or not yet zeroed)
            backward  BlockFn pushes each block's slot; autograd accumulates the tail gradients into a LOCAL staging buffer
-           finish()  push the tail, peer barrier B (every rank's pushes have landed), p.grad -> views of the flat buffer
+           finish()  push the tail, peer barrier B (every rank's pushes have landed); with more than two ranks every rank
+                     re-publishes its 1 / world slice to all (the adds land in arrival order and bf16 addition is not
+                     associative: this makes the copies bit-identical, as DDP's all-reduce does), barrier C;
+                     p.grad -> views of the flat buffer
 
 Memory / streams / symmetric allocation / the barrier come from torch.distributed._symmetric_memory (plumbing, like
 torch.distributed itself); the exchange is the kernel.  Needs NVLink multicast (NVSwitch) -- raises B200Error otherwise.
@@ -186,6 +189,18 @@ class PeerGradSync:
         if self.tail:
             grad_push(self.tail_local, self.mc_ptr + 2 * self.tail_offset, self.total - self.tail_offset, 1.0 / self.world)
         self.handle.barrier(channel=1)
+        if self.world > 2:
+            # slice r of every copy := rank r's sum (multimem.st), so that all replicas apply the SAME gradient
+            per = -(-self.total // self.world)
+            per = (per + 7) // 8 * 8
+            rank = dist.get_rank(self.group)
+            lo = min(rank * per, self.total)
+            hi = min(lo + per, self.total)
+            if hi > lo:
+                rc = _lib.load().b200_grad_publish(self.flat.data_ptr() + 2 * lo, self.mc_ptr + 2 * lo, 2 * (hi - lo), ops._stream())
+                _lib.check(rc, "b200_grad_publish")
+                ops._count()
+            self.handle.barrier(channel=2)
         self._bind(flat=True)
 
     def abort(self):

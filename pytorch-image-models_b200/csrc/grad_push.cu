@@ -47,9 +47,40 @@ __global__ void __launch_bounds__(256) grad_push_kernel(const void* __restrict__
   asm volatile("fence.acq_rel.sys;" ::: "memory");
 }
 
+// Replica consistency.  multimem.red.add applies the ranks' contributions to each copy in ARRIVAL order, and bf16 addition
+// is not associative: with more than two ranks the copies can differ in the last bit.  Data-parallel replicas must stay
+// bit-identical (DDP's all-reduce guarantees it), so after the pushes every rank re-publishes ITS 1 / world_size slice of
+// the buffer to all ranks with multimem.st: slice r of every copy becomes rank r's sum.  16 bytes per thread and step.
+__global__ void __launch_bounds__(256) grad_publish_kernel(const uint4* __restrict__ src_local, uint4* dst_mc, long long nvec) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 v = src_local[i];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_mc + i), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+  }
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_grad_publish(const void* src_local, void* dst_multicast, int64_t bytes, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(src_local != nullptr && dst_multicast != nullptr && bytes > 0, "b200_grad_publish: null pointer or empty range");
+  B200_CHECK_ARG(bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(src_local) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(dst_multicast) & 15) == 0,
+                 "b200_grad_publish: the range must be 16-byte aligned and a multiple of 16 bytes");
+  const long long nvec = bytes / 16;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 4;
+  if (blocks > cap) blocks = cap;
+  grad_publish_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(reinterpret_cast<const uint4*>(src_local),
+                                                                      reinterpret_cast<uint4*>(dst_multicast), nvec);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
 
 extern "C" int b200_grad_push(const void* src, int32_t src_dtype, void* dst_multicast, int64_t n, float scale, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);

@@ -475,6 +475,164 @@ layernorm_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
   }
 }
 
+// Two CTAs per SM (16 warps hide the per-row dependency chain better than 8): <= 128 registers per thread, so xhat / g are
+// recomputed in the dx pass and the weight vector is re-read (L1) per row instead of living in registers.
+template <int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
+layernorm_bwd_ring2_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                          const void* __restrict__ w, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
+                          __nv_bfloat16* __restrict__ dx, float* __restrict__ ws, long long rows, int cols,
+                          int param_f32, int kLnRing) {
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  const bool rms = (param_f32 & 2) != 0;
+  param_f32 &= 1;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int narr = dres != nullptr ? 3 : 2;
+  const uint32_t row_bytes = static_cast<uint32_t>(cols) * 2u;
+  const uint32_t slot_bytes = 3u * row_bytes;
+  uint8_t* my_ring = ring_raw + static_cast<size_t>(warp) * kLnRing * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_raw + static_cast<size_t>(kLnWarps) * kLnRing * slot_bytes) + warp * kLnRing;
+  const long long warp_global = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
+  const long long warp_stride = static_cast<long long>(gridDim.x) * kLnWarps;
+  const int nvec = cols >> 3;
+  const float inv_n = 1.0f / static_cast<float>(cols);
+  if (lane == 0) {
+    for (int sidx = 0; sidx < kLnRing; ++sidx) mbar_init(&bars[sidx], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  auto issue = [&](long long row, int slot) {       // lane 0: request one row's x | dy | dres into ring slot `slot`
+    uint8_t* dst = my_ring + static_cast<size_t>(slot) * slot_bytes;
+    mbar_arrive_expect_tx(&bars[slot], narr * row_bytes);
+    bulk_load_1d(dst, x + row * cols, row_bytes, &bars[slot]);
+    bulk_load_1d(dst + row_bytes, dy + row * cols, row_bytes, &bars[slot]);
+    if (narr == 3) bulk_load_1d(dst + 2 * row_bytes, dres + row * cols, row_bytes, &bars[slot]);
+  };
+  if (lane == 0) {
+    for (int sidx = 0; sidx < kLnRing; ++sidx) {
+      const long long r = warp_global + sidx * warp_stride;
+      if (r < rows) issue(r, sidx);
+    }
+  }
+  // Packed fp32 pairs (FFMA2 / FADD2 / FMUL2: two lanes per instruction) for all per-element math; xhat and g = dy * w of the
+  // row stay in registers between the statistics pass and the dx pass (one CTA per SM: 255 registers per thread are there).
+  f32x2 dw_acc[VPL][4], db_acc[VPL][4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + i * 32;
+    (void)vec;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dw_acc[i][j] = splat(0.f); db_acc[i][j] = splat(0.f); }
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (long long row = warp_global; row < rows; row += warp_stride) {
+    const float mean = rms ? 0.f : __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    mbar_wait(&bars[slot], phase);
+    const uint8_t* src = my_ring + static_cast<size_t>(slot) * slot_bytes;
+    uint4 xr[VPL], dyr[VPL], rr[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        xr[i] = *reinterpret_cast<const uint4*>(src + vec * 16);
+        dyr[i] = *reinterpret_cast<const uint4*>(src + row_bytes + vec * 16);
+        if (narr == 3) rr[i] = *reinterpret_cast<const uint4*>(src + 2 * row_bytes + vec * 16);
+      }
+    }
+    // the slot's data are in registers: hand it back to the copy engine for the row kLnRing iterations ahead
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const long long r = row + kLnRing * warp_stride;
+      if (r < rows) issue(r, slot);
+    }
+    const f32x2 rstd2 = splat(rstd), nmr2 = splat(-mean * rstd);
+    f32x2 s1 = splat(0.f), s2 = splat(0.f);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        const uint32_t xw[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w}, dw_[4] = {dyr[i].x, dyr[i].y, dyr[i].z, dyr[i].w};
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 1.f;
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const f32x2 dyv = bf16x2_to_f32x2(dw_[j]);
+          const f32x2 xh = fma2(bf16x2_to_f32x2(xw[j]), rstd2, nmr2);    // (x - mean) * rstd
+          const f32x2 gg = mul2(dyv, pk(t[2 * j], t[2 * j + 1]));
+          s1 = add2(s1, gg);
+          s2 = fma2(gg, xh, s2);
+          dw_acc[i][j] = fma2(dyv, xh, dw_acc[i][j]);
+          db_acc[i][j] = add2(db_acc[i][j], dyv);
+        }
+      }
+    }
+    float s1a, s1b, s2a, s2b;
+    upk(s1, s1a, s1b);
+    upk(s2, s2a, s2b);
+    const float m1 = rms ? 0.f : warp_sum(s1a + s1b) * inv_n;
+    const float m2 = warp_sum(s2a + s2b) * inv_n;
+    // dx = rstd * (g - m1 - xhat * m2) = g * rstd + (xhat * (-m2 * rstd) - m1 * rstd)
+    const f32x2 a2 = splat(-m2 * rstd), c2 = splat(-m1 * rstd);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vec = lane + i * 32;
+      if (vec < nvec) {
+        const uint32_t rw[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
+        const uint32_t xw[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w}, dw_[4] = {dyr[i].x, dyr[i].y, dyr[i].z, dyr[i].w};
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 1.f;
+        if (w != nullptr) load8_rt(w, param_f32, vec * 8, t);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const f32x2 xh = fma2(bf16x2_to_f32x2(xw[j]), rstd2, nmr2);
+          const f32x2 gg = mul2(bf16x2_to_f32x2(dw_[j]), pk(t[2 * j], t[2 * j + 1]));
+          f32x2 v = fma2(gg, rstd2, fma2(xh, a2, c2));
+          if (narr == 3) v = add2(v, bf16x2_to_f32x2(rw[j]));
+          float lo, hi;
+          upk(v, lo, hi);
+          o[j] = pack_bf16(lo, hi);
+        }
+        *reinterpret_cast<uint4*>(dx + row * cols + vec * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (++slot == kLnRing) { slot = 0; phase ^= 1; }
+  }
+  // per-CTA partial sums of dgamma / dbeta: the ring memory is dead once every warp has left its loop
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(ring_raw);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vec = lane + i * 32;
+    if (vec < nvec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo, hi;
+        upk(dw_acc[i][j], lo, hi);
+        red[warp * 2 * cols + vec * 8 + 2 * j] = lo;
+        red[warp * 2 * cols + vec * 8 + 2 * j + 1] = hi;
+        upk(db_acc[i][j], lo, hi);
+        red[warp * 2 * cols + cols + vec * 8 + 2 * j] = lo;
+        red[warp * 2 * cols + cols + vec * 8 + 2 * j + 1] = hi;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kLnWarps; ++kk) sacc += red[kk * 2 * cols + c];
+    ws[static_cast<long long>(blockIdx.x) * 2 * cols + c] = sacc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Wide rows (2048 < cols <= 8192: the inner norm of an Mlp / gated Mlp over the HIDDEN width -- Mlp(norm_layer=...),
 // `scale_mlp_norm`, EVA-02's SwiGLU norm; timm/layers/mlp.py:44, 100, 148): one CTA of 256 threads per row, the row's
@@ -680,18 +838,21 @@ static int ln_bwd_grid(long long rows) {
   long long cap = static_cast<long long>(sm_count()) * 2;
   return static_cast<int>(want < cap ? want : cap);
 }
-static bool ln_use_ring() {
-  static const bool on = [] { const char* e = getenv("B200_LN_BWD_RING"); return e == nullptr || e[0] != '0'; }();
-  return on;
+static int ln_ring_mode() {       // 0 = register kernel, 1 = ring (1 CTA / SM, deep ring), 2 = ring (2 CTAs / SM, 2 slots; measured equal: 71.9 vs 73.4 us); default 1
+  static const int m = [] { const char* e = getenv("B200_LN_BWD_RING"); return e == nullptr ? 1 : atoi(e); }();
+  return m;
 }
-static int ln_ring_grid(long long rows) {       // one CTA per SM (its ring fills the shared memory)
+static bool ln_use_ring() { return ln_ring_mode() != 0; }
+static bool ln_ring_lean(int cols) { return ln_ring_mode() == 2 && cols <= 768; }    // 2 x (8 warps x 2 slots x 3 rows) fits up to 768 columns
+static int ln_ring_grid(long long rows, int cols = 1024) {       // CTAs per SM: 1 (deep ring) or 2 (lean)
   long long want = (rows + kLnWarps - 1) / kLnWarps;
-  long long cap = static_cast<long long>(sm_count());
+  long long cap = static_cast<long long>(sm_count()) * (ln_ring_lean(cols) ? 2 : 1);
   return static_cast<int>(want < cap ? want : cap);
 }
 static int ln_ring_depth(int cols) {        // as many row slots per warp as ~220 KB of shared memory hold (768 columns: 6)
   static const int forced = [] { const char* e = getenv("B200_LN_RING_DEPTH"); return e ? atoi(e) : 0; }();
   int d = (220 * 1024) / (kLnWarps * 3 * cols * 2);
+  if (ln_ring_lean(cols)) d = 2;
   if (forced > 0 && forced < d) d = forced;
   return d < 2 ? 2 : (d > 8 ? 8 : d);
 }
@@ -737,8 +898,10 @@ static int launch_bwd(const void* dy, const void* x, const void* w, const float*
   else if (VPL <= 4 && ln_use_ring() && (cols * 2) % 16 == 0) {
     // the shared-memory ring kernel (bulk copies keep 4 rows per warp in flight)
     const size_t rsmem = ln_ring_smem(cols);
-    B200_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_ring_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    layernorm_bwd_ring_kernel<VPL><<<ln_ring_grid(rows), threads, rsmem, st>>>(
+    auto kern = ln_ring_lean(cols) ? layernorm_bwd_ring2_kernel<VPL> : layernorm_bwd_ring_kernel<VPL>;
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    kern<<<ln_ring_grid(rows, cols), threads, rsmem, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), w, mean, rstd,
         reinterpret_cast<const __nv_bfloat16*>(dres), reinterpret_cast<__nv_bfloat16*>(dx), ws, rows, cols, pf32, ln_ring_depth(cols));
   } else if (VPL <= 4)   // wider rows would not fit their packed vectors + accumulators in 128 registers
@@ -847,7 +1010,7 @@ static int norm_bwd(const void* dy, const void* x, const void* weight, const flo
   B200_CUDA_OK(cudaGetLastError());
   if (dweight || dbias) {
     const bool ring = !xf && !dyf && vpl <= 4 && ln_use_ring() && (cols * 2) % 16 == 0;     // as launch_bwd chooses
-    const int nrows = ring ? ln_ring_grid(rows) : ln_bwd_grid(rows);
+    const int nrows = ring ? ln_ring_grid(rows, cols) : ln_bwd_grid(rows);
     reduce_rows_kernel<<<(2 * cols + 31) / 32, 256, 0, st>>>(workspace, dweight, dbias, nrows, cols);
     B200_CUDA_OK(cudaGetLastError());
   }
