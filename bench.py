@@ -96,15 +96,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def recorded_traffic():
-    """roofline.traffic: DRAM bytes per GEMM launch (mean over the four block GEMMs) from the committed ncu --set full
-    capture -- bench.py cannot run ncu itself, so the number is the recorded one and says where it came from."""
+def recorded_traffic(train=False):
+    """roofline.traffic: DRAM bytes per GEMM launch (mean over the block's GEMMs: 4 forward ones for inference, all 12 of
+    forward + backward for training) from the committed ncu --set full captures -- bench.py cannot run ncu itself, so the
+    number is the recorded one and says where it came from."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        g = t["gemm_bf16_kernel"]
-        return {"traffic": g["mean_traffic_mb"] * 1e6, "traffic_unit": "bytes/launch (mean of qkv, proj, fc1, fc2)",
-                "traffic_algorithmic": g["mean_algorithmic_mb"] * 1e6, "traffic_source": t["source"]}
+        g = t["gemm_bf16_kernel_train" if train else "gemm_bf16_kernel"]
+        return {"traffic": g["mean_traffic_mb"] * 1e6,
+                "traffic_unit": "bytes/launch (mean of the block's " + ("12 forward + backward GEMMs)" if train else "qkv, proj, fc1, fc2)"),
+                "traffic_algorithmic": g["mean_algorithmic_mb"] * 1e6, "traffic_source": g.get("source", t["source"])}
     except (OSError, KeyError, ValueError):
         return {"traffic": None}
 
@@ -407,13 +409,13 @@ def bench_infer(args, rank, world, dev, clocks=None):
     }
 
 
-def roofline_record(rec, peaks):
+def roofline_record(rec, peaks, train=False):
     g = rec.pop("gemm")
     tf = g["flops"] / (g["ms"] * 1e9) if g["ms"] > 0 else 0.0
     sustained, burst = peaks["bf16_tflops_sustained"], peaks["bf16_tflops"]
     return {"bound": "tensor", "kernel": "gemm_bf16_kernel (CTA pairs, 256x256 tiles; every Linear's forward / dgrad / wgrad GEMM)",
             "achieved": round(tf, 1), "peak": sustained, "unit": "TFLOP/s", "frac": round(tf / sustained, 4),
-            "peak_burst": burst, "frac_burst": round(tf / burst, 4), **recorded_traffic(),
+            "peak_burst": burst, "frac_burst": round(tf / burst, 4), **recorded_traffic(train),
             "launches_timed": g["n"], "timing": "CUDA events around every GEMM launch over eagerly launched steps",
             "peak_source": peaks["source"] + " (cuBLAS bf16: sustained for launches timed inside a step, burst beside it)",
             "whole_step_tflops": rec.pop("whole_step_tflops"),
@@ -459,7 +461,7 @@ def main():
     peaks = measured_peaks()
     train = infer = None
     if args.mode in ("both", "train"):
-        train = train_bench.run(args, rank, world, dev, MODEL, ClockSampler(local_rank) if rank == 0 else None)
+        train = train_bench.run(args, rank, world, dev, MODEL, ClockSampler(local_rank))
         torch.cuda.empty_cache()
     if args.mode in ("both", "infer"):
         infer = bench_infer(args, rank, world, dev, ClockSampler(local_rank) if rank == 0 and train is None else None)
@@ -470,7 +472,7 @@ def main():
         for rec, flops in ((train, 3 * FWD_FLOPS_PER_IMG), (infer, FWD_FLOPS_PER_IMG)):
             if rec is not None:
                 rec["_wsf"] = rec["whole_step_tflops"] / peaks["bf16_tflops_sustained"]
-                rec["roofline"] = roofline_record(rec, peaks)
+                rec["roofline"] = roofline_record(rec, peaks, train=rec is train)
                 rec.pop("_wsf")
         clocks = head.pop("clocks")
         if infer is not None:
@@ -491,6 +493,8 @@ def main():
         }
         if "host_enqueue_ms_per_step" in head:
             line["host_enqueue_ms_per_step"] = head["host_enqueue_ms_per_step"]
+        if head.get("clocks_per_rank"):
+            line["clocks_per_rank"] = head["clocks_per_rank"]
         if train is not None and infer is not None:
             line["infer"] = {k: infer[k] for k in ("value", "unit", "ms_per_step", "parallelism", "launch", "e2e", "gpu_launches",
                                                    "launches_per_step", "roofline")}

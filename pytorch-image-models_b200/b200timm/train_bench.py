@@ -98,6 +98,13 @@ def run(args, rank, world, dev, model_name="vit_base_patch16_224", clocks=None):
     barrier()
     ms = t0.elapsed_time(t1)
     clock_info = clocks.stop() if clocks is not None else None
+    clocks_per_rank = None
+    if world > 1:
+        # every rank's SM clock under load: the slowest (most power-capped) GPU sets the pace of a synchronous step
+        infos = [None] * world
+        dist.all_gather_object(infos, None if clock_info is None else
+                               {"sm_mhz": clock_info.get("sm_mhz"), "reasons": clock_info.get("reasons")})
+        clocks_per_rank = infos
 
     # ---- end to end: inputs from pinned host memory every step (H2D on a copy stream into the buffer the other graph is
     # not reading), the loss read back on the host every step (the previous step's, so that one step stays in flight)
@@ -184,5 +191,5 @@ def run(args, rank, world, dev, model_name="vit_base_patch16_224", clocks=None):
         "host_enqueue_ms_per_step": round(host_ms, 3),
         "gemm": {"flops": gemm_flops, "ms": gemm_ms, "n": gemm_n},
         "whole_step_tflops": round(TRAIN_FLOPS_PER_IMG * value / world / 1e12, 1),
-        "clocks": clock_info,
+        "clocks": clock_info, "clocks_per_rank": clocks_per_rank,
     }
