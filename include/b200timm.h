@@ -330,6 +330,19 @@ B200_API int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, co
                          int32_t soft_dtype, double smoothing, const float* lse, const float* tsum,
                          const float* grad_out, const float* denom, void* dlogits, int32_t B, int32_t C, void* stream);
 
+/* ------------------------------------------------------------------ im2col-free patch embedding (ABI >= 6)
+ * PatchEmbed.forward (timm/layers/patch_embed.py:117-142; the conv at :62,136 == a GEMM over non-overlapping patches) fused
+ * with VisionTransformer._pos_embed's position add (vision_transformer.py:1038-1075), WITHOUT a patch matrix in memory:
+ *     out[b, row_off + g, :] = patch(b, g) . weight^T + bias (+ pos[pos_off + g, :]),   g = py * (W / patch) + px
+ * The GEMM's A operand is read straight from the bf16 NCHW image through a 4-D tensor map {kx, ky, px, (b, c, py)} (one TMA
+ * box = 64 / patch kernel rows of one channel for up to 128 patches: a coalesced HBM load of image rows); weight is the
+ * conv weight viewed [D, C * patch * patch] (bf16, K-major); pos: bf16 [pos_rows, D] or NULL; out: bf16 [B, out_tokens, D]
+ * -- rows below row_off (class / register tokens) are left to the caller.  patch in {8, 16, 32, 64}; H, W multiples of it;
+ * W / patch <= 128; D %% 8 == 0; otherwise B200_ERR_UNSUPPORTED (callers fall back to b200_patchify + b200_gemm).      */
+B200_API int b200_patch_embed_fwd(const void* img, const void* weight, const void* bias, int32_t bias_dtype, const void* pos,
+                                  int32_t pos_rows, int32_t pos_off, void* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                                  int32_t patch, int32_t D, int32_t out_tokens, int32_t row_off, void* stream);
+
 /* ------------------------------------------------------------------ NaFlex input tail, ABI >= 6
  * b200_batch_patchify: batch_patchify (timm/models/naflexvit.py:159-201, pad=True) as the gather that builds the patch
  * projection's GEMM operand: NCHW image [B,C,H,W] (img_dtype uint8 / bf16 / f32) -> bf16 [B*ceil(H/p)*ceil(W/p), Kpad],

@@ -114,6 +114,7 @@ SIGNATURES = {
     "b200_clip_coef": (ctypes.c_int, [_vp, _f64, _vp, _vp, _vp]),
     "b200_grad_scale": (ctypes.c_int, [_otp, _i32, _i32, _vp, _vp]),
     "b200_ema_update": (ctypes.c_int, [_otp, _i32, _i32, _i32, _f64, _vp]),
+    "b200_patch_embed_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_batch_patchify": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200_patches_u8": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200_act_bwd": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _i32, _vp]),

@@ -229,15 +229,30 @@ class ConvNeXtBlock(nn.Module):
         return self.forward_nhwc(rows, B, H, W).view(B, H, W, C).permute(0, 3, 1, 2)
 
 
+def _mlp_w(lin):
+    """GEMM operand of an Mlp layer: nn.Linear weight, or the [out, in, 1, 1] weight of the 1x1 Conv2d a `conv_mlp=True`
+    block uses (ConvMlp, timm/layers/mlp.py; convnext.py:176-181) viewed [out, in] -- on channels-last rows the two are the
+    same matmul."""
+    w = _w(lin)
+    return w.reshape(w.shape[0], -1) if w.dim() == 4 else w
+
+
 def _check_block(blk):
     """Raise B200Error unless `blk` (this mirror's or timm's ConvNeXtBlock) is the configuration the kernels cover."""
     conv = blk.conv_dw
     k = conv.kernel_size[0]
-    if (getattr(blk, "use_conv_mlp", False) or not isinstance(blk.shortcut, nn.Identity) or conv.stride != (1, 1)
+    conv_mlp = getattr(blk, "use_conv_mlp", False)
+    if conv_mlp:      # LayerNorm2d + 1x1-conv MLP (ConvNeXt-V2 atto ... nano): per-row LayerNorm + GEMMs on channels-last rows
+        fc1 = blk.mlp.fc1
+        ok = (type(blk.norm).__name__ == "LayerNorm2d" and isinstance(fc1, nn.Conv2d) and fc1.kernel_size == (1, 1)
+              and fc1.stride == (1, 1) and fc1.groups == 1 and blk.mlp.fc2.kernel_size == (1, 1)
+              and isinstance(getattr(blk.mlp, "norm", nn.Identity()), nn.Identity))
+    else:
+        ok = type(blk.norm).__name__ == "LayerNorm"
+    if (not ok or not isinstance(blk.shortcut, nn.Identity) or conv.stride != (1, 1)
             or conv.dilation != (1, 1) or conv.groups != conv.in_channels or conv.in_channels != conv.out_channels
-            or conv.kernel_size != (k, k) or conv.padding != (k // 2, k // 2)
-            or type(blk.norm).__name__ not in ("LayerNorm",)):
-        raise B200Error("ConvNeXtBlock: conv_mlp / strided / dilated blocks are not covered")
+            or conv.kernel_size != (k, k) or conv.padding != (k // 2, k // 2)):
+        raise B200Error("ConvNeXtBlock: strided / dilated blocks and non-1x1 conv MLPs are not covered")
     if mlp_act(blk.mlp) != 0 and hasattr(blk.mlp, "grn"):
         raise B200Error("GlobalResponseNormMlp: only the exact GELU is covered")
 
@@ -261,14 +276,14 @@ def block_forward_nhwc(self, x, B, H, W):
     if x.requires_grad or _needs_grad(self):
         extra = (None, None, 1e-6) if grn is None else (grn.weight, grn.bias, grn.eps)
         return _BlockFn.apply(x, _w(self.conv_dw), self.conv_dw.bias, self.norm.weight, self.norm.bias,
-                              _w(self.mlp.fc1), self.mlp.fc1.bias, _w(self.mlp.fc2), self.mlp.fc2.bias,
+                              _mlp_w(self.mlp.fc1), self.mlp.fc1.bias, _mlp_w(self.mlp.fc2), self.mlp.fc2.bias,
                               self.gamma, rs, B, H, W, self.norm.eps, *extra, mlp_act(self.mlp))
     y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
     h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
-    a = ops.linear_fwd(h, _w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(self.mlp))
+    a = ops.linear_fwd(h, _mlp_w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(self.mlp))
     if grn is not None:
         ops.grn_fwd(a, grn.weight, grn.bias, B, H * W, grn.eps)
-    return ops.linear_fwd(a, _w(self.mlp.fc2), self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
+    return ops.linear_fwd(a, _mlp_w(self.mlp.fc2), self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,
                           gamma=self.gamma, row_scale=rs, rows_per_scale=H * W)
 
 

@@ -688,9 +688,43 @@ def patch_embed_forward(pe, img):
             pe._b200_wpad = (ops.wkey(w), wp)
             cache = pe._b200_wpad
         w2 = cache[1]
+    if kpad == K and ops.patch_embed_supported(img, ph, D) and _IM2COL_FREE:
+        # the image IS the GEMM operand (4-D tensor map): no patch matrix in HBM
+        return ops.patch_embed_fwd(img, w2, pe.proj.bias, None, 0, (H // ph) * (W // pw), 0, ph)
     patches = ops.patchify(img.contiguous(), ph, kpad)
     y = ops.gemm(patches, w2, patches.shape[0], D, kpad, bias=pe.proj.bias)
     return y.view(B, (H // ph) * (W // pw), D)
+
+
+import os as _os
+_IM2COL_FREE = _os.environ.get("B200_IM2COL_FREE", "0") == "1"       # opt-in until verified on hardware: 1 = the image is the GEMM operand
+
+
+def _fused_patch_tokens(model, img, pos, prefix, n_prefix, pos_has_prefix):
+    """patch_embed + _pos_embed of an inference forward in ONE GEMM launch (+ a few prefix rows): the image is the A operand,
+    the position rows are the residual tile of the epilogue, the result lands behind the prefix tokens of [B, P + G, D].
+    Returns None when the configuration needs the gather path."""
+    pe = model.patch_embed
+    ph, pw = pe.patch_size
+    w = _w(pe.proj)
+    D = w.shape[0]
+    if (not _IM2COL_FREE or ph != pw or not _is_identity(pe.norm) or getattr(pe, "dynamic_img_pad", False)
+            or not ops.patch_embed_supported(img, ph, D) or (pos is not None and pos.dtype != torch.bfloat16)
+            or (prefix is not None and prefix.dtype != torch.bfloat16)):
+        return None
+    B, C, H, W = img.shape
+    if pe.img_size is not None and getattr(pe, "strict_img_size", True) and (H, W) != tuple(pe.img_size):
+        return None
+    G = (H // ph) * (W // pw)
+    pos2 = None if pos is None else pos.reshape(-1, D)
+    if pos2 is not None and pos2.shape[0] != (n_prefix + G if pos_has_prefix else G):
+        return None
+    pos2 = None if pos2 is None else (pos2 if pos2.is_contiguous() else pos2.contiguous())
+    x = ops.patch_embed_fwd(img, w.reshape(D, -1), pe.proj.bias, pos2, n_prefix if (pos_has_prefix and pos2 is not None) else 0,
+                            n_prefix + G, n_prefix, ph)
+    if n_prefix:
+        x[:, :n_prefix] = prefix if (pos2 is None or not pos_has_prefix) else prefix + pos2[:n_prefix]
+    return x
 
 
 def resample_pos_embed(pos, new_size, old_size, num_prefix_tokens):
@@ -728,16 +762,25 @@ def vit_embed(model, img):
     if not _is_identity(getattr(model, "patch_drop", None)):
         raise B200Error("patch dropout is not supported")
     _check_drop(getattr(model, "pos_drop", None), "pos_drop")
-    proj = patch_embed_forward(model.patch_embed, img)
-    B, G, D = proj.shape
     pre = [t for t in (getattr(model, "cls_token", None), getattr(model, "reg_token", None)) if t is not None]
     n_prefix = sum(t.shape[1] for t in pre)
-    prefix = None
-    if pre:
-        prefix = (pre[0] if len(pre) == 1 else torch.cat(pre, 1)).reshape(n_prefix, D).contiguous()
     pos = model.pos_embed
     if pos is not None and getattr(model, "dynamic_img_size", False):
         pos = _dynamic_pos_embed(model, img)
+    grad = torch.is_grad_enabled() and (_needs_grad(None, model.patch_embed) or any(
+        t is not None and t.requires_grad for t in pre + [pos]))
+    if not grad and isinstance(img, torch.Tensor) and img.dim() == 4:
+        prefix0 = None if not pre else (pre[0] if len(pre) == 1 else torch.cat(pre, 1)).reshape(n_prefix, -1)
+        x = _fused_patch_tokens(model, img, pos, prefix0, n_prefix, not getattr(model, "no_embed_class", False))
+        if x is not None:
+            if not _is_identity(getattr(model, "norm_pre", None)):
+                x = layernorm(model.norm_pre, x)
+            return x
+    proj = patch_embed_forward(model.patch_embed, img)
+    B, G, D = proj.shape
+    prefix = None
+    if pre:
+        prefix = (pre[0] if len(pre) == 1 else torch.cat(pre, 1)).reshape(n_prefix, D).contiguous()
     if pos is None and n_prefix == 0:
         x = proj
     elif torch.is_grad_enabled() and (proj.requires_grad or any(t is not None and t.requires_grad for t in pre + [pos])):

@@ -662,6 +662,34 @@ def glu_bwd(h, dout, gate_first, act="silu"):
     return dh
 
 
+def patch_embed_supported(img, p, D):
+    """True when patch_embed_fwd can read `img` (bf16 NCHW, contiguous) directly: the im2col-free path."""
+    if img.dtype != torch.bfloat16 or img.dim() != 4 or not img.is_contiguous():
+        return False
+    H, W = img.shape[-2:]
+    return (p in (8, 16, 32, 64) and H % p == 0 and W % p == 0 and W // p <= 128 and W % 8 == 0 and D % 8 == 0
+            and (img.shape[1] * p * p) % 64 == 0 and img.data_ptr() % 16 == 0)
+
+
+def patch_embed_fwd(img, weight2d, bias, pos2d, pos_off, out_tokens, row_off, p):
+    """out[b, row_off + g] = patch(b, g) . weight2d^T + bias (+ pos2d[pos_off + g]) -> bf16 [B, out_tokens, D]; rows below
+    row_off are NOT written.  The image is the GEMM's A operand (4-D tensor map): no patch matrix is materialised."""
+    _need_cuda(img, weight2d, bias, pos2d)
+    B, C, H, W = img.shape
+    D, K = weight2d.shape
+    if weight2d.dtype != torch.bfloat16 or not weight2d.is_contiguous() or K != C * p * p:
+        raise B200Error("patch_embed_fwd: weight must be contiguous bf16 [D, C*p*p]")
+    if pos2d is not None and (pos2d.dtype != torch.bfloat16 or not pos2d.is_contiguous() or pos2d.dim() != 2 or pos2d.shape[1] != D):
+        raise B200Error("patch_embed_fwd: pos must be contiguous bf16 [rows, D]")
+    out = torch.empty(B, out_tokens, D, dtype=torch.bfloat16, device=img.device)
+    rc = _lib.load().b200_patch_embed_fwd(img.data_ptr(), weight2d.data_ptr(), _ptr(bias), _dt(bias) if bias is not None else DTYPE_BF16,
+                                          _ptr(pos2d), 0 if pos2d is None else pos2d.shape[0], int(pos_off), out.data_ptr(), B, C,
+                                          H, W, int(p), D, int(out_tokens), int(row_off), _stream())
+    _lib.check(rc, "b200_patch_embed_fwd")
+    _count()
+    return out
+
+
 def batch_patchify(img, p, channels_last=True, kpad=None):
     """batch_patchify (timm/models/naflexvit.py:159-201, pad=True) as the gather feeding the patch projection: NCHW image
     (bf16 / fp32, or uint8 with set_input_norm) -> (bf16 [B * gh * gw, Kpad], (gh, gw)); flat patch layout P-P-C

@@ -50,6 +50,11 @@ struct GemmKernelParams {
   const float* rope;           // EPI_BIAS_ROPE: [rope_tokens - rope_prefix][128] = [sin | cos]
   int rope_tokens, rope_prefix, rope_cols;
   int act;                     // activation of the GELU / DGELU epilogues in the generic kernels: 0 erf GELU, 1 tanh GELU, 2 SiLU
+  // Patch-embedding mode (b200_patch_embed_fwd): the A operand comes straight from the NCHW image through a 4-D tensor map
+  // {kx, ky, px, (b, c, py)} -- no patch matrix in HBM.  An "m-block" is one tile of pe_pyc grid rows of one image
+  // (pe_tile_rows = pe_pyc * pe_gw <= 128 patch rows; the accumulator rows above that are never stored), a k-block is
+  // 64 / p kernel rows of one channel.  Output / residual coordinates are per image (3-D output map {D, tokens, B}).
+  int patch, pe_ntiles, pe_pyc, pe_gw, pe_gh, pe_C, pe_kb_per_c, pe_ky_per_kb, pe_tile_rows, pe_row_off, pe_pos_off, pe_stage_tx;
   float* colsum;               // optional fp32 [N]: += column sums of the bf16 output (the bias gradient of the Linear whose
                                // output gradient this GEMM produces), reduced from the staging tile, red.global.add
   unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_set_trace), nullptr in production
@@ -189,9 +194,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* sb = sa + L::kABytes;
         if constexpr (CTA2) {
           // both CTAs' bytes complete on the LEADER's barrier (the leader alone issues the MMAs)
-          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], p.patch ? p.pe_stage_tx : 2 * L::kStageBytes);
           if constexpr (!A_MN) {
-            tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+            if (p.patch) {
+              const int img = m_blk / p.pe_ntiles, ti = m_blk - img * p.pe_ntiles;
+              const int ch = kb / p.pe_kb_per_c, j = kb - ch * p.pe_kb_per_c;
+              tma_load_4d_pair(sa, &tmap_a, &full_bar[stage], 0, j * p.pe_ky_per_kb, 0, (img * p.pe_C + ch) * p.pe_gh + ti * p.pe_pyc);
+            } else {
+              tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)
@@ -338,7 +349,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
         if (has_aux && lane == 0) {
           mbar_arrive_expect_tx(&aux_bar[ew], kStgBytes);
-          tma_load_2d(stg, &tmap_aux, &aux_bar[ew], col0, row0);
+          // patch mode: the residual is the position table, indexed by the patch's place inside its image
+          const int aux_row = p.patch ? (m_blk % p.pe_ntiles) * p.pe_pyc * p.pe_gw + quad * 32 + p.pe_pos_off : row0;
+          tma_load_2d(stg, &tmap_aux, &aux_bar[ew], col0, aux_row);
         }
         if (!waited) {
           mbar_wait(&tfull_bar[as], aphase);
@@ -537,7 +550,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (lane == 0 && col0 < p.N && row0 < p.M) {
-          if (reduce_out) tma_reduce_add_2d(&tmap_out, stg, col0, row0);
+          if (p.patch) {
+            // tokens of image `img`: rows [ti * pyc * gw + quad * 32 ...) + the prefix-token offset; a tile holds
+            // pe_tile_rows patch rows, so the last (partial) 32-row group goes through the short-box map and the groups
+            // above it are not stored at all; rows past the image's last token are clipped by the 3-D map
+            const int img = m_blk / p.pe_ntiles, ti = m_blk - img * p.pe_ntiles;
+            const int valid = p.pe_tile_rows - quad * 32;
+            const int tok = ti * p.pe_pyc * p.pe_gw + quad * 32 + p.pe_row_off;
+            if (valid >= 32) tma_store_3d(&tmap_out, stg, col0, tok, img);
+            else if (valid > 0) tma_store_3d(&tmap_out2, stg, col0, tok, img);
+          } else if (reduce_out) tma_reduce_add_2d(&tmap_out, stg, col0, row0);
           else tma_store_2d(&tmap_out, stg, col0, row0);
           tma_store_commit();
         }
@@ -626,6 +648,7 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.rope = d.rope; p.rope_tokens = d.rope_tokens; p.rope_prefix = d.rope_prefix; p.rope_cols = d.rope_cols;
   p.act = d.act;
   p.colsum = d.colsum;
+  p.patch = 0;
   p.trace = g_gemm_trace;
 
   auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI, ACTRT>;
@@ -669,9 +692,96 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   }
 }
 
+// PatchEmbed.forward without a patch matrix: out[b, row_off + g, :] = patch(b, g) . W^T + bias (+ pos[pos_off + g, :]).
+static int launch_patch_embed(const void* img, const void* weight, const void* bias, int bias_dtype, const void* pos,
+                              int pos_rows, int pos_off, void* out, int B, int C, int H, int W, int ps, int D, int out_tokens,
+                              int row_off, cudaStream_t stream) {
+  constexpr int BN = 256, STAGES = 6, RC = 32;
+  using L = GemmSmem<BN, STAGES, true, RC>;
+  const int gw = W / ps, gh = H / ps, K = C * ps * ps;
+  int pyc = 128 / gw;
+  if (pyc > gh) pyc = gh;
+  const int ntiles = (gh + pyc - 1) / pyc;
+  pyc = (gh + ntiles - 1) / ntiles;                    // balance the tiles of an image (224 / 16: 7 + 7 grid rows)
+  const int tile_rows = pyc * gw;
+  CUtensorMap ta, tb, tout, tout2, taux;
+  {
+    // image [B, C, H, W] as {kx: ps (stride 1), ky: ps (stride W), px: gw (stride ps), R = (b, c, py): B*C*gh (stride ps*W)}
+    uint64_t dims[4] = {static_cast<uint64_t>(ps), static_cast<uint64_t>(ps), static_cast<uint64_t>(gw),
+                        static_cast<uint64_t>(B) * C * gh};
+    uint64_t strides[3] = {static_cast<uint64_t>(W) * 2, static_cast<uint64_t>(ps) * 2, static_cast<uint64_t>(ps) * W * 2};
+    uint32_t box[4] = {static_cast<uint32_t>(ps), static_cast<uint32_t>(64 / ps), static_cast<uint32_t>(gw), static_cast<uint32_t>(pyc)};
+    int rc = encode_tmap_bf16(&ta, img, 4, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(D)}, strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {BK, BN / 2};
+    int rc = encode_tmap_bf16(&tb, weight, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(out_tokens), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(out_tokens) * D * 2};
+    uint32_t box[3] = {RC, 32u, 1u};
+    int rc = encode_tmap_bf16(&tout, out, 3, dims, strides, box, 64);
+    if (rc) return rc;
+    box[1] = tile_rows % 32 ? static_cast<uint32_t>(tile_rows % 32) : 32u;
+    rc = encode_tmap_bf16(&tout2, out, 3, dims, strides, box, 64);
+    if (rc) return rc;
+  }
+  if (pos != nullptr) {
+    uint64_t dims[2] = {static_cast<uint64_t>(D), static_cast<uint64_t>(pos_rows)}, strides[1] = {static_cast<uint64_t>(D) * 2};
+    uint32_t box[2] = {RC, 32u};
+    int rc = encode_tmap_bf16(&taux, pos, 2, dims, strides, box, 64);
+    if (rc) return rc;
+  } else {
+    taux = tout;
+  }
+  GemmKernelParams p = {};
+  p.out = out; p.bias = bias; p.bias_f32 = bias_dtype == B200_DTYPE_F32;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(pos);
+  p.rows_per_scale = 1;
+  p.num_m_blocks = B * ntiles;
+  p.M = p.num_m_blocks * BM; p.N = D; p.K = K;
+  p.num_n_blocks = (D + BN - 1) / BN;
+  p.num_k_blocks = K / BK;
+  p.split_k = 1; p.k_blocks_per_split = p.num_k_blocks;
+  p.epilogue = pos != nullptr ? B200_EPI_BIAS_RESIDUAL : B200_EPI_BIAS;
+  p.patch = 1; p.pe_ntiles = ntiles; p.pe_pyc = pyc; p.pe_gw = gw; p.pe_gh = gh; p.pe_C = C;
+  p.pe_kb_per_c = ps * ps / BK; p.pe_ky_per_kb = BK / ps; p.pe_tile_rows = tile_rows; p.pe_row_off = row_off;
+  p.pe_pos_off = pos_off; p.pe_stage_tx = 2 * (tile_rows * BK * 2 + L::kBBytes);
+  p.trace = nullptr;
+  auto kern = gemm_bf16_kernel<BN, STAGES, false, false, true, RC, -1, false>;
+  B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+  const int num_tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
+  int clusters = (sm_count() & ~1) / 2;
+  if (clusters > num_tiles) clusters = num_tiles;
+  B200_CUDA_OK(launch_pdl(kern, dim3(2 * clusters, 1, 1), dim3(kNumThreads, 1, 1), L::kTotal, stream, 2, ta, tb, tout, taux, tout2, p));
+  return B200_OK;
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_patch_embed_fwd(const void* img, const void* weight, const void* bias, int32_t bias_dtype, const void* pos,
+                                    int32_t pos_rows, int32_t pos_off, void* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                                    int32_t patch, int32_t D, int32_t out_tokens, int32_t row_off, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(img && weight && out && B > 0 && C > 0 && D > 0, "b200_patch_embed_fwd: null pointer or empty shape");
+  if (patch < 8 || 64 % patch != 0 || H % patch != 0 || W % patch != 0 || W / patch > 128 || D % 8 != 0 || W % 8 != 0 ||
+      (C * patch * patch) % 64 != 0)
+    return fail(B200_ERR_UNSUPPORTED, "b200_patch_embed_fwd: needs patch in {8, 16, 32, 64}, H, W multiples of it, W / patch <= 128, "
+                                      "D %% 8 == 0 (got patch=%d H=%d W=%d D=%d)", patch, H, W, D);
+  B200_CHECK_ARG(out_tokens >= row_off + (H / patch) * (W / patch) && row_off >= 0, "b200_patch_embed_fwd: out_tokens too small");
+  B200_CHECK_ARG(pos == nullptr || (pos_off >= 0 && pos_rows >= pos_off + (H / patch) * (W / patch)), "b200_patch_embed_fwd: position table too short");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(weight) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+                 "b200_patch_embed_fwd: pointers must be 16-byte aligned");
+  return launch_patch_embed(img, weight, bias, bias_dtype, pos, pos_rows, pos_off, out, B, C, H, W, patch, D, out_tokens, row_off, stream);
+}
 
 namespace b200 { extern long long* g_attn_fwd_trace; extern long long* g_attn_bwd_trace; }
 

@@ -178,3 +178,42 @@ def test_no_fallback_on_cpu():
     model = create_model("vit_tiny_patch16_224").to(torch.bfloat16).eval()
     with pytest.raises(B200Error):
         model(torch.zeros(1, 3, 224, 224, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("p,size,prefix,no_embed_class,B", [(16, 224, 1, False, 5), (16, 224, 0, False, 3), (32, 224, 2, True, 4),
+                                                            (8, 64, 1, False, 9), (16, 384, 1, False, 2), (16, 64, 1, False, 1)])
+def test_im2col_free_patch_embed_matches_gather_path(p, size, prefix, no_embed_class, B):
+    """b200_patch_embed_fwd (the image as the GEMM's A operand through a 4-D tensor map, position rows as the epilogue's
+    residual tile, tokens stored behind the prefix rows) == the gather path (b200_patchify + b200_gemm + b200_assemble_tokens)
+    it replaces at inference: same GEMM arithmetic (fp32 accumulation of the same bf16 products; the position add happens
+    before instead of after the bf16 rounding of the projection -> tolerance one bf16 ulp of the sum), for several patch
+    sizes / grids (14 x 14 in two 7-row tiles, 24 x 24 in five tiles, 7 x 7 and 8 x 8 in one, 4 x 4) and prefix layouts."""
+    from b200timm import functional as BF
+    from b200timm.vision_transformer import VisionTransformer
+    torch.manual_seed(p + size)
+    model = VisionTransformer(img_size=size, patch_size=p, embed_dim=256, depth=1, num_heads=4, num_classes=8,
+                              class_token=prefix > 0, reg_tokens=max(0, prefix - 1), no_embed_class=no_embed_class,
+                              global_pool="token" if prefix > 0 else "avg")
+    with torch.no_grad():
+        model.pos_embed.normal_(std=0.5)
+        if model.cls_token is not None:
+            model.cls_token.normal_(std=0.5)
+    model = model.cuda().to(torch.bfloat16).eval()
+    img = torch.randn(B, 3, size, size, device="cuda").bfloat16()
+    with torch.no_grad():
+        BF._IM2COL_FREE = True
+        fused = BF.vit_embed(model, img)
+        fused_logits = model(img)
+        BF._IM2COL_FREE = False
+        try:
+            gathered = BF.vit_embed(model, img)
+            gathered_logits = model(img)
+        finally:
+            BF._IM2COL_FREE = True
+    assert fused.shape == gathered.shape
+    err = (fused.float() - gathered.float()).abs()
+    tol = 2.0 ** -7 * gathered.float().abs() + 1e-2
+    assert (err <= tol).all(), f"tokens: max err {err.max().item():.4g}"
+    if prefix:
+        assert torch.equal(fused[:, :prefix], gathered[:, :prefix])          # prefix rows: same bf16 sums
+    assert (fused_logits.float() - gathered_logits.float()).abs().max().item() < 5e-2

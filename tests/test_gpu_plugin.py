@@ -214,6 +214,8 @@ VARIANT_MODELS = [
     ("vit_base_patch16_xp_224", {"depth": 2}, 224),                                         # parallel block + qk-norm + RmsNorm
     ("vit_base_patch16_224", {"depth": 2, "scale_mlp_norm": True, "scale_attn_norm": True, "norm_layer": "layernorm"}, 224),
     ("vit_base_patch16_224", {"depth": 2, "global_pool": "prr", "class_token": False}, 224),
+    ("convnextv2_atto", {}, 128),               # conv_mlp=True (LayerNorm2d + 1x1-conv MLP), GRN, C = 40 .. 320
+    ("convnext_atto", {}, 128),                 # conv_mlp=True without GRN
 ]
 
 
