@@ -189,3 +189,35 @@ def test_loss_and_ema_mirrors_host_logic():
         e.update(m, step=5)                       # CPU model: no fallback
     e32 = BE.ModelEma(m.to(torch.bfloat16), ema_dtype=torch.float32)
     assert e32.module.weight.dtype == torch.float32
+
+
+def test_head_padding_in_the_weights_is_exact():
+    """head_dim < 64 runs on the head_dim-64 kernels through zero padding that lives in the weights
+    (functional._pad_rows / _pad_cols): attention computed on the padded projections with the module's own scale equals
+    the narrow-head attention exactly (the padding columns of q / k add 0 to every score, the padded v columns meet zero
+    columns of the output projection).  Checked here with plain torch math (the algebra, not the kernels)."""
+    from b200timm import functional as BF
+    torch.manual_seed(0)
+    B, N, D, H, hd = 2, 7, 96, 3, 32
+    attn = Attention(D, num_heads=H, qkv_bias=True)
+    x = torch.randn(B, N, D)
+
+    def sdpa(qkv, heads, width, scale):
+        q, k, v = qkv.view(B, N, 3, heads, width).permute(2, 0, 3, 1, 4)
+        p = ((q @ k.transpose(-1, -2)) * scale).softmax(-1)
+        return (p @ v).transpose(1, 2).reshape(B, N, heads * width)
+
+    ref = torch.nn.functional.linear(sdpa(torch.nn.functional.linear(x, attn.qkv.weight, attn.qkv.bias), H, hd, attn.scale),
+                                     attn.proj.weight, attn.proj.bias)
+    wq = BF._pad_rows(attn.qkv.weight, 3, H, hd)
+    bq = BF._pad_rows(attn.qkv.bias, 3, H, hd)
+    wp = BF._pad_cols(attn.proj.weight, H, hd)
+    assert wq.shape == (3 * H * 64, D) and bq.shape == (3 * H * 64,) and wp.shape == (D, H * 64)
+    got = torch.nn.functional.linear(sdpa(torch.nn.functional.linear(x, wq, bq), H, 64, attn.scale), wp, attn.proj.bias)
+    torch.testing.assert_close(got, ref, atol=1e-6, rtol=1e-6)
+    # gradients reach the real parameters through the padding (training builds the padded operands differentiably)
+    got.sum().backward()
+    assert attn.qkv.weight.grad is not None and attn.proj.weight.grad is not None and attn.qkv.bias.grad is not None
+    assert BF.head_pad(32) == 64 and BF.head_pad(64) == 64
+    with pytest.raises(B200Error):
+        BF.head_pad(80)

@@ -1,6 +1,6 @@
 """ONE ViT-B/16 training step (batch 256, bf16: zero_grad + forward + cross entropy + backward + Nesterov SGD, the step
 bench.py times) -- or, with --infer, one inference forward -- between cudaProfilerStart / Stop, eagerly launched, for
-`ncu --profile-from-start off` (tools/gpu_r2n.sh):
+`ncu --profile-from-start off` (tools/gpu_ncu_step.sh):
     ncu --metrics gpu__time_duration.sum ... python tools/ncu_train_step.py              # launch list of a step
     ncu --set full ...                       python tools/ncu_train_step.py --depth 1    # every kernel type once
 A number printed under ncu is never a bench value."""

@@ -1,4 +1,4 @@
-"""gpurun_out/{launches_train,launches_infer}.csv + prof_train_block_raw.csv (tools/gpu_r2n.sh) -> profiles/r02_*.md and
+"""gpurun_out/{launches_train,launches_infer}.csv + prof_train_block_raw.csv (tools/gpu_ncu_step.sh) -> profiles/r02_*.md and
 profiles/traffic.json (the per-launch DRAM traffic bench.py copies into roofline.traffic)."""
 import collections
 import csv
@@ -79,7 +79,7 @@ def block_table():
         pass
     with open(os.path.join(OUT, "r02_train_block_kernels.md"), "w") as f:
         f.write("# r02: every kernel of ONE ViT-B/16 training step at depth 1 (batch 256, bf16) under `ncu --set full --clock-control none`\n\n"
-                "`ncu --set full --clock-control none --profile-from-start off python tools/ncu_train_step.py --depth 1` (tools/gpu_r2n.sh; "
+                "`ncu --set full --clock-control none --profile-from-start off python tools/ncu_train_step.py --depth 1` (tools/gpu_ncu_step.sh; "
                 "the report is converted to CSV on the GPU box, `gpurun_out/prof_train_block_raw.csv`).  Launch order = forward "
                 "(patch embed, block, head), loss, backward, optimizer.  DRAM GB/s = (dram read + write bytes) / duration against the "
                 f"measured HBM peak {peak:.0f} GB/s.  Captures are serialised cold-cache replays: use them for pipe utilisation, traffic "
