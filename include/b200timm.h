@@ -334,8 +334,9 @@ B200_API int b200_cross_entropy_bwd(const void* logits, int32_t logits_dtype, co
  * PatchEmbed.forward (timm/layers/patch_embed.py:117-142; the conv at :62,136 == a GEMM over non-overlapping patches) fused
  * with VisionTransformer._pos_embed's position add (vision_transformer.py:1038-1075), WITHOUT a patch matrix in memory:
  *     out[b, row_off + g, :] = patch(b, g) . weight^T + bias (+ pos[pos_off + g, :]),   g = py * (W / patch) + px
- * The GEMM's A operand is read straight from the bf16 NCHW image through a 4-D tensor map {kx, ky, px, (b, c, py)} (one TMA
- * box = 64 / patch kernel rows of one channel for up to 128 patches: a coalesced HBM load of image rows); weight is the
+ * The GEMM's A operand is read straight from the bf16 NCHW image through a 5-D tensor map {kx %% 8, px, (b, c, py), kx / 8,
+ * ky} (one TMA box = 64 / patch kernel rows of one channel for up to 128 patches, i.e. whole image rows from HBM, landing in
+ * shared memory as the un-swizzled K-major core-matrix layout the MMA reads); weight is the
  * conv weight viewed [D, C * patch * patch] (bf16, K-major); pos: bf16 [pos_rows, D] or NULL; out: bf16 [B, out_tokens, D]
  * -- rows below row_off (class / register tokens) are left to the caller.  patch in {8, 16, 32, 64}; H, W multiples of it;
  * W / patch <= 128; D %% 8 == 0; otherwise B200_ERR_UNSUPPORTED (callers fall back to b200_patchify + b200_gemm).      */

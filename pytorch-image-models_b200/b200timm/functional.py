@@ -689,7 +689,7 @@ def patch_embed_forward(pe, img):
             cache = pe._b200_wpad
         w2 = cache[1]
     if kpad == K and ops.patch_embed_supported(img, ph, D) and _IM2COL_FREE:
-        # the image IS the GEMM operand (4-D tensor map): no patch matrix in HBM
+        # the image IS the GEMM operand (5-D tensor map): no patch matrix in HBM
         return ops.patch_embed_fwd(img, w2, pe.proj.bias, None, 0, (H // ph) * (W // pw), 0, ph)
     patches = ops.patchify(img.contiguous(), ph, kpad)
     y = ops.gemm(patches, w2, patches.shape[0], D, kpad, bias=pe.proj.bias)
@@ -697,7 +697,7 @@ def patch_embed_forward(pe, img):
 
 
 import os as _os
-_IM2COL_FREE = _os.environ.get("B200_IM2COL_FREE", "0") == "1"       # opt-in until verified on hardware: 1 = the image is the GEMM operand
+_IM2COL_FREE = _os.environ.get("B200_IM2COL_FREE", "1") == "1"       # 1 = the image itself is the patch GEMM's A operand (0: gather path)
 
 
 def _fused_patch_tokens(model, img, pos, prefix, n_prefix, pos_has_prefix):

@@ -673,7 +673,7 @@ def patch_embed_supported(img, p, D):
 
 def patch_embed_fwd(img, weight2d, bias, pos2d, pos_off, out_tokens, row_off, p):
     """out[b, row_off + g] = patch(b, g) . weight2d^T + bias (+ pos2d[pos_off + g]) -> bf16 [B, out_tokens, D]; rows below
-    row_off are NOT written.  The image is the GEMM's A operand (4-D tensor map): no patch matrix is materialised."""
+    row_off are NOT written.  The image is the GEMM's A operand (5-D tensor map): no patch matrix is materialised."""
     _need_cuda(img, weight2d, bias, pos2d)
     B, C, H, W = img.shape
     D, K = weight2d.shape

@@ -50,11 +50,15 @@ struct GemmKernelParams {
   const float* rope;           // EPI_BIAS_ROPE: [rope_tokens - rope_prefix][128] = [sin | cos]
   int rope_tokens, rope_prefix, rope_cols;
   int act;                     // activation of the GELU / DGELU epilogues in the generic kernels: 0 erf GELU, 1 tanh GELU, 2 SiLU
-  // Patch-embedding mode (b200_patch_embed_fwd): the A operand comes straight from the NCHW image through a 4-D tensor map
-  // {kx, ky, px, (b, c, py)} -- no patch matrix in HBM.  An "m-block" is one tile of pe_pyc grid rows of one image
-  // (pe_tile_rows = pe_pyc * pe_gw <= 128 patch rows; the accumulator rows above that are never stored), a k-block is
-  // 64 / p kernel rows of one channel.  Output / residual coordinates are per image (3-D output map {D, tokens, B}).
-  int patch, pe_ntiles, pe_pyc, pe_gw, pe_gh, pe_C, pe_kb_per_c, pe_ky_per_kb, pe_tile_rows, pe_row_off, pe_pos_off, pe_stage_tx;
+  // Patch-embedding mode (b200_patch_embed_fwd): the A operand comes straight from the NCHW image through a 5-D tensor map
+  // {kx % 8, px, (b, c, py), kx / 8, ky} -- no patch matrix in HBM.  An "m-block" is one tile of pe_pyc grid rows of one
+  // image (pe_tile_rows = pe_pyc * pe_gw <= 128 patch rows; the accumulator rows above that are never stored), a k-block
+  // is 64 / p kernel rows of one channel.  The box lands as the UN-swizzled K-major core-matrix layout (8 rows x 16 bytes
+  // per core matrix, row pitch 16 B, K chunks pe_lbo = 16 * pe_tile_rows bytes apart): a swizzled box would need its
+  // innermost dimension to span the whole 128-byte row, but a patch row is p * 2 = 32 contiguous bytes of the image
+  // (measured: with SWIZZLE_128B every 32-byte inner row is placed on its own 128-byte line).  Output / residual
+  // coordinates are per image (3-D output map {D, tokens, B}).
+  int patch, pe_ntiles, pe_pyc, pe_gw, pe_gh, pe_C, pe_kb_per_c, pe_ky_per_kb, pe_tile_rows, pe_row_off, pe_pos_off, pe_stage_tx, pe_lbo;
   float* colsum;               // optional fp32 [N]: += column sums of the bf16 output (the bias gradient of the Linear whose
                                // output gradient this GEMM produces), reduced from the staging tile, red.global.add
   unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_set_trace), nullptr in production
@@ -199,7 +203,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (p.patch) {
               const int img = m_blk / p.pe_ntiles, ti = m_blk - img * p.pe_ntiles;
               const int ch = kb / p.pe_kb_per_c, j = kb - ch * p.pe_kb_per_c;
-              tma_load_4d_pair(sa, &tmap_a, &full_bar[stage], 0, j * p.pe_ky_per_kb, 0, (img * p.pe_C + ch) * p.pe_gh + ti * p.pe_pyc);
+              tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], 0, 0, (img * p.pe_C + ch) * p.pe_gh + ti * p.pe_pyc, 0, j * p.pe_ky_per_kb);
             } else {
               tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
             }
@@ -275,15 +279,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
         const uint32_t sb = sa + L::kABytes;
-        const uint64_t adesc = make_smem_desc(sa, a_lbo, 1024, kLayoutSw128);
+        // patch mode: A is the un-swizzled core-matrix layout (K chunks of 8 elements pe_lbo bytes apart, 8-row groups 128 B
+        // apart); one UMMA_K = 16 step = two K chunks
+        const uint64_t adesc = p.patch ? make_smem_desc(sa, static_cast<uint32_t>(p.pe_lbo), 128, kLayoutNone)
+                                       : make_smem_desc(sa, a_lbo, 1024, kLayoutSw128);
+        const uint32_t akstep = p.patch ? static_cast<uint32_t>(2 * p.pe_lbo) >> 4 : a_kstep;
         const uint64_t bdesc = make_smem_desc(sb, b_lbo, 1024, kLayoutSw128);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           if constexpr (CTA2)
-            umma_ss_pair(tmem_d, adesc + static_cast<uint64_t>(k * a_kstep), bdesc + static_cast<uint64_t>(k * b_kstep),
+            umma_ss_pair(tmem_d, adesc + static_cast<uint64_t>(k * akstep), bdesc + static_cast<uint64_t>(k * b_kstep),
                          idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           else
-            umma_ss(tmem_d, adesc + static_cast<uint64_t>(k * a_kstep), bdesc + static_cast<uint64_t>(k * b_kstep),
+            umma_ss(tmem_d, adesc + static_cast<uint64_t>(k * akstep), bdesc + static_cast<uint64_t>(k * b_kstep),
                     idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
@@ -706,12 +714,15 @@ static int launch_patch_embed(const void* img, const void* weight, const void* b
   const int tile_rows = pyc * gw;
   CUtensorMap ta, tb, tout, tout2, taux;
   {
-    // image [B, C, H, W] as {kx: ps (stride 1), ky: ps (stride W), px: gw (stride ps), R = (b, c, py): B*C*gh (stride ps*W)}
-    uint64_t dims[4] = {static_cast<uint64_t>(ps), static_cast<uint64_t>(ps), static_cast<uint64_t>(gw),
-                        static_cast<uint64_t>(B) * C * gh};
-    uint64_t strides[3] = {static_cast<uint64_t>(W) * 2, static_cast<uint64_t>(ps) * 2, static_cast<uint64_t>(ps) * W * 2};
-    uint32_t box[4] = {static_cast<uint32_t>(ps), static_cast<uint32_t>(64 / ps), static_cast<uint32_t>(gw), static_cast<uint32_t>(pyc)};
-    int rc = encode_tmap_bf16(&ta, img, 4, dims, strides, box, true);
+    // image [B, C, H, W] as {kx % 8 (stride 1), px: gw (stride ps), R = (b, c, py): B*C*gh (stride ps*W), kx / 8: ps/8 (stride 8),
+    // ky: ps (stride W)}; box {8, gw, pyc, ps/8, 64/ps}, no swizzle: in shared memory 8 elements (16 B) of a patch row, then
+    // the tile's patch rows at 16-byte pitch, then the eight K chunks of the k-block
+    uint64_t dims[5] = {8, static_cast<uint64_t>(gw), static_cast<uint64_t>(B) * C * gh, static_cast<uint64_t>(ps / 8),
+                        static_cast<uint64_t>(ps)};
+    uint64_t strides[4] = {static_cast<uint64_t>(ps) * 2, static_cast<uint64_t>(ps) * W * 2, 16, static_cast<uint64_t>(W) * 2};
+    uint32_t box[5] = {8, static_cast<uint32_t>(gw), static_cast<uint32_t>(pyc), static_cast<uint32_t>(ps / 8),
+                       static_cast<uint32_t>(64 / ps)};
+    int rc = encode_tmap_bf16(&ta, img, 5, dims, strides, box, 0);
     if (rc) return rc;
   }
   {
@@ -750,7 +761,7 @@ static int launch_patch_embed(const void* img, const void* weight, const void* b
   p.epilogue = pos != nullptr ? B200_EPI_BIAS_RESIDUAL : B200_EPI_BIAS;
   p.patch = 1; p.pe_ntiles = ntiles; p.pe_pyc = pyc; p.pe_gw = gw; p.pe_gh = gh; p.pe_C = C;
   p.pe_kb_per_c = ps * ps / BK; p.pe_ky_per_kb = BK / ps; p.pe_tile_rows = tile_rows; p.pe_row_off = row_off;
-  p.pe_pos_off = pos_off; p.pe_stage_tx = 2 * (tile_rows * BK * 2 + L::kBBytes);
+  p.pe_pos_off = pos_off; p.pe_stage_tx = 2 * (tile_rows * BK * 2 + L::kBBytes); p.pe_lbo = tile_rows * 16;
   p.trace = nullptr;
   auto kern = gemm_bf16_kernel<BN, STAGES, false, false, true, RC, -1, false>;
   B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
