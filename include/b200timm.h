@@ -48,7 +48,7 @@ extern "C" {
                                  `rot` layout, head_dim 64, one [sin | cos] table shared by batch and heads)       */
 
 B200_API const char* b200_last_error(void);
-/* 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
+/* 7 now (6 -> 7: b200_attn_fwd_bias / b200_attn_bwd_bias); 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
 B200_API int b200_abi_version(void);
 /* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
 B200_API int b200_device_check(void);
@@ -160,6 +160,20 @@ B200_API int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H);
 B200_API int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
                   void* dqkv, const int32_t* kv_len, int32_t B, int32_t N, int32_t H, int32_t hd,
                   float scale, float* dbias, void* stream);
+
+/* Attention with an additive bias on the scaled scores (ABI >= 7): softmax(q k^T * scale + bias) v -- the `is_causal` and
+ * general `attn_mask` cases of Attention.forward / AttentionRope.forward (timm/layers/attention.py:108-133, 255-277), whose
+ * resolve_self_attn_mask (attention.py:21-40) turns a causal flag into a -inf upper triangle, a bool keep-mask into 0 / -inf
+ * and passes float masks through.  bias: fp32 [batch or 1, heads or 1, N, bias_ld] (bias_ld >= N, a multiple of 4; 16-byte
+ * aligned); bias_batch_stride / bias_head_stride in elements, 0 = the same bias for every sample / head.  -inf entries give
+ * exactly zero probability; a row that is -inf everywhere yields NaN, as in the reference.  The bias receives no gradient.
+ * All other arguments as b200_attn_fwd / b200_attn_bwd (key-padding lengths are expressed through the bias instead).     */
+B200_API int b200_attn_fwd_bias(const void* qkv, void* out, float* lse, const float* bias, int64_t bias_batch_stride,
+                  int64_t bias_head_stride, int32_t bias_ld, int32_t B, int32_t N, int32_t H, int32_t hd, float scale,
+                  void* stream);
+B200_API int b200_attn_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                  void* dqkv, const float* bias, int64_t bias_batch_stride, int64_t bias_head_stride, int32_t bias_ld,
+                  int32_t B, int32_t N, int32_t H, int32_t hd, float scale, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------ patch embed   timm/layers/patch_embed.py:136-138
  * Gathers non-overlapping p x p patches of an NCHW bf16 image into rows of a [B*gh*gw, Kpad] bf16 matrix

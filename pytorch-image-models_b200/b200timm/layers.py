@@ -243,10 +243,8 @@ class Attention(nn.Module):
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, is_causal: bool = False,
                 kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if is_causal:
-            raise B200Error("causal attention is not supported")
-        if attn_mask is not None:
-            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1], x.shape[0]) if kv_len is None else kv_len
+        if kv_len is None:
+            kv_len = attn_mask_operand(attn_mask, is_causal, x.shape[1], x.shape[0], x.device)
         return BF.attention_forward(self, x, kv_len)
 
 
@@ -286,45 +284,109 @@ class AttentionRope(nn.Module):
 
     def forward(self, x: torch.Tensor, rope: Optional[torch.Tensor] = None, attn_mask: Optional[torch.Tensor] = None,
                 is_causal: bool = False, kv_len: Optional[torch.Tensor] = None) -> torch.Tensor:
-        if is_causal:
-            raise B200Error("causal attention is not supported")
-        if attn_mask is not None:
-            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1], x.shape[0]) if kv_len is None else kv_len
+        if kv_len is None:
+            kv_len = attn_mask_operand(attn_mask, is_causal, x.shape[1], x.shape[0], x.device)
         return BF.attention_rope_forward(self, x, rope, kv_len)
 
 
-_KV_CACHE = {}      # id(mask) -> (weakref to the mask, version, n_tokens, batch, kv_len): one conversion per forward, not per block
+_KV_CACHE = {}      # id(mask) -> (weakref to the mask, version, n_tokens, batch, operand): one conversion per forward, not per block
+_CAUSAL_CACHE = {}  # (n_tokens, device) -> fp32 [1, 1, N, ld] causal bias
 
 
-def BF_mask_to_kv_len(attn_mask: torch.Tensor, n_tokens: int, batch: Optional[int] = None) -> torch.Tensor:
-    """Convert a NaFlex key-padding mask (bool keep-mask or additive float, broadcastable to [B,1,N,N],
-    naflexvit.py:964-1029) into per-sample valid-key counts (int32 [B]).  The collator always emits prefix-valid masks
-    (naflex_dataset.py:136-142); anything else is rejected.  The prefix-validity check reads one flag back from the
-    device, so the result is cached on the mask object: the 24 blocks of a forward that receive the same mask tensor
-    pay for one conversion (and one host sync), and a mask with batch dimension 1 is expanded to `batch` entries."""
+def _as_key_padding(m: torch.Tensor, n_tokens: int):
+    """int32 [B] valid-key counts when the bool keep-mask `m` ([Bm, Hm, Nq or 1, N]) is a pure prefix-valid key-padding mask:
+    every query row that is valid itself keeps exactly the first kv_len keys, for every head (NaFlex:
+    naflexvit.py:964-1029 builds q_valid & k_valid; the rows of padded queries do not matter).  None otherwise."""
+    first = m[:, 0]                                                   # [Bm, Nq or 1, N]
+    keys = first.any(dim=-2)                                          # key kept by at least one query
+    kv_len = keys.sum(-1).to(torch.int32)
+    ar = torch.arange(n_tokens, device=m.device)
+    expect = ar[None, :] < kv_len[:, None]                            # [Bm, N]
+    ok = (keys == expect).all()
+    if first.shape[-2] != 1:
+        rows_valid = ar[None, :, None] < kv_len[:, None, None]        # query rows inside the valid prefix
+        ok = ok & ((first == expect[:, None, :]) | ~rows_valid).all()
+    if m.shape[1] != 1:
+        ok = ok & (m == first[:, None]).all()
+    return kv_len if bool(ok) else None                               # one host read, cached by the caller
+
+
+def attn_bias_operand(attn_mask: torch.Tensor, n_tokens: int) -> torch.Tensor:
+    """The additive fp32 bias libb200timm's b200_attn_fwd_bias / _bwd_bias take, from an attention mask as
+    resolve_self_attn_mask (timm/layers/attention.py:21-40) interprets it: bool = keep-mask -> 0 / -inf, float = additive.
+    Result: contiguous fp32 [Bm, Hm, N, ld] (ld = N rounded up to 4; Bm / Hm = the mask's own batch / head extent, 1 = broadcast)."""
+    m = attn_mask
+    while m.dim() < 4:
+        m = m.unsqueeze(0)
+    if m.dim() != 4 or m.shape[-1] != n_tokens or m.shape[-2] not in (1, n_tokens):
+        raise B200Error(f"attn_mask of shape {tuple(attn_mask.shape)} does not broadcast to [B, H, {n_tokens}, {n_tokens}]")
+    ld = (n_tokens + 3) // 4 * 4
+    out = torch.zeros(m.shape[0], m.shape[1], n_tokens, ld, dtype=torch.float32, device=m.device)
+    if m.dtype == torch.bool:
+        out[..., :n_tokens].masked_fill_(~m.expand(-1, -1, n_tokens, -1), float("-inf"))
+    else:
+        out[..., :n_tokens] = m.expand(-1, -1, n_tokens, -1).float()
+    return out
+
+
+def causal_bias_operand(n_tokens: int, device) -> torch.Tensor:
+    """-inf above the diagonal (attention.py:31-32), fp32 [1, 1, N, ld]; built once per (N, device)."""
+    key = (n_tokens, str(device))
+    hit = _CAUSAL_CACHE.get(key)
+    if hit is None:
+        ld = (n_tokens + 3) // 4 * 4
+        hit = torch.zeros(1, 1, n_tokens, ld, dtype=torch.float32, device=device)
+        hit[0, 0, :, :n_tokens] = torch.full((n_tokens, n_tokens), float("-inf"), device=device).triu_(1)
+        _CAUSAL_CACHE[key] = hit
+    return hit
+
+
+def attn_mask_operand(attn_mask: Optional[torch.Tensor], is_causal: bool, n_tokens: int, batch: Optional[int] = None,
+                      device=None, strict_prefix: bool = False):
+    """What the attention kernels take in place of (attn_mask, is_causal) -- passed down as `kv_len`:
+      None                       no mask
+      int32 [B]                  a prefix-valid key-padding mask as valid-key counts (the NaFlex layout; b200_attn_fwd's kv_len)
+      fp32 [Bm, Hm, N, ld]       anything else -- causal (which takes precedence over attn_mask, attention.py:30-32), general
+                                 bool / additive masks -- as an additive bias (b200_attn_fwd_bias)
+    The classification reads one flag back from the device, so the result is cached on the mask object: the blocks of a
+    forward that receive the same mask tensor pay for one conversion."""
     import weakref
+    if is_causal:
+        return causal_bias_operand(n_tokens, device if device is not None else attn_mask.device)
+    if attn_mask is None:
+        return None
     key = id(attn_mask)
     hit = _KV_CACHE.get(key)
     if hit is not None and hit[0]() is attn_mask and hit[1:4] == (attn_mask._version, n_tokens, batch):
+        if strict_prefix and hit[4].dtype != torch.int32:
+            raise B200Error("only prefix-valid key-padding masks are supported (NaFlex layout)")
         return hit[4]
     m = attn_mask
-    if m.dtype != torch.bool:
-        m = m > -1.0  # additive masks hold 0 (keep) or finfo.min (drop)
     while m.dim() < 4:
         m = m.unsqueeze(0)
-    keys = m[:, 0].any(dim=-2) if m.shape[-2] != 1 else m[:, 0, 0]   # [B, N]: key kept by at least one query
-    kv_len = keys.sum(-1).to(torch.int32)
-    expect = torch.arange(n_tokens, device=m.device)[None, :] < kv_len[:, None]
-    if not bool((keys == expect).all()):
+    keep = m if m.dtype == torch.bool else m > -1.0      # additive key-padding masks hold 0 (keep) or finfo.min / -inf (drop)
+    operand = None
+    if m.dtype == torch.bool or bool(((m == 0) | ~keep).all()):
+        operand = _as_key_padding(keep, n_tokens)
+    if operand is not None:
+        if batch is not None and operand.numel() == 1 and batch > 1:
+            operand = operand.expand(batch)
+        operand = operand.contiguous()
+    elif strict_prefix:
         raise B200Error("only prefix-valid key-padding masks are supported (NaFlex layout)")
-    if batch is not None and kv_len.numel() == 1 and batch > 1:
-        kv_len = kv_len.expand(batch)
-    kv_len = kv_len.contiguous()
+    else:
+        operand = attn_bias_operand(attn_mask, n_tokens)
     if len(_KV_CACHE) > 64:
         for k in [k for k, v in _KV_CACHE.items() if v[0]() is None]:
             del _KV_CACHE[k]
-    _KV_CACHE[key] = (weakref.ref(attn_mask), attn_mask._version, n_tokens, batch, kv_len)
-    return kv_len
+    _KV_CACHE[key] = (weakref.ref(attn_mask), attn_mask._version, n_tokens, batch, operand)
+    return operand
+
+
+def BF_mask_to_kv_len(attn_mask: torch.Tensor, n_tokens: int, batch: Optional[int] = None) -> torch.Tensor:
+    """Prefix-valid key-padding mask -> per-sample valid-key counts (int32 [B]); anything else raises (callers that can
+    take a general mask use attn_mask_operand)."""
+    return attn_mask_operand(attn_mask, False, n_tokens, batch, strict_prefix=True)
 
 
 class PatchEmbed(nn.Module):

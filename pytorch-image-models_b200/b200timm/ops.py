@@ -351,15 +351,34 @@ def convert_f32(src, dst, accumulate=False):
 
 
 # --------------------------------------------------------------------------------------------- attention
+def _attn_bias_args(mask, B, N, H, who):
+    """(ptr, batch stride, head stride, row pitch) of an additive attention bias: contiguous fp32 [B or 1, H or 1, N, ld]."""
+    if (mask.dim() != 4 or not mask.is_contiguous() or mask.shape[0] not in (1, B) or mask.shape[1] not in (1, H)
+            or mask.shape[2] != N or mask.shape[3] < N or mask.shape[3] % 4):
+        raise B200Error(f"{who}: the attention bias must be contiguous fp32 [B or 1, H or 1, N, ld >= N (multiple of 4)], "
+                        f"got {tuple(mask.shape)} for B={B} H={H} N={N}")
+    ld = mask.shape[3]
+    return mask.data_ptr(), (mask.shape[1] * N * ld if mask.shape[0] > 1 else 0), (N * ld if mask.shape[1] > 1 else 0), ld
+
+
 def attention_fwd(qkv, B, N, H, hd, scale, kv_len=None, need_lse=False):
-    """qkv: bf16 [B*N, 3*H*hd] (or [B,N,3*H*hd]) contiguous.  Returns (out [B,N,H*hd] bf16, lse [B,H,N] | None)."""
+    """qkv: bf16 [B*N, 3*H*hd] (or [B,N,3*H*hd]) contiguous.  Returns (out [B,N,H*hd] bf16, lse [B,H,N] | None).
+    kv_len: None, int32 [B] valid-key counts (prefix key-padding mask), or an fp32 4-D additive bias (causal / general masks;
+    layers.attn_mask_operand builds either from the reference's (attn_mask, is_causal))."""
     _need_cuda(qkv, kv_len)
     if qkv.dtype != torch.bfloat16 or not qkv.is_contiguous() or qkv.numel() != B * N * 3 * H * hd:
         raise B200Error("attention_fwd: qkv must be a contiguous bf16 [B,N,3,H,hd] buffer")
-    if kv_len is not None and (kv_len.dtype != torch.int32 or kv_len.numel() != B or not kv_len.is_contiguous()):
-        raise B200Error("attention_fwd: kv_len must be a contiguous int32 [B] tensor")
     out = torch.empty(B, N, H * hd, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device) if need_lse else None
+    if kv_len is not None and kv_len.dtype == torch.float32:
+        ptr, bs, hs, ld = _attn_bias_args(kv_len, B, N, H, "attention_fwd")
+        rc = _lib.load().b200_attn_fwd_bias(qkv.data_ptr(), out.data_ptr(), _ptr(lse), ptr, bs, hs, ld, B, N, H, hd, float(scale),
+                                            _stream())
+        _lib.check(rc, "b200_attn_fwd_bias")
+        _count()
+        return out, lse
+    if kv_len is not None and (kv_len.dtype != torch.int32 or kv_len.numel() != B or not kv_len.is_contiguous()):
+        raise B200Error("attention_fwd: kv_len must be a contiguous int32 [B] tensor")
     rc = _lib.load().b200_attn_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(lse), _ptr(kv_len), B, N, H, hd, float(scale),
                                    _stream())
     _lib.check(rc, "b200_attn_fwd")
@@ -387,6 +406,13 @@ def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None, dbias=No
     delta = torch.empty(lib.b200_attn_bwd_ws_floats(B, N, H), dtype=torch.float32, device=qkv.device)   # delta (+ fp32 dQ)
     if dbias is not None and (dbias.dtype != torch.float32 or dbias.numel() != 3 * H * hd or not dbias.is_contiguous()):
         raise B200Error("attention_bwd: dbias must be a contiguous fp32 [3*H*hd] tensor")
+    if kv_len is not None and kv_len.dtype == torch.float32:
+        ptr, bs, hs, ld = _attn_bias_args(kv_len, B, N, H, "attention_bwd")
+        rc = lib.b200_attn_bwd_bias(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                    dqkv.data_ptr(), ptr, bs, hs, ld, B, N, H, hd, float(scale), _ptr(dbias), _stream())
+        _lib.check(rc, "b200_attn_bwd_bias")
+        _count(2)
+        return dqkv
     rc = lib.b200_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
                                    dqkv.data_ptr(), _ptr(kv_len), B, N, H, hd, float(scale), _ptr(dbias), _stream())
     _lib.check(rc, "b200_attn_bwd")

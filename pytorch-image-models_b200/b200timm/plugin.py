@@ -139,29 +139,24 @@ def _dispatch(name, fast_fn):
     return forward
 
 
-def _kv_len(attn_mask, n, batch=None):
-    if attn_mask is None:
+def _mask(attn_mask, is_causal, x, n=None):
+    """(attn_mask, is_causal) of the reference signatures -> the kernels' mask operand (layers.attn_mask_operand)."""
+    if attn_mask is None and not is_causal:
         return None
-    from .layers import BF_mask_to_kv_len
-    return BF_mask_to_kv_len(attn_mask, n, batch)
+    from .layers import attn_mask_operand
+    return attn_mask_operand(attn_mask, is_causal, x.shape[1] if n is None else n, x.shape[0], x.device)
 
 
 def _block(self, x, attn_mask=None, is_causal=False):
-    if is_causal:
-        raise B200Error("causal attention is not covered")
-    return BF.block_forward(self, x, _kv_len(attn_mask, x.shape[1], x.shape[0]))
+    return BF.block_forward(self, x, _mask(attn_mask, is_causal, x))
 
 
 def _attention(self, x, attn_mask=None, is_causal=False):
-    if is_causal:
-        raise B200Error("causal attention is not covered")
-    return BF.attention_forward(self, x, _kv_len(attn_mask, x.shape[1], x.shape[0]))
+    return BF.attention_forward(self, x, _mask(attn_mask, is_causal, x))
 
 
 def _attention_rope(self, x, rope=None, attn_mask=None, is_causal=False):
-    if is_causal:
-        raise B200Error("causal attention is not covered")
-    return BF.attention_rope_forward(self, x, rope, _kv_len(attn_mask, x.shape[1], x.shape[0]))
+    return BF.attention_rope_forward(self, x, rope, _mask(attn_mask, is_causal, x))
 
 
 def _patch_embed(self, x):
@@ -183,18 +178,21 @@ def _patch_embed(self, x):
     raise B200Error(f"PatchEmbed output format {fmt} is not covered")
 
 
+def _vit_tokens(self, x):
+    """Sequence length the blocks will see for image batch `x` (dynamic_img_size models follow the input)."""
+    ph, pw = self.patch_embed.patch_size
+    H, W = x.shape[-2], x.shape[-1]
+    if getattr(self.patch_embed, "dynamic_img_pad", False):
+        H, W = H + (ph - H % ph) % ph, W + (pw - W % pw) % pw
+    return (H // ph) * (W // pw) + self.num_prefix_tokens
+
+
 def _vit_features(self, x, attn_mask=None, is_causal=False):
-    if is_causal:
-        raise B200Error("causal forward_features is not covered")
-    n = self.patch_embed.num_patches + self.num_prefix_tokens
-    return BF.vit_forward_features(self, x, _kv_len(attn_mask, n, x.shape[0]))
+    return BF.vit_forward_features(self, x, _mask(attn_mask, is_causal, x, _vit_tokens(self, x)))
 
 
 def _vit_forward(self, x, attn_mask=None, is_causal=False):
-    if is_causal:
-        raise B200Error("causal forward is not covered")
-    n = self.patch_embed.num_patches + self.num_prefix_tokens
-    return BF.vit_forward(self, x, _kv_len(attn_mask, n, x.shape[0]))
+    return BF.vit_forward(self, x, _mask(attn_mask, is_causal, x, _vit_tokens(self, x)))
 
 
 def _convnext_forward(self, x):

@@ -45,11 +45,9 @@ class Block(nn.Module):
 
     def forward(self, x, attn_mask: Optional[torch.Tensor] = None, is_causal: bool = False,
                 kv_len: Optional[torch.Tensor] = None):
-        if is_causal:
-            raise B200Error("causal attention is not supported")
-        if attn_mask is not None and kv_len is None:
-            from .layers import BF_mask_to_kv_len
-            kv_len = BF_mask_to_kv_len(attn_mask, x.shape[1], x.shape[0])
+        if kv_len is None and (attn_mask is not None or is_causal):
+            from .layers import attn_mask_operand
+            kv_len = attn_mask_operand(attn_mask, is_causal, x.shape[1], x.shape[0], x.device)
         return BF.block_forward(self, x, kv_len)
 
 
@@ -173,22 +171,20 @@ class VisionTransformer(nn.Module):
         return self.head
 
     def forward_features(self, x, attn_mask=None, is_causal=False, kv_len=None):
-        if is_causal:
-            raise B200Error("causal attention is not supported")
-        if attn_mask is not None and kv_len is None:
-            from .layers import BF_mask_to_kv_len
-            kv_len = BF_mask_to_kv_len(attn_mask, self.patch_embed.num_patches + self.num_prefix_tokens, x.shape[0])
+        if kv_len is None and (attn_mask is not None or is_causal):
+            from .layers import attn_mask_operand
+            kv_len = attn_mask_operand(attn_mask, is_causal, self.patch_embed.num_patches + self.num_prefix_tokens, x.shape[0],
+                                       x.device)
         return BF.vit_forward_features(self, x, kv_len)
 
     def forward_head(self, x, pre_logits: bool = False):
         return BF.vit_forward_head(self, x, pre_logits)
 
     def forward(self, x, attn_mask=None, is_causal=False, kv_len=None):
-        if is_causal:
-            raise B200Error("causal attention is not supported")
-        if attn_mask is not None and kv_len is None:
-            from .layers import BF_mask_to_kv_len
-            kv_len = BF_mask_to_kv_len(attn_mask, self.patch_embed.num_patches + self.num_prefix_tokens, x.shape[0])
+        if kv_len is None and (attn_mask is not None or is_causal):
+            from .layers import attn_mask_operand
+            kv_len = attn_mask_operand(attn_mask, is_causal, self.patch_embed.num_patches + self.num_prefix_tokens, x.shape[0],
+                                       x.device)
         return BF.vit_forward(self, x, kv_len)
 
 

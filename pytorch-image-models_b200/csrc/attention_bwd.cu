@@ -368,12 +368,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
 namespace b200 {
 int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
-                     const int32_t* kv_len, int B, int N, int H, float scale, float* dbias, cudaStream_t st);
-}
-
-namespace b200 {
+                     const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, float scale, float* dbias, cudaStream_t st);
 int launch_attn_bwd_long(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq32, void* dqkv,
-                         const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st);
+                         const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, float scale, cudaStream_t st);
 }
 using namespace b200;
 
@@ -382,8 +379,11 @@ extern "C" int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H) {
   return N > kNQ ? d + static_cast<long long>(B) * N * H * kHd : d;
 }
 
-extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
-                             void* dqkv, const int32_t* kv_len, int32_t B, int32_t N, int32_t H, int32_t hd,
+static int attn_bwd_v1(const void* qkv, const void* dout, const float* lse, float* delta, void* dqkv, const int32_t* kv_len,
+                       int32_t B, int32_t N, int32_t H, float scale, cudaStream_t st);
+
+static int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                             const int32_t* kv_len, const AttnBias* bias, int32_t B, int32_t N, int32_t H, int32_t hd,
                              float scale, float* dbias, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "b200_attn_bwd: null pointer");
@@ -397,16 +397,38 @@ extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout,
     B200_CUDA_OK(cudaGetLastError());
   }
   static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_BWD_V1"); return e != nullptr && e[0] == '1'; }();
-  if (dbias != nullptr && (N > kNQ || use_v1))
+  if (dbias != nullptr && (N > kNQ || (use_v1 && bias == nullptr)))
     return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: the fused qkv-bias gradient is available for N <= %d (v2 kernel) only", kNQ);
   if (N > kNQ) {
     // long sequences (attention_bwd_long.cu): the workspace continues behind delta with the fp32 dq buffer
     float* dq32 = delta + (static_cast<long long>(B) * H * N + 3) / 4 * 4;
-    return launch_attn_bwd_long(qkv, dout, lse, delta, dq32, dqkv, kv_len, B, N, H, scale, st);
+    return launch_attn_bwd_long(qkv, dout, lse, delta, dq32, dqkv, kv_len, bias, B, N, H, scale, st);
   }
   // v2 (attention_bwd2.cu: two query halves, 8 compute warps + issuer warp) is the default; B200_ATTN_BWD_V1=1 keeps
-  // the simpler v1 kernel of this file selectable for A/B comparison and as a cross-check in the tests.
-  if (!use_v1) return launch_attn_bwd2(qkv, dout, lse, delta, dqkv, kv_len, B, N, H, scale, dbias, st);
+  // the simpler v1 kernel of this file selectable for A/B comparison and as a cross-check in the tests (no bias variant).
+  if (!use_v1 || bias != nullptr) return launch_attn_bwd2(qkv, dout, lse, delta, dqkv, kv_len, bias, B, N, H, scale, dbias, st);
+  return attn_bwd_v1(qkv, dout, lse, delta, dqkv, kv_len, B, N, H, scale, st);
+}
+
+extern "C" int b200_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                             void* dqkv, const int32_t* kv_len, int32_t B, int32_t N, int32_t H, int32_t hd,
+                             float scale, float* dbias, void* stream_) {
+  return attn_bwd_dispatch(qkv, out, dout, lse, delta, dqkv, kv_len, nullptr, B, N, H, hd, scale, dbias, stream_);
+}
+
+extern "C" int b200_attn_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, float* delta,
+                                  void* dqkv, const float* bias, int64_t bias_batch_stride, int64_t bias_head_stride,
+                                  int32_t bias_ld, int32_t B, int32_t N, int32_t H, int32_t hd, float scale, float* dbias,
+                                  void* stream_) {
+  B200_CHECK_ARG(bias != nullptr, "b200_attn_bwd_bias: null bias");
+  B200_CHECK_ARG(bias_ld >= N && bias_ld % 4 == 0 && bias_batch_stride >= 0 && bias_head_stride >= 0,
+                 "b200_attn_bwd_bias: bias row pitch %d must be a multiple of 4 and >= N = %d", bias_ld, N);
+  const AttnBias ab{bias, bias_batch_stride, bias_head_stride, bias_ld};
+  return attn_bwd_dispatch(qkv, out, dout, lse, delta, dqkv, nullptr, &ab, B, N, H, hd, scale, dbias, stream_);
+}
+
+static int attn_bwd_v1(const void* qkv, const void* dout, const float* lse, float* delta, void* dqkv, const int32_t* kv_len,
+                       int32_t B, int32_t N, int32_t H, float scale, cudaStream_t st) {
   CUtensorMap tq, tdo;
   uint32_t box[2] = {kHd, kNQ};
   {

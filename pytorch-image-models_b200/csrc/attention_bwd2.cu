@@ -50,6 +50,8 @@ struct AttnBwd2Params {
   const int* kv_len;
   int B, N, H;
   float scale, scale_log2e;
+  AttnBias bias;         // BIAS kernel: additive mask / bias on the scaled scores (common.h)
+  float inv_scale;
 };
 
 // One warp's 32 accumulator rows x 64 columns: TMEM -> bf16 -> 128B-swizzled staging tile -> one TMA store into
@@ -122,6 +124,9 @@ __device__ __forceinline__ void pds8(const uint32_t* s, const uint32_t* dp, cons
   *reinterpret_cast<uint4*>(dsdst) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
 }
 
+// BIAS = true: P is recomputed from scores + additive bias (causal triangle / general attn_mask), added to the S^T registers
+// right after they leave TMEM (add_bias_transposed); the bias itself receives no gradient (a mask, attention.py:21-40).
+template <bool BIAS>
 __global__ void __launch_bounds__(kComputeThreads + 32, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                  const __grid_constant__ CUtensorMap tm_out32, const __grid_constant__ CUtensorMap tm_out16,
@@ -335,6 +340,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       // touching TMEM.  The pass is bound by the TMEM read bandwidth, so this is ~22 % of it at N = 197.
       const bool rows_dead = kt * 128 + (warp & 3) * 32 >= kvlen;
       const int q_a = qh * kQH + c0;
+      const float* bkey = nullptr;       // bias[q_a, key] of this item
+      if constexpr (BIAS)
+        if (key < N) bkey = p.bias.ptr + b * p.bias.bs + h * p.bias.hs + static_cast<long long>(q_a) * p.bias.ld + key;
       auto zero_groups = [&](int g0, int ng) {
         if (!freed && gs > 0) { mbar_wait(bar_free, (gs - 1) & 1); freed = true; }
         for (int g = g0; g < g0 + ng; ++g) {
@@ -353,6 +361,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         // first write into P^T / dS^T: the previous step's dV / dK / dQ MMAs must have finished reading them (their
         // completion normally lies well inside the TMEM reads above)
         if (!freed && gs > 0) { mbar_wait(bar_free, (gs - 1) & 1); freed = true; }
+        if constexpr (BIAS) add_bias_transposed<32>(s, bkey, p.bias.ld, N - q_a, p.inv_scale);
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           pds8(s + g * 8, d + g * 8, l2 + g * 8, dl + g * 8, sc2, scale2, key_ok, prow + g * 2048, dsrow + g * 2048);
@@ -365,6 +374,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         tmem_ld_x16(tmem_row + kColDP + c0 + 32, d);
         tmem_ld_wait_x16(s);
         tmem_ld_wait_x16(d);
+        if constexpr (BIAS)
+          add_bias_transposed<16>(s, bkey ? bkey + 32LL * p.bias.ld : nullptr, p.bias.ld, N - q_a - 32, p.inv_scale);
 #pragma unroll
         for (int g = 0; g < 2; ++g)
           pds8(s + g * 8, d + g * 8, l2 + 32 + g * 8, dl + 32 + g * 8, sc2, scale2, key_ok, prow + (4 + g) * 2048,
@@ -378,6 +389,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         tmem_ld_x8(tmem_row + kColDP + c0 + 48, d);
         tmem_ld_wait_x8(s);
         tmem_ld_wait_x8(d);
+        if constexpr (BIAS)
+          add_bias_transposed<8>(s, bkey ? bkey + 48LL * p.bias.ld : nullptr, p.bias.ld, N - q_a - 48, p.inv_scale);
         pds8(s, d, l2 + 48, dl + 48, sc2, scale2, key_ok, prow + 6 * 2048, dsrow + 6 * 2048);
       }
       fence_proxy_async_smem();
@@ -439,7 +452,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 long long* g_attn_bwd_trace = nullptr;
 
 int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
-                     const int32_t* kv_len, int B, int N, int H, float scale, float* dbias, cudaStream_t st) {
+                     const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, float scale, float* dbias, cudaStream_t st) {
   CUtensorMap tq, tdo;
   uint32_t box[2] = {kHd, kNQ};
   {
@@ -469,14 +482,17 @@ int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const 
   p.dbias = dbias;
   p.trace = g_attn_bwd_trace;
   p.B = B; p.N = N; p.H = H; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    attr_set = true;
+  p.bias = bias != nullptr ? *bias : AttnBias{nullptr, 0, 0, 0};
+  p.inv_scale = 1.0f / scale;
+  auto kern = p.bias.ptr != nullptr ? attn_bwd2_kernel<true> : attn_bwd2_kernel<false>;
+  static decltype(kern) attr_set_for = nullptr;
+  if (attr_set_for != kern) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    attr_set_for = kern;
   }
   int grid = sm_count();
   if (grid > B * H) grid = B * H;
-  attn_bwd2_kernel<<<grid, kComputeThreads + 32, kSmemTotal, st>>>(tq, tdo, to32, to16, p);
+  kern<<<grid, kComputeThreads + 32, kSmemTotal, st>>>(tq, tdo, to32, to16, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

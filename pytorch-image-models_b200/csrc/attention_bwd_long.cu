@@ -45,6 +45,8 @@ struct AttnBwdLongParams {
   __nv_bfloat16* dqkv;
   int B, N, H;
   float scale, scale_log2e;
+  AttnBias bias;         // BIAS kernel: additive mask / bias on the scaled scores (common.h)
+  float inv_scale;
 };
 
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
@@ -73,6 +75,8 @@ __device__ __forceinline__ void pds8_l(const uint32_t* s, const uint32_t* dp, co
   *reinterpret_cast<uint4*>(dsdst) = make_uint4(dso[0], dso[1], dso[2], dso[3]);
 }
 
+// BIAS = true: scores + additive bias (causal triangle / general attn_mask), as in attention_bwd2.cu.
+template <bool BIAS>
 __global__ void __launch_bounds__(kComputeThreads + 32, 1)
 attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                      const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_out32,
@@ -244,12 +248,18 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
           const float* dl = sDelta + qh * kQH + c0;
           uint8_t* prow = sP + (c0 >> 3) * 2048 + rowt * 16;
           uint8_t* dsrow = sDS + (c0 >> 3) * 2048 + rowt * 16;
+          const int q_a = qh * kQH + c0;
+          const float* bkey = nullptr;       // bias[q_a, key] of this item
+          if constexpr (BIAS)
+            if (kt * kKT + rowt < N && q_a < N)
+              bkey = p.bias.ptr + b * p.bias.bs + h * p.bias.hs + static_cast<long long>(q_a) * p.bias.ld + kt * kKT + rowt;
           {
             uint32_t s[32], d[32];
             tmem_ld_x32(tmem_row + kColS + c0, s);
             tmem_ld_x32(tmem_row + kColDP + c0, d);
             tmem_ld_wait_x32(s);
             tmem_ld_wait_x32(d);
+            if constexpr (BIAS) add_bias_transposed<32>(s, bkey, p.bias.ld, N - q_a, p.inv_scale);
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               pds8_l(s + g * 8, d + g * 8, l2 + g * 8, dl + g * 8, sc2, scale2, key_ok, prow + g * 2048, dsrow + g * 2048);
@@ -260,6 +270,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
             tmem_ld_x16(tmem_row + kColDP + c0 + 32, d);
             tmem_ld_wait_x16(s);
             tmem_ld_wait_x16(d);
+            if constexpr (BIAS)
+              add_bias_transposed<16>(s, bkey ? bkey + 32LL * p.bias.ld : nullptr, p.bias.ld, N - q_a - 32, p.inv_scale);
 #pragma unroll
             for (int g = 0; g < 2; ++g)
               pds8_l(s + g * 8, d + g * 8, l2 + 32 + g * 8, dl + 32 + g * 8, sc2, scale2, key_ok, prow + (4 + g) * 2048,
@@ -271,6 +283,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
             tmem_ld_x8(tmem_row + kColDP + c0 + 48, d);
             tmem_ld_wait_x8(s);
             tmem_ld_wait_x8(d);
+            if constexpr (BIAS)
+              add_bias_transposed<8>(s, bkey ? bkey + 48LL * p.bias.ld : nullptr, p.bias.ld, N - q_a - 48, p.inv_scale);
             pds8_l(s, d, l2 + 48, dl + 48, sc2, scale2, key_ok, prow + 6 * 2048, dsrow + 6 * 2048);
           }
           fence_proxy_async_smem();
@@ -376,7 +390,7 @@ attn_dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict
 
 // dq32: fp32 workspace [B, N, H*64] (zeroed here).  Returns B200_ERR_UNSUPPORTED for N > 1120.
 int launch_attn_bwd_long(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq32, void* dqkv,
-                         const int32_t* kv_len, int B, int N, int H, float scale, cudaStream_t st) {
+                         const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, float scale, cudaStream_t st) {
   if (N > kMaxChunks * kQH) return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: N=%d tokens not supported (<= %d)", N, kMaxChunks * kQH);
   const long long HD = static_cast<long long>(H) * kHd;
   B200_CUDA_OK(cudaMemsetAsync(dq32, 0, static_cast<size_t>(B) * N * HD * sizeof(float), st));
@@ -409,14 +423,17 @@ int launch_attn_bwd_long(const void* qkv, const void* dout, const float* lse, co
   AttnBwdLongParams p;
   p.lse = lse; p.delta = delta; p.kv_len = kv_len; p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.B = B; p.N = N; p.H = H; p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    attr_set = true;
+  p.bias = bias != nullptr ? *bias : AttnBias{nullptr, 0, 0, 0};
+  p.inv_scale = 1.0f / scale;
+  auto kern = p.bias.ptr != nullptr ? attn_bwd_long_kernel<true> : attn_bwd_long_kernel<false>;
+  static decltype(kern) attr_set_for = nullptr;
+  if (attr_set_for != kern) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    attr_set_for = kern;
   }
   int grid = sm_count();
   if (grid > B * H) grid = B * H;
-  attn_bwd_long_kernel<<<grid, kComputeThreads + 32, kSmemTotal, st>>>(tkv, tq, tdo, to32, tdq32, tdq16, p);
+  kern<<<grid, kComputeThreads + 32, kSmemTotal, st>>>(tkv, tq, tdo, to32, tdq32, tdq16, p);
   B200_CUDA_OK(cudaGetLastError());
   const long long rows = static_cast<long long>(B) * N;
   long long blocks = (rows * (HD / 8) + 255) / 256;

@@ -360,16 +360,16 @@ static int launch_attn_fwd(const void* qkv, void* out, float* lse, const int32_t
 }  // namespace b200
 
 namespace b200 {
-int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H, float scale,
-                     cudaStream_t st);
-int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H, float scale,
-                         cudaStream_t st);
+int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int B, int N, int H,
+                     float scale, cudaStream_t st);
+int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int B, int N, int H,
+                         float scale, cudaStream_t st);
 }
 
 using namespace b200;
 
-extern "C" int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* kv_len, int32_t B, int32_t N,
-                             int32_t H, int32_t hd, float scale, void* stream_) {
+static int attn_fwd_dispatch(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int32_t B,
+                             int32_t N, int32_t H, int32_t hd, float scale, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv && out, "b200_attn_fwd: null qkv/out");
   B200_CHECK_ARG(B > 0 && N > 0 && H > 0, "b200_attn_fwd: bad shape B=%d N=%d H=%d", B, N, H);
@@ -378,14 +378,41 @@ extern "C" int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "b200_attn_fwd: qkv/out must be 16-byte aligned");
   // N <= 208 (ViT @224/16): the persistent, P-in-TMEM kernel of attention_fwd2.cu; B200_ATTN_FWD_V1=1 keeps the
-  // one-CTA-per-tile kernels of this file selectable for A/B comparison (they remain the path for N > 208).
+  // one-CTA-per-tile kernels of this file selectable for A/B comparison (they remain the path for 208 < N <= 256).
   static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_FWD_V1"); return e != nullptr && e[0] == '1'; }();
-  if (!use_v1 && N <= 208) return launch_attn_fwd2(qkv, out, lse, kv_len, B, N, H, scale, st);
+  if (bias != nullptr) {     // additive bias: the two production kernels only
+    if (N <= 208) return launch_attn_fwd2(qkv, out, lse, kv_len, bias, B, N, H, scale, st);
+    return launch_attn_fwd_long(qkv, out, lse, kv_len, bias, B, N, H, scale, st);
+  }
+  if (!use_v1 && N <= 208) return launch_attn_fwd2(qkv, out, lse, kv_len, nullptr, B, N, H, scale, st);
   static const bool ptmem = [] { const char* e = getenv("B200_ATTN_PTMEM"); return e != nullptr && e[0] == '1'; }();
   if (ptmem && N <= 208) return launch_attn_fwd<208, true, true>(qkv, out, lse, kv_len, B, N, H, scale, st);
   if (N <= 208) return launch_attn_fwd<208, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
   if (N <= 256) return launch_attn_fwd<256, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
   // longer sequences: the double-buffered online-softmax kernel of attention_fwd_long.cu
-  if (!use_v1) return launch_attn_fwd_long(qkv, out, lse, kv_len, B, N, H, scale, st);
+  if (!use_v1) return launch_attn_fwd_long(qkv, out, lse, kv_len, nullptr, B, N, H, scale, st);
   return launch_attn_fwd<128, false, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
+}
+
+extern "C" int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* kv_len, int32_t B, int32_t N,
+                             int32_t H, int32_t hd, float scale, void* stream_) {
+  return attn_fwd_dispatch(qkv, out, lse, kv_len, nullptr, B, N, H, hd, scale, stream_);
+}
+
+// Checks shared with b200_attn_bwd_bias (attention_bwd.cu has its own copy of the test).
+static int check_bias(const char* who, const float* bias, int64_t bs, int64_t hs, int32_t ld, int32_t N) {
+  B200_CHECK_ARG(bias != nullptr, "%s: null bias", who);
+  B200_CHECK_ARG(ld >= N && ld % 4 == 0 && bs >= 0 && hs >= 0 && bs % 4 == 0 && hs % 4 == 0,
+                 "%s: bias row pitch %d (>= N = %d) and the batch / head strides must be multiples of 4 elements", who, ld, N);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "%s: bias must be 16-byte aligned", who);
+  return B200_OK;
+}
+
+extern "C" int b200_attn_fwd_bias(const void* qkv, void* out, float* lse, const float* bias, int64_t bias_batch_stride,
+                                  int64_t bias_head_stride, int32_t bias_ld, int32_t B, int32_t N, int32_t H, int32_t hd,
+                                  float scale, void* stream_) {
+  const int rc = check_bias("b200_attn_fwd_bias", bias, bias_batch_stride, bias_head_stride, bias_ld, N);
+  if (rc) return rc;
+  const AttnBias ab{bias, bias_batch_stride, bias_head_stride, bias_ld};
+  return attn_fwd_dispatch(qkv, out, lse, nullptr, &ab, B, N, H, hd, scale, stream_);
 }

@@ -62,11 +62,15 @@ struct AttnFwd2Params {
   float scale, scale_log2e;
   int stagger;        // cycles the second query tile's pipeline starts behind the first (anti-phase exp passes)
   long long* trace;   // debug (b200_set_trace): 16 cycle counters per CTA, nullptr in production
+  AttnBias bias;      // BIAS kernels: additive mask / bias on the scaled scores (common.h)
+  float inv_scale;
 };
 
 // MASKED = false: no key-padding lengths and N > 192, so the six full 32-column chunks carry no masking code at all
 // (with a run-time condition the compiler if-converts the mask into a compare + select per element of every chunk).
-template <bool TRACE, uint32_t kPolyMask, bool MASKED>
+// BIAS = true: an additive fp32 bias (causal triangle / general attn_mask, attention.py:21-40,129-131) is added to the
+// score tile in TMEM before the two softmax passes read it (tmem_add_bias_row); everything after that is unchanged.
+template <bool TRACE, uint32_t kPolyMask, bool MASKED, bool BIAS = false>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                  const __grid_constant__ CUtensorMap tm_out, const AttnFwd2Params p) {
@@ -195,6 +199,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_wait(&bar_s[t], it & 1);
       tc_fence_after();
       if (TRACE) { const long long c = clock64(); ph[0] += c - ck; ck = c; }
+      if constexpr (BIAS) {
+        const float* brow = row_in_img < N ? p.bias.ptr + b * p.bias.bs + h * p.bias.hs + static_cast<long long>(row_in_img) * p.bias.ld
+                                           : nullptr;
+        tmem_add_bias_row<kFull * 32 + 16>(tmem_row, brow, 0, p.bias.ld, p.inv_scale);
+      }
       // ---- pass 1: row max over the valid keys
       float mb0 = -INFINITY, mb1 = -INFINITY;
       {
@@ -337,8 +346,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 long long* g_attn_fwd_trace = nullptr;
 
-int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H, float scale,
-                     cudaStream_t st) {
+int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int B, int N, int H,
+                     float scale, cudaStream_t st) {
   CUtensorMap tq, tkv;
   uint64_t dims[2] = {static_cast<uint64_t>(3) * H * kHd, static_cast<uint64_t>(B) * N};
   uint64_t strides[1] = {static_cast<uint64_t>(3) * H * kHd * 2};
@@ -361,6 +370,8 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_l
   p.lse = lse; p.kv_len = kv_len; p.B = B; p.N = N; p.H = H; p.num_items = B * H;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.trace = g_attn_fwd_trace;
+  p.bias = bias != nullptr ? *bias : AttnBias{nullptr, 0, 0, 0};
+  p.inv_scale = 1.0f / scale;
   static const int stagger = [] { const char* e = getenv("B200_ATTN_STAGGER"); return e ? atoi(e) : 0; }();
   p.stagger = stagger;
   // B200_ATTN_POLY = how many of every 16 column pairs compute exp2 on the FMA pipe (0, 4, 6, 8, 10, 12)
@@ -368,7 +379,9 @@ int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_l
   using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnFwd2Params);
   const bool masked = kv_len != nullptr || N <= 192;
   Kern kern;
-  if (masked) {
+  if (p.bias.ptr != nullptr) {
+    kern = masked ? attn_fwd2_kernel<false, 0u, true, true> : attn_fwd2_kernel<false, 0u, false, true>;
+  } else if (masked) {
     kern = p.trace ? attn_fwd2_kernel<true, 0u, true> : attn_fwd2_kernel<false, 0u, true>;
   } else if (p.trace) {
     kern = poly == 0 ? attn_fwd2_kernel<true, 0u, false> : attn_fwd2_kernel<true, 0x5555u, false>;

@@ -38,6 +38,8 @@ struct AttnLongParams {
   const int* kv_len;
   int B, N, H;
   float scale, scale_log2e;
+  AttnBias bias;      // BIAS kernels: additive mask / bias on the scaled scores (common.h)
+  float inv_scale;
 };
 
 __device__ __forceinline__ void exp2_poly_pair_l(f32x2 tt, float& e0, float& e1) {
@@ -57,7 +59,10 @@ __device__ __forceinline__ void exp2_poly_pair_l(f32x2 tt, float& e0, float& e1)
 }
 
 // kPolyMask: which of the 16 column pairs of a 32-column chunk take exp2 on the FMA pipe (0 = all on the MUFU)
-template <uint32_t kPolyMask>
+// BIAS = true: an additive fp32 bias (causal triangle / general attn_mask, attention.py:21-40) is added to every score tile
+// in TMEM before the online-softmax passes read it; a key block that is entirely -inf for a row leaves the row's running
+// statistics untouched (P = 0, rescale factor from the old maximum).
+template <uint32_t kPolyMask, bool BIAS = false>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_out, const AttnLongParams p) {
@@ -149,7 +154,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
     }
     const float m_new = fmaxf(m_run, fmaxf(mb0, mb1));
-    const float neg_mc = -m_new * p.scale_log2e;
+    const float neg_mc = (BIAS && m_new == -INFINITY) ? 0.f : -m_new * p.scale_log2e;
     alpha = ex2_approx(fmaf(m_run, p.scale_log2e, neg_mc));
     const f32x2 nm2 = splat(neg_mc);
     f32x2 lsum2 = 0ull;
@@ -210,6 +215,11 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     mbar_wait(bar_s, ph);
     tc_fence_after();
 
+    if constexpr (BIAS) {
+      const float* brow = row_in_img < N ? p.bias.ptr + b * p.bias.bs + h * p.bias.hs + static_cast<long long>(row_in_img) * p.bias.ld
+                                         : nullptr;
+      tmem_add_bias_row<kKB>(tmem_row, brow, j * kKB, p.bias.ld, p.inv_scale);
+    }
     const int nvalid = kvlen - j * kKB;
     float alpha;
     if (nvalid >= kKB) softmax_block(std::false_type{}, nvalid, alpha);
@@ -287,8 +297,8 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
-int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* kv_len, int B, int N, int H, float scale,
-                         cudaStream_t st) {
+int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int B, int N, int H,
+                         float scale, cudaStream_t st) {
   CUtensorMap tq, tkv, tout;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(3) * H * kHd, static_cast<uint64_t>(B) * N};
@@ -308,7 +318,10 @@ int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* 
   p.lse = lse; p.kv_len = kv_len; p.B = B; p.N = N; p.H = H;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   static const int poly = [] { const char* e = getenv("B200_ATTN_LONG_POLY"); return e ? atoi(e) : 0; }();
+  p.bias = bias != nullptr ? *bias : AttnBias{nullptr, 0, 0, 0};
+  p.inv_scale = 1.0f / scale;
   auto kern = poly == 6 ? attn_fwd_long_kernel<0x2525u> : (poly == 4 ? attn_fwd_long_kernel<0x1111u> : attn_fwd_long_kernel<0u>);
+  if (p.bias.ptr != nullptr) kern = attn_fwd_long_kernel<0u, true>;
   static decltype(kern) attr_set_for = nullptr;
   if (attr_set_for != kern) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));

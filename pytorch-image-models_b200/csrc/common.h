@@ -25,6 +25,15 @@ int fail(int code, const char* fmt, ...);
                           __FILE__, __LINE__);                                                    \
   } while (0)
 
+// Additive attention bias (resolve_self_attn_mask of timm/layers/attention.py:21-40: a causal triangle, a bool keep-mask as
+// 0 / -inf, or a float mask): fp32 [batch or 1, heads or 1, N, ld], ld >= N a multiple of 4; bs / hs = batch / head strides
+// in elements (0 = broadcast).  ptr == nullptr: no bias.
+struct AttnBias {
+  const float* ptr;
+  long long bs, hs;
+  int ld;
+};
+
 // Number of SMs of the current device (cached per device).
 int sm_count();
 

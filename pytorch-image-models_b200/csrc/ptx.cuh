@@ -404,4 +404,47 @@ __device__ __forceinline__ void tmem_ld_wait_x16(uint32_t (&r)[16]) {
                : "memory");
 }
 
+// S[row, 0 .. NCOLS) += bias_row[col0 ..] * inv_scale for this thread's TMEM row (NCOLS a multiple of 16): the additive
+// attention bias enters the score tile before the softmax passes read it, in units of the unscaled scores
+// ((s + b / scale) * scale = s * scale + b; -inf stays -inf).  bias_row == nullptr (a padding row) or columns at / past `ld`
+// contribute nothing.  Warp-collective (tcgen05.ld / .st); ends with tcgen05.wait::st so the same thread may read back.
+template <int NCOLS>
+__device__ __forceinline__ void tmem_add_bias_row(uint32_t taddr, const float* bias_row, int col0, int ld, float inv_scale) {
+#pragma unroll 1
+  for (int c = 0; c < NCOLS; c += 16) {
+    uint32_t r[16];
+    tmem_ld_x16(taddr + c, r);
+    float4 bv[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + c + 4 * g;
+      bv[g] = (bias_row != nullptr && col + 4 <= ld) ? __ldg(reinterpret_cast<const float4*>(bias_row + col))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tmem_ld_wait_x16(r);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      r[4 * g + 0] = __float_as_uint(fmaf(bv[g].x, inv_scale, __uint_as_float(r[4 * g + 0])));
+      r[4 * g + 1] = __float_as_uint(fmaf(bv[g].y, inv_scale, __uint_as_float(r[4 * g + 1])));
+      r[4 * g + 2] = __float_as_uint(fmaf(bv[g].z, inv_scale, __uint_as_float(r[4 * g + 2])));
+      r[4 * g + 3] = __float_as_uint(fmaf(bv[g].w, inv_scale, __uint_as_float(r[4 * g + 3])));
+    }
+    tmem_st_x16(taddr + c, r);
+  }
+  tmem_st_wait();
+}
+
+// Transposed-domain counterpart for the attention backward kernels (thread = key, register i = query q0 + i): s[i] +=
+// bias[q0 + i, key] * inv_scale; bias_q0 points at bias[q0, key] (nullptr: key past the sequence), nq = queries left from q0.
+// Lanes hold consecutive keys, so each query's load is one coalesced 128-byte request.
+template <int NQ>
+__device__ __forceinline__ void add_bias_transposed(uint32_t* s, const float* bias_q0, int ld, int nq, float inv_scale) {
+  if (bias_q0 == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const float bv = i < nq ? __ldg(bias_q0 + static_cast<long long>(i) * ld) : 0.f;
+    s[i] = __float_as_uint(fmaf(bv, inv_scale, __uint_as_float(s[i])));
+  }
+}
+
 }  // namespace b200

@@ -443,3 +443,68 @@ def test_layernorm_wide_rows(cols, pdt, rms):
     _close(dw, wr.grad, 3e-2, 2e-3, "wide ln dweight")
     if not rms:
         _close(db, br.grad, 3e-2, 2e-3, "wide ln dbias")
+
+
+# ------------------------------------------------------------------------------------------------ causal / general masks
+def _bias_cases(kind, B, N, H, g):
+    """(reference additive bias broadcastable to [B,H,N,N], the reference's attn_mask / is_causal arguments)."""
+    if kind == "causal":
+        return torch.full((N, N), float("-inf"), device=DEV).triu_(1), None, True
+    if kind == "bool_per_sample":       # random keep-mask per sample, the diagonal always kept (no empty rows)
+        keep = torch.rand(B, 1, N, N, device=DEV, generator=g) > 0.4
+        keep |= torch.eye(N, device=DEV, dtype=torch.bool)
+        return torch.zeros(B, 1, N, N, device=DEV).masked_fill(~keep, float("-inf")), keep, False
+    if kind == "float_per_head":        # additive bias per head (relative-position style), shared by the batch
+        bias = torch.randn(1, H, N, N, device=DEV, generator=g)
+        return bias, bias, False
+    if kind == "float_full":
+        bias = torch.randn(B, H, N, N, device=DEV, generator=g)
+        return bias, bias.bfloat16(), False      # a bf16 mask is accepted (converted to fp32)
+    raise AssertionError(kind)
+
+
+@pytest.mark.parametrize("kind", ["causal", "bool_per_sample", "float_per_head", "float_full"])
+@pytest.mark.parametrize("B,N,H", [(2, 197, 3), (2, 65, 2), (2, 208, 1), (1, 577, 2), (2, 300, 1)])
+def test_attention_bias_fwd_bwd(kind, B, N, H):
+    """softmax(q k^T * scale + bias) v and its gradient (b200_attn_fwd_bias / b200_attn_bwd_bias: is_causal and general
+    attn_mask of timm/layers/attention.py:21-40,108-133) against fp32 autograd; all four production kernels
+    (N <= 208: attention_fwd2 / bwd2, above: the long-sequence pair)."""
+    import b200timm.layers as L
+    ops = _ops()
+    hd, scale = 64, 0.125
+    g = torch.Generator(device=DEV).manual_seed(N + 7 * H + len(kind))
+    qkv = torch.randn(B, N, 3 * H * hd, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B, N, H * hd, device=DEV, generator=g).bfloat16()
+    ref_bias, mask_arg, causal = _bias_cases(kind, B, N, H, g)
+    if mask_arg is not None and mask_arg.dtype == torch.bfloat16:
+        ref_bias = mask_arg.float()
+    operand = L.attn_mask_operand(mask_arg, causal, N, B, DEV)
+    assert operand.dtype == torch.float32 and operand.dim() == 4 and operand.shape[-1] % 4 == 0
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, scale, kv_len=operand, need_lse=True)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=operand)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = ref_in.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    sc = (q @ k.transpose(-1, -2)) * scale + ref_bias
+    ref = (sc.softmax(-1) @ v).transpose(1, 2).reshape(B, N, H * hd)
+    ref.backward(dout.float())
+    _close(out, ref, 1e-2, 2e-2, f"biased attention {kind} N={N}")
+    _close(lse, torch.logsumexp(sc, -1), 1e-2, 1e-3, "biased lse")
+    _close(dqkv, ref_in.grad, 2e-2, 2e-2, f"biased attention bwd {kind} N={N}")
+    if kind == "causal":      # token 0 sees only itself: its output row is exactly v[0]
+        v0 = qkv.view(B, N, 3, H, hd)[:, 0, 2].reshape(B, H * hd)
+        assert torch.equal(out[:, 0], v0)
+
+
+def test_attention_bias_with_fused_qkv_bias_gradient():
+    """The dbias column sums of the N <= 208 backward also come out of the bias variant."""
+    import b200timm.layers as L
+    ops = _ops()
+    B, N, H, hd = 2, 197, 2, 64
+    g = torch.Generator(device=DEV).manual_seed(5)
+    qkv = torch.randn(B, N, 3 * H * hd, device=DEV, generator=g).bfloat16()
+    dout = torch.randn(B, N, H * hd, device=DEV, generator=g).bfloat16()
+    operand = L.attn_mask_operand(None, True, N, B, DEV)
+    out, lse = ops.attention_fwd(qkv, B, N, H, hd, 0.125, kv_len=operand, need_lse=True)
+    db = torch.zeros(3 * H * hd, device=DEV)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125, kv_len=operand, dbias=db)
+    _close(db, dqkv.float().view(B * N, -1).sum(0), 5e-2, 1e-2, "dbias under a causal mask")

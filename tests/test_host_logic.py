@@ -221,3 +221,40 @@ def test_head_padding_in_the_weights_is_exact():
     assert BF.head_pad(32) == 64 and BF.head_pad(64) == 64
     with pytest.raises(B200Error):
         BF.head_pad(80)
+
+
+def test_attn_mask_operand_classifies_masks():
+    """layers.attn_mask_operand: (attn_mask, is_causal) of the reference signatures (attention.py:21-40) -> None / int32
+    valid-key counts for prefix key-padding masks (the NaFlex layout) / an fp32 additive bias for everything else."""
+    import b200timm.layers as L
+    from b200timm._lib import B200Error
+    N, B = 6, 2
+    assert L.attn_mask_operand(None, False, N, B) is None
+    c = L.attn_mask_operand(None, True, N, B, torch.device("cpu"))
+    assert c.shape == (1, 1, N, 8) and c.dtype == torch.float32
+    assert torch.equal(c[0, 0, :, :N], torch.full((N, N), float("-inf")).triu_(1)) and bool((c[..., N:] == 0).all())
+    assert L.attn_mask_operand(torch.ones(B, 1, N, N, dtype=torch.bool), True, N, B, torch.device("cpu")) is c   # causal wins
+    # NaFlex: q_valid & k_valid, bool and additive (finfo.min) forms -> key counts
+    valid = torch.tensor([[1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1]], dtype=torch.bool)
+    m = (valid[:, None, :, None] & valid[:, None, None, :])
+    kv = L.attn_mask_operand(m, False, N, B)
+    assert kv.dtype == torch.int32 and kv.tolist() == [4, 6]
+    add = torch.zeros(B, 1, N, N).masked_fill(~m, torch.finfo(torch.float32).min)
+    assert L.attn_mask_operand(add, False, N, B).tolist() == [4, 6]
+    assert L.attn_mask_operand(m, False, N, B) is kv                      # cached on the mask object
+    # a lower-triangular keep-mask keeps every key for SOME query but is not key padding -> additive bias
+    tri = torch.ones(N, N, dtype=torch.bool).tril()
+    t = L.attn_mask_operand(tri, False, N, B)
+    assert t.dtype == torch.float32 and t.shape == (1, 1, N, 8)
+    assert torch.equal(t[0, 0, :, :N], torch.zeros(N, N).masked_fill(~tri, float("-inf")))
+    with pytest.raises(B200Error):
+        L.BF_mask_to_kv_len(tri, N, B)                                    # strict callers still reject it
+    # float bias per head; key-only [B, 1, 1, N] masks broadcast over the queries
+    fb = torch.randn(1, 3, N, N)
+    f = L.attn_mask_operand(fb, False, N, B)
+    assert f.shape == (1, 3, N, 8) and torch.equal(f[..., :N], fb)
+    hole = torch.tensor([[1, 0, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1]], dtype=torch.bool)[:, None, None, :]
+    h = L.attn_mask_operand(hole, False, N, B)
+    assert h.shape == (B, 1, N, 8) and bool(torch.isinf(h[0, 0, :, 1]).all()) and bool((h[1] == 0).all())
+    with pytest.raises(B200Error):
+        L.attn_bias_operand(torch.zeros(2, 1, N, N + 1), N)

@@ -72,8 +72,8 @@ def test_mirror_and_timm_state_dicts_are_interchangeable():
 
 def test_convnext_is_rebound_and_covered_configs_are_recognised(plugin):
     """timm's ConvNeXt / ConvNeXtBlock dispatch through the plugin; the duck-typed coverage checks accept timm's
-    convnext_tiny modules (patch stem, LayerNorm, Linear MLP, exact GELU) and reject ConvNeXt-V2's GRN blocks; a
-    CPU call keeps timm's own forward."""
+    convnext_tiny modules (patch stem, LayerNorm, Linear MLP, exact GELU) and ConvNeXt-V2 atto's (LayerNorm2d + 1x1-conv MLP
+    + GRN), reject dilated blocks (output_stride=16); a CPU call keeps timm's own forward."""
     from timm.models.convnext import ConvNeXt, ConvNeXtBlock
     from b200timm import convnext as CN
     from b200timm._lib import B200Error
@@ -83,8 +83,10 @@ def test_convnext_is_rebound_and_covered_configs_are_recognised(plugin):
         for blk in stage.blocks:
             CN._check_block(blk)
     v2 = timm.create_model("convnextv2_atto", num_classes=5)
+    CN._check_block(v2.stages[0].blocks[0])
+    dilated = timm.create_model("convnext_tiny", num_classes=5, output_stride=16)
     with pytest.raises(B200Error):
-        CN._check_block(v2.stages[0].blocks[0])
+        CN._check_block(dilated.stages[3].blocks[1])
     x = torch.randn(1, 3, 64, 64)
     with torch.no_grad():
         y_plugin = model(x)
