@@ -48,7 +48,7 @@ extern "C" {
                                  `rot` layout, head_dim 64, one [sin | cos] table shared by batch and heads)       */
 
 B200_API const char* b200_last_error(void);
-/* 7 now (6 -> 7: b200_attn_fwd_bias / b200_attn_bwd_bias); 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
+/* 8 now (7 -> 8: head_dim 128 in b200_attn_fwd / b200_attn_bwd and their _bias variants, b200_attn_bwd_ws_floats_hd); 6 -> 7: b200_attn_fwd_bias / b200_attn_bwd_bias; 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
 B200_API int b200_abi_version(void);
 /* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
 B200_API int b200_device_check(void);
@@ -146,12 +146,17 @@ B200_API int b200_rmsnorm_bwd(const void* dy, const void* x, const void* weight,
  * out: bf16 [B, N, H*hd] (== x.transpose(1,2).reshape(B,N,C) of attention.py:135);
  * lse: fp32 [B, H, N] natural-log-sum-exp of the scaled scores (NULL: not written);
  * kv_len: int32 [B] number of valid (prefix) keys per sample or NULL (all N) -- the NaFlex key-padding
- * mask of naflexvit.py:964-1029 given as lengths.  hd must be 64.                                    */
+ * mask of naflexvit.py:964-1029 given as lengths.  hd: 64, or 128 (ABI >= 8: any N in the forward, N <= 1120 in the
+ * backward).  Other head widths (attention.py:85-93: `attn_head_dim` or dim // num_heads -- 32 of timm's test_vit models, 72
+ * of SigLIP SO400M, 80 of ViT-H, 96) are served by zero-padding every head to the next supported width inside the qkv / proj
+ * weights (b200timm/functional.py: head_pad), which leaves the scores and the output columns unchanged.                    */
 B200_API int b200_attn_fwd(const void* qkv, void* out, float* lse, const int32_t* kv_len, int32_t B, int32_t N,
                   int32_t H, int32_t hd, float scale, void* stream);
 /* Floats of workspace b200_attn_bwd needs behind its `delta` argument: B*H*N for the row sums delta[b,h,q] = sum_d
  * dO*O, plus -- for N > 208, where dQ is accumulated over key tiles in fp32 through TMA reduce-adds -- B*N*H*64. */
 B200_API int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H);
+/* The same for a head width hd (ABI >= 8): the fp32 dQ buffer B*N*H*hd is needed for N > 208 or hd = 128. */
+B200_API int64_t b200_attn_bwd_ws_floats_hd(int32_t B, int32_t N, int32_t H, int32_t hd);
 
 /* Backward: dqkv bf16 [B,N,3,H,hd] from dout bf16 [B,N,H*hd]; recomputes P from qkv and lse.
  * delta: fp32 workspace [B,H,N].  dbias (ABI >= 6): NULL, or a zero-initialised fp32 [3*H*hd] that receives the column sums

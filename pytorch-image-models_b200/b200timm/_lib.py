@@ -87,6 +87,7 @@ SIGNATURES = {
     "b200_convert_f32": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "b200_attn_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp]),
     "b200_attn_bwd_ws_floats": (ctypes.c_int64, [_i32, _i32, _i32]),
+    "b200_attn_bwd_ws_floats_hd": (ctypes.c_int64, [_i32, _i32, _i32, _i32]),
     "b200_attn_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp]),
     "b200_attn_fwd_bias": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "b200_attn_bwd_bias": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _f32,

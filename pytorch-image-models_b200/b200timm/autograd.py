@@ -277,7 +277,7 @@ class BlockFn(torch.autograd.Function):
         ops.linear_wgrad(dbr1, o.view(B * N, -1), out=v[4])
         if bproj is not None:
             ops.colsum(dbr1, out=v[5], accumulate=True)
-        fused_dbqkv = bqkv is not None and ops.attn_bwd_bias_fused(N)       # the qkv bias gradient rides in the attention backward
+        fused_dbqkv = bqkv is not None and ops.attn_bwd_bias_fused(N, hd)       # the qkv bias gradient rides in the attention backward
         dqkv = ops.attention_bwd(qkv, o, do.view(B, N, -1), lse, B, N, H, hd, scale, kv_len,
                                  dbias=v[3] if fused_dbqkv else None).view(B * N, -1)
         dh1 = ops.linear_dgrad(dqkv, wqkv)

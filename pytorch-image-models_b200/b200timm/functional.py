@@ -162,21 +162,23 @@ def _w(linear):
     return cache[1]
 
 
-# ------------------------------------------------------------------------------------------------ head_dim < 64
-# The attention kernels are built for head_dim 64 (one 128-byte swizzle atom per token row and head).  Narrower heads
-# (timm's test_vit* models: 32; attention.py:85-93 allows any dim // num_heads) run on the SAME kernels through zero
-# padding that lives entirely in the WEIGHTS: the rows of the qkv projection (and its bias) are spread to 64 per head with
-# zero rows in between, the columns of the output projection likewise -- the GEMM then writes a [M, 3 * H * 64] buffer whose
+# ------------------------------------------------------------------------------------------------ head_dim != 64
+# The attention kernels are built for head widths 64 (one 128-byte swizzle atom per token row and head) and 128 (two atoms:
+# the long-sequence kernels with NH = 2).  Other widths (attention.py:85-93 allows any dim // num_heads or attn_head_dim: 32 in
+# timm's test_vit* models, 72 in SigLIP SO400M, 80 in ViT-H, 96) run on the SAME kernels through zero
+# padding that lives entirely in the WEIGHTS: the rows of the qkv projection (and its bias) are spread to P = 64 / 128 per head
+# with zero rows in between, the columns of the output projection likewise -- the GEMM then writes a [M, 3 * H * P] buffer whose
 # padding columns are exact zeros (q . k over the padding adds 0, the padded v columns produce output columns that meet zero
 # weights), and softmax scaling uses the module's own scale (true head_dim ** -0.5).  Padded weights are cached at inference
 # and built differentiably (F.pad on a view) in training, so gradients reach the real parameters through autograd.
 def head_pad(hd):
-    """Padded head width the kernels run (64), or raises for widths that cannot be padded."""
-    if hd == 64:
+    """Padded head width P the kernels run (64 or 128), or raises for widths that cannot be padded."""
+    if hd % 8 == 0 and 0 < hd <= 64:
         return 64
-    if hd < 64 and hd % 8 == 0:
-        return 64
-    raise B200Error(f"head_dim {hd} is not supported (64, or a multiple of 8 below 64 through weight padding)")
+    if hd % 8 == 0 and 64 < hd <= 128:
+        return 128
+    raise B200Error(f"head_dim {hd} is not supported (a multiple of 8 up to 128; 64 and 128 natively, the others through "
+                    f"weight padding)")
 
 
 def _cached(module, attr, key, build):
@@ -189,27 +191,29 @@ def _cached(module, attr, key, build):
 
 
 def _pad_rows(t, groups, H, hd):
-    """[groups * H * hd, ...] -> [groups * H * 64, ...]: every head's hd rows followed by 64 - hd zero rows."""
-    if t is None or hd == 64:
+    """[groups * H * hd, ...] -> [groups * H * P, ...]: every head's hd rows followed by P - hd zero rows (P = head_pad(hd))."""
+    P = head_pad(hd)
+    if t is None or hd == P:
         return t
     tail = t.shape[1:]
     v = t.reshape(groups * H, hd, *tail)
-    pad = [0, 0] * len(tail) + [0, 64 - hd]
-    return F.pad(v, pad).reshape(groups * H * 64, *tail)
+    pad = [0, 0] * len(tail) + [0, P - hd]
+    return F.pad(v, pad).reshape(groups * H * P, *tail)
 
 
 def _pad_cols(w, H, hd):
-    """[out, H * hd] -> [out, H * 64]: zero columns after every head's hd columns."""
-    if hd == 64:
+    """[out, H * hd] -> [out, H * P]: zero columns after every head's hd columns."""
+    P = head_pad(hd)
+    if hd == P:
         return w
-    return F.pad(w.reshape(w.shape[0], H, hd), (0, 64 - hd)).reshape(w.shape[0], H * 64)
+    return F.pad(w.reshape(w.shape[0], H, hd), (0, P - hd)).reshape(w.shape[0], H * P)
 
 
 def head_padded_linear_in(linear, groups, H, hd, bias=None, weight=None):
-    """(weight, bias) of a projection INTO head space (qkv: groups = 3, kv: 2, q: 1) with heads padded to 64 rows."""
+    """(weight, bias) of a projection INTO head space (qkv: groups = 3, kv: 2, q: 1) with heads padded to head_pad(hd) rows."""
     w = _w(linear) if weight is None else weight
     b = linear.bias if bias is None else bias
-    if hd == 64:
+    if hd == head_pad(hd):
         return w, b
     if torch.is_grad_enabled() and (w.requires_grad or (b is not None and b.requires_grad)):
         return _pad_rows(w, groups, H, hd), _pad_rows(b, groups, H, hd)
@@ -219,9 +223,9 @@ def head_padded_linear_in(linear, groups, H, hd, bias=None, weight=None):
 
 
 def head_padded_linear_out(linear, H, hd):
-    """weight of a projection OUT of head space (attention's proj) with every head's columns padded to 64."""
+    """weight of a projection OUT of head space (attention's proj) with every head's columns padded to head_pad(hd)."""
     w = _w(linear)
-    if hd == 64:
+    if hd == head_pad(hd):
         return w
     if torch.is_grad_enabled() and w.requires_grad:
         return _pad_cols(w, H, hd)
@@ -284,7 +288,7 @@ def attention_forward(attn, x, kv_len=None, residual=None, gamma=None):
     qkv = ops.linear_fwd(x2, wqkv, bqkv)
     if qk is not None:
         ops.qk_norm_fwd(qkv, B * N, H, *qk)
-    o, _ = ops.attention_fwd(qkv, B, N, H, 64, attn.scale, kv_len)
+    o, _ = ops.attention_fwd(qkv, B, N, H, head_pad(hd), attn.scale, kv_len)
     o2 = o.view(B * N, -1)
     if sn is not None:
         o2 = ops.layernorm_fwd(o2, *sn)[0]
@@ -573,7 +577,7 @@ def parallel_block_forward(blk, x, kv_len=None):
     else:
         w_ao, w_mo = _w(blk.attn_out_proj), _w(blk.mlp_out_proj)
         b_ao, b_mo = blk.attn_out_proj.bias, blk.mlp_out_proj.bias
-    if hd != 64:      # heads padded to 64 inside the weights (see head_pad): not cached here -- slices of a fused projection
+    if hd != head_pad(hd):      # heads padded inside the weights (see head_pad): not cached here -- slices of a fused projection
         w_qkv, b_qkv, w_ao = _pad_rows(w_qkv, 3, H, hd), _pad_rows(b_qkv, 3, H, hd), _pad_cols(w_ao, H, hd)
         if not (torch.is_grad_enabled() and w_qkv.requires_grad):
             w_qkv, w_ao = w_qkv.contiguous(), w_ao.contiguous()
@@ -602,7 +606,7 @@ def parallel_block_forward(blk, x, kv_len=None):
     qkv = ops.linear_fwd(y, w_qkv, b_qkv)
     if qk is not None:
         ops.qk_norm_fwd(qkv, B * N, H, *qk)
-    o, _ = ops.attention_fwd(qkv, B, N, H, 64, blk.scale, kv_len)
+    o, _ = ops.attention_fwd(qkv, B, N, H, head_pad(hd), blk.scale, kv_len)
     t = ops.linear_fwd(o.view(B * N, -1), w_ao, b_ao, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=gamma, row_scale=rs,
                        rows_per_scale=N)
     out = ops.linear_fwd(hmlp, w_mo, b_mo, epilogue=ops.EPI_BIAS_RESIDUAL, aux=t, gamma=gamma, row_scale=rs, rows_per_scale=N)
@@ -638,7 +642,7 @@ def block_forward(blk, x, kv_len=None):
     h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
     wqkv, bqkv = head_padded_linear_in(attn.qkv, 3, attn.num_heads, attn.head_dim)
     qkv = ops.linear_fwd(h, wqkv, bqkv)
-    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, 64, attn.scale, kv_len)
+    o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, head_pad(attn.head_dim), attn.scale, kv_len)
     x2 = ops.linear_fwd(o.view(B * N, -1), head_padded_linear_out(attn.proj, attn.num_heads, attn.head_dim), attn.proj.bias,
                         epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
                         gamma=_gamma(blk.ls1), row_scale=rs1, rows_per_scale=N)
@@ -843,12 +847,12 @@ def attention_pool_forward(pool, x):
         raise B200Error(f"AttentionPoolLatent: pool={pool.pool!r} is not covered")
     qk_norm = not _is_identity(pool.q_norm) or not _is_identity(pool.k_norm)
     H, hd = pool.num_heads, pool.head_dim
-    head_pad(hd)
+    P = head_pad(hd)
     if hd != 64 and qk_norm:
         raise B200Error("qk_norm with head_dim != 64 is not covered")
     _check_drop(getattr(pool, "proj_drop", None), "proj_drop")
     B, N, D = x.shape
-    Dp = H * 64
+    Dp = H * P
     L = pool.latent_len
     if L > N:
         raise B200Error("AttentionPoolLatent: more latent queries than tokens is not covered")
@@ -875,7 +879,7 @@ def attention_pool_forward(pool, x):
             if float(qe) != float(ke) or (qb is None) != (kb is None):
                 raise B200Error("q_norm / k_norm need equal eps and affine parameters")
             ops.qk_norm_fwd(qkv, B * N, H, qw, qb, kw, kb, qe)
-        o = ops.attention_fwd(qkv, B, N, H, 64, pool.scale, None)[0][:, :L].contiguous()
+        o = ops.attention_fwd(qkv, B, N, H, P, pool.scale, None)[0][:, :L].contiguous()
     if not _is_identity(pool.proj):
         wp = head_padded_linear_out(pool.proj, H, hd)
         if _needs_grad(o, pool.proj):
@@ -883,8 +887,8 @@ def attention_pool_forward(pool, x):
             o = LinearFn.apply(o, wp, pool.proj.bias)
         else:
             o = ops.linear_fwd(o.reshape(-1, Dp), wp, pool.proj.bias).view(B, L, -1)
-    elif hd != 64:
-        o = o.view(B, L, H, 64)[..., :hd].reshape(B, L, D)
+    elif hd != P:
+        o = o.view(B, L, H, P)[..., :hd].reshape(B, L, D)
     if pool.mlp is not None:
         h = o if _is_identity(pool.norm) else layernorm(pool.norm, o)
         o = o + mlp_forward(pool.mlp, h)
@@ -901,13 +905,13 @@ def attention_pool_prr_forward(pool, x):
     the [B, N, 3, H, 64] layout the attention kernels read (a data-movement cat; its autograd adds dq + dk + dv)."""
     B, N, D = x.shape
     H, hd = pool.num_heads, pool.head_dim
-    head_pad(hd)
+    P = head_pad(hd)
     _bf16_2d(x, D)
     h = x if _is_identity(pool.pre_norm) else layernorm(pool.pre_norm, x)
-    hp = h if hd == 64 else F.pad(h.reshape(B, N, H, hd), (0, 64 - hd)).reshape(B, N, H * 64)
+    hp = h if hd == P else F.pad(h.reshape(B, N, H, hd), (0, P - hd)).reshape(B, N, H * P)
     o = sdpa_packed(torch.cat([hp, hp, hp], dim=-1), H, pool.scale)
-    if hd != 64:
-        o = o.view(B, N, H, 64)[..., :hd].reshape(B, N, D)
+    if hd != P:
+        o = o.view(B, N, H, P)[..., :hd].reshape(B, N, D)
     o = o if _is_identity(pool.post_norm) else layernorm(pool.post_norm, o)
     if pool.pool == "token":
         return o[:, 0]

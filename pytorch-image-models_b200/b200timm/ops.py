@@ -386,10 +386,10 @@ def attention_fwd(qkv, B, N, H, hd, scale, kv_len=None, need_lse=False):
     return out, lse
 
 
-def attn_bwd_bias_fused(N):
+def attn_bwd_bias_fused(N, hd=64):
     """True when attention_bwd(..., dbias=...) can reduce the qkv bias gradient from its output tiles."""
     import os
-    return N <= 208 and os.environ.get("B200_ATTN_BWD_V1", "0")[:1] != "1"
+    return N <= 208 and hd == 64 and os.environ.get("B200_ATTN_BWD_V1", "0")[:1] != "1"
 
 
 def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None, dbias=None):
@@ -403,7 +403,7 @@ def attention_bwd(qkv, out, dout, lse, B, N, H, hd, scale, kv_len=None, dbias=No
         raise B200Error("attention_bwd: lse must be contiguous fp32 [B,H,N]")
     dqkv = torch.empty_like(qkv)
     lib = _lib.load()
-    delta = torch.empty(lib.b200_attn_bwd_ws_floats(B, N, H), dtype=torch.float32, device=qkv.device)   # delta (+ fp32 dQ)
+    delta = torch.empty(lib.b200_attn_bwd_ws_floats_hd(B, N, H, hd), dtype=torch.float32, device=qkv.device)   # delta (+ fp32 dQ)
     if dbias is not None and (dbias.dtype != torch.float32 or dbias.numel() != 3 * H * hd or not dbias.is_contiguous()):
         raise B200Error("attention_bwd: dbias must be a contiguous fp32 [3*H*hd] tensor")
     if kv_len is not None and kv_len.dtype == torch.float32:

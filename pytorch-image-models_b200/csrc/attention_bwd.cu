@@ -46,19 +46,21 @@ struct AttnBwdParams {
   float scale, scale_log2e;
 };
 
-// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (fp32); one warp per (b, q) row of H*64 elements.
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (fp32); one warp per (b, q) row of H*hd elements (LPH = hd / 8 lanes per head).
+template <int LPH>
 __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                       float* __restrict__ delta, int B, int N, int H) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= static_cast<long long>(B) * N) return;
   const int b = static_cast<int>(row / N), q = static_cast<int>(row % N);
-  // a head's 64 elements = 8 lanes x 8 elements; 4 heads per warp pass
-  for (int h0 = 0; h0 < H; h0 += 4) {
-    const int h = h0 + (lane >> 3);
+  constexpr int hd = LPH * 8;
+  // a head's hd elements = LPH lanes x 8 elements; 32 / LPH heads per warp pass
+  for (int h0 = 0; h0 < H; h0 += 32 / LPH) {
+    const int h = h0 + lane / LPH;
     float s = 0.f;
     if (h < H) {
-      const long long off = row * (H * kHd) + h * kHd + (lane & 7) * 8;
+      const long long off = row * (H * hd) + h * hd + (lane % LPH) * 8;
       const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + off));
       const uint4 g = __ldg(reinterpret_cast<const uint4*>(dout + off));
       s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
@@ -68,7 +70,8 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (h < H && (lane & 7) == 0) delta[(static_cast<long long>(b) * H + h) * N + q] = s;
+    if (LPH == 16) s += __shfl_xor_sync(0xffffffffu, s, 8);
+    if (h < H && lane % LPH == 0) delta[(static_cast<long long>(b) * H + h) * N + q] = s;
   }
 }
 
@@ -370,14 +373,16 @@ namespace b200 {
 int launch_attn_bwd2(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
                      const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, float scale, float* dbias, cudaStream_t st);
 int launch_attn_bwd_long(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq32, void* dqkv,
-                         const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, float scale, cudaStream_t st);
+                         const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, int hd, float scale, cudaStream_t st);
 }
 using namespace b200;
 
-extern "C" int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H) {
+extern "C" int64_t b200_attn_bwd_ws_floats_hd(int32_t B, int32_t N, int32_t H, int32_t hd) {
   const long long d = (static_cast<long long>(B) * H * N + 3) / 4 * 4;
-  return N > kNQ ? d + static_cast<long long>(B) * N * H * kHd : d;
+  return (N > kNQ || hd > kHd) ? d + static_cast<long long>(B) * N * H * hd : d;     // + the long kernel's fp32 dQ buffer
 }
+
+extern "C" int64_t b200_attn_bwd_ws_floats(int32_t B, int32_t N, int32_t H) { return b200_attn_bwd_ws_floats_hd(B, N, H, kHd); }
 
 static int attn_bwd_v1(const void* qkv, const void* dout, const float* lse, float* delta, void* dqkv, const int32_t* kv_len,
                        int32_t B, int32_t N, int32_t H, float scale, cudaStream_t st);
@@ -388,21 +393,23 @@ static int attn_bwd_dispatch(const void* qkv, const void* out, const void* dout,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv && out && dout && lse && delta && dqkv, "b200_attn_bwd: null pointer");
   B200_CHECK_ARG(B > 0 && N > 0 && H > 0 && B <= 65535, "b200_attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
-  if (hd != kHd) return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: head_dim %d not supported (64 only)", hd);
+  if (hd != kHd && hd != 2 * kHd)
+    return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: head_dim %d not supported (64 or 128; other widths are zero-padded by the caller)", hd);
   {
     const long long rows = static_cast<long long>(B) * N;
     const int wpb = 8;
-    attn_bwd_delta_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+    auto dk = hd == kHd ? attn_bwd_delta_kernel<8> : attn_bwd_delta_kernel<16>;
+    dk<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, N, H);
     B200_CUDA_OK(cudaGetLastError());
   }
   static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_BWD_V1"); return e != nullptr && e[0] == '1'; }();
-  if (dbias != nullptr && (N > kNQ || (use_v1 && bias == nullptr)))
-    return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: the fused qkv-bias gradient is available for N <= %d (v2 kernel) only", kNQ);
-  if (N > kNQ) {
-    // long sequences (attention_bwd_long.cu): the workspace continues behind delta with the fp32 dq buffer
+  if (dbias != nullptr && (N > kNQ || hd != kHd || (use_v1 && bias == nullptr)))
+    return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: the fused qkv-bias gradient is available for N <= %d, head_dim 64 (v2 kernel) only", kNQ);
+  if (N > kNQ || hd != kHd) {
+    // long sequences and 128-wide heads (attention_bwd_long.cu): the workspace continues behind delta with the fp32 dq buffer
     float* dq32 = delta + (static_cast<long long>(B) * H * N + 3) / 4 * 4;
-    return launch_attn_bwd_long(qkv, dout, lse, delta, dq32, dqkv, kv_len, bias, B, N, H, scale, st);
+    return launch_attn_bwd_long(qkv, dout, lse, delta, dq32, dqkv, kv_len, bias, B, N, H, hd, scale, st);
   }
   // v2 (attention_bwd2.cu: two query halves, 8 compute warps + issuer warp) is the default; B200_ATTN_BWD_V1=1 keeps
   // the simpler v1 kernel of this file selectable for A/B comparison and as a cross-check in the tests (no bias variant).

@@ -1,4 +1,5 @@
-// Attention backward for long sequences (208 < N <= 1120 tokens: ViT-L/14 @336 = 577, NaFlex batches), head_dim 64.
+// Attention backward for long sequences (208 < N <= 2240 tokens: ViT-L/14 @336 = 577, DINOv2 @518 = 1370, NaFlex batches), head_dim 64, and for
+// head_dim 128 at any N <= 1120 (NH = 2, see the end of this comment).
 // Same transposed-domain mathematics as attention_bwd2.cu, re-tiled so that nothing scales with N on chip:
 //   * persistent CTAs loop over (image, head) items; per item an outer loop over 128-key tiles and an inner loop over
 //     112-query chunks.  K / V of the key tile stay in shared memory, Q / dO chunks stream through a two-stage TMA ring;
@@ -7,6 +8,11 @@
 //   * the dQ partial of a (key tile, query chunk) step leaves as fp32 through a swizzled staging tile and a TMA
 //     reduce-add into a zero-initialised fp32 dq buffer [B, N, H*64] (the sum over key tiles happens in L2);
 //     attn_dq_convert_kernel writes it into the q third of dqkv afterwards.  dK / dV tiles leave as bf16 TMA stores.
+// head_dim 128 (NH = 2; 72 / 80 / 96-wide heads arrive zero-padded through the weights): every operand tile is kept as two
+// 64-wide sub-tiles (one 128-byte swizzle atom per token row each).  TMEM cannot hold both halves of dV / dK / dQ next to
+// S^T / dP^T (608 columns), so a work item is (image, head, HALF): S^T and dP^T contract over the full 128-wide head (8
+// k-steps over the two sub-tiles), the three accumulations run for the item's half only and the other half is a second item
+// (S^T / dP^T are computed twice: 14 instead of 10 64-wide MMA units per head).  The Q / dO ring has one stage (shared memory).
 // The reference has no backward code (gradients of timm/layers/attention.py:115-135 come from autograd's SDPA backward);
 // the kernel is validated against autograd of the oracle, like the short-sequence kernels.
 #include "common.h"
@@ -21,19 +27,25 @@ constexpr int kKT = 128;                        // keys per tile
 constexpr int kRowB = kHd * 2;                  // 128 B per token row
 constexpr int kKVB = kKT * kRowB;               // 16384
 constexpr int kQB = kQH * kRowB;                // 14336 (14 x 1024: SW128 atoms stay aligned)
-constexpr int kOffK = 0, kOffV = kKVB;
-constexpr int kOffQ = 2 * kKVB;                 // stage s: Q chunk at kOffQ + s * kStage, dO chunk right behind it
-constexpr int kStage = 2 * kQB;                 // 28672
-constexpr int kOffP = kOffQ + 2 * kStage;       // 90112: P^T, 14 chunks of [128 keys x 8 queries] bf16
 constexpr int kPB = (kQH / 8) * 2048;           // 28672
-constexpr int kOffDS = kOffP + kPB;             // 118784: dS^T, 16 chunks (the dQ MMA reads a full 128-query M tile)
 constexpr int kDSB = 16 * 2048;
-constexpr int kOffOut = kOffDS + kDSB;          // 151552: 8 warps x (32 rows x 128 B) output staging
-constexpr int kMaxChunks = 10;                  // N <= 1120
-constexpr int kOffLse = kOffOut + 8 * 4096;     // 184320
-constexpr int kOffDelta = kOffLse + kMaxChunks * kQH * 4;
-constexpr int kOffBar = kOffDelta + kMaxChunks * kQH * 4;   // 193280
-constexpr int kSmemTotal = kOffBar + 128;
+// shared-memory layout for NH 64-wide halves of the head (offsets in the comments: NH = 1)
+template <int NH>
+struct BwdLongSmem {
+  static constexpr int kStages = NH == 1 ? 2 : 1;         // Q / dO ring depth (NH = 2: one stage is all that fits)
+  static constexpr int kMaxChunks = NH == 1 ? 20 : 10;    // query chunks whose lse / delta fit: N <= 2240 (DINOv2 @518: 1370) / 1120
+  static constexpr int kOffK = 0, kOffV = NH * kKVB;      // NH sub-tiles each
+  static constexpr int kOffQ = 2 * NH * kKVB;             // stage s: Q chunk (NH sub-tiles) at kOffQ + s * kStage, dO chunk behind it
+  static constexpr int kStage = 2 * NH * kQB;             // 28672
+  static constexpr int kOffP = kOffQ + kStages * kStage;  // 90112: P^T, 14 chunks of [128 keys x 8 queries] bf16
+  static constexpr int kOffDS = kOffP + kPB;              // 118784: dS^T, 16 chunks (the dQ MMA reads a full 128-query M tile)
+  static constexpr int kOffOut = kOffDS + kDSB;           // 151552: 8 warps x (32 rows x 128 B) output staging
+  static constexpr int kOffLse = kOffOut + 8 * 4096;      // 184320
+  static constexpr int kOffDelta = kOffLse + kMaxChunks * kQH * 4;
+  static constexpr int kOffBar = kOffDelta + kMaxChunks * kQH * 4;   // 202240
+  static constexpr int kSmemTotal = kOffBar + 128;
+};
+static_assert(BwdLongSmem<2>::kSmemTotal <= 232448, "head_dim 128: shared memory");
 constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
 constexpr int kComputeThreads = 256;
 }  // namespace
@@ -76,13 +88,18 @@ __device__ __forceinline__ void pds8_l(const uint32_t* s, const uint32_t* dp, co
 }
 
 // BIAS = true: scores + additive bias (causal triangle / general attn_mask), as in attention_bwd2.cu.
-template <bool BIAS>
+template <bool BIAS, int NH = 1>
 __global__ void __launch_bounds__(kComputeThreads + 32, 1)
 attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_constant__ CUtensorMap tm_q,
                      const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_out32,
                      const __grid_constant__ CUtensorMap tm_dq32, const __grid_constant__ CUtensorMap tm_dq16,
                      const AttnBwdLongParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  using L = BwdLongSmem<NH>;
+  constexpr int kStages = L::kStages, kOffK = L::kOffK, kOffV = L::kOffV, kOffQ = L::kOffQ, kStage = L::kStage, kOffP = L::kOffP,
+                kOffDS = L::kOffDS, kOffOut = L::kOffOut, kOffLse = L::kOffLse, kOffDelta = L::kOffDelta, kOffBar = L::kOffBar;
+  static_assert(L::kSmemTotal <= 232448, "shared memory");
+  constexpr int kHD = NH * kHd;                            // the (padded) head width
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
   uint8_t* sP = smem + kOffP;
@@ -102,9 +119,9 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, H = p.H;
-  const int num_items = p.B * H;
+  const int num_items = p.B * H * NH;                      // item = ((image, head), half of the head)
   const int nq = (N + kQH - 1) / kQH;                      // query chunks per item
-  auto item_kvlen = [&](int item) { return p.kv_len != nullptr ? max(1, min(p.kv_len[item / H], N)) : N; };
+  auto item_kvlen = [&](int item) { return p.kv_len != nullptr ? max(1, min(p.kv_len[item / (H * NH)], N)) : N; };
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_kv);
@@ -145,52 +162,68 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
       uint32_t gs = 0, gk = 0;                 // global step / key-tile counters (barrier phases)
       uint32_t loads[2] = {0, 0}, uses[2] = {0, 0};
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int b = item / H, h = item - b * H;
+        const int bh = item / NH, hf = item - bh * NH;     // hf: which 64-wide half this item accumulates
+        const int b = bh / H, h = bh - b * H;
         const int nkt = (item_kvlen(item) + kKT - 1) / kKT;
         const int total = nkt * nq;
         auto load_chunk = [&](int qh, int st) {
           if (loads[st] > 0) mbar_wait(&bar_qfree[st], (loads[st] - 1) & 1);   // the stage's previous readers are done
           uint8_t* dst = smem + kOffQ + st * kStage;
-          mbar_arrive_expect_tx(&bar_q[st], 2 * kQB);
-          tma_load_2d(dst, &tm_q, &bar_q[st], h * kHd, b * N + qh * kQH);
-          tma_load_2d(dst + kQB, &tm_do, &bar_q[st], h * kHd, b * N + qh * kQH);
+          mbar_arrive_expect_tx(&bar_q[st], 2 * NH * kQB);
+#pragma unroll
+          for (int i = 0; i < NH; ++i) {
+            tma_load_2d(dst + i * kQB, &tm_q, &bar_q[st], h * kHD + i * kHd, b * N + qh * kQH);
+            tma_load_2d(dst + (NH + i) * kQB, &tm_do, &bar_q[st], h * kHD + i * kHd, b * N + qh * kQH);
+          }
           ++loads[st];
         };
-        load_chunk(0, gs & 1);
+        load_chunk(0, gs % kStages);
         for (int s = 0; s < total; ++s, ++gs) {
           const int kt = s / nq, qh = s - kt * nq;
-          const int st = gs & 1;
+          const int st = gs % kStages;
           if (qh == 0) {
             if (gk > 0) mbar_wait(bar_kvdone, (gk - 1) & 1);       // every MMA reading the previous K / V tile is done
-            mbar_arrive_expect_tx(bar_kv, 2 * kKVB);
-            tma_load_2d(sK, &tm_kv, bar_kv, (H + h) * kHd, b * N + kt * kKT);
-            tma_load_2d(sV, &tm_kv, bar_kv, (2 * H + h) * kHd, b * N + kt * kKT);
+            mbar_arrive_expect_tx(bar_kv, 2 * NH * kKVB);
+#pragma unroll
+            for (int i = 0; i < NH; ++i) {
+              tma_load_2d(sK + i * kKVB, &tm_kv, bar_kv, (H + h) * kHD + i * kHd, b * N + kt * kKT);
+              tma_load_2d(sV + i * kKVB, &tm_kv, bar_kv, (2 * H + h) * kHD + i * kHd, b * N + kt * kKT);
+            }
             mbar_wait(bar_kv, gk & 1);
           }
           mbar_wait(&bar_q[st], uses[st] & 1);
           ++uses[st];
           tc_fence_after();
-          const uint32_t qs = smem_u32(smem + kOffQ + st * kStage), dos = qs + kQB;
+          const uint32_t qs = smem_u32(smem + kOffQ + st * kStage), dos = qs + NH * kQB;
           {
-            const uint64_t kd = make_smem_desc(smem_u32(sK), 16, 1024, kLayoutSw128);
-            const uint64_t vd = make_smem_desc(smem_u32(sV), 16, 1024, kLayoutSw128);
-            const uint64_t qd = make_smem_desc(qs, 16, 1024, kLayoutSw128);
-            const uint64_t dod = make_smem_desc(dos, 16, 1024, kLayoutSw128);
 #pragma unroll
-            for (int k = 0; k < kHd / 16; ++k) umma_ss(tmem_base + kColS, kd + 2 * k, qd + 2 * k, idesc_sd, k > 0 ? 1u : 0u);
+            for (int i = 0; i < NH; ++i) {      // S^T = K Q^T: the contraction runs over every 64-wide half of the head
+              const uint64_t kd = make_smem_desc(smem_u32(sK + i * kKVB), 16, 1024, kLayoutSw128);
+              const uint64_t qd = make_smem_desc(qs + i * kQB, 16, 1024, kLayoutSw128);
 #pragma unroll
-            for (int k = 0; k < kHd / 16; ++k) umma_ss(tmem_base + kColDP, vd + 2 * k, dod + 2 * k, idesc_sd, k > 0 ? 1u : 0u);
+              for (int k = 0; k < kHd / 16; ++k)
+                umma_ss(tmem_base + kColS, kd + 2 * k, qd + 2 * k, idesc_sd, (i > 0 || k > 0) ? 1u : 0u);
+            }
+#pragma unroll
+            for (int i = 0; i < NH; ++i) {      // dP^T = V dO^T
+              const uint64_t vd = make_smem_desc(smem_u32(sV + i * kKVB), 16, 1024, kLayoutSw128);
+              const uint64_t dod = make_smem_desc(dos + i * kQB, 16, 1024, kLayoutSw128);
+#pragma unroll
+              for (int k = 0; k < kHd / 16; ++k)
+                umma_ss(tmem_base + kColDP, vd + 2 * k, dod + 2 * k, idesc_sd, (i > 0 || k > 0) ? 1u : 0u);
+            }
             umma_commit(bar_sd);
           }
-          if (s + 1 < total) load_chunk((s + 1) % nq, (gs + 1) & 1);   // next chunk streams in under this step
+          if (kStages == 2 && s + 1 < total) load_chunk((s + 1) % nq, (gs + 1) % kStages);   // next chunk streams in under this step
           mbar_wait(bar_p, gs & 1);
           if (gs > 0) mbar_wait(bar_dqfree, (gs - 1) & 1);          // the previous dQ partial has left TMEM
           if (qh == 0 && gk > 0) mbar_wait(bar_tail, (gk - 1) & 1);  // the previous key tile's dV / dK have left TMEM
           tc_fence_after();
           const uint64_t pd = make_smem_desc(smem_u32(sP), 2048, 128, kLayoutNone);
           const uint64_t dsd = make_smem_desc(smem_u32(sDS), 2048, 128, kLayoutNone);
-          const uint64_t dob = make_smem_desc(dos, 1024, 1024, kLayoutSw128);
-          const uint64_t qb = make_smem_desc(qs, 1024, 1024, kLayoutSw128);
+          // the accumulations of this item's half hf: dV[:, hf] / dK[:, hf] / dQ[:, hf] read sub-tile hf of dO / Q / K
+          const uint64_t dob = make_smem_desc(dos + hf * kQB, 1024, 1024, kLayoutSw128);
+          const uint64_t qb = make_smem_desc(qs + hf * kQB, 1024, 1024, kLayoutSw128);
 #pragma unroll
           for (int k = 0; k < kQH / 16; ++k)     // dV_kt (+)= P^T dO_qh
             umma_ss(tmem_base + kColDV, pd + static_cast<uint64_t>(k * (4096 >> 4)), dob + static_cast<uint64_t>(k * (2048 >> 4)),
@@ -200,7 +233,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
             umma_ss(tmem_base + kColDK, dsd + static_cast<uint64_t>(k * (4096 >> 4)), qb + static_cast<uint64_t>(k * (2048 >> 4)),
                     idesc_kv, (qh > 0 || k > 0) ? 1u : 0u);
           const uint64_t ad = make_smem_desc(smem_u32(sDS), 128, 2048, kLayoutNone);
-          const uint64_t kb = make_smem_desc(smem_u32(sK), 1024, 1024, kLayoutSw128);
+          const uint64_t kb = make_smem_desc(smem_u32(sK + hf * kKVB), 1024, 1024, kLayoutSw128);
 #pragma unroll
           for (int k = 0; k < kKT / 16; ++k)     // dQ partial = dS K_kt   (A: dS^T read MN-major; B: K_kt MN-major in place)
             umma_ss(tmem_base + kColDQ, ad + static_cast<uint64_t>(k * (256 >> 4)), kb + static_cast<uint64_t>(k * (2048 >> 4)),
@@ -211,6 +244,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
             umma_commit(bar_kvdone);
             ++gk;
           }
+          // one-stage ring: the next chunk can only be requested once this step's MMAs have released the stage
+          if (kStages == 1 && s + 1 < total) load_chunk((s + 1) % nq, 0);
         }
       }
     }
@@ -224,16 +259,17 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
     uint8_t* ostg = smem + kOffOut + warp * 4096;
     const uint32_t ostg_row = smem_u32(ostg) + lane * 128;
     const uint32_t osw = static_cast<uint32_t>(lane & 7);
-    const long long tok_stride = 3LL * H * kHd;
+    const long long tok_stride = 3LL * H * kHD;
     uint32_t gs = 0, gk = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int b = item / H, h = item - b * H;
+      const int bh = item / NH, hf = item - bh * NH;
+      const int b = bh / H, h = bh - b * H;
       const int kvlen = item_kvlen(item);
       const int nkt = (kvlen + kKT - 1) / kKT;
       // softmax statistics of the item's queries (lse in the log2 domain; +inf -> P = 0 for padding queries)
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int q = tid; q < nq * kQH; q += kComputeThreads) {
-        const long long idx = static_cast<long long>(item) * N + q;
+        const long long idx = static_cast<long long>(bh) * N + q;
         sLse[q] = (q < N) ? p.lse[idx] * 1.4426950408889634f : INFINITY;
         sDelta[q] = (q < N) ? p.delta[idx] : 0.f;
       }
@@ -313,7 +349,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
             const int q0 = qh * kQH + wrow;                      // first query row of this warp's tile
             if (lane == 0 && wrow < kQH && q0 < N) {
               // the last quadrant of a 112-query chunk holds 16 rows only
-              tma_reduce_add_3d(wrow + 32 <= kQH ? &tm_dq32 : &tm_dq16, ostg, h * kHd + wg * 32, q0, b);
+              tma_reduce_add_3d(wrow + 32 <= kQH ? &tm_dq32 : &tm_dq16, ostg, h * kHD + hf * kHd + wg * 32, q0, b);
               tma_store_commit();
             }
           }
@@ -347,7 +383,7 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && prow0 < N) {
-            tma_store_3d(&tm_out32, ostg, ((wg == 0 ? 2 : 1) * H + h) * kHd, prow0, b);
+            tma_store_3d(&tm_out32, ostg, ((wg == 0 ? 2 : 1) * H + h) * kHD + hf * kHd, prow0, b);
             tma_store_commit();
           }
           ++gk;
@@ -356,7 +392,8 @@ attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_kv, const __grid_con
       // keys beyond kv_len (padding keys of a NaFlex batch) never entered a tile: their dK / dV are zero
       for (int key = nkt * kKT + tid; key < N; key += kComputeThreads) {
         for (int which = 1; which <= 2; ++which) {
-          uint4* dst = reinterpret_cast<uint4*>(p.dqkv + (static_cast<long long>(b) * N + key) * tok_stride + (which * H + h) * kHd);
+          uint4* dst = reinterpret_cast<uint4*>(p.dqkv + (static_cast<long long>(b) * N + key) * tok_stride + (which * H + h) * kHD +
+                                                hf * kHd);
 #pragma unroll
           for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -388,11 +425,13 @@ attn_dq_convert_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict
   }
 }
 
-// dq32: fp32 workspace [B, N, H*64] (zeroed here).  Returns B200_ERR_UNSUPPORTED for N > 1120.
+// dq32: fp32 workspace [B, N, H*hd] (zeroed here); hd = 64 or 128.  Returns B200_ERR_UNSUPPORTED for N > 2240 (1120 at hd 128).
 int launch_attn_bwd_long(const void* qkv, const void* dout, const float* lse, const float* delta, float* dq32, void* dqkv,
-                         const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, float scale, cudaStream_t st) {
-  if (N > kMaxChunks * kQH) return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: N=%d tokens not supported (<= %d)", N, kMaxChunks * kQH);
-  const long long HD = static_cast<long long>(H) * kHd;
+                         const int32_t* kv_len, const AttnBias* bias, int B, int N, int H, int hd, float scale, cudaStream_t st) {
+  const int NH = hd / kHd;
+  const int max_n = (NH == 1 ? BwdLongSmem<1>::kMaxChunks : BwdLongSmem<2>::kMaxChunks) * kQH;
+  if (N > max_n) return fail(B200_ERR_UNSUPPORTED, "b200_attn_bwd: N=%d tokens not supported (<= %d at head_dim %d)", N, max_n, hd);
+  const long long HD = static_cast<long long>(H) * hd;
   B200_CUDA_OK(cudaMemsetAsync(dq32, 0, static_cast<size_t>(B) * N * HD * sizeof(float), st));
   CUtensorMap tkv, tq, tdo, to32, tdq32, tdq16;
   {
@@ -426,14 +465,19 @@ int launch_attn_bwd_long(const void* qkv, const void* dout, const float* lse, co
   p.bias = bias != nullptr ? *bias : AttnBias{nullptr, 0, 0, 0};
   p.inv_scale = 1.0f / scale;
   auto kern = p.bias.ptr != nullptr ? attn_bwd_long_kernel<true> : attn_bwd_long_kernel<false>;
+  int smem_bytes = BwdLongSmem<1>::kSmemTotal;
+  if (NH == 2) {
+    kern = p.bias.ptr != nullptr ? attn_bwd_long_kernel<true, 2> : attn_bwd_long_kernel<false, 2>;
+    smem_bytes = BwdLongSmem<2>::kSmemTotal;
+  }
   static decltype(kern) attr_set_for = nullptr;
   if (attr_set_for != kern) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set_for = kern;
   }
   int grid = sm_count();
-  if (grid > B * H) grid = B * H;
-  kern<<<grid, kComputeThreads + 32, kSmemTotal, st>>>(tkv, tq, tdo, to32, tdq32, tdq16, p);
+  if (grid > B * H * NH) grid = B * H * NH;
+  kern<<<grid, kComputeThreads + 32, smem_bytes, st>>>(tkv, tq, tdo, to32, tdq32, tdq16, p);
   B200_CUDA_OK(cudaGetLastError());
   const long long rows = static_cast<long long>(B) * N;
   long long blocks = (rows * (HD / 8) + 255) / 256;

@@ -363,7 +363,7 @@ namespace b200 {
 int launch_attn_fwd2(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int B, int N, int H,
                      float scale, cudaStream_t st);
 int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int B, int N, int H,
-                         float scale, cudaStream_t st);
+                         int hd, float scale, cudaStream_t st);
 }
 
 using namespace b200;
@@ -373,16 +373,19 @@ static int attn_fwd_dispatch(const void* qkv, void* out, float* lse, const int32
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   B200_CHECK_ARG(qkv && out, "b200_attn_fwd: null qkv/out");
   B200_CHECK_ARG(B > 0 && N > 0 && H > 0, "b200_attn_fwd: bad shape B=%d N=%d H=%d", B, N, H);
-  if (hd != kHd) return fail(B200_ERR_UNSUPPORTED, "b200_attn_fwd: head_dim %d not supported (64 only)", hd);
+  if (hd != kHd && hd != 2 * kHd)
+    return fail(B200_ERR_UNSUPPORTED, "b200_attn_fwd: head_dim %d not supported (64 or 128; other widths are zero-padded by the caller)", hd);
   B200_CHECK_ARG(B <= 65535 && H <= 65535, "b200_attn_fwd: B/H exceed the grid limits");
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "b200_attn_fwd: qkv/out must be 16-byte aligned");
   // N <= 208 (ViT @224/16): the persistent, P-in-TMEM kernel of attention_fwd2.cu; B200_ATTN_FWD_V1=1 keeps the
   // one-CTA-per-tile kernels of this file selectable for A/B comparison (they remain the path for 208 < N <= 256).
   static const bool use_v1 = [] { const char* e = getenv("B200_ATTN_FWD_V1"); return e != nullptr && e[0] == '1'; }();
+  // 128-wide heads: the online-softmax kernel of attention_fwd_long.cu with two 64-wide halves per operand, at any N
+  if (hd == 2 * kHd) return launch_attn_fwd_long(qkv, out, lse, kv_len, bias, B, N, H, hd, scale, st);
   if (bias != nullptr) {     // additive bias: the two production kernels only
     if (N <= 208) return launch_attn_fwd2(qkv, out, lse, kv_len, bias, B, N, H, scale, st);
-    return launch_attn_fwd_long(qkv, out, lse, kv_len, bias, B, N, H, scale, st);
+    return launch_attn_fwd_long(qkv, out, lse, kv_len, bias, B, N, H, kHd, scale, st);
   }
   if (!use_v1 && N <= 208) return launch_attn_fwd2(qkv, out, lse, kv_len, nullptr, B, N, H, scale, st);
   static const bool ptmem = [] { const char* e = getenv("B200_ATTN_PTMEM"); return e != nullptr && e[0] == '1'; }();
@@ -390,7 +393,7 @@ static int attn_fwd_dispatch(const void* qkv, void* out, float* lse, const int32
   if (N <= 208) return launch_attn_fwd<208, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
   if (N <= 256) return launch_attn_fwd<256, true, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
   // longer sequences: the double-buffered online-softmax kernel of attention_fwd_long.cu
-  if (!use_v1) return launch_attn_fwd_long(qkv, out, lse, kv_len, nullptr, B, N, H, scale, st);
+  if (!use_v1) return launch_attn_fwd_long(qkv, out, lse, kv_len, nullptr, B, N, H, kHd, scale, st);
   return launch_attn_fwd<128, false, false>(qkv, out, lse, kv_len, B, N, H, scale, st);
 }
 

@@ -1,4 +1,8 @@
-// Attention forward for long sequences (N > 256 tokens: ViT-L/14 @336 = 577, NaFlex batches), head_dim 64.
+// Attention forward for long sequences (N > 256 tokens: ViT-L/14 @336 = 577, NaFlex batches), head_dim 64, and for
+// head_dim 128 at any N (NH = 2: ViT-H 80 / SO400M 72 / 96-wide heads arrive zero-padded to 128 through the weights, see
+// functional.head_pad).  A 128-wide head is handled as two 64-wide halves so that every operand sub-tile stays one
+// 128-byte swizzle atom per token row: S = Q0 K0^T + Q1 K1^T (8 instead of 4 k-steps into the same accumulator),
+// O = [P V0 | P V1] (two N = 64 MMAs into neighbouring TMEM columns); one CTA per SM (192 KB of shared memory).
 // One CTA (128 threads = 128 query rows) per (query tile, head, image), two CTAs per SM; online softmax over
 // 128-key blocks (flash-attention recurrence), same operand / result layout as attention_fwd.cu.  Differences to the
 // single-buffer kernel it replaces on this path:
@@ -24,13 +28,17 @@ constexpr int kKB = 128;                    // keys per block
 constexpr int kQBytes = kQT * kHd * 2;      // 16384
 constexpr int kKBytes = kKB * kHd * 2;      // 16384
 constexpr int kPBytes = (kKB / 8) * (kQT * 16);   // 32768: P as bf16 K-major core matrices
-constexpr int kOffQ = 0;
-constexpr int kOffK = kQBytes;              // two K buffers
-constexpr int kOffV = kOffK + 2 * kKBytes;  // two V buffers
-constexpr int kOffP = kOffV + 2 * kKBytes;
-constexpr int kOffBar = kOffP + kPBytes;
-constexpr int kSmem = kOffBar + 64;         // 114752: two CTAs per SM need 2 x (kSmem + 1 KB reserved) <= 228 KB, so the
-                                            // buffer is declared 1024-byte aligned instead of carrying alignment slack
+// shared-memory layout for NH 64-wide halves of the head: Q (NH sub-tiles), two K buffers, two V buffers (NH sub-tiles each), P
+template <int NH>
+struct FwdLongSmem {
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffK = NH * kQBytes;
+  static constexpr int kOffV = kOffK + 2 * NH * kKBytes;
+  static constexpr int kOffP = kOffV + 2 * NH * kKBytes;
+  static constexpr int kOffBar = kOffP + kPBytes;
+  static constexpr int kSmem = kOffBar + 64;  // NH = 1: 114752 -- two CTAs per SM need 2 x (kSmem + 1 KB reserved) <= 228 KB, so
+                                              // the buffer is declared 1024-byte aligned instead of carrying alignment slack
+};
 }  // namespace
 
 struct AttnLongParams {
@@ -62,11 +70,14 @@ __device__ __forceinline__ void exp2_poly_pair_l(f32x2 tt, float& e0, float& e1)
 // BIAS = true: an additive fp32 bias (causal triangle / general attn_mask, attention.py:21-40) is added to every score tile
 // in TMEM before the online-softmax passes read it; a key block that is entirely -inf for a row leaves the row's running
 // statistics untouched (P = 0, rescale factor from the old maximum).
-template <uint32_t kPolyMask, bool BIAS = false>
-__global__ void __launch_bounds__(128, 2)
+template <uint32_t kPolyMask, bool BIAS = false, int NH = 1>
+__global__ void __launch_bounds__(128, 3 - NH)
 attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                      const __grid_constant__ CUtensorMap tm_out, const AttnLongParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  using L = FwdLongSmem<NH>;
+  constexpr int kOffQ = L::kOffQ, kOffK = L::kOffK, kOffV = L::kOffV, kOffP = L::kOffP, kOffBar = L::kOffBar;
+  constexpr int kHD = NH * kHd;               // the (padded) head width
   uint8_t* sQ = smem + kOffQ;
   uint8_t* sP = smem + kOffP;
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -82,7 +93,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (p.kv_len != nullptr) kvlen = max(1, min(p.kv_len[b], N));
   const int nblk = (kvlen + kKB - 1) / kKB;
   const int row_in_img = qt * kQT + tid;
-  const int col_q = h * kHd, col_k = (H + h) * kHd, col_v = (2 * H + h) * kHd;
+  const int col_q = h * kHD, col_k = (H + h) * kHD, col_v = (2 * H + h) * kHD;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_q);
@@ -105,17 +116,21 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  constexpr int kOCol = 128;        // S in columns [0,128), the block's O in [128,192)
+  constexpr int kOCol = 128;        // S in columns [0,128), the block's O in [128, 128 + 64 NH)
 
   auto load_kv = [&](int blk) {
     const int buf = blk & 1;
-    mbar_arrive_expect_tx(&bar_kv[buf], 2 * kKBytes);
-    tma_load_2d(smem + kOffK + buf * kKBytes, &tm_kv, &bar_kv[buf], col_k, b * N + blk * kKB);
-    tma_load_2d(smem + kOffV + buf * kKBytes, &tm_kv, &bar_kv[buf], col_v, b * N + blk * kKB);
+    mbar_arrive_expect_tx(&bar_kv[buf], 2 * NH * kKBytes);
+#pragma unroll
+    for (int i = 0; i < NH; ++i) {
+      tma_load_2d(smem + kOffK + (buf * NH + i) * kKBytes, &tm_kv, &bar_kv[buf], col_k + i * kHd, b * N + blk * kKB);
+      tma_load_2d(smem + kOffV + (buf * NH + i) * kKBytes, &tm_kv, &bar_kv[buf], col_v + i * kHd, b * N + blk * kKB);
+    }
   };
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, kQBytes);
-    tma_load_2d(sQ, &tm_q, bar_q, col_q, b * N + qt * kQT);
+    mbar_arrive_expect_tx(bar_q, NH * kQBytes);
+#pragma unroll
+    for (int i = 0; i < NH; ++i) tma_load_2d(sQ + i * kQBytes, &tm_q, bar_q, col_q + i * kHd, b * N + qt * kQT);
     load_kv(0);
     if (nblk > 1) load_kv(1);
   }
@@ -123,9 +138,9 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   constexpr uint32_t idesc_s = make_idesc_bf16(kQT, kKB, false, false);
   constexpr uint32_t idesc_o = make_idesc_bf16(kQT, kHd, false, true);
   float m_run = -INFINITY, l_run = 0.f;
-  f32x2 acc[kHd / 2];
+  f32x2 acc[kHD / 2];
 #pragma unroll
-  for (int i = 0; i < kHd / 2; ++i) acc[i] = 0ull;
+  for (int i = 0; i < kHD / 2; ++i) acc[i] = 0ull;
   const f32x2 sc2 = splat(p.scale_log2e);
   uint8_t* prow = sP + tid * 16;
 
@@ -205,10 +220,13 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       if (j == 0) mbar_wait(bar_q, 0);
       mbar_wait(&bar_kv[buf], (j >> 1) & 1);
       tc_fence_after();
-      const uint64_t qd = make_smem_desc(smem_u32(sQ), 16, 1024, kLayoutSw128);
-      const uint64_t kd = make_smem_desc(smem_u32(smem + kOffK + buf * kKBytes), 16, 1024, kLayoutSw128);
 #pragma unroll
-      for (int k = 0; k < kHd / 16; ++k) umma_ss(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+      for (int i = 0; i < NH; ++i) {
+        const uint64_t qd = make_smem_desc(smem_u32(sQ + i * kQBytes), 16, 1024, kLayoutSw128);
+        const uint64_t kd = make_smem_desc(smem_u32(smem + kOffK + (buf * NH + i) * kKBytes), 16, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k) umma_ss(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, (i > 0 || k > 0) ? 1u : 0u);
+      }
       umma_commit(bar_s);
     }
     __syncwarp();
@@ -233,11 +251,14 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // P: K-major, no swizzle: core matrices 8 rows x 16 B, row groups 128 B apart (SBO), the two 8-key chunks of a
       //    K=16 step 2048 B apart (LBO).   V: MN-major SW128, 16 keys = 2048 B.
       const uint64_t pd = make_smem_desc(smem_u32(sP), kQT * 16, 128, kLayoutNone);
-      const uint64_t vd = make_smem_desc(smem_u32(smem + kOffV + buf * kKBytes), 1024, 1024, kLayoutSw128);
 #pragma unroll
-      for (int k = 0; k < kKB / 16; ++k)
-        umma_ss(tmem_base + kOCol, pd + static_cast<uint64_t>(k * ((2 * kQT * 16) >> 4)),
-                vd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o, k > 0 ? 1u : 0u);
+      for (int i = 0; i < NH; ++i) {      // one N = 64 MMA chain per 64-wide half of V
+        const uint64_t vd = make_smem_desc(smem_u32(smem + kOffV + (buf * NH + i) * kKBytes), 1024, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < kKB / 16; ++k)
+          umma_ss(tmem_base + kOCol + i * kHd, pd + static_cast<uint64_t>(k * ((2 * kQT * 16) >> 4)),
+                  vd + static_cast<uint64_t>(k * (2048 >> 4)), idesc_o, k > 0 ? 1u : 0u);
+      }
       umma_commit(bar_o);
     }
     __syncwarp();
@@ -247,7 +268,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     if (tid == 0 && j + 2 < nblk) load_kv(j + 2);
     const f32x2 al2 = splat(alpha);
 #pragma unroll
-    for (int c = 0; c < kHd; c += 32) {
+    for (int c = 0; c < kHD; c += 32) {
       uint32_t r[32];
       tmem_ld_x32(tmem_row + kOCol + c, r);
       tmem_ld_wait_x32(r);
@@ -267,7 +288,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t srow = smem_u32(sQ) + tid * 128;
     const uint32_t sw = static_cast<uint32_t>(tid & 7);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 8 * NH; ++g) {     // half g / 8 of the head -> Q sub-tile g / 8
       uint32_t o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -275,13 +296,14 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         upk(mul2(acc[g * 4 + i], il2), lo, hi);
         o[i] = pack_bf16(lo, hi);
       }
-      const uint32_t addr = srow + ((static_cast<uint32_t>(g) ^ sw) << 4);
+      const uint32_t addr = srow + (g >> 3) * kQBytes + ((static_cast<uint32_t>(g & 7) ^ sw) << 4);
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && qt * kQT + warp * 32 < N) {
-      tma_store_3d(&tm_out, sQ + warp * (32 * 128), col_q, qt * kQT + warp * 32, b);
+#pragma unroll
+      for (int i = 0; i < NH; ++i) tma_store_3d(&tm_out, sQ + i * kQBytes + warp * (32 * 128), col_q + i * kHd, qt * kQT + warp * 32, b);
       tma_store_commit();
       tma_store_wait_read<0>();   // the staging rows have been read; the global writes complete on their own
     }
@@ -297,19 +319,20 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
 }
 
+// hd = 64 or 128 (the padded head width the qkv buffer carries)
 int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* kv_len, const AttnBias* bias, int B, int N, int H,
-                         float scale, cudaStream_t st) {
+                         int hd, float scale, cudaStream_t st) {
   CUtensorMap tq, tkv, tout;
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(3) * H * kHd, static_cast<uint64_t>(B) * N};
-    uint64_t strides[1] = {static_cast<uint64_t>(3) * H * kHd * 2};
+    uint64_t dims[2] = {static_cast<uint64_t>(3) * H * hd, static_cast<uint64_t>(B) * N};
+    uint64_t strides[1] = {static_cast<uint64_t>(3) * H * hd * 2};
     uint32_t box[2] = {kHd, kQT};
     int rc = encode_tmap_bf16(&tq, qkv, 2, dims, strides, box, true);
     if (rc) return rc;
     rc = encode_tmap_bf16(&tkv, qkv, 2, dims, strides, box, true);
     if (rc) return rc;
-    uint64_t odims[3] = {static_cast<uint64_t>(H) * kHd, static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
-    uint64_t ostr[2] = {static_cast<uint64_t>(H) * kHd * 2, static_cast<uint64_t>(N) * H * kHd * 2};
+    uint64_t odims[3] = {static_cast<uint64_t>(H) * hd, static_cast<uint64_t>(N), static_cast<uint64_t>(B)};
+    uint64_t ostr[2] = {static_cast<uint64_t>(H) * hd * 2, static_cast<uint64_t>(N) * H * hd * 2};
     uint32_t obox[3] = {kHd, 32, 1};
     rc = encode_tmap_bf16(&tout, out, 3, odims, ostr, obox, 128);
     if (rc) return rc;
@@ -322,13 +345,18 @@ int launch_attn_fwd_long(const void* qkv, void* out, float* lse, const int32_t* 
   p.inv_scale = 1.0f / scale;
   auto kern = poly == 6 ? attn_fwd_long_kernel<0x2525u> : (poly == 4 ? attn_fwd_long_kernel<0x1111u> : attn_fwd_long_kernel<0u>);
   if (p.bias.ptr != nullptr) kern = attn_fwd_long_kernel<0u, true>;
+  int smem_bytes = FwdLongSmem<1>::kSmem;
+  if (hd == 2 * kHd) {
+    kern = p.bias.ptr != nullptr ? attn_fwd_long_kernel<0u, true, 2> : attn_fwd_long_kernel<0u, false, 2>;
+    smem_bytes = FwdLongSmem<2>::kSmem;
+  }
   static decltype(kern) attr_set_for = nullptr;
   if (attr_set_for != kern) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set_for = kern;
   }
   dim3 grid((N + kQT - 1) / kQT, H, B);
-  kern<<<grid, 128, kSmem, st>>>(tq, tkv, tout, p);
+  kern<<<grid, 128, smem_bytes, st>>>(tq, tkv, tout, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

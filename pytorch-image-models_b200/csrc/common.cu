@@ -143,7 +143,7 @@ bool pdl_enabled() {
 }
 }  // namespace b200
 
-extern "C" int b200_abi_version(void) { return 7; }
+extern "C" int b200_abi_version(void) { return 8; }
 
 extern "C" int b200_device_check(void) {
   int dev = 0;

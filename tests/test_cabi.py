@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string_without_gpu():
     lib = _lib.load()
-    assert lib.b200_abi_version() == 7
+    assert lib.b200_abi_version() == 8
     assert isinstance(lib.b200_last_error(), bytes)
 
 

@@ -49,7 +49,11 @@ def test_models_take_uint8_batches_from_the_prefetch_loader():
             assert torch.equal(tgt.cpu(), ref_tgt)
             x = _reference_normalise(img).to(torch.bfloat16)
             with torch.no_grad():
-                assert torch.equal(vit(img), vit(x))
+                # the patch values are bit-identical (test above); the bf16 image takes the im2col-free projection (K runs in
+                # the tensor map's order), the uint8 image the gather + GEMM: fp32 sums in a different order, bf16 logits
+                # within a few ulps
+                a, b = vit(img).float(), vit(x).float()
+                assert (a - b).abs().max().item() <= 4e-3 + 1.6e-2 * b.abs().max().item()
                 assert torch.equal(cnx(img), cnx(x))
             seen += 1
         assert seen == 3

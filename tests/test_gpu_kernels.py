@@ -223,7 +223,8 @@ def test_assemble_tokens_and_colsum():
 
 # ------------------------------------------------------------------------------------------------ backward kernels
 @pytest.mark.parametrize("B,N,H", [(2, 197, 12), (3, 64, 2), (2, 208, 3), (2, 129, 2), (1, 17, 1),
-                                   (2, 577, 4), (1, 300, 2), (3, 224, 1), (1, 1025, 1)])   # N > 208: attention_bwd_long.cu
+                                   (2, 577, 4), (1, 300, 2), (3, 224, 1), (1, 1025, 1),    # N > 208: attention_bwd_long.cu
+                                   (1, 1370, 2), (1, 2240, 1)])                            # DINOv2 @518; the kernel's limit
 def test_attention_bwd(B, N, H):
     """dq/dk/dv against PyTorch autograd of the fp32 restatement of attention.py:115-135."""
     ops = _ops()

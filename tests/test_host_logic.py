@@ -191,14 +191,15 @@ def test_loss_and_ema_mirrors_host_logic():
     assert e32.module.weight.dtype == torch.float32
 
 
-def test_head_padding_in_the_weights_is_exact():
-    """head_dim < 64 runs on the head_dim-64 kernels through zero padding that lives in the weights
+@pytest.mark.parametrize("D,H,hd,P", [(96, 3, 32, 64), (160, 2, 80, 128), (144, 2, 72, 128), (192, 2, 96, 128)])
+def test_head_padding_in_the_weights_is_exact(D, H, hd, P):
+    """head_dim other than 64 / 128 runs on the 64- / 128-wide kernels through zero padding that lives in the weights
     (functional._pad_rows / _pad_cols): attention computed on the padded projections with the module's own scale equals
     the narrow-head attention exactly (the padding columns of q / k add 0 to every score, the padded v columns meet zero
     columns of the output projection).  Checked here with plain torch math (the algebra, not the kernels)."""
     from b200timm import functional as BF
     torch.manual_seed(0)
-    B, N, D, H, hd = 2, 7, 96, 3, 32
+    B, N = 2, 7
     attn = Attention(D, num_heads=H, qkv_bias=True)
     x = torch.randn(B, N, D)
 
@@ -212,15 +213,16 @@ def test_head_padding_in_the_weights_is_exact():
     wq = BF._pad_rows(attn.qkv.weight, 3, H, hd)
     bq = BF._pad_rows(attn.qkv.bias, 3, H, hd)
     wp = BF._pad_cols(attn.proj.weight, H, hd)
-    assert wq.shape == (3 * H * 64, D) and bq.shape == (3 * H * 64,) and wp.shape == (D, H * 64)
-    got = torch.nn.functional.linear(sdpa(torch.nn.functional.linear(x, wq, bq), H, 64, attn.scale), wp, attn.proj.bias)
+    assert wq.shape == (3 * H * P, D) and bq.shape == (3 * H * P,) and wp.shape == (D, H * P)
+    got = torch.nn.functional.linear(sdpa(torch.nn.functional.linear(x, wq, bq), H, P, attn.scale), wp, attn.proj.bias)
     torch.testing.assert_close(got, ref, atol=1e-6, rtol=1e-6)
     # gradients reach the real parameters through the padding (training builds the padded operands differentiably)
     got.sum().backward()
     assert attn.qkv.weight.grad is not None and attn.proj.weight.grad is not None and attn.qkv.bias.grad is not None
-    assert BF.head_pad(32) == 64 and BF.head_pad(64) == 64
-    with pytest.raises(B200Error):
-        BF.head_pad(80)
+    assert BF.head_pad(32) == 64 and BF.head_pad(64) == 64 and BF.head_pad(80) == 128 and BF.head_pad(128) == 128
+    for bad in (136, 36, 0):
+        with pytest.raises(B200Error):
+            BF.head_pad(bad)
 
 
 def test_attn_mask_operand_classifies_masks():
