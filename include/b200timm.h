@@ -48,7 +48,7 @@ extern "C" {
                                  `rot` layout, head_dim 64, one [sin | cos] table shared by batch and heads)       */
 
 B200_API const char* b200_last_error(void);
-/* 8 now (7 -> 8: head_dim 128 in b200_attn_fwd / b200_attn_bwd and their _bias variants, b200_attn_bwd_ws_floats_hd); 6 -> 7: b200_attn_fwd_bias / b200_attn_bwd_bias; 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
+/* 8 now (7 -> 8: head_dim 128 in b200_attn_fwd / b200_attn_bwd and their _bias variants, b200_attn_bwd_ws_floats_hd; b200_gemm_desc.ln_* and b200_gemm_ln_slots); 6 -> 7: b200_attn_fwd_bias / b200_attn_bwd_bias; 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
 B200_API int b200_abi_version(void);
 /* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
 B200_API int b200_device_check(void);
@@ -94,9 +94,28 @@ typedef struct b200_gemm_desc {
                        `out` are ADDED (red.global.add from the epilogue's staging tile) -- the bias gradient of the Linear
                        whose output gradient this GEMM produces (db1 = sum_rows dY1; the reference gets it from autograd of
                        F.linear, timm/layers/mlp.py:48).  The caller zero-initialises it.                             */
+  /* ABI >= 8 -- LayerNorm folded into the GEMMs either side of it (inference): `x = x + ls(f(..))` followed by `norm(x)` and the
+   * next Linear (timm/models/vision_transformer.py:212-213, timm/layers/norm.py:85-90) without a LayerNorm pass over HBM.
+   * The statistics buffer is fp32 [S + 1][M][2] with S = b200_gemm_ln_slots(M, N) of the PRODUCER's output shape.
+   * Producer (EPI_BIAS / EPI_BIAS_RESIDUAL, one bf16 output): ln_stats_out receives in slots 0 .. S-1, per row and slot (a
+   * slot = the columns one epilogue warp stores), the sum and the sum of squares of the bf16 values written to `out`.
+   * Consumer (EPI_BIAS / EPI_BIAS_GELU, bf16 output, a_mn = 0): `a` is the UN-normalised activation, `b` = weight * ln_weight
+   * (column-wise, rounded to bf16), ln_stats the producer's buffer and ln_slots = S, ln_eps the norm's eps, ln_c1 = fp32 [N]
+   * row sums of `b`, `bias` = fp32 [N] ln_bias . weight^T + the Linear's bias; the call first reduces the slots to
+   * (rstd, -mean * rstd) per row in slot S of the buffer (mean / var over the K columns of the row, var = E[x^2] - mean^2 in
+   * fp32 -- the one place the buffer is written through ln_stats), then the GEMM's epilogue evaluates
+   * rstd * (acc - mean * ln_c1[n]) + bias[n].                                                                              */
+  float* ln_stats_out;
+  float* ln_stats;
+  const float* ln_c1;
+  int32_t ln_slots;
+  float ln_eps;
 } b200_gemm_desc;
 
 B200_API int b200_gemm(const b200_gemm_desc* desc, void* stream);
+/* Number S of partial-statistic slots a b200_gemm launch with ln_stats_out writes for an [M, N] output (ABI >= 8); the
+ * buffer holds S + 1 slots (see b200_gemm_desc.ln_stats). */
+B200_API int32_t b200_gemm_ln_slots(int32_t M, int32_t N);
 
 /* In-place rotary embedding of the q and k thirds of a fused QKV activation qkv[B*N, 3*H*64] (bf16); replaces
  * apply_rot_embed_cat at timm/layers/attention.py:249-253 (pos_embed_sincos.py:227-297).  emb: fp32 [N - num_prefix, 128]

@@ -57,6 +57,11 @@ class GemmDesc(ctypes.Structure):
         ("rope_cols", ctypes.c_int32),
         ("act", ctypes.c_int32),
         ("colsum", ctypes.c_void_p),
+        ("ln_stats_out", ctypes.c_void_p),
+        ("ln_stats", ctypes.c_void_p),
+        ("ln_c1", ctypes.c_void_p),
+        ("ln_slots", ctypes.c_int32),
+        ("ln_eps", ctypes.c_float),
     ]
 
 
@@ -77,6 +82,7 @@ SIGNATURES = {
     "b200_abi_version": (ctypes.c_int, []),
     "b200_device_check": (ctypes.c_int, []),
     "b200_gemm": (ctypes.c_int, [ctypes.POINTER(GemmDesc), _vp]),
+    "b200_gemm_ln_slots": (ctypes.c_int32, [_i32, _i32]),
     "b200_set_trace": (None, [_i32, _vp]),
     "b200_rope_qk": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_layernorm_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),

@@ -5,13 +5,17 @@ The functions are duck-typed on timm's own attribute names (``blk.norm1``, ``blk
 b200timm.vision_transformer and -- through b200timm.plugin -- timm's unmodified classes.
 
 Fusion map per transformer block (reference: timm/models/vision_transformer.py:206-214):
-    LN1            -> layernorm kernel                              (norm.py:85-90)
+    LN1            -> folded into the qkv GEMM (below); a layernorm kernel for the first block  (norm.py:85-90)
     qkv            -> GEMM + bias epilogue                          (attention.py:115)
     sdpa           -> tcgen05 attention, reads qkv in place         (attention.py:115-135)
     proj + ls1 + residual -> GEMM epilogue  x + gamma*(acc+b)       (attention.py:137, layer_scale.py:27, :212)
-    LN2            -> layernorm kernel
+    LN2            -> folded into the fc1 GEMM
     fc1 + GELU     -> GEMM epilogue                                 (mlp.py:48-49)
     fc2 + ls2 + residual -> GEMM epilogue                           (mlp.py:52, :213)
+Folded LayerNorm (inference; B200_LN_FOLD=0 switches it off): the residual GEMM that produces x also emits per-row partial
+sums (sum x, sum x^2 of the bf16 values it stores); the Linear that follows norm(x) runs on x itself against the weight
+pre-multiplied by the norm's gamma, and its epilogue finishes LN(x) W^T + b = rstd * (x W'^T - mean * rowsum(W')) + (W beta + b).
+No LayerNorm pass over HBM remains between the blocks (b200_gemm_desc.ln_*).
 Anything the kernels do not cover (qk-norm, attention dropout, non-GELU activations, head_dim != 64, ...)
 raises B200Error: there is no PyTorch fallback on this path.
 """
@@ -45,6 +49,55 @@ def _ln_params(norm):
     if not isinstance(norm, nn.LayerNorm):
         raise B200Error(f"unsupported norm layer {type(norm).__name__} (LayerNorm / RmsNorm only)")
     return norm.weight, norm.bias, norm.eps
+
+
+# ------------------------------------------------------------------------------------------------ folded LayerNorm
+import os as _os
+
+_LN_FOLD = _os.environ.get("B200_LN_FOLD", "1")[:1] != "0"
+
+
+def _ln_fold(norm, linear, w, b, tag):
+    """Operands of `linear(norm(x))` evaluated on x itself (b200_gemm_desc.ln_*): (W * gamma as bf16 [N, K], c1 = row sums of
+    that operand fp32 [N], c2 = W beta + b fp32 [N], eps), cached on the Linear and rebuilt when any of the four parameters
+    changes; None when the pair is not foldable (RmsNorm / no affine / narrow output).  w, b: the GEMM operands the unfused
+    path would use (bf16 cast / head-padded views of linear.weight / linear.bias)."""
+    if not _LN_FOLD or type(norm) is not nn.LayerNorm and type(norm).__name__ != "LayerNorm":
+        return None
+    g, beta = norm.weight, norm.bias
+    if g is None or beta is None or w.shape[0] <= 128:
+        return None
+    key = (ops.wkey(linear.weight), None if linear.bias is None else ops.wkey(linear.bias), ops.wkey(g), ops.wkey(beta),
+           tuple(w.shape))
+
+    def build():
+        wf = w.detach().float()
+        wg = (wf * g.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        c2 = wf @ beta.detach().float()
+        if b is not None:
+            c2 = c2 + b.detach().float()
+        return wg, wg.float().sum(1).contiguous(), c2.contiguous()
+    return (*_cached(linear, "_b200_lnfold_" + tag, key, build), float(norm.eps))
+
+
+def _tver(t):
+    """Version counter of a tensor; inference-mode tensors have none (reading `_version` raises on them)."""
+    return -1 if t.is_inference() else t._version
+
+
+def _tag_ln_stats(out, stats):
+    """Remember the row statistics the producing GEMM left for `out` ON the tensor object; the next block's forward picks
+    them up when it receives this very object unmodified (the model's `for blk in blocks` / nn.Sequential loop)."""
+    if stats is not None:
+        out._b200_ln_stats = (stats, out.data_ptr(), _tver(out), tuple(out.shape))
+    return out
+
+
+def _take_ln_stats(x):
+    t = getattr(x, "_b200_ln_stats", None)
+    if t is None or t[1] != x.data_ptr() or t[2] != _tver(x) or t[3] != tuple(x.shape) or not x.is_contiguous():
+        return None
+    return t[0]
 
 
 def _gamma(ls):
@@ -637,21 +690,35 @@ def block_forward(blk, x, kv_len=None):
                              _w(mlp.fc1), mlp.fc1.bias, _w(mlp.fc2), mlp.fc2.bias, _gamma(blk.ls1), _gamma(blk.ls2),
                              rs1, rs2, kv_len, attn.num_heads, attn.scale, e1, e2, mlp_act(mlp))
     rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)   # None in eval mode
+    M = B * N
+    fold = _LN_FOLD and M >= 256 and D > 128       # the shapes the folded-LayerNorm GEMM instantiations serve
+    st_in = _take_ln_stats(x) if fold else None     # left by the GEMM that produced x (the previous block's fc2)
     x2 = _bf16_2d(x, D)
-    w1, b1, eps1 = _ln_params(blk.norm1)
-    h = ops.layernorm_fwd(x2, w1, b1, eps1)[0]
     wqkv, bqkv = head_padded_linear_in(attn.qkv, 3, attn.num_heads, attn.head_dim)
-    qkv = ops.linear_fwd(h, wqkv, bqkv)
+    f1 = _ln_fold(blk.norm1, attn.qkv, wqkv, bqkv, "qkv") if st_in is not None else None
+    if f1 is not None:
+        qkv = ops.linear_fwd(x2, f1[0], f1[2], ln_in=(st_in, f1[1], f1[3]))
+    else:
+        w1, b1, eps1 = _ln_params(blk.norm1)
+        qkv = ops.linear_fwd(ops.layernorm_fwd(x2, w1, b1, eps1)[0], wqkv, bqkv)
     o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, head_pad(attn.head_dim), attn.scale, kv_len)
+    act = mlp_act(mlp)
+    f2 = _ln_fold(blk.norm2, mlp.fc1, _w(mlp.fc1), mlp.fc1.bias, "fc1") if fold and act == 0 else None
+    st2 = ops.ln_stats_buffer(M, D, x.device) if f2 is not None else None
     x2 = ops.linear_fwd(o.view(B * N, -1), head_padded_linear_out(attn.proj, attn.num_heads, attn.head_dim), attn.proj.bias,
                         epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
-                        gamma=_gamma(blk.ls1), row_scale=rs1, rows_per_scale=N)
-    w2, b2, eps2 = _ln_params(blk.norm2)
-    h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
-    h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(mlp))
+                        gamma=_gamma(blk.ls1), row_scale=rs1, rows_per_scale=N, ln_stats_out=st2)
+    if f2 is not None:
+        h = ops.linear_fwd(x2, f2[0], f2[2], epilogue=ops.EPI_BIAS_GELU, ln_in=(st2, f2[1], f2[3]))
+    else:
+        w2, b2, eps2 = _ln_params(blk.norm2)
+        h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
+        h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=act)
+    # the statistics of the block's output ride along for the next block's norm1 (a plain LayerNorm follows in every ViT)
+    st3 = ops.ln_stats_buffer(M, D, x.device) if fold else None
     x2 = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=_gamma(blk.ls2),
-                        row_scale=rs2, rows_per_scale=N)
-    return x2.view(B, N, D)
+                        row_scale=rs2, rows_per_scale=N, ln_stats_out=st3)
+    return _tag_ln_stats(x2.view(B, N, D), st3)
 
 
 def patch_embed_forward(pe, img):

@@ -204,10 +204,13 @@ ACTS = {"gelu": 0, "gelu_tanh": 1, "silu": 2}     # b200_gemm_desc.act: the acti
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None, aux=None, gamma=None, out=None,
          out_dtype=torch.bfloat16, accumulate=False, split_k=1, out2=None, row_scale=None, rows_per_scale=0, rope=None,
-         act=0, colsum=None):
+         act=0, colsum=None, ln_stats_out=None, ln_in=None):
     """out[M,N] = epilogue(sum_k A[m,k] B[n,k]).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True) bf16.
+    ln_stats_out: fp32 [ln_slots(M, N) + 1, M, 2] (ln_stats_buffer) that receives the row statistics of `out` (producer side of
+    a folded LayerNorm); ln_in = (that buffer, c1 fp32 [N], eps): consumer side -- `a` is the un-normalised activation, `b` the weight times
+    the norm's weight, `bias` the fp32 vector ln_bias . W^T + linear bias (b200_gemm_desc.ln_*).
     """
     _need_cuda(a, b, bias, aux, gamma, out, out2)
     _check_2d_bf16(a, "a")
@@ -258,6 +261,20 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
         if colsum.dtype != torch.float32 or colsum.numel() != N or not colsum.is_contiguous() or not colsum.is_cuda:
             raise B200Error("gemm: colsum must be a contiguous fp32 CUDA tensor [N]")
         d.colsum = colsum.data_ptr()
+    if ln_stats_out is not None:
+        if (ln_stats_out.dtype != torch.float32 or not ln_stats_out.is_contiguous() or not ln_stats_out.is_cuda
+                or tuple(ln_stats_out.shape) != (ln_slots(M, N) + 1, M, 2)):
+            raise B200Error("gemm: ln_stats_out must be a contiguous fp32 CUDA tensor [ln_slots(M, N) + 1, M, 2]")
+        d.ln_stats_out = ln_stats_out.data_ptr()
+    if ln_in is not None:
+        st, c1, eps = ln_in
+        if (st.dtype != torch.float32 or not st.is_contiguous() or st.dim() != 3 or st.shape[0] < 2 or st.shape[1] != M or st.shape[2] != 2
+                or c1.dtype != torch.float32 or c1.numel() != N or not c1.is_contiguous()
+                or bias is None or bias.dtype != torch.float32):
+            raise B200Error("gemm: ln_in needs stats fp32 [slots + 1, M, 2], c1 fp32 [N] and an fp32 bias")
+        _need_cuda(st, c1)
+        d.ln_stats, d.ln_c1, d.ln_slots, d.ln_eps = st.data_ptr(), c1.data_ptr(), int(st.shape[0]) - 1, float(eps)
+        _count()           # the statistics finalisation launch
     if _gemm_timing is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -270,13 +287,23 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, epilogue=EPI_BIAS, bias=None,
     return out
 
 
+def ln_slots(M, N):
+    """Partial-statistic slots a gemm(..., ln_stats_out=...) launch writes for an [M, N] output."""
+    return int(_lib.load().b200_gemm_ln_slots(int(M), int(N)))
+
+
+def ln_stats_buffer(M, N, device):
+    """The statistics buffer of a folded LayerNorm over an [M, N] GEMM output: the producer's slots + the finalised slot."""
+    return torch.empty(ln_slots(M, N) + 1, M, 2, dtype=torch.float32, device=device)
+
+
 def linear_fwd(x2d, weight, bias=None, epilogue=EPI_BIAS, aux=None, gamma=None, out=None, out2=None, row_scale=None,
-               rows_per_scale=0, rope=None, act=0):
+               rows_per_scale=0, rope=None, act=0, ln_stats_out=None, ln_in=None):
     """F.linear on a [M,K] bf16 activation with a fused epilogue (weight: [N,K] bf16)."""
     M, K = x2d.shape
     N = weight.shape[0]
     return gemm(x2d, weight, M, N, K, epilogue=epilogue, bias=bias, aux=aux, gamma=gamma, out=out, out2=out2,
-                row_scale=row_scale, rows_per_scale=rows_per_scale, rope=rope, act=act)
+                row_scale=row_scale, rows_per_scale=rows_per_scale, rope=rope, act=act, ln_stats_out=ln_stats_out, ln_in=ln_in)
 
 
 def _check_rope(emb, tokens, prefix, batch=None):

@@ -61,6 +61,19 @@ struct GemmKernelParams {
   int patch, pe_ntiles, pe_pyc, pe_gw, pe_gh, pe_C, pe_kb_per_c, pe_ky_per_kb, pe_tile_rows, pe_row_off, pe_pos_off, pe_stage_tx, pe_lbo;
   float* colsum;               // optional fp32 [N]: += column sums of the bf16 output (the bias gradient of the Linear whose
                                // output gradient this GEMM produces), reduced from the staging tile, red.global.add
+  // LayerNorm folded into the GEMMs either side of it (inference; b200_gemm_desc.ln_*):
+  //   producer (ln_stats_out): every epilogue warp adds up, per accumulator row, the sum and the sum of squares of the bf16
+  //     values it stores (its BN/4 columns) and writes the pair to slot n_blk * 4 + part of a [slots][M][2] fp32 buffer --
+  //     one coalesced 8-byte store per lane and tile, no atomics, the same bits on every run;
+  //   consumer (ln_stats): A is the UN-normalised activation, B = weight * ln_gamma; ln_finalize_kernel first turns the slots
+  //     into one (rstd, -mean * rstd) pair per row (slot index ln_slots of the same buffer), the epilogue reads its row's pair
+  //     one tile ahead and out = rstd * (acc - mean * c1[n]) + c2[n] replaces the bias add
+  //     (c1[n] = sum_k B[n,k], c2[n] = sum_k ln_beta[k] W[n,k] + bias[n] arrive as ln_c1 and as the fp32 `bias`).
+  float* ln_stats_out;
+  const float* ln_stats;
+  const float* ln_c1;
+  int ln_slots;
+  float ln_eps, ln_inv_k;
   unsigned long long* trace;   // debug: 12 timestamps / wait totals per CTA (b200_set_trace), nullptr in production
 };
 
@@ -97,7 +110,9 @@ __device__ __forceinline__ void load8_param2(const void* base, int f32, int col,
 // without the per-chunk epilogue-type branches; EPI = -1 is the generic kernel that reads p.epilogue at run time.
 // ACTRT: the GELU / DGELU epilogues of the generic kernel read the activation kind from p.act (tanh GELU, SiLU); the
 // default instantiations (ACTRT = false) are the exact-GELU kernels with no trace of that switch.
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2, int RC, int EPI, bool ACTRT>
+// LNF: the folded-LayerNorm epilogues (GemmKernelParams::ln_*) exist only in the instantiations built with LNF = 1 (consumer)
+// or LNF = 2 (producer) -- K-major pair kernels of the inference forward -- so that every other kernel is untouched by them.
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2, int RC, int EPI, bool ACTRT, int LNF>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
@@ -327,10 +342,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool reduce_out = out_f32 && (p.accumulate || p.split_k > 1);
     const int round_cols = out_f32 ? RC / 2 : RC;     // output columns per staging tile
     const int sub_cols = out_f32 ? 16 : 32;           // output columns per 64-byte span (one tcgen05.ld)
+    constexpr bool ln_produce = LNF == 2 && EPI < 0;   // row statistics of the stored tile (see GemmKernelParams)
+    constexpr bool ln_consume = LNF == 1;
     uint32_t aux_phase = 0;
     int as = 0;
     uint32_t aphase = 0;
     unsigned long long first_acc = 0, last_acc = 0, ntiles = 0;
+    // folded LayerNorm, consumer side: (rstd, -mean * rstd) of this lane's row, fetched one tile ahead
+    const float2* ln_fin = ln_consume ? reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(p.ln_slots) * p.M : nullptr;
+    auto ln_row_of = [&](int t) {
+      const int m_unit_t = (t % tiles_mn) / p.num_n_blocks;
+      return (CTA2 ? 2 * m_unit_t + static_cast<int>(cta_rank) : m_unit_t) * BM + quad * 32 + lane;
+    };
+    float2 ln_next = make_float2(0.f, 0.f);
+    if (ln_consume && tile0 < num_tiles) {
+      const int r = ln_row_of(tile0);
+      if (r < p.M) ln_next = __ldg(ln_fin + r);
+    }
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int ks = tile / tiles_mn;
       const int mn = tile - ks * tiles_mn;
@@ -348,6 +376,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int tok = (row0 + lane) % p.rope_tokens - p.rope_prefix;
         if (tok >= 0) rope_row = p.rope + static_cast<long long>(tok) * 128;
       }
+      const f32x2 ln_rstd2 = splat(ln_next.x), ln_nmr2 = splat(ln_next.y);
+      if (ln_consume && tile + tile_step < num_tiles) {
+        const int r = ln_row_of(tile + tile_step);
+        ln_next = r < p.M ? __ldg(ln_fin + r) : make_float2(0.f, 0.f);
+      }
+      f32x2 ln_sum2 = splat(0.f), ln_sq2 = splat(0.f);
       bool waited = false;
 #pragma unroll 1
       for (int rc = 0; rc < kColsPerWarp; rc += round_cols) {
@@ -414,7 +448,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = pk(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
               if (col < p.N) {
-                if (p.bias != nullptr) {
+                if (ln_consume) {       // LayerNorm(x) W^T + b from x (W * gamma)^T: rstd * (acc - mean * c1) + c2
+                  f32x2 c1v[4], bv[4];
+                  load8_param2(p.ln_c1, 1, col, c1v);
+                  load8_param2(p.bias, 1, col, bv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) v[j] = fma2(v[j], ln_rstd2, fma2(c1v[j], ln_nmr2, bv[j]));
+                } else if (p.bias != nullptr) {
                   f32x2 bv[4];
                   load8_param2(p.bias, p.bias_f32, col, bv);
 #pragma unroll
@@ -467,6 +507,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 float lo, hi;
                 upk(v[j], lo, hi);
                 o[j] = pack_bf16(lo, hi);
+              }
+              if (ln_produce) {         // statistics of exactly the bf16 values the next LayerNorm would read
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const f32x2 xv = bf16x2_to_f32x2(o[j]);
+                  ln_sum2 = add2(ln_sum2, xv);
+                  ln_sq2 = fma2(xv, xv, ln_sq2);
+                }
               }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
                            : "memory");
@@ -572,6 +620,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tma_store_commit();
         }
       }
+      if (ln_produce && row0 + lane < p.M) {
+        float s0, s1, q0, q1;
+        upk(ln_sum2, s0, s1);
+        upk(ln_sq2, q0, q1);
+        reinterpret_cast<float2*>(p.ln_stats_out)[static_cast<long long>(n_blk * 4 + part) * p.M + row0 + lane] =
+            make_float2(s0 + s1, q0 + q1);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -587,9 +642,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (trace && threadIdx.x == 0) trace[6] = gtime();
 }
 
+// Folded LayerNorm: the producer's [slots][M][2] partial (sum, sum of squares) -> slot `slots`: (rstd, -mean * rstd) per row.
+__global__ void __launch_bounds__(256) ln_finalize_kernel(float2* __restrict__ stats, int M, int slots, float inv_k, float eps) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= M) return;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < slots; ++i) {
+    const float2 v = stats[static_cast<long long>(i) * M + r];
+    s += v.x;
+    q += v.y;
+  }
+  const float mean = s * inv_k;
+  const float rstd = rsqrtf(fmaxf(fmaf(q, inv_k, -mean * mean), 0.f) + eps);
+  stats[static_cast<long long>(slots) * M + r] = make_float2(rstd, -mean * rstd);
+}
+
 static unsigned long long* g_gemm_trace = nullptr;
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2 = false, int RC = 32, int EPI = -1, bool ACTRT = false>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool CTA2 = false, int RC = 32, int EPI = -1, bool ACTRT = false, int LNF = 0>
 static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, CTA2, RC>;
   static_assert(L::kTotal <= 227 * 1024, "shared memory budget");
@@ -656,10 +726,12 @@ static int launch_gemm(const b200_gemm_desc& d, cudaStream_t stream) {
   p.rope = d.rope; p.rope_tokens = d.rope_tokens; p.rope_prefix = d.rope_prefix; p.rope_cols = d.rope_cols;
   p.act = d.act;
   p.colsum = d.colsum;
+  p.ln_stats_out = d.ln_stats_out; p.ln_stats = d.ln_stats; p.ln_c1 = d.ln_c1; p.ln_slots = d.ln_slots; p.ln_eps = d.ln_eps;
+  p.ln_inv_k = 1.0f / static_cast<float>(d.K);
   p.patch = 0;
   p.trace = g_gemm_trace;
 
-  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI, ACTRT>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN, CTA2, RC, EPI, ACTRT, LNF>;
   static bool attr_set = false;  // idempotent; a benign race sets the same value twice
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -763,7 +835,7 @@ static int launch_patch_embed(const void* img, const void* weight, const void* b
   p.pe_kb_per_c = ps * ps / BK; p.pe_ky_per_kb = BK / ps; p.pe_tile_rows = tile_rows; p.pe_row_off = row_off;
   p.pe_pos_off = pos_off; p.pe_stage_tx = 2 * (tile_rows * BK * 2 + L::kBBytes); p.pe_lbo = tile_rows * 16;
   p.trace = nullptr;
-  auto kern = gemm_bf16_kernel<BN, STAGES, false, false, true, RC, -1, false>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, false, false, true, RC, -1, false, 0>;
   B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
   const int num_tiles = ((p.num_m_blocks + 1) / 2) * p.num_n_blocks;
   int clusters = (sm_count() & ~1) / 2;
@@ -800,6 +872,14 @@ extern "C" void b200_set_trace(int32_t kernel, void* device_buf) {
   if (kernel == 0) g_gemm_trace = reinterpret_cast<unsigned long long*>(device_buf);
   else if (kernel == 1) b200::g_attn_fwd_trace = reinterpret_cast<long long*>(device_buf);
   else if (kernel == 2) b200::g_attn_bwd_trace = reinterpret_cast<long long*>(device_buf);
+}
+
+// Slots of row statistics a b200_gemm launch with ln_stats_out writes for an [M, N] output: 4 per n-block of the tile width
+// the dispatcher below picks (256 columns when N > 128, else 128).
+extern "C" int32_t b200_gemm_ln_slots(int32_t M, int32_t N) {
+  (void)M;
+  const int bn = N > 128 ? 256 : 128;
+  return 4 * ((N + bn - 1) / bn);
 }
 
 extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
@@ -842,6 +922,16 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
                        (reinterpret_cast<uintptr_t>(d.colsum) & 7) == 0,
                    "b200_gemm: colsum rides in the EPI_DGELU epilogue of the 64-column-round kernels only (bf16 output, "
                    "M >= 256, N > 128, 8-byte aligned fp32 [N])");
+  if (d.ln_stats_out != nullptr)
+    B200_CHECK_ARG((d.epilogue == B200_EPI_BIAS || d.epilogue == B200_EPI_BIAS_RESIDUAL) && d.out_dtype == B200_DTYPE_BF16 &&
+                       d.out2 == nullptr && d.split_k <= 1 && (reinterpret_cast<uintptr_t>(d.ln_stats_out) & 7) == 0,
+                   "b200_gemm: ln_stats_out needs the bias / residual epilogue, one bf16 output and an 8-byte aligned buffer");
+  if (d.ln_stats != nullptr)
+    B200_CHECK_ARG((d.epilogue == B200_EPI_BIAS || d.epilogue == B200_EPI_BIAS_GELU) && d.out_dtype == B200_DTYPE_BF16 &&
+                       d.out2 == nullptr && !d.a_mn && d.ln_c1 != nullptr && d.bias != nullptr && d.bias_dtype == B200_DTYPE_F32 &&
+                       d.ln_slots > 0 && (reinterpret_cast<uintptr_t>(d.ln_stats) & 7) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d.ln_c1) & 15) == 0,
+                   "b200_gemm: ln_stats needs the bias / GELU epilogue, a bf16 output, fp32 ln_c1 and fp32 bias (c2), ln_slots > 0");
   if (d.row_scale != nullptr)
     B200_CHECK_ARG(d.epilogue == B200_EPI_BIAS_RESIDUAL && d.rows_per_scale > 0,
                    "b200_gemm: row_scale needs the residual epilogue and rows_per_scale > 0");
@@ -854,6 +944,19 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
 
   // Tile-N selection: 256 wide unless N is small (wasted columns) -- 128 then.
   const bool wide = d.N > 128;
+  if (d.ln_stats_out != nullptr || d.ln_stats != nullptr) {
+    // folded LayerNorm: the K-major pair kernels of the inference forward (callers fall back to a LayerNorm pass otherwise)
+    if (!(wide && d.M >= 256 && !d.a_mn && !d.b_mn && d.act == 0))
+      return fail(B200_ERR_UNSUPPORTED, "b200_gemm: ln_stats / ln_stats_out need M >= 256, N > 128, K-major operands and act = 0");
+    if (d.ln_stats != nullptr && d.ln_stats_out != nullptr)
+      return fail(B200_ERR_UNSUPPORTED, "b200_gemm: one launch is either the producer or the consumer of a folded LayerNorm");
+    if (d.ln_stats_out != nullptr) return launch_gemm<256, 6, false, false, true, 32, -1, false, 2>(d, stream);
+    ln_finalize_kernel<<<(d.M + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(d.ln_stats), d.M, d.ln_slots,
+                                                             1.0f / static_cast<float>(d.K), d.ln_eps);
+    B200_CUDA_OK(cudaGetLastError());
+    if (d.epilogue == B200_EPI_BIAS_GELU) return launch_gemm<256, 5, false, false, true, 64, B200_EPI_BIAS_GELU, false, 1>(d, stream);
+    return launch_gemm<256, 6, false, false, true, 32, -1, false, 1>(d, stream);
+  }
   // CTA pairs (256 x 256 tiles, cta_group::2) once there are enough 256-row tile pairs to fill the GPU
   if (d.act != 0) {
     // tanh GELU / SiLU: the activation-at-run-time instantiations of the two shapes an MLP produces -- fc1 forward

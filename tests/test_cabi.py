@@ -48,7 +48,7 @@ def test_gemm_desc_layout_matches_header(tmp_path):
     nums = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert ctypes.sizeof(_lib.GemmDesc) == nums[0]
     assert [getattr(_lib.GemmDesc, f).offset for f in fields] == nums[1:]
-    assert fields[-1] == "colsum" and _lib.GemmDesc.M.offset == 104
+    assert fields[-1] == "ln_eps" and _lib.GemmDesc.M.offset == 104
 
 
 def test_argument_errors_are_reported_not_crashed():

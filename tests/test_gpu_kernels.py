@@ -509,3 +509,88 @@ def test_attention_bias_with_fused_qkv_bias_gradient():
     db = torch.zeros(3 * H * hd, device=DEV)
     dqkv = ops.attention_bwd(qkv, out, dout, lse, B, N, H, hd, 0.125, kv_len=operand, dbias=db)
     _close(db, dqkv.float().view(B * N, -1).sum(0), 5e-2, 1e-2, "dbias under a causal mask")
+
+
+# ------------------------------------------------------------------------------------------------ folded LayerNorm
+@pytest.mark.parametrize("M,D,N,gelu", [(1576, 768, 2304, False), (1576, 768, 3072, True), (300, 192, 576, False), (1000, 384, 1536, True)])
+def test_gemm_folded_layernorm(M, D, N, gelu):
+    """b200_gemm_desc.ln_*: the residual GEMM leaves per-row partial sums of the bf16 values it stores; the next Linear runs on
+    the un-normalised rows against weight * gamma and finishes LayerNorm in its epilogue.  Against fp32 LayerNorm + Linear
+    (+ exact GELU) of timm/layers/norm.py:85-90, mlp.py:48-49 on the same bf16 inputs."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    a = torch.randn(M, D, device=DEV, generator=g).bfloat16()
+    wp = (torch.randn(D, D, device=DEV, generator=g) * D ** -0.5).bfloat16()
+    bp = torch.randn(D, device=DEV, generator=g).bfloat16()
+    # a residual stream with a per-row offset and a few large channels (what a ViT's looks like)
+    res = (torch.randn(M, D, device=DEV, generator=g) + torch.randn(M, 1, device=DEV, generator=g) * 0.5)
+    res[:, :4] *= 12.0
+    res = res.bfloat16()
+    stats = ops.ln_stats_buffer(M, D, DEV)
+    x = ops.linear_fwd(a, wp, bp, epilogue=ops.EPI_BIAS_RESIDUAL, aux=res, ln_stats_out=stats)
+    x_plain = ops.linear_fwd(a, wp, bp, epilogue=ops.EPI_BIAS_RESIDUAL, aux=res)
+    assert torch.equal(x, x_plain)                      # the producer stores the same values with and without statistics
+    xf = x.float()
+    s = stats[:-1].sum(0)
+    _close(s[:, 0], xf.sum(1), 2e-2, 1e-4, "row sums")
+    _close(s[:, 1], (xf * xf).sum(1), 1e-1, 1e-4, "row sums of squares")
+    gamma = (1.0 + 0.2 * torch.randn(D, device=DEV, generator=g)).bfloat16()
+    beta = (0.1 * torch.randn(D, device=DEV, generator=g)).bfloat16()
+    w = (torch.randn(N, D, device=DEV, generator=g) * D ** -0.5).bfloat16()
+    b = torch.randn(N, device=DEV, generator=g).bfloat16()
+    eps = 1e-6
+    wg = (w.float() * gamma.float()[None]).bfloat16().contiguous()
+    c1 = wg.float().sum(1).contiguous()
+    c2 = (w.float() @ beta.float() + b.float()).contiguous()
+    epi = ops.EPI_BIAS_GELU if gelu else ops.EPI_BIAS
+    y = ops.linear_fwd(x, wg, c2, epilogue=epi, ln_in=(stats, c1, eps))
+    ref = torch.nn.functional.layer_norm(xf, (D,), gamma.float(), beta.float(), eps) @ w.float().t() + b.float()
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    _close(y, ref, 3e-2, 2e-2, f"folded LayerNorm -> Linear M={M} N={N} gelu={gelu}")
+    # and against the unfolded kernel sequence (LayerNorm kernel, bf16 h, GEMM): the two differ by bf16 roundings only
+    h = ops.layernorm_fwd(x, gamma, beta, eps)[0]
+    y2 = ops.linear_fwd(h, w, b, epilogue=epi)
+    _close(y, y2, 4e-2, 2e-2, "folded vs unfolded")
+
+
+def test_gemm_folded_layernorm_rejects_unsupported_shapes():
+    ops = _ops()
+    a = torch.zeros(64, 256, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(256, 256, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(ops.B200Error):       # M < 256: no folded instantiation; callers keep the LayerNorm kernel
+        ops.linear_fwd(a, w, None, ln_stats_out=ops.ln_stats_buffer(64, 256, DEV))
+
+
+def test_vit_forward_with_and_without_folded_layernorm():
+    """The whole inference forward with the LayerNorms folded into the GEMMs (default) and with LayerNorm kernels
+    (functional._LN_FOLD = False): same logits within bf16 rounding, both within tolerance of the CPU oracle."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import vit_oracle as O
+    from b200timm import functional as BF
+    from b200timm.vision_transformer import VisionTransformer
+    ops = _ops()
+    cfg = dict(img_size=224, patch_size=16, embed_dim=256, depth=3, num_heads=4, init_values=0.3)
+    sd = {k: v.bfloat16().float() for k, v in O.random_state_dict(cfg, seed=21, num_classes=40).items()}
+    model = VisionTransformer(num_classes=40, **cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().to(torch.bfloat16).eval()
+    img = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(1)).bfloat16()
+    ref = O.vit_forward(img.float(), sd, dict(cfg, num_prefix_tokens=1))
+    outs = {}
+    for fold in (True, False):
+        BF._LN_FOLD = fold
+        try:
+            ops.reset_counters()
+            with torch.no_grad():
+                outs[fold] = model(img.cuda()).float().cpu()
+            launches = ops.launch_count()
+        finally:
+            BF._LN_FOLD = True
+        outs[(fold, "launches")] = launches
+        assert (outs[fold] - ref).abs().max().item() <= 2e-2 + 2e-2 * ref.abs().max().item()
+    # 5 of the 6 LayerNorm launches are gone (the first block's norm1 stays); each became a statistics finalisation
+    assert outs[(True, "launches")] == outs[(False, "launches")], outs
+    assert (outs[True] - outs[False]).abs().max().item() <= 1e-2 + 1e-2 * ref.abs().max().item()

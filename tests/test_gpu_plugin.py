@@ -214,6 +214,10 @@ VARIANT_MODELS = [
     ("vit_base_patch16_xp_224", {"depth": 2}, 224),                                         # parallel block + qk-norm + RmsNorm
     ("vit_base_patch16_224", {"depth": 2, "scale_mlp_norm": True, "scale_attn_norm": True, "norm_layer": "layernorm"}, 224),
     ("vit_base_patch16_224", {"depth": 2, "global_pool": "prr", "class_token": False}, 224),
+    ("vit_huge_patch14_224", {"depth": 2}, 224),                                            # head_dim 80 -> 128-wide kernels, N = 257
+    ("vit_so400m_patch14_siglip_224", {"depth": 2}, 224),                                   # head_dim 72, 'map' pool with 72-wide heads
+    ("vit_giant_patch14_224", {"depth": 1, "img_size": 112}, 112),                                          # head_dim 88, N = 65 (short sequence)
+    ("vit_base_patch16_224", {"depth": 2, "num_heads": 6}, 224),                            # head_dim 128, N = 197
     ("convnextv2_atto", {}, 128),               # conv_mlp=True (LayerNorm2d + 1x1-conv MLP), GRN, C = 40 .. 320
     ("convnext_atto", {}, 128),                 # conv_mlp=True without GRN
 ]
