@@ -80,24 +80,15 @@ def _ln_fold(norm, linear, w, b, tag):
     return (*_cached(linear, "_b200_lnfold_" + tag, key, build), float(norm.eps))
 
 
-def _tver(t):
-    """Version counter of a tensor; inference-mode tensors have none (reading `_version` raises on them)."""
-    return -1 if t.is_inference() else t._version
+class LnCarry:
+    """Row statistics of the residual stream, handed from the GEMM that produced it (a block's fc2) to the next block's
+    norm1 by the loop that calls the blocks (vit_forward_features, NaFlexVit.forward_features): `stats` describes exactly the
+    tensor the previous block_forward returned.  Calls without a carrier (a block invoked on its own, timm's own loop through
+    the plugin's per-module rebinding) fold norm2 only -- nothing is ever attached to tensors."""
+    __slots__ = ("stats",)
 
-
-def _tag_ln_stats(out, stats):
-    """Remember the row statistics the producing GEMM left for `out` ON the tensor object; the next block's forward picks
-    them up when it receives this very object unmodified (the model's `for blk in blocks` / nn.Sequential loop)."""
-    if stats is not None:
-        out._b200_ln_stats = (stats, out.data_ptr(), _tver(out), tuple(out.shape))
-    return out
-
-
-def _take_ln_stats(x):
-    t = getattr(x, "_b200_ln_stats", None)
-    if t is None or t[1] != x.data_ptr() or t[2] != _tver(x) or t[3] != tuple(x.shape) or not x.is_contiguous():
-        return None
-    return t[0]
+    def __init__(self):
+        self.stats = None
 
 
 def _gamma(ls):
@@ -666,8 +657,12 @@ def parallel_block_forward(blk, x, kv_len=None):
     return out.view(B, N, D)
 
 
-def block_forward(blk, x, kv_len=None):
-    """Block.forward (timm/models/vision_transformer.py:206-214), eval mode."""
+def block_forward(blk, x, kv_len=None, carry=None):
+    """Block.forward (timm/models/vision_transformer.py:206-214), eval mode.  carry: the calling loop's LnCarry (folded
+    LayerNorm across blocks) or None."""
+    st_in = None
+    if carry is not None:
+        st_in, carry.stats = carry.stats, None        # consumed here; set again below only by the fused inference path
     if is_parallel_block(blk):
         return parallel_block_forward(blk, x, kv_len)
     attn, mlp = blk.attn, blk.mlp
@@ -692,7 +687,8 @@ def block_forward(blk, x, kv_len=None):
     rs1, rs2 = _drop_path_factor(blk.drop_path1, x), _drop_path_factor(blk.drop_path2, x)   # None in eval mode
     M = B * N
     fold = _LN_FOLD and M >= 256 and D > 128       # the shapes the folded-LayerNorm GEMM instantiations serve
-    st_in = _take_ln_stats(x) if fold else None     # left by the GEMM that produced x (the previous block's fc2)
+    if not fold or not x.is_contiguous():
+        st_in = None                                # else: left by the GEMM that produced x (the previous block's fc2)
     x2 = _bf16_2d(x, D)
     wqkv, bqkv = head_padded_linear_in(attn.qkv, 3, attn.num_heads, attn.head_dim)
     f1 = _ln_fold(blk.norm1, attn.qkv, wqkv, bqkv, "qkv") if st_in is not None else None
@@ -714,11 +710,13 @@ def block_forward(blk, x, kv_len=None):
         w2, b2, eps2 = _ln_params(blk.norm2)
         h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]
         h = ops.linear_fwd(h, _w(mlp.fc1), mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=act)
-    # the statistics of the block's output ride along for the next block's norm1 (a plain LayerNorm follows in every ViT)
-    st3 = ops.ln_stats_buffer(M, D, x.device) if fold else None
+    # the statistics of the block's output ride along for the next block's norm1 when the calling loop carries them
+    st3 = ops.ln_stats_buffer(M, D, x.device) if fold and carry is not None else None
     x2 = ops.linear_fwd(h, _w(mlp.fc2), mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2, gamma=_gamma(blk.ls2),
                         row_scale=rs2, rows_per_scale=N, ln_stats_out=st3)
-    return _tag_ln_stats(x2.view(B, N, D), st3)
+    if carry is not None:
+        carry.stats = st3
+    return x2.view(B, N, D)
 
 
 def patch_embed_forward(pe, img):
@@ -877,8 +875,9 @@ def vit_forward_features(model, img, kv_len=None, final_norm=True):
         for blk in model.blocks:
             x = checkpoint(block_forward, blk, x, kv_len, use_reentrant=False)
     else:
+        carry = LnCarry()
         for blk in model.blocks:
-            x = block_forward(blk, x, kv_len)
+            x = block_forward(blk, x, kv_len, carry)
     if final_norm and not _is_identity(model.norm):
         x = layernorm(model.norm, x)
     return x

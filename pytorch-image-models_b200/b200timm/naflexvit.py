@@ -185,8 +185,9 @@ class NaFlexVit(nn.Module):
         x, kv_len = self._tokens(patches, patch_coord, patch_valid, rows)
         if not isinstance(self.norm_pre, nn.Identity):
             x = BF.layernorm(self.norm_pre, x)
+        carry = BF.LnCarry()
         for blk in self.blocks:
-            x = BF.block_forward(blk, x, kv_len)
+            x = BF.block_forward(blk, x, kv_len, carry)
         if not isinstance(self.norm, nn.Identity):
             x = BF.layernorm(self.norm, x)
         return {"patches": x, "patch_valid": patch_valid}

@@ -356,13 +356,54 @@ def _wgrad_split(rows_out, cols_out, k):
     return split
 
 
+_WGRAD_NSPLIT = __import__("os").environ.get("B200_WGRAD_NSPLIT", "1")[:1] != "0"
+
+
+def _wgrad_parts(rows_out, cols_out, k):
+    """Output-row chunks for one weight gradient.  The pair kernel covers [rows_out, cols_out] with 256 x 256 tiles, each
+    split along K so that the tile-pairs fill the 74 CTA pairs of the GPU; a shape whose tile count divides 74 badly (ViT-L's
+    fused qkv projection [3072, 1024]: 48 tiles, no split -> 48 of 74 pairs busy) runs as several launches over row chunks
+    that do (2 x [1536, 1024]: 24 tiles, split 3 -> 72 pairs each; measured 191 -> 166 us at 36928 rows).  Chunks that would
+    need a deep split are not taken (ViT-B's [2304, 768] as 3 x [768, 768] with split 8 measured 147 us against 139 us for the
+    single launch at 54 pairs: the reduce-add traffic of 8 partial tiles outweighs the idle SMs).  Returns [(row0, rows,
+    split_k)] or None."""
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    pairs = max(1, sms // 2)
+
+    def plan(rows):
+        tiles = ((rows + 255) // 256) * ((cols_out + 255) // 256)
+        split = max(1, min(pairs // max(tiles, 1), (k + 4095) // 4096))
+        return tiles, split
+    tiles, split = plan(rows_out)
+    if not _WGRAD_NSPLIT or rows_out < 512 or cols_out <= 128 or k < 256 or tiles * split >= 0.85 * pairs:
+        return None
+    best = None
+    for parts in (2, 3, 4):
+        if rows_out % (parts * 256):
+            continue
+        t, sp = plan(rows_out // parts)
+        util = t * sp / pairs
+        if util <= 1.0 and sp <= 4 and (best is None or util > best[0]):
+            best = (util, parts, sp)
+    if best is None or best[0] < tiles * split / pairs + 0.15:
+        return None
+    _, parts, sp = best
+    rows = rows_out // parts
+    return [(i * rows, rows, max(2, sp)) for i in range(parts)]
+
+
 def linear_wgrad(dy2d, x2d, out=None):
     """dW[N,K] = dY[M,N]^T @ X[M,K] in fp32 (both operands MN-major in place, split-K through TMA reduce-add).
     `out`: optional ZERO-INITIALISED (or to-be-accumulated-into) fp32 [N,K] buffer."""
     M, N = dy2d.shape
     K = x2d.shape[1]
     ws = out if out is not None else torch.zeros(N, K, dtype=torch.float32, device=dy2d.device)
-    gemm(dy2d, x2d, N, K, M, a_mn=True, b_mn=True, out=ws, split_k=max(2, _wgrad_split(N, K, M)))
+    parts = _wgrad_parts(N, K, M) if M >= 256 and ws.is_contiguous() else None
+    if parts is None:
+        gemm(dy2d, x2d, N, K, M, a_mn=True, b_mn=True, out=ws, split_k=max(2, _wgrad_split(N, K, M)))
+    else:
+        for r0, rows, split in parts:      # column ranges of dY (views: same row pitch) -> row ranges of dW
+            gemm(dy2d[:, r0:r0 + rows], x2d, rows, K, M, a_mn=True, b_mn=True, out=ws[r0:r0 + rows], split_k=split)
     return ws
 
 

@@ -594,3 +594,25 @@ def test_vit_forward_with_and_without_folded_layernorm():
     # 5 of the 6 LayerNorm launches are gone (the first block's norm1 stays); each became a statistics finalisation
     assert outs[(True, "launches")] == outs[(False, "launches")], outs
     assert (outs[True] - outs[False]).abs().max().item() <= 1e-2 + 1e-2 * ref.abs().max().item()
+
+
+def test_wgrad_row_chunks_match_one_launch(monkeypatch):
+    """ops.linear_wgrad splits a badly tiling weight gradient (ViT-L's fused qkv projection: 3072 x 1024, 48 tiles for 74 CTA
+    pairs) into launches over row chunks; same result as the single split-K launch and as fp32 matmul."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    assert ops._wgrad_parts(3072, 1024, 36928) == [(0, 1536, 3), (1536, 1536, 3)]
+    assert ops._wgrad_parts(2304, 768, 50432) is None and ops._wgrad_parts(768, 768, 50432) is None
+    M, N, K = 1576, 3072, 1024
+    dy = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    x = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    monkeypatch.setattr(ops, "_wgrad_parts", lambda n, k, m: [(0, 1536, 3), (1536, 1536, 3)])     # the plan of the full-size call
+    got = ops.linear_wgrad(dy, x)
+    one = torch.zeros(N, K, device=DEV)
+    ops.gemm(dy, x, N, K, M, a_mn=True, b_mn=True, out=one, split_k=2)
+    ref = dy.float().t() @ x.float()
+    _close(got, ref, 5e-2, 1e-3, "wgrad in row chunks")
+    _close(got, one, 2e-3, 1e-4, "row chunks vs one launch")
+    acc = torch.ones(N, K, device=DEV)               # accumulates into a non-zero buffer like the single launch
+    ops.linear_wgrad(dy, x, out=acc)
+    _close(acc, ref + 1.0, 5e-2, 1e-3, "wgrad accumulation")
