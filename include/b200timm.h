@@ -48,7 +48,7 @@ extern "C" {
                                  `rot` layout, head_dim 64, one [sin | cos] table shared by batch and heads)       */
 
 B200_API const char* b200_last_error(void);
-/* 8 now (7 -> 8: head_dim 128 in b200_attn_fwd / b200_attn_bwd and their _bias variants, b200_attn_bwd_ws_floats_hd; b200_gemm_desc.ln_* and b200_gemm_ln_slots); 6 -> 7: b200_attn_fwd_bias / b200_attn_bwd_bias; 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
+/* 8 now (7 -> 8: head_dim 128 in b200_attn_fwd / b200_attn_bwd and their _bias variants, b200_attn_bwd_ws_floats_hd; b200_gemm_desc.ln_*, b200_gemm_ln_slots, b200_dwconv_nhwc_ln); 6 -> 7: b200_attn_fwd_bias / b200_attn_bwd_bias; 5 at the end of round 1 (4 -> 5: optimizer / loss / EMA / qk-norm / GLU / GRN / uint8 entry points, b200_gemm_desc.act). */
 B200_API int b200_abi_version(void);
 /* 0 if the current device is sm_100 and the tensor-map driver entry point resolves. */
 B200_API int b200_device_check(void);
@@ -277,6 +277,13 @@ B200_API int b200_glu_bwd(const void* h, const void* dout, void* dh, int64_t M, 
  * dx = dwconv(dy, spatially flipped weight) + shortcut gradient.                                                 */
 B200_API int b200_dwconv_nhwc(const void* x, const void* weight_t, const void* bias, const void* residual, void* y,
                      int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype, void* stream);
+/* ABI >= 8.  The same convolution as the PRODUCER of a folded LayerNorm (b200_gemm_desc.ln_*): `y = conv_dw(x)` followed by
+ * `norm(y)` and `fc1` of ConvNeXtBlock.forward (convnext.py:200-207) without a LayerNorm pass over HBM.  ln_stats_out: fp32
+ * [C / 64 + 1][B*H*W][2]; slot c / 64 receives, per pixel, the sum and the sum of squares of the 64 bf16 channel values the
+ * kernel stores; the consuming b200_gemm call gets ln_slots = C / 64.  Needs C % 64 == 0 and ksize == 7 (the TMA-staged
+ * kernel), otherwise B200_ERR_UNSUPPORTED and the caller keeps the LayerNorm kernel.                                      */
+B200_API int b200_dwconv_nhwc_ln(const void* x, const void* weight_t, const void* bias, void* y, float* ln_stats_out, int32_t B,
+                        int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype, void* stream);
 /* dweight_t[ky,kx,c] += sum_{b,y,x} dy[b,y,x,c] * x[b,y+ky-k/2,x+kx-k/2,c]  (fp32 [k,k,C], zero-initialised by the caller). */
 B200_API int b200_dwconv_nhwc_wgrad(const void* x, const void* dy, float* dweight_t, int32_t B, int32_t H, int32_t W,
                            int32_t C, int32_t ksize, void* stream);

@@ -108,6 +108,7 @@ SIGNATURES = {
     "b200_colsum_mul": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "b200_colsum": (ctypes.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "b200_dwconv_nhwc": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "b200_dwconv_nhwc_ln": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_dwconv_nhwc_wgrad": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_unpatchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "b200_patchify_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),

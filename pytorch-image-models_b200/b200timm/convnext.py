@@ -22,6 +22,7 @@ from ._lib import B200Error
 from .layers import DropPath, Mlp
 
 
+from . import functional as BF  # noqa: E402
 from .functional import _w, mlp_act  # noqa: E402  (bf16 GEMM operand of a Linear / Conv2d: bf16 params as is, fp32 params cast)
 
 
@@ -278,9 +279,20 @@ def block_forward_nhwc(self, x, B, H, W):
         return _BlockFn.apply(x, _w(self.conv_dw), self.conv_dw.bias, self.norm.weight, self.norm.bias,
                               _mlp_w(self.mlp.fc1), self.mlp.fc1.bias, _mlp_w(self.mlp.fc2), self.mlp.fc2.bias,
                               self.gamma, rs, B, H, W, self.norm.eps, *extra, mlp_act(self.mlp))
-    y = ops.dwconv_nhwc(x.view(B, H, W, C), _dw_weight_t(self.conv_dw), self.conv_dw.bias).view(B * H * W, C)
-    h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
-    a = ops.linear_fwd(h, _mlp_w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=mlp_act(self.mlp))
+    # the block's LayerNorm folded into its neighbours (inference): the depthwise convolution leaves per-pixel partial sums,
+    # fc1 runs on the un-normalised rows against weight * gamma and finishes LN in its epilogue (functional._ln_fold)
+    wt = _dw_weight_t(self.conv_dw)
+    act = mlp_act(self.mlp)
+    fold = None
+    if B * H * W >= 256 and act == 0 and ops.dwconv_ln_fusable(C, wt.shape[0]) and x.data_ptr() % 16 == 0:
+        fold = BF._ln_fold(self.norm, self.mlp.fc1, _mlp_w(self.mlp.fc1), self.mlp.fc1.bias, "fc1")
+    if fold is not None:
+        y, st = ops.dwconv_nhwc_ln(x.view(B, H, W, C), wt, self.conv_dw.bias)
+        a = ops.linear_fwd(y.view(B * H * W, C), fold[0], fold[2], epilogue=ops.EPI_BIAS_GELU, ln_in=(st, fold[1], fold[3]))
+    else:
+        y = ops.dwconv_nhwc(x.view(B, H, W, C), wt, self.conv_dw.bias).view(B * H * W, C)
+        h = ops.layernorm_fwd(y, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+        a = ops.linear_fwd(h, _mlp_w(self.mlp.fc1), self.mlp.fc1.bias, epilogue=ops.EPI_BIAS_GELU, act=act)
     if grn is not None:
         ops.grn_fwd(a, grn.weight, grn.bias, B, H * W, grn.eps)
     return ops.linear_fwd(a, _mlp_w(self.mlp.fc2), self.mlp.fc2.bias, epilogue=ops.EPI_BIAS_RESIDUAL, aux=x,

@@ -598,6 +598,32 @@ def dwconv_nhwc(x, weight_t, bias, residual=None):
     return y
 
 
+def dwconv_ln_fusable(C, k):
+    """True when dwconv_nhwc(..., ln_stats=True) can produce the statistics of a folded LayerNorm (the TMA-staged kernel)."""
+    return C % 64 == 0 and k == 7
+
+
+def dwconv_nhwc_ln(x, weight_t, bias):
+    """dwconv_nhwc that also returns the partial LayerNorm statistics of its output rows: (y [B,H,W,C], stats fp32
+    [C / 64 + 1, B*H*W, 2]) -- the `ln_in` buffer of the GEMM that follows the block's norm (b200_dwconv_nhwc_ln)."""
+    _need_cuda(x, weight_t, bias)
+    if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise B200Error("dwconv_nhwc_ln: need a contiguous bf16 [B,H,W,C] tensor")
+    B, H, W, C = x.shape
+    k = weight_t.shape[0]
+    if tuple(weight_t.shape) != (k, k, C) or weight_t.dtype != torch.bfloat16 or not weight_t.is_contiguous():
+        raise B200Error("dwconv_nhwc_ln: weight_t must be contiguous bf16 [k,k,C] (see dwconv_weight_t)")
+    if not dwconv_ln_fusable(C, k):
+        raise B200Error("dwconv_nhwc_ln: needs C % 64 == 0 and a 7 x 7 kernel")
+    y = torch.empty_like(x)
+    stats = torch.empty(C // 64 + 1, B * H * W, 2, dtype=torch.float32, device=x.device)
+    rc = _lib.load().b200_dwconv_nhwc_ln(x.data_ptr(), weight_t.data_ptr(), _ptr(bias), y.data_ptr(), stats.data_ptr(), B, H, W, C, k,
+                                         _dt(bias) if bias is not None else DTYPE_BF16, _stream())
+    _lib.check(rc, "b200_dwconv_nhwc_ln")
+    _count()
+    return y, stats
+
+
 def dwconv_nhwc_wgrad(x, dy, k, out=None):
     """fp32 [k,k,C] gradient of the depthwise weight (transposed layout); `out` must be zero-initialised."""
     _need_cuda(x, dy, out)
@@ -949,5 +975,5 @@ def _timed(name, fn):
 
 
 for _n in ("layernorm_fwd", "layernorm_bwd", "gemm", "attention_fwd", "attention_bwd", "patchify", "assemble_tokens",
-           "colsum", "convert_f32", "dwconv_nhwc", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc", "avgpool_nhwc", "naflex_assemble"):
+           "colsum", "convert_f32", "dwconv_nhwc", "dwconv_nhwc_ln", "dwconv_nhwc_wgrad", "unpatchify_nhwc", "patchify_nhwc", "avgpool_nhwc", "naflex_assemble"):
     globals()[_n] = _timed(_n, globals()[_n])

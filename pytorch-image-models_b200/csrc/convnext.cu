@@ -266,8 +266,23 @@ int launch_dwconv_tma(const void* x, const void* wt, const void* bias, const voi
                       int C, int ksize, int bias_f32, cudaStream_t st);
 int launch_dwconv_wgrad_tma(const void* x, const void* dy, float* dwt, int B, int H, int W, int C, int ksize,
                             cudaStream_t st);
+int launch_dwconv_tma_ln(const void* x, const void* wt, const void* bias, void* y, float* ln_stats, int B, int H, int W, int C,
+                         int ksize, int bias_f32, cudaStream_t st);
 }
 using namespace b200;
+
+extern "C" int b200_dwconv_nhwc_ln(const void* x, const void* weight_t, const void* bias, void* y, float* ln_stats_out,
+                                   int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  B200_CHECK_ARG(x && weight_t && y && ln_stats_out, "b200_dwconv_nhwc_ln: null pointer");
+  B200_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "b200_dwconv_nhwc_ln: bad shape");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(ln_stats_out) & 7) == 0,
+                 "b200_dwconv_nhwc_ln: x must be 16-byte, ln_stats_out 8-byte aligned");
+  const int rc = launch_dwconv_tma_ln(x, weight_t, bias, y, ln_stats_out, B, H, W, C, ksize, bias_dtype == B200_DTYPE_F32, st);
+  if (rc == B200_ERR_UNSUPPORTED)
+    return fail(B200_ERR_UNSUPPORTED, "b200_dwconv_nhwc_ln: needs C %% 64 == 0 and a 7 x 7 kernel (got C=%d k=%d)", C, ksize);
+  return rc;
+}
 
 extern "C" int b200_dwconv_nhwc(const void* x, const void* weight_t, const void* bias, const void* residual, void* y,
                                 int32_t B, int32_t H, int32_t W, int32_t C, int32_t ksize, int32_t bias_dtype,

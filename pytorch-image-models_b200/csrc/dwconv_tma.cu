@@ -44,6 +44,9 @@ struct DwTmaParams {
   int B, H, W, C, bias_f32;
   int tiles_y, tiles_x, cblocks;
   long long num_items;
+  // STATS instantiation (b200_dwconv_nhwc_ln): fp32 [C / 64 + 1][B*H*W][2] -- per pixel and 64-channel block the sum and
+  // the sum of squares of the bf16 values stored, the producer side of a LayerNorm folded into the next GEMM (gemm.cu)
+  float* ln_stats;
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -61,7 +64,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
-template <int KS>
+template <int KS, bool STATS = false>
 __global__ void __launch_bounds__(kThreads, 2)
 dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const DwTmaParams p) {
   using L = DwTmaSmem<KS>;
@@ -190,6 +193,11 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const DwTmaParams p)
       issue(item + 2 * step, buf);
     }
 
+    float st_s[kSW], st_q[kSW];      // STATS: this thread's 8 channels of each of its pixels
+    if constexpr (STATS) {
+#pragma unroll
+      for (int t = 0; t < kSW; ++t) st_s[t] = st_q[t] = 0.f;
+    }
     if (oy < p.H) {
       const long long rowoff = ((static_cast<long long>(b) * p.H + oy) * p.W) * p.C + c;
 #pragma unroll
@@ -210,15 +218,46 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const DwTmaParams p)
             o[j] = pack_bf16(lo, hi);
           }
           *reinterpret_cast<uint4*>(p.y + off) = make_uint4(o[0], o[1], o[2], o[3]);
+          if constexpr (STATS) {
+            f32x2 s2 = splat(0.f), q2 = splat(0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const f32x2 v = bf16x2_to_f32x2(o[j]);        // exactly the values the LayerNorm would read
+              s2 = add2(s2, v);
+              q2 = fma2(v, v, q2);
+            }
+            float a0, a1, b0, b1;
+            upk(s2, a0, a1);
+            upk(q2, b0, b1);
+            st_s[t] = a0 + a1;
+            st_q[t] = b0 + b1;
+          }
         }
+      }
+    }
+    if constexpr (STATS) {
+      // the 8 lanes cv = 0..7 of a (row, strip) hold the 64 channels of the same pixels: butterfly over them (all 32 lanes
+      // take part: kThreads is a whole number of warps), lane cv == 0 stores the block's (sum, sum of squares) per pixel
+      const long long rows_total = static_cast<long long>(p.B) * p.H * p.W;
+      float2* dst = reinterpret_cast<float2*>(p.ln_stats) + static_cast<long long>(cb) * rows_total +
+                    (static_cast<long long>(b) * p.H + oy) * p.W;
+#pragma unroll
+      for (int t = 0; t < kSW; ++t) {
+        float sv = st_s[t], qv = st_q[t];
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+          sv += __shfl_xor_sync(0xffffffffu, sv, m);
+          qv += __shfl_xor_sync(0xffffffffu, qv, m);
+        }
+        if (cv == 0 && oy < p.H && oxs + t < p.W) dst[oxs + t] = make_float2(sv, qv);
       }
     }
   }
 }
 
-template <int KS>
+template <int KS, bool STATS = false>
 static int launch_dwconv_tma_ks(const void* x, const void* wt, const void* bias, const void* residual, void* y, int B, int H,
-                                int W, int C, int bias_f32, cudaStream_t st) {
+                                int W, int C, int bias_f32, cudaStream_t st, float* ln_stats = nullptr) {
   using L = DwTmaSmem<KS>;
   CUtensorMap tm;
   {
@@ -234,7 +273,8 @@ static int launch_dwconv_tma_ks(const void* x, const void* wt, const void* bias,
   p.B = B; p.H = H; p.W = W; p.C = C; p.bias_f32 = bias_f32;
   p.tiles_y = (H + kTH - 1) / kTH; p.tiles_x = (W + kTWt - 1) / kTWt; p.cblocks = C / kCB;
   p.num_items = static_cast<long long>(p.cblocks) * B * p.tiles_y * p.tiles_x;
-  auto kern = dwconv_tma_kernel<KS>;
+  p.ln_stats = ln_stats;
+  auto kern = dwconv_tma_kernel<KS, STATS>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -253,6 +293,13 @@ int launch_dwconv_tma(const void* x, const void* wt, const void* bias, const voi
                       int C, int ksize, int bias_f32, cudaStream_t st) {
   if (C % kCB != 0 || ksize != 7) return B200_ERR_UNSUPPORTED;
   return launch_dwconv_tma_ks<7>(x, wt, bias, residual, y, B, H, W, C, bias_f32, st);
+}
+
+// The same convolution + per-pixel partial LayerNorm statistics (ln_stats: fp32 [C / 64 + 1][B*H*W][2], slot = channel block).
+int launch_dwconv_tma_ln(const void* x, const void* wt, const void* bias, void* y, float* ln_stats, int B, int H, int W, int C,
+                         int ksize, int bias_f32, cudaStream_t st) {
+  if (C % kCB != 0 || ksize != 7) return B200_ERR_UNSUPPORTED;
+  return launch_dwconv_tma_ks<7, true>(x, wt, bias, nullptr, y, B, H, W, C, bias_f32, st, ln_stats);
 }
 
 

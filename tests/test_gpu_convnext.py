@@ -260,3 +260,57 @@ def test_convnext_v2_grn_matches_reference_golden():
     out.float().mean().backward()
     _check_grads(model, fx["grads"], rel_tol=6e-2, min_cos=0.997)
 
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 14, 14, 512), (1, 56, 56, 128), (3, 7, 7, 1024), (2, 30, 17, 192)])
+def test_dwconv_with_layernorm_statistics(B, H, W, C):
+    """b200_dwconv_nhwc_ln: the same output bits as b200_dwconv_nhwc plus, per pixel and 64-channel block, the sum and the
+    sum of squares of the stored bf16 values (the producer side of the LayerNorm folded into fc1)."""
+    from b200timm import ops
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, 1, 7, 7, device="cuda", generator=g) * 0.2).bfloat16()
+    b = torch.randn(C, device="cuda", generator=g).bfloat16()
+    wt = ops.dwconv_weight_t(w)
+    y, st = ops.dwconv_nhwc_ln(x, wt, b)
+    assert torch.equal(y, ops.dwconv_nhwc(x, wt, b))
+    assert tuple(st.shape) == (C // 64 + 1, B * H * W, 2)
+    yf = y.float().view(B * H * W, C // 64, 64)
+    _check(st[:-1, :, 0].t(), yf.sum(-1), 1e-3, 1e-5, "partial sums", min_cos=0.99999)
+    _check(st[:-1, :, 1].t(), (yf * yf).sum(-1), 1e-3, 1e-5, "partial sums of squares", min_cos=0.99999)
+
+
+def test_convnext_block_with_and_without_folded_layernorm():
+    """ConvNeXtBlock inference with the LayerNorm folded between the depthwise convolution and fc1 (default) and with the
+    LayerNorm kernel: same output within bf16 rounding, both within tolerance of fp32 PyTorch math (convnext.py:197-213)."""
+    from b200timm import functional as BF, ops
+    from b200timm.convnext import ConvNeXtBlock
+    torch.manual_seed(3)
+    for C, HW in ((128, 28), (256, 14)):
+        blk = ConvNeXtBlock(C, ls_init_value=0.5).cuda().eval()
+        with torch.no_grad():
+            blk.norm.weight.normal_(1.0, 0.2)
+            blk.norm.bias.normal_(0.0, 0.2)
+            for p in blk.parameters():
+                p.copy_(p.bfloat16().float())
+        x = torch.randn(2, C, HW, HW, device="cuda").bfloat16()
+        with torch.no_grad():
+            xf = x.float()
+            r = torch.nn.functional.conv2d(xf, blk.conv_dw.weight, blk.conv_dw.bias, padding=3, groups=C).permute(0, 2, 3, 1)
+            r = torch.nn.functional.layer_norm(r, (C,), blk.norm.weight, blk.norm.bias, blk.norm.eps)
+            r = torch.nn.functional.gelu(r @ blk.mlp.fc1.weight.t() + blk.mlp.fc1.bias) @ blk.mlp.fc2.weight.t() + blk.mlp.fc2.bias
+            ref = xf + (r * blk.gamma).permute(0, 3, 1, 2)
+        blk = blk.to(torch.bfloat16)
+        outs = {}
+        for fold in (True, False):
+            BF._LN_FOLD = fold
+            try:
+                ops.reset_counters()
+                with torch.no_grad():
+                    outs[fold] = blk(x).float()
+                outs[(fold, "n")] = ops.launch_count()
+            finally:
+                BF._LN_FOLD = True
+            _check(outs[fold], ref, 3e-2, 2e-2, f"ConvNeXtBlock C={C} fold={fold}")
+        assert outs[(True, "n")] == outs[(False, "n")], outs      # LayerNorm launch <-> statistics finalisation
+        _check(outs[True], outs[False], 2e-2, 1e-2, "folded vs LayerNorm kernel")

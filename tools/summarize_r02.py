@@ -47,8 +47,8 @@ def unit_scale(u):
     return {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
 
 
-def block_table():
-    rows = list(csv.reader(open(os.path.join(SRC, "prof_train_block_raw.csv"))))
+def block_table(src="prof_train_block_raw.csv", dst="r02_train_block_kernels.md", header=None):
+    rows = list(csv.reader(open(os.path.join(SRC, src))))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
 
@@ -77,17 +77,42 @@ def block_table():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except (OSError, KeyError, ValueError):
         pass
-    with open(os.path.join(OUT, "r02_train_block_kernels.md"), "w") as f:
-        f.write("# r02: every kernel of ONE ViT-B/16 training step at depth 1 (batch 256, bf16) under `ncu --set full --clock-control none`\n\n"
+    with open(os.path.join(OUT, dst), "w") as f:
+        f.write(header if header is not None else "# r02: every kernel of ONE ViT-B/16 training step at depth 1 (batch 256, bf16) under `ncu --set full --clock-control none`\n\n"
                 "`ncu --set full --clock-control none --profile-from-start off python tools/ncu_train_step.py --depth 1` (tools/gpu_ncu_step.sh; "
                 "the report is converted to CSV on the GPU box, `gpurun_out/prof_train_block_raw.csv`).  Launch order = forward "
                 "(patch embed, block, head), loss, backward, optimizer.  DRAM GB/s = (dram read + write bytes) / duration against the "
                 f"measured HBM peak {peak:.0f} GB/s.  Captures are serialised cold-cache replays: use them for pipe utilisation, traffic "
                 "and stall shares; steady-state timings come from CUDA events (bench.py, tools/*).\n\n"
-                "| # | kernel | grid | us | DRAM MB | DRAM GB/s | % HBM peak | tensor % | FMA % | XU % | regs |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
+"")
+        f.write("| # | kernel | grid | us | DRAM MB | DRAM GB/s | % HBM peak | tensor % | FMA % | XU % | regs |\n|---|---|---|---|---|---|---|---|---|---|---|\n")
         for i, (name, grid, us, mb, gbs, tc, fma, xu, issue, regs) in enumerate(out):
             f.write(f"| {i} | `{name}` | {grid} | {us:.1f} | {mb:.1f} | {gbs:.0f} | {100 * gbs / peak:.0f} | {tc:.0f} | {fma:.0f} | {xu:.0f} | {regs} |\n")
     return out
+
+
+def main_b():
+    """The final-tree captures (tools/gpu_ncu_r02b.sh) -> profiles/r02b_*.md and the inference entry of profiles/traffic.json."""
+    launch_list("launches_infer_b.csv", "r02b_launches_infer.md",
+                "r02b: ncu launch list of ONE inference forward of the bench workload (ViT-B/16 bf16, batch 256), eager -- final tree: "
+                "LayerNorm folded into the GEMMs",
+                "ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python tools/ncu_train_step.py --infer")
+    note = ("DRAM GB/s = (dram read + write bytes) / duration against the measured HBM peak.  Serialised cold-cache replays: use them for "
+            "pipe utilisation, traffic and stall shares; steady-state timings come from CUDA events (bench.py, tools/*).\n\n")
+    rows = block_table("prof_infer2_raw.csv", "r02b_infer_block_kernels.md",
+                       "# r02b: every kernel of a depth-2 ViT-B/16 inference forward (batch 256, bf16) under `ncu --set full --clock-control none`\n\n"
+                       "`ncu --set full --clock-control none --profile-from-start off python tools/ncu_train_step.py --infer --depth 2` "
+                       "(tools/gpu_ncu_r02b.sh).  Block 0: LayerNorm kernel + plain qkv GEMM, proj GEMM producing statistics (LNF = 2), "
+                       "ln_finalize_kernel, fc1 + GELU consuming them (LNF = 1), fc2 producing; block 1: qkv consuming.  " + note)
+    block_table("prof_new_raw.csv", "r02b_new_kernels.md",
+                "# r02b: the kernels added late in round 2 under `ncu --set full --clock-control none` (tools/ncu_new_kernels.py)\n\n"
+                "128-wide attention forward / backward at ViT-H/14 geometry (B = 64, N = 257, H = 16: attn_fwd_long_kernel<.., 2>, "
+                "attn_bwd_delta_kernel<16>, attn_bwd_long_kernel<.., 2>, attn_dq_convert_kernel), the depthwise convolution producing "
+                "LayerNorm statistics (dwconv_tma_kernel<7, true>, ConvNeXt-B stage 3) with ln_finalize_kernel and the consuming fc1 GEMM.  " + note)
+    gem = [r for r in rows if r[0].startswith("gemm_bf16_kernel") and r[2] > 40]
+    for r in gem:
+        print(f"{r[2]:7.1f} us {r[3]:7.1f} MB tensor {r[5]:.0f}%  {r[0][:90]}")
+    return rows
 
 
 def main():
@@ -106,4 +131,5 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main_b() if len(sys.argv) > 1 and sys.argv[1] == "b" else main()
