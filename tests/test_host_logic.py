@@ -260,3 +260,43 @@ def test_attn_mask_operand_classifies_masks():
     assert h.shape == (B, 1, N, 8) and bool(torch.isinf(h[0, 0, :, 1]).all()) and bool((h[1] == 0).all())
     with pytest.raises(B200Error):
         L.attn_bias_operand(torch.zeros(2, 1, N, N + 1), N)
+
+
+def test_folded_layernorm_operands_are_the_same_affine_map():
+    """functional._ln_fold: Linear(LayerNorm(x)) == rstd * (x W'^T - mean * c1) + c2 with W' = W * gamma, c1 = rowsum(W'),
+    c2 = W beta + b (timm/layers/norm.py:85-90 followed by attention.py:115 / mlp.py:48) -- the algebra the GEMM epilogue
+    evaluates (b200_gemm_desc.ln_*), checked in fp64 torch math on the operands the host builds; the cache follows the
+    parameters' version counters."""
+    from b200timm import functional as BF
+    torch.manual_seed(0)
+    D, N = 192, 384
+    norm, lin = torch.nn.LayerNorm(D, eps=1e-6), torch.nn.Linear(D, N)
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.3)
+        norm.bias.normal_(0.0, 0.3)
+    norm, lin = norm.to(torch.bfloat16), lin.to(torch.bfloat16)
+    f = BF._ln_fold(norm, lin, lin.weight, lin.bias, "t")
+    assert f is not None and f is not BF._ln_fold(norm, lin, lin.weight, lin.bias, "t")       # tuples; the cached tensors are shared
+    wg, c1, c2, eps = f
+    assert wg.dtype == torch.bfloat16 and c1.dtype == c2.dtype == torch.float32 and eps == 1e-6
+    assert BF._ln_fold(norm, lin, lin.weight, lin.bias, "t")[0] is wg
+    x = (torch.randn(17, D) * 2 + 0.7).bfloat16().double()
+    mean = x.mean(-1, keepdim=True)
+    rstd = (x.var(-1, unbiased=False, keepdim=True) + eps).rsqrt()
+    got = rstd * (x @ wg.double().t() - mean * c1.double()) + c2.double()
+    xh = (x - mean) * rstd
+    # reference with the SAME rounded operand W' (what the tensor cores multiply): exact up to fp64 rounding
+    ref_same = xh @ wg.double().t() + c2.double()
+    torch.testing.assert_close(got, ref_same, atol=1e-5, rtol=1e-6)      # c1 is held in fp32
+    # and against the module pair itself: differs only by the bf16 rounding of W * gamma
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (D,), norm.weight.double(), norm.bias.double(), eps),
+                                     lin.weight.double(), lin.bias.double())
+    assert (got - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    with torch.no_grad():
+        norm.weight.mul_(2.0)                     # version bump -> rebuilt
+    assert BF._ln_fold(norm, lin, lin.weight, lin.bias, "t")[0] is not wg
+    assert BF._ln_fold(torch.nn.Identity(), lin, lin.weight, lin.bias, "t") is None
+    small = torch.nn.Linear(D, 64).to(torch.bfloat16)
+    assert BF._ln_fold(norm, small, small.weight, small.bias, "t") is None       # N <= 128: no folded instantiation
+    carry = BF.LnCarry()
+    assert carry.stats is None

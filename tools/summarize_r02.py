@@ -12,6 +12,7 @@ OUT, SRC = os.path.join(ROOT, "profiles"), os.path.join(ROOT, "gpurun_out")
 
 def short(name):
     name = re.sub(r"^void ", "", name)
+    name = re.sub(r"\((?:int|bool|unsigned int)\)", "", name)      # template-argument casts: (int)-1, (bool)1
     name = re.sub(r"\(.*", "", name)
     name = name.replace("b200::", "").replace("(anonymous namespace)::", "")
     return name[:96]
