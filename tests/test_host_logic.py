@@ -300,3 +300,19 @@ def test_folded_layernorm_operands_are_the_same_affine_map():
     assert BF._ln_fold(norm, small, small.weight, small.bias, "t") is None       # N <= 128: no folded instantiation
     carry = BF.LnCarry()
     assert carry.stats is None
+
+
+def test_weight_gradient_row_chunk_plan(monkeypatch):
+    """ops._wgrad_parts (host logic): which weight gradients run as several launches over row chunks on a 148-SM device."""
+    from b200timm import ops
+
+    class Props:
+        multi_processor_count = 148
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: Props())
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    assert ops._wgrad_parts(3072, 1024, 36928) == [(0, 1536, 3), (1536, 1536, 3)]      # ViT-L qkv: 48 tiles -> 2 x 24 x split 3
+    for n, k in ((2304, 768), (768, 768), (3072, 768), (768, 3072), (1024, 1024), (4096, 1024), (1152, 384)):
+        assert ops._wgrad_parts(n, k, 50432) is None, (n, k)                             # fill the pairs, or would need a deep split
+    assert ops._wgrad_parts(3072, 1024, 128) is None                                     # short K: nothing to split
+    monkeypatch.setattr(ops, "_WGRAD_NSPLIT", False)
+    assert ops._wgrad_parts(3072, 1024, 36928) is None
