@@ -699,13 +699,13 @@ def block_forward(blk, x, kv_len=None, carry=None):
         qkv = ops.linear_fwd(ops.layernorm_fwd(x2, w1, b1, eps1)[0], wqkv, bqkv)
     o, _ = ops.attention_fwd(qkv, B, N, attn.num_heads, head_pad(attn.head_dim), attn.scale, kv_len)
     act = mlp_act(mlp)
-    f2 = _ln_fold(blk.norm2, mlp.fc1, _w(mlp.fc1), mlp.fc1.bias, "fc1") if fold and act == 0 else None
+    f2 = _ln_fold(blk.norm2, mlp.fc1, _w(mlp.fc1), mlp.fc1.bias, "fc1") if fold else None
     st2 = ops.ln_stats_buffer(M, D, x.device) if f2 is not None else None
     x2 = ops.linear_fwd(o.view(B * N, -1), head_padded_linear_out(attn.proj, attn.num_heads, attn.head_dim), attn.proj.bias,
                         epilogue=ops.EPI_BIAS_RESIDUAL, aux=x2,
                         gamma=_gamma(blk.ls1), row_scale=rs1, rows_per_scale=N, ln_stats_out=st2)
     if f2 is not None:
-        h = ops.linear_fwd(x2, f2[0], f2[2], epilogue=ops.EPI_BIAS_GELU, ln_in=(st2, f2[1], f2[3]))
+        h = ops.linear_fwd(x2, f2[0], f2[2], epilogue=ops.EPI_BIAS_GELU, act=act, ln_in=(st2, f2[1], f2[3]))
     else:
         w2, b2, eps2 = _ln_params(blk.norm2)
         h = ops.layernorm_fwd(x2, w2, b2, eps2)[0]

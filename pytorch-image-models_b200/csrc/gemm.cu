@@ -946,14 +946,16 @@ extern "C" int b200_gemm(const b200_gemm_desc* dp, void* stream_) {
   const bool wide = d.N > 128;
   if (d.ln_stats_out != nullptr || d.ln_stats != nullptr) {
     // folded LayerNorm: the K-major pair kernels of the inference forward (callers fall back to a LayerNorm pass otherwise)
-    if (!(wide && d.M >= 256 && !d.a_mn && !d.b_mn && d.act == 0))
-      return fail(B200_ERR_UNSUPPORTED, "b200_gemm: ln_stats / ln_stats_out need M >= 256, N > 128, K-major operands and act = 0");
+    if (!(wide && d.M >= 256 && !d.a_mn && !d.b_mn && (d.act == 0 || (d.ln_stats != nullptr && d.epilogue == B200_EPI_BIAS_GELU))))
+      return fail(B200_ERR_UNSUPPORTED, "b200_gemm: ln_stats / ln_stats_out need M >= 256, N > 128 and K-major operands");
     if (d.ln_stats != nullptr && d.ln_stats_out != nullptr)
       return fail(B200_ERR_UNSUPPORTED, "b200_gemm: one launch is either the producer or the consumer of a folded LayerNorm");
     if (d.ln_stats_out != nullptr) return launch_gemm<256, 6, false, false, true, 32, -1, false, 2>(d, stream);
     ln_finalize_kernel<<<(d.M + 255) / 256, 256, 0, stream>>>(reinterpret_cast<float2*>(d.ln_stats), d.M, d.ln_slots,
                                                              1.0f / static_cast<float>(d.K), d.ln_eps);
     B200_CUDA_OK(cudaGetLastError());
+    if (d.epilogue == B200_EPI_BIAS_GELU && d.act != 0)      // tanh GELU / SiLU: the activation-at-run-time kernel as consumer
+      return launch_gemm<256, 5, false, false, true, 64, -1, true, 1>(d, stream);
     if (d.epilogue == B200_EPI_BIAS_GELU) return launch_gemm<256, 5, false, false, true, 64, B200_EPI_BIAS_GELU, false, 1>(d, stream);
     return launch_gemm<256, 6, false, false, true, 32, -1, false, 1>(d, stream);
   }

@@ -512,7 +512,8 @@ def test_attention_bias_with_fused_qkv_bias_gradient():
 
 
 # ------------------------------------------------------------------------------------------------ folded LayerNorm
-@pytest.mark.parametrize("M,D,N,gelu", [(1576, 768, 2304, False), (1576, 768, 3072, True), (300, 192, 576, False), (1000, 384, 1536, True)])
+@pytest.mark.parametrize("M,D,N,gelu", [(1576, 768, 2304, False), (1576, 768, 3072, True), (300, 192, 576, False), (1000, 384, 1536, True),
+                                       (1576, 768, 3072, "gelu_tanh"), (788, 384, 1536, "silu")])
 def test_gemm_folded_layernorm(M, D, N, gelu):
     """b200_gemm_desc.ln_*: the residual GEMM leaves per-row partial sums of the bf16 values it stores; the next Linear runs on
     the un-normalised rows against weight * gamma and finishes LayerNorm in its epilogue.  Against fp32 LayerNorm + Linear
@@ -543,14 +544,19 @@ def test_gemm_folded_layernorm(M, D, N, gelu):
     c1 = wg.float().sum(1).contiguous()
     c2 = (w.float() @ beta.float() + b.float()).contiguous()
     epi = ops.EPI_BIAS_GELU if gelu else ops.EPI_BIAS
-    y = ops.linear_fwd(x, wg, c2, epilogue=epi, ln_in=(stats, c1, eps))
+    act = ops.ACTS[gelu] if isinstance(gelu, str) else 0          # tanh GELU / SiLU: the activation-at-run-time consumer
+    y = ops.linear_fwd(x, wg, c2, epilogue=epi, act=act, ln_in=(stats, c1, eps))
     ref = torch.nn.functional.layer_norm(xf, (D,), gamma.float(), beta.float(), eps) @ w.float().t() + b.float()
-    if gelu:
+    if gelu == "gelu_tanh":
+        ref = torch.nn.functional.gelu(ref, approximate="tanh")
+    elif gelu == "silu":
+        ref = torch.nn.functional.silu(ref)
+    elif gelu:
         ref = torch.nn.functional.gelu(ref)
     _close(y, ref, 3e-2, 2e-2, f"folded LayerNorm -> Linear M={M} N={N} gelu={gelu}")
     # and against the unfolded kernel sequence (LayerNorm kernel, bf16 h, GEMM): the two differ by bf16 roundings only
     h = ops.layernorm_fwd(x, gamma, beta, eps)[0]
-    y2 = ops.linear_fwd(h, w, b, epilogue=epi)
+    y2 = ops.linear_fwd(h, w, b, epilogue=epi, act=act)
     _close(y, y2, 4e-2, 2e-2, "folded vs unfolded")
 
 
