@@ -436,7 +436,17 @@ def prefetch_case():
     print("prefetch", x.dtype, float(x.abs().max()))
 
 
+# head_dim 80 (ViT-H's width: attention.py:85-93 takes dim // num_heads): the file name deliberately does not match the
+# vit_*.pt glob of the GPU model tests -- the wide-head GPU tests (tests/test_gpu_wide_heads.py) compare against the oracle,
+# this fixture pins the oracle at that width to the unmodified reference (tests/test_oracle_golden.py)
+WIDE_KWARGS = dict(img_size=64, patch_size=16, in_chans=3, num_classes=10, embed_dim=160, depth=2, num_heads=2,
+                   mlp_ratio=4.0, qkv_bias=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":
+        os.makedirs(OUT, exist_ok=True)
+        return vit_case("wide_vit_g10_head80", 13, 2, WIDE_KWARGS)
     if len(sys.argv) > 1 and sys.argv[1] == "prefetch":
         os.makedirs(OUT, exist_ok=True)
         return prefetch_case()
@@ -505,6 +515,7 @@ def main():
     vit_case("vit_g9_siglip_like", 11, 2, SIGLIP_KWARGS)
     convnext_case("convnext_g3_tanh_k7553", 12, 2, CNX_TANH_KWARGS, 64, backward=True)
     prefetch_case()
+    vit_case("wide_vit_g10_head80", 13, 2, WIDE_KWARGS)
 
 
 if __name__ == "__main__":

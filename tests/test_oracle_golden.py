@@ -67,6 +67,24 @@ def test_vit_backward_matches_reference(path):
         torch.testing.assert_close(sd[k].grad, ref, atol=1e-6 + 2e-6 * scale, rtol=2e-4, msg=lambda m: f"{k}: {m}")
 
 
+def test_wide_head_vit_matches_reference():
+    """head_dim 80 (dim // num_heads of ViT-H, attention.py:85-93): the oracle against the unmodified reference's block
+    outputs, logits and parameter gradients -- the pin behind tests/test_gpu_wide_heads.py, which checks the 128-wide
+    attention kernels (heads padded 80 -> 128 through the weights) against this oracle."""
+    fx = torch.load(os.path.join(GOLDEN, "wide_vit_g10_head80.pt"))
+    cfg = _cfg(fx["kwargs"])
+    assert cfg["embed_dim"] // cfg["num_heads"] == 80
+    feats, blocks = O.vit_forward_features(fx["img"], fx["state_dict"], cfg, return_blocks=True)
+    for i, (got, ref) in enumerate(zip(blocks, fx["block_outputs"])):
+        torch.testing.assert_close(got, ref, atol=1e-5, rtol=1e-5, msg=lambda m: f"block {i}: {m}")
+    torch.testing.assert_close(O.vit_forward_head(feats, fx["state_dict"], cfg), fx["logits"], atol=1e-5, rtol=1e-5)
+    sd = {k: v.clone().requires_grad_(True) for k, v in fx["state_dict"].items()}
+    O.vit_forward(fx["img"], sd, cfg).mean().backward()
+    scale = max(g.abs().max().item() for g in fx["grads"].values())
+    for k, ref in fx["grads"].items():
+        torch.testing.assert_close(sd[k].grad, ref, atol=1e-6 + 2e-6 * scale, rtol=2e-4, msg=lambda m: f"{k}: {m}")
+
+
 def test_layer_goldens():
     fx = torch.load(os.path.join(GOLDEN, "layers.pt"))
     a = fx["attention"]
